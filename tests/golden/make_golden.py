@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures from the UNMODIFIED reference source.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports ``jaxtronomy`` from /root/reference through ``refshim`` (NumPy-backed jax, restated
+lenstronomy host helpers -- see refshim.py for what is and is not substituted) and writes
+
+    tests/golden/profiles.npz     deflections of every hot-path lens profile + light profiles + 2F1 sweep
+    tests/golden/lens_models.npz  LensModel / LensModelBulk / MultiPlane ray shooting
+    tests/golden/imsim.npz        grid bookkeeping, re-bin + convolution, ImageModel, ImageLinearFit
+
+Parameter sets follow the reference's own tests (test/test_LensModel/test_Profiles/*.py,
+test/test_ImSim/*.py) plus the clamps/edge cases listed in SURVEY.md 7 "Hard parts".
+Each case is stored as ``<case>/in/<name>`` and ``<case>/out/<name>`` arrays; scalar kwargs are
+stored as 0-d arrays, strings as JSON in ``<case>/meta``.
+"""
+
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refshim  # noqa: E402
+
+refshim.install()
+
+from jaxtronomy.LensModel.lens_model import LensModel  # noqa: E402
+from jaxtronomy.LensModel.lens_model_bulk import LensModelBulk  # noqa: E402
+from jaxtronomy.LightModel.light_model import LightModel  # noqa: E402
+from jaxtronomy.Util.hyp2f1_util import hyp2f1_lopez_temme_8  # noqa: E402
+from jaxtronomy.LensModel.Profiles.epl import EPLMajorAxis  # noqa: E402
+from jaxtronomy.ImSim.Numerics.grid import RegularGrid  # noqa: E402
+from jaxtronomy.ImSim.Numerics.numerics import Numerics  # noqa: E402
+from jaxtronomy.ImSim.image_model import ImageModel  # noqa: E402
+from jaxtronomy.ImSim.image_linear_solve import ImageLinearFit  # noqa: E402
+from jaxtronomy.Data.imaging_data import ImageData  # noqa: E402
+from lenstronomy.Data.psf import PSF  # noqa: E402
+from lenstronomy.Data.pixel_grid import PixelGrid  # noqa: E402
+import lenstronomy.Util.simulation_util as sim_util  # noqa: E402
+
+
+class Store:
+    def __init__(self):
+        self.d = {}
+
+    def add(self, case, inputs, outputs, meta=None):
+        for k, v in inputs.items():
+            self.d["%s/in/%s" % (case, k)] = np.asarray(v)
+        for k, v in outputs.items():
+            self.d["%s/out/%s" % (case, k)] = np.asarray(v)
+        self.d["%s/meta" % case] = np.asarray(json.dumps(meta or {}, default=lambda o: np.asarray(o).tolist()))
+
+    def save(self, name):
+        path = os.path.join(HERE, name)
+        np.savez_compressed(path, **self.d)
+        print("wrote %s: %d arrays, %.1f KiB" % (name, len(self.d), os.path.getsize(path) / 1024))
+
+
+def points(rng, n=97, span=3.0):
+    """Scattered points plus the awkward ones: the origin, axis points (zero crossings), far field."""
+    x = rng.uniform(-span, span, n)
+    y = rng.uniform(-span, span, n)
+    x = np.concatenate([x, [0.0, 0.0, 1.0, -1.0, 0.0, 1e-7, 25.0, 1e-12]])
+    y = np.concatenate([y, [0.0, 1.0, 0.0, 0.0, -1.3, -1e-7, -40.0, 0.0]])
+    return x, y
+
+
+def e_from(mod, ang):
+    return mod * np.cos(ang), mod * np.sin(ang)
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_profiles():
+    st = Store()
+    rng = np.random.default_rng(20261017)
+    x, y = points(rng)
+
+    def lens_case(case, name, kw, xx=x, yy=y, profile_kwargs=None):
+        lm = LensModel([name], profile_kwargs_list=[profile_kwargs or {}])
+        fx, fy = lm.lens_model.alpha(xx, yy, [kw])
+        st.add(case, dict(x=xx, y=yy, **kw), dict(f_x=fx, f_y=fy),
+               dict(profile=name, profile_kwargs=profile_kwargs or {}))
+
+    # EPL: one case per nmax bracket (|e| thresholds epl.py:311-317), plus e==0, q->clamp, gamma extremes
+    n = 0
+    for emod, ang, gamma in [(0.0, 0.0, 2.0), (0.05, 0.3, 1.9), (0.119, -2.0, 1.5), (0.12, 1.0, 2.0),
+                             (0.25, 0.7, 2.1), (0.399, 2.5, 2.5), (0.45, -0.4, 1.7), (0.65, 1.9, 2.2),
+                             (0.8, 0.1, 2.0), (0.9, -1.1, 1.8), (0.95, 0.6, 2.3), (0.99995, 0.2, 2.0)]:
+        e1, e2 = e_from(emod, ang)
+        lens_case("epl_%02d" % n, "EPL", dict(theta_E=1.3, gamma=gamma, e1=e1, e2=e2, center_x=0.1, center_y=-0.2))
+        n += 1
+    # the reference's own sweep (test_epl.py:199-206) on the major-axis function
+    ys = np.linspace(-10, 10, 101)
+    xs = np.ones_like(ys)
+    fx_all, fy_all = [], []
+    qs = np.linspace(0.03, 1, 200)[::-1]
+    for q in qs[::8]:
+        fx, fy = EPLMajorAxis.derivatives(xs, ys, 1.7, 0.9, q)
+        fx_all.append(fx)
+        fy_all.append(fy)
+    st.add("epl_major_sweep", dict(x=xs, y=ys, b=1.7, t=0.9, q=qs[::8]), dict(f_x=np.array(fx_all), f_y=np.array(fy_all)))
+
+    for i, (e1, e2) in enumerate([(0.1, -0.05), (0.0, 0.0), (-0.4, 0.3), (0.7, 0.7)]):
+        lens_case("sie_%d" % i, "SIE", dict(theta_E=1.1, e1=e1, e2=e2, center_x=-0.1, center_y=0.3))
+        lens_case("nie_%d" % i, "NIE", dict(theta_E=0.9, e1=e1, e2=e2, s_scale=0.1 + 0.2 * i, center_x=0.2, center_y=0.0))
+    lens_case("sie_epl", "SIE", dict(theta_E=1.1, e1=0.2, e2=0.1, center_x=0.0, center_y=0.0),
+              profile_kwargs=dict(NIE=False, gamma=2))
+    lens_case("sis_0", "SIS", dict(theta_E=1.4, center_x=0.0, center_y=0.0))
+    lens_case("sis_1", "SIS", dict(theta_E=0.7, center_x=0.3, center_y=-0.6))
+    lens_case("shear_0", "SHEAR", dict(gamma1=0.05, gamma2=-0.03, ra_0=0.0, dec_0=0.0))
+    lens_case("shear_1", "SHEAR", dict(gamma1=-0.2, gamma2=0.4, ra_0=0.5, dec_0=-1.0))
+    lens_case("convergence_0", "CONVERGENCE", dict(kappa=0.12, ra_0=0.1, dec_0=0.2))
+    # NFW: X<1, X==1 exactly, X>1, X below the 1e-6 clamp, tiny Rs clamp
+    xn = np.concatenate([x, [2.4, 0.0, 1e-9]])
+    yn = np.concatenate([y, [0.0, 2.4, 0.0]])
+    lens_case("nfw_0", "NFW", dict(Rs=2.4, alpha_Rs=1.5, center_x=0.0, center_y=0.0), xn, yn)
+    lens_case("nfw_1", "NFW", dict(Rs=0.3, alpha_Rs=0.7, center_x=1.0, center_y=2.0))
+    lens_case("nfw_2", "NFW", dict(Rs=1e-8, alpha_Rs=1e-9, center_x=0.0, center_y=0.0))
+    # TNFW: reference test parameters (test_tnfw.py:48-79) and x==1, tau<1, tau>1
+    lens_case("tnfw_0", "TNFW", dict(Rs=1.4, alpha_Rs=3.5, r_trunc=3.2, center_x=0.0, center_y=0.0),
+              np.concatenate([x, [1.4]]), np.concatenate([y, [0.0]]))
+    lens_case("tnfw_1", "TNFW", dict(Rs=2.4, alpha_Rs=1.5, r_trunc=1.2, center_x=1.0, center_y=2.0))
+    lens_case("tnfw_2", "TNFW", dict(Rs=4.0, alpha_Rs=0.5, r_trunc=8.0, center_x=1.0, center_y=2.0))
+    lens_case("tnfw_3", "TNFW", dict(Rs=0.01, alpha_Rs=0.002, r_trunc=0.07, center_x=-0.5, center_y=0.25))
+    for m in (1, 2, 3, 4):
+        lens_case("multipole_m%d" % m, "MULTIPOLE",
+                  dict(m=m, a_m=0.05, phi_m=0.3 * m, center_x=0.1, center_y=-0.1, r_E=1.2))
+    for i, (emod, ang) in enumerate([(0.2, 0.4), (0.0, 0.0), (0.45, -1.0)]):
+        e1, e2 = e_from(emod, ang)
+        lens_case("epl_m1m3m4_%d" % i, "EPL_MULTIPOLE_M1M3M4",
+                  dict(theta_E=1.2, gamma=2.05, e1=e1, e2=e2, center_x=0.05, center_y=0.02, a1_a=0.02,
+                       delta_phi_m1=0.5, a3_a=-0.01, delta_phi_m3=0.2, a4_a=0.015, delta_phi_m4=-0.1))
+    for axis in ("product_avg", "major"):
+        lens_case("cse_%s" % axis, "CSE", dict(a=1.3, s=0.4, e1=0.15, e2=-0.2, center_x=0.1, center_y=0.0),
+                  profile_kwargs=dict(axis=axis))
+    for hi in (True, False):
+        lens_case("nfw_ellipse_cse_%d" % hi, "NFW_ELLIPSE_CSE",
+                  dict(Rs=1.7, alpha_Rs=1.1, e1=0.12, e2=0.08, center_x=-0.05, center_y=0.1),
+                  profile_kwargs=dict(high_accuracy=hi))
+    lens_case("hernquist_ellipse_cse", "HERNQUIST_ELLIPSE_CSE",
+              dict(sigma0=0.9, Rs=1.2, e1=-0.1, e2=0.2, center_x=0.0, center_y=0.05))
+
+    # light profiles (test_sersic_ellipse.py / test_gaussian.py style) incl. clamps: R<1e-4, R/Rs > 1000
+    def light_case(case, name, kw, xx=x, yy=y):
+        lm = LightModel([name])
+        st.add(case, dict(x=xx, y=yy, **kw), dict(flux=lm.surface_brightness(xx, yy, [kw])), dict(profile=name))
+
+    xl = np.concatenate([x, [0.05, 0.05 + 1e-6, 200.0]])
+    yl = np.concatenate([y, [0.1, 0.1, 0.0]])
+    light_case("sersic_ellipse_0", "SERSIC_ELLIPSE",
+               dict(amp=10.0, R_sersic=0.2, n_sersic=2.0, e1=0.1, e2=0.1, center_x=0.05, center_y=0.1), xl, yl)
+    light_case("sersic_ellipse_1", "SERSIC_ELLIPSE",
+               dict(amp=1.4, R_sersic=0.6, n_sersic=7.0, e1=0.3, e2=-0.4, center_x=0.0, center_y=0.0), xl, yl)
+    light_case("sersic_ellipse_2", "SERSIC_ELLIPSE",
+               dict(amp=2.0, R_sersic=0.1, n_sersic=0.5, e1=-0.2, e2=0.0, center_x=0.3, center_y=-0.3), xl, yl)
+    light_case("sersic_ellipse_3", "SERSIC_ELLIPSE",
+               dict(amp=2.0, R_sersic=-0.1, n_sersic=1.0, e1=0.0, e2=0.0, center_x=0.0, center_y=0.0), xl, yl)
+    light_case("sersic_0", "SERSIC", dict(amp=1.0, R_sersic=0.1, n_sersic=2.0, center_x=0.0, center_y=0.0), xl, yl)
+    light_case("sersic_1", "SERSIC", dict(amp=3.0, R_sersic=1.0, n_sersic=4.0, center_x=0.5, center_y=0.5), xl, yl)
+    light_case("gaussian_0", "GAUSSIAN", dict(amp=4.0, sigma=0.3, center_x=0.1, center_y=-0.2), xl, yl)
+
+    # 2F1 sweep in the EPL configuration (a=1, b=t/2, c=2-t/2, |z|=f)
+    t = np.array([0.5, 0.9, 1.0, 1.4])
+    ang = np.linspace(-np.pi, np.pi, 41)
+    for nmax, f in [(10, 0.1), (20, 0.39), (35, 0.59), (50, 0.72), (100, 0.85), (200, 0.91), (500, 0.99)]:
+        z = f * np.exp(1j * ang)
+        out = np.array([hyp2f1_lopez_temme_8(1, tt / 2, 2 - tt / 2, z, nmax=nmax) for tt in t])
+        st.add("hyp2f1_nmax%d" % nmax, dict(t=t, z=z, nmax=nmax), dict(h=out))
+    st.save("profiles.npz")
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_lens_models():
+    st = Store()
+    rng = np.random.default_rng(7)
+    x, y = points(rng, n=61)
+    names = ["EPL", "SHEAR", "SIS", "NFW"]
+    kw = [dict(theta_E=1.2, gamma=2.1, e1=0.2, e2=-0.1, center_x=0.05, center_y=-0.02),
+          dict(gamma1=0.03, gamma2=-0.02, ra_0=0.0, dec_0=0.0),
+          dict(theta_E=0.2, center_x=0.8, center_y=0.5),
+          dict(Rs=0.5, alpha_Rs=0.1, center_x=-0.7, center_y=0.3)]
+    lm = LensModel(names)
+    for k in (None, 0, (0, 2), [True, True, False, True]):
+        bx, by = lm.ray_shooting(x, y, kw, k=k)
+        st.add("single_plane_k%s" % json.dumps(k).replace(" ", ""), dict(x=x, y=y), dict(beta_x=bx, beta_y=by),
+               dict(lens_model_list=names, kwargs=kw, k=k))
+
+    # bulk single plane: 1 EPL + 40 TNFW (+ NULL padding to 48), substructure-notebook shape
+    nh = 40
+    bulk_names = ["EPL"] + ["TNFW"] * nh
+    bulk_kw = [kw[0]] + [dict(Rs=float(rng.uniform(0.01, 0.1)), alpha_Rs=float(rng.uniform(1e-4, 5e-3)),
+                              r_trunc=float(rng.uniform(0.05, 0.5)), center_x=float(rng.uniform(-2, 2)),
+                              center_y=float(rng.uniform(-2, 2))) for _ in range(nh)]
+    lmb = LensModelBulk(["EPL", "TNFW"], multi_plane=False)
+    rs_kw = lmb.prepare_ray_shooting_kwargs(bulk_names, bulk_kw, num_deflectors=48)
+    bx, by = lmb.ray_shooting(x, y, rs_kw)
+    st.add("bulk_single_plane", dict(x=x, y=y, index_list=rs_kw["index_list"],
+                                     **{"kw_" + k: v for k, v in rs_kw["all_kwargs"].items()}),
+           dict(beta_x=bx, beta_y=by), dict(unique_lens_model_list=["EPL", "TNFW"], lens_model_list=bulk_names,
+                                            kwargs=bulk_kw, num_deflectors=48))
+
+    # multi-plane, config-5 shape: EPL (z=0.5), NFW_ELLIPSE_CSE (z=0.5, same plane), SIS (z=0.2), SHEAR (z=0.8)
+    mp_names = ["EPL", "NFW_ELLIPSE_CSE", "SIS", "SHEAR"]
+    mp_z = [0.5, 0.5, 0.2, 0.8]
+    mp_kw = [kw[0], dict(Rs=1.5, alpha_Rs=0.3, e1=0.1, e2=0.05, center_x=0.0, center_y=0.1),
+             dict(theta_E=0.15, center_x=0.6, center_y=-0.4), kw[1]]
+    z_source = 1.5
+    lmm = LensModel(mp_names, z_source=z_source, lens_redshift_list=mp_z, multi_plane=True)
+    bx, by = lmm.ray_shooting(x, y, mp_kw)
+    mp = lmm.lens_model
+    base = mp.multi_plane_base
+    st.add("multi_plane", dict(x=x, y=y, sorted_index=np.asarray(base.sorted_redshift_index),
+                               T_ij_list=np.asarray(base.T_ij_list, dtype=float), T_z_list=np.asarray(base.T_z_list, dtype=float),
+                               reduced2physical=np.asarray(base._reduced2physical_factor, dtype=float),
+                               T_ij_stop=float(mp.T_ij_stop), T_z_source=float(mp._T_z_source)),
+           dict(beta_x=bx, beta_y=by),
+           dict(lens_model_list=mp_names, lens_redshift_list=mp_z, z_source=z_source, kwargs=mp_kw,
+                cosmology="flat LCDM H0=70 Om0=0.3 stand-in (refshim.Background)"))
+    st.save("lens_models.npz")
+
+
+# ------------------------------------------------------------------------------------------------
+def gauss_kernel(n, sigma):
+    a = np.arange(n) - (n - 1) / 2
+    k = np.exp(-(a[:, None] ** 2 + a[None, :] ** 2) / (2 * sigma**2))
+    return k / k.sum()
+
+
+def gen_imsim():
+    st = Store()
+    rng = np.random.default_rng(11)
+
+    # grid bookkeeping: coordinates and index maps must be bit-exact (test_grid.py)
+    M = np.array([[0.05, 0.002], [-0.001, 0.05]])
+    for ss in (1, 2, 3):
+        g = RegularGrid(6, 6, M, -0.15, -0.14, supersampling_factor=ss)
+        ra, dec = g.coordinates_evaluate
+        flux = rng.uniform(0, 1, ra.shape)
+        low, high = g.flux_array2image_low_high(flux)
+        st.add("grid_ss%d" % ss, dict(nx=6, ny=6, transform_pix2angle=M, ra_at_xy_0=-0.15, dec_at_xy_0=-0.14, ss=ss,
+                                      flux=flux),
+               dict(ra=ra, dec=dec, compute_indexes=g._compute_indexes, low=low,
+                    high=(high if high is not None else np.zeros(0))))
+
+    # re_size_convolve: PIXEL psf (fft and grid), GAUSSIAN psf (edge padded), NONE
+    kd = sim_util.data_configure_simple(20, 0.08, 100, 0.05, inverse=True)
+    pg = PixelGrid(20, 20, kd["transform_pix2angle"], kd["ra_at_xy_0"], kd["dec_at_xy_0"])
+    kern = gauss_kernel(7, 1.3) + 0.02 * rng.uniform(0, 1, (7, 7)) / 49  # not separable, not symmetric
+    for name, psf_kw, num_kw in [
+        ("pixel_fft", dict(psf_type="PIXEL", kernel_point_source=kern), dict(supersampling_factor=3, convolution_type="fft")),
+        ("pixel_grid", dict(psf_type="PIXEL", kernel_point_source=kern), dict(supersampling_factor=2, convolution_type="grid")),
+        ("pixel_cut", dict(psf_type="PIXEL", kernel_point_source=kern), dict(supersampling_factor=1, convolution_kernel_size=5)),
+        ("gaussian", dict(psf_type="GAUSSIAN", fwhm=0.2, truncation=5), dict(supersampling_factor=2)),
+        ("gaussian_trunc", dict(psf_type="GAUSSIAN", fwhm=0.15, truncation=3), dict(supersampling_factor=1, truncation_conv=4)),
+        ("none", dict(psf_type="NONE"), dict(supersampling_factor=2)),
+    ]:
+        psf = PSF(**psf_kw)
+        psf.set_pixel_size(pg.pixel_width)
+        num = Numerics(pg, psf, **num_kw)
+        ra, dec = num.coordinates_evaluate
+        flux = np.exp(-((ra - 0.1) ** 2 + (dec + 0.2) ** 2) / 0.05) + 0.01 * rng.uniform(0, 1, ra.shape)
+        out = num.re_size_convolve(flux)
+        outu = num.re_size_convolve(flux, unconvolved=True)
+        ins = dict(flux=flux, transform_pix2angle=kd["transform_pix2angle"], ra_at_xy_0=kd["ra_at_xy_0"],
+                   dec_at_xy_0=kd["dec_at_xy_0"])
+        if "kernel_point_source" in psf_kw:
+            ins["kernel"] = kern
+        meta_psf = {k: v for k, v in psf_kw.items() if k != "kernel_point_source"}
+        st.add("numerics_%s" % name, ins, dict(image=out, image_unconvolved=outu, ra=ra, dec=dec),
+               dict(nx=20, ny=20, kwargs_psf=meta_psf, kwargs_numerics=num_kw))
+
+    # ImageModel / ImageLinearFit cases
+    def image_case(case, numPix, deltaPix, lens_names, kw_lens, src_names, kw_src, ll_names, kw_ll, psf_kw, num_kw,
+                   mask=None, noise_map=False, exposure_map=False, inverse=False, profile_kwargs=None):
+        kd = sim_util.data_configure_simple(numPix, deltaPix, 100.0, 0.05, inverse=inverse)
+        if exposure_map:
+            kd["exposure_time"] = 80.0 + 40.0 * rng.uniform(0, 1, (numPix, numPix))
+        data = ImageData(**kd)
+        psf = PSF(**psf_kw)
+        lens = LensModel(lens_names, profile_kwargs_list=profile_kwargs)
+        src = LightModel(src_names)
+        ll = LightModel(ll_names)
+        im = ImageModel(data, psf, lens, src, ll, kwargs_numerics=num_kw, likelihood_mask=mask)
+        truth = np.asarray(im.image(kw_lens, kw_src, kw_ll))
+        noisy = truth + rng.normal(0, 0.05, truth.shape) + rng.normal(0, 1, truth.shape) * np.sqrt(np.maximum(truth, 0) / 100.0)
+        kd2 = dict(kd)
+        kd2["image_data"] = noisy
+        if noise_map:
+            kd2["noise_map"] = 0.05 + 0.02 * rng.uniform(0, 1, truth.shape)
+        data = ImageData(**kd2)
+        im = ImageModel(data, psf, lens, src, ll, kwargs_numerics=num_kw, likelihood_mask=mask)
+        lin = ImageLinearFit(data, psf, lens, src, ll, kwargs_numerics=num_kw, likelihood_mask=mask)
+        # perturbed parameters -> the model differs from the data
+        kw_lens_p = [dict(k) for k in kw_lens]
+        for k in kw_lens_p:
+            if "theta_E" in k:
+                k["theta_E"] *= 1.02
+        image = np.asarray(im.image(kw_lens_p, kw_src, kw_ll))
+        image_unc = np.asarray(im.image(kw_lens_p, kw_src, kw_ll, unconvolved=True))
+        src_only = np.asarray(im.source_surface_brightness(kw_src, kw_lens_p))
+        ll_only = np.asarray(im.lens_surface_brightness(kw_ll))
+        logL = float(im.likelihood_data_given_model(kw_lens_p, kw_src, kw_ll))
+        # the reference's update_linear_kwargs writes the solved amplitudes into the kwargs dicts: pass copies
+        cp = lambda kws: [dict(k) for k in kws]  # noqa: E731
+        A = np.asarray(lin.linear_response_matrix(kw_lens_p, cp(kw_src), cp(kw_ll), None))
+        model, _, _, param = lin.image_linear_solve(kw_lens_p, cp(kw_src), cp(kw_ll))
+        logL_lin, param2 = lin.likelihood_data_given_model(kw_lens_p, cp(kw_src), cp(kw_ll))
+        logL_marg, _ = lin.likelihood_data_given_model(kw_lens_p, cp(kw_src), cp(kw_ll), source_marg=True)
+        ins = dict(image_data=noisy, transform_pix2angle=kd["transform_pix2angle"], ra_at_xy_0=kd["ra_at_xy_0"],
+                   dec_at_xy_0=kd["dec_at_xy_0"], exposure_time=kd["exposure_time"], background_rms=0.05)
+        if mask is not None:
+            ins["likelihood_mask"] = mask
+        if noise_map:
+            ins["noise_map"] = kd2["noise_map"]
+        if "kernel_point_source" in psf_kw:
+            ins["kernel"] = psf_kw["kernel_point_source"]
+        st.add(case, ins,
+               dict(image=image, image_unconvolved=image_unc, source=src_only, lens_light=ll_only, logL=logL, A=A,
+                    wls_model=np.asarray(model), param=np.asarray(param), logL_linear=float(logL_lin),
+                    logL_marg=float(logL_marg)),
+               dict(numPix=numPix, deltaPix=deltaPix, lens_model_list=lens_names, kwargs_lens=kw_lens_p,
+                    source_model_list=src_names, kwargs_source=kw_src, lens_light_model_list=ll_names,
+                    kwargs_lens_light=kw_ll, kwargs_psf={k: v for k, v in psf_kw.items() if k != "kernel_point_source"},
+                    kwargs_numerics=num_kw, lens_profile_kwargs=profile_kwargs))
+
+    sersic_src = dict(amp=12.0, R_sersic=0.25, n_sersic=2.0, e1=0.1, e2=0.1, center_x=0.05, center_y=0.1)
+    sersic_ll = dict(amp=20.0, R_sersic=0.5, n_sersic=3.0, e1=-0.1, e2=0.05, center_x=0.02, center_y=-0.01)
+    shear = dict(gamma1=0.03, gamma2=-0.02, ra_0=0.0, dec_0=0.0)
+    # C1: SIE+SHEAR, SERSIC_ELLIPSE source, Gaussian PSF (Einstein-ring notebook shape, shrunk to 40x40)
+    image_case("c1_sie_shear_gauss", 40, 0.1, ["SIE", "SHEAR"],
+               [dict(theta_E=1.2, e1=0.1, e2=-0.05, center_x=0.02, center_y=-0.01), shear],
+               ["SERSIC_ELLIPSE"], [sersic_src], ["SERSIC_ELLIPSE"], [sersic_ll],
+               dict(psf_type="GAUSSIAN", fwhm=0.2, truncation=5), dict(supersampling_factor=1))
+    # headline shape shrunk: EPL+SHEAR, ss 3, 11x11 non-separable pixel PSF, likelihood mask
+    kern = gauss_kernel(11, 1.6) + 0.05 * rng.uniform(0, 1, (11, 11)) / 121
+    mask = np.ones((36, 36))
+    mask[:4, :] = 0
+    mask[20:24, 10:15] = 0
+    image_case("headline_epl_shear_pixel", 36, 0.09, ["EPL", "SHEAR"],
+               [dict(theta_E=1.1, gamma=2.05, e1=0.2, e2=-0.1, center_x=0.02, center_y=-0.01), shear],
+               ["SERSIC_ELLIPSE"], [sersic_src], ["SERSIC_ELLIPSE"], [sersic_ll],
+               dict(psf_type="PIXEL", kernel_point_source=kern), dict(supersampling_factor=3), mask=mask)
+    # test_image_linear_solve.py shape: SIS, 2 x SERSIC_ELLIPSE source + SERSIC lens light, Gaussian PSF truncation 5, ss 2
+    e1, e2 = 0.1 / 1.9 * np.cos(0.4), 0.1 / 1.9 * np.sin(0.4)
+    image_case("linear_sis_3comp", 40, 0.1, ["SIS"], [dict(theta_E=1.0, center_x=0.0, center_y=0.0)],
+               ["SERSIC_ELLIPSE", "SERSIC_ELLIPSE"],
+               [dict(amp=1.4, R_sersic=0.6, n_sersic=7.0, center_x=0.0, center_y=0.0, e1=e1, e2=e2),
+                dict(amp=2.1, R_sersic=0.3, n_sersic=6.0, center_x=0.0, center_y=0.0, e1=e1, e2=e2)],
+               ["SERSIC"], [dict(amp=1.0, R_sersic=0.1, n_sersic=2.0, center_x=0.0, center_y=0.0)],
+               dict(psf_type="GAUSSIAN", fwhm=0.5, truncation=5), dict(supersampling_factor=2), inverse=True)
+    # config-3 shape shrunk: EPL_MULTIPOLE_M1M3M4 + SHEAR, noise map, per-pixel exposure map, GAUSSIAN light
+    image_case("c3_multipole_noise_map", 32, 0.1, ["EPL_MULTIPOLE_M1M3M4", "SHEAR"],
+               [dict(theta_E=1.0, gamma=1.95, e1=-0.15, e2=0.1, center_x=0.0, center_y=0.03, a1_a=0.02,
+                     delta_phi_m1=0.4, a3_a=0.01, delta_phi_m3=0.1, a4_a=-0.015, delta_phi_m4=0.05), shear],
+               ["SERSIC_ELLIPSE", "GAUSSIAN"],
+               [sersic_src, dict(amp=0.5, sigma=0.15, center_x=-0.1, center_y=0.0)],
+               ["SERSIC_ELLIPSE"], [sersic_ll],
+               dict(psf_type="PIXEL", kernel_point_source=gauss_kernel(5, 0.9)),
+               dict(supersampling_factor=2, convolution_type="grid"), noise_map=True, exposure_map=True)
+    # degenerate linear system: two identical basis functions -> cond gate -> amplitudes 0 (de_lens.py:26-33)
+    image_case("linear_degenerate", 24, 0.1, ["SIS"], [dict(theta_E=0.8, center_x=0.0, center_y=0.0)],
+               ["SERSIC_ELLIPSE", "SERSIC_ELLIPSE"], [sersic_src, sersic_src], [], [],
+               dict(psf_type="NONE"), dict(supersampling_factor=1))
+    st.save("imsim.npz")
+
+
+if __name__ == "__main__":
+    gen_profiles()
+    gen_lens_models()
+    gen_imsim()
