@@ -1,0 +1,219 @@
+/*
+ * lsim.h -- C ABI of the B200-native forward image-simulation hot path.
+ *
+ * The reference (JAXtronomy, /root/reference/jaxtronomy) has no FFI / plugin boundary: its hot path is
+ * Python methods traced by XLA.  This header is the boundary a JAXtronomy maintainer would bind instead
+ * (ctypes today, an XLA-FFI custom call where jax is installed -- see INTEGRATION.md).  Every entry
+ * point names the reference method(s) it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA runtime types in signatures: device pointers are `double*`, the stream is
+ *     passed as `void*` (a cudaStream_t).
+ *   - the caller owns every buffer (inputs, outputs, workspace).  A plan owns device copies of the static
+ *     configuration only (profile descriptors, evaluation grid, PSF kernel, data/noise/mask).
+ *   - launch calls allocate nothing and never synchronise; all work is enqueued on the given stream.
+ *   - every function returns 0 on success or a negative LSIM_E_* code; lsim_strerror() explains it.
+ *   - parameters of a batch of B parameter sets ("particles") are a dense row-major [B, P] fp64 matrix,
+ *     exactly the `positions` array the reference's batch boundary receives
+ *     (Sampling/Samplers/pso.py:51-66, Sampling/sampler.py:215-251).  Each profile parameter is either a
+ *     column of that matrix or a per-plan constant (a fixed parameter), mirroring Param.args2kwargs
+ *     (Sampling/likelihood.py:305).
+ *   - all arithmetic is IEEE fp64.
+ */
+#ifndef LSIM_H
+#define LSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSIM_ABI_VERSION 1
+#define LSIM_MAX_PARAMS 12 /* largest param_names list on the path: EPL_MULTIPOLE_M1M3M4 */
+#define LSIM_MAX_SLOTS 8   /* output / linear-basis images per parameter set */
+
+/* error codes */
+enum {
+  LSIM_OK = 0,
+  LSIM_E_INVALID = -1,     /* malformed descriptor / argument */
+  LSIM_E_UNSUPPORTED = -2, /* valid in the reference but outside this library's scope */
+  LSIM_E_CUDA = -3,        /* CUDA runtime error (lsim_last_cuda_error() has the text) */
+  LSIM_E_WORKSPACE = -4,   /* workspace too small */
+  LSIM_E_NO_IMAGE = -5     /* plan was created without grid / data but an image / logl call needs it */
+};
+
+/* Lens profiles: `derivatives` of the reference classes; parameter order = the class's `param_names`. */
+enum {
+  LSIM_LENS_NULL = 0,                  /* Profiles/null.py:30-38 */
+  LSIM_LENS_EPL = 1,                   /* Profiles/epl.py:178-200,366-394  theta_E,gamma,e1,e2,center_x,center_y */
+  LSIM_LENS_SIE = 2,                   /* Profiles/sie.py:104-124         theta_E,e1,e2,center_x,center_y; opt[0]=s_scale, opt[1]=gamma; flag NIE_FALSE -> EPL */
+  LSIM_LENS_NIE = 3,                   /* Profiles/nie.py:85-107,280-294  theta_E,e1,e2,s_scale,center_x,center_y */
+  LSIM_LENS_SIS = 4,                   /* Profiles/sis.py:35-43           theta_E,center_x,center_y */
+  LSIM_LENS_SHEAR = 5,                 /* Profiles/shear.py:39-53         gamma1,gamma2,ra_0,dec_0 */
+  LSIM_LENS_CONVERGENCE = 6,           /* Profiles/convergence.py:35-46   kappa,ra_0,dec_0 */
+  LSIM_LENS_NFW = 7,                   /* Profiles/nfw.py:88-105,259-279,347-365  Rs,alpha_Rs,center_x,center_y */
+  LSIM_LENS_TNFW = 8,                  /* Profiles/tnfw.py:69-87,228-349  Rs,alpha_Rs,r_trunc,center_x,center_y */
+  LSIM_LENS_MULTIPOLE = 9,             /* Profiles/multipole.py:72-119    m,a_m,phi_m,center_x,center_y,r_E */
+  LSIM_LENS_EPL_MULTIPOLE_M1M3M4 = 10, /* Profiles/epl_multipole_m1m3m4.py:463-535,608-678  (12 params, param_names order) */
+  LSIM_LENS_CSE = 11,                  /* Profiles/cored_steep_ellipsoid.py:107-132  a,s,e1,e2,center_x,center_y; flag CSE_MAJOR */
+  LSIM_LENS_NFW_ELLIPSE_CSE = 12,      /* Profiles/nfw_ellipse_cse.py:250-280  Rs,alpha_Rs,e1,e2,center_x,center_y; flag CSE_LOW_ACCURACY */
+  LSIM_LENS_HERNQUIST_ELLIPSE_CSE = 13,/* Profiles/hernquist_ellipse_cse.py:151-164  sigma0,Rs,e1,e2,center_x,center_y */
+  LSIM_LENS_TYPE_COUNT = 14
+};
+
+/* Light profiles: `function` of the reference classes. */
+enum {
+  LSIM_LIGHT_SERSIC = 0,         /* LightModel/Profiles/sersic.py:54-76          amp,R_sersic,n_sersic,center_x,center_y */
+  LSIM_LIGHT_SERSIC_ELLIPSE = 1, /* LightModel/Profiles/sersic_ellipse.py:61-93  amp,R_sersic,n_sersic,e1,e2,center_x,center_y */
+  LSIM_LIGHT_GAUSSIAN = 2,       /* LightModel/Profiles/gaussian.py:27-42        amp,sigma,center_x,center_y */
+  LSIM_LIGHT_TYPE_COUNT = 3
+};
+
+/* profile option flags (the reference's profile_kwargs, profile_list_base.py:161-232) */
+#define LSIM_FLAG_SIE_NIE_FALSE 1u       /* SIE(NIE=False): evaluate through EPL with gamma=opt[1] */
+#define LSIM_FLAG_CSE_MAJOR 2u           /* CSE(axis="major") instead of "product_avg" */
+#define LSIM_FLAG_CSE_LOW_ACCURACY 4u    /* NFW_ELLIPSE_CSE(high_accuracy=False): 16-term table */
+
+typedef struct lsim_lens_desc {
+  int32_t type;                 /* LSIM_LENS_* */
+  uint32_t flags;               /* LSIM_FLAG_* */
+  int32_t col[LSIM_MAX_PARAMS]; /* column of params[B,P] per parameter (param_names order), or -1: use cst */
+  double cst[LSIM_MAX_PARAMS];  /* value of the parameter when col < 0 */
+  double opt[2];                /* SIE: s_scale, gamma */
+  /* multi-plane only (lsim_plan_desc.multi_plane != 0): deflectors sorted by redshift,
+   * constants of MultiPlaneBase.set_T_zs_and_T_ijs (MultiPlane/multi_plane_base.py:89-115) */
+  double delta_T;               /* comoving step from the previous deflector (0 on the same plane) */
+  double T_z;                   /* transverse comoving distance observer -> this plane */
+  double red2phys;              /* reduced -> physical deflection factor D_s / D_ds */
+} lsim_lens_desc;
+
+typedef struct lsim_light_desc {
+  int32_t type;    /* LSIM_LIGHT_* */
+  int32_t lensed;  /* 1: source light, evaluated at the ray-shot position; 0: lens light at the image position */
+  int32_t slot;    /* output image this component is accumulated into (0..n_slots-1), -1: skipped (the `k` selection) */
+  int32_t use_amp; /* 1: multiply by the `amp` parameter; 0: amp = 1 (LinearBasis.functions_split, linear_basis.py:61-64) */
+  int32_t col[LSIM_MAX_PARAMS];
+  double cst[LSIM_MAX_PARAMS];
+} lsim_light_desc;
+
+/* PSF convolution on the pixel grid (ImSim/Numerics/convolution.py) */
+enum {
+  LSIM_CONV_NONE = 0,      /* psf_type NONE or unconvolved=True (numerics.py:170-171) */
+  LSIM_CONV_ZERO = 1,      /* PixelKernelConvolution: "same" convolution, zero boundary (convolution.py:73-96) */
+  LSIM_CONV_EDGE = 2       /* GaussianConvolution: image edge-replicated by the kernel radius (convolution.py:216-236) */
+};
+
+typedef struct lsim_plan_desc {
+  int32_t abi_version;      /* LSIM_ABI_VERSION */
+  int32_t n_param_cols;     /* P */
+
+  /* lens model: SinglePlane.alpha / ray_shooting (LensModel/single_plane.py:38-56,112-139) or, with
+   * multi_plane, MultiPlane.ray_shooting (LensModel/MultiPlane/multi_plane.py:236-275) */
+  int32_t n_lens;
+  const lsim_lens_desc* lens; /* host array [n_lens] */
+  int32_t multi_plane;
+  double alpha_scaling;     /* single plane (single_plane.py:139); 1 by default */
+  double T_ij_end;          /* multi plane: last deflector -> source */
+  double T_z_source;        /* multi plane: observer -> source */
+
+  /* light model: LightModelBase.surface_brightness / LinearBasis.functions_split
+   * (LightModel/light_model_base.py:230-252, linear_basis.py:24-91) */
+  int32_t n_light;
+  const lsim_light_desc* light; /* host array [n_light] */
+  int32_t n_slots;          /* 1..LSIM_MAX_SLOTS */
+
+  /* ---- everything below is needed by lsim_image / lsim_logl only (may be zero for ray shooting) ---- */
+  /* evaluation grid: RegularGrid (ImSim/Numerics/grid.py:22-64); coordinates in the reference's
+   * flattened order (row-major over [ny*ss, nx*ss]) */
+  int32_t nx, ny, ss;
+  const double* x_sub;      /* host [ny*ss*nx*ss] */
+  const double* y_sub;
+  /* PSF */
+  int32_t conv_mode;        /* LSIM_CONV_* */
+  int32_t kernel_size;      /* K (odd) */
+  const double* kernel;     /* host [K*K], row-major */
+  int32_t kernel_separable; /* 1: kernel == outer(kernel_1d, kernel_1d); lets the library do two 1-D passes */
+  const double* kernel_1d;  /* host [K] when kernel_separable */
+  double image_scale;       /* pixel_width^2 * flux_scaling (numerics.py:177, image_model.py:368,393) */
+
+  /* data and noise model: ImageData / ImageNoise (Data/imaging_data.py, Data/image_noise.py) */
+  const double* data;       /* host [ny*nx] or NULL */
+  const double* cd_data;    /* host [ny*nx]: C_D estimated from the data (+ model error): WLS weights 1/cd_data (image_model.py:594) */
+  const double* noise_map2; /* host [ny*nx] noise_map^2, or NULL -> Poisson + background from the model (image_noise.py:99-110) */
+  const double* exposure;   /* host [ny*nx] exposure map (already clamped >= 1e-10), used when noise_map2 is NULL */
+  double background_rms;
+  const uint8_t* mask;      /* host [ny*nx] likelihood mask (1 = use), or NULL = all ones (image_model.py:134-142) */
+} lsim_plan_desc;
+
+typedef struct lsim_plan lsim_plan;
+
+/* Validate a descriptor, upload static data to the current CUDA device and build a plan. */
+int lsim_plan_create(const lsim_plan_desc* desc, lsim_plan** out);
+void lsim_plan_destroy(lsim_plan* plan);
+
+/* LensModel.ray_shooting (LensModel/lens_model.py:236-252) / LensModelBulk.ray_shooting
+ * (LensModel/lens_model_bulk.py:113-128), batched over B parameter sets.
+ *   x, y       device [N] (shared by all sets) or [B,N] when coords_batched != 0
+ *   out_x/y    device [B,N]
+ *   what       0: source position beta = theta - alpha (ray_shooting); 1: deflection alpha (SinglePlane.alpha) */
+int lsim_ray_shoot(const lsim_plan* plan, const double* params, int64_t B, const double* x, const double* y,
+                   int64_t N, int coords_batched, double* out_x, double* out_y, int what, void* stream);
+
+/* LightModel.surface_brightness / functions_split on arbitrary points (no lensing applied here).
+ *   out        device [B, n_slots, N] */
+int lsim_surface_brightness(const lsim_plan* plan, const double* params, int64_t B, const double* x,
+                            const double* y, int64_t N, int coords_batched, double* out, void* stream);
+
+/* Bytes of caller-provided scratch lsim_image / lsim_logl want for B sets (they accept less, down to
+ * lsim_workspace_bytes(plan, 1), and then process the batch in more chunks). */
+size_t lsim_workspace_bytes(const lsim_plan* plan, int64_t B);
+
+/* ImageModel.image / source_surface_brightness / lens_surface_brightness and the rows of
+ * ImageLinearFit.linear_response_matrix (ImSim/image_model.py:223-393,431-492,
+ * ImSim/image_linear_solve.py:361-455): ray-shoot + light on the supersampled grid, re-bin, convolve, scale.
+ *   images     device [B, n_slots, ny, nx] */
+int lsim_image(const lsim_plan* plan, const double* params, int64_t B, double* images, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* Numerics.re_size_convolve (ImSim/Numerics/numerics.py:157-177) for a caller-supplied flux on the supersampled
+ * evaluation grid: re-bin (ss x ss mean), convolve, scale by pixel_width^2.
+ *   flux       device [n_images, ny*ss * nx*ss] in the reference's flattened order
+ *   images     device [n_images, ny, nx]
+ *   unconvolved != 0 skips the PSF (numerics.py:170-171) */
+int lsim_resize_convolve(const lsim_plan* plan, const double* flux, int64_t n_images, int unconvolved,
+                         double* images, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ImageModel.likelihood_data_given_model (image_model.py:162-221) when linear_solve == 0, or
+ * ImageLinearFit.likelihood_data_given_model (image_linear_solve.py:228-339, de_lens.py:10-49) when
+ * linear_solve != 0 (then the slots are the linear basis and amplitudes are solved by WLS).
+ *   logl       device [B]
+ *   amps       device [B, n_slots] or NULL (linear_solve only)
+ *   model      device [B, ny, nx] or NULL: the model image the likelihood was evaluated on
+ *   source_marg != 0 adds the marginalisation constant (de_lens.py:39-49) */
+int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear_solve, int source_marg,
+              double* logl, double* amps, double* model, void* workspace, size_t workspace_bytes, void* stream);
+
+/* introspection */
+int lsim_abi_version(void);
+const char* lsim_strerror(int code);
+const char* lsim_last_cuda_error(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+int64_t lsim_launch_count(void);
+
+/* Per-kernel device timing for bench.py's roofline: while enabled, every launch of this library is bracketed by
+ * CUDA events on the stream it is launched on.  lsim_timing_read synchronises on those events, returns the summed
+ * milliseconds and launch counts per kernel class (0 = k_image, 1 = k_conv_*, 2 = k_likelihood, 3 = other) and
+ * clears the record.  Not for use inside a timed region (the events cost a few microseconds per launch). */
+int lsim_timing_enable(int on);
+int lsim_timing_read(double ms[4], int64_t count[4]);
+
+/* fp64 FMA-pipe microbenchmark used for the roofline denominator: runs `iters` dependent DFMA chains
+ * on every SM, returns achieved FLOP/s (2 flop per FMA) through *flops, timed with CUDA events. */
+int lsim_measure_fp64_peak(int64_t iters, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSIM_H */

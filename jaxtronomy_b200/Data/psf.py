@@ -1,0 +1,63 @@
+"""PSF container (host): lenstronomy.Data.psf.PSF as consumed by jaxtronomy/ImSim/Numerics/numerics.py:78-139."""
+
+import numpy as np
+
+from jaxtronomy_b200.Util import util
+
+
+class PSF(object):
+    def __init__(self, psf_type="NONE", fwhm=None, truncation=5, pixel_size=None, kernel_point_source=None,
+                 psf_variance_map=None, point_source_supersampling_factor=1, kernel_point_source_init=None,
+                 kernel_point_source_normalisation=True):
+        self.psf_type = psf_type
+        self._pixel_size = pixel_size
+        self.kernel_point_source_init = kernel_point_source_init
+        self.point_source_supersampling_factor = point_source_supersampling_factor
+        if psf_type == "GAUSSIAN":
+            if fwhm is None:
+                raise ValueError("fwhm must be set for GAUSSIAN psf type!")
+            self._fwhm = fwhm
+            self._sigma_gaussian = util.fwhm2sigma(fwhm)
+            self._truncation = truncation
+        elif psf_type == "PIXEL":
+            if kernel_point_source is None:
+                raise ValueError("kernel_point_source needs to be specified for PIXEL PSF type!")
+            kernel = np.array(kernel_point_source, dtype=float)
+            if len(kernel) % 2 == 0:
+                raise ValueError("kernel needs to have odd axis number, not ", np.shape(kernel))
+            if point_source_supersampling_factor > 1:
+                raise ValueError("supersampled point-source kernels are outside the scope of jaxtronomy_b200 "
+                                 "(point sources are not on the forward-simulation path)")
+            if kernel_point_source_normalisation:
+                kernel = kernel / np.sum(kernel)
+            self._kernel_point_source = kernel
+        elif psf_type == "NONE":
+            k = np.zeros((3, 3))
+            k[1, 1] = 1
+            self._kernel_point_source = k
+        else:
+            raise ValueError("psf_type %s not supported!" % psf_type)
+        if psf_variance_map is not None:
+            raise ValueError("psf_variance_map is only used with point sources, which are outside the scope of "
+                             "jaxtronomy_b200")
+        self.psf_variance_map_bool = False
+
+    @property
+    def kernel_point_source(self):
+        if self.psf_type == "GAUSSIAN":
+            raise ValueError("the pixelised kernel of a GAUSSIAN PSF is only needed for point sources "
+                             "(outside the scope of jaxtronomy_b200)")
+        return self._kernel_point_source
+
+    @property
+    def fwhm(self):
+        if self.psf_type == "GAUSSIAN":
+            return self._fwhm
+        raise ValueError("fwhm of a %s PSF is not used on the forward-simulation path" % self.psf_type)
+
+    @property
+    def truncation(self):
+        return self._truncation
+
+    def set_pixel_size(self, deltaPix):
+        self._pixel_size = deltaPix

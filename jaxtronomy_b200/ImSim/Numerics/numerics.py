@@ -1,0 +1,147 @@
+"""Numerics: wiring of grid, re-binning and PSF convolution, jaxtronomy/ImSim/Numerics/numerics.py:24-229 and
+convolution.py.  On the host this class only *describes* the numerics (grid arrays, convolution mode, kernel);
+the arithmetic happens in the CUDA kernels (k_image / k_rebin / k_conv_*).
+
+Mapping of the reference's convolution classes onto kernel modes:
+  PixelKernelConvolution  ("fft", "fft_static" and "grid" alike)  -> LSIM_CONV_ZERO, direct "same" convolution
+  GaussianConvolution                                            -> LSIM_CONV_EDGE with the exact [2r+1]^2 kernel;
+                                                                    the kernel is outer(k1, k1), so two 1-d passes
+  psf_type NONE / unconvolved=True                                -> LSIM_CONV_NONE
+Outside the round-1 scope: supersampling_convolution=True, flux_evaluate_indexes sub-frames,
+compute_mode="adaptive".
+"""
+
+import numpy as np
+
+from jaxtronomy_b200 import _lib
+from jaxtronomy_b200.ImSim.Numerics.grid import RegularGrid
+from jaxtronomy_b200.Util import kernel_util, util
+
+__all__ = ["Numerics", "NumericsSubFrame"]
+
+
+def gaussian_pixel_kernel(sigma_scaled, num_pix):
+    """GaussianConvolution.pixel_kernel (convolution.py:254-273): normalised Gaussian.function on make_grid(n, 1)."""
+    if num_pix % 2 == 0:
+        raise ValueError("num_pix must be an odd integer")
+    if num_pix < 3:
+        raise ValueError("psf kernel size must be 3 or greater")
+    x, y = util.make_grid(numPix=num_pix, deltapix=1)
+    c = 1.0 / (2 * np.pi * sigma_scaled**2)
+    r2 = x**2 / sigma_scaled**2 + y**2 / sigma_scaled**2
+    kernel = util.array2image(c * np.exp(-r2 / 2.0))
+    return kernel / np.sum(kernel)
+
+
+class Numerics(object):
+    def __init__(self, pixel_grid, psf, supersampling_factor=1, compute_mode="regular",
+                 supersampling_convolution=False, supersampling_kernel_size=5, flux_evaluate_indexes=None,
+                 supersampled_indexes=None, compute_indexes=None, point_source_supersampling_factor=1,
+                 convolution_kernel_size=None, convolution_type="fft", truncation_conv=None):
+        if compute_mode != "regular":
+            if compute_mode == "adaptive":
+                raise ValueError("AdaptiveConvolution not implemented in Jaxtronomy. Please use lenstronomy instead.")
+            raise ValueError('compute_mode specified as %s not valid. Options are "regular" and "adaptive" '
+                             "(adaptive only supported in lenstronomy)" % compute_mode)
+        self._psf_type = psf.psf_type
+        if not isinstance(supersampling_factor, int):
+            raise TypeError("supersampling_factor needs to be an integer! Current type is %s"
+                            % type(supersampling_factor))
+        if supersampling_factor == 1:
+            supersampling_convolution = False
+        if supersampling_convolution is True and self._psf_type != "NONE":
+            raise NotImplementedError("supersampling_convolution=True is not built yet in jaxtronomy_b200 "
+                                      "(SURVEY.md 8(f)-2); use supersampling_convolution=False")
+        if flux_evaluate_indexes is not None and not bool(np.all(flux_evaluate_indexes)):
+            raise NotImplementedError("flux_evaluate_indexes sub-frames are not built yet in jaxtronomy_b200 "
+                                      "(SURVEY.md 8(f)-2)")
+        if convolution_type not in ("fft", "fft_static", "grid"):
+            raise ValueError("convolution_type %s not supported!" % convolution_type)
+        self._pixel_width = pixel_grid.pixel_width
+        nx, ny = pixel_grid.num_pixel_axes
+        ra0, dec0 = pixel_grid.radec_at_xy_0
+        self._nx, self._ny = nx, ny
+        self._grid = RegularGrid(nx, ny, pixel_grid.transform_pix2angle, ra0, dec0, supersampling_factor, None)
+        self._kernel = None
+        self._kernel_1d = None
+        if self._psf_type == "PIXEL":
+            kernel = psf.kernel_point_source
+            kernel = self._supersampling_cut_kernel(kernel, convolution_kernel_size, supersampling_factor=1)
+            if kernel.shape[0] != kernel.shape[1] or kernel.shape[0] % 2 == 0:
+                raise ValueError("PSF kernel must be square with an odd side, got %s" % (kernel.shape,))
+            self._conv_mode, self._kernel = _lib.CONV_ZERO, np.array(kernel, dtype=float)
+        elif self._psf_type == "GAUSSIAN":
+            sigma = util.fwhm2sigma(psf.fwhm)
+            if truncation_conv is None:
+                truncation_conv = psf.truncation
+            sigma_scaled = sigma / pixel_grid.pixel_width
+            kernel_radius = max(round(sigma_scaled * truncation_conv), 1)
+            num_pix = 2 * int(kernel_radius) + 1
+            self._conv_mode = _lib.CONV_EDGE
+            self._kernel = gaussian_pixel_kernel(sigma_scaled, num_pix)
+            self._kernel_1d = kernel_util.kernel_gaussian_1d(num_pix, sigma_scaled)
+        elif self._psf_type == "NONE":
+            self._conv_mode = _lib.CONV_NONE
+        else:
+            raise ValueError("psf_type %s not valid! Chose either NONE, GAUSSIAN or PIXEL." % self._psf_type)
+        self._plans = {}
+
+    # -- descriptors for _lib.Plan -----------------------------------------------------------------------
+    def grid_dict(self):
+        xs, ys = self._grid.coordinates_full
+        return dict(nx=self._nx, ny=self._ny, ss=self._grid.supersampling_factor, x_sub=xs, y_sub=ys)
+
+    def psf_dict(self, unconvolved=False):
+        if unconvolved or self._conv_mode == _lib.CONV_NONE:
+            return dict(mode=_lib.CONV_NONE)
+        return dict(mode=self._conv_mode, kernel=self._kernel, kernel_1d=self._kernel_1d)
+
+    @property
+    def pixel_area(self):
+        return self._pixel_width**2
+
+    def re_size_convolve(self, flux_array, unconvolved=False):
+        """flux on ``coordinates_evaluate`` (last axis) -> convolved image on the pixel grid [..., ny, nx] * pixel
+        area (numerics.py:157-177).  NumPy in -> NumPy out; torch CUDA in -> torch CUDA out."""
+        want_torch = type(flux_array).__module__.startswith("torch")
+        full = self._grid.flux_to_full_grid(flux_array)
+        lead = tuple(full.shape[:-1])
+        flat = full.reshape((-1, full.shape[-1]))
+        key = bool(unconvolved)
+        if key not in self._plans:
+            self._plans[key] = _lib.Plan(0, grid=self.grid_dict(), psf=self.psf_dict(unconvolved),
+                                         image_scale=self.pixel_area)
+        out = self._plans[key].resize_convolve(flat, unconvolved=unconvolved)
+        out = out.reshape(lead + (self._ny, self._nx))
+        return out if want_torch else out.cpu().numpy()
+
+    @property
+    def grid_supersampling_factor(self):
+        return self._grid.supersampling_factor
+
+    @property
+    def coordinates_evaluate(self):
+        return self._grid.coordinates_evaluate
+
+    @staticmethod
+    def _supersampling_cut_kernel(kernel_super, convolution_kernel_size, supersampling_factor):
+        """numerics.py:197-214."""
+        if convolution_kernel_size is not None:
+            size = convolution_kernel_size * supersampling_factor
+            if size % 2 == 0:
+                size += 1
+            return kernel_util.cut_psf(kernel_super, size, normalisation=False)
+        return kernel_super
+
+    @property
+    def convolution_kernel(self):
+        return self._kernel
+
+    @property
+    def grid_class(self):
+        return self._grid
+
+
+class NumericsSubFrame(Numerics):
+    """numerics_subframe.py: with flux_evaluate_indexes=None the sub-frame is the full frame, which is the only
+    case built so far; the class name is kept so that ImageModel reads like the reference."""

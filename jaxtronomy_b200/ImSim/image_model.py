@@ -1,0 +1,227 @@
+"""ImageModel façade, jaxtronomy/ImSim/image_model.py:23-694: same constructor and method signatures for the
+extended-source path; every image / likelihood call is one lsim_image / lsim_logl launch sequence.
+
+Batching: any kwargs value may be a ``[B]`` array instead of a scalar; outputs then carry a leading B axis
+(the reference gets the same with ``jax.vmap``).  ``image_batch`` / ``logL_batch`` take a ready-made ``[B, P]``
+parameter matrix in the column order of ``self.param_layout.names`` and skip all Python-side packing.
+"""
+
+import numpy as np
+
+from jaxtronomy_b200 import _arrays, _lib, _model
+from jaxtronomy_b200.ImSim.Numerics.numerics import NumericsSubFrame
+from jaxtronomy_b200.LensModel.lens_model import LensModel
+from jaxtronomy_b200.LightModel.light_model import LightModel
+from jaxtronomy_b200.Util import util
+
+__all__ = ["ImageModel"]
+
+
+class ImageModel(object):
+    """This class uses functions of lens_model and source_model to make a lensed image."""
+
+    def __init__(self, data_class, psf_class, lens_model_class=None, source_model_class=None,
+                 lens_light_model_class=None, point_source_class=None, extinction_class=None, kwargs_numerics=None,
+                 likelihood_mask=None, psf_error_map_bool_list=None, kwargs_pixelbased=None):
+        self.type = "single-band"
+        self.num_bands = 1
+        self.PSF = psf_class
+        self.Data = data_class
+        self._flux_scaling = getattr(self.Data, "flux_scaling", 1)
+        self.PSF.set_pixel_size(self.Data.pixel_width)
+        if kwargs_numerics is None:
+            kwargs_numerics = {}
+        self.ImageNumerics = NumericsSubFrame(pixel_grid=self.Data, psf=self.PSF, **kwargs_numerics)
+        if lens_model_class is None:
+            lens_model_class = LensModel(lens_model_list=[])
+        self.LensModel = lens_model_class
+        if point_source_class is not None and len(getattr(point_source_class, "point_source_type_list", [])) > 0:
+            raise ValueError("point sources are outside the scope of jaxtronomy_b200 (SURVEY.md 8(f)-3)")
+        self.PointSource = point_source_class
+        if source_model_class is None:
+            source_model_class = LightModel(light_model_list=[])
+        self.SourceModel = source_model_class
+        if lens_light_model_class is None:
+            lens_light_model_class = LightModel(light_model_list=[])
+        self.LensLightModel = lens_light_model_class
+        self._kwargs_numerics = kwargs_numerics
+        if extinction_class is not None:
+            raise ValueError("Extinction is not implemented in JAXtronomy yet")
+        if kwargs_pixelbased is not None:
+            raise ValueError("pixelbased solver not supported in JAXtronomy")
+        self._pixelbased_bool = False
+        if likelihood_mask is None:
+            likelihood_mask = np.ones(data_class.num_pixel_axes)
+        self.likelihood_mask = np.array(likelihood_mask, dtype=bool)
+        self.num_data_evaluate = int(np.sum(self.likelihood_mask))
+        self._mask1d = util.image2array(self.likelihood_mask)
+        if data_class.primary_beam is not None:
+            raise ValueError("primary beam not supported in jaxtronomy")
+        # one column per parameter, in the order lens -> source -> lens light (Param.args2kwargs order)
+        self.param_layout = _model.ColumnLayout()
+        self.LensModel.lens_descs(self.param_layout)
+        self.SourceModel.light_descs(self.param_layout, "source", True, [0] * self.SourceModel._num_func, True)
+        self.LensLightModel.light_descs(self.param_layout, "lens_light", False, [0] * self.LensLightModel._num_func,
+                                        True)
+        self._plans = {}
+
+    # ----------------------------------------------------------------------------------------------------
+    # plans
+    # ----------------------------------------------------------------------------------------------------
+    def _data_dict(self):
+        d = self.Data
+        return dict(data=d.data, cd_data=d.C_D, noise_map2=None if d._noise_map is None else d._noise_map**2,
+                    exposure=getattr(d, "exposure_map", None), background_rms=d.background_rms,
+                    mask=None if bool(np.all(self.likelihood_mask)) else self.likelihood_mask)
+
+    def _build_plan(self, source_slots, lens_light_slots, n_slots, use_amp, unconvolved, lensed=True):
+        layout = _model.ColumnLayout()
+        lens_descs = self.LensModel.lens_descs(layout)  # always registers the lens columns
+        if not lensed:
+            lens_descs = []
+        light = self.SourceModel.light_descs(layout, "source", lensed=lensed, slots=source_slots, use_amp=use_amp)
+        light += self.LensLightModel.light_descs(layout, "lens_light", lensed=False, slots=lens_light_slots,
+                                                 use_amp=use_amp)
+        return _lib.Plan(layout.n_cols, lens_descs=lens_descs, light_descs=light, n_slots=n_slots,
+                         grid=self.ImageNumerics.grid_dict(), psf=self.ImageNumerics.psf_dict(unconvolved),
+                         image_scale=self.ImageNumerics.pixel_area * self._flux_scaling, data=self._data_dict(),
+                         **self.LensModel.plan_kwargs())
+
+    def _joint_plan(self, source_bool, lens_light_bool, unconvolved=False, de_lensed=False):
+        """All selected components summed with their amplitudes into one image."""
+        key = ("joint", tuple(source_bool), tuple(lens_light_bool), bool(unconvolved), bool(de_lensed))
+        if key not in self._plans:
+            self._plans[key] = self._build_plan([0 if b else -1 for b in source_bool],
+                                                [0 if b else -1 for b in lens_light_bool], 1, True, unconvolved,
+                                                lensed=not de_lensed)
+        return self._plans[key]
+
+    def _pack(self, kwargs_lens, kwargs_source, kwargs_lens_light):
+        values = _model.gather_values(self.LensModel.param_name_list, kwargs_lens or [], "lens")
+        values += _model.gather_values(self.SourceModel.param_name_list, kwargs_source or [], "source light")
+        values += _model.gather_values(self.LensLightModel.param_name_list, kwargs_lens_light or [], "lens light")
+        return _model.pack_columns(values)
+
+    @staticmethod
+    def _want_torch(*kwargs_lists):
+        for kl in kwargs_lists:
+            for kw in kl or []:
+                for v in kw.values():
+                    if _arrays.is_torch(v):
+                        return True
+        return False
+
+    @staticmethod
+    def _finish(t, batched, want_torch):
+        if not batched:
+            t = t[0]
+        return t if want_torch else t.cpu().numpy()
+
+    # ----------------------------------------------------------------------------------------------------
+    # images
+    # ----------------------------------------------------------------------------------------------------
+    def image(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None, kwargs_ps=None,
+              kwargs_extinction=None, kwargs_special=None, unconvolved=False, source_add=True, lens_light_add=True,
+              point_source_add=True):
+        """Make an image with a realisation of linear parameter values (image_model.py:431-492)."""
+        if kwargs_extinction:
+            raise ValueError("Extinction is not implemented in JAXtronomy yet")
+        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light)
+        plan = self._joint_plan([bool(source_add)] * self.SourceModel._num_func,
+                                [bool(lens_light_add)] * self.LensLightModel._num_func, unconvolved)
+        out = plan.image(mat)[:, 0]
+        return self._finish(out, batched, self._want_torch(kwargs_lens, kwargs_source, kwargs_lens_light))
+
+    def source_surface_brightness(self, kwargs_source, kwargs_lens=None, kwargs_extinction=None, kwargs_special=None,
+                                  unconvolved=False, de_lensed=False, k=None, update_pixelbased_mapping=True):
+        """image_model.py:223-368."""
+        if len(self.SourceModel.profile_type_list) == 0:
+            return np.zeros(self.Data.num_pixel_axes)
+        if kwargs_extinction:
+            raise ValueError("Extinction is not implemented in JAXtronomy yet")
+        mat, B, batched = self._pack(kwargs_lens, kwargs_source, self._dummy_lens_light())
+        plan = self._joint_plan(self.SourceModel._bool_list(k), [False] * self.LensLightModel._num_func, unconvolved,
+                                de_lensed=de_lensed)
+        return self._finish(plan.image(mat)[:, 0], batched, self._want_torch(kwargs_lens, kwargs_source))
+
+    def lens_surface_brightness(self, kwargs_lens_light, unconvolved=False, k=None):
+        """image_model.py:370-393."""
+        mat, B, batched = self._pack(self._dummy_lens(), self._dummy_source(), kwargs_lens_light)
+        plan = self._joint_plan([False] * self.SourceModel._num_func, self.LensLightModel._bool_list(k), unconvolved)
+        return self._finish(plan.image(mat)[:, 0], batched, self._want_torch(kwargs_lens_light))
+
+    def _dummy(self, names_list):
+        return [{n: 1.0 for n in names} for names in names_list]
+
+    def _dummy_lens(self):
+        return self._dummy(self.LensModel.param_name_list)
+
+    def _dummy_source(self):
+        return self._dummy(self.SourceModel.param_name_list)
+
+    def _dummy_lens_light(self):
+        return self._dummy(self.LensLightModel.param_name_list)
+
+    # ----------------------------------------------------------------------------------------------------
+    # likelihood
+    # ----------------------------------------------------------------------------------------------------
+    def likelihood_data_given_model(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None,
+                                    kwargs_ps=None, kwargs_extinction=None, kwargs_special=None, source_marg=False,
+                                    linear_prior=None, check_positive_flux=False):
+        """log-likelihood of the data given the model, amplitudes taken from the kwargs
+        (image_model.py:162-221)."""
+        if check_positive_flux:
+            raise ValueError("check positive flux is not supported in jaxtronomy")
+        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light)
+        logl = self.logL_batch(mat)
+        return self._finish(logl, batched, self._want_torch(kwargs_lens, kwargs_source, kwargs_lens_light))
+
+    def logL_batch(self, params, out=None):
+        """[B, P] parameter matrix (columns = self.param_layout order: lens, source, lens light) -> logL [B]
+        as a CUDA tensor on the current stream."""
+        plan = self._joint_plan([True] * self.SourceModel._num_func, [True] * self.LensLightModel._num_func)
+        return plan.logl(params, linear_solve=False, out=out)[0]
+
+    def image_batch(self, params):
+        """[B, P] -> model images [B, ny, nx] (CUDA tensor)."""
+        plan = self._joint_plan([True] * self.SourceModel._num_func, [True] * self.LensLightModel._num_func)
+        return plan.image(params)[:, 0]
+
+    @property
+    def param_names(self):
+        """(component, profile index, parameter name) of every column of the batch parameter matrix."""
+        return self.param_layout.names
+
+    # ----------------------------------------------------------------------------------------------------
+    # masks (host bookkeeping, bit-exact: image_model.py:542-574)
+    # ----------------------------------------------------------------------------------------------------
+    def image2array_masked(self, image):
+        if _arrays.is_torch(image):
+            import torch
+
+            return image.reshape(image.shape[:-2] + (-1,))[..., torch.as_tensor(self._mask1d, device=image.device)]
+        image = np.asarray(image)
+        return image.reshape(image.shape[:-2] + (-1,))[..., self._mask1d]
+
+    def array_masked2image(self, array):
+        nx, ny = self.Data.num_pixel_axes
+        array = np.asarray(array)
+        grid1d = np.zeros(array.shape[:-1] + (nx * ny,))
+        grid1d[..., self._mask1d] = array
+        return grid1d.reshape(array.shape[:-1] + (ny, nx))
+
+    @property
+    def data_response(self):
+        return self.image2array_masked(self.Data.data)
+
+    def error_response(self, kwargs_lens, kwargs_ps, kwargs_special):
+        """C_D of the data on the unmasked pixels (+ model error, zero without point sources),
+        image_model.py:576-595."""
+        model_error = np.zeros(self.Data.num_pixel_axes)
+        return self.image2array_masked(self.Data.C_D + model_error), model_error
+
+    def update_psf(self, psf_class):
+        raise ValueError("Updating psf class not supported in jaxtronomy. Create a new instance of ImageModel instead.")
+
+    def update_data(self, data_class):
+        raise ValueError("Updating data class not supported in jaxtronomy. Create a new instance of ImageModel instead.")

@@ -1,0 +1,535 @@
+// lsim_api.cu -- C ABI (include/lsim.h) over the kernels in lsim_kernels.cuh.  Single translation unit.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/lsim.h"
+#include "lsim_kernels.cuh"
+
+using namespace lsim;
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+  return LSIM_E_CUDA;
+}
+
+#define LSIM_CUDA(call)                                   \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+int after_launch(const char* name) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, name);
+  return LSIM_OK;
+}
+
+// ---- optional per-kernel timing (lsim_timing_enable): CUDA events around every launch, on its stream ----------
+struct TimedEvent {
+  int cls;
+  cudaEvent_t e0, e1;
+};
+std::atomic<int> g_timing{0};
+std::mutex g_timing_mu;
+std::vector<TimedEvent> g_timed;
+
+struct Timed {
+  bool on;
+  TimedEvent ev;
+  cudaStream_t st;
+  Timed(int cls, cudaStream_t stream) : on(g_timing.load() != 0), st(stream) {
+    if (!on) return;
+    ev.cls = cls;
+    cudaEventCreate(&ev.e0);
+    cudaEventCreate(&ev.e1);
+    cudaEventRecord(ev.e0, st);
+  }
+  ~Timed() {
+    if (!on) return;
+    cudaEventRecord(ev.e1, st);
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_timed.push_back(ev);
+  }
+};
+enum { kClsImage = 0, kClsConv = 1, kClsLike = 2, kClsOther = 3 };
+
+const int kLensParams[LSIM_LENS_TYPE_COUNT] = {0, 6, 5, 6, 3, 4, 3, 4, 5, 6, 12, 6, 6, 6};
+const int kLightParams[LSIM_LIGHT_TYPE_COUNT] = {5, 7, 4};
+
+}  // namespace
+
+struct lsim_plan {
+  PlanDev dev;
+  std::vector<void*> owned;
+  bool full = false;
+  int n_series = 0;
+  bool has_image = false, has_data = false;
+  size_t image_smem = 0;
+  int n_sm = 148;
+
+  ~lsim_plan() {
+    for (void* p : owned) cudaFree(p);
+  }
+  template <class T>
+  int upload(const T* host, size_t n, const T** dev_out) {
+    void* d = nullptr;
+    LSIM_CUDA(cudaMalloc(&d, n * sizeof(T)));
+    owned.push_back(d);
+    LSIM_CUDA(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dev_out = static_cast<const T*>(d);
+    return LSIM_OK;
+  }
+};
+
+namespace {
+
+int upload_tables() {
+  // constant memory is per device (per context): upload on every plan creation; it is 1.4 KB
+  LSIM_CUDA(cudaMemcpyToSymbol(d_nfw_cse_high_s, LSIM_NFW_CSE_HIGH_S, sizeof(LSIM_NFW_CSE_HIGH_S)));
+  LSIM_CUDA(cudaMemcpyToSymbol(d_nfw_cse_high_a, LSIM_NFW_CSE_HIGH_A, sizeof(LSIM_NFW_CSE_HIGH_A)));
+  LSIM_CUDA(cudaMemcpyToSymbol(d_nfw_cse_low_s, LSIM_NFW_CSE_LOW_S, sizeof(LSIM_NFW_CSE_LOW_S)));
+  LSIM_CUDA(cudaMemcpyToSymbol(d_nfw_cse_low_a, LSIM_NFW_CSE_LOW_A, sizeof(LSIM_NFW_CSE_LOW_A)));
+  LSIM_CUDA(cudaMemcpyToSymbol(d_hernquist_cse_s, LSIM_HERNQUIST_CSE_S, sizeof(LSIM_HERNQUIST_CSE_S)));
+  LSIM_CUDA(cudaMemcpyToSymbol(d_hernquist_cse_a, LSIM_HERNQUIST_CSE_A, sizeof(LSIM_HERNQUIST_CSE_A)));
+  return LSIM_OK;
+}
+
+constexpr size_t kRaySmem = kLensChunk * sizeof(LensC) + (size_t)kMaxSeriesProfiles * kMaxSeries * sizeof(double);
+constexpr size_t kConvSmemMax = 200 * 1024;
+
+int configure_kernels() {
+  LSIM_CUDA(cudaFuncSetAttribute(k_conv_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
+  LSIM_CUDA(cudaFuncSetAttribute(k_conv_separable, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
+  return LSIM_OK;
+}
+
+double series_tol_default() {
+  const char* s = getenv("LSIM_SERIES_TOL");
+  if (s && *s) return atof(s);
+  return 1e-14;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lsim_abi_version(void) { return LSIM_ABI_VERSION; }
+
+const char* lsim_strerror(int code) {
+  switch (code) {
+    case LSIM_OK: return "ok";
+    case LSIM_E_INVALID: return "invalid descriptor or argument";
+    case LSIM_E_UNSUPPORTED: return "configuration outside the scope of this library";
+    case LSIM_E_CUDA: return "CUDA runtime error (see lsim_last_cuda_error)";
+    case LSIM_E_WORKSPACE: return "workspace too small (see lsim_workspace_bytes)";
+    case LSIM_E_NO_IMAGE: return "plan has no evaluation grid / data for this call";
+    default: return "unknown error";
+  }
+}
+
+const char* lsim_last_cuda_error(void) { return g_cuda_err; }
+
+int64_t lsim_launch_count(void) { return g_launches.load(); }
+
+int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
+  if (!d || !out) return LSIM_E_INVALID;
+  *out = nullptr;
+  if (d->abi_version != LSIM_ABI_VERSION) return LSIM_E_INVALID;
+  if (d->n_param_cols < 0 || d->n_lens < 0 || d->n_light < 0) return LSIM_E_INVALID;
+  if (d->n_lens > 0 && !d->lens) return LSIM_E_INVALID;
+  if (d->n_light > 0 && !d->light) return LSIM_E_INVALID;
+  if (d->n_light > kMaxLight) return LSIM_E_UNSUPPORTED;
+  if (d->n_slots < 1 || d->n_slots > LSIM_MAX_SLOTS) return LSIM_E_INVALID;
+  bool full = false;
+  int n_series = 0;
+  for (int i = 0; i < d->n_lens; ++i) {
+    const lsim_lens_desc& L = d->lens[i];
+    if (L.type < 0 || L.type >= LSIM_LENS_TYPE_COUNT) return LSIM_E_INVALID;
+    for (int k = 0; k < kLensParams[L.type]; ++k)
+      if (L.col[k] >= d->n_param_cols) return LSIM_E_INVALID;
+    full = full || lens_type_is_full(L.type);
+    if (lens_type_has_series(L)) ++n_series;
+    if (d->multi_plane && !(L.T_z > 0)) return LSIM_E_INVALID;
+  }
+  // every window of kLensChunk consecutive profiles may hold at most kMaxSeriesProfiles series-bearing ones
+  for (int c0 = 0; c0 < d->n_lens; c0 += kLensChunk) {
+    int cnt = 0;
+    for (int i = c0; i < d->n_lens && i < c0 + kLensChunk; ++i) cnt += lens_type_has_series(d->lens[i]) ? 1 : 0;
+    if (cnt > kMaxSeriesProfiles) return LSIM_E_UNSUPPORTED;
+  }
+  for (int i = 0; i < d->n_light; ++i) {
+    const lsim_light_desc& G = d->light[i];
+    if (G.type < 0 || G.type >= LSIM_LIGHT_TYPE_COUNT) return LSIM_E_INVALID;
+    if (G.slot >= d->n_slots) return LSIM_E_INVALID;
+    for (int k = 0; k < kLightParams[G.type]; ++k)
+      if (G.col[k] >= d->n_param_cols) return LSIM_E_INVALID;
+  }
+  if (d->multi_plane && !(d->T_z_source > 0)) return LSIM_E_INVALID;
+  const bool has_image = d->x_sub != nullptr;
+  if (has_image) {
+    if (d->nx <= 0 || d->ny <= 0 || d->ss <= 0 || !d->y_sub) return LSIM_E_INVALID;
+    if (d->n_lens > kMaxImageLens) return LSIM_E_UNSUPPORTED;
+    if (d->conv_mode < LSIM_CONV_NONE || d->conv_mode > LSIM_CONV_EDGE) return LSIM_E_INVALID;
+    if (d->conv_mode != LSIM_CONV_NONE) {
+      if (d->kernel_size < 1 || d->kernel_size % 2 == 0 || !d->kernel) return LSIM_E_INVALID;
+      if (d->kernel_separable && !d->kernel_1d) return LSIM_E_INVALID;
+    }
+  }
+  const bool has_data = has_image && d->data && d->cd_data && (d->noise_map2 || d->exposure);
+
+  lsim_plan* p = new (std::nothrow) lsim_plan();
+  if (!p) return LSIM_E_INVALID;
+  int rc;
+#define TRY(x)          \
+  do {                  \
+    rc = (x);           \
+    if (rc != LSIM_OK) { \
+      delete p;         \
+      return rc;        \
+    }                   \
+  } while (0)
+  TRY(upload_tables());
+  TRY(configure_kernels());
+  int devid = 0;
+  cudaGetDevice(&devid);
+  cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, devid);
+  PlanDev& D = p->dev;
+  memset(&D, 0, sizeof(D));
+  D.n_param_cols = d->n_param_cols;
+  D.n_lens = d->n_lens;
+  D.ray.multi_plane = d->multi_plane;
+  D.ray.alpha_scaling = d->multi_plane ? 1.0 : d->alpha_scaling;
+  D.ray.T_ij_end = d->T_ij_end;
+  D.ray.inv_T_z_source = d->multi_plane ? 1.0 / d->T_z_source : 0.0;
+  D.n_light = d->n_light;
+  D.n_slots = d->n_slots;
+  D.series_tol = series_tol_default();
+  if (d->n_lens) TRY(p->upload(d->lens, (size_t)d->n_lens, &D.lens));
+  if (d->n_light) TRY(p->upload(d->light, (size_t)d->n_light, &D.light));
+  p->full = full;
+  p->n_series = n_series;
+  p->has_image = has_image;
+  p->has_data = has_data;
+  if (has_image) {
+    D.nx = d->nx;
+    D.ny = d->ny;
+    D.ss = d->ss;
+    const size_t nsub = (size_t)d->nx * d->ny * d->ss * d->ss, npix = (size_t)d->nx * d->ny;
+    TRY(p->upload(d->x_sub, nsub, &D.x_sub));
+    TRY(p->upload(d->y_sub, nsub, &D.y_sub));
+    D.conv_mode = d->conv_mode;
+    D.K = d->conv_mode != LSIM_CONV_NONE ? d->kernel_size : 0;
+    D.image_scale = d->image_scale;
+    if (d->conv_mode != LSIM_CONV_NONE) {
+      TRY(p->upload(d->kernel, (size_t)d->kernel_size * d->kernel_size, &D.kernel));
+      if (d->kernel_separable) TRY(p->upload(d->kernel_1d, (size_t)d->kernel_size, &D.kernel_1d));
+    }
+    p->image_smem = (size_t)d->n_lens * sizeof(LensC) + (size_t)d->n_light * sizeof(LightC) +
+                    (size_t)n_series * kMaxSeries * sizeof(double);
+    if (p->image_smem > 48 * 1024) {
+      delete p;
+      return LSIM_E_UNSUPPORTED;
+    }
+    if (has_data) {
+      TRY(p->upload(d->data, npix, &D.data));
+      std::vector<double> w(npix);
+      for (size_t i = 0; i < npix; ++i) w[i] = 1.0 / d->cd_data[i];
+      TRY(p->upload(w.data(), npix, &D.w_data));
+      if (d->noise_map2) {
+        TRY(p->upload(d->noise_map2, npix, &D.noise_map2));
+      } else {
+        for (size_t i = 0; i < npix; ++i) w[i] = 1.0 / d->exposure[i];
+        TRY(p->upload(w.data(), npix, &D.inv_exposure));
+      }
+      D.bkg2 = d->background_rms * d->background_rms;
+      if (d->mask) TRY(p->upload(d->mask, npix, &D.mask));
+    }
+  }
+#undef TRY
+  *out = p;
+  return LSIM_OK;
+}
+
+void lsim_plan_destroy(lsim_plan* plan) { delete plan; }
+
+int lsim_ray_shoot(const lsim_plan* plan, const double* params, int64_t B, const double* x, const double* y,
+                   int64_t N, int coords_batched, double* out_x, double* out_y, int what, void* stream) {
+  if (!plan || B < 0 || N < 0 || (what != 0 && what != 1)) return LSIM_E_INVALID;
+  if (B == 0 || N == 0) return LSIM_OK;
+  if (!x || !y || !out_x || !out_y || (plan->dev.n_param_cols > 0 && !params)) return LSIM_E_INVALID;
+  if (what == 1 && plan->dev.ray.multi_plane) return LSIM_E_UNSUPPORTED;
+  if (B > 65535) return LSIM_E_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)((N + kBlock * kRayItems - 1) / (kBlock * kRayItems)), (unsigned)B);
+  if (plan->full)
+    k_ray_shoot<true><<<grid, kBlock, kRaySmem, st>>>(plan->dev, params, x, y, N, coords_batched, out_x, out_y, what);
+  else
+    k_ray_shoot<false><<<grid, kBlock, kRaySmem, st>>>(plan->dev, params, x, y, N, coords_batched, out_x, out_y, what);
+  return after_launch("k_ray_shoot");
+}
+
+int lsim_surface_brightness(const lsim_plan* plan, const double* params, int64_t B, const double* x,
+                            const double* y, int64_t N, int coords_batched, double* out, void* stream) {
+  if (!plan || B < 0 || N < 0) return LSIM_E_INVALID;
+  if (B == 0 || N == 0) return LSIM_OK;
+  if (!x || !y || !out || (plan->dev.n_param_cols > 0 && !params)) return LSIM_E_INVALID;
+  if (B > 65535) return LSIM_E_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t bx = (N + kBlock - 1) / kBlock;
+  if (bx > 4096) bx = 4096;
+  dim3 grid((unsigned)bx, (unsigned)B);
+  k_surface_brightness<<<grid, kBlock, 0, st>>>(plan->dev, params, x, y, N, coords_batched, out);
+  return after_launch("k_surface_brightness");
+}
+
+}  // extern "C"
+
+namespace {
+
+size_t per_set_bytes(const lsim_plan* plan, bool need_conv_out) {
+  const size_t npix = (size_t)plan->dev.nx * plan->dev.ny;
+  const bool conv = plan->dev.conv_mode != LSIM_CONV_NONE;
+  size_t n = 0;
+  n += npix * plan->dev.n_slots;                           // unconvolved basis images
+  if (conv && need_conv_out) n += npix * plan->dev.n_slots;  // convolved basis images
+  return n * sizeof(double);
+}
+
+int64_t chunk_sets(const lsim_plan* plan) { return (int64_t)plan->n_sm * 8; }
+
+template <int NSLOT>
+int launch_image_ns(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
+                    double scale, double* out, cudaStream_t st) {
+  dim3 grid((unsigned)tiles, (unsigned)n);
+  Timed timed(kClsImage, st);
+  if (plan->full)
+    k_image<NSLOT, true><<<grid, kBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out);
+  else
+    k_image<NSLOT, false><<<grid, kBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out);
+  return after_launch("k_image");
+}
+
+// ray-shoot + light + re-bin for sets [set0, set0+n) -> out[n][n_slots][npix]
+int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, double scale, double* out,
+                 cudaStream_t st) {
+  const int npix = plan->dev.nx * plan->dev.ny;
+  int64_t want = ((int64_t)plan->n_sm * 4 + n - 1) / n;  // CTAs per set so that the grid fills the chip
+  int max_tiles = (npix + kBlock - 1) / kBlock;
+  int tiles = (int)(want < 1 ? 1 : (want > max_tiles ? max_tiles : want));
+  int ppt = (npix + tiles - 1) / tiles;
+  ppt = ((ppt + kBlock - 1) / kBlock) * kBlock;
+  tiles = (npix + ppt - 1) / ppt;
+  const int ns = plan->dev.n_slots;
+  if (ns <= 1) return launch_image_ns<1>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  if (ns <= 2) return launch_image_ns<2>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  if (ns <= 4) return launch_image_ns<4>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  return launch_image_ns<8>(plan, params, set0, n, ppt, tiles, scale, out, st);
+}
+
+int launch_conv(const lsim_plan* plan, const double* in, double* out, int64_t n_images, cudaStream_t st) {
+  const PlanDev& D = plan->dev;
+  const int K = D.K, TW = kConvT + K - 1, pitch = TW | 1;
+  const int tiles = ((D.nx + kConvT - 1) / kConvT) * ((D.ny + kConvT - 1) / kConvT);
+  for (int64_t i0 = 0; i0 < n_images; i0 += 65535) {
+    int64_t ni = n_images - i0 < 65535 ? n_images - i0 : 65535;
+    dim3 grid((unsigned)tiles, (unsigned)ni);
+    const size_t off = (size_t)i0 * D.nx * D.ny;
+    Timed timed(kClsConv, st);
+    if (D.kernel_1d) {
+      size_t smem = ((size_t)TW * pitch + (size_t)TW * (kConvT + 1) + K) * sizeof(double);
+      if (smem > kConvSmemMax) return LSIM_E_UNSUPPORTED;
+      k_conv_separable<<<grid, kBlock, smem, st>>>(in + off, out + off, D.nx, D.ny, K, D.kernel_1d, D.conv_mode,
+                                                   D.image_scale);
+    } else {
+      size_t smem = ((size_t)TW * pitch + (size_t)K * K) * sizeof(double);
+      if (smem > kConvSmemMax) return LSIM_E_UNSUPPORTED;
+      k_conv_direct<<<grid, kBlock, smem, st>>>(in + off, out + off, D.nx, D.ny, K, D.kernel, D.conv_mode,
+                                                D.image_scale);
+    }
+    int rc = after_launch("k_conv");
+    if (rc != LSIM_OK) return rc;
+  }
+  return LSIM_OK;
+}
+
+int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, int64_t n, int linear, int marg,
+                      double* logl, double* amps, double* model, cudaStream_t st) {
+  const int ns = plan->dev.n_slots;
+  dim3 grid((unsigned)n);
+  Timed timed(kClsLike, st);
+  if (ns <= 1)
+    k_likelihood<1><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model);
+  else if (ns <= 2)
+    k_likelihood<2><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model);
+  else if (ns <= 4)
+    k_likelihood<4><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model);
+  else
+    k_likelihood<8><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model);
+  return after_launch("k_likelihood");
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t lsim_workspace_bytes(const lsim_plan* plan, int64_t B) {
+  if (!plan || !plan->has_image || B <= 0) return 0;
+  int64_t c = chunk_sets(plan);
+  if (B < c) c = B;
+  return per_set_bytes(plan, true) * (size_t)c;
+}
+
+int lsim_image(const lsim_plan* plan, const double* params, int64_t B, double* images, void* workspace,
+               size_t workspace_bytes, void* stream) {
+  if (!plan || B < 0) return LSIM_E_INVALID;
+  if (!plan->has_image) return LSIM_E_NO_IMAGE;
+  if (B == 0) return LSIM_OK;
+  if (!images || (plan->dev.n_param_cols > 0 && !params)) return LSIM_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PlanDev& D = plan->dev;
+  const size_t img = (size_t)D.nx * D.ny * D.n_slots;
+  if (D.conv_mode == LSIM_CONV_NONE) {
+    for (int64_t s0 = 0; s0 < B; s0 += 32768) {
+      int64_t n = B - s0 < 32768 ? B - s0 : 32768;
+      int rc = launch_image(plan, params, s0, n, D.image_scale, images + (size_t)s0 * img, st);
+      if (rc != LSIM_OK) return rc;
+    }
+    return LSIM_OK;
+  }
+  const size_t per = per_set_bytes(plan, false);
+  int64_t chunk = (int64_t)(workspace_bytes / per);
+  if (!workspace || chunk < 1) return LSIM_E_WORKSPACE;
+  if (chunk > chunk_sets(plan)) chunk = chunk_sets(plan);
+  double* U = static_cast<double*>(workspace);
+  for (int64_t s0 = 0; s0 < B; s0 += chunk) {
+    int64_t n = B - s0 < chunk ? B - s0 : chunk;
+    int rc = launch_image(plan, params, s0, n, 1.0, U, st);
+    if (rc != LSIM_OK) return rc;
+    rc = launch_conv(plan, U, images + (size_t)s0 * img, n * D.n_slots, st);
+    if (rc != LSIM_OK) return rc;
+  }
+  return LSIM_OK;
+}
+
+int lsim_resize_convolve(const lsim_plan* plan, const double* flux, int64_t n_images, int unconvolved,
+                         double* images, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!plan || n_images < 0) return LSIM_E_INVALID;
+  if (!plan->has_image) return LSIM_E_NO_IMAGE;
+  if (n_images == 0) return LSIM_OK;
+  if (!flux || !images) return LSIM_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PlanDev& D = plan->dev;
+  const size_t npix = (size_t)D.nx * D.ny, nsub = npix * D.ss * D.ss;
+  const bool conv = D.conv_mode != LSIM_CONV_NONE && !unconvolved;
+  const unsigned tiles = (unsigned)((npix + kBlock - 1) / kBlock);
+  int64_t chunk = conv ? (int64_t)(workspace_bytes / (npix * sizeof(double))) : n_images;
+  if (conv && (!workspace || chunk < 1)) return LSIM_E_WORKSPACE;
+  if (chunk > 65535) chunk = 65535;
+  for (int64_t i0 = 0; i0 < n_images; i0 += chunk) {
+    int64_t n = n_images - i0 < chunk ? n_images - i0 : chunk;
+    double* dst = conv ? static_cast<double*>(workspace) : images + (size_t)i0 * npix;
+    k_rebin<<<dim3(tiles, (unsigned)n), kBlock, 0, st>>>(flux + (size_t)i0 * nsub, dst, D.nx, D.ny, D.ss,
+                                                          conv ? 1.0 : D.image_scale);
+    int rc = after_launch("k_rebin");
+    if (rc != LSIM_OK) return rc;
+    if (conv) {
+      rc = launch_conv(plan, dst, images + (size_t)i0 * npix, n, st);
+      if (rc != LSIM_OK) return rc;
+    }
+  }
+  return LSIM_OK;
+}
+
+int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear_solve, int source_marg,
+              double* logl, double* amps, double* model, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!plan || B < 0) return LSIM_E_INVALID;
+  if (!plan->has_image || !plan->has_data) return LSIM_E_NO_IMAGE;
+  if (B == 0) return LSIM_OK;
+  if (!logl || (plan->dev.n_param_cols > 0 && !params)) return LSIM_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PlanDev& D = plan->dev;
+  const bool conv = D.conv_mode != LSIM_CONV_NONE;
+  const size_t per = per_set_bytes(plan, true);
+  int64_t chunk = (int64_t)(workspace_bytes / per);
+  if (!workspace || chunk < 1) return LSIM_E_WORKSPACE;
+  if (chunk > chunk_sets(plan)) chunk = chunk_sets(plan);
+  const size_t img = (size_t)D.nx * D.ny * D.n_slots;
+  double* U = static_cast<double*>(workspace);
+  double* C = conv ? U + (size_t)chunk * img : U;
+  for (int64_t s0 = 0; s0 < B; s0 += chunk) {
+    int64_t n = B - s0 < chunk ? B - s0 : chunk;
+    int rc = launch_image(plan, params, s0, n, conv ? 1.0 : D.image_scale, U, st);
+    if (rc != LSIM_OK) return rc;
+    if (conv) {
+      rc = launch_conv(plan, U, C, n * D.n_slots, st);
+      if (rc != LSIM_OK) return rc;
+    }
+    rc = launch_likelihood(plan, C, s0, n, linear_solve, source_marg, logl, amps, model, st);
+    if (rc != LSIM_OK) return rc;
+  }
+  return LSIM_OK;
+}
+
+int lsim_timing_enable(int on) {
+  g_timing.store(on ? 1 : 0);
+  return LSIM_OK;
+}
+
+int lsim_timing_read(double ms[4], int64_t count[4]) {
+  if (!ms || !count) return LSIM_E_INVALID;
+  for (int i = 0; i < 4; ++i) {
+    ms[i] = 0.0;
+    count[i] = 0;
+  }
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (TimedEvent& ev : g_timed) {
+    LSIM_CUDA(cudaEventSynchronize(ev.e1));
+    float t = 0;
+    LSIM_CUDA(cudaEventElapsedTime(&t, ev.e0, ev.e1));
+    ms[ev.cls] += t;
+    count[ev.cls] += 1;
+    cudaEventDestroy(ev.e0);
+    cudaEventDestroy(ev.e1);
+  }
+  g_timed.clear();
+  return LSIM_OK;
+}
+
+int lsim_measure_fp64_peak(int64_t iters, double* flops, void* stream) {
+  if (!flops || iters <= 0) return LSIM_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, n_sm = 148;
+  LSIM_CUDA(cudaGetDevice(&dev));
+  LSIM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  double* sink = nullptr;
+  LSIM_CUDA(cudaMalloc(&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  LSIM_CUDA(cudaEventCreate(&e0));
+  LSIM_CUDA(cudaEventCreate(&e1));
+  const int ctas = n_sm * 8;
+  k_fp64_peak<<<ctas, kBlock, 0, st>>>(iters / 8 + 1, sink);  // warm-up
+  LSIM_CUDA(cudaEventRecord(e0, st));
+  k_fp64_peak<<<ctas, kBlock, 0, st>>>(iters, sink);
+  LSIM_CUDA(cudaEventRecord(e1, st));
+  LSIM_CUDA(cudaEventSynchronize(e1));
+  g_launches.fetch_add(2);
+  float ms = 0;
+  LSIM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *flops = 2.0 * 8.0 * (double)iters * (double)ctas * kBlock / (ms * 1e-3);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return LSIM_OK;
+}
+
+}  // extern "C"

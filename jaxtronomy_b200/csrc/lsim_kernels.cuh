@@ -1,0 +1,541 @@
+// lsim_kernels.cuh -- the CUDA kernels of the forward-simulation path (sm_100a).
+//
+//   k_ray_shoot            LensModel.ray_shooting / SinglePlane.alpha / LensModelBulk / MultiPlane on N points x B sets
+//   k_surface_brightness   LightModel.surface_brightness / functions_split on N points x B sets
+//   k_image                fused ray-shoot + light + ss x ss re-bin: one thread per *pixel*, looping its
+//                          ss^2 sub-pixels in registers, so the supersampled flux never exists in memory
+//   k_conv_*               PSF convolution of the re-binned basis images (direct, shared-memory tiled)
+//   k_likelihood           WLS amplitudes (normal equations reduced per CTA, solved in registers) + chi^2
+//   k_fp64_peak            DFMA-chain microbenchmark for the roofline denominator
+//
+// Layout: parameter sets are the slow (grid.y / blockIdx) axis, pixels the fast axis; all global stores
+// are unit-stride over pixels.  Per-set constants live in shared memory (see lsim_profiles.cuh).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "lsim_profiles.cuh"
+
+namespace lsim {
+
+constexpr int kBlock = 256;
+constexpr int kLensChunk = 96;    // lens profiles resident in shared memory at a time (k_ray_shoot streams chunks)
+constexpr int kMaxImageLens = 32; // k_image keeps the whole lens list resident
+constexpr int kMaxLight = 16;
+constexpr int kMaxSeriesProfiles = 4;  // EPL-family profiles per chunk (each owns kMaxSeries coefficients)
+
+// Device view of a plan; passed by value (fits the kernel parameter bank).
+struct PlanDev {
+  int32_t n_param_cols;
+  int32_t n_lens;
+  const lsim_lens_desc* lens;
+  RayCfg ray;
+  int32_t n_light;
+  const lsim_light_desc* light;
+  int32_t n_slots;
+  double series_tol;
+  // image
+  int32_t nx, ny, ss;
+  const double* x_sub;
+  const double* y_sub;
+  int32_t conv_mode, K;
+  const double* kernel;     // [K*K]
+  const double* kernel_1d;  // [K] or null
+  double image_scale;
+  const double* data;
+  const double* w_data;     // 1 / cd_data
+  const double* noise_map2;
+  const double* inv_exposure;
+  double bkg2;
+  const uint8_t* mask;
+};
+
+// ---- shared-memory staging of per-set constants -----------------------------------------------------------
+// Prepares lens profiles [c0, c0+n_c) of the plan for parameter row `row` into L[0..n_c) (+ coefficient pool).
+__device__ __forceinline__ void stage_lens(const PlanDev& P, const double* row, int c0, int n_c, LensC* L,
+                                           double* pool) {
+  for (int i = threadIdx.x; i < n_c; i += blockDim.x) {
+    const lsim_lens_desc& d = P.lens[c0 + i];
+    int off = 0;
+    if (lens_type_has_series(d)) {
+      for (int j = 0; j < i; ++j) off += lens_type_has_series(P.lens[c0 + j]) ? 1 : 0;
+    }
+    L[i].coef_off = off * kMaxSeries;
+    lens_prepare(d, row, L[i], pool + off * kMaxSeries, P.series_tol);
+  }
+}
+
+__device__ __forceinline__ void stage_light(const PlanDev& P, const double* row, LightC* G) {
+  for (int i = threadIdx.x; i < P.n_light; i += blockDim.x) light_prepare(P.light[i], row, G[i]);
+}
+
+// ---- k_ray_shoot ---------------------------------------------------------------------------------------------
+constexpr int kRayItems = 2;
+
+template <bool FULL>
+__global__ void __launch_bounds__(kBlock)
+k_ray_shoot(PlanDev P, const double* __restrict__ params, const double* __restrict__ x, const double* __restrict__ y,
+            int64_t N, int coords_batched, double* __restrict__ ox, double* __restrict__ oy, int what) {
+  extern __shared__ double smem[];
+  LensC* L = reinterpret_cast<LensC*>(smem);
+  double* pool = reinterpret_cast<double*>(L + kLensChunk);
+  const int64_t b = blockIdx.y;
+  const double* row = params + b * P.n_param_cols;
+  const double* xb = coords_batched ? x + b * N : x;
+  const double* yb = coords_batched ? y + b * N : y;
+
+  Ray r[kRayItems];
+  double x0[kRayItems], y0[kRayItems];
+  int64_t idx[kRayItems];
+#pragma unroll
+  for (int k = 0; k < kRayItems; ++k) {
+    idx[k] = (int64_t)blockIdx.x * (kBlock * kRayItems) + k * kBlock + threadIdx.x;
+    x0[k] = idx[k] < N ? xb[idx[k]] : 0.0;
+    y0[k] = idx[k] < N ? yb[idx[k]] : 0.0;
+    ray_init(P.ray, x0[k], y0[k], r[k]);
+  }
+  for (int c0 = 0; c0 < P.n_lens; c0 += kLensChunk) {
+    int n_c = min(kLensChunk, P.n_lens - c0);
+    __syncthreads();
+    stage_lens(P, row, c0, n_c, L, pool);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kRayItems; ++k) {
+      if (idx[k] < N) ray_apply<FULL>(P.ray, L, pool, n_c, r[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kRayItems; ++k) {
+    if (idx[k] < N) {
+      double bx, by;
+      if (what == 1 && !P.ray.multi_plane) {
+        bx = r[k].ax * P.ray.alpha_scaling;
+        by = r[k].ay * P.ray.alpha_scaling;
+      } else {
+        ray_finish(P.ray, r[k], bx, by);
+      }
+      ox[b * N + idx[k]] = bx;
+      oy[b * N + idx[k]] = by;
+    }
+  }
+}
+
+// ---- k_surface_brightness ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+k_surface_brightness(PlanDev P, const double* __restrict__ params, const double* __restrict__ x,
+                     const double* __restrict__ y, int64_t N, int coords_batched, double* __restrict__ out) {
+  __shared__ LightC G[kMaxLight];
+  const int64_t b = blockIdx.y;
+  const double* row = params + b * P.n_param_cols;
+  stage_light(P, row, G);
+  __syncthreads();
+  const double* xb = coords_batched ? x + b * N : x;
+  const double* yb = coords_batched ? y + b * N : y;
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < N; i += (int64_t)gridDim.x * kBlock) {
+    double xx = xb[i], yy = yb[i];
+    for (int s = 0; s < P.n_slots; ++s) {
+      double acc = 0;
+      for (int g = 0; g < P.n_light; ++g) {
+        if (G[g].slot == s) acc += light_eval(G[g], xx, yy);
+      }
+      out[(b * P.n_slots + s) * N + i] = acc;
+    }
+  }
+}
+
+// ---- k_image: fused ray-shoot + light + re-bin ---------------------------------------------------------------
+// grid = (tiles, sets); each CTA owns pixels [tile*ppt, (tile+1)*ppt) of one parameter set.
+// out[(set_local * n_slots + slot) * npix + pixel] = mean over the ss x ss sub-pixels  (* out_scale)
+// (RegularGrid.flux_array2image_low_high + image_util.re_size: grid.py:101-117, image_util.py:78-98).
+template <int NSLOT, bool FULL>
+__global__ void __launch_bounds__(kBlock)
+k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, double out_scale,
+        double* __restrict__ out) {
+  extern __shared__ double smem[];
+  LensC* L = reinterpret_cast<LensC*>(smem);
+  LightC* G = reinterpret_cast<LightC*>(L + P.n_lens);
+  double* pool = reinterpret_cast<double*>(G + P.n_light);
+  const int64_t bl = blockIdx.y;
+  const double* row = params + (set0 + bl) * P.n_param_cols;
+  stage_lens(P, row, 0, P.n_lens, L, pool);
+  stage_light(P, row, G);
+  __syncthreads();
+
+  const int npix = P.nx * P.ny;
+  const int ss = P.ss;
+  const int64_t sub_stride = (int64_t)P.nx * ss;
+  const double inv_ss = 1.0 / ss;
+  const int p_end = min(npix, (int)(blockIdx.x + 1) * ppt);
+  for (int p = blockIdx.x * ppt + threadIdx.x; p < p_end; p += kBlock) {
+    const int py = p / P.nx, px = p - py * P.nx;
+    double acc[NSLOT];
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) acc[k] = 0.0;
+    for (int i = 0; i < ss; ++i) {
+      double racc[NSLOT];
+#pragma unroll
+      for (int k = 0; k < NSLOT; ++k) racc[k] = 0.0;
+      const int64_t base = ((int64_t)py * ss + i) * sub_stride + (int64_t)px * ss;
+      for (int j = 0; j < ss; ++j) {
+        const double x = __ldg(P.x_sub + base + j), y = __ldg(P.y_sub + base + j);
+        Ray r;
+        ray_init(P.ray, x, y, r);
+        ray_apply<FULL>(P.ray, L, pool, P.n_lens, r);
+        double bx, by;
+        ray_finish(P.ray, r, bx, by);
+        for (int g = 0; g < P.n_light; ++g) {
+          const int slot = G[g].slot;
+          if (slot < 0) continue;
+          const double v = G[g].lensed ? light_eval(G[g], bx, by) : light_eval(G[g], x, y);
+#pragma unroll
+          for (int k = 0; k < NSLOT; ++k) racc[k] += (slot == k) ? v : 0.0;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NSLOT; ++k) acc[k] += racc[k] * inv_ss;
+    }
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) {
+      if (k < P.n_slots) out[(bl * P.n_slots + k) * npix + p] = acc[k] * inv_ss * out_scale;
+    }
+  }
+}
+
+// ---- k_rebin: Numerics.re_size_convolve for a caller-supplied supersampled flux ------------------------------
+// flux [n_img][ny*ss][nx*ss] -> out [n_img][ny][nx] = block mean (* scale)  (grid.py:101-117, image_util.py:78-98)
+__global__ void __launch_bounds__(kBlock)
+k_rebin(const double* __restrict__ flux, double* __restrict__ out, int nx, int ny, int ss, double scale) {
+  const int npix = nx * ny;
+  const int64_t nsub = (int64_t)npix * ss * ss;
+  const double* f = flux + (int64_t)blockIdx.y * nsub;
+  const double inv_ss = 1.0 / ss;
+  for (int p = blockIdx.x * kBlock + threadIdx.x; p < npix; p += gridDim.x * kBlock) {
+    const int py = p / nx, px = p - py * nx;
+    double acc = 0.0;
+    for (int i = 0; i < ss; ++i) {
+      double r = 0.0;
+      const double* row = f + ((int64_t)py * ss + i) * ((int64_t)nx * ss) + (int64_t)px * ss;
+      for (int j = 0; j < ss; ++j) r += row[j];
+      acc += r * inv_ss;
+    }
+    out[(int64_t)blockIdx.y * npix + p] = acc * inv_ss * scale;
+  }
+}
+
+// ---- k_conv_direct: "same" 2-D convolution, runtime K, shared-memory tile + halo -----------------------------
+// One CTA computes a kConvT x kConvT output tile of one image; thread (tx, ty) produces kConvR rows.
+// mode ZERO: out = sum_{i,j} in[y - i + r, x - j + r] k[i,j] with zeros outside (fftconvolve "same",
+// convolution.py:73-96); mode EDGE: the image is edge-replicated (convolution.py:216-236).
+constexpr int kConvT = 32;
+constexpr int kConvR = 4;  // rows per thread: 256 threads = 32 x 8, 8*4 = 32 rows
+
+__device__ __forceinline__ double conv_fetch(const double* img, int nx, int ny, int x, int y, int mode) {
+  if (mode == LSIM_CONV_EDGE) {
+    x = min(max(x, 0), nx - 1);
+    y = min(max(y, 0), ny - 1);
+    return img[(int64_t)y * nx + x];
+  }
+  return (x >= 0 && x < nx && y >= 0 && y < ny) ? img[(int64_t)y * nx + x] : 0.0;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_conv_direct(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
+              const double* __restrict__ kernel, int mode, double scale) {
+  extern __shared__ double smem[];
+  const int r = (K - 1) / 2;
+  const int TW = kConvT + K - 1;     // tile width incl. halo
+  const int pitch = TW | 1;          // odd pitch: conflict-free column walks
+  double* tile = smem;               // [TW][pitch]
+  double* w = smem + TW * pitch;     // [K*K], flipped so that the inner loop is a correlation
+  const int tiles_x = (nx + kConvT - 1) / kConvT;
+  const int tx0 = (blockIdx.x % tiles_x) * kConvT, ty0 = (blockIdx.x / tiles_x) * kConvT;
+  const double* img = in + (int64_t)blockIdx.y * nx * ny;
+  for (int i = threadIdx.x; i < K * K; i += kBlock) w[i] = kernel[K * K - 1 - i];
+  for (int i = threadIdx.x; i < TW * TW; i += kBlock) {
+    int ly = i / TW, lx = i - ly * TW;
+    tile[ly * pitch + lx] = conv_fetch(img, nx, ny, tx0 + lx - r, ty0 + ly - r, mode);
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  double acc[kConvR];
+#pragma unroll
+  for (int o = 0; o < kConvR; ++o) acc[o] = 0.0;
+  for (int dy = 0; dy < K; ++dy) {
+    const double* trow = tile + (ty * kConvR + dy) * pitch + tx;
+    const double* wrow = w + dy * K;
+    for (int dx = 0; dx < K; ++dx) {
+      const double wv = wrow[dx];
+#pragma unroll
+      for (int o = 0; o < kConvR; ++o) acc[o] = fma(wv, trow[o * pitch + dx], acc[o]);
+    }
+  }
+  double* dst = out + (int64_t)blockIdx.y * nx * ny;
+#pragma unroll
+  for (int o = 0; o < kConvR; ++o) {
+    int x = tx0 + tx, y = ty0 + ty * kConvR + o;
+    if (x < nx && y < ny) dst[(int64_t)y * nx + x] = acc[o] * scale;
+  }
+}
+
+// Separable variant (kernel == outer(k1, k1), e.g. the Gaussian PSF): row pass into shared memory, column pass out.
+__global__ void __launch_bounds__(kBlock)
+k_conv_separable(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
+                 const double* __restrict__ k1, int mode, double scale) {
+  extern __shared__ double smem[];
+  const int r = (K - 1) / 2;
+  const int TW = kConvT + K - 1;
+  const int pitch = TW | 1;
+  double* tile = smem;                 // [TW rows][pitch]   input with halo
+  double* rowp = tile + TW * pitch;    // [TW rows][kConvT+1] after the row pass
+  double* w = rowp + TW * (kConvT + 1);
+  const int tiles_x = (nx + kConvT - 1) / kConvT;
+  const int tx0 = (blockIdx.x % tiles_x) * kConvT, ty0 = (blockIdx.x / tiles_x) * kConvT;
+  const double* img = in + (int64_t)blockIdx.y * nx * ny;
+  for (int i = threadIdx.x; i < K; i += kBlock) w[i] = k1[K - 1 - i];
+  for (int i = threadIdx.x; i < TW * TW; i += kBlock) {
+    int ly = i / TW, lx = i - ly * TW;
+    tile[ly * pitch + lx] = conv_fetch(img, nx, ny, tx0 + lx - r, ty0 + ly - r, mode);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW * kConvT; i += kBlock) {
+    int ly = i / kConvT, lx = i - ly * kConvT;
+    double a = 0.0;
+    for (int dx = 0; dx < K; ++dx) a = fma(w[dx], tile[ly * pitch + lx + dx], a);
+    rowp[ly * (kConvT + 1) + lx] = a;
+  }
+  __syncthreads();
+  double* dst = out + (int64_t)blockIdx.y * nx * ny;
+  for (int i = threadIdx.x; i < kConvT * kConvT; i += kBlock) {
+    int ly = i / kConvT, lx = i - ly * kConvT;
+    double a = 0.0;
+    for (int dy = 0; dy < K; ++dy) a = fma(w[dy], rowp[(ly + dy) * (kConvT + 1) + lx], a);
+    int x = tx0 + lx, y = ty0 + ly;
+    if (x < nx && y < ny) dst[(int64_t)y * nx + x] = a * scale;
+  }
+}
+
+// ---- reductions -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum `n` per-thread values over the CTA; result valid in thread 0's vals[]. scratch: [n][kBlock/32] doubles.
+template <int N>
+__device__ __forceinline__ void block_sum(double (&vals)[N], double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double v = warp_sum(vals[i]);
+    if (lane == 0) scratch[i * (kBlock / 32) + wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = 0.0;
+      for (int w = 0; w < kBlock / 32; ++w) s += scratch[i * (kBlock / 32) + w];
+      vals[i] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// ---- small dense symmetric solves, one thread ---------------------------------------------------------------
+// Eigenvalues of a symmetric n x n matrix by cyclic Jacobi (destroys a); n <= LSIM_MAX_SLOTS.
+__device__ inline void sym_eigenvalues(double* a, int n, double* ev) {
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; ++i) {
+      diag += a[i * n + i] * a[i * n + i];
+      for (int j = i + 1; j < n; ++j) off += a[i * n + j] * a[i * n + j];
+    }
+    if (!(off > 1e-34 * diag)) break;
+    for (int p = 0; p < n - 1; ++p) {
+      for (int q = p + 1; q < n; ++q) {
+        double apq = a[p * n + q];
+        if (apq == 0.0) continue;
+        double theta = (a[q * n + q] - a[p * n + p]) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; ++k) {
+          double akp = a[k * n + p], akq = a[k * n + q];
+          a[k * n + p] = c * akp - s * akq;
+          a[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          double apk = a[p * n + k], aqk = a[q * n + k];
+          a[p * n + k] = c * apk - s * aqk;
+          a[q * n + k] = s * apk + c * aqk;
+        }
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i) ev[i] = a[i * n + i];
+}
+
+// Solve m x = r by Gaussian elimination with partial pivoting (destroys m, r). Returns false if singular.
+__device__ inline bool lu_solve(double* m, double* r, int n) {
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    double best = fabs(m[c * n + c]);
+    for (int i = c + 1; i < n; ++i) {
+      if (fabs(m[i * n + c]) > best) {
+        best = fabs(m[i * n + c]);
+        piv = i;
+      }
+    }
+    if (!(best > 0.0)) return false;
+    if (piv != c) {
+      for (int k = 0; k < n; ++k) {
+        double t = m[c * n + k];
+        m[c * n + k] = m[piv * n + k];
+        m[piv * n + k] = t;
+      }
+      double t = r[c];
+      r[c] = r[piv];
+      r[piv] = t;
+    }
+    double inv = 1.0 / m[c * n + c];
+    for (int i = c + 1; i < n; ++i) {
+      double f = m[i * n + c] * inv;
+      for (int k = c; k < n; ++k) m[i * n + k] -= f * m[c * n + k];
+      r[i] -= f * r[c];
+    }
+  }
+  for (int c = n - 1; c >= 0; --c) {
+    double s = r[c];
+    for (int k = c + 1; k < n; ++k) s -= m[c * n + k] * r[k];
+    r[c] = s / m[c * n + c];
+  }
+  return true;
+}
+
+// ---- k_likelihood ---------------------------------------------------------------------------------------------
+// One CTA per parameter set.  `conv` holds the convolved, scaled basis images [set][slot][pixel].
+//   linear == 0: model = sum_slots conv                                   (image_model.py:162-221)
+//   linear != 0: A_k = nan_to_num(conv_k[mask]); M = A W A^T, R = A W d, W = 1/C_D(data);
+//                amplitudes = cond2(M) < 5/eps ? solve(M, R) (0 if non-finite) : 0; model = sum B_k A_k
+//                (image_linear_solve.py:97-181,361-455, de_lens.py:10-36,91-105)
+//   logL = -1/2 sum mask (model - data)^2 / C_D(model)                    (imaging_data.py:159-182)
+//          C_D(model) = noise_map^2  or  max(model,0)/t_exp + sigma_bkg^2 (image_noise.py:99-137)
+//   marg != 0: + 1/2 sign log|det M^-1|, -1e15 if singular               (de_lens.py:39-49)
+template <int NS>
+__global__ void __launch_bounds__(kBlock)
+k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linear, int marg, double* __restrict__ logl,
+             double* __restrict__ amps, double* __restrict__ model_out) {
+  constexpr int NM = NS * (NS + 1) / 2;
+  __shared__ double scratch[(NM + NS + 1) * (kBlock / 32)];
+  __shared__ double s_amp[NS];
+  __shared__ double s_marg;
+  const int64_t bl = blockIdx.x;
+  const int npix = P.nx * P.ny;
+  const int ns = P.n_slots;
+  const double* A = conv + bl * ns * (int64_t)npix;
+
+  if (linear) {
+    double acc[NM + NS];
+#pragma unroll
+    for (int i = 0; i < NM + NS; ++i) acc[i] = 0.0;
+    for (int p = threadIdx.x; p < npix; p += kBlock) {
+      if (P.mask && !P.mask[p]) continue;
+      double a[NS];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) a[k] = (k < ns) ? nan_to_num(A[(int64_t)k * npix + p]) : 0.0;
+      const double wgt = P.w_data[p], wd = wgt * P.data[p];
+      int m = 0;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+#pragma unroll
+        for (int j = i; j < NS; ++j) acc[m++] += wgt * a[i] * a[j];
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) acc[NM + i] += wd * a[i];
+    }
+    block_sum(acc, scratch);
+    if (threadIdx.x == 0) {
+      double M[NS * NS], M2[NS * NS], R[NS], ev[NS];
+      int m = 0;
+      for (int i = 0; i < NS; ++i)
+        for (int j = i; j < NS; ++j) {
+          M[i * NS + j] = acc[m];
+          M[j * NS + i] = acc[m];
+          ++m;
+        }
+      // work on the leading ns x ns block, repacked contiguously
+      for (int i = 0; i < ns; ++i)
+        for (int j = 0; j < ns; ++j) M2[i * ns + j] = M[i * NS + j];
+      for (int i = 0; i < ns; ++i) R[i] = acc[NM + i];
+      double Mw[NS * NS];
+      for (int i = 0; i < ns * ns; ++i) Mw[i] = M2[i];
+      sym_eigenvalues(Mw, ns, ev);
+      double emax = 0.0, emin = HUGE_VAL, logdet = 0.0, sign = 1.0;
+      for (int i = 0; i < ns; ++i) {
+        double e = fabs(ev[i]);
+        emax = fmax(emax, e);
+        emin = fmin(emin, e);
+        logdet += log(e);
+        if (ev[i] < 0) sign = -sign;
+        if (ev[i] == 0) sign = 0.0;
+      }
+      bool stable = (emax / emin) < 5.0 / DBL_EPSILON;  // NaN compares false, like jnp
+      bool ok = stable && lu_solve(M2, R, ns);
+      if (ok)
+        for (int i = 0; i < ns; ++i) ok = ok && (fabs(R[i]) <= DBL_MAX);
+      for (int i = 0; i < NS; ++i) s_amp[i] = (ok && i < ns) ? R[i] : 0.0;
+      // log det(M_inv) = -log det(M); M_inv = 0 (unstable) -> sign 0 -> -1e15
+      s_marg = (stable && sign != 0.0 && (logdet == logdet)) ? sign * (-logdet) / 2 : -1e15;
+    }
+    __syncthreads();
+  }
+
+  double chi[1] = {0.0};
+  for (int p = threadIdx.x; p < npix; p += kBlock) {
+    const bool use = !P.mask || P.mask[p];
+    double mdl = 0.0;
+    if (linear) {
+      if (use) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+          if (k < ns) mdl += s_amp[k] * nan_to_num(A[(int64_t)k * npix + p]);
+      }
+    } else {
+      for (int k = 0; k < ns; ++k) mdl += A[(int64_t)k * npix + p];
+    }
+    if (model_out) model_out[(set0 + bl) * npix + p] = mdl;
+    if (use) {
+      const double cd = P.noise_map2 ? P.noise_map2[p] : fmax(mdl, 0.0) * P.inv_exposure[p] + P.bkg2;
+      const double d = mdl - P.data[p];
+      chi[0] += d * d / cd;
+    }
+  }
+  block_sum(chi, scratch);
+  if (threadIdx.x == 0) {
+    double l = -chi[0] / 2;
+    if (linear && marg) l += s_marg;
+    logl[set0 + bl] = l;
+    if (amps && linear)
+      for (int k = 0; k < ns; ++k) amps[(set0 + bl) * ns + k] = s_amp[k];
+  }
+}
+
+// ---- k_fp64_peak ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_fp64_peak(int64_t iters, double* sink) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-7;
+  for (int64_t i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c);
+    a1 = fma(a1, m, c);
+    a2 = fma(a2, m, c);
+    a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c);
+    a5 = fma(a5, m, c);
+    a6 = fma(a6, m, c);
+    a7 = fma(a7, m, c);
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 1.2345) sink[0] = s;
+}
+
+}  // namespace lsim

@@ -1,0 +1,701 @@
+// lsim_profiles.cuh -- per-parameter-set constant preparation and per-point evaluation of every lens and
+// light profile on the hot path.  Host + device (see lsim_math.cuh for why).
+//
+// Split of work, B200-first: everything that depends only on the parameter set (ellipticity -> (phi, q),
+// trig of the position angle, the 2F1 series coefficients F_n(t), Sersic b_n, normalisations ...) is
+// computed ONCE per CTA into shared memory (`*_prepare`), so the per-point code (`*_eval`) is a straight
+// FMA stream with at most one log2, two exp2 and one reciprocal for the headline EPL+SHEAR+SERSIC path.
+//
+// Reference arithmetic being reproduced (clamps and sentinels included), under
+// /root/reference/jaxtronomy/:
+//   EPL            LensModel/Profiles/epl.py:93-124,178-200,297-319,366-394 + Util/hyp2f1_util.py:135-176
+//   SIE / NIE      LensModel/Profiles/sie.py:56-63,104-124, nie.py:85-107,181-200,230-246,280-294,333-342
+//   SIS            LensModel/Profiles/sis.py:35-43          SHEAR  shear.py:39-53   CONVERGENCE convergence.py:35-46
+//   NFW            LensModel/Profiles/nfw.py:88-105,259-279,347-365,386-395
+//   TNFW           LensModel/Profiles/tnfw.py:43,69-87,228-248,278-349
+//   MULTIPOLE      LensModel/Profiles/multipole.py:72-119
+//   EPL_MULTIPOLE_M1M3M4  LensModel/Profiles/epl_multipole_m1m3m4.py:463-535,608-678
+//   CSE family     LensModel/Profiles/cored_steep_ellipsoid.py:107-132,227-245,434-477,536-564,
+//                  nfw_ellipse_cse.py:250-280,338-349, hernquist_ellipse_cse.py:151-164,190-202
+//   SERSIC(_ELLIPSE)  LightModel/Profiles/sersic_ellipse.py:61-93, sersic.py:54-76,
+//                  LensModel/Profiles/sersic_utils.py:67-110,238-267, Util/param_util.py:102-123
+//   GAUSSIAN       LightModel/Profiles/gaussian.py:27-42
+//   helpers        Util/util.py:102-139 (rotate, shift_center), Util/param_util.py:6-24,87-99
+#pragma once
+
+#include "../../include/lsim.h"
+#include "lsim_cse_tables.h"
+#include "lsim_math.cuh"
+
+namespace lsim {
+
+constexpr int kMaxSeries = 512;  // >= the reference's largest nmax (500, epl.py:317)
+
+// Prepared (per parameter set) constants of one lens profile.
+struct LensC {
+  int32_t type;
+  uint32_t flags;
+  int32_t n_coef;    // EPL family: number of series coefficients actually used
+  int32_t coef_off;  // EPL family: offset of this profile's coefficients in the coefficient pool
+  double delta_T, inv_T_z, red2phys;  // multi-plane stepping
+  double c[24];
+};
+
+struct LightC {
+  int32_t type;
+  int32_t lensed;
+  int32_t slot;
+  int32_t pad;
+  double c[12];
+};
+
+// ---- CSE tables: device copies live in constant memory, host copies are the header arrays -------------
+#if defined(__CUDACC__)
+__constant__ double d_nfw_cse_high_s[LSIM_NFW_CSE_HIGH_S_N];
+__constant__ double d_nfw_cse_high_a[LSIM_NFW_CSE_HIGH_A_N];
+__constant__ double d_nfw_cse_low_s[LSIM_NFW_CSE_LOW_S_N];
+__constant__ double d_nfw_cse_low_a[LSIM_NFW_CSE_LOW_A_N];
+__constant__ double d_hernquist_cse_s[LSIM_HERNQUIST_CSE_S_N];
+__constant__ double d_hernquist_cse_a[LSIM_HERNQUIST_CSE_A_N];
+#endif
+
+LSIM_HD const double* cse_table(int which) {
+#if defined(__CUDA_ARCH__)
+  switch (which) {
+    case 0: return d_nfw_cse_high_s;
+    case 1: return d_nfw_cse_high_a;
+    case 2: return d_nfw_cse_low_s;
+    case 3: return d_nfw_cse_low_a;
+    case 4: return d_hernquist_cse_s;
+    default: return d_hernquist_cse_a;
+  }
+#else
+  switch (which) {
+    case 0: return LSIM_NFW_CSE_HIGH_S;
+    case 1: return LSIM_NFW_CSE_HIGH_A;
+    case 2: return LSIM_NFW_CSE_LOW_S;
+    case 3: return LSIM_NFW_CSE_LOW_A;
+    case 4: return LSIM_HERNQUIST_CSE_S;
+    default: return LSIM_HERNQUIST_CSE_A;
+  }
+#endif
+}
+
+// ---- parameter fetch ------------------------------------------------------------------------------------
+template <class Desc>
+LSIM_HD double param_of(const Desc& d, const double* row, int i) {
+  int c = d.col[i];
+  return c >= 0 ? row[c] : d.cst[i];
+}
+
+// Util/param_util.py:87-99
+LSIM_HD void ellipticity2phi_q(double e1, double e2, double& phi, double& q) {
+  phi = atan2(e2, e1) / 2;
+  double c = sqrt(e1 * e1 + e2 * e2);
+  c = fmin(c, 0.9999);
+  q = (1 - c) / (1 + c);
+}
+
+// nmax schedule of EPLMajorAxis._hyp2f1_evaluate (epl.py:308-319); 0 encodes "return 1" (f == 0)
+LSIM_HD int epl_nmax(double f) {
+  if (f == 0) return 0;
+  if (f < 0.12) return 10;
+  if (f < 0.4) return 20;
+  if (f < 0.6) return 35;
+  if (f < 0.73) return 50;
+  if (f < 0.86) return 100;
+  if (f < 0.92) return 200;
+  return 500;
+}
+
+// EPL family constants.  c[0..8]: cx, cy, cos(phi), sin(phi), q, f, -t/2, t*log2(b), 2/(1+q).
+// The reference evaluates 2F1(1, t/2; 2 - t/2; z) with the Lopez-Temme series truncated at nmax terms:
+//   2F1 = (1 - z/2)^-1 * sum_{n<nmax} F_n w^n,  w = z/(z-2),
+//   F_0 = 1, F_1 = 1 - 2b/c, F_n = ((n-1) F_{n-2} - (2b-c) F_{n-1}) / (c+n-1)   (hyp2f1_util.py:152-176, a = 1)
+// F_n depends on t only, so it is tabulated here once per parameter set.  |w| <= f/(2-f) =: wmax for
+// every point, so terms with |F_n| wmax^n below `series_tol` relative to the leading term cannot change
+// the truncated sum at that level and are dropped (series_tol = 0 keeps all nmax terms).
+LSIM_HD void epl_prepare(LensC& L, double* coef, double theta_E, double gamma, double e1, double e2, double cx,
+                         double cy, double series_tol) {
+  double t = gamma - 1;
+  double phi, q;
+  ellipticity2phi_q(e1, e2, phi, q);
+  double b = theta_E * sqrt(q);
+  double f = (1.0 - q) / (1.0 + q);
+  L.c[0] = cx;
+  L.c[1] = cy;
+  L.c[2] = cos(phi);
+  L.c[3] = sin(phi);
+  L.c[4] = q;
+  L.c[5] = f;
+  L.c[6] = -0.5 * t;
+  L.c[7] = t * log2(b);
+  L.c[8] = 2.0 / (1.0 + q);
+  int nmax = epl_nmax(f);
+  double B = t / 2.0, C = 2.0 - B;
+  coef[0] = 1.0;
+  int n_used = 1;
+  if (nmax > 0) {
+    double ppF = 1.0, pF = 1.0 - 2.0 * B / C;
+    coef[1] = pF;
+    n_used = 2;
+    double wmax = f / (2.0 - f);
+    double wn = wmax;  // wmax^n
+    for (int n = 2; n < nmax; ++n) {
+      double nF = ((n - 1.0) * ppF - (2.0 * B - C) * pF) / (C + n - 1.0);
+      coef[n] = nF;
+      ppF = pF;
+      pF = nF;
+      wn *= wmax;
+      if (fabs(nF) * wn > series_tol) n_used = n + 1;
+    }
+    // the bound must also hold for everything after the cut: |F_n| is non-increasing in practice, and
+    // wmax^n decays geometrically, so the last term above the tolerance closes the sum; keep one extra.
+    if (n_used < nmax) n_used += 1;
+  }
+  L.n_coef = n_used;
+}
+
+// Deflection of the EPL in the profile frame, for a point already shifted by the centre.
+// Tessore & Metcalf eq. 22/23 reorganised so that the only non-FMA work is one reciprocal, one log2 and
+// one exp2:  with Z = q x' + i y', R2 = |Z|^2, D = f Z^2 + 2 R2:
+//   w = f Z^2 conj(D)/|D|^2,  (1 - z/2)^-1 = 2 R2 conj(D)/|D|^2,  (b/R)^t = exp2(t log2 b - t/2 log2 R2)
+LSIM_HD void epl_eval(const LensC& L, const double* coef, double xs, double ys, double& ax, double& ay) {
+  const double cph = L.c[2], sph = L.c[3], q = L.c[4], f = L.c[5];
+  double xr = xs * cph + ys * sph;
+  double yr = -xs * sph + ys * cph;
+  double a = q * xr, c = yr;
+  double R2 = a * a + c * c;
+  double z2r = a * a - c * c, z2i = 2.0 * a * c;
+  double Dr = fma(f, z2r, 2.0 * R2), Di = f * z2i;
+  double inv = 1.0 / (Dr * Dr + Di * Di);
+  double cDr = Dr * inv, cDi = -Di * inv;  // conj(D)/|D|^2
+  double wr = f * (z2r * cDr - z2i * cDi);
+  double wi = f * (z2r * cDi + z2i * cDr);
+  // Horner: S = sum F_n w^n
+  int n = L.n_coef - 1;
+  double Sr = coef[n], Si = 0.0;
+  for (--n; n >= 0; --n) {
+    double tr = fma(Sr, wr, fma(-Si, wi, coef[n]));
+    Si = fma(Sr, wi, Si * wr);
+    Sr = tr;
+  }
+  // hyp = 2 R2 conj(D)/|D|^2 * S ; R_omega = Z * hyp
+  double pr = 2.0 * R2 * cDr, pi = 2.0 * R2 * cDi;
+  double hr = pr * Sr - pi * Si, hi = pr * Si + pi * Sr;
+  double or_ = a * hr - c * hi, oi = a * hi + c * hr;
+  double R2c = fmax(R2, 1e-18);  // R = max(|Z|, 1e-9)
+  double P = L.c[8] * exp2_fin(fma(L.c[6], log2_pos(R2c), L.c[7]));
+  double fr = nan_to_num(P * or_, 1e10, -1e10);
+  double fi = nan_to_num(P * oi, 1e10, -1e10);
+  ax = fr * cph - fi * sph;  // rotate(f, -phi)
+  ay = fr * sph + fi * cph;
+}
+
+// cos / sin of m*(phi - phi_m) and cos/sin(phi) from the shifted point, no trig calls:
+// u = (x + i y)/r = e^{i phi}; u^m by repeated multiplication; rotate by e^{-i m phi_m}.
+LSIM_HD void multipole_terms(double xs, double ys, int m, double cmp, double smp, double& cphi, double& sphi,
+                             double& cmd, double& smd, double& r2) {
+  r2 = xs * xs + ys * ys;
+  if (r2 > 0) {
+    double ir = 1.0 / sqrt(r2);
+    cphi = xs * ir;
+    sphi = ys * ir;
+  } else {  // atan2(0, 0) = 0
+    cphi = 1.0;
+    sphi = 0.0;
+  }
+  double ur = cphi, ui = sphi;
+  for (int k = 1; k < m; ++k) {
+    double tr = ur * cphi - ui * sphi;
+    ui = ur * sphi + ui * cphi;
+    ur = tr;
+  }
+  cmd = ur * cmp + ui * smp;
+  smd = ui * cmp - ur * smp;
+}
+
+// multipole.py:72-119.  A = a_m/(1-m^2) (m != 1) or a_m/2 (m == 1); (cmp, smp) = cos/sin(m phi_m); lnrE = ln r_E
+LSIM_HD void multipole_eval(double xs, double ys, int m, double A, double cmp, double smp, double lnrE,
+                            double& fx, double& fy) {
+  double cphi, sphi, cmd, smd, r2;
+  multipole_terms(xs, ys, m, cmp, smp, cphi, sphi, cmd, smd, r2);
+  if (m == 1) {
+    double r2c = fmax(r2, 1e-12);  // r = max(r, 1e-6)
+    double lg = 0.5 * kLn2 * log2_pos(r2c) - lnrE;
+    fx = A * (cmp * lg + cmd * cphi);
+    fy = A * (smp * lg + cmd * sphi);
+  } else {
+    fx = cphi * A * cmd + sphi * m * A * smd;
+    fy = sphi * A * cmd - cphi * m * A * smd;
+  }
+}
+
+// nfw.py:347-365
+LSIM_HD double nfw_g(double X) {
+  const double c = 0.000001;
+  if (X < c) X = c;
+  if (X < 1) return log(X / 2.0) + 1 / sqrt(1 - X * X) * acosh(1.0 / X);
+  if (X == 1) return 1 + log(1.0 / 2.0);
+  return log(X / 2) + 1 / sqrt(X * X - 1) * acos(1.0 / X);
+}
+
+// tnfw.py:290-304
+LSIM_HD double tnfw_F(double x) {
+  if (x < 1) {
+    double s = sqrt(1 - x * x);
+    return atanh(s) / s;
+  }
+  if (x > 1) {
+    double s = sqrt(x * x - 1);
+    return atan(s) / s;
+  }
+  return x;
+}
+
+// cored_steep_ellipsoid.py:227-245 summed over a table, x,y already in units of Rs; product-average variant
+// applies cored_steep_ellipsoid.py:434-443,463-477 per component.
+LSIM_HD void cse_set_eval(double x, double y, double q, const double* A, const double* S, int n, bool prod_avg,
+                          double& fx, double& fy) {
+  double sq = sqrt(q);
+  double xx = prod_avg ? x * sq : x, yy = prod_avg ? y * sq : y;
+  double q2 = q * q;
+  double sx = 0, sy = 0;
+  for (int i = 0; i < n; ++i) {
+    double s = S[i], a = prod_avg ? A[i] / q : A[i];
+    double psi = sqrt(q2 * (s * s + xx * xx) + yy * yy);
+    double Phi = (psi + s) * (psi + s) + (1 - q2) * xx * xx;
+    double den = 1.0 / (s * psi * Phi);
+    sx += a * (q * xx * (psi + q2 * s) * den);
+    sy += a * (q * yy * (psi + s) * den);
+  }
+  fx = prod_avg ? sq * sx : sx;
+  fy = prod_avg ? sq * sy : sy;
+}
+
+// ---- lens: prepare ---------------------------------------------------------------------------------------
+// `coef` points at this profile's kMaxSeries-sized slice of the coefficient pool (EPL family only).
+LSIM_HD void lens_prepare(const lsim_lens_desc& d, const double* row, LensC& L, double* coef, double series_tol) {
+  L.type = d.type;
+  L.flags = d.flags;
+  L.n_coef = 0;
+  L.delta_T = d.delta_T;
+  L.inv_T_z = d.T_z != 0 ? 1.0 / d.T_z : 0.0;
+  L.red2phys = d.red2phys;
+  auto P = [&](int i) { return param_of(d, row, i); };
+  switch (d.type) {
+    case LSIM_LENS_EPL:
+      epl_prepare(L, coef, P(0), P(1), P(2), P(3), P(4), P(5), series_tol);
+      break;
+    case LSIM_LENS_EPL_MULTIPOLE_M1M3M4: {
+      double theta_E = P(0), e1 = P(2), e2 = P(3);
+      epl_prepare(L, coef, theta_E, P(1), e1, e2, P(4), P(5), series_tol);
+      double phi, q;
+      ellipticity2phi_q(e1, e2, phi, q);
+      double rescale = theta_E / sqrt(q);
+      double a1 = P(6) * rescale, p1 = phi + P(7);
+      double a3 = P(8) * rescale, p3 = phi + P(9);
+      double a4 = P(10) * rescale, p4 = phi + P(11);
+      L.c[9] = a1 / 2;
+      L.c[10] = cos(p1);
+      L.c[11] = sin(p1);
+      L.c[12] = log(theta_E);
+      L.c[13] = a3 / (1 - 9);
+      L.c[14] = cos(3 * p3);
+      L.c[15] = sin(3 * p3);
+      L.c[16] = a4 / (1 - 16);
+      L.c[17] = cos(4 * p4);
+      L.c[18] = sin(4 * p4);
+      break;
+    }
+    case LSIM_LENS_SIE:
+    case LSIM_LENS_NIE: {
+      double theta_E = P(0), e1 = P(1), e2 = P(2), s_scale, cx, cy;
+      if (d.type == LSIM_LENS_SIE) {
+        cx = P(3);
+        cy = P(4);
+        if (d.flags & LSIM_FLAG_SIE_NIE_FALSE) {
+          L.type = LSIM_LENS_EPL;
+          epl_prepare(L, coef, theta_E, d.opt[1], e1, e2, cx, cy, series_tol);
+          break;
+        }
+        s_scale = d.opt[0];
+      } else {
+        s_scale = P(3);
+        cx = P(4);
+        cy = P(5);
+      }
+      L.type = LSIM_LENS_NIE;
+      double phi, q;
+      ellipticity2phi_q(e1, e2, phi, q);
+      double theta_conv = theta_E / sqrt((1.0 + q * q) / (2.0 * q));
+      double b = theta_conv * sqrt((1 + q * q) / 2);
+      double s = s_scale / sqrt(q);
+      if (q >= 1) q = 0.99999999;  // NIEMajorAxis.derivatives, nie.py:284
+      double rt = sqrt(1.0 - q * q);
+      L.c[0] = cx;
+      L.c[1] = cy;
+      L.c[2] = cos(phi);
+      L.c[3] = sin(phi);
+      L.c[4] = q * q;
+      L.c[5] = s;
+      L.c[6] = rt;
+      L.c[7] = b / rt;
+      L.c[8] = q * q * s;
+      break;
+    }
+    case LSIM_LENS_SIS:
+      L.c[0] = P(1);
+      L.c[1] = P(2);
+      L.c[2] = P(0);
+      break;
+    case LSIM_LENS_SHEAR:
+      L.c[0] = P(2);
+      L.c[1] = P(3);
+      L.c[2] = P(0);
+      L.c[3] = P(1);
+      break;
+    case LSIM_LENS_CONVERGENCE:
+      L.c[0] = P(1);
+      L.c[1] = P(2);
+      L.c[2] = P(0);
+      break;
+    case LSIM_LENS_NFW: {
+      double Rs = P(0), alpha_Rs = P(1);
+      double rho0 = alpha_Rs / (4.0 * Rs * Rs * (1.0 + log(1.0 / 2.0)));
+      if (Rs < 0.0000001) Rs = 0.0000001;
+      L.c[0] = P(2);
+      L.c[1] = P(3);
+      L.c[2] = Rs;
+      L.c[3] = 4 * rho0 * Rs;
+      break;
+    }
+    case LSIM_LENS_TNFW: {
+      double Rs = P(0), alpha_Rs = P(1), r_trunc = P(2);
+      double rho0 = alpha_Rs / (4.0 * Rs * Rs * (1.0 + log(1.0 / 2.0)));
+      double tau = r_trunc / Rs, t2 = tau * tau;
+      L.c[0] = P(3);
+      L.c[1] = P(4);
+      L.c[2] = Rs;
+      L.c[3] = 4 * rho0 * Rs;
+      L.c[4] = tau;
+      L.c[5] = t2;
+      L.c[6] = t2 / ((t2 + 1) * (t2 + 1));
+      L.c[7] = tau * kPi + (t2 - 1) * log(tau);
+      L.c[8] = (t2 - 1) / tau;
+      L.c[9] = 0.001 * Rs;
+      break;
+    }
+    case LSIM_LENS_MULTIPOLE: {
+      int m = (int)P(0);
+      double a_m = P(1), phi_m = P(2);
+      L.c[0] = P(3);
+      L.c[1] = P(4);
+      L.c[2] = (double)m;
+      L.c[3] = (m == 1) ? a_m / 2 : a_m / (1 - m * m);
+      L.c[4] = cos(m * phi_m);
+      L.c[5] = sin(m * phi_m);
+      L.c[6] = log(P(5));
+      break;
+    }
+    case LSIM_LENS_CSE:
+    case LSIM_LENS_NFW_ELLIPSE_CSE:
+    case LSIM_LENS_HERNQUIST_ELLIPSE_CSE: {
+      double phi, q;
+      ellipticity2phi_q(P(2), P(3), phi, q);
+      L.c[0] = P(4);
+      L.c[1] = P(5);
+      L.c[2] = cos(phi);
+      L.c[3] = sin(phi);
+      L.c[4] = q;
+      if (d.type == LSIM_LENS_CSE) {
+        L.c[5] = P(0);  // a
+        L.c[6] = P(1);  // s
+      } else if (d.type == LSIM_LENS_NFW_ELLIPSE_CSE) {
+        double Rs = P(0), alpha_Rs = P(1);
+        double rho0 = alpha_Rs / (4.0 * Rs * Rs * (1.0 + log(1.0 / 2.0)));
+        L.c[5] = Rs;
+        L.c[6] = 4 * rho0 * Rs * Rs * Rs / Rs;  // _normalization / Rs
+      } else {
+        double sigma0 = P(0), Rs = P(1);
+        double rs_ = Rs / sqrt(q);
+        L.c[5] = Rs;
+        L.c[6] = sigma0 * rs_ * rs_ / Rs;
+      }
+      break;
+    }
+    default:
+      L.type = LSIM_LENS_NULL;
+      break;
+  }
+}
+
+// ---- lens: evaluate the reduced deflection of one profile at (x, y) ----------------------------------
+template <bool FULL>
+LSIM_HD void lens_eval(const LensC& L, const double* coef_pool, double x, double y, double& fx, double& fy) {
+  const double xs = x - L.c[0], ys = y - L.c[1];
+  switch (L.type) {
+    case LSIM_LENS_EPL:
+      epl_eval(L, coef_pool + L.coef_off, xs, ys, fx, fy);
+      return;
+    case LSIM_LENS_SHEAR:
+      fx = L.c[2] * xs + L.c[3] * ys;
+      fy = L.c[3] * xs - L.c[2] * ys;
+      return;
+    case LSIM_LENS_SIS: {
+      const double eps = 0.000001;
+      double R = sqrt(xs * xs + ys * ys);
+      if (R < eps) R = eps;
+      double a = L.c[2] / R;
+      fx = a * xs;
+      fy = a * ys;
+      return;
+    }
+    case LSIM_LENS_CONVERGENCE:
+      fx = L.c[2] * xs;
+      fy = L.c[2] * ys;
+      return;
+    case LSIM_LENS_NIE: {
+      const double cph = L.c[2], sph = L.c[3];
+      double xr = xs * cph + ys * sph, yr = -xs * sph + ys * cph;
+      double s = L.c[5];
+      double psi = sqrt(L.c[4] * (s * s + xr * xr) + yr * yr);
+      double gx = L.c[7] * atan(L.c[6] * xr / (psi + s));
+      double gy = L.c[7] * atanh(L.c[6] * yr / (psi + L.c[8]));
+      fx = gx * cph - gy * sph;
+      fy = gx * sph + gy * cph;
+      return;
+    }
+    default:
+      break;
+  }
+  if (FULL) {
+    switch (L.type) {
+      case LSIM_LENS_EPL_MULTIPOLE_M1M3M4: {
+        double ex, ey, mx, my;
+        epl_eval(L, coef_pool + L.coef_off, xs, ys, ex, ey);
+        multipole_eval(xs, ys, 3, L.c[13], L.c[14], L.c[15], 0.0, mx, my);
+        ex += mx;
+        ey += my;
+        multipole_eval(xs, ys, 4, L.c[16], L.c[17], L.c[18], 0.0, mx, my);
+        ex += mx;
+        ey += my;
+        multipole_eval(xs, ys, 1, L.c[9], L.c[10], L.c[11], L.c[12], mx, my);
+        fx = ex + mx;
+        fy = ey + my;
+        return;
+      }
+      case LSIM_LENS_MULTIPOLE:
+        multipole_eval(xs, ys, (int)L.c[2], L.c[3], L.c[4], L.c[5], L.c[6], fx, fy);
+        return;
+      case LSIM_LENS_NFW: {
+        double R = sqrt(xs * xs + ys * ys);
+        R = fmax(R, 0.00000001);
+        double X = R / L.c[2];
+        double a = L.c[3] * nfw_g(X) / (X * X);
+        fx = a * xs;
+        fy = a * ys;
+        return;
+      }
+      case LSIM_LENS_TNFW: {
+        double R = sqrt(xs * xs + ys * ys);
+        R = fmax(R, L.c[9]);
+        double X = fmax(R / L.c[2], 0.001);
+        double tau = L.c[4], t2 = L.c[5];
+        double rt = sqrt(t2 + X * X);
+        double Lg = log(X / (tau + rt));
+        double g = L.c[6] * ((t2 + 1 + 2 * (X * X - 1)) * tnfw_F(X) + L.c[7] + rt * (-kPi + Lg * L.c[8]));
+        double a = L.c[3] * g / (X * X);
+        fx = a * xs;
+        fy = a * ys;
+        return;
+      }
+      case LSIM_LENS_CSE:
+      case LSIM_LENS_NFW_ELLIPSE_CSE:
+      case LSIM_LENS_HERNQUIST_ELLIPSE_CSE: {
+        const double cph = L.c[2], sph = L.c[3], q = L.c[4];
+        double xr = xs * cph + ys * sph, yr = -xs * sph + ys * cph;
+        double gx, gy;
+        if (L.type == LSIM_LENS_CSE) {
+          double a = L.c[5], s = L.c[6];
+          cse_set_eval(xr, yr, q, &a, &s, 1, !(L.flags & LSIM_FLAG_CSE_MAJOR), gx, gy);
+        } else if (L.type == LSIM_LENS_NFW_ELLIPSE_CSE) {
+          bool low = (L.flags & LSIM_FLAG_CSE_LOW_ACCURACY) != 0;
+          double iRs = 1.0 / L.c[5];
+          cse_set_eval(xr * iRs, yr * iRs, q, cse_table(low ? 3 : 1), cse_table(low ? 2 : 0),
+                       low ? LSIM_NFW_CSE_LOW_S_N : LSIM_NFW_CSE_HIGH_S_N, true, gx, gy);
+          gx *= L.c[6];
+          gy *= L.c[6];
+        } else {
+          double iRs = 1.0 / L.c[5];
+          cse_set_eval(xr * iRs, yr * iRs, q, cse_table(5), cse_table(4), LSIM_HERNQUIST_CSE_S_N, false, gx, gy);
+          gx *= L.c[6];
+          gy *= L.c[6];
+        }
+        fx = gx * cph - gy * sph;
+        fy = gx * sph + gy * cph;
+        return;
+      }
+      default:
+        break;
+    }
+  }
+  fx = 0.0;
+  fy = 0.0;
+}
+
+// true when the profile needs the FULL kernel variant
+LSIM_HD bool lens_type_is_full(int type) {
+  switch (type) {
+    case LSIM_LENS_NULL:
+    case LSIM_LENS_EPL:
+    case LSIM_LENS_SIE:
+    case LSIM_LENS_NIE:
+    case LSIM_LENS_SIS:
+    case LSIM_LENS_SHEAR:
+    case LSIM_LENS_CONVERGENCE:
+      return false;
+    default:
+      return true;
+  }
+}
+
+LSIM_HD bool lens_type_has_series(const lsim_lens_desc& d) {
+  return d.type == LSIM_LENS_EPL || d.type == LSIM_LENS_EPL_MULTIPOLE_M1M3M4 ||
+         (d.type == LSIM_LENS_SIE && (d.flags & LSIM_FLAG_SIE_NIE_FALSE));
+}
+
+// ---- rays -----------------------------------------------------------------------------------------------
+// Ray-shooting configuration shared by all kernels (single plane: beta = theta - scaling * sum alpha,
+// single_plane.py:38-56,112-139; multi plane: comoving recursion, multi_plane_base.py:159-233).
+struct RayCfg {
+  int32_t multi_plane;
+  double alpha_scaling, T_ij_end, inv_T_z_source;
+};
+
+// State of one ray while it is pushed through the deflector list.
+struct Ray {
+  double x, y;    // single plane: image position; multi plane: comoving position
+  double ax, ay;  // single plane: accumulated deflection; multi plane: current angle
+};
+
+template <bool FULL>
+LSIM_HD void ray_apply(const RayCfg& P, const LensC* L, const double* pool, int n_c, Ray& r) {
+  if (!P.multi_plane) {
+    for (int l = 0; l < n_c; ++l) {
+      double fx, fy;
+      lens_eval<FULL>(L[l], pool, r.x, r.y, fx, fy);
+      r.ax += fx;
+      r.ay += fy;
+    }
+  } else {
+    // MultiPlaneBase.ray_shooting_partial_comoving (multi_plane_base.py:195-233)
+    for (int l = 0; l < n_c; ++l) {
+      r.x += r.ax * L[l].delta_T;
+      r.y += r.ay * L[l].delta_T;
+      double fx, fy;
+      lens_eval<FULL>(L[l], pool, r.x * L[l].inv_T_z, r.y * L[l].inv_T_z, fx, fy);
+      r.ax -= fx * L[l].red2phys;
+      r.ay -= fy * L[l].red2phys;
+    }
+  }
+}
+
+LSIM_HD void ray_init(const RayCfg& P, double x, double y, Ray& r) {
+  if (!P.multi_plane) {
+    r.x = x;
+    r.y = y;
+    r.ax = 0;
+    r.ay = 0;
+  } else {
+    r.x = 0;
+    r.y = 0;
+    r.ax = x;
+    r.ay = y;
+  }
+}
+
+// -> source-plane position
+LSIM_HD void ray_finish(const RayCfg& P, const Ray& r, double& bx, double& by) {
+  if (!P.multi_plane) {
+    bx = r.x - r.ax * P.alpha_scaling;
+    by = r.y - r.ay * P.alpha_scaling;
+  } else {
+    bx = (r.x + r.ax * P.T_ij_end) * P.inv_T_z_source;
+    by = (r.y + r.ay * P.T_ij_end) * P.inv_T_z_source;
+  }
+}
+
+
+// ---- light -----------------------------------------------------------------------------------------------
+// c[0..1] centre; SERSIC family: c[2..4] = product-average transform rows / norm, c[5] = 1/(2n),
+// c[6] = -log2(Rs_)/n, c[7] = -bn log2(e), c[8] = bn log2(e), c[9] = (max_R_frac Rs_)^2, c[10] = amp
+LSIM_HD void light_prepare(const lsim_light_desc& d, const double* row, LightC& G) {
+  G.type = d.type;
+  G.lensed = d.lensed;
+  G.slot = d.slot;
+  G.pad = 0;
+  auto P = [&](int i) { return param_of(d, row, i); };
+  double amp = d.use_amp ? P(0) : 1.0;
+  switch (d.type) {
+    case LSIM_LIGHT_SERSIC:
+    case LSIM_LIGHT_SERSIC_ELLIPSE: {
+      double R_sersic = P(1), n = P(2), e1 = 0, e2 = 0, cx, cy;
+      if (d.type == LSIM_LIGHT_SERSIC_ELLIPSE) {
+        R_sersic = fmax(0.0, R_sersic);  // sersic_ellipse.py:90
+        e1 = P(3);
+        e2 = P(4);
+        cx = P(5);
+        cy = P(6);
+      } else {
+        cx = P(3);
+        cy = P(4);
+      }
+      double norm = fmax(sqrt(fabs(1 - e1 * e1 - e2 * e2)), 0.000001);
+      double Rs_ = fmax(0.0001, R_sersic);
+      double bn = fmax(1.9992 * n - 0.3271, 0.00001);
+      G.c[0] = cx;
+      G.c[1] = cy;
+      G.c[2] = (1 - e1) / norm;
+      G.c[3] = -e2 / norm;
+      G.c[4] = (1 + e1) / norm;
+      G.c[5] = 0.5 / n;
+      G.c[6] = -log2(Rs_) / n;
+      G.c[7] = -bn * kLog2e;
+      G.c[8] = bn * kLog2e;
+      G.c[9] = (1000.0 * Rs_) * (1000.0 * Rs_);
+      G.c[10] = amp;
+      G.type = LSIM_LIGHT_SERSIC_ELLIPSE;
+      break;
+    }
+    case LSIM_LIGHT_GAUSSIAN: {
+      double sigma = P(1);
+      G.c[0] = P(2);
+      G.c[1] = P(3);
+      G.c[2] = -0.5 * kLog2e / (sigma * sigma);
+      G.c[3] = amp / (2 * kPi * sigma * sigma);
+      break;
+    }
+    default:
+      G.slot = -1;
+      break;
+  }
+}
+
+LSIM_HD double light_eval(const LightC& G, double x, double y) {
+  const double xs = x - G.c[0], ys = y - G.c[1];
+  if (G.type == LSIM_LIGHT_SERSIC_ELLIPSE) {
+    double xt = G.c[2] * xs + G.c[3] * ys;
+    double yt = G.c[3] * xs + G.c[4] * ys;
+    double R2 = xt * xt + yt * yt;
+    double R2c = fmax(R2, 1e-8);  // R_ = max(1e-4, R)
+    double k = exp2_fin(fma(G.c[5], log2_pos(R2c), G.c[6]));
+    double v = exp2_fin(fma(G.c[7], k, G.c[8]));
+    v = (R2c <= G.c[9]) ? v : 0.0;
+    return G.c[10] * nan_to_num(v);
+  }
+  // GAUSSIAN
+  return G.c[3] * exp2_fin(G.c[2] * (xs * xs + ys * ys));
+}
+
+}  // namespace lsim

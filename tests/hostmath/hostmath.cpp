@@ -1,0 +1,64 @@
+// tests/hostmath -- TEST HARNESS ONLY.  Compiles the product's host+device profile arithmetic
+// (jaxtronomy_b200/csrc/lsim_profiles.cuh) with g++ so that the exact per-point code the CUDA kernels run
+// can be checked against the oracle on a machine without a GPU.  Not linked into, or loaded by, the product.
+#include <vector>
+
+#include "../../jaxtronomy_b200/csrc/lsim_profiles.cuh"
+
+using namespace lsim;
+
+extern "C" {
+
+int hm_ray_shoot(const lsim_lens_desc* lens, int n_lens, int multi_plane, double alpha_scaling, double T_ij_end,
+                 double T_z_source, const double* row, const double* x, const double* y, int64_t N, double* ox,
+                 double* oy, int what, double series_tol) {
+  std::vector<LensC> L(n_lens);
+  std::vector<double> pool((size_t)(n_lens + 1) * kMaxSeries);
+  int off = 0;
+  for (int i = 0; i < n_lens; ++i) {
+    L[i].coef_off = off * kMaxSeries;
+    lens_prepare(lens[i], row, L[i], pool.data() + (size_t)off * kMaxSeries, series_tol);
+    if (lens_type_has_series(lens[i])) ++off;
+  }
+  RayCfg cfg{multi_plane, multi_plane ? 1.0 : alpha_scaling, T_ij_end, multi_plane ? 1.0 / T_z_source : 0.0};
+  for (int64_t i = 0; i < N; ++i) {
+    Ray r;
+    ray_init(cfg, x[i], y[i], r);
+    ray_apply<true>(cfg, L.data(), pool.data(), n_lens, r);
+    if (what == 1 && !multi_plane) {
+      ox[i] = r.ax * cfg.alpha_scaling;
+      oy[i] = r.ay * cfg.alpha_scaling;
+    } else {
+      ray_finish(cfg, r, ox[i], oy[i]);
+    }
+  }
+  return 0;
+}
+
+int hm_surface_brightness(const lsim_light_desc* light, int n_light, int n_slots, const double* row, const double* x,
+                          const double* y, int64_t N, double* out) {
+  std::vector<LightC> G(n_light);
+  for (int i = 0; i < n_light; ++i) light_prepare(light[i], row, G[i]);
+  for (int s = 0; s < n_slots; ++s)
+    for (int64_t i = 0; i < N; ++i) {
+      double acc = 0;
+      for (int g = 0; g < n_light; ++g)
+        if (G[g].slot == s) acc += light_eval(G[g], x[i], y[i]);
+      out[(size_t)s * N + i] = acc;
+    }
+  return 0;
+}
+
+void hm_log2(const double* x, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = log2_pos(x[i]);
+}
+void hm_exp2(const double* x, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = exp2_fin(x[i]);
+}
+int hm_epl_terms(const lsim_lens_desc* lens, const double* row, double series_tol) {
+  LensC L;
+  std::vector<double> pool(kMaxSeries);
+  lens_prepare(*lens, row, L, pool.data(), series_tol);
+  return L.n_coef;
+}
+}

@@ -1,0 +1,103 @@
+"""Build + bind tests/hostmath (the product's host+device profile arithmetic compiled with g++).  Test-only."""
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from jaxtronomy_b200 import _lib, _model
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostmath", "hostmath.cpp")
+SO = os.path.join(HERE, "hostmath", "libhostmath.so")
+_DEPS = [SRC] + [os.path.join(HERE, "..", "jaxtronomy_b200", "csrc", f)
+                 for f in ("lsim_profiles.cuh", "lsim_math.cuh", "lsim_cse_tables.h")] + \
+    [os.path.join(HERE, "..", "include", "lsim.h")]
+
+_dp = C.POINTER(C.c_double)
+_h = None
+
+
+def build():
+    if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in _DEPS):
+        return SO
+    # -ffp-contract=off: explicit fma() calls stay, nothing else is contracted -- the device build
+    # contracts more (nvcc -fmad=true), which is exactly the kind of 1-ulp freedom the parity bar allows
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", SO, SRC])
+    return SO
+
+
+def lib():
+    global _h
+    if _h is None:
+        h = C.CDLL(build())
+        h.hm_ray_shoot.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp,
+                                   _dp, _dp, C.c_int64, _dp, _dp, C.c_int, C.c_double]
+        h.hm_surface_brightness.argtypes = [C.POINTER(_lib.LightDesc), C.c_int, C.c_int, _dp, _dp, _dp, C.c_int64, _dp]
+        h.hm_log2.argtypes = [_dp, C.c_int64, _dp]
+        h.hm_exp2.argtypes = [_dp, C.c_int64, _dp]
+        h.hm_epl_terms.argtypes = [C.POINTER(_lib.LensDesc), _dp, C.c_double]
+        _h = h
+    return _h
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def ray_shoot(lens_model_list, kwargs_list, x, y, what=0, profile_kwargs_list=None, multi_plane=None,
+              alpha_scaling=1.0, series_tol=1e-14):
+    """All parameters go through a one-row parameter matrix (columns), like the façade does."""
+    names = [_model.LENS_PARAM_NAMES[n] for n in lens_model_list]
+    values = _model.gather_values(names, kwargs_list)
+    row = np.asarray(values, dtype=np.float64)
+    layout = _model.ColumnLayout()
+    descs = []
+    for i, n in enumerate(lens_model_list):
+        src = layout.add_profile("lens", i, names[i])
+        extra = {}
+        if multi_plane is not None:
+            extra = dict(delta_T=multi_plane["delta_T"][i], T_z=multi_plane["T_z"][i], red2phys=multi_plane["red2phys"][i])
+        descs.append(_model.lens_desc(n, src, (profile_kwargs_list or [{}] * len(names))[i], **extra))
+    arr = (_lib.LensDesc * max(1, len(descs)))(*descs)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    ox, oy = np.empty_like(x), np.empty_like(y)
+    mp = multi_plane is not None
+    lib().hm_ray_shoot(arr, len(descs), int(mp), alpha_scaling, multi_plane["T_ij_end"] if mp else 0.0,
+                       multi_plane["T_z_source"] if mp else 0.0, _p(row), _p(x), _p(y), x.size, _p(ox), _p(oy), what,
+                       series_tol)
+    return ox, oy
+
+
+def surface_brightness(light_model_list, kwargs_list, x, y, split=False):
+    names = [_model.LIGHT_PARAM_NAMES[n] for n in light_model_list]
+    values = _model.gather_values(names, kwargs_list, "light")
+    row = np.asarray(values, dtype=np.float64)
+    layout = _model.ColumnLayout()
+    descs = []
+    for i, n in enumerate(light_model_list):
+        src = layout.add_profile("light", i, names[i])
+        descs.append(_model.light_desc(n, src, lensed=False, slot=i if split else 0, use_amp=not split))
+    n_slots = len(descs) if split else 1
+    arr = (_lib.LightDesc * max(1, len(descs)))(*descs)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.empty((n_slots, x.size))
+    lib().hm_surface_brightness(arr, len(descs), n_slots, _p(row), _p(x), _p(y), x.size, _p(out))
+    return out
+
+
+def log2(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    lib().hm_log2(_p(x), x.size, _p(out))
+    return out
+
+
+def exp2(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    lib().hm_exp2(_p(x), x.size, _p(out))
+    return out

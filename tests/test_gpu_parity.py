@@ -1,0 +1,385 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> liblsim.so), against
+  (a) the committed golden fixtures produced by the unmodified reference source, and
+  (b) the NumPy oracle on seeded inputs (batched and at the headline size).
+Bar (north star): |a - b| <= 1e-10 |b| + 1e-12 max|b|  (fp64; SURVEY.md fact 10 for the atol companion);
+index / grid bookkeeping bit-exact.
+"""
+
+import numpy as np
+import pytest
+
+from tests.golden_io import assert_close, load
+
+pytestmark = pytest.mark.gpu
+
+PROFILES = load("profiles.npz")
+LENS_MODELS = load("lens_models.npz")
+IMSIM = load("imsim.npz")
+BAR = dict(rtol=1e-10, atol_frac=1e-12)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_loaded():
+    """Fail loudly if the CUDA extension is missing: there is no fallback to fall back to."""
+    from jaxtronomy_b200 import _lib
+
+    lib = _lib.load()
+    import torch
+
+    assert torch.cuda.is_available()
+    before = _lib.launch_count()
+    yield
+    assert _lib.launch_count() > before, "GPU tests ran without launching a single lsim kernel"
+
+
+def _lens_models():
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+
+    return LensModel
+
+
+def _conditioning_rtol(prof, kw, x, y):
+    from tests.test_hostmath import conditioning_rtol
+
+    return conditioning_rtol(prof, kw, x, y)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# profiles
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", [n for n, c in PROFILES.items() if "f_x" in c.out and "profile" in c.meta])
+def test_lens_profile_deflection(name):
+    from jaxtronomy_b200 import _model
+
+    c = PROFILES[name]
+    prof = c.meta["profile"]
+    kw = c.scalar_kwargs(_model.LENS_PARAM_NAMES[prof])
+    lm = _lens_models()([prof], profile_kwargs_list=[c.meta["profile_kwargs"]])
+    fx, fy = lm.alpha(c.inp["x"], c.inp["y"], [kw])
+    scale = max(np.max(np.abs(c.out["f_x"])), np.max(np.abs(c.out["f_y"])))
+    rtol = _conditioning_rtol(prof, kw, c.inp["x"], c.inp["y"])
+    for got, want, lab in ((fx, c.out["f_x"], "f_x"), (fy, c.out["f_y"], "f_y")):
+        err = np.abs(got - want)
+        tol = rtol * np.abs(want) + 1e-12 * scale
+        i = int(np.argmax(err - tol))
+        assert np.all(err <= tol), "%s %s: |diff| %.3g > tol %.3g at %d (want %.17g got %.17g)" % (
+            name, lab, err[i], tol[i], i, want[i], got[i])
+    # ray_shooting = theta - alpha
+    bx, by = lm.ray_shooting(c.inp["x"], c.inp["y"], [kw])
+    np.testing.assert_allclose(bx, c.inp["x"] - fx, rtol=0, atol=1e-15 * max(1.0, scale))
+
+
+def test_epl_major_axis_reference_sweep():
+    """test_epl.py:199-206: q in [0.03, 1] x y in [-10, 10], through EPL with phi = 0 (e2 = 0, e1 = (1-q)/(1+q))."""
+    c = PROFILES["epl_major_sweep"]
+    lm = _lens_models()(["EPL"])
+    b, t = float(c.inp["b"]), float(c.inp["t"])
+    for i, q in enumerate(c.inp["q"]):
+        q = max(float(q), (1 - 0.9999) / (1 + 0.9999))
+        e1 = (1 - q) / (1 + q)
+        kw = dict(theta_E=b / np.sqrt(q), gamma=t + 1, e1=e1, e2=0.0, center_x=0.0, center_y=0.0)
+        fx, fy = lm.alpha(c.inp["x"], c.inp["y"], [kw])
+        if float(c.inp["q"][i]) < q:
+            continue  # below the ellipticity clamp of param_util.ellipticity2phi_q the profile frame differs
+        scale = max(np.max(np.abs(c.out["f_x"][i])), np.max(np.abs(c.out["f_y"][i])))
+        assert np.max(np.abs(fx - c.out["f_x"][i])) <= 1e-10 * scale, (q, np.max(np.abs(fx - c.out["f_x"][i])))
+        assert np.max(np.abs(fy - c.out["f_y"][i])) <= 1e-10 * scale, q
+
+
+@pytest.mark.parametrize("name", [n for n, c in PROFILES.items() if "flux" in c.out])
+def test_light_profile(name):
+    from jaxtronomy_b200 import _model
+    from jaxtronomy_b200.LightModel.light_model import LightModel
+
+    c = PROFILES[name]
+    prof = c.meta["profile"]
+    kw = c.scalar_kwargs(_model.LIGHT_PARAM_NAMES[prof])
+    lm = LightModel([prof])
+    assert_close(lm.surface_brightness(c.inp["x"], c.inp["y"], [kw]), c.out["flux"], what=name, **BAR)
+    resp, n = lm.functions_split(c.inp["x"], c.inp["y"], [kw])
+    assert n == 1
+    assert_close(resp[0] * kw["amp"], c.out["flux"], what=name + " split", **BAR)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# lens models
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", [n for n in LENS_MODELS if n.startswith("single_plane")])
+def test_single_plane_ray_shooting(name):
+    c = LENS_MODELS[name]
+    k = c.meta["k"]
+    if isinstance(k, list) and not isinstance(k[0], bool):
+        k = tuple(k)
+    lm = _lens_models()(c.meta["lens_model_list"])
+    bx, by = lm.ray_shooting(c.inp["x"], c.inp["y"], c.meta["kwargs"], k=k)
+    assert_close(bx, c.out["beta_x"], what=name, **BAR)
+    assert_close(by, c.out["beta_y"], what=name, **BAR)
+
+
+def test_batched_kwargs_and_torch_io():
+    """[B] arrays in kwargs = vmap over parameter sets; 2-d coordinate arrays keep their shape; torch in -> torch out."""
+    import torch
+
+    from oracle import lens_model as olm
+
+    rng = np.random.default_rng(5)
+    x, y = rng.uniform(-2, 2, (7, 9)), rng.uniform(-2, 2, (7, 9))
+    B = 5
+    th, g1 = rng.uniform(0.8, 1.5, B), rng.uniform(-0.05, 0.05, B)
+    kw = [dict(theta_E=th, gamma=2.0, e1=0.1, e2=-0.2, center_x=0.0, center_y=0.05),
+          dict(gamma1=g1, gamma2=0.02, ra_0=0.0, dec_0=0.0)]
+    lm = _lens_models()(["EPL", "SHEAR"])
+    bx, by = lm.ray_shooting(x, y, kw)
+    assert bx.shape == (B, 7, 9)
+    for b in range(B):
+        kwb = [dict(kw[0], theta_E=th[b]), dict(kw[1], gamma1=g1[b])]
+        ox, oy = olm.ray_shooting(["EPL", "SHEAR"], x, y, kwb)
+        assert_close(bx[b], ox, what="batched %d" % b, **BAR)
+        assert_close(by[b], oy, what="batched %d" % b, **BAR)
+    tx, ty = lm.ray_shooting(torch.as_tensor(x, device="cuda"), torch.as_tensor(y, device="cuda"), kw)
+    assert isinstance(tx, torch.Tensor) and tx.is_cuda and tx.shape == (B, 7, 9)
+    np.testing.assert_array_equal(tx.cpu().numpy(), bx)
+    # empty input
+    ex, ey = lm.ray_shooting(np.zeros(0), np.zeros(0), kw)
+    assert ex.shape == (B, 0)
+
+
+def test_bulk_single_plane():
+    from jaxtronomy_b200.LensModel.lens_model_bulk import LensModelBulk
+
+    c = LENS_MODELS["bulk_single_plane"]
+    lmb = LensModelBulk(c.meta["unique_lens_model_list"], multi_plane=False)
+    rs = lmb.prepare_ray_shooting_kwargs(c.meta["lens_model_list"], c.meta["kwargs"],
+                                         num_deflectors=c.meta["num_deflectors"])
+    np.testing.assert_array_equal(rs["index_list"], c.inp["index_list"])
+    for k, v in rs["all_kwargs"].items():
+        np.testing.assert_array_equal(v, c.inp["kw_" + k])
+    bx, by = lmb.ray_shooting(c.inp["x"], c.inp["y"], rs)
+    assert_close(bx, c.out["beta_x"], what="bulk", **BAR)
+    assert_close(by, c.out["beta_y"], what="bulk", **BAR)
+
+
+def test_bulk_many_deflectors_streams_in_chunks():
+    """> kLensChunk deflectors: 1 EPL + 300 TNFW against the oracle (substructure-notebook shape)."""
+    from jaxtronomy_b200.LensModel.lens_model_bulk import LensModelBulk
+    from oracle import lens_model as olm
+
+    rng = np.random.default_rng(8)
+    nh = 300
+    names = ["EPL"] + ["TNFW"] * nh
+    kws = [dict(theta_E=1.0, gamma=2.0, e1=0.1, e2=0.1, center_x=0.0, center_y=0.0)]
+    kws += [dict(Rs=float(rng.uniform(0.01, 0.1)), alpha_Rs=float(rng.uniform(1e-4, 5e-3)),
+                 r_trunc=float(rng.uniform(0.05, 0.5)), center_x=float(rng.uniform(-2, 2)),
+                 center_y=float(rng.uniform(-2, 2))) for _ in range(nh)]
+    x, y = rng.uniform(-2, 2, 2000), rng.uniform(-2, 2, 2000)
+    lmb = LensModelBulk(["EPL", "TNFW"], multi_plane=False)
+    bx, by = lmb.ray_shooting(x, y, lmb.prepare_ray_shooting_kwargs(names, kws, num_deflectors=320))
+    ox, oy = olm.ray_shooting(names, x, y, kws)
+    assert_close(bx, ox, what="bulk 300", rtol=1e-10, atol_frac=1e-11)
+    assert_close(by, oy, what="bulk 300", rtol=1e-10, atol_frac=1e-11)
+
+
+def test_multi_plane():
+    c = LENS_MODELS["multi_plane"]
+    lm = _lens_models()(c.meta["lens_model_list"], z_source=c.meta["z_source"],
+                        lens_redshift_list=c.meta["lens_redshift_list"], multi_plane=True)
+    # same cosmological constants as the fixture (the reference takes them from astropy)
+    assert lm._sorted_redshift_index == [int(i) for i in c.inp["sorted_index"]]
+    lm.set_multi_plane_constants(c.inp["T_ij_list"], c.inp["T_z_list"], c.inp["reduced2physical"],
+                                 float(c.inp["T_ij_stop"]), float(c.inp["T_z_source"]))
+    bx, by = lm.ray_shooting(c.inp["x"], c.inp["y"], c.meta["kwargs"])
+    assert_close(bx, c.out["beta_x"], what="multi-plane", **BAR)
+    assert_close(by, c.out["beta_y"], what="multi-plane", **BAR)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# numerics: re-bin + convolution
+# ---------------------------------------------------------------------------------------------------------------
+def _psf(meta_psf, inp):
+    from jaxtronomy_b200.Data.psf import PSF
+
+    kw = dict(meta_psf)
+    if kw["psf_type"] == "PIXEL":
+        kw["kernel_point_source"] = inp["kernel"]
+    return PSF(**kw)
+
+
+@pytest.mark.parametrize("name", [n for n in IMSIM if n.startswith("numerics_")])
+def test_numerics_re_size_convolve(name):
+    from jaxtronomy_b200.Data.pixel_grid import PixelGrid
+    from jaxtronomy_b200.ImSim.Numerics.numerics import Numerics
+
+    c = IMSIM[name]
+    pg = PixelGrid(c.meta["nx"], c.meta["ny"], c.inp["transform_pix2angle"], float(c.inp["ra_at_xy_0"]),
+                   float(c.inp["dec_at_xy_0"]))
+    psf = _psf(c.meta["kwargs_psf"], c.inp)
+    psf.set_pixel_size(pg.pixel_width)
+    num = Numerics(pg, psf, **c.meta["kwargs_numerics"])
+    assert_close(num.re_size_convolve(c.inp["flux"]), c.out["image"], what=name, **BAR)
+    assert_close(num.re_size_convolve(c.inp["flux"], unconvolved=True), c.out["image_unconvolved"], what=name, **BAR)
+    # batched flux: leading axes are kept
+    stack = np.stack([c.inp["flux"], 2 * c.inp["flux"]])
+    out = num.re_size_convolve(stack)
+    assert out.shape == (2,) + c.out["image"].shape
+    assert_close(out[1], 2 * c.out["image"], what=name + " batched", **BAR)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ImageModel / ImageLinearFit against the reference fixtures
+# ---------------------------------------------------------------------------------------------------------------
+def build_image_model(c, linear=True):
+    from jaxtronomy_b200.Data.imaging_data import ImageData
+    from jaxtronomy_b200.ImSim.image_linear_solve import ImageLinearFit
+    from jaxtronomy_b200.ImSim.image_model import ImageModel
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+    from jaxtronomy_b200.LightModel.light_model import LightModel
+
+    kd = dict(image_data=c.inp["image_data"], transform_pix2angle=c.inp["transform_pix2angle"],
+              ra_at_xy_0=float(c.inp["ra_at_xy_0"]), dec_at_xy_0=float(c.inp["dec_at_xy_0"]),
+              background_rms=float(c.inp["background_rms"]),
+              exposure_time=c.inp["exposure_time"] if c.inp["exposure_time"].ndim else float(c.inp["exposure_time"]))
+    if "noise_map" in c.inp:
+        kd["noise_map"] = c.inp["noise_map"]
+    cls = ImageLinearFit if linear else ImageModel
+    return cls(ImageData(**kd), _psf(c.meta["kwargs_psf"], c.inp),
+               LensModel(c.meta["lens_model_list"], profile_kwargs_list=c.meta.get("lens_profile_kwargs")),
+               LightModel(c.meta["source_model_list"]), LightModel(c.meta["lens_light_model_list"]),
+               kwargs_numerics=c.meta["kwargs_numerics"], likelihood_mask=c.inp.get("likelihood_mask"))
+
+
+IMAGE_CASES = [n for n, c in IMSIM.items() if "logL_linear" in c.out]
+
+
+@pytest.mark.parametrize("name", IMAGE_CASES)
+def test_image_model(name):
+    c = IMSIM[name]
+    im = build_image_model(c, linear=False)
+    kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
+    assert_close(im.image(kl, ks, kll), c.out["image"], what=name + " image", **BAR)
+    assert_close(im.image(kl, ks, kll, unconvolved=True), c.out["image_unconvolved"], what=name + " unconvolved", **BAR)
+    assert_close(im.source_surface_brightness(ks, kl), c.out["source"], what=name + " source", **BAR)
+    assert_close(im.image(kl, ks, kll, lens_light_add=False), c.out["source"], what=name + " source_add only", **BAR)
+    if kll:
+        assert_close(im.lens_surface_brightness(kll), c.out["lens_light"], what=name + " lens light", **BAR)
+    logL = im.likelihood_data_given_model(kl, ks, kll)
+    assert abs(logL - float(c.out["logL"])) <= 1e-10 * abs(float(c.out["logL"])), (logL, float(c.out["logL"]))
+
+
+@pytest.mark.parametrize("name", IMAGE_CASES)
+def test_image_linear_fit(name):
+    c = IMSIM[name]
+    lin = build_image_model(c, linear=True)
+    kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
+    A = lin.linear_response_matrix(kl, ks, kll)
+    assert A.shape == c.out["A"].shape
+    assert_close(A, c.out["A"], what=name + " response matrix", **BAR)
+    model, model_error, cov, param = lin.image_linear_solve(kl, ks, kll)
+    # amplitudes inherit the conditioning of the normal equations: the reference's own tests use 2e-9 on param
+    cond = np.linalg.cond((c.out["A"] / 1.0) @ c.out["A"].T) if c.out["A"].shape[0] > 1 else 1.0
+    ptol = max(1e-10, 10 * 2.2e-16 * cond)
+    if np.all(c.out["param"] == 0):
+        assert np.all(param == 0)  # cond gate of de_lens.py:26-33
+    else:
+        assert_close(param, c.out["param"], what=name + " param", rtol=ptol, atol_frac=ptol)
+    assert_close(model, c.out["wls_model"], what=name + " wls model", rtol=max(1e-10, ptol), atol_frac=max(1e-12, ptol))
+    assert cov is None and np.all(model_error == 0)
+    logL, param2 = lin.likelihood_data_given_model(kl, ks, kll)
+    want = float(c.out["logL_linear"])
+    assert abs(logL - want) <= max(1e-10, ptol) * abs(want), (logL, want)
+    np.testing.assert_array_equal(param2, param)
+    logLm, _ = lin.likelihood_data_given_model(kl, ks, kll, source_marg=True)
+    wantm = float(c.out["logL_marg"])
+    assert abs(logLm - wantm) <= max(1e-10, ptol) * abs(wantm), (logLm, wantm)
+    # covariance on request
+    _, _, cov, _ = lin.image_linear_solve(kl, ks, kll, inv_bool=True)
+    assert cov.shape == (len(param), len(param))
+
+
+def test_batched_likelihood_matches_oracle_per_set():
+    """A [B, P] parameter matrix through the batch entry points vs the oracle, one set at a time."""
+    import torch
+
+    from tests.test_oracle_golden import build_oracle_image_model
+
+    c = IMSIM["headline_epl_shear_pixel"]
+    lin = build_image_model(c, linear=True)
+    om = build_oracle_image_model(c)
+    kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
+    names = lin.param_names
+    base = np.array([({"lens": kl, "source": ks, "lens_light": kll}[comp][i])[n] for comp, i, n in names], dtype=float)
+    rng = np.random.default_rng(2)
+    B = 33
+    mat = np.tile(base, (B, 1))
+    free = [j for j, (comp, i, n) in enumerate(names) if n in ("theta_E", "gamma", "e1", "e2", "gamma1", "R_sersic")]
+    mat[:, free] += rng.normal(0, 0.03, (B, len(free)))
+    logl, amps, model = lin.logL_linear_batch(torch.as_tensor(mat, device="cuda"), return_model=True)
+    logl_j = lin.logL_batch(torch.as_tensor(mat, device="cuda"))
+    logl, amps, model, logl_j = logl.cpu().numpy(), amps.cpu().numpy(), model.cpu().numpy(), logl_j.cpu().numpy()
+    for b in (0, 7, 32):
+        row = mat[b]
+        kws = {"lens": [dict() for _ in kl], "source": [dict() for _ in ks], "lens_light": [dict() for _ in kll]}
+        for j, (comp, i, n) in enumerate(names):
+            kws[comp][i][n] = row[j]
+        ol, op = om.likelihood_data_given_model_linear(kws["lens"], kws["source"], kws["lens_light"])
+        assert abs(logl[b] - ol) <= 1e-9 * abs(ol), (b, logl[b], ol)
+        np.testing.assert_allclose(amps[b], op, rtol=1e-8)
+        oj = om.likelihood_data_given_model(kws["lens"], kws["source"], kws["lens_light"])
+        assert abs(logl_j[b] - oj) <= 1e-10 * abs(oj), (b, logl_j[b], oj)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# headline size: 180 x 180, ss 3, 21 x 21 PSF -- oracle spot checks + size-independent properties
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def headline():
+    from bench import build_headline
+
+    return build_headline(n_sets=296, seed=77)
+
+
+def test_headline_matches_oracle(headline):
+    from bench import oracle_headline_logl
+
+    logl, amps, _ = headline["model"].logL_linear_batch(headline["params"])
+    logl, amps = logl.cpu().numpy(), amps.cpu().numpy()
+    assert np.all(np.isfinite(logl))
+    for b in (0, 295):
+        ol, op = oracle_headline_logl(headline, b)
+        assert abs(logl[b] - ol) <= 1e-10 * abs(ol), (b, logl[b], ol)
+        np.testing.assert_allclose(amps[b], op, rtol=1e-10)
+
+
+def test_headline_properties(headline):
+    import torch
+
+    model, params = headline["model"], headline["params"]
+    sub = params[:24].clone()
+    img1 = model.image_batch(sub)
+    # linearity in the amplitude (column 10 = source amp)
+    sub2 = sub.clone()
+    sub2[:, 10] *= 3.0
+    img3 = model.image_batch(sub2)
+    assert torch.allclose(img3, 3.0 * img1, rtol=1e-13, atol=0)
+    # basis image (amp = 1) x solved amplitude = WLS model returned by the likelihood kernel
+    logl, amps, wls = model.logL_linear_batch(sub, return_model=True)
+    basis = model.response_batch(sub)[:, 0]
+    assert torch.allclose(wls, amps[:, :1, None] * basis, rtol=1e-12, atol=1e-300)
+    # batch order / chunking independence: one big call == concatenation of small calls
+    l_a, _, _ = model.logL_linear_batch(params[:200])
+    l_b, _, _ = model.logL_linear_batch(params[200:])
+    l_all, _, _ = model.logL_linear_batch(params)
+    assert torch.equal(torch.cat([l_a, l_b]), l_all)
+    # convolution with a normalised PSF conserves flux up to what leaks over the frame edge
+    unconv = model._split_plan(True).image(sub)[:, 0]
+    assert torch.all(basis.sum(dim=(1, 2)) <= unconv.sum(dim=(1, 2)) * (1 + 1e-12))
+    assert torch.all(basis.sum(dim=(1, 2)) >= unconv.sum(dim=(1, 2)) * 0.9)
+    # determinism
+    l_again, _, _ = model.logL_linear_batch(params)
+    assert torch.equal(l_again, l_all)
+
+
+def test_fp64_peak_microbenchmark_runs():
+    from jaxtronomy_b200 import _lib
+
+    flops = _lib.measure_fp64_peak(20000)
+    assert 1e12 < flops < 1e14

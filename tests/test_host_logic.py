@@ -1,0 +1,182 @@
+"""CPU: host-side logic of the product (grid bookkeeping, kwargs packing, selection lists, sharding)."""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from jaxtronomy_b200 import _model, parallel
+from jaxtronomy_b200.Data.imaging_data import ImageData
+from jaxtronomy_b200.Data.psf import PSF
+from jaxtronomy_b200.ImSim.Numerics.grid import RegularGrid
+from jaxtronomy_b200.ImSim.Numerics.numerics import Numerics, gaussian_pixel_kernel
+from jaxtronomy_b200.Util import kernel_util, simulation_util, util
+from tests.golden_io import load
+
+IMSIM = load("imsim.npz")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("ss", [1, 2, 3])
+def test_regular_grid_bit_exact(ss):
+    """coordinates and index maps are array_equal to the reference's (test_grid.py)."""
+    c = IMSIM["grid_ss%d" % ss]
+    g = RegularGrid(6, 6, c.inp["transform_pix2angle"], float(c.inp["ra_at_xy_0"]), float(c.inp["dec_at_xy_0"]), ss)
+    ra, dec = g.coordinates_evaluate
+    np.testing.assert_array_equal(g._compute_indexes, c.out["compute_indexes"])
+    np.testing.assert_array_equal(ra, c.out["ra"])
+    np.testing.assert_array_equal(dec, c.out["dec"])
+    assert g.num_grid_points_axes == (6 * ss, 6 * ss)
+
+
+def test_regular_grid_mask_scatter():
+    mask = np.zeros((4, 4))
+    mask[1:3, 2] = 1
+    g = RegularGrid(4, 4, np.eye(2) * 0.1, 0.0, 0.0, 2, flux_evaluate_indexes=mask)
+    assert g._compute_indexes.sum() == 2 * 4
+    flux = np.arange(8.0)
+    full = g.flux_to_full_grid(flux)
+    assert full.shape == (64,)
+    np.testing.assert_array_equal(full[g._compute_indexes], flux)
+    assert full.sum() == flux.sum()
+
+
+@pytest.mark.parametrize("name", [n for n in IMSIM if n.startswith("numerics_")])
+def test_numerics_coordinates_and_kernel(name):
+    c = IMSIM[name]
+    from jaxtronomy_b200.Data.pixel_grid import PixelGrid
+
+    pg = PixelGrid(c.meta["nx"], c.meta["ny"], c.inp["transform_pix2angle"], float(c.inp["ra_at_xy_0"]),
+                   float(c.inp["dec_at_xy_0"]))
+    kw = dict(c.meta["kwargs_psf"])
+    if kw["psf_type"] == "PIXEL":
+        kw["kernel_point_source"] = c.inp["kernel"]
+    psf = PSF(**kw)
+    psf.set_pixel_size(pg.pixel_width)
+    num = Numerics(pg, psf, **c.meta["kwargs_numerics"])
+    ra, dec = num.coordinates_evaluate
+    np.testing.assert_array_equal(ra, c.out["ra"])
+    np.testing.assert_array_equal(dec, c.out["dec"])
+    if kw["psf_type"] == "GAUSSIAN":
+        k2, k1 = num._kernel, num._kernel_1d
+        assert k2.shape[0] % 2 == 1 and abs(k2.sum() - 1) < 1e-14
+        # the separable factorisation the kernels use reproduces the reference's 2-d kernel to rounding
+        assert np.max(np.abs(np.outer(k1, k1) - k2)) < 1e-16
+
+
+def test_gaussian_kernel_matches_reference_definition():
+    k = gaussian_pixel_kernel(1.7, 9)
+    x, y = util.make_grid(9, 1)
+    ref = np.exp(-(x**2 + y**2) / (2 * 1.7**2)).reshape(9, 9)
+    np.testing.assert_allclose(k, ref / ref.sum(), rtol=1e-14)
+    with pytest.raises(ValueError):
+        gaussian_pixel_kernel(1.0, 4)
+
+
+def test_unsupported_numerics_raise():
+    kd = simulation_util.data_configure_simple(10, 0.1, 100, 0.1)
+    data = ImageData(**kd)
+    psf = PSF(psf_type="PIXEL", kernel_point_source=np.ones((3, 3)))
+    with pytest.raises(NotImplementedError):
+        Numerics(data, psf, supersampling_factor=2, supersampling_convolution=True)
+    with pytest.raises(ValueError):
+        Numerics(data, psf, compute_mode="adaptive")
+    with pytest.raises(TypeError):
+        Numerics(data, psf, supersampling_factor=2.0)
+    with pytest.raises(ValueError):
+        PSF(psf_type="PIXEL", kernel_point_source=np.ones((4, 4)))
+    with pytest.raises(ValueError):
+        PSF(psf_type="FOO")
+
+
+def test_image_data_noise_model():
+    img = np.array([[1.0, -2.0], [0.5, 4.0]])
+    d = ImageData(img, exposure_time=100.0, background_rms=0.1, transform_pix2angle=np.eye(2) * 0.05)
+    np.testing.assert_allclose(d.C_D, np.maximum(img, 0) / 100.0 + 0.01)
+    assert d.num_pixel_axes == (2, 2) and abs(d.pixel_width - 0.05) < 1e-15
+    d2 = ImageData(img, noise_map=np.full((2, 2), 0.3))
+    np.testing.assert_allclose(d2.C_D, 0.09)
+    with pytest.raises(ValueError):
+        ImageData(img, background_rms=0.1)
+    d3 = ImageData(img, exposure_time=np.array([[0.0, 1.0], [1.0, 1.0]]), background_rms=0.1)
+    assert d3.exposure_map[0, 0] == 1e-10
+
+
+def test_convert_bool_list():
+    assert util.convert_bool_list(3, None) == [True, True, True]
+    assert util.convert_bool_list(3, 1) == [False, True, False]
+    assert util.convert_bool_list(4, [0, 3]) == [True, False, False, True]
+    assert util.convert_bool_list(2, [True, False]) == [True, False]
+    with pytest.raises(ValueError):
+        util.convert_bool_list(2, [True, False, True])
+
+
+def test_kwargs_packing():
+    names = [_model.LENS_PARAM_NAMES["SIS"], _model.LENS_PARAM_NAMES["SHEAR"]]
+    kw = [dict(theta_E=np.array([1.0, 1.1, 1.2]), center_x=0.1), dict(gamma1=0.01, gamma2=np.array([0.0, 0.1, 0.2]))]
+    values = _model.gather_values(names, kw)
+    mat, B, batched = _model.pack_columns(values)
+    assert mat.shape == (3, 7) and B == 3 and batched
+    np.testing.assert_array_equal(mat[:, 0], [1.0, 1.1, 1.2])
+    np.testing.assert_array_equal(mat[:, 1], 0.1)      # broadcast scalar
+    np.testing.assert_array_equal(mat[:, 2], 0.0)      # default center_y
+    np.testing.assert_array_equal(mat[:, 4], [0.0, 0.1, 0.2])
+    mat1, B1, batched1 = _model.pack_columns(_model.gather_values(names, [dict(theta_E=1.0), dict(gamma1=0.0, gamma2=0.0)]))
+    assert mat1.shape == (1, 7) and not batched1
+    with pytest.raises(ValueError):
+        _model.gather_values(names, [dict(theta_E=1.0, foo=2.0), dict(gamma1=0, gamma2=0)])
+    with pytest.raises(ValueError):
+        _model.gather_values(names, [dict(center_x=1.0), dict(gamma1=0, gamma2=0)])
+    with pytest.raises(ValueError):
+        _model.gather_values(names, [dict(theta_E=1.0)])
+    with pytest.raises(ValueError):
+        _model.pack_columns([np.zeros(3), np.zeros(4)])
+
+
+def test_lens_desc_options():
+    from jaxtronomy_b200 import _lib
+
+    d = _model.lens_desc("SIE", [("cst", 1.0)] * 5, dict(NIE=False, gamma=2.1))
+    assert d.flags & _lib.FLAG_SIE_NIE_FALSE and d.opt[1] == 2.1
+    d = _model.lens_desc("CSE", [("col", k) for k in range(6)], dict(axis="major"))
+    assert d.flags & _lib.FLAG_CSE_MAJOR and list(d.col[:6]) == list(range(6))
+    with pytest.raises(ValueError):
+        _model.lens_desc("CSE", [("cst", 0.0)] * 6, dict(axis="minor"))
+    with pytest.raises(ValueError):
+        _model.lens_desc("FOO", [])
+    with pytest.raises(Exception):
+        _model.lens_desc("NFW", [("cst", 1.0)] * 4, dict(interpol=True))
+
+
+def test_cut_psf():
+    k = np.arange(49.0).reshape(7, 7)
+    c = kernel_util.cut_psf(k, 3, normalisation=False)
+    np.testing.assert_array_equal(c, k[2:5, 2:5])
+    assert abs(kernel_util.cut_psf(k, 5).sum() - 1) < 1e-15
+    with pytest.raises(ValueError):
+        kernel_util.cut_psf(k, 4)
+
+
+def test_shard_bounds():
+    for n, w in ((65536, 8), (10, 3), (5, 8), (0, 2)):
+        got = [parallel.shard_bounds(n, w, r) for r in range(w)]
+        assert got[0][0] == 0 and got[-1][1] == n
+        for (a, b), (c2, d) in zip(got[:-1], got[1:]):
+            assert b == c2 and b >= a
+        sizes = parallel.shard_sizes(n, w)
+        assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("n", [16, 11])
+def test_all_gather_logl_gloo_world2(n):
+    """N > 1 path on CPU: two gloo ranks shard a batch, evaluate a toy logL, all-gather it."""
+    script = os.path.join(ROOT, "tests", "gloo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29500 + n), PYTHONPATH=ROOT)
+    procs = [subprocess.Popen([sys.executable, script, str(r), "2", str(n)], env=env, stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "OK" in o, o
