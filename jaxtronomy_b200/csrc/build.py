@@ -15,7 +15,7 @@ DEPS = ["lsim_api.cu", "lsim_kernels.cuh", "lsim_profiles.cuh", "lsim_math.cuh",
         os.path.join(ROOT, "include", "lsim.h")]
 OUT = os.path.join(HERE, "liblsim.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--split-compile", "8"]
 
 
 def up_to_date():

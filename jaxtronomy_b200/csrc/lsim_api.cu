@@ -307,16 +307,28 @@ size_t per_set_bytes(const lsim_plan* plan, bool need_conv_out) {
 
 int64_t chunk_sets(const lsim_plan* plan) { return (int64_t)plan->n_sm * 8; }
 
+template <int NSLOT, bool FULL, int SS>
+int launch_image_k(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
+                   double scale, double* out, cudaStream_t st) {
+  dim3 grid((unsigned)tiles, (unsigned)n);
+  Timed timed(kClsImage, st);
+  k_image<NSLOT, FULL, SS><<<grid, kBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out);
+  return after_launch("k_image");
+}
+
+// Kernel variants: the EPL/SIE/SIS/SHEAR/CONVERGENCE profile set ("FULL = false") is specialised on the
+// supersampling factor (1, 2, 3 -> sub-pixels of a row evaluated in lock step); everything else runs the generic
+// variant (runtime supersampling factor, one sub-pixel at a time).
 template <int NSLOT>
 int launch_image_ns(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
                     double scale, double* out, cudaStream_t st) {
-  dim3 grid((unsigned)tiles, (unsigned)n);
-  Timed timed(kClsImage, st);
-  if (plan->full)
-    k_image<NSLOT, true><<<grid, kBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out);
-  else
-    k_image<NSLOT, false><<<grid, kBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out);
-  return after_launch("k_image");
+  if (plan->full) return launch_image_k<NSLOT, true, 0>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  switch (plan->dev.ss) {
+    case 1: return launch_image_k<NSLOT, false, 1>(plan, params, set0, n, ppt, tiles, scale, out, st);
+    case 2: return launch_image_k<NSLOT, false, 2>(plan, params, set0, n, ppt, tiles, scale, out, st);
+    case 3: return launch_image_k<NSLOT, false, 3>(plan, params, set0, n, ppt, tiles, scale, out, st);
+    default: return launch_image_k<NSLOT, false, 0>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  }
 }
 
 // ray-shoot + light + re-bin for sets [set0, set0+n) -> out[n][n_slots][npix]
@@ -336,8 +348,46 @@ int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int6
   return launch_image_ns<8>(plan, params, set0, n, ppt, tiles, scale, out, st);
 }
 
+template <int KT, int R, int NW>
+int launch_conv_tiled(const PlanDev& D, const double* in, double* out, int64_t n_images, cudaStream_t st) {
+  constexpr int TH = R * NW, HALO = KT - 1, PITCH = (32 + HALO) | 1, WS = KT + 1;
+  constexpr size_t smem = ((size_t)(TH + HALO) * PITCH + (size_t)KT * WS) * sizeof(double);
+  static bool configured = false;  // per process; the attribute is per function, set once
+  if (!configured) {
+    LSIM_CUDA(cudaFuncSetAttribute(k_conv_tiled<KT, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int tiles = ((D.nx + 31) / 32) * ((D.ny + TH - 1) / TH);
+  for (int64_t i0 = 0; i0 < n_images; i0 += 65535) {
+    const int64_t ni = n_images - i0 < 65535 ? n_images - i0 : 65535;
+    const size_t off = (size_t)i0 * D.nx * D.ny;
+    Timed timed(kClsConv, st);
+    k_conv_tiled<KT, R, NW><<<dim3((unsigned)tiles, (unsigned)ni), NW * 32, smem, st>>>(
+        in + off, out + off, D.nx, D.ny, D.K, D.kernel, D.conv_mode, D.image_scale);
+    int rc = after_launch("k_conv_tiled");
+    if (rc != LSIM_OK) return rc;
+  }
+  return LSIM_OK;
+}
+
+template <int KT>
+int launch_conv_tiled_kt(const PlanDev& D, const double* in, double* out, int64_t n_images, cudaStream_t st) {
+  // pick the tile height (64 = 8 warps x 8 rows, or 60 = 6 warps x 10 rows) that wastes fewer rows
+  const int w64 = ((D.ny + 63) / 64) * 64, w60 = ((D.ny + 59) / 60) * 60;
+  if (w60 < w64) return launch_conv_tiled<KT, 10, 6>(D, in, out, n_images, st);
+  return launch_conv_tiled<KT, 8, 8>(D, in, out, n_images, st);
+}
+
 int launch_conv(const lsim_plan* plan, const double* in, double* out, int64_t n_images, cudaStream_t st) {
   const PlanDev& D = plan->dev;
+  if (!D.kernel_1d && !getenv("LSIM_CONV_GENERIC")) {
+    if (D.K <= 7) return launch_conv_tiled_kt<7>(D, in, out, n_images, st);
+    if (D.K <= 11) return launch_conv_tiled_kt<11>(D, in, out, n_images, st);
+    if (D.K <= 15) return launch_conv_tiled_kt<15>(D, in, out, n_images, st);
+    if (D.K <= 21) return launch_conv_tiled_kt<21>(D, in, out, n_images, st);
+    if (D.K <= 25) return launch_conv_tiled_kt<25>(D, in, out, n_images, st);
+    if (D.K <= 31) return launch_conv_tiled_kt<31>(D, in, out, n_images, st);
+  }
   const int K = D.K, TW = kConvT + K - 1, pitch = TW | 1;
   const int tiles = ((D.nx + kConvT - 1) / kConvT) * ((D.ny + kConvT - 1) / kConvT);
   for (int64_t i0 = 0; i0 < n_images; i0 += 65535) {

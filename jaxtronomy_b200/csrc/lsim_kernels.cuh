@@ -84,35 +84,31 @@ k_ray_shoot(PlanDev P, const double* __restrict__ params, const double* __restri
   const double* xb = coords_batched ? x + b * N : x;
   const double* yb = coords_batched ? y + b * N : y;
 
-  Ray r[kRayItems];
-  double x0[kRayItems], y0[kRayItems];
+  Rays<kRayItems> r;
   int64_t idx[kRayItems];
 #pragma unroll
   for (int k = 0; k < kRayItems; ++k) {
     idx[k] = (int64_t)blockIdx.x * (kBlock * kRayItems) + k * kBlock + threadIdx.x;
-    x0[k] = idx[k] < N ? xb[idx[k]] : 0.0;
-    y0[k] = idx[k] < N ? yb[idx[k]] : 0.0;
-    ray_init(P.ray, x0[k], y0[k], r[k]);
+    const double x0 = idx[k] < N ? xb[idx[k]] : 0.0;
+    const double y0 = idx[k] < N ? yb[idx[k]] : 0.0;
+    ray_init(P.ray, k, x0, y0, r);
   }
   for (int c0 = 0; c0 < P.n_lens; c0 += kLensChunk) {
     int n_c = min(kLensChunk, P.n_lens - c0);
     __syncthreads();
     stage_lens(P, row, c0, n_c, L, pool);
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kRayItems; ++k) {
-      if (idx[k] < N) ray_apply<FULL>(P.ray, L, pool, n_c, r[k]);
-    }
+    ray_apply<FULL, kRayItems>(P.ray, L, pool, n_c, r);
   }
 #pragma unroll
   for (int k = 0; k < kRayItems; ++k) {
     if (idx[k] < N) {
       double bx, by;
       if (what == 1 && !P.ray.multi_plane) {
-        bx = r[k].ax * P.ray.alpha_scaling;
-        by = r[k].ay * P.ray.alpha_scaling;
+        bx = r.ax[k] * P.ray.alpha_scaling;
+        by = r.ay[k] * P.ray.alpha_scaling;
       } else {
-        ray_finish(P.ray, r[k], bx, by);
+        ray_finish(P.ray, r, k, bx, by);
       }
       ox[b * N + idx[k]] = bx;
       oy[b * N + idx[k]] = by;
@@ -147,10 +143,13 @@ k_surface_brightness(PlanDev P, const double* __restrict__ params, const double*
 // grid = (tiles, sets); each CTA owns pixels [tile*ppt, (tile+1)*ppt) of one parameter set.
 // out[(set_local * n_slots + slot) * npix + pixel] = mean over the ss x ss sub-pixels  (* out_scale)
 // (RegularGrid.flux_array2image_low_high + image_util.re_size: grid.py:101-117, image_util.py:78-98).
-template <int NSLOT, bool FULL>
-__global__ void __launch_bounds__(kBlock)
+// SS > 0: compile-time supersampling factor, the SS sub-pixels of a row are evaluated in lock step (J = SS);
+// SS == 0: runtime supersampling factor, one sub-pixel at a time.
+template <int NSLOT, bool FULL, int SS>
+__global__ void __launch_bounds__(kBlock, 2)
 k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, double out_scale,
         double* __restrict__ out) {
+  constexpr int J = SS > 0 ? SS : 1;
   extern __shared__ double smem[];
   LensC* L = reinterpret_cast<LensC*>(smem);
   LightC* G = reinterpret_cast<LightC*>(L + P.n_lens);
@@ -162,7 +161,7 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
   __syncthreads();
 
   const int npix = P.nx * P.ny;
-  const int ss = P.ss;
+  const int ss = SS > 0 ? SS : P.ss;
   const int64_t sub_stride = (int64_t)P.nx * ss;
   const double inv_ss = 1.0 / ss;
   const int p_end = min(npix, (int)(blockIdx.x + 1) * ppt);
@@ -176,19 +175,30 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
 #pragma unroll
       for (int k = 0; k < NSLOT; ++k) racc[k] = 0.0;
       const int64_t base = ((int64_t)py * ss + i) * sub_stride + (int64_t)px * ss;
-      for (int j = 0; j < ss; ++j) {
-        const double x = __ldg(P.x_sub + base + j), y = __ldg(P.y_sub + base + j);
-        Ray r;
-        ray_init(P.ray, x, y, r);
-        ray_apply<FULL>(P.ray, L, pool, P.n_lens, r);
-        double bx, by;
-        ray_finish(P.ray, r, bx, by);
+      for (int j0 = 0; j0 < ss; j0 += J) {
+        double x[J], y[J], bx[J], by[J], v[J];
+        Rays<J> r;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          x[j] = __ldg(P.x_sub + base + j0 + j);
+          y[j] = __ldg(P.y_sub + base + j0 + j);
+          ray_init(P.ray, j, x[j], y[j], r);
+        }
+        ray_apply<FULL, J>(P.ray, L, pool, P.n_lens, r);
+#pragma unroll
+        for (int j = 0; j < J; ++j) ray_finish(P.ray, r, j, bx[j], by[j]);
         for (int g = 0; g < P.n_light; ++g) {
           const int slot = G[g].slot;
           if (slot < 0) continue;
-          const double v = G[g].lensed ? light_eval(G[g], bx, by) : light_eval(G[g], x, y);
+          if (G[g].lensed)
+            light_eval<J>(G[g], bx, by, v);
+          else
+            light_eval<J>(G[g], x, y, v);
+          double vs = v[0];
 #pragma unroll
-          for (int k = 0; k < NSLOT; ++k) racc[k] += (slot == k) ? v : 0.0;
+          for (int j = 1; j < J; ++j) vs += v[j];
+#pragma unroll
+          for (int k = 0; k < NSLOT; ++k) racc[k] += (slot == k) ? vs : 0.0;
         }
       }
 #pragma unroll
@@ -273,6 +283,61 @@ k_conv_direct(const double* __restrict__ in, double* __restrict__ out, int nx, i
 #pragma unroll
   for (int o = 0; o < kConvR; ++o) {
     int x = tx0 + tx, y = ty0 + ty * kConvR + o;
+    if (x < nx && y < ny) dst[(int64_t)y * nx + x] = acc[o] * scale;
+  }
+}
+
+// Register-tiled direct convolution for K <= KT (the common PSF sizes; the kernel is zero-padded to KT x KT).
+// A warp owns a 32-column x R-row strip, NW warps stack to a 32 x (R NW) tile.  For each kernel column dx a
+// thread pulls its R + KT - 1 input values of that column into registers once and reuses each of them for up
+// to KT of the R x KT FMAs; the KT weights of the column are warp-uniform shared-memory broadcasts.  Shared
+// memory traffic per FMA drops from 2 loads (k_conv_direct) to (R + 2 KT - 1) / (R KT) ~ 0.24 (R = 10, KT = 21),
+// which moves the kernel from shared-memory-bandwidth-bound to fp64-pipe-bound.
+template <int KT, int R, int NW>
+__global__ void __launch_bounds__(NW * 32, 2)
+k_conv_tiled(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
+             const double* __restrict__ kernel, int mode, double scale) {
+  constexpr int NT = NW * 32, TH = R * NW, HALO = KT - 1, TWD = 32 + HALO, PITCH = TWD | 1, WS = KT + 1;
+  extern __shared__ double smem[];
+  double* tile = smem;                      // [TH + HALO][PITCH]
+  double* wT = smem + (TH + HALO) * PITCH;  // [KT][WS]: wT[dx][dy], flipped (correlation form), zero padded
+  const int rT = HALO / 2, pad = (KT - K) / 2;
+  const int tiles_x = (nx + 31) / 32;
+  const int tx0 = (blockIdx.x % tiles_x) * 32, ty0 = (blockIdx.x / tiles_x) * TH;
+  const double* img = in + (int64_t)blockIdx.y * nx * ny;
+  for (int i = threadIdx.x; i < KT * KT; i += NT) {
+    const int a = i / KT, b = i - a * KT, ka = a - pad, kb = b - pad;
+    const bool inside = ka >= 0 && ka < K && kb >= 0 && kb < K;
+    wT[b * WS + a] = inside ? kernel[(K - 1 - ka) * K + (K - 1 - kb)] : 0.0;
+  }
+  for (int i = threadIdx.x; i < (TH + HALO) * TWD; i += NT) {
+    const int ly = i / TWD, lx = i - ly * TWD;
+    tile[ly * PITCH + lx] = conv_fetch(img, nx, ny, tx0 + lx - rT, ty0 + ly - rT, mode);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[R];
+#pragma unroll
+  for (int o = 0; o < R; ++o) acc[o] = 0.0;
+  const double* tcol = tile + (warp * R) * PITCH + lane;
+#pragma unroll 1
+  for (int dx = 0; dx < KT; ++dx) {
+    double v[R + KT - 1];
+#pragma unroll
+    for (int i = 0; i < R + KT - 1; ++i) v[i] = tcol[i * PITCH + dx];
+    const double* w = wT + dx * WS;
+#pragma unroll
+    for (int dy = 0; dy < KT; ++dy) {
+      const double wv = w[dy];
+#pragma unroll
+      for (int o = 0; o < R; ++o) acc[o] = fma(wv, v[o + dy], acc[o]);
+    }
+  }
+  double* dst = out + (int64_t)blockIdx.y * nx * ny;
+  const int x = tx0 + lane;
+#pragma unroll
+  for (int o = 0; o < R; ++o) {
+    const int y = ty0 + warp * R + o;
     if (x < nx && y < ny) dst[(int64_t)y * nx + x] = acc[o] * scale;
   }
 }

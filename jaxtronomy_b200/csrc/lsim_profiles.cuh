@@ -156,40 +156,83 @@ LSIM_HD void epl_prepare(LensC& L, double* coef, double theta_E, double gamma, d
   L.n_coef = n_used;
 }
 
-// Deflection of the EPL in the profile frame, for a point already shifted by the centre.
-// Tessore & Metcalf eq. 22/23 reorganised so that the only non-FMA work is one reciprocal, one log2 and
-// one exp2:  with Z = q x' + i y', R2 = |Z|^2, D = f Z^2 + 2 R2:
+// Deflection of the EPL for J points at once (already shifted by the centre).  J independent points are
+// evaluated in lock step so that the series coefficients are read from shared memory once per J points and
+// the compiler can interleave J independent FMA chains.
+//
+// Tessore & Metcalf eq. 22/23 reorganised so that the only non-FMA work per point is one reciprocal, one
+// log2 and one exp2:  with Z = q x' + i y', R2 = |Z|^2, D = f Z^2 + 2 R2:
 //   w = f Z^2 conj(D)/|D|^2,  (1 - z/2)^-1 = 2 R2 conj(D)/|D|^2,  (b/R)^t = exp2(t log2 b - t/2 log2 R2)
-LSIM_HD void epl_eval(const LensC& L, const double* coef, double xs, double ys, double& ax, double& ay) {
+// The series S = sum_n F_n w^n has REAL coefficients, so it is summed with the quadratic-factor (Goertzel /
+// Clenshaw) recurrence  b_k = F_k + p b_{k+1} - |w|^2 b_{k+2},  p = 2 Re w,  S = F_0 - |w|^2 b_2 + b_1 w:
+// two real FMAs per term instead of the four of a complex Horner step.  |w| <= f/(2-f) < 1, so the
+// recurrence is contractive (its characteristic roots are w and conj(w)).
+template <int J>
+LSIM_HD void epl_eval(const LensC& L, const double* coef, const double (&xs)[J], const double (&ys)[J],
+                      double (&ax)[J], double (&ay)[J]) {
   const double cph = L.c[2], sph = L.c[3], q = L.c[4], f = L.c[5];
-  double xr = xs * cph + ys * sph;
-  double yr = -xs * sph + ys * cph;
-  double a = q * xr, c = yr;
-  double R2 = a * a + c * c;
-  double z2r = a * a - c * c, z2i = 2.0 * a * c;
-  double Dr = fma(f, z2r, 2.0 * R2), Di = f * z2i;
-  double inv = 1.0 / (Dr * Dr + Di * Di);
-  double cDr = Dr * inv, cDi = -Di * inv;  // conj(D)/|D|^2
-  double wr = f * (z2r * cDr - z2i * cDi);
-  double wi = f * (z2r * cDi + z2i * cDr);
-  // Horner: S = sum F_n w^n
-  int n = L.n_coef - 1;
-  double Sr = coef[n], Si = 0.0;
-  for (--n; n >= 0; --n) {
-    double tr = fma(Sr, wr, fma(-Si, wi, coef[n]));
-    Si = fma(Sr, wi, Si * wr);
-    Sr = tr;
+  double a[J], c[J], R2[J], wr[J], wi[J], pr[J], pi[J], pp[J], qq[J], b1[J], b2[J];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    const double xr = fma(ys[j], sph, xs[j] * cph);
+    c[j] = fma(ys[j], cph, -(xs[j] * sph));
+    a[j] = q * xr;
+    const double aa = a[j] * a[j];
+    R2[j] = fma(c[j], c[j], aa);
+    const double z2r = fma(-c[j], c[j], aa), z2i = 2.0 * a[j] * c[j];
+    const double R2x2 = R2[j] + R2[j];
+    const double Dr = fma(f, z2r, R2x2), Di = f * z2i;
+    const double inv = rcp_fast(fma(Dr, Dr, Di * Di));
+    const double finv = f * inv, s2 = R2x2 * inv;
+    wr[j] = fma(z2i, Di, z2r * Dr) * finv;  // Re(Z^2 conj D) f / |D|^2
+    wi[j] = fma(z2i, Dr, -(z2r * Di)) * finv;
+    pr[j] = s2 * Dr;                        // 2 R2 conj(D) / |D|^2
+    pi[j] = -(s2 * Di);
+    pp[j] = wr[j] + wr[j];
+    qq[j] = -fma(wr[j], wr[j], wi[j] * wi[j]);
+    b1[j] = 0.0;
+    b2[j] = 0.0;
   }
-  // hyp = 2 R2 conj(D)/|D|^2 * S ; R_omega = Z * hyp
-  double pr = 2.0 * R2 * cDr, pi = 2.0 * R2 * cDi;
-  double hr = pr * Sr - pi * Si, hi = pr * Si + pi * Sr;
-  double or_ = a * hr - c * hi, oi = a * hi + c * hr;
-  double R2c = fmax(R2, 1e-18);  // R = max(|Z|, 1e-9)
-  double P = L.c[8] * exp2_fin(fma(L.c[6], log2_pos(R2c), L.c[7]));
-  double fr = nan_to_num(P * or_, 1e10, -1e10);
-  double fi = nan_to_num(P * oi, 1e10, -1e10);
-  ax = fr * cph - fi * sph;  // rotate(f, -phi)
-  ay = fr * sph + fi * cph;
+  for (int k = L.n_coef - 1; k >= 1; --k) {
+    const double ck = coef[k];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < J; ++j) {
+      const double t = fma(pp[j], b1[j], fma(qq[j], b2[j], ck));
+      b2[j] = b1[j];
+      b1[j] = t;
+    }
+  }
+  const double c0 = coef[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    const double Sr = fma(b1[j], wr[j], fma(qq[j], b2[j], c0)), Si = b1[j] * wi[j];
+    // hyp = 2 R2 conj(D)/|D|^2 * S ; R_omega = Z * hyp
+    const double hr = fma(pr[j], Sr, -(pi[j] * Si)), hi = fma(pr[j], Si, pi[j] * Sr);
+    const double orr = fma(a[j], hr, -(c[j] * hi)), oi = fma(a[j], hi, c[j] * hr);
+    const double R2c = fmax(R2[j], 1e-18);  // R = max(|Z|, 1e-9)
+    const double P = L.c[8] * exp2_fin(fma(L.c[6], log2_pos(R2c), L.c[7]));
+    double fr = P * orr, fi = P * oi;
+    if (!(fabs(fr) + fabs(fi) <= DBL_MAX)) {  // nan_to_num(posinf=1e10, neginf=-1e10), epl.py:391-392
+      fr = nan_to_num(fr, 1e10, -1e10);
+      fi = nan_to_num(fi, 1e10, -1e10);
+    }
+    ax[j] = fma(-fi, sph, fr * cph);  // rotate(f, -phi)
+    ay[j] = fma(fi, cph, fr * sph);
+  }
+}
+
+LSIM_HD void epl_eval1(const LensC& L, const double* coef, double xs, double ys, double& ax, double& ay) {
+  const double x1[1] = {xs}, y1[1] = {ys};
+  double fx1[1], fy1[1];
+  epl_eval<1>(L, coef, x1, y1, fx1, fy1);
+  ax = fx1[0];
+  ay = fy1[0];
 }
 
 // cos / sin of m*(phi - phi_m) and cos/sin(phi) from the shifted point, no trig calls:
@@ -432,11 +475,11 @@ LSIM_HD void lens_prepare(const lsim_lens_desc& d, const double* row, LensC& L, 
 
 // ---- lens: evaluate the reduced deflection of one profile at (x, y) ----------------------------------
 template <bool FULL>
-LSIM_HD void lens_eval(const LensC& L, const double* coef_pool, double x, double y, double& fx, double& fy) {
+LSIM_HD void lens_eval1(const LensC& L, const double* coef_pool, double x, double y, double& fx, double& fy) {
   const double xs = x - L.c[0], ys = y - L.c[1];
   switch (L.type) {
     case LSIM_LENS_EPL:
-      epl_eval(L, coef_pool + L.coef_off, xs, ys, fx, fy);
+      epl_eval1(L, coef_pool + L.coef_off, xs, ys, fx, fy);
       return;
     case LSIM_LENS_SHEAR:
       fx = L.c[2] * xs + L.c[3] * ys;
@@ -473,7 +516,7 @@ LSIM_HD void lens_eval(const LensC& L, const double* coef_pool, double x, double
     switch (L.type) {
       case LSIM_LENS_EPL_MULTIPOLE_M1M3M4: {
         double ex, ey, mx, my;
-        epl_eval(L, coef_pool + L.coef_off, xs, ys, ex, ey);
+        epl_eval1(L, coef_pool + L.coef_off, xs, ys, ex, ey);
         multipole_eval(xs, ys, 3, L.c[13], L.c[14], L.c[15], 0.0, mx, my);
         ex += mx;
         ey += my;
@@ -544,6 +587,40 @@ LSIM_HD void lens_eval(const LensC& L, const double* coef_pool, double x, double
   fy = 0.0;
 }
 
+// J points at once: the hot profiles (EPL, SHEAR) are evaluated in lock step, everything else point by point.
+template <bool FULL, int J>
+LSIM_HD void lens_eval(const LensC& L, const double* coef_pool, const double (&x)[J], const double (&y)[J],
+                       double (&fx)[J], double (&fy)[J]) {
+  if (L.type == LSIM_LENS_EPL) {
+    double xs[J], ys[J];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < J; ++j) {
+      xs[j] = x[j] - L.c[0];
+      ys[j] = y[j] - L.c[1];
+    }
+    epl_eval<J>(L, coef_pool + L.coef_off, xs, ys, fx, fy);
+    return;
+  }
+  if (L.type == LSIM_LENS_SHEAR) {
+    const double g1 = L.c[2], g2 = L.c[3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < J; ++j) {
+      const double xs = x[j] - L.c[0], ys = y[j] - L.c[1];
+      fx[j] = fma(g2, ys, g1 * xs);
+      fy[j] = fma(-g1, ys, g2 * xs);
+    }
+    return;
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) lens_eval1<FULL>(L, coef_pool, x[j], y[j], fx[j], fy[j]);
+}
+
 // true when the profile needs the FULL kernel variant
 LSIM_HD bool lens_type_is_full(int type) {
   switch (type) {
@@ -573,59 +650,78 @@ struct RayCfg {
   double alpha_scaling, T_ij_end, inv_T_z_source;
 };
 
-// State of one ray while it is pushed through the deflector list.
-struct Ray {
-  double x, y;    // single plane: image position; multi plane: comoving position
-  double ax, ay;  // single plane: accumulated deflection; multi plane: current angle
+// State of J rays while they are pushed through the deflector list.
+template <int J>
+struct Rays {
+  double x[J], y[J];    // single plane: image position; multi plane: comoving position
+  double ax[J], ay[J];  // single plane: accumulated deflection; multi plane: current angle
 };
 
-template <bool FULL>
-LSIM_HD void ray_apply(const RayCfg& P, const LensC* L, const double* pool, int n_c, Ray& r) {
+template <bool FULL, int J>
+LSIM_HD void ray_apply(const RayCfg& P, const LensC* L, const double* pool, int n_c, Rays<J>& r) {
+  double fx[J], fy[J];
   if (!P.multi_plane) {
     for (int l = 0; l < n_c; ++l) {
-      double fx, fy;
-      lens_eval<FULL>(L[l], pool, r.x, r.y, fx, fy);
-      r.ax += fx;
-      r.ay += fy;
+      lens_eval<FULL, J>(L[l], pool, r.x, r.y, fx, fy);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < J; ++j) {
+        r.ax[j] += fx[j];
+        r.ay[j] += fy[j];
+      }
     }
   } else {
     // MultiPlaneBase.ray_shooting_partial_comoving (multi_plane_base.py:195-233)
+    double tx[J], ty[J];
     for (int l = 0; l < n_c; ++l) {
-      r.x += r.ax * L[l].delta_T;
-      r.y += r.ay * L[l].delta_T;
-      double fx, fy;
-      lens_eval<FULL>(L[l], pool, r.x * L[l].inv_T_z, r.y * L[l].inv_T_z, fx, fy);
-      r.ax -= fx * L[l].red2phys;
-      r.ay -= fy * L[l].red2phys;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < J; ++j) {
+        r.x[j] += r.ax[j] * L[l].delta_T;
+        r.y[j] += r.ay[j] * L[l].delta_T;
+        tx[j] = r.x[j] * L[l].inv_T_z;
+        ty[j] = r.y[j] * L[l].inv_T_z;
+      }
+      lens_eval<FULL, J>(L[l], pool, tx, ty, fx, fy);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < J; ++j) {
+        r.ax[j] -= fx[j] * L[l].red2phys;
+        r.ay[j] -= fy[j] * L[l].red2phys;
+      }
     }
   }
 }
 
-LSIM_HD void ray_init(const RayCfg& P, double x, double y, Ray& r) {
+template <int J>
+LSIM_HD void ray_init(const RayCfg& P, int j, double x, double y, Rays<J>& r) {
   if (!P.multi_plane) {
-    r.x = x;
-    r.y = y;
-    r.ax = 0;
-    r.ay = 0;
+    r.x[j] = x;
+    r.y[j] = y;
+    r.ax[j] = 0;
+    r.ay[j] = 0;
   } else {
-    r.x = 0;
-    r.y = 0;
-    r.ax = x;
-    r.ay = y;
+    r.x[j] = 0;
+    r.y[j] = 0;
+    r.ax[j] = x;
+    r.ay[j] = y;
   }
 }
 
 // -> source-plane position
-LSIM_HD void ray_finish(const RayCfg& P, const Ray& r, double& bx, double& by) {
+template <int J>
+LSIM_HD void ray_finish(const RayCfg& P, const Rays<J>& r, int j, double& bx, double& by) {
   if (!P.multi_plane) {
-    bx = r.x - r.ax * P.alpha_scaling;
-    by = r.y - r.ay * P.alpha_scaling;
+    bx = r.x[j] - r.ax[j] * P.alpha_scaling;
+    by = r.y[j] - r.ay[j] * P.alpha_scaling;
   } else {
-    bx = (r.x + r.ax * P.T_ij_end) * P.inv_T_z_source;
-    by = (r.y + r.ay * P.T_ij_end) * P.inv_T_z_source;
+    bx = (r.x[j] + r.ax[j] * P.T_ij_end) * P.inv_T_z_source;
+    by = (r.y[j] + r.ay[j] * P.T_ij_end) * P.inv_T_z_source;
   }
 }
-
 
 // ---- light -----------------------------------------------------------------------------------------------
 // c[0..1] centre; SERSIC family: c[2..4] = product-average transform rows / norm, c[5] = 1/(2n),
@@ -682,20 +778,42 @@ LSIM_HD void light_prepare(const lsim_light_desc& d, const double* row, LightC& 
   }
 }
 
-LSIM_HD double light_eval(const LightC& G, double x, double y) {
-  const double xs = x - G.c[0], ys = y - G.c[1];
+// J points at once (sersic_utils.py:247-267 with R^2 in place of R: no square root is needed because
+// (R/Rs)^(1/n) = exp2(log2(R^2)/(2n) - log2(Rs)/n)).
+template <int J>
+LSIM_HD void light_eval(const LightC& G, const double (&x)[J], const double (&y)[J], double (&v)[J]) {
   if (G.type == LSIM_LIGHT_SERSIC_ELLIPSE) {
-    double xt = G.c[2] * xs + G.c[3] * ys;
-    double yt = G.c[3] * xs + G.c[4] * ys;
-    double R2 = xt * xt + yt * yt;
-    double R2c = fmax(R2, 1e-8);  // R_ = max(1e-4, R)
-    double k = exp2_fin(fma(G.c[5], log2_pos(R2c), G.c[6]));
-    double v = exp2_fin(fma(G.c[7], k, G.c[8]));
-    v = (R2c <= G.c[9]) ? v : 0.0;
-    return G.c[10] * nan_to_num(v);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < J; ++j) {
+      const double xs = x[j] - G.c[0], ys = y[j] - G.c[1];
+      const double xt = fma(G.c[3], ys, G.c[2] * xs);
+      const double yt = fma(G.c[4], ys, G.c[3] * xs);
+      const double R2c = fmax(fma(yt, yt, xt * xt), 1e-8);  // R_ = max(1e-4, R)
+      const double k = exp2_fin(fma(G.c[5], log2_pos(R2c), G.c[6]));
+      double e = exp2_fin(fma(G.c[7], k, G.c[8]));
+      e = (R2c <= G.c[9]) ? e : 0.0;  // R_/Rs_ <= max_R_frac
+      e = (e == e) ? e : 0.0;         // nan_to_num (the exponent is bounded above, so no +inf)
+      v[j] = G.c[10] * e;
+    }
+    return;
   }
   // GAUSSIAN
-  return G.c[3] * exp2_fin(G.c[2] * (xs * xs + ys * ys));
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    const double xs = x[j] - G.c[0], ys = y[j] - G.c[1];
+    v[j] = G.c[3] * exp2_fin(G.c[2] * fma(ys, ys, xs * xs));
+  }
+}
+
+LSIM_HD double light_eval(const LightC& G, double x, double y) {
+  const double x1[1] = {x}, y1[1] = {y};
+  double v1[1];
+  light_eval<1>(G, x1, y1, v1);
+  return v1[0];
 }
 
 }  // namespace lsim

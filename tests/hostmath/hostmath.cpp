@@ -21,15 +21,30 @@ int hm_ray_shoot(const lsim_lens_desc* lens, int n_lens, int multi_plane, double
     if (lens_type_has_series(lens[i])) ++off;
   }
   RayCfg cfg{multi_plane, multi_plane ? 1.0 : alpha_scaling, T_ij_end, multi_plane ? 1.0 / T_z_source : 0.0};
-  for (int64_t i = 0; i < N; ++i) {
-    Ray r;
-    ray_init(cfg, x[i], y[i], r);
-    ray_apply<true>(cfg, L.data(), pool.data(), n_lens, r);
+  // points go through the same J-batched code path the kernels use (J = 3), tail with J = 1
+  int64_t i = 0;
+  for (; i + 3 <= N; i += 3) {
+    Rays<3> r;
+    for (int j = 0; j < 3; ++j) ray_init(cfg, j, x[i + j], y[i + j], r);
+    ray_apply<true, 3>(cfg, L.data(), pool.data(), n_lens, r);
+    for (int j = 0; j < 3; ++j) {
+      if (what == 1 && !multi_plane) {
+        ox[i + j] = r.ax[j] * cfg.alpha_scaling;
+        oy[i + j] = r.ay[j] * cfg.alpha_scaling;
+      } else {
+        ray_finish(cfg, r, j, ox[i + j], oy[i + j]);
+      }
+    }
+  }
+  for (; i < N; ++i) {
+    Rays<1> r;
+    ray_init(cfg, 0, x[i], y[i], r);
+    ray_apply<true, 1>(cfg, L.data(), pool.data(), n_lens, r);
     if (what == 1 && !multi_plane) {
-      ox[i] = r.ax * cfg.alpha_scaling;
-      oy[i] = r.ay * cfg.alpha_scaling;
+      ox[i] = r.ax[0] * cfg.alpha_scaling;
+      oy[i] = r.ay[0] * cfg.alpha_scaling;
     } else {
-      ray_finish(cfg, r, ox[i], oy[i]);
+      ray_finish(cfg, r, 0, ox[i], oy[i]);
     }
   }
   return 0;
