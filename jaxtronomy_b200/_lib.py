@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblsim.so")
+LIB_PATH = os.environ.get("LSIM_LIB") or os.path.join(_HERE, "csrc", "liblsim.so")  # LSIM_LIB: kernel experiments
 
 MAX_PARAMS = 12
 MAX_SLOTS = 8

@@ -73,6 +73,7 @@ struct lsim_plan {
   std::vector<void*> owned;
   bool full = false;
   int n_series = 0;
+  int sig = -1;  // index of the specialised image kernel for this model, or -1
   bool has_image = false, has_data = false;
   size_t image_smem = 0;
   int n_sm = 148;
@@ -112,6 +113,8 @@ int configure_kernels() {
   LSIM_CUDA(cudaFuncSetAttribute(k_conv_separable, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
   return LSIM_OK;
 }
+
+int find_signature(const lsim_plan_desc* d);  // defined with the kernel-variant tables below
 
 double series_tol_default() {
   const char* s = getenv("LSIM_SERIES_TOL");
@@ -218,6 +221,7 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
   if (d->n_light) TRY(p->upload(d->light, (size_t)d->n_light, &D.light));
   p->full = full;
   p->n_series = n_series;
+  p->sig = find_signature(d);
   p->has_image = has_image;
   p->has_data = has_data;
   if (has_image) {
@@ -307,16 +311,74 @@ size_t per_set_bytes(const lsim_plan* plan, bool need_conv_out) {
 
 int64_t chunk_sets(const lsim_plan* plan) { return (int64_t)plan->n_sm * 8; }
 
-template <int NSLOT, bool FULL, int SS>
+template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = RuntimeTypes>
 int launch_image_k(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
                    double scale, double* out, cudaStream_t st) {
   dim3 grid((unsigned)tiles, (unsigned)n);
   Timed timed(kClsImage, st);
-  k_image<NSLOT, FULL, SS><<<grid, kBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out);
+  k_image<NSLOT, FULL, SS, LT, GT><<<grid, kBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out);
   return after_launch("k_image");
 }
 
-// Kernel variants: the EPL/SIE/SIS/SHEAR/CONVERGENCE profile set ("FULL = false") is specialised on the
+// ---- model signatures with a specialised image kernel ------------------------------------------------------------
+// (effective lens types) x (effective light types, source components first).  The list covers the BASELINE.json
+// configurations and their SIE variants; every other model runs the interpreted kernel.
+constexpr int kSE = LSIM_LIGHT_SERSIC_ELLIPSE;
+using LT_EplShear = TypeList<LSIM_LENS_EPL, LSIM_LENS_SHEAR>;
+using LT_NieShear = TypeList<LSIM_LENS_NIE, LSIM_LENS_SHEAR>;
+using LT_EplmShear = TypeList<LSIM_LENS_EPL_MULTIPOLE_M1M3M4, LSIM_LENS_SHEAR>;
+using GT_S = TypeList<kSE>;
+using GT_SS = TypeList<kSE, kSE>;
+enum { kSigNone = -1, kSigEplShear_S, kSigEplShear_SS, kSigNieShear_S, kSigNieShear_SS, kSigEplmShear_SS };
+
+int effective_lens_type(const lsim_lens_desc& d) {
+  if (d.type == LSIM_LENS_SIE) return (d.flags & LSIM_FLAG_SIE_NIE_FALSE) ? LSIM_LENS_EPL : LSIM_LENS_NIE;
+  return d.type;
+}
+int effective_light_type(const lsim_light_desc& d) {
+  return d.type == LSIM_LIGHT_SERSIC ? LSIM_LIGHT_SERSIC_ELLIPSE : d.type;
+}
+
+template <class LT, class GT>
+bool sig_matches(const lsim_plan_desc* d) {
+  if (d->multi_plane || d->n_lens != LT::N || d->n_light != GT::N) return false;
+  for (int i = 0; i < LT::N; ++i)
+    if (effective_lens_type(d->lens[i]) != LT::at(i)) return false;
+  for (int i = 0; i < GT::N; ++i)
+    if (effective_light_type(d->light[i]) != GT::at(i)) return false;
+  return true;
+}
+
+int find_signature(const lsim_plan_desc* d) {
+  if (getenv("LSIM_NO_SPECIALISE")) return kSigNone;
+  if (sig_matches<LT_EplShear, GT_S>(d)) return kSigEplShear_S;
+  if (sig_matches<LT_EplShear, GT_SS>(d)) return kSigEplShear_SS;
+  if (sig_matches<LT_NieShear, GT_S>(d)) return kSigNieShear_S;
+  if (sig_matches<LT_NieShear, GT_SS>(d)) return kSigNieShear_SS;
+  if (sig_matches<LT_EplmShear, GT_SS>(d)) return kSigEplmShear_SS;
+  return kSigNone;
+}
+
+// returns LSIM_E_UNSUPPORTED when (NSLOT, ss) has no specialised instantiation -> caller falls back
+template <bool FULL, class LT, class GT>
+int launch_image_sig(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
+                     double scale, double* out, cudaStream_t st) {
+  const int ns = plan->dev.n_slots, ss = plan->dev.ss;
+#define LSIM_SIG_CASE(NS, SSV) \
+  if (ns == NS && ss == SSV) return launch_image_k<NS, FULL, SSV, LT, GT>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  LSIM_SIG_CASE(1, 3)
+  LSIM_SIG_CASE(2, 3)
+  if (!FULL) {
+    LSIM_SIG_CASE(1, 1)
+    LSIM_SIG_CASE(1, 2)
+    LSIM_SIG_CASE(2, 1)
+    LSIM_SIG_CASE(2, 2)
+  }
+#undef LSIM_SIG_CASE
+  return LSIM_E_UNSUPPORTED;
+}
+
+// Interpreted variants: the EPL/SIE/SIS/SHEAR/CONVERGENCE profile set ("FULL = false") is specialised on the
 // supersampling factor (1, 2, 3 -> sub-pixels of a row evaluated in lock step); everything else runs the generic
 // variant (runtime supersampling factor, one sub-pixel at a time).
 template <int NSLOT>
@@ -342,6 +404,16 @@ int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int6
   ppt = ((ppt + kBlock - 1) / kBlock) * kBlock;
   tiles = (npix + ppt - 1) / ppt;
   const int ns = plan->dev.n_slots;
+  int rc = LSIM_E_UNSUPPORTED;
+  switch (plan->sig) {
+    case kSigEplShear_S: rc = launch_image_sig<false, LT_EplShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, st); break;
+    case kSigEplShear_SS: rc = launch_image_sig<false, LT_EplShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, st); break;
+    case kSigNieShear_S: rc = launch_image_sig<false, LT_NieShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, st); break;
+    case kSigNieShear_SS: rc = launch_image_sig<false, LT_NieShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, st); break;
+    case kSigEplmShear_SS: rc = launch_image_sig<true, LT_EplmShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, st); break;
+    default: break;
+  }
+  if (rc != LSIM_E_UNSUPPORTED) return rc;
   if (ns <= 1) return launch_image_ns<1>(plan, params, set0, n, ppt, tiles, scale, out, st);
   if (ns <= 2) return launch_image_ns<2>(plan, params, set0, n, ppt, tiles, scale, out, st);
   if (ns <= 4) return launch_image_ns<4>(plan, params, set0, n, ppt, tiles, scale, out, st);

@@ -145,8 +145,15 @@ k_surface_brightness(PlanDev P, const double* __restrict__ params, const double*
 // (RegularGrid.flux_array2image_low_high + image_util.re_size: grid.py:101-117, image_util.py:78-98).
 // SS > 0: compile-time supersampling factor, the SS sub-pixels of a row are evaluated in lock step (J = SS);
 // SS == 0: runtime supersampling factor, one sub-pixel at a time.
-template <int NSLOT, bool FULL, int SS>
-__global__ void __launch_bounds__(kBlock, 2)
+// LT / GT: compile-time lists of the (prepared) lens / light profile types, or RuntimeTypes.  A plan whose model
+// matches one of the registered signatures (lsim_api.cu) runs a kernel in which both lists are constants: the
+// profile loops unroll, the type dispatch disappears and the per-set constants are read at fixed shared-memory
+// offsets.  Any other model runs the RuntimeTypes instantiation (same code, interpreted).
+#ifndef LSIM_IMAGE_MIN_BLOCKS
+#define LSIM_IMAGE_MIN_BLOCKS 2
+#endif
+template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = RuntimeTypes>
+__global__ void __launch_bounds__(kBlock, LSIM_IMAGE_MIN_BLOCKS)
 k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, double out_scale,
         double* __restrict__ out) {
   constexpr int J = SS > 0 ? SS : 1;
@@ -184,21 +191,27 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
           y[j] = __ldg(P.y_sub + base + j0 + j);
           ray_init(P.ray, j, x[j], y[j], r);
         }
-        ray_apply<FULL, J>(P.ray, L, pool, P.n_lens, r);
+        ray_apply<FULL, J, LT>(P.ray, L, pool, P.n_lens, r);
 #pragma unroll
         for (int j = 0; j < J; ++j) ray_finish(P.ray, r, j, bx[j], by[j]);
-        for (int g = 0; g < P.n_light; ++g) {
-          const int slot = G[g].slot;
-          if (slot < 0) continue;
-          if (G[g].lensed)
-            light_eval<J>(G[g], bx, by, v);
+        auto one_light = [&](int type, const LightC& Gg) {
+          const int slot = Gg.slot;
+          if (slot < 0) return;
+          if (Gg.lensed)
+            light_eval<J>(type, Gg, bx, by, v);
           else
-            light_eval<J>(G[g], x, y, v);
+            light_eval<J>(type, Gg, x, y, v);
           double vs = v[0];
 #pragma unroll
           for (int j = 1; j < J; ++j) vs += v[j];
 #pragma unroll
           for (int k = 0; k < NSLOT; ++k) racc[k] += (slot == k) ? vs : 0.0;
+        };
+        if (GT::N >= 0) {
+#pragma unroll
+          for (int g = 0; g < GT::N; ++g) one_light(GT::at(g), G[g]);
+        } else {
+          for (int g = 0; g < P.n_light; ++g) one_light(G[g].type, G[g]);
         }
       }
 #pragma unroll
@@ -486,6 +499,8 @@ __device__ inline bool lu_solve(double* m, double* r, int n) {
 //   logL = -1/2 sum mask (model - data)^2 / C_D(model)                    (imaging_data.py:159-182)
 //          C_D(model) = noise_map^2  or  max(model,0)/t_exp + sigma_bkg^2 (image_noise.py:99-137)
 //   marg != 0: + 1/2 sign log|det M^-1|, -1e15 if singular               (de_lens.py:39-49)
+constexpr int kLikeUnroll = 4;
+
 template <int NS>
 __global__ void __launch_bounds__(kBlock)
 k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linear, int marg, double* __restrict__ logl,
@@ -503,20 +518,32 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
     double acc[NM + NS];
 #pragma unroll
     for (int i = 0; i < NM + NS; ++i) acc[i] = 0.0;
-    for (int p = threadIdx.x; p < npix; p += kBlock) {
-      if (P.mask && !P.mask[p]) continue;
-      double a[NS];
+    // 4 pixels per thread per trip: all loads of a trip are issued before any arithmetic (latency hiding)
+    for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kBlock) {
+      double a[kLikeUnroll][NS], wgt[kLikeUnroll], dat[kLikeUnroll];
 #pragma unroll
-      for (int k = 0; k < NS; ++k) a[k] = (k < ns) ? nan_to_num(A[(int64_t)k * npix + p]) : 0.0;
-      const double wgt = P.w_data[p], wd = wgt * P.data[p];
-      int m = 0;
+      for (int u = 0; u < kLikeUnroll; ++u) {
+        const int p = p0 + u * kBlock;
+        const bool use = p < npix && (!P.mask || P.mask[p]);
+        wgt[u] = use ? __ldg(P.w_data + p) : 0.0;  // masked / out-of-range pixels get zero weight
+        dat[u] = use ? __ldg(P.data + p) : 0.0;
 #pragma unroll
-      for (int i = 0; i < NS; ++i) {
-#pragma unroll
-        for (int j = i; j < NS; ++j) acc[m++] += wgt * a[i] * a[j];
+        for (int k = 0; k < NS; ++k) a[u][k] = (use && k < ns) ? A[(int64_t)k * npix + p] : 0.0;
       }
 #pragma unroll
-      for (int i = 0; i < NS; ++i) acc[NM + i] += wd * a[i];
+      for (int u = 0; u < kLikeUnroll; ++u) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) a[u][k] = nan_to_num(a[u][k]);
+        const double wd = wgt[u] * dat[u];
+        int m = 0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+#pragma unroll
+          for (int j = i; j < NS; ++j) acc[m++] += wgt[u] * a[u][i] * a[u][j];
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) acc[NM + i] += wd * a[u][i];
+      }
     }
     block_sum(acc, scratch);
     if (threadIdx.x == 0) {
@@ -556,23 +583,35 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
   }
 
   double chi[1] = {0.0};
-  for (int p = threadIdx.x; p < npix; p += kBlock) {
-    const bool use = !P.mask || P.mask[p];
-    double mdl = 0.0;
-    if (linear) {
-      if (use) {
+  for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kBlock) {
+    double mdl[kLikeUnroll], dat[kLikeUnroll], aux[kLikeUnroll];
+    bool use[kLikeUnroll], valid[kLikeUnroll];
+#pragma unroll
+    for (int u = 0; u < kLikeUnroll; ++u) {
+      const int p = p0 + u * kBlock;
+      valid[u] = p < npix;
+      use[u] = valid[u] && (!P.mask || P.mask[p]);
+      dat[u] = use[u] ? __ldg(P.data + p) : 0.0;
+      aux[u] = use[u] ? (P.noise_map2 ? __ldg(P.noise_map2 + p) : __ldg(P.inv_exposure + p)) : 1.0;
+      double m = 0.0;
+      if (linear) {
 #pragma unroll
         for (int k = 0; k < NS; ++k)
-          if (k < ns) mdl += s_amp[k] * nan_to_num(A[(int64_t)k * npix + p]);
+          if (k < ns && use[u]) m += s_amp[k] * nan_to_num(A[(int64_t)k * npix + p]);
+      } else if (valid[u]) {
+        for (int k = 0; k < ns; ++k) m += A[(int64_t)k * npix + p];
       }
-    } else {
-      for (int k = 0; k < ns; ++k) mdl += A[(int64_t)k * npix + p];
+      mdl[u] = m;
     }
-    if (model_out) model_out[(set0 + bl) * npix + p] = mdl;
-    if (use) {
-      const double cd = P.noise_map2 ? P.noise_map2[p] : fmax(mdl, 0.0) * P.inv_exposure[p] + P.bkg2;
-      const double d = mdl - P.data[p];
-      chi[0] += d * d / cd;
+#pragma unroll
+    for (int u = 0; u < kLikeUnroll; ++u) {
+      const int p = p0 + u * kBlock;
+      if (model_out && valid[u]) model_out[(set0 + bl) * npix + p] = mdl[u];
+      if (use[u]) {
+        const double cd = P.noise_map2 ? aux[u] : fma(fmax(mdl[u], 0.0), aux[u], P.bkg2);
+        const double d = mdl[u] - dat[u];
+        chi[0] += d * d / cd;
+      }
     }
   }
   block_sum(chi, scratch);

@@ -474,10 +474,13 @@ LSIM_HD void lens_prepare(const lsim_lens_desc& d, const double* row, LensC& L, 
 }
 
 // ---- lens: evaluate the reduced deflection of one profile at (x, y) ----------------------------------
+// `type` is passed explicitly (normally L.type) so that kernels specialised on a compile-time profile list
+// can pass a constant and let the compiler drop the dispatch.
 template <bool FULL>
-LSIM_HD void lens_eval1(const LensC& L, const double* coef_pool, double x, double y, double& fx, double& fy) {
+LSIM_HD void lens_eval1(int type, const LensC& L, const double* coef_pool, double x, double y, double& fx,
+                        double& fy) {
   const double xs = x - L.c[0], ys = y - L.c[1];
-  switch (L.type) {
+  switch (type) {
     case LSIM_LENS_EPL:
       epl_eval1(L, coef_pool + L.coef_off, xs, ys, fx, fy);
       return;
@@ -513,7 +516,7 @@ LSIM_HD void lens_eval1(const LensC& L, const double* coef_pool, double x, doubl
       break;
   }
   if (FULL) {
-    switch (L.type) {
+    switch (type) {
       case LSIM_LENS_EPL_MULTIPOLE_M1M3M4: {
         double ex, ey, mx, my;
         epl_eval1(L, coef_pool + L.coef_off, xs, ys, ex, ey);
@@ -559,10 +562,10 @@ LSIM_HD void lens_eval1(const LensC& L, const double* coef_pool, double x, doubl
         const double cph = L.c[2], sph = L.c[3], q = L.c[4];
         double xr = xs * cph + ys * sph, yr = -xs * sph + ys * cph;
         double gx, gy;
-        if (L.type == LSIM_LENS_CSE) {
+        if (type == LSIM_LENS_CSE) {
           double a = L.c[5], s = L.c[6];
           cse_set_eval(xr, yr, q, &a, &s, 1, !(L.flags & LSIM_FLAG_CSE_MAJOR), gx, gy);
-        } else if (L.type == LSIM_LENS_NFW_ELLIPSE_CSE) {
+        } else if (type == LSIM_LENS_NFW_ELLIPSE_CSE) {
           bool low = (L.flags & LSIM_FLAG_CSE_LOW_ACCURACY) != 0;
           double iRs = 1.0 / L.c[5];
           cse_set_eval(xr * iRs, yr * iRs, q, cse_table(low ? 3 : 1), cse_table(low ? 2 : 0),
@@ -589,9 +592,9 @@ LSIM_HD void lens_eval1(const LensC& L, const double* coef_pool, double x, doubl
 
 // J points at once: the hot profiles (EPL, SHEAR) are evaluated in lock step, everything else point by point.
 template <bool FULL, int J>
-LSIM_HD void lens_eval(const LensC& L, const double* coef_pool, const double (&x)[J], const double (&y)[J],
-                       double (&fx)[J], double (&fy)[J]) {
-  if (L.type == LSIM_LENS_EPL) {
+LSIM_HD void lens_eval(int type, const LensC& L, const double* coef_pool, const double (&x)[J],
+                       const double (&y)[J], double (&fx)[J], double (&fy)[J]) {
+  if (type == LSIM_LENS_EPL) {
     double xs[J], ys[J];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -603,7 +606,7 @@ LSIM_HD void lens_eval(const LensC& L, const double* coef_pool, const double (&x
     epl_eval<J>(L, coef_pool + L.coef_off, xs, ys, fx, fy);
     return;
   }
-  if (L.type == LSIM_LENS_SHEAR) {
+  if (type == LSIM_LENS_SHEAR) {
     const double g1 = L.c[2], g2 = L.c[3];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -618,8 +621,23 @@ LSIM_HD void lens_eval(const LensC& L, const double* coef_pool, const double (&x
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int j = 0; j < J; ++j) lens_eval1<FULL>(L, coef_pool, x[j], y[j], fx[j], fy[j]);
+  for (int j = 0; j < J; ++j) lens_eval1<FULL>(type, L, coef_pool, x[j], y[j], fx[j], fy[j]);
 }
+
+// Compile-time list of effective profile types (LensC::type / LightC::type after *_prepare).  N < 0 means
+// "not known at compile time": loops run over the runtime count and dispatch on the prepared type.
+template <int... T>
+struct TypeList {
+  static constexpr int N = sizeof...(T);
+  LSIM_HD static constexpr int at(int i) {
+    constexpr int v[sizeof...(T) + 1] = {T..., 0};
+    return v[i];
+  }
+};
+struct RuntimeTypes {
+  static constexpr int N = -1;
+  LSIM_HD static constexpr int at(int) { return -1; }
+};
 
 // true when the profile needs the FULL kernel variant
 LSIM_HD bool lens_type_is_full(int type) {
@@ -657,12 +675,29 @@ struct Rays {
   double ax[J], ay[J];  // single plane: accumulated deflection; multi plane: current angle
 };
 
-template <bool FULL, int J>
+template <bool FULL, int J, class LT = RuntimeTypes>
 LSIM_HD void ray_apply(const RayCfg& P, const LensC* L, const double* pool, int n_c, Rays<J>& r) {
   double fx[J], fy[J];
+  if (LT::N >= 0) {
+    // single plane, profile list known at compile time: fully unrolled, no dispatch
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int l = 0; l < LT::N; ++l) {
+      lens_eval<FULL, J>(LT::at(l), L[l], pool, r.x, r.y, fx, fy);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < J; ++j) {
+        r.ax[j] += fx[j];
+        r.ay[j] += fy[j];
+      }
+    }
+    return;
+  }
   if (!P.multi_plane) {
     for (int l = 0; l < n_c; ++l) {
-      lens_eval<FULL, J>(L[l], pool, r.x, r.y, fx, fy);
+      lens_eval<FULL, J>(L[l].type, L[l], pool, r.x, r.y, fx, fy);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -684,7 +719,7 @@ LSIM_HD void ray_apply(const RayCfg& P, const LensC* L, const double* pool, int 
         tx[j] = r.x[j] * L[l].inv_T_z;
         ty[j] = r.y[j] * L[l].inv_T_z;
       }
-      lens_eval<FULL, J>(L[l], pool, tx, ty, fx, fy);
+      lens_eval<FULL, J>(L[l].type, L[l], pool, tx, ty, fx, fy);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -781,8 +816,8 @@ LSIM_HD void light_prepare(const lsim_light_desc& d, const double* row, LightC& 
 // J points at once (sersic_utils.py:247-267 with R^2 in place of R: no square root is needed because
 // (R/Rs)^(1/n) = exp2(log2(R^2)/(2n) - log2(Rs)/n)).
 template <int J>
-LSIM_HD void light_eval(const LightC& G, const double (&x)[J], const double (&y)[J], double (&v)[J]) {
-  if (G.type == LSIM_LIGHT_SERSIC_ELLIPSE) {
+LSIM_HD void light_eval(int type, const LightC& G, const double (&x)[J], const double (&y)[J], double (&v)[J]) {
+  if (type == LSIM_LIGHT_SERSIC_ELLIPSE) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -812,7 +847,7 @@ LSIM_HD void light_eval(const LightC& G, const double (&x)[J], const double (&y)
 LSIM_HD double light_eval(const LightC& G, double x, double y) {
   const double x1[1] = {x}, y1[1] = {y};
   double v1[1];
-  light_eval<1>(G, x1, y1, v1);
+  light_eval<1>(G.type, G, x1, y1, v1);
   return v1[0];
 }
 
