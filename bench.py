@@ -214,7 +214,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = args.cpu_images if args.cpu_images else 2 * cores
+    n = args.cpu_images if args.cpu_images else 8 * cores
     vals = []
     for _ in range(args.warmup):
         cpu_images_per_s(cores, cores)
@@ -304,7 +304,7 @@ def run_gpu(args):
     if rank == 0:
         peak = _lib.measure_fp64_peak(400000)
         _lib.set_timing(True)
-        step_device()
+        model.logL_linear_batch(shard, out=logl_all[lo:hi])  # local work only: no collective outside the timed steps
         torch.cuda.synchronize()
         tm = _lib.get_timing()
         _lib.set_timing(False)
@@ -323,7 +323,7 @@ def run_gpu(args):
                 "whole_step_frac": value / world * FLOP_PER_IMAGE / peak}
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            n = args.cpu_images if args.cpu_images else 2 * cores
+            n = args.cpu_images if args.cpu_images else 16 * cores
             v, dt = cpu_images_per_s(n, cores)
             cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": "%d parameter sets of the same workload, NumPy oracle restatement, one process per core, "
