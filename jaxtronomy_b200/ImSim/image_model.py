@@ -74,15 +74,18 @@ class ImageModel(object):
                     exposure=getattr(d, "exposure_map", None), background_rms=d.background_rms,
                     mask=None if bool(np.all(self.likelihood_mask)) else self.likelihood_mask)
 
-    def _build_plan(self, source_slots, lens_light_slots, n_slots, use_amp, unconvolved, lensed=True):
+    def _build_plan(self, source_slots, lens_light_slots, n_slots, use_amp, unconvolved, lensed=True,
+                    source_fn=None, n_cols=None):
         layout = _model.ColumnLayout()
-        lens_descs = self.LensModel.lens_descs(layout)  # always registers the lens columns
+        lens_descs = self.LensModel.lens_descs(layout, source_fn=source_fn)  # always registers the lens columns
         if not lensed:
             lens_descs = []
-        light = self.SourceModel.light_descs(layout, "source", lensed=lensed, slots=source_slots, use_amp=use_amp)
+        light = self.SourceModel.light_descs(layout, "source", lensed=lensed, slots=source_slots, use_amp=use_amp,
+                                             source_fn=source_fn)
         light += self.LensLightModel.light_descs(layout, "lens_light", lensed=False, slots=lens_light_slots,
-                                                 use_amp=use_amp)
-        return _lib.Plan(layout.n_cols, lens_descs=lens_descs, light_descs=light, n_slots=n_slots,
+                                                 use_amp=use_amp, source_fn=source_fn)
+        return _lib.Plan(layout.n_cols if n_cols is None else n_cols, lens_descs=lens_descs, light_descs=light,
+                         n_slots=n_slots,
                          grid=self.ImageNumerics.grid_dict(), psf=self.ImageNumerics.psf_dict(unconvolved),
                          image_scale=self.ImageNumerics.pixel_area * self._flux_scaling, data=self._data_dict(),
                          **self.LensModel.plan_kwargs())
@@ -95,6 +98,22 @@ class ImageModel(object):
                                                 [0 if b else -1 for b in lens_light_bool], 1, True, unconvolved,
                                                 lensed=not de_lensed)
         return self._plans[key]
+
+    def sampler_plan(self, source_fn, n_cols, linear_solver):
+        """Plan for the sampler boundary: ``source_fn`` maps every model parameter to a column of the sampler's
+        `positions` matrix or to a constant (Param.args2kwargs, Sampling/likelihood.py:305)."""
+        ns, nl = self.SourceModel._num_func, self.LensLightModel._num_func
+        if linear_solver:
+            n_slots = max(ns + nl, 1)
+            if n_slots > _lib.MAX_SLOTS:
+                raise ValueError("at most %d linear components are supported" % _lib.MAX_SLOTS)
+            return self._build_plan(list(range(ns)), [ns + i for i in range(nl)], n_slots, False, False,
+                                    source_fn=source_fn, n_cols=n_cols)
+        return self._build_plan([0] * ns, [0] * nl, 1, True, False, source_fn=source_fn, n_cols=n_cols)
+
+    def sampler_plans(self, param_class, n_cols, linear_solver, index_lists=None):
+        """List of plans whose log-likelihoods add up to this model's (one entry for a single band)."""
+        return [self.sampler_plan(param_class.column_source_fn(index_lists), n_cols, linear_solver)]
 
     def _pack(self, kwargs_lens, kwargs_source, kwargs_lens_light):
         values = _model.gather_values(self.LensModel.param_name_list, kwargs_lens or [], "lens")

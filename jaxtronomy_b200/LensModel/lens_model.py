@@ -112,10 +112,15 @@ class LensModel(object):
         return convert_bool_list(n=self._num_func, k=k)
 
     # -- descriptors (shared with ImageModel) -----------------------------------------------------------
-    def lens_descs(self, layout, bool_list=None):
+    def lens_descs(self, layout, bool_list=None, source_fn=None):
         """Append this model's parameters to `layout` (one column each) and return the descriptors of the
-        selected profiles, in evaluation order (redshift-sorted for multi plane)."""
-        sources = [layout.add_profile("lens", i, names) for i, names in enumerate(self.param_name_list)]
+        selected profiles, in evaluation order (redshift-sorted for multi plane).  With ``source_fn(component, i,
+        names) -> [("col", j) | ("cst", value), ...]`` the caller decides where every parameter comes from
+        (sampler boundary: sampled parameters are columns of `positions`, fixed ones constants)."""
+        if source_fn is not None:
+            sources = [source_fn("lens", i, names) for i, names in enumerate(self.param_name_list)]
+        else:
+            sources = [layout.add_profile("lens", i, names) for i, names in enumerate(self.param_name_list)]
         if bool_list is None:
             bool_list = [True] * self._num_func
         descs = []

@@ -36,11 +36,14 @@ class LightModel(object):
         _model.gather_values(self.param_name_list, kwargs_list, "light")
 
     # -- descriptors (shared with ImageModel) -----------------------------------------------------------
-    def light_descs(self, layout, component, lensed, slots, use_amp):
-        """slots: per profile, the output slot or -1."""
+    def light_descs(self, layout, component, lensed, slots, use_amp, source_fn=None):
+        """slots: per profile, the output slot or -1.  ``source_fn``: see LensModel.lens_descs."""
         descs = []
         for i, name in enumerate(self.profile_type_list):
-            src = layout.add_profile(component, i, self.param_name_list[i])
+            if source_fn is not None:
+                src = source_fn(component, i, self.param_name_list[i])
+            else:
+                src = layout.add_profile(component, i, self.param_name_list[i])
             descs.append(_model.light_desc(name, src, lensed=lensed, slot=slots[i], use_amp=use_amp))
         return descs
 

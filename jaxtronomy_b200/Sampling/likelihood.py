@@ -1,0 +1,80 @@
+"""LikelihoodModule: flat sampler vector -> log-likelihood, jaxtronomy/Sampling/likelihood.py:293-405 and
+Sampling/Likelihoods/image_likelihood.py:56-96 for the imaging likelihood (no priors / position / custom terms:
+out of scope).
+
+The reference evaluates ``jit(vmap(logL))`` over the particle axis (Sampling/sampler.py:241-246).  Here the whole
+``positions[B, n]`` matrix goes to the GPU as is: the plan's column map *is* ``Param.args2kwargs``, the bound check
+is a reduction over the matrix, and one lsim_logl call returns ``logL[B]``.
+"""
+
+import numpy as np
+
+from jaxtronomy_b200 import _lib
+
+__all__ = ["LikelihoodModule"]
+
+
+class LikelihoodModule(object):
+    def __init__(self, image_model, param_class, check_bounds=True, source_marg=False, linear_solver=True):
+        """
+        :param image_model: ImageModel / ImageLinearFit / MultiLinear instance (the imaging likelihood)
+        :param param_class: jaxtronomy_b200.Sampling.parameters.Param
+        """
+        self.imSim = image_model
+        self.param = param_class
+        self._check_bounds = check_bounds
+        self._source_marg = source_marg
+        self._linear_solver = linear_solver
+        self._lower_limit, self._upper_limit = self.param.param_limits()
+        self._n = self.param.num_param()[0]
+        self._bounds_dev = None
+        self._plans = self.imSim.sampler_plans(self.param, self._n, linear_solver)
+
+    def __call__(self, a):
+        return self.logL(a)
+
+    @staticmethod
+    def check_bounds(args, lowerLimit, upperLimit, verbose=False):
+        """likelihood.py:374-405 -> (penalty, bound_hit)"""
+        args = np.atleast_1d(np.asarray(args))
+        hit = bool(np.any((args < np.atleast_1d(lowerLimit)) | (args > np.atleast_1d(upperLimit))))
+        return (10.0**5 if hit else 0.0), hit
+
+    def logL(self, args, verbose=False):
+        """One parameter vector -> float (likelihood.py:293-319)."""
+        return float(self.logL_batch(np.asarray(args, dtype=float)[None, :])[0])
+
+    def logL_batch_device(self, positions, out=None):
+        """positions: [B, n] CUDA tensor -> logL [B] CUDA tensor on the current stream."""
+        import torch
+
+        total = None
+        for plan in self._plans:
+            l, _, _ = plan.logl(positions, linear_solve=self._linear_solver, source_marg=self._source_marg)
+            l = torch.where(torch.isnan(l), torch.full_like(l, -(10.0**15)), l)  # image_likelihood.py:95
+            total = l if total is None else total + l
+        if self._check_bounds:
+            if self._bounds_dev is None or self._bounds_dev[0].device != positions.device:
+                self._bounds_dev = (torch.as_tensor(self._lower_limit, device=positions.device),
+                                    torch.as_tensor(self._upper_limit, device=positions.device))
+            lo, hi = self._bounds_dev
+            hit = ((positions < lo) | (positions > hi)).any(dim=1)
+            total = torch.where(hit, torch.full_like(total, -(10.0**18)), total)
+        total = torch.where(torch.isnan(total), torch.full_like(total, 1e-18), total)  # likelihood.py:370
+        if out is not None:
+            out.copy_(total)
+            return out
+        return total
+
+    def logL_batch(self, positions):
+        """positions: [B, n] NumPy array -> logL NumPy array [B] (the `new_logL_func` of prepare_logL_func)."""
+        import torch
+
+        pos = torch.as_tensor(np.ascontiguousarray(positions, dtype=np.float64)).to("cuda")
+        if pos.ndim != 2 or pos.shape[1] != self._n:
+            raise _lib.LsimError("positions must be [B, %d]" % self._n)
+        return self.logL_batch_device(pos).cpu().numpy()
+
+    @property
+    def num_data(self):
+        return self.imSim.num_data_evaluate

@@ -1,0 +1,109 @@
+"""GPU: the sampler boundary (LikelihoodModule / prepare_logL_func) and multi-band likelihood, through the C ABI."""
+
+import numpy as np
+import pytest
+
+from tests.golden_io import load
+
+pytestmark = pytest.mark.gpu
+IMSIM = load("imsim.npz")
+
+
+def _setup(case="headline_epl_shear_pixel"):
+    from jaxtronomy_b200.Sampling.likelihood import LikelihoodModule
+    from jaxtronomy_b200.Sampling.parameters import Param
+    from tests.test_gpu_parity import build_image_model
+
+    c = IMSIM[case]
+    lin = build_image_model(c, linear=True)
+    km = dict(lens_model_list=c.meta["lens_model_list"], source_light_model_list=c.meta["source_model_list"],
+              lens_light_model_list=c.meta["lens_light_model_list"])
+    fixed_lens = [{} for _ in c.meta["lens_model_list"]]
+    fixed_lens[-1] = {"ra_0": 0.0, "dec_0": 0.0}
+    param = Param(km, kwargs_fixed_lens=fixed_lens, kwargs_lower_lens=[{"theta_E": 0.6}, {}],
+                  kwargs_upper_lens=[{"theta_E": 1.6}, {}])
+    return c, lin, param, LikelihoodModule(lin, param)
+
+
+def test_likelihood_module_batch_matches_kwargs_path():
+    c, lin, param, like = _setup()
+    kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
+    x0 = param.kwargs2args(kl, ks, kll)
+    rng = np.random.default_rng(4)
+    B = 37
+    pos = x0[None, :] + rng.normal(0, 0.01, (B, x0.size))
+    pos[5, 0] = 5.0    # theta_E above its upper bound
+    pos[9, 1] = 0.2    # gamma below the default lower bound 1.5
+    logl = like.logL_batch(pos)
+    assert logl.shape == (B,)
+    assert logl[5] == -1e18 and logl[9] == -1e18          # likelihood.py:312-315
+    for b in (0, 6, 36):
+        kw = param.args2kwargs(pos[b])
+        want, _ = lin.likelihood_data_given_model(kw["kwargs_lens"], kw["kwargs_source"], kw["kwargs_lens_light"])
+        assert abs(logl[b] - want) <= 1e-12 * abs(want), (b, logl[b], want)
+    assert like.logL(pos[0]) == logl[0]
+    # against the reference fixture at the fixture's own parameters
+    assert abs(like.logL(x0) - float(c.out["logL_linear"])) <= 1e-10 * abs(float(c.out["logL_linear"]))
+
+
+def test_prepare_logL_func_and_pso_improve_the_fit():
+    from jaxtronomy_b200.Sampling.sampler import ParticleSwarmOptimizer, prepare_logL_func
+
+    c, lin, param, like = _setup()
+    f = prepare_logL_func("gpu", like)
+    x0 = param.kwargs2args(c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"])
+    lo, hi = x0 - 0.05, x0 + 0.05
+    pso = ParticleSwarmOptimizer(f, lo, hi, particle_count=64, seed=0)
+    best, hist, _ = pso.optimize(max_iter=15)
+    assert np.all(np.diff(hist) >= 0)
+    assert hist[-1] > hist[0]
+    assert hist[-1] >= like.logL(x0) - 50.0
+
+
+def test_multi_band_likelihood_is_the_sum_of_bands():
+    """Two bands with different data / PSF / supersampling sharing the lens and source, each with its own lens
+    light (index lists), against the oracle evaluated per band (multi_linear.py:112-161)."""
+    from jaxtronomy_b200.ImSim.MultiBand.multi_linear import MultiLinear
+    from jaxtronomy_b200.Sampling.likelihood import LikelihoodModule
+    from jaxtronomy_b200.Sampling.parameters import Param
+    from jaxtronomy_b200.Util import simulation_util
+    from oracle import imsim as oimsim
+    from oracle.lenstronomy_port import PSF as OPSF
+
+    rng = np.random.default_rng(21)
+    kl = [dict(theta_E=1.1, gamma=2.05, e1=0.2, e2=-0.1, center_x=0.02, center_y=-0.01),
+          dict(gamma1=0.03, gamma2=-0.02, ra_0=0.0, dec_0=0.0)]
+    ks = [dict(amp=12.0, R_sersic=0.25, n_sersic=2.0, e1=0.1, e2=0.1, center_x=0.05, center_y=0.1)]
+    kll = [dict(amp=20.0, R_sersic=0.5, n_sersic=3.0, e1=-0.1, e2=0.05, center_x=0.02, center_y=-0.01),
+           dict(amp=9.0, R_sersic=0.4, n_sersic=2.5, e1=0.0, e2=0.1, center_x=0.02, center_y=-0.01)]
+    km = dict(lens_model_list=["EPL", "SHEAR"], source_light_model_list=["SERSIC_ELLIPSE"],
+              lens_light_model_list=["SERSIC_ELLIPSE", "SERSIC_ELLIPSE"],
+              index_lens_light_model_list=[[0], [1]])
+    a = np.arange(7) - 3.0
+    kern = np.exp(-(a[:, None] ** 2 + a[None, :] ** 2) / 3.0)
+    bands, oracles = [], []
+    for band, (npx, dpx, ss, psf_kw) in enumerate([
+            (30, 0.1, 2, dict(psf_type="PIXEL", kernel_point_source=kern)),
+            (24, 0.12, 1, dict(psf_type="GAUSSIAN", fwhm=0.25, truncation=4))]):
+        kd = simulation_util.data_configure_simple(npx, dpx, 100.0, 0.05)
+        kd["image_data"] = rng.uniform(0, 1, (npx, npx))
+        bands.append([kd, psf_kw, dict(supersampling_factor=ss)])
+        od = oimsim.ImageData(**kd)
+        oracles.append(oimsim.ImageModel(od, OPSF(**psf_kw), km["lens_model_list"], km["source_light_model_list"],
+                                         [km["lens_light_model_list"][band]], dict(supersampling_factor=ss)))
+    ml = MultiLinear(bands, km)
+    logL, params = ml.likelihood_data_given_model(kl, ks, kll)
+    want, want_p = 0.0, []
+    for band, om in enumerate(oracles):
+        l, p = om.likelihood_data_given_model_linear(kl, ks, [kll[band]])
+        want += l
+        want_p.append(p)
+    assert abs(logL - want) <= 1e-10 * abs(want), (logL, want)
+    for p, wp in zip(params, want_p):
+        np.testing.assert_allclose(p, wp, rtol=1e-9)
+    # sampler boundary over both bands: one positions matrix, plans per band, sum on the device
+    param = Param(km)
+    like = LikelihoodModule(ml, param)
+    x0 = param.kwargs2args(kl, ks, kll)
+    got = like.logL_batch(np.stack([x0, x0]))
+    assert abs(got[0] - want) <= 1e-10 * abs(want) and got[0] == got[1]

@@ -180,3 +180,46 @@ def test_all_gather_logl_gloo_world2(n):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "OK" in o, o
+
+
+def test_param_mapping_round_trip():
+    from jaxtronomy_b200.Sampling.parameters import Param
+
+    km = dict(lens_model_list=["EPL", "SHEAR"], source_light_model_list=["SERSIC_ELLIPSE"],
+              lens_light_model_list=["SERSIC"])
+    p = Param(km, kwargs_fixed_lens=[{}, {"ra_0": 0, "dec_0": 0}], kwargs_fixed_lens_light=[{"n_sersic": 4.0}],
+              kwargs_lower_lens=[{"theta_E": 0.5}, {}], kwargs_upper_lens=[{"theta_E": 2.0}, {}])
+    n, names = p.num_param()
+    assert n == 6 + 2 + 6 + 3 and names[0] == "theta_E_lens0" and names[-1] == "center_y_lens_light0"
+    args = np.arange(n, dtype=float)
+    kw = p.args2kwargs(args)
+    assert kw["kwargs_lens"][1] == {"gamma1": 6.0, "gamma2": 7.0, "ra_0": 0, "dec_0": 0}
+    assert kw["kwargs_source"][0]["amp"] == 1 and kw["kwargs_lens_light"][0]["n_sersic"] == 4.0
+    np.testing.assert_array_equal(p.kwargs2args(kw["kwargs_lens"], kw["kwargs_source"], kw["kwargs_lens_light"]), args)
+    lo, hi = p.param_limits()
+    assert lo[0] == 0.5 and hi[0] == 2.0 and lo[1] == 1.5 and hi[1] == 2.5
+    # batched: [B, n] matrix -> [B] arrays per parameter
+    kwb = p.args2kwargs(np.stack([args, args + 1]))
+    np.testing.assert_array_equal(kwb["kwargs_lens"][0]["gamma"], [1.0, 2.0])
+    fn = p.column_source_fn()
+    assert fn("lens", 1, ["gamma1", "gamma2", "ra_0", "dec_0"]) == [("col", 6), ("col", 7), ("cst", 0.0), ("cst", 0.0)]
+    assert fn("source", 0, ["amp", "R_sersic"]) == [("cst", 1.0), ("col", 8)]
+    # band sub-model: local profile 0 of the band is global profile 1
+    fn2 = p.column_source_fn({"lens": [1], "source": None, "lens_light": None})
+    assert fn2("lens", 0, ["gamma1", "gamma2", "ra_0", "dec_0"])[0] == ("col", 6)
+    with pytest.raises(ValueError):
+        Param(km, kwargs_fixed_lens=[{}])
+    nolin = Param(km, linear_solver=False)
+    assert nolin.num_param()[0] == 6 + 4 + 7 + 5
+
+
+def test_pso_runs_on_a_toy_likelihood():
+    from jaxtronomy_b200.Sampling.sampler import ParticleSwarmOptimizer, prepare_logL_func
+
+    pso = ParticleSwarmOptimizer(lambda x: -np.sum((x - 0.3) ** 2, axis=1), [-1, -1], [1, 1], particle_count=32, seed=1)
+    best, hist, _ = pso.optimize(max_iter=60)
+    assert hist[-1] >= hist[0] and np.allclose(best, 0.3, atol=1e-2)
+    with pytest.raises(ValueError):
+        prepare_logL_func("cpu", None)
+    with pytest.raises(ValueError):
+        prepare_logL_func("tpu", None)

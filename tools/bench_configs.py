@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""Secondary measurements on the other BASELINE.json configurations (one GPU).  Not the driver's bench line
+(that is bench.py); these feed profiles/r1_configs.md.
+
+    python tools/bench_configs.py [c2] [c3] [c4] [c5]
+"""
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from bench import psf_kernel, static_config  # noqa: E402
+from jaxtronomy_b200 import _lib  # noqa: E402
+from jaxtronomy_b200.Data.imaging_data import ImageData  # noqa: E402
+from jaxtronomy_b200.Data.psf import PSF  # noqa: E402
+from jaxtronomy_b200.ImSim.image_linear_solve import ImageLinearFit  # noqa: E402
+from jaxtronomy_b200.ImSim.MultiBand.multi_linear import MultiLinear  # noqa: E402
+from jaxtronomy_b200.ImSim.Numerics.grid import RegularGrid  # noqa: E402
+from jaxtronomy_b200.LensModel.lens_model import LensModel  # noqa: E402
+from jaxtronomy_b200.LensModel.lens_model_bulk import LensModelBulk  # noqa: E402
+from jaxtronomy_b200.LightModel.light_model import LightModel  # noqa: E402
+from jaxtronomy_b200.Sampling.likelihood import LikelihoodModule  # noqa: E402
+from jaxtronomy_b200.Sampling.parameters import Param  # noqa: E402
+
+
+def timed(fn, steps=3, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def c2():
+    """EPL+SHEAR ray shooting, 180x180 ss 3 grid, 1024 parameter sets."""
+    st = static_config()
+    grid = RegularGrid(180, 180, st["kwargs_data"]["transform_pix2angle"], st["kwargs_data"]["ra_at_xy_0"],
+                       st["kwargs_data"]["dec_at_xy_0"], 3)
+    x, y = grid.coordinates_evaluate
+    xt, yt = torch.as_tensor(x, device="cuda"), torch.as_tensor(y, device="cuda")
+    rng = np.random.default_rng(1)
+    B = 1024
+    em, ea = rng.uniform(0.15, 0.35, B), rng.uniform(0, 2 * np.pi, B)
+    kw = [dict(theta_E=torch.as_tensor(rng.uniform(0.8, 1.6, B), device="cuda"),
+               gamma=torch.as_tensor(rng.uniform(1.7, 2.3, B), device="cuda"),
+               e1=torch.as_tensor(em * np.cos(ea), device="cuda"), e2=torch.as_tensor(em * np.sin(ea), device="cuda"),
+               center_x=0.0, center_y=0.0),
+          dict(gamma1=torch.as_tensor(rng.uniform(-0.08, 0.08, B), device="cuda"), gamma2=0.01, ra_0=0.0, dec_0=0.0)]
+    lm = LensModel(["EPL", "SHEAR"])
+    ms = timed(lambda: lm.ray_shooting(xt, yt, kw))
+    n = B * x.size
+    return dict(config="C2 EPL+SHEAR ray shooting 180x180 ss3 x 1024 sets", ms=ms, rays_per_s=n / ms * 1e3,
+                sets_per_s=B / ms * 1e3, out_GBps=n * 16 / ms / 1e6,
+                fp64_TFLOPs_algorithmic=n * 418 / ms / 1e9)
+
+
+def c3():
+    """EPL_MULTIPOLE_M1M3M4+SHEAR, SERSIC_ELLIPSE source + lens light, 21x21 pixel PSF, ImageLinearFit, 8192 sets."""
+    st = static_config()
+    rng = np.random.default_rng(2)
+    data = ImageData(image_data=rng.normal(0, 0.05, (180, 180)) + 0.1, **st["kwargs_data"])
+    psf = PSF(psf_type="PIXEL", kernel_point_source=psf_kernel(21))
+    km = dict(lens_model_list=["EPL_MULTIPOLE_M1M3M4", "SHEAR"], source_light_model_list=["SERSIC_ELLIPSE"],
+              lens_light_model_list=["SERSIC_ELLIPSE"])
+    lin = ImageLinearFit(data, psf, LensModel(km["lens_model_list"]), LightModel(km["source_light_model_list"]),
+                         LightModel(km["lens_light_model_list"]), kwargs_numerics=dict(supersampling_factor=3))
+    param = Param(km, kwargs_fixed_lens=[{}, {"ra_0": 0.0, "dec_0": 0.0}])
+    like = LikelihoodModule(lin, param)
+    lo, hi = param.param_limits()
+    B = 8192
+    kl = [dict(theta_E=1.2, gamma=2.0, e1=0.2, e2=-0.1, center_x=0.0, center_y=0.0, a1_a=0.01, delta_phi_m1=0.1,
+               a3_a=0.01, delta_phi_m3=0.1, a4_a=0.01, delta_phi_m4=0.1), dict(gamma1=0.03, gamma2=0.01, ra_0=0, dec_0=0)]
+    ks = [dict(amp=1, R_sersic=0.3, n_sersic=2.0, e1=0.1, e2=0.1, center_x=0.05, center_y=0.0)]
+    kll = [dict(amp=1, R_sersic=0.6, n_sersic=3.0, e1=0.05, e2=0.0, center_x=0.0, center_y=0.0)]
+    x0 = param.kwargs2args(kl, ks, kll)
+    pos = torch.as_tensor(x0[None, :] + rng.normal(0, 0.02, (B, x0.size)), device="cuda")
+    ms = timed(lambda: like.logL_batch_device(pos))
+    flop = 291600 * (713 + 3 * 80) + 32400 * (1764 + 10 + 24 + 4)
+    return dict(config="C3 EPL_MULTIPOLE_M1M3M4+SHEAR, 2 SERSIC_ELLIPSE (n_lin=2), 21x21 PSF, 8192 sets", ms=ms,
+                images_per_s=B / ms * 1e3, fp64_TFLOPs_algorithmic=B * flop / ms / 1e9)
+
+
+def c4():
+    """1 EPL + 1000 TNFW on a 1000x1000 ray grid (substructure notebook shape)."""
+    rng = np.random.default_rng(3)
+    nh = 1000
+    names = ["EPL"] + ["TNFW"] * nh
+    kws = [dict(theta_E=1.0, gamma=2.0, e1=0.1, e2=0.1, center_x=0.0, center_y=0.0)]
+    kws += [dict(Rs=float(rng.uniform(0.01, 0.1)), alpha_Rs=float(rng.uniform(1e-4, 5e-3)),
+                 r_trunc=float(rng.uniform(0.05, 0.5)), center_x=float(rng.uniform(-2, 2)),
+                 center_y=float(rng.uniform(-2, 2))) for _ in range(nh)]
+    g = np.linspace(-2, 2, 1000)
+    xx, yy = np.meshgrid(g, g)
+    xt, yt = torch.as_tensor(xx.ravel(), device="cuda"), torch.as_tensor(yy.ravel(), device="cuda")
+    lmb = LensModelBulk(["EPL", "TNFW"], multi_plane=False)
+    rs = lmb.prepare_ray_shooting_kwargs(names, kws)
+    ms = timed(lambda: lmb.ray_shooting(xt, yt, rs))
+    return dict(config="C4 EPL + 1000 TNFW, 1000x1000 rays", ms=ms, deflection_evals_per_s=1e6 * 1001 / ms * 1e3,
+                fp64_TFLOPs_algorithmic=1e6 * (404 + 1000 * 230) / ms / 1e9)
+
+
+def c5():
+    """3 planes (EPL, NFW_ELLIPSE_CSE, SIS), 4 bands of 180x180 (ss 1), 4096 sets, multi-band linear likelihood."""
+    rng = np.random.default_rng(4)
+    km = dict(lens_model_list=["EPL", "NFW_ELLIPSE_CSE", "SIS"], lens_redshift_list=[0.5, 0.3, 0.8], z_source=1.5,
+              multi_plane=True, source_light_model_list=["SERSIC_ELLIPSE"], lens_light_model_list=["SERSIC_ELLIPSE"])
+    st = static_config()
+    bands = []
+    for b in range(4):
+        kd = dict(st["kwargs_data"], image_data=rng.normal(0, 0.05, (180, 180)) + 0.1)
+        bands.append([kd, dict(psf_type="PIXEL", kernel_point_source=psf_kernel(11, 1.5 + 0.2 * b)),
+                      dict(supersampling_factor=1)])
+    ml = MultiLinear(bands, km)
+    param = Param(km)
+    like = LikelihoodModule(ml, param)
+    kl = [dict(theta_E=1.1, gamma=2.0, e1=0.1, e2=-0.1, center_x=0.0, center_y=0.0),
+          dict(Rs=1.5, alpha_Rs=0.2, e1=0.05, e2=0.05, center_x=0.3, center_y=-0.2),
+          dict(theta_E=0.1, center_x=-0.5, center_y=0.4)]
+    ks = [dict(amp=1, R_sersic=0.3, n_sersic=2.0, e1=0.1, e2=0.1, center_x=0.05, center_y=0.0)]
+    kll = [dict(amp=1, R_sersic=0.6, n_sersic=3.0, e1=0.05, e2=0.0, center_x=0.0, center_y=0.0)]
+    x0 = param.kwargs2args(kl, ks, kll)
+    B = 4096
+    pos = torch.as_tensor(x0[None, :] + rng.normal(0, 0.01, (B, x0.size)), device="cuda")
+    ms = timed(lambda: like.logL_batch_device(pos), steps=2, warmup=1)
+    return dict(config="C5 multi-plane EPL+NFW_ELLIPSE_CSE+SIS, 4 bands 180x180 ss1, 4096 sets", ms=ms,
+                band_images_per_s=4 * B / ms * 1e3, sets_per_s=B / ms * 1e3)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c2", "c3", "c4", "c5"]
+    t0 = time.time()
+    for name in which:
+        out = globals()[name]()
+        out["launches_total"] = _lib.launch_count()
+        print(json.dumps(out), flush=True)
+    print("# wall %.1f s" % (time.time() - t0))
