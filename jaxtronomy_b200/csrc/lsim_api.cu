@@ -316,7 +316,7 @@ int launch_image_k(const lsim_plan* plan, const double* params, int64_t set0, in
                    double scale, double* out, cudaStream_t st) {
   dim3 grid((unsigned)tiles, (unsigned)n);
   Timed timed(kClsImage, st);
-  k_image<NSLOT, FULL, SS, LT, GT><<<grid, kBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out);
+  k_image<NSLOT, FULL, SS, LT, GT><<<grid, kImageBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out);
   return after_launch("k_image");
 }
 
@@ -398,10 +398,10 @@ int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int6
                  cudaStream_t st) {
   const int npix = plan->dev.nx * plan->dev.ny;
   int64_t want = ((int64_t)plan->n_sm * 4 + n - 1) / n;  // CTAs per set so that the grid fills the chip
-  int max_tiles = (npix + kBlock - 1) / kBlock;
+  int max_tiles = (npix + kImageBlock - 1) / kImageBlock;
   int tiles = (int)(want < 1 ? 1 : (want > max_tiles ? max_tiles : want));
   int ppt = (npix + tiles - 1) / tiles;
-  ppt = ((ppt + kBlock - 1) / kBlock) * kBlock;
+  ppt = ((ppt + kImageBlock - 1) / kImageBlock) * kImageBlock;
   tiles = (npix + ppt - 1) / ppt;
   const int ns = plan->dev.n_slots;
   int rc = LSIM_E_UNSUPPORTED;

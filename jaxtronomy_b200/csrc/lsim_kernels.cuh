@@ -149,11 +149,16 @@ k_surface_brightness(PlanDev P, const double* __restrict__ params, const double*
 // matches one of the registered signatures (lsim_api.cu) runs a kernel in which both lists are constants: the
 // profile loops unroll, the type dispatch disappears and the per-set constants are read at fixed shared-memory
 // offsets.  Any other model runs the RuntimeTypes instantiation (same code, interpreted).
-#ifndef LSIM_IMAGE_MIN_BLOCKS
-#define LSIM_IMAGE_MIN_BLOCKS 2
+// CTA shape of the image kernel (tunable at build time; see profiles/r1_bench_log.md for the sweep)
+#ifndef LSIM_IMAGE_BLOCK
+#define LSIM_IMAGE_BLOCK 256
 #endif
+#ifndef LSIM_IMAGE_MIN_BLOCKS
+#define LSIM_IMAGE_MIN_BLOCKS 3  // 24 warps/SM at 80 registers (a few spilled values) beats 16 warps at 114
+#endif
+constexpr int kImageBlock = LSIM_IMAGE_BLOCK;
 template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = RuntimeTypes>
-__global__ void __launch_bounds__(kBlock, LSIM_IMAGE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kImageBlock, LSIM_IMAGE_MIN_BLOCKS)
 k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, double out_scale,
         double* __restrict__ out) {
   constexpr int J = SS > 0 ? SS : 1;
@@ -172,7 +177,7 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
   const int64_t sub_stride = (int64_t)P.nx * ss;
   const double inv_ss = 1.0 / ss;
   const int p_end = min(npix, (int)(blockIdx.x + 1) * ppt);
-  for (int p = blockIdx.x * ppt + threadIdx.x; p < p_end; p += kBlock) {
+  for (int p = blockIdx.x * ppt + threadIdx.x; p < p_end; p += kImageBlock) {
     const int py = p / P.nx, px = p - py * P.nx;
     double acc[NSLOT];
 #pragma unroll

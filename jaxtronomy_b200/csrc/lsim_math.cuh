@@ -18,6 +18,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "lsim_math_tables.h"
+
 #if defined(__CUDACC__)
 #define LSIM_HD __host__ __device__ __forceinline__
 #define LSIM_D __device__ __forceinline__
@@ -34,13 +36,21 @@ constexpr double kPi = 3.14159265358979323846;
 constexpr double kLog2e = 1.44269504088896340736;
 constexpr double kLn2 = 0.69314718055994530942;
 
-// atanh(s)/s = 1 + z/3 + z^2/5 + ...  (z = s^2): coefficients 1/(2k+1), k = 1..10, highest first
-LSIM_TABLE kAtanhC[10] = {1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0,
-                          1.0 / 11.0, 1.0 / 9.0,  1.0 / 7.0,  1.0 / 5.0,  1.0 / 3.0};
-// exp(r) Taylor coefficients 1/k!, k = 13..2, highest first
-LSIM_TABLE kExpC[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0,
-                        1.0 / 362880.0,     1.0 / 40320.0,     1.0 / 5040.0,     1.0 / 720.0,
-                        1.0 / 120.0,        1.0 / 24.0,        1.0 / 6.0,        0.5};
+// log2(1+u)/u = (1/ln2) (1 - u/2 + u^2/3 - ...): coefficients (-1)^(k+1)/(k ln2), k = 10..1, highest first
+LSIM_TABLE kLog2C[10] = {-kLog2e / 10.0, kLog2e / 9.0, -kLog2e / 8.0, kLog2e / 7.0, -kLog2e / 6.0,
+                         kLog2e / 5.0,   -kLog2e / 4.0, kLog2e / 3.0, -kLog2e / 2.0, kLog2e};
+// exp(y) Taylor coefficients 1/k!, k = 6..2, highest first
+LSIM_TABLE kExpC[5] = {1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+
+// Lookup tables (tools/gen_math_tables.py): exp2 T[j] = 2^(j/32); log2 {R[i], L[i]} = {~1/c_i, -log2 R[i]} for
+// the 32 bins of the mantissa.  On the device they live in global memory and are read through the read-only
+// L1 path: the index differs from lane to lane, which constant memory would serialise.
+#if defined(__CUDACC__)
+__device__ double d_exp2_tab[32] = LSIM_EXP2_TABLE;
+__device__ double d_log2_tab[64] = LSIM_LOG2_TABLE;
+#endif
+static const double h_exp2_tab[32] = LSIM_EXP2_TABLE;
+static const double h_log2_tab[64] = LSIM_LOG2_TABLE;
 
 LSIM_HD int64_t d2i(double x) {
 #if defined(__CUDA_ARCH__)
@@ -88,48 +98,54 @@ LSIM_HD double rcp_fast(double x) {
 
 // ---- fast fp64 log2 / exp2 --------------------------------------------------------------------------
 // The hot loop needs pow(x, s) = exp2(s * log2(x)) and exp(-b (k - 1)) for finite positive normal x.
-// libdevice's log/exp/pow carry special-case handling (denormals, inf/nan, exact rounding paths) that
-// costs more fp64-pipe instructions than the polynomial core.  These versions keep the core only:
-//   log2_pos(x): x positive, finite, normal.  |rel err| < 3e-16 on the result as a real number
-//                (abs err < 2e-16 near x = 1).
-//   exp2_fin(x): any x; underflows to 0 below -1022, +inf above 1024, nan -> nan.
+// libdevice's log/exp/pow carry special-case handling and long polynomials; on a kernel bound by the fp64 pipe
+// every DFMA counts, so both functions are table-driven here (32-entry tables, short Taylor polynomials):
+//   log2_pos(x): x positive, finite, normal.  12 fp64 instructions.  |abs err| < 3e-16 max(1, |log2 x|)
+//                (the result feeds exponents, where absolute accuracy is what matters).
+//   exp2_fin(x): any x; 10 fp64 instructions in the fast path; |rel err| < 4e-16; underflow / overflow / nan
+//                are delegated to the library.
 
-// log2(x) = e + log2(m), m in [sqrt(1/2), sqrt(2)); log(m) = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716
+// x = 2^e m, m in [1,2); bin i = top 5 mantissa bits; u = m R_i - 1, |u| <= 1/64;
+// log2 x = e + L_i + log2(1 + u)
 LSIM_HD double log2_pos(double x) {
-  int64_t ix = d2i(x);
-  const int64_t kSqrtHalfBits = 0x3fe6a09e667f3bcdLL;  // bits of sqrt(0.5)
-  int64_t e = (ix - kSqrtHalfBits) >> 52;              // exponent relative to sqrt(1/2)
-  double m = i2d(ix - (e << 52));                      // m in [sqrt(1/2), sqrt(2))
-  double num = m - 1.0, den = m + 1.0;
-  double r = rcp_fast(den);
-  double s = num * r;
-  s = fma(fma(-s, den, num), r, s);  // one correction step: s = num/den to < 1 ulp
-  double z = s * s;
-  double p = kAtanhC[0];
+  const int64_t ix = d2i(x);
+  const int e = (int)(ix >> 52) - 1023;
+  const double m = i2d((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const int i = (int)(ix >> 47) & 31;
+#if defined(__CUDA_ARCH__)
+  const double2 rl = __ldg(reinterpret_cast<const double2*>(d_log2_tab) + i);
+  const double R = rl.x, L = rl.y;
+#else
+  const double R = h_log2_tab[2 * i], L = h_log2_tab[2 * i + 1];
+#endif
+  const double u = fma(m, R, -1.0);
+  double p = kLog2C[0];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int k = 1; k < 10; ++k) p = fma(p, z, kAtanhC[k]);
-  // log2(m) = (2/ln2) * s * (1 + z p)
-  const double c = 2.0 * kLog2e;
-  double lm = fma(c, s * z * p, c * s);
-  return (double)(int)e + lm;
+  for (int k = 1; k < 10; ++k) p = fma(p, u, kLog2C[k]);
+  return (double)e + fma(u, p, L);
 }
 
-// exp2(x) = 2^n * 2^r, r = x - n in [-1/2, 1/2]; 2^r = exp(r ln2) by a degree-13 Taylor polynomial
+// x = k/32 + r, k = rint(32 x), |r| <= 1/64: 2^x = 2^(k>>5) T[k&31] exp(r ln2)
 LSIM_HD double exp2_fin(double x) {
   if (!(fabs(x) < 1021.0)) return exp2(x);  // rare: underflow / overflow / nan -> the library handles them
-  double n = rint(x);
-  int in = (int)n;
-  double r = (x - n) * kLn2;  // |r| <= 0.3466
+  const double kf = rint(x * 32.0);
+  const int ki = (int)kf;
+  const double y = fma(kf, -0.03125, x) * kLn2;  // r is exact; |y| <= 0.0109
   double p = kExpC[0];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int k = 1; k < 12; ++k) p = fma(p, r, kExpC[k]);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return i2d(d2i(p) + ((int64_t)in << 52));  // scale by 2^n: p in [0.7, 1.42], |n| <= 1021 -> stays normal
+  for (int k = 1; k < 5; ++k) p = fma(p, y, kExpC[k]);
+  p = fma(p, y, 1.0);
+  p = fma(p, y, 1.0);
+#if defined(__CUDA_ARCH__)
+  const double t = __ldg(d_exp2_tab + (ki & 31)) * p;
+#else
+  const double t = h_exp2_tab[ki & 31] * p;
+#endif
+  return i2d(d2i(t) + ((int64_t)(ki >> 5) << 52));  // t in [0.98, 2), |k>>5| <= 1021: stays normal
 }
 
 }  // namespace lsim
