@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LSIM_ABI_VERSION 1
+#define LSIM_ABI_VERSION 2
 #define LSIM_MAX_PARAMS 12 /* largest param_names list on the path: EPL_MULTIPOLE_M1M3M4 */
 #define LSIM_MAX_SLOTS 8   /* output / linear-basis images per parameter set */
 
@@ -137,6 +137,15 @@ typedef struct lsim_plan_desc {
   int32_t kernel_separable; /* 1: kernel == outer(kernel_1d, kernel_1d); lets the library do two 1-D passes */
   const double* kernel_1d;  /* host [K] when kernel_separable */
   double image_scale;       /* pixel_width^2 * flux_scaling (numerics.py:177, image_model.py:368,393) */
+  /* supersampling_convolution=True (SubgridKernelConvolution, convolution.py:99-166; GaussianConvolution with
+   * supersampling_convolution, convolution.py:238-252): the image is convolved on the supersampled grid with
+   * `kernel_hi`, re-binned, and -- when `kernel` (above) is present -- the re-binned unconvolved image convolved
+   * with `kernel` on the pixel grid is added.  conv_mode gives the boundary rule of both. */
+  int32_t supersampled_conv;   /* 0 / 1 */
+  int32_t kernel_hi_size;      /* odd */
+  const double* kernel_hi;     /* host [Kh*Kh] */
+  int32_t kernel_hi_separable;
+  const double* kernel_hi_1d;  /* host [Kh] when separable */
 
   /* data and noise model: ImageData / ImageNoise (Data/imaging_data.py, Data/image_noise.py) */
   const double* data;       /* host [ny*nx] or NULL */

@@ -26,8 +26,12 @@ class PSF(object):
             if len(kernel) % 2 == 0:
                 raise ValueError("kernel needs to have odd axis number, not ", np.shape(kernel))
             if point_source_supersampling_factor > 1:
-                raise ValueError("supersampled point-source kernels are outside the scope of jaxtronomy_b200 "
-                                 "(point sources are not on the forward-simulation path)")
+                # the given kernel is sampled at `point_source_supersampling_factor` points per pixel
+                from jaxtronomy_b200.Util import kernel_util
+
+                self._kernel_point_source_supersampled = kernel / np.sum(kernel) \
+                    if kernel_point_source_normalisation else kernel
+                kernel = kernel_util.degrade_kernel(kernel, point_source_supersampling_factor)
             if kernel_point_source_normalisation:
                 kernel = kernel / np.sum(kernel)
             self._kernel_point_source = kernel
@@ -48,6 +52,22 @@ class PSF(object):
             raise ValueError("the pixelised kernel of a GAUSSIAN PSF is only needed for point sources "
                              "(outside the scope of jaxtronomy_b200)")
         return self._kernel_point_source
+
+    def kernel_point_source_supersampled(self, supersampling_factor):
+        """Kernel sampled at `supersampling_factor` points per pixel.  Only available when the PSF was given
+        supersampled at that factor: lenstronomy otherwise interpolates the pixel kernel iteratively
+        (kernel_util.subgrid_kernel), which is not reproduced here."""
+        if self.psf_type != "PIXEL":
+            raise ValueError("supersampled kernels are defined for PIXEL PSFs")
+        if supersampling_factor == 1:
+            return self._kernel_point_source
+        if getattr(self, "_kernel_point_source_supersampled", None) is not None and \
+                self.point_source_supersampling_factor == supersampling_factor:
+            return self._kernel_point_source_supersampled
+        raise NotImplementedError(
+            "supersampling_convolution=True needs the PSF at the supersampled resolution: pass "
+            "PSF(psf_type='PIXEL', kernel_point_source=<supersampled kernel>, point_source_supersampling_factor=%d)"
+            % supersampling_factor)
 
     @property
     def fwhm(self):

@@ -7,8 +7,10 @@ Mapping of the reference's convolution classes onto kernel modes:
   GaussianConvolution                                            -> LSIM_CONV_EDGE with the exact [2r+1]^2 kernel;
                                                                     the kernel is outer(k1, k1), so two 1-d passes
   psf_type NONE / unconvolved=True                                -> LSIM_CONV_NONE
-Outside the round-1 scope: supersampling_convolution=True, flux_evaluate_indexes sub-frames,
-compute_mode="adaptive".
+  SubgridKernelConvolution / Gaussian with supersampling_convolution=True
+                                                                  -> kernel_hi on the supersampled grid, re-bin,
+                                                                     + low-resolution "hole" kernel on the pixel grid
+Not built: flux_evaluate_indexes sub-frames, compute_mode="adaptive" (not in the reference either).
 """
 
 import numpy as np
@@ -49,9 +51,6 @@ class Numerics(object):
                             % type(supersampling_factor))
         if supersampling_factor == 1:
             supersampling_convolution = False
-        if supersampling_convolution is True and self._psf_type != "NONE":
-            raise NotImplementedError("supersampling_convolution=True is not built yet in jaxtronomy_b200 "
-                                      "(SURVEY.md 8(f)-2); use supersampling_convolution=False")
         if flux_evaluate_indexes is not None and not bool(np.all(flux_evaluate_indexes)):
             raise NotImplementedError("flux_evaluate_indexes sub-frames are not built yet in jaxtronomy_b200 "
                                       "(SURVEY.md 8(f)-2)")
@@ -64,7 +63,22 @@ class Numerics(object):
         self._grid = RegularGrid(nx, ny, pixel_grid.transform_pix2angle, ra0, dec0, supersampling_factor, None)
         self._kernel = None
         self._kernel_1d = None
-        if self._psf_type == "PIXEL":
+        self._kernel_hi = None     # supersampled convolution: kernel on the [ny ss, nx ss] grid
+        self._kernel_hi_1d = None
+        self._high_res_return = bool(supersampling_convolution)
+        if self._psf_type == "PIXEL" and supersampling_convolution is True:
+            # SubgridKernelConvolution (convolution.py:99-166)
+            kernel_super = psf.kernel_point_source_supersampled(supersampling_factor)
+            if convolution_kernel_size is not None:
+                kernel_super = self._supersampling_cut_kernel(kernel_super, convolution_kernel_size,
+                                                              supersampling_factor)
+            self._conv_mode = _lib.CONV_ZERO
+            if supersampling_kernel_size is None:
+                self._kernel_hi = np.array(kernel_super, dtype=float)
+            else:
+                low, high = kernel_util.split_kernel(kernel_super, supersampling_kernel_size, supersampling_factor)
+                self._kernel, self._kernel_hi = np.array(low, dtype=float), np.array(high, dtype=float)
+        elif self._psf_type == "PIXEL":
             kernel = psf.kernel_point_source
             kernel = self._supersampling_cut_kernel(kernel, convolution_kernel_size, supersampling_factor=1)
             if kernel.shape[0] != kernel.shape[1] or kernel.shape[0] % 2 == 0:
@@ -75,11 +89,17 @@ class Numerics(object):
             if truncation_conv is None:
                 truncation_conv = psf.truncation
             sigma_scaled = sigma / pixel_grid.pixel_width
+            if supersampling_convolution is True:
+                sigma_scaled *= supersampling_factor  # convolution.py:199-200
             kernel_radius = max(round(sigma_scaled * truncation_conv), 1)
             num_pix = 2 * int(kernel_radius) + 1
             self._conv_mode = _lib.CONV_EDGE
-            self._kernel = gaussian_pixel_kernel(sigma_scaled, num_pix)
-            self._kernel_1d = kernel_util.kernel_gaussian_1d(num_pix, sigma_scaled)
+            k2d = gaussian_pixel_kernel(sigma_scaled, num_pix)
+            k1d = kernel_util.kernel_gaussian_1d(num_pix, sigma_scaled)
+            if supersampling_convolution is True:
+                self._kernel_hi, self._kernel_hi_1d = k2d, k1d
+            else:
+                self._kernel, self._kernel_1d = k2d, k1d
         elif self._psf_type == "NONE":
             self._conv_mode = _lib.CONV_NONE
         else:
@@ -94,7 +114,8 @@ class Numerics(object):
     def psf_dict(self, unconvolved=False):
         if unconvolved or self._conv_mode == _lib.CONV_NONE:
             return dict(mode=_lib.CONV_NONE)
-        return dict(mode=self._conv_mode, kernel=self._kernel, kernel_1d=self._kernel_1d)
+        return dict(mode=self._conv_mode, kernel=self._kernel, kernel_1d=self._kernel_1d,
+                    kernel_hi=self._kernel_hi, kernel_hi_1d=self._kernel_hi_1d)
 
     @property
     def pixel_area(self):

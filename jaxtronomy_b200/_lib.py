@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("LSIM_LIB") or os.path.join(_HERE, "csrc", "liblsim.so
 
 MAX_PARAMS = 12
 MAX_SLOTS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enum mirrors (include/lsim.h)
 LENS_TYPES = {
@@ -53,6 +53,8 @@ class PlanDesc(C.Structure):
         ("nx", C.c_int32), ("ny", C.c_int32), ("ss", C.c_int32), ("x_sub", _dp), ("y_sub", _dp),
         ("conv_mode", C.c_int32), ("kernel_size", C.c_int32), ("kernel", _dp), ("kernel_separable", C.c_int32),
         ("kernel_1d", _dp), ("image_scale", C.c_double),
+        ("supersampled_conv", C.c_int32), ("kernel_hi_size", C.c_int32), ("kernel_hi", _dp),
+        ("kernel_hi_separable", C.c_int32), ("kernel_hi_1d", _dp),
         ("data", _dp), ("cd_data", _dp), ("noise_map2", _dp), ("exposure", _dp), ("background_rms", C.c_double),
         ("mask", C.POINTER(C.c_uint8)),
     ]
@@ -184,15 +186,27 @@ class Plan:
             d.image_scale = float(image_scale)
             d.conv_mode = CONV_NONE
             if psf is not None and psf["mode"] != CONV_NONE:
-                k = _f64(psf["kernel"])
-                if k.ndim != 2 or k.shape[0] != k.shape[1]:
-                    raise LsimError("PSF kernel must be square, got %s" % (k.shape,))
-                keep.append(k)
-                d.conv_mode, d.kernel_size, d.kernel = int(psf["mode"]), k.shape[0], _ptr(k)
-                if psf.get("kernel_1d") is not None:
-                    k1 = _f64(psf["kernel_1d"])
-                    keep.append(k1)
-                    d.kernel_separable, d.kernel_1d = 1, _ptr(k1)
+                d.conv_mode = int(psf["mode"])
+                if psf.get("kernel") is not None:
+                    k = _f64(psf["kernel"])
+                    if k.ndim != 2 or k.shape[0] != k.shape[1]:
+                        raise LsimError("PSF kernel must be square, got %s" % (k.shape,))
+                    keep.append(k)
+                    d.kernel_size, d.kernel = k.shape[0], _ptr(k)
+                    if psf.get("kernel_1d") is not None:
+                        k1 = _f64(psf["kernel_1d"])
+                        keep.append(k1)
+                        d.kernel_separable, d.kernel_1d = 1, _ptr(k1)
+                if psf.get("kernel_hi") is not None:  # supersampled convolution
+                    kh = _f64(psf["kernel_hi"])
+                    if kh.ndim != 2 or kh.shape[0] != kh.shape[1]:
+                        raise LsimError("supersampled PSF kernel must be square, got %s" % (kh.shape,))
+                    keep.append(kh)
+                    d.supersampled_conv, d.kernel_hi_size, d.kernel_hi = 1, kh.shape[0], _ptr(kh)
+                    if psf.get("kernel_hi_1d") is not None:
+                        kh1 = _f64(psf["kernel_hi_1d"])
+                        keep.append(kh1)
+                        d.kernel_hi_separable, d.kernel_hi_1d = 1, _ptr(kh1)
             if data is not None:
                 npix = self.nx * self.ny
                 for name in ("data", "cd_data", "noise_map2", "exposure"):

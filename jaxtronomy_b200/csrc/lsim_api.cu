@@ -184,7 +184,13 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
     if (d->n_lens > kMaxImageLens) return LSIM_E_UNSUPPORTED;
     if (d->conv_mode < LSIM_CONV_NONE || d->conv_mode > LSIM_CONV_EDGE) return LSIM_E_INVALID;
     if (d->conv_mode != LSIM_CONV_NONE) {
-      if (d->kernel_size < 1 || d->kernel_size % 2 == 0 || !d->kernel) return LSIM_E_INVALID;
+      if (d->supersampled_conv) {
+        if (d->kernel_hi_size < 1 || d->kernel_hi_size % 2 == 0 || !d->kernel_hi) return LSIM_E_INVALID;
+        if (d->kernel_hi_separable && !d->kernel_hi_1d) return LSIM_E_INVALID;
+        if (d->kernel && (d->kernel_size < 1 || d->kernel_size % 2 == 0)) return LSIM_E_INVALID;
+      } else {
+        if (d->kernel_size < 1 || d->kernel_size % 2 == 0 || !d->kernel) return LSIM_E_INVALID;
+      }
       if (d->kernel_separable && !d->kernel_1d) return LSIM_E_INVALID;
     }
   }
@@ -232,11 +238,19 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
     TRY(p->upload(d->x_sub, nsub, &D.x_sub));
     TRY(p->upload(d->y_sub, nsub, &D.y_sub));
     D.conv_mode = d->conv_mode;
-    D.K = d->conv_mode != LSIM_CONV_NONE ? d->kernel_size : 0;
+    D.K = (d->conv_mode != LSIM_CONV_NONE && d->kernel) ? d->kernel_size : 0;
     D.image_scale = d->image_scale;
     if (d->conv_mode != LSIM_CONV_NONE) {
-      TRY(p->upload(d->kernel, (size_t)d->kernel_size * d->kernel_size, &D.kernel));
-      if (d->kernel_separable) TRY(p->upload(d->kernel_1d, (size_t)d->kernel_size, &D.kernel_1d));
+      if (d->kernel) {
+        TRY(p->upload(d->kernel, (size_t)d->kernel_size * d->kernel_size, &D.kernel));
+        if (d->kernel_separable) TRY(p->upload(d->kernel_1d, (size_t)d->kernel_size, &D.kernel_1d));
+      }
+      if (d->supersampled_conv) {
+        D.ss_conv = 1;
+        D.K_hi = d->kernel_hi_size;
+        TRY(p->upload(d->kernel_hi, (size_t)d->kernel_hi_size * d->kernel_hi_size, &D.kernel_hi));
+        if (d->kernel_hi_separable) TRY(p->upload(d->kernel_hi_1d, (size_t)d->kernel_hi_size, &D.kernel_hi_1d));
+      }
     }
     p->image_smem = (size_t)d->n_lens * sizeof(LensC) + (size_t)d->n_light * sizeof(LightC) +
                     (size_t)n_series * kMaxSeries * sizeof(double);
@@ -300,12 +314,15 @@ int lsim_surface_brightness(const lsim_plan* plan, const double* params, int64_t
 
 namespace {
 
+// Scratch doubles per parameter set.  Regular path: U (unconvolved pixels) [+ C (convolved pixels)].
+// Supersampled convolution: Usub + Hsub (sub-pixel flux and its convolution) + U + C.
 size_t per_set_bytes(const lsim_plan* plan, bool need_conv_out) {
-  const size_t npix = (size_t)plan->dev.nx * plan->dev.ny;
-  const bool conv = plan->dev.conv_mode != LSIM_CONV_NONE;
-  size_t n = 0;
-  n += npix * plan->dev.n_slots;                           // unconvolved basis images
-  if (conv && need_conv_out) n += npix * plan->dev.n_slots;  // convolved basis images
+  const PlanDev& D = plan->dev;
+  const size_t npix = (size_t)D.nx * D.ny, nsub = npix * D.ss * D.ss;
+  const bool conv = D.conv_mode != LSIM_CONV_NONE;
+  size_t n = npix * D.n_slots;
+  if (conv && need_conv_out) n += npix * D.n_slots;
+  if (conv && D.ss_conv) n += 2 * nsub * D.n_slots + (need_conv_out ? 0 : npix * D.n_slots);
   return n * sizeof(double);
 }
 
@@ -313,10 +330,11 @@ int64_t chunk_sets(const lsim_plan* plan) { return (int64_t)plan->n_sm * 8; }
 
 template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = RuntimeTypes>
 int launch_image_k(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
-                   double scale, double* out, cudaStream_t st) {
+                   double scale, double* out, double* sub_out, cudaStream_t st) {
   dim3 grid((unsigned)tiles, (unsigned)n);
   Timed timed(kClsImage, st);
-  k_image<NSLOT, FULL, SS, LT, GT><<<grid, kImageBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out);
+  k_image<NSLOT, FULL, SS, LT, GT><<<grid, kImageBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale,
+                                                                                out, sub_out);
   return after_launch("k_image");
 }
 
@@ -362,10 +380,10 @@ int find_signature(const lsim_plan_desc* d) {
 // returns LSIM_E_UNSUPPORTED when (NSLOT, ss) has no specialised instantiation -> caller falls back
 template <bool FULL, class LT, class GT>
 int launch_image_sig(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
-                     double scale, double* out, cudaStream_t st) {
+                     double scale, double* out, double* sub_out, cudaStream_t st) {
   const int ns = plan->dev.n_slots, ss = plan->dev.ss;
 #define LSIM_SIG_CASE(NS, SSV) \
-  if (ns == NS && ss == SSV) return launch_image_k<NS, FULL, SSV, LT, GT>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  if (ns == NS && ss == SSV) return launch_image_k<NS, FULL, SSV, LT, GT>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
   LSIM_SIG_CASE(1, 3)
   LSIM_SIG_CASE(2, 3)
   if (!FULL) {
@@ -383,19 +401,30 @@ int launch_image_sig(const lsim_plan* plan, const double* params, int64_t set0, 
 // variant (runtime supersampling factor, one sub-pixel at a time).
 template <int NSLOT>
 int launch_image_ns(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
-                    double scale, double* out, cudaStream_t st) {
-  if (plan->full) return launch_image_k<NSLOT, true, 0>(plan, params, set0, n, ppt, tiles, scale, out, st);
+                    double scale, double* out, double* sub_out, cudaStream_t st) {
+  if (sub_out) {  // supersampled convolution: the SUB instantiations (runtime supersampling factor)
+    dim3 grid((unsigned)tiles, (unsigned)n);
+    Timed timed(kClsImage, st);
+    if (plan->full)
+      k_image<NSLOT, true, 0, RuntimeTypes, RuntimeTypes, true><<<grid, kImageBlock, plan->image_smem, st>>>(
+          plan->dev, params, set0, ppt, scale, out, sub_out);
+    else
+      k_image<NSLOT, false, 0, RuntimeTypes, RuntimeTypes, true><<<grid, kImageBlock, plan->image_smem, st>>>(
+          plan->dev, params, set0, ppt, scale, out, sub_out);
+    return after_launch("k_image");
+  }
+  if (plan->full) return launch_image_k<NSLOT, true, 0>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
   switch (plan->dev.ss) {
-    case 1: return launch_image_k<NSLOT, false, 1>(plan, params, set0, n, ppt, tiles, scale, out, st);
-    case 2: return launch_image_k<NSLOT, false, 2>(plan, params, set0, n, ppt, tiles, scale, out, st);
-    case 3: return launch_image_k<NSLOT, false, 3>(plan, params, set0, n, ppt, tiles, scale, out, st);
-    default: return launch_image_k<NSLOT, false, 0>(plan, params, set0, n, ppt, tiles, scale, out, st);
+    case 1: return launch_image_k<NSLOT, false, 1>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
+    case 2: return launch_image_k<NSLOT, false, 2>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
+    case 3: return launch_image_k<NSLOT, false, 3>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
+    default: return launch_image_k<NSLOT, false, 0>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
   }
 }
 
 // ray-shoot + light + re-bin for sets [set0, set0+n) -> out[n][n_slots][npix]
 int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, double scale, double* out,
-                 cudaStream_t st) {
+                 double* sub_out, cudaStream_t st) {
   const int npix = plan->dev.nx * plan->dev.ny;
   int64_t want = ((int64_t)plan->n_sm * 4 + n - 1) / n;  // CTAs per set so that the grid fills the chip
   int max_tiles = (npix + kImageBlock - 1) / kImageBlock;
@@ -405,23 +434,33 @@ int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int6
   tiles = (npix + ppt - 1) / ppt;
   const int ns = plan->dev.n_slots;
   int rc = LSIM_E_UNSUPPORTED;
-  switch (plan->sig) {
-    case kSigEplShear_S: rc = launch_image_sig<false, LT_EplShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, st); break;
-    case kSigEplShear_SS: rc = launch_image_sig<false, LT_EplShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, st); break;
-    case kSigNieShear_S: rc = launch_image_sig<false, LT_NieShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, st); break;
-    case kSigNieShear_SS: rc = launch_image_sig<false, LT_NieShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, st); break;
-    case kSigEplmShear_SS: rc = launch_image_sig<true, LT_EplmShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, st); break;
+  switch (sub_out ? kSigNone : plan->sig) {
+    case kSigEplShear_S: rc = launch_image_sig<false, LT_EplShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
+    case kSigEplShear_SS: rc = launch_image_sig<false, LT_EplShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
+    case kSigNieShear_S: rc = launch_image_sig<false, LT_NieShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
+    case kSigNieShear_SS: rc = launch_image_sig<false, LT_NieShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
+    case kSigEplmShear_SS: rc = launch_image_sig<true, LT_EplmShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
     default: break;
   }
   if (rc != LSIM_E_UNSUPPORTED) return rc;
-  if (ns <= 1) return launch_image_ns<1>(plan, params, set0, n, ppt, tiles, scale, out, st);
-  if (ns <= 2) return launch_image_ns<2>(plan, params, set0, n, ppt, tiles, scale, out, st);
-  if (ns <= 4) return launch_image_ns<4>(plan, params, set0, n, ppt, tiles, scale, out, st);
-  return launch_image_ns<8>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  if (ns <= 1) return launch_image_ns<1>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
+  if (ns <= 2) return launch_image_ns<2>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
+  if (ns <= 4) return launch_image_ns<4>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
+  return launch_image_ns<8>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
 }
 
+// One "same" convolution pass: n_images images of nx x ny with a K x K kernel (or its 1-d factor).
+struct ConvSpec {
+  int nx, ny, K;
+  const double* kernel;
+  const double* kernel_1d;
+  int mode;
+  double scale;
+  int accumulate;  // out += scale * conv(in) instead of out = ...
+};
+
 template <int KT, int R, int NW>
-int launch_conv_tiled(const PlanDev& D, const double* in, double* out, int64_t n_images, cudaStream_t st) {
+int launch_conv_tiled(const ConvSpec& c, const double* in, double* out, int64_t n_images, cudaStream_t st) {
   constexpr int TH = R * NW, HALO = KT - 1, PITCH = (32 + HALO) | 1, WS = KT + 1;
   constexpr size_t smem = ((size_t)(TH + HALO) * PITCH + (size_t)KT * WS) * sizeof(double);
   static bool configured = false;  // per process; the attribute is per function, set once
@@ -429,13 +468,13 @@ int launch_conv_tiled(const PlanDev& D, const double* in, double* out, int64_t n
     LSIM_CUDA(cudaFuncSetAttribute(k_conv_tiled<KT, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int tiles = ((D.nx + 31) / 32) * ((D.ny + TH - 1) / TH);
+  const int tiles = ((c.nx + 31) / 32) * ((c.ny + TH - 1) / TH);
   for (int64_t i0 = 0; i0 < n_images; i0 += 65535) {
     const int64_t ni = n_images - i0 < 65535 ? n_images - i0 : 65535;
-    const size_t off = (size_t)i0 * D.nx * D.ny;
+    const size_t off = (size_t)i0 * c.nx * c.ny;
     Timed timed(kClsConv, st);
     k_conv_tiled<KT, R, NW><<<dim3((unsigned)tiles, (unsigned)ni), NW * 32, smem, st>>>(
-        in + off, out + off, D.nx, D.ny, D.K, D.kernel, D.conv_mode, D.image_scale);
+        in + off, out + off, c.nx, c.ny, c.K, c.kernel, c.mode, c.scale, c.accumulate);
     int rc = after_launch("k_conv_tiled");
     if (rc != LSIM_OK) return rc;
   }
@@ -443,45 +482,103 @@ int launch_conv_tiled(const PlanDev& D, const double* in, double* out, int64_t n
 }
 
 template <int KT>
-int launch_conv_tiled_kt(const PlanDev& D, const double* in, double* out, int64_t n_images, cudaStream_t st) {
+int launch_conv_tiled_kt(const ConvSpec& c, const double* in, double* out, int64_t n_images, cudaStream_t st) {
   // pick the tile height (64 = 8 warps x 8 rows, or 60 = 6 warps x 10 rows) that wastes fewer rows
-  const int w64 = ((D.ny + 63) / 64) * 64, w60 = ((D.ny + 59) / 60) * 60;
-  if (w60 < w64) return launch_conv_tiled<KT, 10, 6>(D, in, out, n_images, st);
-  return launch_conv_tiled<KT, 8, 8>(D, in, out, n_images, st);
+  const int w64 = ((c.ny + 63) / 64) * 64, w60 = ((c.ny + 59) / 60) * 60;
+  if (w60 < w64) return launch_conv_tiled<KT, 10, 6>(c, in, out, n_images, st);
+  return launch_conv_tiled<KT, 8, 8>(c, in, out, n_images, st);
 }
 
-int launch_conv(const lsim_plan* plan, const double* in, double* out, int64_t n_images, cudaStream_t st) {
-  const PlanDev& D = plan->dev;
-  if (!D.kernel_1d && !getenv("LSIM_CONV_GENERIC")) {
-    if (D.K <= 7) return launch_conv_tiled_kt<7>(D, in, out, n_images, st);
-    if (D.K <= 11) return launch_conv_tiled_kt<11>(D, in, out, n_images, st);
-    if (D.K <= 15) return launch_conv_tiled_kt<15>(D, in, out, n_images, st);
-    if (D.K <= 21) return launch_conv_tiled_kt<21>(D, in, out, n_images, st);
-    if (D.K <= 25) return launch_conv_tiled_kt<25>(D, in, out, n_images, st);
-    if (D.K <= 31) return launch_conv_tiled_kt<31>(D, in, out, n_images, st);
+int launch_conv_spec(const ConvSpec& c, const double* in, double* out, int64_t n_images, cudaStream_t st) {
+  if (!c.kernel_1d && !getenv("LSIM_CONV_GENERIC")) {
+    if (c.K <= 7) return launch_conv_tiled_kt<7>(c, in, out, n_images, st);
+    if (c.K <= 11) return launch_conv_tiled_kt<11>(c, in, out, n_images, st);
+    if (c.K <= 15) return launch_conv_tiled_kt<15>(c, in, out, n_images, st);
+    if (c.K <= 21) return launch_conv_tiled_kt<21>(c, in, out, n_images, st);
+    if (c.K <= 25) return launch_conv_tiled_kt<25>(c, in, out, n_images, st);
+    if (c.K <= 31) return launch_conv_tiled_kt<31>(c, in, out, n_images, st);
   }
-  const int K = D.K, TW = kConvT + K - 1, pitch = TW | 1;
-  const int tiles = ((D.nx + kConvT - 1) / kConvT) * ((D.ny + kConvT - 1) / kConvT);
+  const int K = c.K, TW = kConvT + K - 1, pitch = TW | 1;
+  const int tiles = ((c.nx + kConvT - 1) / kConvT) * ((c.ny + kConvT - 1) / kConvT);
   for (int64_t i0 = 0; i0 < n_images; i0 += 65535) {
     int64_t ni = n_images - i0 < 65535 ? n_images - i0 : 65535;
     dim3 grid((unsigned)tiles, (unsigned)ni);
-    const size_t off = (size_t)i0 * D.nx * D.ny;
+    const size_t off = (size_t)i0 * c.nx * c.ny;
     Timed timed(kClsConv, st);
-    if (D.kernel_1d) {
+    if (c.kernel_1d) {
       size_t smem = ((size_t)TW * pitch + (size_t)TW * (kConvT + 1) + K) * sizeof(double);
       if (smem > kConvSmemMax) return LSIM_E_UNSUPPORTED;
-      k_conv_separable<<<grid, kBlock, smem, st>>>(in + off, out + off, D.nx, D.ny, K, D.kernel_1d, D.conv_mode,
-                                                   D.image_scale);
+      k_conv_separable<<<grid, kBlock, smem, st>>>(in + off, out + off, c.nx, c.ny, K, c.kernel_1d, c.mode, c.scale,
+                                                   c.accumulate);
     } else {
       size_t smem = ((size_t)TW * pitch + (size_t)K * K) * sizeof(double);
       if (smem > kConvSmemMax) return LSIM_E_UNSUPPORTED;
-      k_conv_direct<<<grid, kBlock, smem, st>>>(in + off, out + off, D.nx, D.ny, K, D.kernel, D.conv_mode,
-                                                D.image_scale);
+      k_conv_direct<<<grid, kBlock, smem, st>>>(in + off, out + off, c.nx, c.ny, K, c.kernel, c.mode, c.scale,
+                                                c.accumulate);
     }
     int rc = after_launch("k_conv");
     if (rc != LSIM_OK) return rc;
   }
   return LSIM_OK;
+}
+
+int launch_rebin(const PlanDev& D, const double* sub, double* out, int64_t n_images, double scale, cudaStream_t st) {
+  const size_t npix = (size_t)D.nx * D.ny, nsub = npix * D.ss * D.ss;
+  const unsigned tiles = (unsigned)((npix + kBlock - 1) / kBlock);
+  for (int64_t i0 = 0; i0 < n_images; i0 += 65535) {
+    const int64_t ni = n_images - i0 < 65535 ? n_images - i0 : 65535;
+    Timed timed(kClsOther, st);
+    k_rebin<<<dim3(tiles, (unsigned)ni), kBlock, 0, st>>>(sub + (size_t)i0 * nsub, out + (size_t)i0 * npix, D.nx, D.ny,
+                                                           D.ss, scale);
+    int rc = after_launch("k_rebin");
+    if (rc != LSIM_OK) return rc;
+  }
+  return LSIM_OK;
+}
+
+// pixel-grid convolution of the plan (regular path): out = image_scale * conv(in)
+int launch_conv(const lsim_plan* plan, const double* in, double* out, int64_t n_images, cudaStream_t st) {
+  const PlanDev& D = plan->dev;
+  ConvSpec c{D.nx, D.ny, D.K, D.kernel, D.kernel_1d, D.conv_mode, D.image_scale, 0};
+  return launch_conv_spec(c, in, out, n_images, st);
+}
+
+// supersampled convolution (SubgridKernelConvolution.re_size_convolve, convolution.py:153-166):
+//   out = image_scale * ( re_size(conv_hi(sub)) + conv_lo(low) ),  low = re_size(sub) (already in `low`)
+int launch_conv_supersampled(const lsim_plan* plan, const double* sub, double* hsub, const double* low, double* out,
+                             int64_t n_images, cudaStream_t st) {
+  const PlanDev& D = plan->dev;
+  ConvSpec hi{D.nx * D.ss, D.ny * D.ss, D.K_hi, D.kernel_hi, D.kernel_hi_1d, D.conv_mode, 1.0, 0};
+  int rc = launch_conv_spec(hi, sub, hsub, n_images, st);
+  if (rc != LSIM_OK) return rc;
+  rc = launch_rebin(D, hsub, out, n_images, D.image_scale, st);
+  if (rc != LSIM_OK) return rc;
+  if (D.K > 0) {
+    ConvSpec lo{D.nx, D.ny, D.K, D.kernel, D.kernel_1d, D.conv_mode, D.image_scale, 1};
+    rc = launch_conv_spec(lo, low, out, n_images, st);
+  }
+  return rc;
+}
+
+// One chunk of the forward path: ray-shoot + light + re-bin (+ PSF) for sets [s0, s0+n).
+//   ws   : scratch, laid out for `chunk` sets
+//   dst  : where the final (convolved, scaled) basis images [n][n_slots][npix] go
+int run_chunk(const lsim_plan* plan, const double* params, int64_t s0, int64_t n, int64_t chunk, double* ws,
+              double* dst, cudaStream_t st) {
+  const PlanDev& D = plan->dev;
+  const size_t npix = (size_t)D.nx * D.ny, nsub = npix * D.ss * D.ss, ns = (size_t)D.n_slots;
+  if (D.conv_mode == LSIM_CONV_NONE) return launch_image(plan, params, s0, n, D.image_scale, dst, nullptr, st);
+  double* U = ws;  // [chunk][ns][npix]
+  if (!D.ss_conv) {
+    int rc = launch_image(plan, params, s0, n, 1.0, U, nullptr, st);
+    if (rc != LSIM_OK) return rc;
+    return launch_conv(plan, U, dst, n * D.n_slots, st);
+  }
+  double* Usub = ws + (size_t)chunk * ns * npix;
+  double* Hsub = Usub + (size_t)chunk * ns * nsub;
+  int rc = launch_image(plan, params, s0, n, 1.0, U, Usub, st);
+  if (rc != LSIM_OK) return rc;
+  return launch_conv_supersampled(plan, Usub, Hsub, U, dst, n * D.n_slots, st);
 }
 
 int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, int64_t n, int linear, int marg,
@@ -520,24 +617,15 @@ int lsim_image(const lsim_plan* plan, const double* params, int64_t B, double* i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const PlanDev& D = plan->dev;
   const size_t img = (size_t)D.nx * D.ny * D.n_slots;
-  if (D.conv_mode == LSIM_CONV_NONE) {
-    for (int64_t s0 = 0; s0 < B; s0 += 32768) {
-      int64_t n = B - s0 < 32768 ? B - s0 : 32768;
-      int rc = launch_image(plan, params, s0, n, D.image_scale, images + (size_t)s0 * img, st);
-      if (rc != LSIM_OK) return rc;
-    }
-    return LSIM_OK;
+  int64_t chunk = 32768;
+  if (D.conv_mode != LSIM_CONV_NONE) {
+    chunk = (int64_t)(workspace_bytes / per_set_bytes(plan, false));
+    if (!workspace || chunk < 1) return LSIM_E_WORKSPACE;
+    if (chunk > chunk_sets(plan)) chunk = chunk_sets(plan);
   }
-  const size_t per = per_set_bytes(plan, false);
-  int64_t chunk = (int64_t)(workspace_bytes / per);
-  if (!workspace || chunk < 1) return LSIM_E_WORKSPACE;
-  if (chunk > chunk_sets(plan)) chunk = chunk_sets(plan);
-  double* U = static_cast<double*>(workspace);
   for (int64_t s0 = 0; s0 < B; s0 += chunk) {
-    int64_t n = B - s0 < chunk ? B - s0 : chunk;
-    int rc = launch_image(plan, params, s0, n, 1.0, U, st);
-    if (rc != LSIM_OK) return rc;
-    rc = launch_conv(plan, U, images + (size_t)s0 * img, n * D.n_slots, st);
+    const int64_t n = B - s0 < chunk ? B - s0 : chunk;
+    int rc = run_chunk(plan, params, s0, n, chunk, static_cast<double*>(workspace), images + (size_t)s0 * img, st);
     if (rc != LSIM_OK) return rc;
   }
   return LSIM_OK;
@@ -553,21 +641,23 @@ int lsim_resize_convolve(const lsim_plan* plan, const double* flux, int64_t n_im
   const PlanDev& D = plan->dev;
   const size_t npix = (size_t)D.nx * D.ny, nsub = npix * D.ss * D.ss;
   const bool conv = D.conv_mode != LSIM_CONV_NONE && !unconvolved;
-  const unsigned tiles = (unsigned)((npix + kBlock - 1) / kBlock);
-  int64_t chunk = conv ? (int64_t)(workspace_bytes / (npix * sizeof(double))) : n_images;
-  if (conv && (!workspace || chunk < 1)) return LSIM_E_WORKSPACE;
+  if (!conv) return launch_rebin(D, flux, images, n_images, D.image_scale, st);
+  // scratch per image: re-binned unconvolved pixels (+ convolved sub-pixels for the supersampled convolution)
+  const size_t per = (npix + (D.ss_conv ? nsub : 0)) * sizeof(double);
+  int64_t chunk = (int64_t)(workspace_bytes / per);
+  if (!workspace || chunk < 1) return LSIM_E_WORKSPACE;
   if (chunk > 65535) chunk = 65535;
+  double* low = static_cast<double*>(workspace);
+  double* hsub = low + (size_t)chunk * npix;
   for (int64_t i0 = 0; i0 < n_images; i0 += chunk) {
-    int64_t n = n_images - i0 < chunk ? n_images - i0 : chunk;
-    double* dst = conv ? static_cast<double*>(workspace) : images + (size_t)i0 * npix;
-    k_rebin<<<dim3(tiles, (unsigned)n), kBlock, 0, st>>>(flux + (size_t)i0 * nsub, dst, D.nx, D.ny, D.ss,
-                                                          conv ? 1.0 : D.image_scale);
-    int rc = after_launch("k_rebin");
+    const int64_t n = n_images - i0 < chunk ? n_images - i0 : chunk;
+    int rc = launch_rebin(D, flux + (size_t)i0 * nsub, low, n, 1.0, st);
     if (rc != LSIM_OK) return rc;
-    if (conv) {
-      rc = launch_conv(plan, dst, images + (size_t)i0 * npix, n, st);
-      if (rc != LSIM_OK) return rc;
-    }
+    if (D.ss_conv)
+      rc = launch_conv_supersampled(plan, flux + (size_t)i0 * nsub, hsub, low, images + (size_t)i0 * npix, n, st);
+    else
+      rc = launch_conv(plan, low, images + (size_t)i0 * npix, n, st);
+    if (rc != LSIM_OK) return rc;
   }
   return LSIM_OK;
 }
@@ -585,17 +675,14 @@ int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear
   int64_t chunk = (int64_t)(workspace_bytes / per);
   if (!workspace || chunk < 1) return LSIM_E_WORKSPACE;
   if (chunk > chunk_sets(plan)) chunk = chunk_sets(plan);
-  const size_t img = (size_t)D.nx * D.ny * D.n_slots;
-  double* U = static_cast<double*>(workspace);
-  double* C = conv ? U + (size_t)chunk * img : U;
+  const size_t img = (size_t)D.nx * D.ny * D.n_slots, sub = img * D.ss * D.ss;
+  // layout: [U | Usub, Hsub (supersampled conv only) | C]; without a PSF the images land in U directly
+  double* ws = static_cast<double*>(workspace);
+  double* C = conv ? ws + (size_t)chunk * img + (D.ss_conv ? 2 * (size_t)chunk * sub : 0) : ws;
   for (int64_t s0 = 0; s0 < B; s0 += chunk) {
-    int64_t n = B - s0 < chunk ? B - s0 : chunk;
-    int rc = launch_image(plan, params, s0, n, conv ? 1.0 : D.image_scale, U, st);
+    const int64_t n = B - s0 < chunk ? B - s0 : chunk;
+    int rc = run_chunk(plan, params, s0, n, chunk, ws, C, st);
     if (rc != LSIM_OK) return rc;
-    if (conv) {
-      rc = launch_conv(plan, U, C, n * D.n_slots, st);
-      if (rc != LSIM_OK) return rc;
-    }
     rc = launch_likelihood(plan, C, s0, n, linear_solve, source_marg, logl, amps, model, st);
     if (rc != LSIM_OK) return rc;
   }

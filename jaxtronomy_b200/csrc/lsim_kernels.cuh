@@ -41,6 +41,9 @@ struct PlanDev {
   int32_t conv_mode, K;
   const double* kernel;     // [K*K]
   const double* kernel_1d;  // [K] or null
+  int32_t ss_conv, K_hi;    // supersampled convolution: kernel_hi on the [ny ss, nx ss] grid (+ kernel on pixels)
+  const double* kernel_hi;
+  const double* kernel_hi_1d;
   double image_scale;
   const double* data;
   const double* w_data;     // 1 / cd_data
@@ -157,10 +160,12 @@ k_surface_brightness(PlanDev P, const double* __restrict__ params, const double*
 #define LSIM_IMAGE_MIN_BLOCKS 3  // 24 warps/SM at 80 registers (a few spilled values) beats 16 warps at 114
 #endif
 constexpr int kImageBlock = LSIM_IMAGE_BLOCK;
-template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = RuntimeTypes>
+// SUB: also write the sub-pixel fluxes (supersampled convolution); a separate instantiation so that the common
+// kernels carry no trace of it.
+template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = RuntimeTypes, bool SUB = false>
 __global__ void __launch_bounds__(kImageBlock, LSIM_IMAGE_MIN_BLOCKS)
 k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, double out_scale,
-        double* __restrict__ out) {
+        double* __restrict__ out, double* __restrict__ sub_out) {
   constexpr int J = SS > 0 ? SS : 1;
   extern __shared__ double smem[];
   LensC* L = reinterpret_cast<LensC*>(smem);
@@ -199,6 +204,7 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
         ray_apply<FULL, J, LT>(P.ray, L, pool, P.n_lens, r);
 #pragma unroll
         for (int j = 0; j < J; ++j) ray_finish(P.ray, r, j, bx[j], by[j]);
+        unsigned written = 0;  // slots whose sub-pixels of this batch hold a value already (sub_out only)
         auto one_light = [&](int type, const LightC& Gg) {
           const int slot = Gg.slot;
           if (slot < 0) return;
@@ -206,6 +212,12 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
             light_eval<J>(type, Gg, bx, by, v);
           else
             light_eval<J>(type, Gg, x, y, v);
+          if (SUB) {  // supersampled convolution: keep the sub-pixel fluxes [set][slot][ny ss][nx ss]
+            double* dsub = sub_out + (bl * P.n_slots + slot) * ((int64_t)npix * ss * ss) + base + j0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) dsub[j] = ((written >> slot) & 1u) ? dsub[j] + v[j] : v[j];
+            written |= 1u << slot;
+          }
           double vs = v[0];
 #pragma unroll
           for (int j = 1; j < J; ++j) vs += v[j];
@@ -218,13 +230,21 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
         } else {
           for (int g = 0; g < P.n_light; ++g) one_light(G[g].type, G[g]);
         }
+        if (SUB) {
+          for (int k = 0; k < P.n_slots; ++k) {
+            if ((written >> k) & 1u) continue;  // a slot without any component is an all-zero image
+            double* dsub = sub_out + (bl * P.n_slots + k) * ((int64_t)npix * ss * ss) + base + j0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) dsub[j] = 0.0;
+          }
+        }
       }
 #pragma unroll
       for (int k = 0; k < NSLOT; ++k) acc[k] += racc[k] * inv_ss;
     }
 #pragma unroll
     for (int k = 0; k < NSLOT; ++k) {
-      if (k < P.n_slots) out[(bl * P.n_slots + k) * npix + p] = acc[k] * inv_ss * out_scale;
+      if (k < P.n_slots && out) out[(bl * P.n_slots + k) * npix + p] = acc[k] * inv_ss * out_scale;
     }
   }
 }
@@ -268,7 +288,7 @@ __device__ __forceinline__ double conv_fetch(const double* img, int nx, int ny, 
 
 __global__ void __launch_bounds__(kBlock)
 k_conv_direct(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
-              const double* __restrict__ kernel, int mode, double scale) {
+              const double* __restrict__ kernel, int mode, double scale, int accumulate) {
   extern __shared__ double smem[];
   const int r = (K - 1) / 2;
   const int TW = kConvT + K - 1;     // tile width incl. halo
@@ -301,7 +321,10 @@ k_conv_direct(const double* __restrict__ in, double* __restrict__ out, int nx, i
 #pragma unroll
   for (int o = 0; o < kConvR; ++o) {
     int x = tx0 + tx, y = ty0 + ty * kConvR + o;
-    if (x < nx && y < ny) dst[(int64_t)y * nx + x] = acc[o] * scale;
+    if (x < nx && y < ny) {
+      double* d = dst + (int64_t)y * nx + x;
+      *d = accumulate ? fma(acc[o], scale, *d) : acc[o] * scale;
+    }
   }
 }
 
@@ -314,7 +337,7 @@ k_conv_direct(const double* __restrict__ in, double* __restrict__ out, int nx, i
 template <int KT, int R, int NW>
 __global__ void __launch_bounds__(NW * 32, 2)
 k_conv_tiled(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
-             const double* __restrict__ kernel, int mode, double scale) {
+             const double* __restrict__ kernel, int mode, double scale, int accumulate) {
   constexpr int NT = NW * 32, TH = R * NW, HALO = KT - 1, TWD = 32 + HALO, PITCH = TWD | 1, WS = KT + 1;
   extern __shared__ double smem[];
   double* tile = smem;                      // [TH + HALO][PITCH]
@@ -356,14 +379,17 @@ k_conv_tiled(const double* __restrict__ in, double* __restrict__ out, int nx, in
 #pragma unroll
   for (int o = 0; o < R; ++o) {
     const int y = ty0 + warp * R + o;
-    if (x < nx && y < ny) dst[(int64_t)y * nx + x] = acc[o] * scale;
+    if (x < nx && y < ny) {
+      double* d = dst + (int64_t)y * nx + x;
+      *d = accumulate ? fma(acc[o], scale, *d) : acc[o] * scale;
+    }
   }
 }
 
 // Separable variant (kernel == outer(k1, k1), e.g. the Gaussian PSF): row pass into shared memory, column pass out.
 __global__ void __launch_bounds__(kBlock)
 k_conv_separable(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
-                 const double* __restrict__ k1, int mode, double scale) {
+                 const double* __restrict__ k1, int mode, double scale, int accumulate) {
   extern __shared__ double smem[];
   const int r = (K - 1) / 2;
   const int TW = kConvT + K - 1;
@@ -393,7 +419,10 @@ k_conv_separable(const double* __restrict__ in, double* __restrict__ out, int nx
     double a = 0.0;
     for (int dy = 0; dy < K; ++dy) a = fma(w[dy], rowp[(ly + dy) * (kConvT + 1) + lx], a);
     int x = tx0 + lx, y = ty0 + ly;
-    if (x < nx && y < ny) dst[(int64_t)y * nx + x] = a * scale;
+    if (x < nx && y < ny) {
+      double* d = dst + (int64_t)y * nx + x;
+      *d = accumulate ? fma(a, scale, *d) : a * scale;
+    }
   }
 }
 

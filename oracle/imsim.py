@@ -21,7 +21,7 @@ from scipy import signal
 
 from . import lens_model as _lens
 from . import light_profiles as _light
-from .lenstronomy_port import PixelGrid, cut_psf, fwhm2sigma, make_grid, make_subgrid
+from .lenstronomy_port import PixelGrid, cut_psf, fwhm2sigma, make_grid, make_subgrid, split_kernel
 from .util import array2image, image2array, nan_to_num, re_size
 
 EPSILON = sys.float_info.epsilon
@@ -83,6 +83,28 @@ class PixelKernelConvolution:
         return self.convolution2d(image_low_res)
 
 
+class SubgridKernelConvolution:
+    """convolution.py:99-166."""
+
+    def __init__(self, kernel_supersampled, supersampling_factor, supersampling_kernel_size=None,
+                 convolution_type="fft_static"):
+        self._ss = supersampling_factor
+        if supersampling_kernel_size is None:
+            kernel_low_res, kernel_high_res = np.zeros((3, 3)), kernel_supersampled
+            self._low_res_convolution = False
+        else:
+            kernel_low_res, kernel_high_res = split_kernel(kernel_supersampled, supersampling_kernel_size, self._ss)
+            self._low_res_convolution = True
+        self._low_res_conv = PixelKernelConvolution(kernel_low_res, convolution_type=convolution_type)
+        self._high_res_conv = PixelKernelConvolution(kernel_high_res, convolution_type=convolution_type)
+
+    def re_size_convolve(self, image_low_res, image_high_res):
+        out = re_size(self._high_res_conv.convolution2d(image_high_res), self._ss)
+        if self._low_res_convolution is True:
+            out = out + self._low_res_conv.convolution2d(image_low_res)
+        return out
+
+
 class GaussianConvolution:
     def __init__(self, sigma, pixel_scale, supersampling_factor=1, supersampling_convolution=False, truncation=2):
         self._sigma_scaled = sigma / pixel_scale
@@ -114,7 +136,7 @@ class GaussianConvolution:
 class Numerics:
     def __init__(self, pixel_grid, psf, supersampling_factor=1, supersampling_convolution=False,
                  convolution_kernel_size=None, convolution_type="fft", truncation_conv=None,
-                 flux_evaluate_indexes=None, **unused):
+                 flux_evaluate_indexes=None, supersampling_kernel_size=5, **unused):
         if flux_evaluate_indexes is not None:
             raise NotImplementedError("oracle: flux_evaluate_indexes not restated (SURVEY 8(f)-2)")
         if not isinstance(supersampling_factor, int):
@@ -128,14 +150,23 @@ class Numerics:
         self._grid = RegularGrid(nx, ny, pixel_grid.transform_pix2angle, ra0, dec0, supersampling_factor)
         if self._psf_type == "PIXEL":
             if supersampling_convolution is True:
-                raise NotImplementedError("oracle: SubgridKernelConvolution not restated (SURVEY 8(f)-2)")
-            kernel = psf.kernel_point_source
-            if convolution_kernel_size is not None:
-                size = convolution_kernel_size
-                if size % 2 == 0:
-                    size += 1
-                kernel = cut_psf(kernel, size, normalisation=False)
-            self._conv = PixelKernelConvolution(kernel, convolution_type=convolution_type)
+                kernel_super = psf.kernel_point_source_supersampled(supersampling_factor)
+                if convolution_kernel_size is not None:
+                    size = convolution_kernel_size * supersampling_factor
+                    if size % 2 == 0:
+                        size += 1
+                    kernel_super = cut_psf(kernel_super, size, normalisation=False)
+                self._conv = SubgridKernelConvolution(kernel_super, supersampling_factor,
+                                                      supersampling_kernel_size=supersampling_kernel_size,
+                                                      convolution_type=convolution_type)
+            else:
+                kernel = psf.kernel_point_source
+                if convolution_kernel_size is not None:
+                    size = convolution_kernel_size
+                    if size % 2 == 0:
+                        size += 1
+                    kernel = cut_psf(kernel, size, normalisation=False)
+                self._conv = PixelKernelConvolution(kernel, convolution_type=convolution_type)
         elif self._psf_type == "GAUSSIAN":
             sigma = fwhm2sigma(psf.fwhm)
             if truncation_conv is None:

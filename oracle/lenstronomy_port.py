@@ -161,9 +161,53 @@ def cut_psf(psf_data, psf_size, normalisation=True):
     return kernel
 
 
+def averaging(grid, numGrid, numPix):
+    n = int(numGrid / numPix)
+    return np.reshape(grid, (numPix, n, numPix, n)).mean(-1).mean(1)
+
+
+def degrade_kernel(kernel_super, degrading_factor):
+    """lenstronomy.Util.kernel_util.degrade_kernel, odd factors (averaging_odd_kernel)."""
+    if degrading_factor == 1:
+        return kernel_super
+    assert degrading_factor % 2 == 1
+    n_high = len(kernel_super)
+    num_pix = int(round(n_high / degrading_factor + 0.5))
+    if num_pix % 2 == 0:
+        num_pix += 1
+    n_pad = num_pix * degrading_factor
+    padded = np.zeros((n_pad, n_pad))
+    i0 = int((n_pad - n_high) / 2)
+    padded[i0:i0 + n_high, i0:i0 + n_high] = kernel_super
+    return averaging(padded, n_pad, num_pix) * degrading_factor**2
+
+
+def split_kernel(kernel_super, supersampling_kernel_size, supersampling_factor, normalized=True):
+    """lenstronomy.Util.kernel_util.split_kernel (convolution.py:123)."""
+    kernel_super = np.array(kernel_super, dtype=float)
+    n_super = len(kernel_super)
+    n_sub = supersampling_kernel_size * supersampling_factor
+    if n_sub % 2 == 0:
+        n_sub += 1
+    if n_sub > n_super:
+        n_sub = n_super
+    hole = kernel_super.copy()
+    n_min = int((n_super - 1) / 2 - (n_sub - 1) / 2)
+    n_max = int((n_super - 1) / 2 + (n_sub - 1) / 2 + 1)
+    hole[n_min:n_max, n_min:n_max] = 0
+    hole_resized = degrade_kernel(hole, supersampling_factor)
+    cut = kernel_super[n_min:n_max, n_min:n_max].copy()
+    if normalized:
+        cut = cut * (1.0 - np.sum(hole_resized)) / np.sum(cut)
+    else:
+        hole_resized = hole_resized / supersampling_factor**2
+    return hole_resized, cut
+
+
 class PSF:
     def __init__(self, psf_type="NONE", fwhm=None, truncation=5, pixel_size=None,
-                 kernel_point_source=None, kernel_point_source_normalisation=True):
+                 kernel_point_source=None, kernel_point_source_normalisation=True,
+                 point_source_supersampling_factor=1):
         self.psf_type = psf_type
         self._pixel_size = pixel_size
         if psf_type == "GAUSSIAN":
@@ -177,6 +221,10 @@ class PSF:
             k = np.array(kernel_point_source, dtype=float)
             if len(k) % 2 == 0:
                 raise ValueError("kernel needs to have odd axis number, not ", np.shape(k))
+            self.point_source_supersampling_factor = point_source_supersampling_factor
+            if point_source_supersampling_factor > 1:
+                self._kernel_super = k / np.sum(k) if kernel_point_source_normalisation else k
+                k = degrade_kernel(k, point_source_supersampling_factor)
             if kernel_point_source_normalisation:
                 k = k / np.sum(k)
             self.kernel_point_source = k
@@ -186,6 +234,14 @@ class PSF:
             self.kernel_point_source = k
         else:
             raise ValueError("psf_type %s not supported!" % psf_type)
+
+    def kernel_point_source_supersampled(self, supersampling_factor, updata_cache=True):
+        if supersampling_factor == 1:
+            return self.kernel_point_source
+        if getattr(self, "_kernel_super", None) is not None and \
+                self.point_source_supersampling_factor == supersampling_factor:
+            return self._kernel_super
+        raise NotImplementedError("oracle: kernel_util.subgrid_kernel interpolation is not restated")
 
     def set_pixel_size(self, deltaPix):
         self._pixel_size = deltaPix

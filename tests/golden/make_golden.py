@@ -367,6 +367,39 @@ def gen_imsim():
     image_case("linear_degenerate", 24, 0.1, ["SIS"], [dict(theta_E=0.8, center_x=0.0, center_y=0.0)],
                ["SERSIC_ELLIPSE", "SERSIC_ELLIPSE"], [sersic_src, sersic_src], [], [],
                dict(psf_type="NONE"), dict(supersampling_factor=1))
+    # ---- supersampling_convolution=True (appended last so that the random stream of the cases above is unchanged)
+    kd = sim_util.data_configure_simple(20, 0.08, 100, 0.05, inverse=True)
+    pg = PixelGrid(20, 20, kd["transform_pix2angle"], kd["ra_at_xy_0"], kd["dec_at_xy_0"])
+    kern_super = gauss_kernel(27, 3.5) + 0.05 * rng.uniform(0, 1, (27, 27)) / 729  # sampled at 3 points per pixel
+    for name, psf_kw, num_kw in [
+        ("ss_pixel_split", dict(psf_type="PIXEL", kernel_point_source=kern_super, point_source_supersampling_factor=3),
+         dict(supersampling_factor=3, supersampling_convolution=True, supersampling_kernel_size=5)),
+        ("ss_pixel_full", dict(psf_type="PIXEL", kernel_point_source=kern_super, point_source_supersampling_factor=3),
+         dict(supersampling_factor=3, supersampling_convolution=True, supersampling_kernel_size=None,
+              convolution_type="grid")),
+        ("ss_gaussian", dict(psf_type="GAUSSIAN", fwhm=0.2, truncation=4),
+         dict(supersampling_factor=2, supersampling_convolution=True)),
+    ]:
+        psf = PSF(**psf_kw)
+        psf.set_pixel_size(pg.pixel_width)
+        num = Numerics(pg, psf, **num_kw)
+        ra, dec = num.coordinates_evaluate
+        flux = np.exp(-((ra - 0.1) ** 2 + (dec + 0.2) ** 2) / 0.05) + 0.01 * rng.uniform(0, 1, ra.shape)
+        out = num.re_size_convolve(flux)
+        outu = num.re_size_convolve(flux, unconvolved=True)
+        ins = dict(flux=flux, transform_pix2angle=kd["transform_pix2angle"], ra_at_xy_0=kd["ra_at_xy_0"],
+                   dec_at_xy_0=kd["dec_at_xy_0"])
+        if "kernel_point_source" in psf_kw:
+            ins["kernel"] = kern_super
+        meta_psf = {k: v for k, v in psf_kw.items() if k != "kernel_point_source"}
+        st.add("numerics_%s" % name, ins, dict(image=out, image_unconvolved=outu, ra=ra, dec=dec),
+               dict(nx=20, ny=20, kwargs_psf=meta_psf, kwargs_numerics=num_kw))
+    image_case("ss_conv_sie_shear", 30, 0.1, ["SIE", "SHEAR"],
+               [dict(theta_E=1.0, e1=0.1, e2=-0.05, center_x=0.02, center_y=-0.01), shear],
+               ["SERSIC_ELLIPSE"], [sersic_src], ["SERSIC"],
+               [dict(amp=31.0, R_sersic=0.1, n_sersic=2.0, center_x=0.0, center_y=0.0)],
+               dict(psf_type="PIXEL", kernel_point_source=kern_super, point_source_supersampling_factor=3),
+               dict(supersampling_factor=3, supersampling_convolution=True))
     st.save("imsim.npz")
 
 

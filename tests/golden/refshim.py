@@ -409,7 +409,7 @@ def _make_lenstronomy():
                      psf_variance_map=None, point_source_supersampling_factor=1, kernel_point_source_init=None,
                      kernel_point_source_normalisation=True):
             port.PSF.__init__(self, psf_type, fwhm, truncation, pixel_size, kernel_point_source,
-                              kernel_point_source_normalisation)
+                              kernel_point_source_normalisation, point_source_supersampling_factor)
             self.point_source_supersampling_factor = point_source_supersampling_factor
             self.psf_variance_map_bool = psf_variance_map is not None
 
@@ -419,9 +419,7 @@ def _make_lenstronomy():
                 k = np.zeros((n, n))
                 k[1, 1] = 1
                 return k
-            if supersampling_factor == 1:
-                return self.kernel_point_source
-            raise NotImplementedError("refshim: supersampled PIXEL kernel")
+            return port.PSF.kernel_point_source_supersampled(self, supersampling_factor)
 
     class Image2SourceMapping(object):
         """lenstronomy.ImSim.image2source_mapping, single source plane."""
@@ -475,7 +473,8 @@ def _make_lenstronomy():
         local_minima_2d=None, selectBest=None, map_coord2pix=port.map_coord2pix,
         make_grid_with_coordtransform=port.make_grid_with_coordtransform,
     )
-    kutil = mod("lenstronomy.Util.kernel_util", cut_psf=port.cut_psf)
+    kutil = mod("lenstronomy.Util.kernel_util", cut_psf=port.cut_psf, split_kernel=port.split_kernel,
+                degrade_kernel=port.degrade_kernel)
     mods = {
         "lenstronomy.Util.util": lutil,
         "lenstronomy.Util.kernel_util": kutil,

@@ -60,7 +60,8 @@ def test_numerics_coordinates_and_kernel(name):
     np.testing.assert_array_equal(ra, c.out["ra"])
     np.testing.assert_array_equal(dec, c.out["dec"])
     if kw["psf_type"] == "GAUSSIAN":
-        k2, k1 = num._kernel, num._kernel_1d
+        ss_conv = c.meta["kwargs_numerics"].get("supersampling_convolution", False)
+        k2, k1 = (num._kernel_hi, num._kernel_hi_1d) if ss_conv else (num._kernel, num._kernel_1d)
         assert k2.shape[0] % 2 == 1 and abs(k2.sum() - 1) < 1e-14
         # the separable factorisation the kernels use reproduces the reference's 2-d kernel to rounding
         assert np.max(np.abs(np.outer(k1, k1) - k2)) < 1e-16
@@ -79,8 +80,10 @@ def test_unsupported_numerics_raise():
     kd = simulation_util.data_configure_simple(10, 0.1, 100, 0.1)
     data = ImageData(**kd)
     psf = PSF(psf_type="PIXEL", kernel_point_source=np.ones((3, 3)))
+    with pytest.raises(NotImplementedError):  # pixel PSF not given at the supersampled resolution
+        Numerics(data, psf, supersampling_factor=3, supersampling_convolution=True)
     with pytest.raises(NotImplementedError):
-        Numerics(data, psf, supersampling_factor=2, supersampling_convolution=True)
+        Numerics(data, psf, flux_evaluate_indexes=np.eye(10))
     with pytest.raises(ValueError):
         Numerics(data, psf, compute_mode="adaptive")
     with pytest.raises(TypeError):
