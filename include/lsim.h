@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LSIM_ABI_VERSION 2
+#define LSIM_ABI_VERSION 3
 #define LSIM_MAX_PARAMS 12 /* largest param_names list on the path: EPL_MULTIPOLE_M1M3M4 */
 #define LSIM_MAX_SLOTS 8   /* output / linear-basis images per parameter set */
 
@@ -130,6 +130,8 @@ typedef struct lsim_plan_desc {
   int32_t nx, ny, ss;
   const double* x_sub;      /* host [ny*ss*nx*ss] */
   const double* y_sub;
+  const uint8_t* eval_mask; /* host [ny*nx] or NULL: pixels with 0 are not evaluated and get zero flux
+                               (flux_evaluate_indexes, grid.py:51-64 / numerics_subframe.py:150-161) */
   /* PSF */
   int32_t conv_mode;        /* LSIM_CONV_* */
   int32_t kernel_size;      /* K (odd) */
@@ -154,6 +156,8 @@ typedef struct lsim_plan_desc {
   const double* exposure;   /* host [ny*nx] exposure map (already clamped >= 1e-10), used when noise_map2 is NULL */
   double background_rms;
   const uint8_t* mask;      /* host [ny*nx] likelihood mask (1 = use), or NULL = all ones (image_model.py:134-142) */
+  double logl_offset;       /* added to every log-likelihood: -chi^2/2 of the likelihood pixels outside the
+                               evaluated sub-frame, where the model is identically zero (numerics_subframe.py:134-148) */
 } lsim_plan_desc;
 
 typedef struct lsim_plan lsim_plan;

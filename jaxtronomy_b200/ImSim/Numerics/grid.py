@@ -57,8 +57,10 @@ class RegularGrid(Coordinates1D):
     @staticmethod
     def _subgrid_index(idex_mask, subgrid_res, nx, ny):
         """1d mask at pixel resolution -> equivalent 1d mask at subgrid resolution (grid.py:119-131)."""
+        # the reference calls lenstronomy's array2image here, which reshapes to (nx, ny) (jaxtronomy's own uses
+        # (ny, nx)): each pixel's flag is repeated along x, then whole rows are repeated
         idex_sub = np.repeat(idex_mask, subgrid_res, axis=0)
-        idex_sub = util.array2image(idex_sub, nx=nx, ny=ny * subgrid_res)
+        idex_sub = np.reshape(idex_sub, (int(nx), int(ny * subgrid_res)))
         idex_sub = np.repeat(idex_sub, subgrid_res, axis=0)
         return util.image2array(idex_sub)
 

@@ -51,16 +51,17 @@ class Numerics(object):
                             % type(supersampling_factor))
         if supersampling_factor == 1:
             supersampling_convolution = False
-        if flux_evaluate_indexes is not None and not bool(np.all(flux_evaluate_indexes)):
-            raise NotImplementedError("flux_evaluate_indexes sub-frames are not built yet in jaxtronomy_b200 "
-                                      "(SURVEY.md 8(f)-2)")
         if convolution_type not in ("fft", "fft_static", "grid"):
             raise ValueError("convolution_type %s not supported!" % convolution_type)
         self._pixel_width = pixel_grid.pixel_width
         nx, ny = pixel_grid.num_pixel_axes
         ra0, dec0 = pixel_grid.radec_at_xy_0
         self._nx, self._ny = nx, ny
-        self._grid = RegularGrid(nx, ny, pixel_grid.transform_pix2angle, ra0, dec0, supersampling_factor, None)
+        self._grid = RegularGrid(nx, ny, pixel_grid.transform_pix2angle, ra0, dec0, supersampling_factor,
+                                 flux_evaluate_indexes)
+        self._eval_mask = None
+        if flux_evaluate_indexes is not None and not bool(np.all(flux_evaluate_indexes)):
+            self._eval_mask = util.image2array(np.asarray(flux_evaluate_indexes)).astype(bool)
         self._kernel = None
         self._kernel_1d = None
         self._kernel_hi = None     # supersampled convolution: kernel on the [ny ss, nx ss] grid
@@ -109,7 +110,8 @@ class Numerics(object):
     # -- descriptors for _lib.Plan -----------------------------------------------------------------------
     def grid_dict(self):
         xs, ys = self._grid.coordinates_full
-        return dict(nx=self._nx, ny=self._ny, ss=self._grid.supersampling_factor, x_sub=xs, y_sub=ys)
+        return dict(nx=self._nx, ny=self._ny, ss=self._grid.supersampling_factor, x_sub=xs, y_sub=ys,
+                    eval_mask=self._eval_mask)
 
     def psf_dict(self, unconvolved=False):
         if unconvolved or self._conv_mode == _lib.CONV_NONE:
@@ -163,6 +165,110 @@ class Numerics(object):
         return self._grid
 
 
-class NumericsSubFrame(Numerics):
-    """numerics_subframe.py: with flux_evaluate_indexes=None the sub-frame is the full frame, which is the only
-    case built so far; the class name is kept so that ImageModel reads like the reference."""
+class NumericsSubFrame(object):
+    """Finds the rectangular sub-frame that contains all flux_evaluate_indexes, runs the numerics only there and
+    pads zeros around it (jaxtronomy/ImSim/Numerics/numerics_subframe.py:15-199).
+
+    The reference cuts ``image[x_min:x_max+1, y_min:y_max+1]`` with x := array axis 0 and builds the sub-frame grid as
+    ``PixelGrid(nx_sub = x extent, ny_sub = y extent, ra/dec at map_pix2coord(x_min, y_min))``; that is reproduced
+    verbatim.  It only works when the sub-frame is square (otherwise ``_complete_frame`` cannot place the result),
+    which is checked here."""
+
+    def __init__(self, pixel_grid, psf, supersampling_factor=1, compute_mode="regular",
+                 supersampling_convolution=False, supersampling_kernel_size=5, flux_evaluate_indexes=None,
+                 supersampled_indexes=None, compute_indexes=None, point_source_supersampling_factor=1,
+                 convolution_kernel_size=None, convolution_type="fft", truncation_conv=None):
+        from jaxtronomy_b200.Data.pixel_grid import PixelGrid
+
+        self._nx, self._ny = pixel_grid.num_pixel_axes
+        self._init_sub_frame(flux_evaluate_indexes)
+        if self._subframe_calc:
+            nx_sub = self._x_max_sub - self._x_min_sub + 1
+            ny_sub = self._y_max_sub - self._y_min_sub + 1
+            if nx_sub != ny_sub:
+                raise ValueError("the sub-frame enclosing flux_evaluate_indexes must be square (%d x %d): the "
+                                 "reference cannot place a rectangular sub-frame back into the full frame"
+                                 % (nx_sub, ny_sub))
+            ra0, dec0 = pixel_grid.map_pix2coord(self._x_min_sub, self._y_min_sub)
+            pixel_grid_sub = PixelGrid(nx=nx_sub, ny=ny_sub, transform_pix2angle=pixel_grid.transform_pix2angle,
+                                       ra_at_xy_0=ra0, dec_at_xy_0=dec0)
+        else:
+            pixel_grid_sub = pixel_grid
+        self._numerics_subframe = Numerics(
+            pixel_grid=pixel_grid_sub, psf=psf, supersampling_factor=supersampling_factor, compute_mode=compute_mode,
+            supersampling_convolution=supersampling_convolution, supersampling_kernel_size=supersampling_kernel_size,
+            flux_evaluate_indexes=self._cut_frame(flux_evaluate_indexes),
+            point_source_supersampling_factor=point_source_supersampling_factor,
+            convolution_kernel_size=convolution_kernel_size, convolution_type=convolution_type,
+            truncation_conv=truncation_conv)
+
+    def _init_sub_frame(self, flux_evaluate_indexes):
+        if flux_evaluate_indexes is None:
+            self._subframe_calc = False
+            self._x_min_sub, self._y_min_sub = 0, 0
+            self._x_max_sub, self._y_max_sub = self._nx, self._ny
+        else:
+            self._subframe_calc = True
+            idx = np.where(flux_evaluate_indexes)
+            self._x_min_sub, self._x_max_sub = int(np.min(idx[0])), int(np.max(idx[0]))
+            self._y_min_sub, self._y_max_sub = int(np.min(idx[1])), int(np.max(idx[1]))
+
+    def _cut_frame(self, image):
+        """Sub-frame of a full-frame 2d array (numerics_subframe.py:163-176); works on the last two axes."""
+        if self._subframe_calc is True and image is not None:
+            return image[..., self._x_min_sub:self._x_max_sub + 1, self._y_min_sub:self._y_max_sub + 1]
+        return image
+
+    def _complete_frame(self, image_sub_frame):
+        """Zero-pad a sub-frame image (last two axes) back to the full frame (numerics_subframe.py:134-148)."""
+        if not self._subframe_calc:
+            return image_sub_frame
+        lead = tuple(image_sub_frame.shape[:-2])
+        if type(image_sub_frame).__module__.startswith("torch"):
+            import torch
+
+            image = torch.zeros(lead + (self._nx, self._ny), dtype=image_sub_frame.dtype,
+                                device=image_sub_frame.device)
+        else:
+            image = np.zeros(lead + (self._nx, self._ny))
+        image[..., self._x_min_sub:self._x_max_sub + 1, self._y_min_sub:self._y_max_sub + 1] = image_sub_frame
+        return image
+
+    @property
+    def subframe_calc(self):
+        return self._subframe_calc
+
+    def cut_frame(self, image):
+        return self._cut_frame(image)
+
+    def complete_frame(self, image_sub_frame):
+        return self._complete_frame(image_sub_frame)
+
+    def grid_dict(self):
+        return self._numerics_subframe.grid_dict()
+
+    def psf_dict(self, unconvolved=False):
+        return self._numerics_subframe.psf_dict(unconvolved)
+
+    @property
+    def pixel_area(self):
+        return self._numerics_subframe.pixel_area
+
+    def re_size_convolve(self, flux_array, unconvolved=False):
+        return self._complete_frame(self._numerics_subframe.re_size_convolve(flux_array, unconvolved=unconvolved))
+
+    @property
+    def grid_supersampling_factor(self):
+        return self._numerics_subframe.grid_supersampling_factor
+
+    @property
+    def coordinates_evaluate(self):
+        return self._numerics_subframe.coordinates_evaluate
+
+    @property
+    def convolution_kernel(self):
+        return self._numerics_subframe.convolution_kernel
+
+    @property
+    def grid_class(self):
+        return self._numerics_subframe.grid_class

@@ -45,12 +45,15 @@ class ImageLinearFit(ImageModel):
     # -- batch entry points (CUDA tensors, no Python-side packing) ----------------------------------------------
     def logL_linear_batch(self, params, source_marg=False, return_model=False, out=None):
         """[B, P] parameter matrix -> (logL [B], amplitudes [B, n_lin], model [B, ny, nx] or None)."""
-        return self._split_plan().logl(params, linear_solve=True, source_marg=source_marg, return_model=return_model,
-                                       out=out)
+        logl, amps, model = self._split_plan().logl(params, linear_solve=True, source_marg=source_marg,
+                                                    return_model=return_model, out=out)
+        if model is not None:
+            model = self.ImageNumerics.complete_frame(model)
+        return logl, amps, model
 
     def response_batch(self, params, unconvolved=False):
-        """[B, P] -> convolved amp=1 basis images [B, n_lin, ny, nx]."""
-        return self._split_plan(unconvolved).image(params)
+        """[B, P] -> convolved amp=1 basis images [B, n_lin, ny, nx] (full frame)."""
+        return self.ImageNumerics.complete_frame(self._split_plan(unconvolved).image(params))
 
     # -- reference API --------------------------------------------------------------------------------------------
     def linear_response_matrix(self, kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps=None,

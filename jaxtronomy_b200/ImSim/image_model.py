@@ -69,10 +69,25 @@ class ImageModel(object):
     # plans
     # ----------------------------------------------------------------------------------------------------
     def _data_dict(self):
-        d = self.Data
-        return dict(data=d.data, cd_data=d.C_D, noise_map2=None if d._noise_map is None else d._noise_map**2,
-                    exposure=getattr(d, "exposure_map", None), background_rms=d.background_rms,
-                    mask=None if bool(np.all(self.likelihood_mask)) else self.likelihood_mask)
+        """Data / noise / mask arrays on the frame the kernels work on (the evaluated sub-frame when
+        flux_evaluate_indexes is set).  Likelihood pixels outside the sub-frame see a model of exactly zero; their
+        chi^2 does not depend on the parameters and enters as a constant offset."""
+        d, num = self.Data, self.ImageNumerics
+        nm2 = None if d._noise_map is None else d._noise_map**2
+        full = lambda a: None if a is None else np.broadcast_to(np.asarray(a, dtype=float), d.data.shape)  # noqa: E731
+        exposure = full(getattr(d, "exposure_map", None))
+        offset = 0.0
+        if num.subframe_calc:
+            outside = np.array(self.likelihood_mask, dtype=bool)
+            inside = np.zeros_like(outside)
+            num.cut_frame(inside)[...] = True
+            outside &= ~inside
+            cd0 = nm2 if nm2 is not None else np.full(d.data.shape, float(d.background_rms) ** 2)
+            offset = -0.5 * float(np.sum((d.data**2 / cd0)[outside]))
+        cut = num.cut_frame
+        mask = cut(self.likelihood_mask)
+        return dict(data=cut(d.data), cd_data=cut(np.asarray(d.C_D)), noise_map2=cut(nm2), exposure=cut(exposure),
+                    background_rms=d.background_rms, mask=None if bool(np.all(mask)) else mask, logl_offset=offset)
 
     def _build_plan(self, source_slots, lens_light_slots, n_slots, use_amp, unconvolved, lensed=True,
                     source_fn=None, n_cols=None):
@@ -148,7 +163,7 @@ class ImageModel(object):
         mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light)
         plan = self._joint_plan([bool(source_add)] * self.SourceModel._num_func,
                                 [bool(lens_light_add)] * self.LensLightModel._num_func, unconvolved)
-        out = plan.image(mat)[:, 0]
+        out = self.ImageNumerics.complete_frame(plan.image(mat)[:, 0])
         return self._finish(out, batched, self._want_torch(kwargs_lens, kwargs_source, kwargs_lens_light))
 
     def source_surface_brightness(self, kwargs_source, kwargs_lens=None, kwargs_extinction=None, kwargs_special=None,
@@ -161,13 +176,15 @@ class ImageModel(object):
         mat, B, batched = self._pack(kwargs_lens, kwargs_source, self._dummy_lens_light())
         plan = self._joint_plan(self.SourceModel._bool_list(k), [False] * self.LensLightModel._num_func, unconvolved,
                                 de_lensed=de_lensed)
-        return self._finish(plan.image(mat)[:, 0], batched, self._want_torch(kwargs_lens, kwargs_source))
+        return self._finish(self.ImageNumerics.complete_frame(plan.image(mat)[:, 0]), batched,
+                            self._want_torch(kwargs_lens, kwargs_source))
 
     def lens_surface_brightness(self, kwargs_lens_light, unconvolved=False, k=None):
         """image_model.py:370-393."""
         mat, B, batched = self._pack(self._dummy_lens(), self._dummy_source(), kwargs_lens_light)
         plan = self._joint_plan([False] * self.SourceModel._num_func, self.LensLightModel._bool_list(k), unconvolved)
-        return self._finish(plan.image(mat)[:, 0], batched, self._want_torch(kwargs_lens_light))
+        return self._finish(self.ImageNumerics.complete_frame(plan.image(mat)[:, 0]), batched,
+                            self._want_torch(kwargs_lens_light))
 
     def _dummy(self, names_list):
         return [{n: 1.0 for n in names} for names in names_list]
@@ -204,7 +221,7 @@ class ImageModel(object):
     def image_batch(self, params):
         """[B, P] -> model images [B, ny, nx] (CUDA tensor)."""
         plan = self._joint_plan([True] * self.SourceModel._num_func, [True] * self.LensLightModel._num_func)
-        return plan.image(params)[:, 0]
+        return self.ImageNumerics.complete_frame(plan.image(params)[:, 0])
 
     @property
     def param_names(self):

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("LSIM_LIB") or os.path.join(_HERE, "csrc", "liblsim.so
 
 MAX_PARAMS = 12
 MAX_SLOTS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enum mirrors (include/lsim.h)
 LENS_TYPES = {
@@ -51,12 +51,12 @@ class PlanDesc(C.Structure):
         ("alpha_scaling", C.c_double), ("T_ij_end", C.c_double), ("T_z_source", C.c_double),
         ("n_light", C.c_int32), ("light", C.POINTER(LightDesc)), ("n_slots", C.c_int32),
         ("nx", C.c_int32), ("ny", C.c_int32), ("ss", C.c_int32), ("x_sub", _dp), ("y_sub", _dp),
-        ("conv_mode", C.c_int32), ("kernel_size", C.c_int32), ("kernel", _dp), ("kernel_separable", C.c_int32),
+        ("eval_mask", C.POINTER(C.c_uint8)), ("conv_mode", C.c_int32), ("kernel_size", C.c_int32), ("kernel", _dp), ("kernel_separable", C.c_int32),
         ("kernel_1d", _dp), ("image_scale", C.c_double),
         ("supersampled_conv", C.c_int32), ("kernel_hi_size", C.c_int32), ("kernel_hi", _dp),
         ("kernel_hi_separable", C.c_int32), ("kernel_hi_1d", _dp),
         ("data", _dp), ("cd_data", _dp), ("noise_map2", _dp), ("exposure", _dp), ("background_rms", C.c_double),
-        ("mask", C.POINTER(C.c_uint8)),
+        ("mask", C.POINTER(C.c_uint8)), ("logl_offset", C.c_double),
     ]
 
 
@@ -184,6 +184,12 @@ class Plan:
             keep += [xs, ys]
             d.nx, d.ny, d.ss, d.x_sub, d.y_sub = self.nx, self.ny, self.ss, _ptr(xs), _ptr(ys)
             d.image_scale = float(image_scale)
+            if grid.get("eval_mask") is not None:
+                em = np.ascontiguousarray(np.asarray(grid["eval_mask"]).astype(np.uint8)).ravel()
+                if em.size != self.nx * self.ny:
+                    raise LsimError("eval_mask must hold nx*ny values")
+                keep.append(em)
+                d.eval_mask = em.ctypes.data_as(C.POINTER(C.c_uint8))
             d.conv_mode = CONV_NONE
             if psf is not None and psf["mode"] != CONV_NONE:
                 d.conv_mode = int(psf["mode"])
@@ -218,6 +224,7 @@ class Plan:
                     keep.append(a)
                     setattr(d, name, _ptr(a))
                 d.background_rms = float(data.get("background_rms") or 0.0)
+                d.logl_offset = float(data.get("logl_offset") or 0.0)
                 if data.get("mask") is not None:
                     m = np.ascontiguousarray(np.asarray(data["mask"]).astype(np.uint8)).ravel()
                     assert m.size == npix

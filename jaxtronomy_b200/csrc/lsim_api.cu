@@ -237,6 +237,16 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
     const size_t nsub = (size_t)d->nx * d->ny * d->ss * d->ss, npix = (size_t)d->nx * d->ny;
     TRY(p->upload(d->x_sub, nsub, &D.x_sub));
     TRY(p->upload(d->y_sub, nsub, &D.y_sub));
+    D.n_eval = (int32_t)npix;
+    if (d->eval_mask) {
+      std::vector<int32_t> list;
+      for (size_t i = 0; i < npix; ++i)
+        if (d->eval_mask[i]) list.push_back((int32_t)i);
+      if (list.size() < npix) {
+        D.n_eval = (int32_t)list.size();
+        if (!list.empty()) TRY(p->upload(list.data(), list.size(), &D.eval_list));
+      }
+    }
     D.conv_mode = d->conv_mode;
     D.K = (d->conv_mode != LSIM_CONV_NONE && d->kernel) ? d->kernel_size : 0;
     D.image_scale = d->image_scale;
@@ -271,6 +281,7 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
       }
       D.bkg2 = d->background_rms * d->background_rms;
       if (d->mask) TRY(p->upload(d->mask, npix, &D.mask));
+      D.logl_offset = d->logl_offset;
     }
   }
 #undef TRY
@@ -405,11 +416,25 @@ int launch_image_ns(const lsim_plan* plan, const double* params, int64_t set0, i
   if (sub_out) {  // supersampled convolution: the SUB instantiations (runtime supersampling factor)
     dim3 grid((unsigned)tiles, (unsigned)n);
     Timed timed(kClsImage, st);
+    const bool masked = plan->dev.eval_list != nullptr;
+#define LSIM_SUB_LAUNCH(FULLV, MASKV)                                                                          \
+  k_image<NSLOT, FULLV, 0, RuntimeTypes, RuntimeTypes, true, MASKV><<<grid, kImageBlock, plan->image_smem, st>>>( \
+      plan->dev, params, set0, ppt, scale, out, sub_out)
+    if (plan->full && masked) LSIM_SUB_LAUNCH(true, true);
+    else if (plan->full) LSIM_SUB_LAUNCH(true, false);
+    else if (masked) LSIM_SUB_LAUNCH(false, true);
+    else LSIM_SUB_LAUNCH(false, false);
+#undef LSIM_SUB_LAUNCH
+    return after_launch("k_image");
+  }
+  if (plan->dev.eval_list) {  // masked evaluation: interpreted kernel, runtime supersampling factor
+    dim3 grid((unsigned)tiles, (unsigned)n);
+    Timed timed(kClsImage, st);
     if (plan->full)
-      k_image<NSLOT, true, 0, RuntimeTypes, RuntimeTypes, true><<<grid, kImageBlock, plan->image_smem, st>>>(
+      k_image<NSLOT, true, 0, RuntimeTypes, RuntimeTypes, false, true><<<grid, kImageBlock, plan->image_smem, st>>>(
           plan->dev, params, set0, ppt, scale, out, sub_out);
     else
-      k_image<NSLOT, false, 0, RuntimeTypes, RuntimeTypes, true><<<grid, kImageBlock, plan->image_smem, st>>>(
+      k_image<NSLOT, false, 0, RuntimeTypes, RuntimeTypes, false, true><<<grid, kImageBlock, plan->image_smem, st>>>(
           plan->dev, params, set0, ppt, scale, out, sub_out);
     return after_launch("k_image");
   }
@@ -425,7 +450,14 @@ int launch_image_ns(const lsim_plan* plan, const double* params, int64_t set0, i
 // ray-shoot + light + re-bin for sets [set0, set0+n) -> out[n][n_slots][npix]
 int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, double scale, double* out,
                  double* sub_out, cudaStream_t st) {
-  const int npix = plan->dev.nx * plan->dev.ny;
+  const int npix_all = plan->dev.nx * plan->dev.ny;
+  const int npix = plan->dev.n_eval;  // evaluated pixels
+  if (npix < npix_all) {              // masked pixels keep zero flux
+    const size_t ns = (size_t)plan->dev.n_slots, sub = (size_t)plan->dev.ss * plan->dev.ss;
+    if (out) LSIM_CUDA(cudaMemsetAsync(out, 0, (size_t)n * ns * npix_all * sizeof(double), st));
+    if (sub_out) LSIM_CUDA(cudaMemsetAsync(sub_out, 0, (size_t)n * ns * npix_all * sub * sizeof(double), st));
+    if (npix == 0) return LSIM_OK;
+  }
   int64_t want = ((int64_t)plan->n_sm * 4 + n - 1) / n;  // CTAs per set so that the grid fills the chip
   int max_tiles = (npix + kImageBlock - 1) / kImageBlock;
   int tiles = (int)(want < 1 ? 1 : (want > max_tiles ? max_tiles : want));
@@ -434,7 +466,7 @@ int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int6
   tiles = (npix + ppt - 1) / ppt;
   const int ns = plan->dev.n_slots;
   int rc = LSIM_E_UNSUPPORTED;
-  switch (sub_out ? kSigNone : plan->sig) {
+  switch ((sub_out || plan->dev.eval_list) ? kSigNone : plan->sig) {
     case kSigEplShear_S: rc = launch_image_sig<false, LT_EplShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
     case kSigEplShear_SS: rc = launch_image_sig<false, LT_EplShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
     case kSigNieShear_S: rc = launch_image_sig<false, LT_NieShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;

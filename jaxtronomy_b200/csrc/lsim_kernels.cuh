@@ -38,6 +38,8 @@ struct PlanDev {
   int32_t nx, ny, ss;
   const double* x_sub;
   const double* y_sub;
+  const int32_t* eval_list;  // [n_eval] indices of the pixels that are evaluated, or null = all of them
+  int32_t n_eval;            // number of evaluated pixels (= nx*ny without a mask)
   int32_t conv_mode, K;
   const double* kernel;     // [K*K]
   const double* kernel_1d;  // [K] or null
@@ -51,6 +53,7 @@ struct PlanDev {
   const double* inv_exposure;
   double bkg2;
   const uint8_t* mask;
+  double logl_offset;
 };
 
 // ---- shared-memory staging of per-set constants -----------------------------------------------------------
@@ -162,7 +165,9 @@ k_surface_brightness(PlanDev P, const double* __restrict__ params, const double*
 constexpr int kImageBlock = LSIM_IMAGE_BLOCK;
 // SUB: also write the sub-pixel fluxes (supersampled convolution); a separate instantiation so that the common
 // kernels carry no trace of it.
-template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = RuntimeTypes, bool SUB = false>
+// MASKED: visit only the pixels of P.eval_list (flux_evaluate_indexes); instantiated for the interpreted kernels.
+template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = RuntimeTypes, bool SUB = false,
+          bool MASKED = false>
 __global__ void __launch_bounds__(kImageBlock, LSIM_IMAGE_MIN_BLOCKS)
 k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, double out_scale,
         double* __restrict__ out, double* __restrict__ sub_out) {
@@ -181,8 +186,11 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
   const int ss = SS > 0 ? SS : P.ss;
   const int64_t sub_stride = (int64_t)P.nx * ss;
   const double inv_ss = 1.0 / ss;
-  const int p_end = min(npix, (int)(blockIdx.x + 1) * ppt);
-  for (int p = blockIdx.x * ppt + threadIdx.x; p < p_end; p += kImageBlock) {
+  // flux_evaluate_indexes: only the listed pixels are visited (the others were zero-filled by the host side),
+  // so masked pixels cost nothing and warps stay full
+  const int q_end = min(MASKED ? P.n_eval : npix, (int)(blockIdx.x + 1) * ppt);
+  for (int q = blockIdx.x * ppt + threadIdx.x; q < q_end; q += kImageBlock) {
+    const int p = MASKED ? __ldg(P.eval_list + q) : q;
     const int py = p / P.nx, px = p - py * P.nx;
     double acc[NSLOT];
 #pragma unroll
@@ -244,7 +252,7 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
     }
 #pragma unroll
     for (int k = 0; k < NSLOT; ++k) {
-      if (k < P.n_slots && out) out[(bl * P.n_slots + k) * npix + p] = acc[k] * inv_ss * out_scale;
+      if (k < P.n_slots && (!SUB || out)) out[(bl * P.n_slots + k) * npix + p] = acc[k] * inv_ss * out_scale;
     }
   }
 }
@@ -650,7 +658,7 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
   }
   block_sum(chi, scratch);
   if (threadIdx.x == 0) {
-    double l = -chi[0] / 2;
+    double l = -chi[0] / 2 + P.logl_offset;
     if (linear && marg) l += s_marg;
     logl[set0 + bl] = l;
     if (amps && linear)

@@ -171,27 +171,33 @@ template <int J>
 LSIM_HD void epl_eval(const LensC& L, const double* coef, const double (&xs)[J], const double (&ys)[J],
                       double (&ax)[J], double (&ay)[J]) {
   const double cph = L.c[2], sph = L.c[3], q = L.c[4], f = L.c[5];
-  double a[J], c[J], R2[J], wr[J], wi[J], pr[J], pi[J], pp[J], qq[J], b1[J], b2[J];
+  // Only seven values per point stay live across the series loop: everything that multiplies the series
+  // (Z, (1 - z/2)^-1, the radial power law) is folded into one complex prefactor G beforehand.
+  double wi[J], gr[J], gi[J], pp[J], qq[J], b1[J], b2[J];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int j = 0; j < J; ++j) {
     const double xr = fma(ys[j], sph, xs[j] * cph);
-    c[j] = fma(ys[j], cph, -(xs[j] * sph));
-    a[j] = q * xr;
-    const double aa = a[j] * a[j];
-    R2[j] = fma(c[j], c[j], aa);
-    const double z2r = fma(-c[j], c[j], aa), z2i = 2.0 * a[j] * c[j];
-    const double R2x2 = R2[j] + R2[j];
+    const double c = fma(ys[j], cph, -(xs[j] * sph));
+    const double a = q * xr;
+    const double aa = a * a;
+    const double R2 = fma(c, c, aa);
+    const double z2r = fma(-c, c, aa), z2i = 2.0 * a * c;
+    const double R2x2 = R2 + R2;
     const double Dr = fma(f, z2r, R2x2), Di = f * z2i;
     const double inv = rcp_fast(fma(Dr, Dr, Di * Di));
-    const double finv = f * inv, s2 = R2x2 * inv;
-    wr[j] = fma(z2i, Di, z2r * Dr) * finv;  // Re(Z^2 conj D) f / |D|^2
+    const double finv = f * inv;
+    const double wr = fma(z2i, Di, z2r * Dr) * finv;  // Re(Z^2 conj D) f / |D|^2
     wi[j] = fma(z2i, Dr, -(z2r * Di)) * finv;
-    pr[j] = s2 * Dr;                        // 2 R2 conj(D) / |D|^2
-    pi[j] = -(s2 * Di);
-    pp[j] = wr[j] + wr[j];
-    qq[j] = -fma(wr[j], wr[j], wi[j] * wi[j]);
+    const double R2c = fmax(R2, 1e-18);  // R = max(|Z|, 1e-9)
+    const double P = L.c[8] * exp2_fin(fma(L.c[6], log2_pos(R2c), L.c[7]));
+    const double s2 = R2x2 * inv * P;
+    const double pr = s2 * Dr, pi = -(s2 * Di);  // P 2 R2 conj(D) / |D|^2
+    gr[j] = fma(a, pr, -(c * pi));               // ... times Z
+    gi[j] = fma(a, pi, c * pr);
+    pp[j] = wr + wr;
+    qq[j] = -fma(wr, wr, wi[j] * wi[j]);
     b1[j] = 0.0;
     b2[j] = 0.0;
   }
@@ -211,13 +217,9 @@ LSIM_HD void epl_eval(const LensC& L, const double* coef, const double (&xs)[J],
 #pragma unroll
 #endif
   for (int j = 0; j < J; ++j) {
-    const double Sr = fma(b1[j], wr[j], fma(qq[j], b2[j], c0)), Si = b1[j] * wi[j];
-    // hyp = 2 R2 conj(D)/|D|^2 * S ; R_omega = Z * hyp
-    const double hr = fma(pr[j], Sr, -(pi[j] * Si)), hi = fma(pr[j], Si, pi[j] * Sr);
-    const double orr = fma(a[j], hr, -(c[j] * hi)), oi = fma(a[j], hi, c[j] * hr);
-    const double R2c = fmax(R2[j], 1e-18);  // R = max(|Z|, 1e-9)
-    const double P = L.c[8] * exp2_fin(fma(L.c[6], log2_pos(R2c), L.c[7]));
-    double fr = P * orr, fi = P * oi;
+    const double Sr = fma(b1[j], 0.5 * pp[j], fma(qq[j], b2[j], c0)), Si = b1[j] * wi[j];
+    // R_omega * (b/R)^t 2/(1+q) = G * S
+    double fr = fma(gr[j], Sr, -(gi[j] * Si)), fi = fma(gr[j], Si, gi[j] * Sr);
     if (!(fabs(fr) + fabs(fi) <= DBL_MAX)) {  // nan_to_num(posinf=1e10, neginf=-1e10), epl.py:391-392
       fr = nan_to_num(fr, 1e10, -1e10);
       fi = nan_to_num(fi, 1e10, -1e10);

@@ -10,8 +10,7 @@ Follows (all under /root/reference/jaxtronomy/)
   ImSim/image_model.py:27-150,162-221,223-393,431-492,542-595   ImageModel
   ImSim/image_linear_solve.py:97-181,228-339,361-455            ImageLinearFit
   ImSim/de_lens.py:10-36,39-49,77-105             WLS solve, marginalisation constant
-(NumericsSubFrame with flux_evaluate_indexes -- numerics_subframe.py -- is not restated: out of the
-round-1 scope; flux_evaluate_indexes must be None.)
+  ImSim/Numerics/numerics_subframe.py:15-199      NumericsSubFrame (sub-frame cut / zero padding)
 """
 
 import sys
@@ -45,8 +44,10 @@ class RegularGrid:
 
     @staticmethod
     def _subgrid_index(idex_mask, subgrid_res, nx, ny):
+        # grid.py:119-131 with lenstronomy's array2image, which reshapes to (nx, ny) -- unlike
+        # jaxtronomy's own (ny, nx) -- so each pixel's flag is repeated along x, then whole rows are repeated
         idex_sub = np.repeat(idex_mask, subgrid_res, axis=0)
-        idex_sub = array2image(idex_sub, nx=nx, ny=ny * subgrid_res)
+        idex_sub = np.reshape(idex_sub, (int(nx), int(ny * subgrid_res)))
         idex_sub = np.repeat(idex_sub, subgrid_res, axis=0)
         return image2array(idex_sub)
 
@@ -137,8 +138,6 @@ class Numerics:
     def __init__(self, pixel_grid, psf, supersampling_factor=1, supersampling_convolution=False,
                  convolution_kernel_size=None, convolution_type="fft", truncation_conv=None,
                  flux_evaluate_indexes=None, supersampling_kernel_size=5, **unused):
-        if flux_evaluate_indexes is not None:
-            raise NotImplementedError("oracle: flux_evaluate_indexes not restated (SURVEY 8(f)-2)")
         if not isinstance(supersampling_factor, int):
             raise TypeError("supersampling_factor needs to be an integer! Current type is %s" % type(supersampling_factor))
         if supersampling_factor == 1:
@@ -147,7 +146,8 @@ class Numerics:
         self._pixel_width = pixel_grid.pixel_width
         nx, ny = pixel_grid.num_pixel_axes
         ra0, dec0 = pixel_grid.radec_at_xy_0
-        self._grid = RegularGrid(nx, ny, pixel_grid.transform_pix2angle, ra0, dec0, supersampling_factor)
+        self._grid = RegularGrid(nx, ny, pixel_grid.transform_pix2angle, ra0, dec0, supersampling_factor,
+                                 flux_evaluate_indexes)
         if self._psf_type == "PIXEL":
             if supersampling_convolution is True:
                 kernel_super = psf.kernel_point_source_supersampled(supersampling_factor)
@@ -189,6 +189,39 @@ class Numerics:
         else:
             conv = self._conv.re_size_convolve(low, high)
         return conv * self._pixel_width**2
+
+
+class NumericsSubFrame:
+    """numerics_subframe.py:15-199 (x := array axis 0, as in the reference)."""
+
+    def __init__(self, pixel_grid, psf, flux_evaluate_indexes=None, **kwargs):
+        self._nx, self._ny = pixel_grid.num_pixel_axes
+        if flux_evaluate_indexes is None:
+            self._subframe_calc = False
+            pixel_grid_sub = pixel_grid
+            cut = None
+        else:
+            self._subframe_calc = True
+            idx = np.where(flux_evaluate_indexes)
+            self._x_min, self._x_max = np.min(idx[0]), np.max(idx[0])
+            self._y_min, self._y_max = np.min(idx[1]), np.max(idx[1])
+            ra0, dec0 = pixel_grid.map_pix2coord(self._x_min, self._y_min)
+            pixel_grid_sub = PixelGrid(self._x_max - self._x_min + 1, self._y_max - self._y_min + 1,
+                                       pixel_grid.transform_pix2angle, ra0, dec0)
+            cut = np.asarray(flux_evaluate_indexes)[self._x_min:self._x_max + 1, self._y_min:self._y_max + 1]
+        self._numerics = Numerics(pixel_grid_sub, psf, flux_evaluate_indexes=cut, **kwargs)
+
+    @property
+    def coordinates_evaluate(self):
+        return self._numerics.coordinates_evaluate
+
+    def re_size_convolve(self, flux_array, unconvolved=False):
+        sub = self._numerics.re_size_convolve(flux_array, unconvolved=unconvolved)
+        if not self._subframe_calc:
+            return sub
+        image = np.zeros((self._nx, self._ny))
+        image[self._x_min:self._x_max + 1, self._y_min:self._y_max + 1] = sub
+        return image
 
 
 def covariance_matrix(data, background_rms, exposure_map):
@@ -276,7 +309,7 @@ class ImageModel:
         self.PSF = psf_class
         self._flux_scaling = getattr(data_class, "flux_scaling", 1)
         self.PSF.set_pixel_size(self.Data.pixel_width)
-        self.ImageNumerics = Numerics(pixel_grid=self.Data, psf=self.PSF, **(kwargs_numerics or {}))
+        self.ImageNumerics = NumericsSubFrame(pixel_grid=self.Data, psf=self.PSF, **(kwargs_numerics or {}))
         self.lens_model_list = list(lens_model_list or [])
         self.lens_profile_kwargs_list = lens_profile_kwargs_list
         self.source_model_list = list(source_model_list or [])

@@ -25,6 +25,18 @@ def fwhm2sigma(fwhm):
     return fwhm / (2 * np.sqrt(2 * np.log(2)))
 
 
+def array2image_lenstronomy(array, nx=0, ny=0):
+    """lenstronomy.Util.util.array2image reshapes to (nx, ny); jaxtronomy's own array2image (Util/util.py:18-37)
+    reshapes to (ny, nx).  The reference mixes both (grid.py:128 uses this one)."""
+    array = np.asarray(array)
+    if nx == 0 or ny == 0:
+        n = int(np.sqrt(len(array)))
+        if n**2 != len(array):
+            raise ValueError("length of input array given as %s is not square of integer number!" % len(array))
+        nx, ny = n, n
+    return array.reshape(int(nx), int(ny))
+
+
 def make_grid(numPix, deltapix, subgrid_res=1, left_lower=False):
     if isinstance(numPix, (tuple, list, np.ndarray)):
         numPix = np.asarray(numPix, dtype=int)

@@ -314,6 +314,9 @@ def gen_imsim():
         logL_marg, _ = lin.likelihood_data_given_model(kw_lens_p, cp(kw_src), cp(kw_ll), source_marg=True)
         ins = dict(image_data=noisy, transform_pix2angle=kd["transform_pix2angle"], ra_at_xy_0=kd["ra_at_xy_0"],
                    dec_at_xy_0=kd["dec_at_xy_0"], exposure_time=kd["exposure_time"], background_rms=0.05)
+        num_meta = dict(num_kw)
+        if "flux_evaluate_indexes" in num_meta:
+            ins["flux_evaluate_indexes"] = num_meta.pop("flux_evaluate_indexes")
         if mask is not None:
             ins["likelihood_mask"] = mask
         if noise_map:
@@ -327,7 +330,7 @@ def gen_imsim():
                dict(numPix=numPix, deltaPix=deltaPix, lens_model_list=lens_names, kwargs_lens=kw_lens_p,
                     source_model_list=src_names, kwargs_source=kw_src, lens_light_model_list=ll_names,
                     kwargs_lens_light=kw_ll, kwargs_psf={k: v for k, v in psf_kw.items() if k != "kernel_point_source"},
-                    kwargs_numerics=num_kw, lens_profile_kwargs=profile_kwargs))
+                    kwargs_numerics=num_meta, lens_profile_kwargs=profile_kwargs))
 
     sersic_src = dict(amp=12.0, R_sersic=0.25, n_sersic=2.0, e1=0.1, e2=0.1, center_x=0.05, center_y=0.1)
     sersic_ll = dict(amp=20.0, R_sersic=0.5, n_sersic=3.0, e1=-0.1, e2=0.05, center_x=0.02, center_y=-0.01)
@@ -400,6 +403,37 @@ def gen_imsim():
                [dict(amp=31.0, R_sersic=0.1, n_sersic=2.0, center_x=0.0, center_y=0.0)],
                dict(psf_type="PIXEL", kernel_point_source=kern_super, point_source_supersampling_factor=3),
                dict(supersampling_factor=3, supersampling_convolution=True))
+    # ---- flux_evaluate_indexes: sub-frame evaluation + zero padding (numerics_subframe.py), appended last
+    from jaxtronomy.ImSim.Numerics.numerics_subframe import NumericsSubFrame
+
+    yy, xx = np.mgrid[:20, :20]
+    disk = ((xx - 9.5) ** 2 + (yy - 9.5) ** 2 < 7.2**2)  # symmetric: square sub-frame [3:17, 3:17]
+    for name, psf_kw, num_kw in [
+        ("subframe_pixel", dict(psf_type="PIXEL", kernel_point_source=kern), dict(supersampling_factor=2)),
+        ("subframe_gaussian", dict(psf_type="GAUSSIAN", fwhm=0.2, truncation=5), dict(supersampling_factor=1)),
+    ]:
+        psf = PSF(**psf_kw)
+        psf.set_pixel_size(pg.pixel_width)
+        num = NumericsSubFrame(pg, psf, flux_evaluate_indexes=disk, **num_kw)
+        ra, dec = num.coordinates_evaluate
+        flux = np.exp(-((ra - 0.1) ** 2 + (dec + 0.2) ** 2) / 0.05) + 0.01 * rng.uniform(0, 1, ra.shape)
+        out = np.asarray(num.re_size_convolve(flux))
+        ins = dict(flux=flux, transform_pix2angle=kd["transform_pix2angle"], ra_at_xy_0=kd["ra_at_xy_0"],
+                   dec_at_xy_0=kd["dec_at_xy_0"], flux_evaluate_indexes=disk)
+        if "kernel_point_source" in psf_kw:
+            ins["kernel"] = psf_kw["kernel_point_source"]
+        st.add("numerics_%s" % name, ins,
+               dict(image=out, image_unconvolved=np.asarray(num.re_size_convolve(flux, unconvolved=True)), ra=ra, dec=dec),
+               dict(nx=20, ny=20, kwargs_psf={k: v for k, v in psf_kw.items() if k != "kernel_point_source"},
+                    kwargs_numerics=num_kw, subframe=True))
+    yy, xx = np.mgrid[:36, :36]
+    disk36 = ((xx - 17.5) ** 2 + (yy - 17.5) ** 2 < 13.0**2)
+    lmask = ((xx - 17.5) ** 2 + (yy - 17.5) ** 2 < 15.5**2).astype(float)  # likelihood mask larger than the sub-frame
+    image_case("subframe_epl_shear", 36, 0.09, ["EPL", "SHEAR"],
+               [dict(theta_E=1.1, gamma=2.05, e1=0.2, e2=-0.1, center_x=0.02, center_y=-0.01), shear],
+               ["SERSIC_ELLIPSE"], [sersic_src], ["SERSIC_ELLIPSE"], [sersic_ll],
+               dict(psf_type="PIXEL", kernel_point_source=gauss_kernel(7, 1.2)),
+               dict(supersampling_factor=2, flux_evaluate_indexes=disk36), mask=lmask)
     st.save("imsim.npz")
 
 

@@ -468,7 +468,7 @@ def _make_lenstronomy():
     lutil = mod(
         "lenstronomy.Util.util",
         make_grid=port.make_grid, make_subgrid=lambda ra, dec, subgrid_res=2: port.make_subgrid(ra, dec, subgrid_res),
-        array2image=outil.array2image, image2array=outil.image2array, fwhm2sigma=port.fwhm2sigma,
+        array2image=port.array2image_lenstronomy, image2array=outil.image2array, fwhm2sigma=port.fwhm2sigma,
         convert_bool_list=lambda n, k=None: _bool_list(n, k),
         local_minima_2d=None, selectBest=None, map_coord2pix=port.map_coord2pix,
         make_grid_with_coordtransform=port.make_grid_with_coordtransform,

@@ -57,6 +57,8 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(lsim_plan_desc), offsetof(lsim_plan_desc, lens),
          offsetof(lsim_plan_desc, light), offsetof(lsim_plan_desc, x_sub), offsetof(lsim_plan_desc, data),
          offsetof(lsim_plan_desc, mask));
+  printf("%zu %zu %zu\\n", offsetof(lsim_plan_desc, eval_mask), offsetof(lsim_plan_desc, kernel_hi),
+         offsetof(lsim_plan_desc, logl_offset));
   return 0;
 }''')
     exe = tmp_path / "layout"
@@ -66,7 +68,8 @@ int main(void) {
     L, G, P = _lib.LensDesc, _lib.LightDesc, _lib.PlanDesc
     want = [C.sizeof(L), L.cst.offset, L.opt.offset, L.delta_T.offset, L.red2phys.offset,
             C.sizeof(G), G.col.offset, G.cst.offset,
-            C.sizeof(P), P.lens.offset, P.light.offset, P.x_sub.offset, P.data.offset, P.mask.offset]
+            C.sizeof(P), P.lens.offset, P.light.offset, P.x_sub.offset, P.data.offset, P.mask.offset,
+            P.eval_mask.offset, P.kernel_hi.offset, P.logl_offset.offset]
     assert got == want
 
 

@@ -214,7 +214,13 @@ def test_numerics_re_size_convolve(name):
                    float(c.inp["dec_at_xy_0"]))
     psf = _psf(c.meta["kwargs_psf"], c.inp)
     psf.set_pixel_size(pg.pixel_width)
-    num = Numerics(pg, psf, **c.meta["kwargs_numerics"])
+    if c.meta.get("subframe"):
+        from jaxtronomy_b200.ImSim.Numerics.numerics import NumericsSubFrame
+
+        num = NumericsSubFrame(pg, psf, flux_evaluate_indexes=c.inp["flux_evaluate_indexes"],
+                               **c.meta["kwargs_numerics"])
+    else:
+        num = Numerics(pg, psf, **c.meta["kwargs_numerics"])
     assert_close(num.re_size_convolve(c.inp["flux"]), c.out["image"], what=name, **BAR)
     assert_close(num.re_size_convolve(c.inp["flux"], unconvolved=True), c.out["image_unconvolved"], what=name, **BAR)
     # batched flux: leading axes are kept
@@ -241,10 +247,13 @@ def build_image_model(c, linear=True):
     if "noise_map" in c.inp:
         kd["noise_map"] = c.inp["noise_map"]
     cls = ImageLinearFit if linear else ImageModel
+    kwargs_numerics = dict(c.meta["kwargs_numerics"])
+    if "flux_evaluate_indexes" in c.inp:
+        kwargs_numerics["flux_evaluate_indexes"] = c.inp["flux_evaluate_indexes"]
     return cls(ImageData(**kd), _psf(c.meta["kwargs_psf"], c.inp),
                LensModel(c.meta["lens_model_list"], profile_kwargs_list=c.meta.get("lens_profile_kwargs")),
                LightModel(c.meta["source_model_list"]), LightModel(c.meta["lens_light_model_list"]),
-               kwargs_numerics=c.meta["kwargs_numerics"], likelihood_mask=c.inp.get("likelihood_mask"))
+               kwargs_numerics=kwargs_numerics, likelihood_mask=c.inp.get("likelihood_mask"))
 
 
 IMAGE_CASES = [n for n, c in IMSIM.items() if "logL_linear" in c.out]

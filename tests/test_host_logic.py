@@ -55,13 +55,21 @@ def test_numerics_coordinates_and_kernel(name):
         kw["kernel_point_source"] = c.inp["kernel"]
     psf = PSF(**kw)
     psf.set_pixel_size(pg.pixel_width)
-    num = Numerics(pg, psf, **c.meta["kwargs_numerics"])
+    if c.meta.get("subframe"):
+        from jaxtronomy_b200.ImSim.Numerics.numerics import NumericsSubFrame
+
+        num = NumericsSubFrame(pg, psf, flux_evaluate_indexes=c.inp["flux_evaluate_indexes"],
+                               **c.meta["kwargs_numerics"])
+        assert num.subframe_calc and num.grid_dict()["nx"] < c.meta["nx"]
+    else:
+        num = Numerics(pg, psf, **c.meta["kwargs_numerics"])
     ra, dec = num.coordinates_evaluate
     np.testing.assert_array_equal(ra, c.out["ra"])
     np.testing.assert_array_equal(dec, c.out["dec"])
     if kw["psf_type"] == "GAUSSIAN":
         ss_conv = c.meta["kwargs_numerics"].get("supersampling_convolution", False)
-        k2, k1 = (num._kernel_hi, num._kernel_hi_1d) if ss_conv else (num._kernel, num._kernel_1d)
+        inner = num._numerics_subframe if c.meta.get("subframe") else num
+        k2, k1 = (inner._kernel_hi, inner._kernel_hi_1d) if ss_conv else (inner._kernel, inner._kernel_1d)
         assert k2.shape[0] % 2 == 1 and abs(k2.sum() - 1) < 1e-14
         # the separable factorisation the kernels use reproduces the reference's 2-d kernel to rounding
         assert np.max(np.abs(np.outer(k1, k1) - k2)) < 1e-16
@@ -82,8 +90,12 @@ def test_unsupported_numerics_raise():
     psf = PSF(psf_type="PIXEL", kernel_point_source=np.ones((3, 3)))
     with pytest.raises(NotImplementedError):  # pixel PSF not given at the supersampled resolution
         Numerics(data, psf, supersampling_factor=3, supersampling_convolution=True)
-    with pytest.raises(NotImplementedError):
-        Numerics(data, psf, flux_evaluate_indexes=np.eye(10))
+    from jaxtronomy_b200.ImSim.Numerics.numerics import NumericsSubFrame
+
+    rect = np.zeros((10, 10))
+    rect[2:5, 1:8] = 1
+    with pytest.raises(ValueError):  # rectangular sub-frame: the reference cannot place it back either
+        NumericsSubFrame(data, psf, flux_evaluate_indexes=rect)
     with pytest.raises(ValueError):
         Numerics(data, psf, compute_mode="adaptive")
     with pytest.raises(TypeError):

@@ -139,7 +139,11 @@ def test_numerics_re_size_convolve(name):
                    float(c.inp["dec_at_xy_0"]))
     psf = _psf(c.meta["kwargs_psf"], c.inp)
     psf.set_pixel_size(pg.pixel_width)
-    num = imsim.Numerics(pg, psf, **c.meta["kwargs_numerics"])
+    if c.meta.get("subframe"):
+        num = imsim.NumericsSubFrame(pg, psf, flux_evaluate_indexes=c.inp["flux_evaluate_indexes"],
+                                     **c.meta["kwargs_numerics"])
+    else:
+        num = imsim.Numerics(pg, psf, **c.meta["kwargs_numerics"])
     ra, dec = num.coordinates_evaluate
     np.testing.assert_array_equal(ra, c.out["ra"])
     np.testing.assert_array_equal(dec, c.out["dec"])
@@ -156,8 +160,11 @@ def build_oracle_image_model(c):
         kd["noise_map"] = c.inp["noise_map"]
     data = imsim.ImageData(**kd)
     psf = _psf(c.meta["kwargs_psf"], c.inp)
+    kwargs_numerics = dict(c.meta["kwargs_numerics"])
+    if "flux_evaluate_indexes" in c.inp:
+        kwargs_numerics["flux_evaluate_indexes"] = c.inp["flux_evaluate_indexes"]
     return imsim.ImageModel(data, psf, c.meta["lens_model_list"], c.meta["source_model_list"],
-                            c.meta["lens_light_model_list"], c.meta["kwargs_numerics"],
+                            c.meta["lens_light_model_list"], kwargs_numerics,
                             likelihood_mask=c.inp.get("likelihood_mask"),
                             lens_profile_kwargs_list=c.meta.get("lens_profile_kwargs"))
 
