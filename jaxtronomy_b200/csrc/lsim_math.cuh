@@ -36,21 +36,20 @@ constexpr double kPi = 3.14159265358979323846;
 constexpr double kLog2e = 1.44269504088896340736;
 constexpr double kLn2 = 0.69314718055994530942;
 
-// log2(1+u)/u = (1/ln2) (1 - u/2 + u^2/3 - ...): coefficients (-1)^(k+1)/(k ln2), k = 10..1, highest first
-LSIM_TABLE kLog2C[10] = {-kLog2e / 10.0, kLog2e / 9.0, -kLog2e / 8.0, kLog2e / 7.0, -kLog2e / 6.0,
-                         kLog2e / 5.0,   -kLog2e / 4.0, kLog2e / 3.0, -kLog2e / 2.0, kLog2e};
-// exp(y) Taylor coefficients 1/k!, k = 6..2, highest first
-LSIM_TABLE kExpC[5] = {1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+// log2(1+u)/u = (1/ln2) (1 - u/2 + u^2/3 - ...): coefficients (-1)^(k+1)/(k ln2), k = 6..1, highest first
+LSIM_TABLE kLog2C[6] = {-kLog2e / 6.0, kLog2e / 5.0, -kLog2e / 4.0, kLog2e / 3.0, -kLog2e / 2.0, kLog2e};
+// (2^r - 1)/r = ln2 + ln2^2 r/2 + ...: coefficients ln2^k/k!, k = 4..1, highest first
+LSIM_TABLE kExp2C[4] = {kLn2 * kLn2 * kLn2 * kLn2 / 24.0, kLn2 * kLn2 * kLn2 / 6.0, kLn2 * kLn2 / 2.0, kLn2};
 
-// Lookup tables (tools/gen_math_tables.py): exp2 T[j] = 2^(j/32); log2 {R[i], L[i]} = {~1/c_i, -log2 R[i]} for
-// the 32 bins of the mantissa.  On the device they live in global memory and are read through the read-only
-// L1 path: the index differs from lane to lane, which constant memory would serialise.
+// Lookup tables (tools/gen_math_tables.py): exp2 T[j] = 2^(j/256); log2 {R[i], L[i]} = {~1/c_i, -log2 R[i]} for
+// the 128 bins of the mantissa (2 KB each).  On the device they live in global memory and are read through the
+// read-only L1 path: the index differs from lane to lane, which constant memory would serialise.
 #if defined(__CUDACC__)
-__device__ double d_exp2_tab[32] = LSIM_EXP2_TABLE;
-__device__ double d_log2_tab[64] = LSIM_LOG2_TABLE;
+__device__ double d_exp2_tab[LSIM_EXP2_N] = LSIM_EXP2_TABLE;
+__device__ double d_log2_tab[2 * LSIM_LOG2_N] = LSIM_LOG2_TABLE;
 #endif
-static const double h_exp2_tab[32] = LSIM_EXP2_TABLE;
-static const double h_log2_tab[64] = LSIM_LOG2_TABLE;
+static const double h_exp2_tab[LSIM_EXP2_N] = LSIM_EXP2_TABLE;
+static const double h_log2_tab[2 * LSIM_LOG2_N] = LSIM_LOG2_TABLE;
 
 LSIM_HD int64_t d2i(double x) {
 #if defined(__CUDA_ARCH__)
@@ -96,22 +95,30 @@ LSIM_HD double rcp_fast(double x) {
 #endif
 }
 
+// max(x, lo) / min(x, hi) that PROPAGATE nan like jnp.maximum / jnp.minimum (fmax / fmin drop it and cost a
+// dozen instructions for that): one compare and a select.
+LSIM_HD double max_nan(double x, double lo) { return (x < lo) ? lo : x; }
+LSIM_HD double min_nan(double x, double hi) { return (x > hi) ? hi : x; }
+
 // ---- fast fp64 log2 / exp2 --------------------------------------------------------------------------
 // The hot loop needs pow(x, s) = exp2(s * log2(x)) and exp(-b (k - 1)) for finite positive normal x.
-// libdevice's log/exp/pow carry special-case handling and long polynomials; on a kernel bound by the fp64 pipe
-// every DFMA counts, so both functions are table-driven here (32-entry tables, short Taylor polynomials):
-//   log2_pos(x): x positive, finite, normal.  12 fp64 instructions.  |abs err| < 3e-16 max(1, |log2 x|)
+// libdevice's log/exp/pow carry special-case branches and long polynomials; on a kernel bound by the fp64 pipe
+// every DFMA counts and every branch cuts the instruction stream into blocks the scheduler cannot interleave,
+// so both functions are table-driven and BRANCH-FREE here:
+//   log2_pos(x): x positive, finite, normal.  8 fp64 instructions.  |abs err| < 3e-16 max(1, |log2 x|)
 //                (the result feeds exponents, where absolute accuracy is what matters).
-//   exp2_fin(x): any x; 10 fp64 instructions in the fast path; |rel err| < 4e-16; underflow / overflow / nan
-//                are delegated to the library.
+//   exp2_fin(x): any x; 7 fp64 instructions; |rel err| < 4e-16.  The argument is clamped to [-1022, 1022] with
+//                integer instructions, i.e. results saturate at 2^-1022 (2.2e-308, instead of denormals / 0) and
+//                2^1022 (instead of +inf); nan propagates.
+//   exp2_neg(x): the same for arguments known to stay below 1022 (only the lower clamp).
 
-// x = 2^e m, m in [1,2); bin i = top 5 mantissa bits; u = m R_i - 1, |u| <= 1/64;
+// x = 2^e m, m in [1,2); bin i = top 7 mantissa bits; u = m R_i - 1, |u| <= 1/256;
 // log2 x = e + L_i + log2(1 + u)
 LSIM_HD double log2_pos(double x) {
   const int64_t ix = d2i(x);
   const int e = (int)(ix >> 52) - 1023;
   const double m = i2d((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-  const int i = (int)(ix >> 47) & 31;
+  const int i = (int)(ix >> 45) & (LSIM_LOG2_N - 1);
 #if defined(__CUDA_ARCH__)
   const double2 rl = __ldg(reinterpret_cast<const double2*>(d_log2_tab) + i);
   const double R = rl.x, L = rl.y;
@@ -119,33 +126,47 @@ LSIM_HD double log2_pos(double x) {
   const double R = h_log2_tab[2 * i], L = h_log2_tab[2 * i + 1];
 #endif
   const double u = fma(m, R, -1.0);
-  double p = kLog2C[0];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int k = 1; k < 10; ++k) p = fma(p, u, kLog2C[k]);
+  double p = fma(kLog2C[0], u, kLog2C[1]);
+  p = fma(p, u, kLog2C[2]);
+  p = fma(p, u, kLog2C[3]);
+  p = fma(p, u, kLog2C[4]);
+  p = fma(p, u, kLog2C[5]);
   return (double)e + fma(u, p, L);
 }
 
-// x = k/32 + r, k = rint(32 x), |r| <= 1/64: 2^x = 2^(k>>5) T[k&31] exp(r ln2)
-LSIM_HD double exp2_fin(double x) {
-  if (!(fabs(x) < 1021.0)) return exp2(x);  // rare: underflow / overflow / nan -> the library handles them
-  const double kf = rint(x * 32.0);
+// x = k/256 + r, k = rint(256 x), |r| <= 1/512: 2^x = 2^(k>>8) T[k&255] (1 + r P(r)).  |x| <= 1022 or nan.
+LSIM_HD double exp2_core(double x) {
+#if !defined(__CUDA_ARCH__)
+  if (x != x) return x;  // (int)nan is undefined on the host; the device conversion gives 0 and nan flows through r
+#endif
+  const double kf = rint(x * 256.0);
   const int ki = (int)kf;
-  const double y = fma(kf, -0.03125, x) * kLn2;  // r is exact; |y| <= 0.0109
-  double p = kExpC[0];
+  const double r = fma(kf, -0.00390625, x);  // exact
+  double p = fma(kExp2C[0], r, kExp2C[1]);
+  p = fma(p, r, kExp2C[2]);
+  p = fma(p, r, kExp2C[3]);
 #if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int k = 1; k < 5; ++k) p = fma(p, y, kExpC[k]);
-  p = fma(p, y, 1.0);
-  p = fma(p, y, 1.0);
-#if defined(__CUDA_ARCH__)
-  const double t = __ldg(d_exp2_tab + (ki & 31)) * p;
+  const double T = __ldg(d_exp2_tab + (ki & (LSIM_EXP2_N - 1)));
 #else
-  const double t = h_exp2_tab[ki & 31] * p;
+  const double T = h_exp2_tab[ki & (LSIM_EXP2_N - 1)];
 #endif
-  return i2d(d2i(t) + ((int64_t)(ki >> 5) << 52));  // t in [0.98, 2), |k>>5| <= 1021: stays normal
+  const double t = fma(T * r, p, T);                    // in [0.9986, 1.9974]
+  return i2d(d2i(t) + ((int64_t)(ki >> 8) << 52));      // |k>>8| <= 1022 and (k>>8 = -1022 => t >= 1): stays normal
+}
+
+// 1022.0 = 0x408FF000_00000000: the clamps compare the high word only (exact, the low word of the bound is zero)
+LSIM_HD double exp2_fin(double x) {
+  const int64_t ix = d2i(x);
+  const uint32_t hx = (uint32_t)((uint64_t)ix >> 32), ax = hx & 0x7fffffffu;
+  const bool big = (uint32_t)(ax - 0x408FF000u) <= (0x7ff00000u - 0x408FF000u);  // 1022 <= |x| <= inf, not nan
+  const double xc = big ? i2d((int64_t)(((uint64_t)((hx & 0x80000000u) | 0x408FF000u)) << 32)) : x;
+  return exp2_core(xc);
+}
+
+LSIM_HD double exp2_neg(double x) {
+  const uint32_t hx = (uint32_t)((uint64_t)d2i(x) >> 32);
+  const bool low = (uint32_t)(hx - 0xC08FF000u) <= (0xFFF00000u - 0xC08FF000u);  // -inf <= x <= -1022, not nan
+  return exp2_core(low ? -1022.0 : x);
 }
 
 }  // namespace lsim

@@ -190,7 +190,7 @@ LSIM_HD void epl_eval(const LensC& L, const double* coef, const double (&xs)[J],
     const double finv = f * inv;
     const double wr = fma(z2i, Di, z2r * Dr) * finv;  // Re(Z^2 conj D) f / |D|^2
     wi[j] = fma(z2i, Dr, -(z2r * Di)) * finv;
-    const double R2c = fmax(R2, 1e-18);  // R = max(|Z|, 1e-9)
+    const double R2c = max_nan(R2, 1e-18);  // R = max(|Z|, 1e-9)
     const double P = L.c[8] * exp2_fin(fma(L.c[6], log2_pos(R2c), L.c[7]));
     const double s2 = R2x2 * inv * P;
     const double pr = s2 * Dr, pi = -(s2 * Di);  // P 2 R2 conj(D) / |D|^2
@@ -213,19 +213,36 @@ LSIM_HD void epl_eval(const LensC& L, const double* coef, const double (&xs)[J],
     }
   }
   const double c0 = coef[0];
+  double fr[J], fi[J];
+  uint32_t worst = 0;  // largest |high word| of the results: >= 0x7ff00000 <=> some component is inf / nan
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int j = 0; j < J; ++j) {
     const double Sr = fma(b1[j], 0.5 * pp[j], fma(qq[j], b2[j], c0)), Si = b1[j] * wi[j];
     // R_omega * (b/R)^t 2/(1+q) = G * S
-    double fr = fma(gr[j], Sr, -(gi[j] * Si)), fi = fma(gr[j], Si, gi[j] * Sr);
-    if (!(fabs(fr) + fabs(fi) <= DBL_MAX)) {  // nan_to_num(posinf=1e10, neginf=-1e10), epl.py:391-392
-      fr = nan_to_num(fr, 1e10, -1e10);
-      fi = nan_to_num(fi, 1e10, -1e10);
+    fr[j] = fma(gr[j], Sr, -(gi[j] * Si));
+    fi[j] = fma(gr[j], Si, gi[j] * Sr);
+    const uint32_t hr = (uint32_t)((uint64_t)d2i(fr[j]) >> 32) & 0x7fffffffu;
+    const uint32_t hi = (uint32_t)((uint64_t)d2i(fi[j]) >> 32) & 0x7fffffffu;
+    worst = worst > hr ? worst : hr;
+    worst = worst > hi ? worst : hi;
+  }
+  if (worst >= 0x7ff00000u) {  // rare; one test for all J points: nan_to_num(posinf=1e10, neginf=-1e10), epl.py:391-392
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < J; ++j) {
+      fr[j] = nan_to_num(fr[j], 1e10, -1e10);
+      fi[j] = nan_to_num(fi[j], 1e10, -1e10);
     }
-    ax[j] = fma(-fi, sph, fr * cph);  // rotate(f, -phi)
-    ay[j] = fma(fi, cph, fr * sph);
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    ax[j] = fma(-fi[j], sph, fr[j] * cph);  // rotate(f, -phi)
+    ay[j] = fma(fi[j], cph, fr[j] * sph);
   }
 }
 
@@ -795,7 +812,7 @@ LSIM_HD void light_prepare(const lsim_light_desc& d, const double* row, LightC& 
       G.c[5] = 0.5 / n;
       G.c[6] = -log2(Rs_) / n;
       G.c[7] = -bn * kLog2e;
-      G.c[8] = bn * kLog2e;
+      G.c[8] = fmin(bn * kLog2e, 1021.0);  // exp(bn) overflows beyond (n_sersic > 354): saturate
       G.c[9] = (1000.0 * Rs_) * (1000.0 * Rs_);
       G.c[10] = amp;
       G.type = LSIM_LIGHT_SERSIC_ELLIPSE;
@@ -827,9 +844,9 @@ LSIM_HD void light_eval(int type, const LightC& G, const double (&x)[J], const d
       const double xs = x[j] - G.c[0], ys = y[j] - G.c[1];
       const double xt = fma(G.c[3], ys, G.c[2] * xs);
       const double yt = fma(G.c[4], ys, G.c[3] * xs);
-      const double R2c = fmax(fma(yt, yt, xt * xt), 1e-8);  // R_ = max(1e-4, R)
+      const double R2c = max_nan(fma(yt, yt, xt * xt), 1e-8);  // R_ = max(1e-4, R)
       const double k = exp2_fin(fma(G.c[5], log2_pos(R2c), G.c[6]));
-      double e = exp2_fin(fma(G.c[7], k, G.c[8]));
+      double e = exp2_neg(fma(G.c[7], k, G.c[8]));  // k >= 0, c[7] <= 0: the argument is at most c[8] <= 1021
       e = (R2c <= G.c[9]) ? e : 0.0;  // R_/Rs_ <= max_R_frac
       e = (e == e) ? e : 0.0;         // nan_to_num (the exponent is bounded above, so no +inf)
       v[j] = G.c[10] * e;

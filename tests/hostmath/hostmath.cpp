@@ -70,6 +70,9 @@ void hm_log2(const double* x, int64_t n, double* out) {
 void hm_exp2(const double* x, int64_t n, double* out) {
   for (int64_t i = 0; i < n; ++i) out[i] = exp2_fin(x[i]);
 }
+void hm_exp2_neg(const double* x, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = exp2_neg(x[i]);
+}
 int hm_epl_terms(const lsim_lens_desc* lens, const double* row, double series_tol) {
   LensC L;
   std::vector<double> pool(kMaxSeries);

@@ -37,6 +37,7 @@ def lib():
         h.hm_surface_brightness.argtypes = [C.POINTER(_lib.LightDesc), C.c_int, C.c_int, _dp, _dp, _dp, C.c_int64, _dp]
         h.hm_log2.argtypes = [_dp, C.c_int64, _dp]
         h.hm_exp2.argtypes = [_dp, C.c_int64, _dp]
+        h.hm_exp2_neg.argtypes = [_dp, C.c_int64, _dp]
         h.hm_epl_terms.argtypes = [C.POINTER(_lib.LensDesc), _dp, C.c_double]
         _h = h
     return _h
@@ -100,4 +101,11 @@ def exp2(x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty_like(x)
     lib().hm_exp2(_p(x), x.size, _p(out))
+    return out
+
+
+def exp2_neg(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    lib().hm_exp2_neg(_p(x), x.size, _p(out))
     return out

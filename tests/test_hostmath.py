@@ -40,12 +40,19 @@ def test_log2_exp2_accuracy():
     near1 = np.abs(x - 1) < 0.3
     assert np.max(np.abs(got[near1] - ref[near1])) < 3e-16
     assert abs(hm.log2(np.array([1.0]))[0]) < 1e-17
-    e = np.concatenate([rng.uniform(-1000, 1000, 40000), rng.uniform(-2, 2, 20000), [0.0, 1.0, -1.0, 0.5, -1021.5]])
+    e = np.concatenate([rng.uniform(-1022, 1022, 40000), rng.uniform(-2, 2, 20000),
+                        [0.0, 1.0, -1.0, 0.5, -1021.5, -1022.0, 1022.0, 1021.999, -1021.999]])
     got, ref = hm.exp2(e), np.exp2(e)
     assert np.max(np.abs(got - ref) / ref) < 4e-16
     assert hm.exp2(np.array([0.0]))[0] == 1.0
-    assert hm.exp2(np.array([-1100.0, -5000.0]))[0] == 0.0 and hm.exp2(np.array([-5000.0]))[0] == 0.0
-    assert np.isinf(hm.exp2(np.array([1025.0]))[0]) and np.isnan(hm.exp2(np.array([np.nan]))[0])
+    # branch-free saturation: results below 2^-1022 (denormals, 0) read 2^-1022 = 2.2e-308, above 2^1022 read 2^1022
+    lo, hi = 2.0 ** -1022, 2.0 ** 1022
+    assert list(hm.exp2(np.array([-1022.5, -1100.0, -5000.0, -1e300, -np.inf]))) == [lo] * 5
+    assert list(hm.exp2(np.array([1022.5, 1025.0, 1e300, np.inf]))) == [hi] * 4
+    assert np.isnan(hm.exp2(np.array([np.nan]))[0]) and np.isnan(hm.exp2(np.array([-np.nan]))[0])
+    neg = np.concatenate([rng.uniform(-1022, 1021, 20000), [-1022.0, -1500.0, -np.inf, 0.0, 1021.0]])
+    got, ref = hm.exp2_neg(neg), np.maximum(np.exp2(np.maximum(neg, -1022.0)), lo)
+    assert np.max(np.abs(got - ref) / ref) < 4e-16 and np.isnan(hm.exp2_neg(np.array([np.nan]))[0])
 
 
 @pytest.mark.parametrize("name", [n for n, c in PROFILES.items() if "f_x" in c.out and "profile" in c.meta])
