@@ -90,6 +90,7 @@ k_ray_shoot(PlanDev P, const double* __restrict__ params, const double* __restri
   const double* xb = coords_batched ? x + b * N : x;
   const double* yb = coords_batched ? y + b * N : y;
 
+  stage_math_tables();  // made visible by the __syncthreads() of the first chunk
   Rays<kRayItems> r;
   int64_t idx[kRayItems];
 #pragma unroll
@@ -129,6 +130,7 @@ k_surface_brightness(PlanDev P, const double* __restrict__ params, const double*
   __shared__ LightC G[kMaxLight];
   const int64_t b = blockIdx.y;
   const double* row = params + b * P.n_param_cols;
+  stage_math_tables();
   stage_light(P, row, G);
   __syncthreads();
   const double* xb = coords_batched ? x + b * N : x;
@@ -143,6 +145,13 @@ k_surface_brightness(PlanDev P, const double* __restrict__ params, const double*
       out[(b * P.n_slots + s) * N + i] = acc;
     }
   }
+}
+
+// A second read of a value loaded before: `volatile` keeps the compiler from merging it with the first load.
+__device__ __forceinline__ double ldg_again(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
 }
 
 // ---- k_image: fused ray-shoot + light + re-bin ---------------------------------------------------------------
@@ -178,6 +187,7 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
   double* pool = reinterpret_cast<double*>(G + P.n_light);
   const int64_t bl = blockIdx.y;
   const double* row = params + (set0 + bl) * P.n_param_cols;
+  stage_math_tables();
   stage_lens(P, row, 0, P.n_lens, L, pool);
   stage_light(P, row, G);
   __syncthreads();
@@ -201,17 +211,30 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
       for (int k = 0; k < NSLOT; ++k) racc[k] = 0.0;
       const int64_t base = ((int64_t)py * ss + i) * sub_stride + (int64_t)px * ss;
       for (int j0 = 0; j0 < ss; j0 += J) {
+        constexpr bool kSingle = LT::N >= 0;  // specialised kernels are single-plane
         double x[J], y[J], bx[J], by[J], v[J];
         Rays<J> r;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
           x[j] = __ldg(P.x_sub + base + j0 + j);
           y[j] = __ldg(P.y_sub + base + j0 + j);
-          ray_init(P.ray, j, x[j], y[j], r);
+          ray_init<J, kSingle>(P.ray, j, x[j], y[j], r);
         }
         ray_apply<FULL, J, LT>(P.ray, L, pool, P.n_lens, r);
+        if (kSingle) {
+          // the image-plane coordinates are needed again only now (beta = theta - alpha, unlensed light): read them
+          // a second time (L1 hit) instead of keeping 4 J registers alive across the deflector evaluation
 #pragma unroll
-        for (int j = 0; j < J; ++j) ray_finish(P.ray, r, j, bx[j], by[j]);
+          for (int j = 0; j < J; ++j) {
+            x[j] = ldg_again(P.x_sub + base + j0 + j);
+            y[j] = ldg_again(P.y_sub + base + j0 + j);
+            bx[j] = x[j] - r.ax[j] * P.ray.alpha_scaling;
+            by[j] = y[j] - r.ay[j] * P.ray.alpha_scaling;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < J; ++j) ray_finish(P.ray, r, j, bx[j], by[j]);
+        }
         unsigned written = 0;  // slots whose sub-pixels of this batch hold a value already (sub_out only)
         auto one_light = [&](int type, const LightC& Gg) {
           const int slot = Gg.slot;

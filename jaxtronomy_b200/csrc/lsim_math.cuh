@@ -42,11 +42,21 @@ LSIM_TABLE kLog2C[6] = {-kLog2e / 6.0, kLog2e / 5.0, -kLog2e / 4.0, kLog2e / 3.0
 LSIM_TABLE kExp2C[4] = {kLn2 * kLn2 * kLn2 * kLn2 / 24.0, kLn2 * kLn2 * kLn2 / 6.0, kLn2 * kLn2 / 2.0, kLn2};
 
 // Lookup tables (tools/gen_math_tables.py): exp2 T[j] = 2^(j/256); log2 {R[i], L[i]} = {~1/c_i, -log2 R[i]} for
-// the 128 bins of the mantissa (2 KB each).  On the device they live in global memory and are read through the
-// read-only L1 path: the index differs from lane to lane, which constant memory would serialise.
+// the 128 bins of the mantissa (2 KB each).  The index differs from lane to lane, which constant memory would
+// serialise, so every kernel that evaluates profiles copies the tables from global into SHARED memory once per CTA
+// (stage_math_tables): a lookup is then one LDS at a 32-bit offset (no 64-bit address arithmetic, lower latency
+// than an L1 hit).
 #if defined(__CUDACC__)
 __device__ double d_exp2_tab[LSIM_EXP2_N] = LSIM_EXP2_TABLE;
 __device__ double d_log2_tab[2 * LSIM_LOG2_N] = LSIM_LOG2_TABLE;
+__shared__ double s_exp2_tab[LSIM_EXP2_N];
+__shared__ double2 s_log2_tab[LSIM_LOG2_N];
+// call at kernel entry, followed by a __syncthreads() before the first log2_pos / exp2_*
+__device__ __forceinline__ void stage_math_tables() {
+  for (int i = threadIdx.x; i < LSIM_EXP2_N; i += blockDim.x) s_exp2_tab[i] = d_exp2_tab[i];
+  for (int i = threadIdx.x; i < LSIM_LOG2_N; i += blockDim.x)
+    s_log2_tab[i] = reinterpret_cast<const double2*>(d_log2_tab)[i];
+}
 #endif
 static const double h_exp2_tab[LSIM_EXP2_N] = LSIM_EXP2_TABLE;
 static const double h_log2_tab[2 * LSIM_LOG2_N] = LSIM_LOG2_TABLE;
@@ -120,7 +130,7 @@ LSIM_HD double log2_pos(double x) {
   const double m = i2d((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
   const int i = (int)(ix >> 45) & (LSIM_LOG2_N - 1);
 #if defined(__CUDA_ARCH__)
-  const double2 rl = __ldg(reinterpret_cast<const double2*>(d_log2_tab) + i);
+  const double2 rl = s_log2_tab[i];
   const double R = rl.x, L = rl.y;
 #else
   const double R = h_log2_tab[2 * i], L = h_log2_tab[2 * i + 1];
@@ -146,12 +156,18 @@ LSIM_HD double exp2_core(double x) {
   p = fma(p, r, kExp2C[2]);
   p = fma(p, r, kExp2C[3]);
 #if defined(__CUDA_ARCH__)
-  const double T = __ldg(d_exp2_tab + (ki & (LSIM_EXP2_N - 1)));
+  const double T = s_exp2_tab[ki & (LSIM_EXP2_N - 1)];
 #else
   const double T = h_exp2_tab[ki & (LSIM_EXP2_N - 1)];
 #endif
-  const double t = fma(T * r, p, T);                    // in [0.9986, 1.9974]
-  return i2d(d2i(t) + ((int64_t)(ki >> 8) << 52));      // |k>>8| <= 1022 and (k>>8 = -1022 => t >= 1): stays normal
+  const double t = fma(T * r, p, T);  // in [0.9986, 1.9974]
+  // scale by 2^(k>>8): |k>>8| <= 1022 and (k>>8 = -1022 => t >= 1), so the result stays normal and the exponent
+  // can be added to the high word alone
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(t) + ((ki >> 8) << 20), __double2loint(t));
+#else
+  return i2d(d2i(t) + ((int64_t)(ki >> 8) << 52));
+#endif
 }
 
 // 1022.0 = 0x408FF000_00000000: the clamps compare the high word only (exact, the low word of the bound is zero)

@@ -750,9 +750,10 @@ LSIM_HD void ray_apply(const RayCfg& P, const LensC* L, const double* pool, int 
   }
 }
 
-template <int J>
+// SINGLE: single-plane lensing known at compile time (the specialised kernels)
+template <int J, bool SINGLE = false>
 LSIM_HD void ray_init(const RayCfg& P, int j, double x, double y, Rays<J>& r) {
-  if (!P.multi_plane) {
+  if (SINGLE || !P.multi_plane) {
     r.x[j] = x;
     r.y[j] = y;
     r.ax[j] = 0;
@@ -766,9 +767,9 @@ LSIM_HD void ray_init(const RayCfg& P, int j, double x, double y, Rays<J>& r) {
 }
 
 // -> source-plane position
-template <int J>
+template <int J, bool SINGLE = false>
 LSIM_HD void ray_finish(const RayCfg& P, const Rays<J>& r, int j, double& bx, double& by) {
-  if (!P.multi_plane) {
+  if (SINGLE || !P.multi_plane) {
     bx = r.x[j] - r.ax[j] * P.alpha_scaling;
     by = r.y[j] - r.ay[j] * P.alpha_scaling;
   } else {
