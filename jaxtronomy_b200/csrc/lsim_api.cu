@@ -458,7 +458,12 @@ int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int6
     if (sub_out) LSIM_CUDA(cudaMemsetAsync(sub_out, 0, (size_t)n * ns * npix_all * sub * sizeof(double), st));
     if (npix == 0) return LSIM_OK;
   }
-  int64_t want = ((int64_t)plan->n_sm * 4 + n - 1) / n;  // CTAs per set so that the grid fills the chip
+  // CTAs per set: all CTAs of a launch cost the same, so a grid of w.x "waves" of resident CTAs runs like
+  // ceil(w.x) waves (1184 sets x 1 CTA on 148 SMs x 3 resident = 2.67 waves took the time of 3).  Ask for >= 16
+  // waves: the partial last wave then costs at most ~3 %, and the per-CTA parameter preparation stays amortised
+  // over thousands of pixels.
+  const int64_t resident = (int64_t)plan->n_sm * LSIM_IMAGE_MIN_BLOCKS;
+  int64_t want = (16 * resident + n - 1) / n;
   int max_tiles = (npix + kImageBlock - 1) / kImageBlock;
   int tiles = (int)(want < 1 ? 1 : (want > max_tiles ? max_tiles : want));
   int ppt = (npix + tiles - 1) / tiles;
