@@ -107,3 +107,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_xla_ffi_shim_is_header_gated(tmp_path):
+    """csrc/lsim_xla_ffi.cc must compile without the jax headers (to the one-symbol stub) so that it can sit in
+    the tree of a box that has no jax; with the headers it defines the three XLA-FFI handlers."""
+    import subprocess
+
+    src = os.path.join(ROOT, "jaxtronomy_b200", "csrc", "lsim_xla_ffi.cc")
+    so = str(tmp_path / "shim.so")
+    subprocess.check_call(["g++", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), src, "-o", so])
+    h = C.CDLL(so)
+    assert h.lsim_xla_ffi_unavailable() == 1
+    text = open(src).read()
+    for handler in ("LsimLogl", "LsimImage", "LsimRayShoot"):
+        assert "XLA_FFI_DEFINE_HANDLER_SYMBOL(%s" % handler in text
