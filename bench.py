@@ -250,6 +250,10 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.batch
+    if args.precision == "f32":
+        import jaxtronomy_b200
+
+        jaxtronomy_b200.config.update("enable_x64", False)
     cfg = build_headline(n_sets=B, seed=1234)
     model = cfg["model"]
     lo, hi = parallel.shard_bounds(B, world, rank)
@@ -336,7 +340,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "headline: EPL+SHEAR, SERSIC_ELLIPSE source, 180x180, ss=3, 21x21 pixel PSF, "
                                    "ImageLinearFit likelihood", "particles": B, "parallelism": "particle shards x%d, "
                        "NCCL all-gather of logL" % world,
@@ -361,6 +365,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-images", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
+                    help="f32: the opt-in single-precision image kernel (NOT the headline; dtype is reported)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

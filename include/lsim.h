@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LSIM_ABI_VERSION 3
+#define LSIM_ABI_VERSION 4
 #define LSIM_MAX_PARAMS 12 /* largest param_names list on the path: EPL_MULTIPOLE_M1M3M4 */
 #define LSIM_MAX_SLOTS 8   /* output / linear-basis images per parameter set */
 
@@ -98,6 +98,8 @@ typedef struct lsim_light_desc {
   double cst[LSIM_MAX_PARAMS];
 } lsim_light_desc;
 
+enum { LSIM_PRECISION_F64 = 0, LSIM_PRECISION_F32 = 1 };
+
 /* PSF convolution on the pixel grid (ImSim/Numerics/convolution.py) */
 enum {
   LSIM_CONV_NONE = 0,      /* psf_type NONE or unconvolved=True (numerics.py:170-171) */
@@ -158,6 +160,11 @@ typedef struct lsim_plan_desc {
   const uint8_t* mask;      /* host [ny*nx] likelihood mask (1 = use), or NULL = all ones (image_model.py:134-142) */
   double logl_offset;       /* added to every log-likelihood: -chi^2/2 of the likelihood pixels outside the
                                evaluated sub-frame, where the model is identically zero (numerics_subframe.py:134-148) */
+  /* arithmetic of the fused image kernel (ray shooting + light + re-bin).  LSIM_PRECISION_F64 (0, default): fp64,
+   * the parity-tested path.  LSIM_PRECISION_F32: opt-in single precision for that kernel only (the reference's
+   * counterpart is running without jax_enable_x64); convolution and likelihood stay fp64.  Refused with
+   * LSIM_E_UNSUPPORTED for models outside its scope (see csrc/lsim_f32.cuh) -- never a silent fp64 fallback. */
+  int32_t precision;
 } lsim_plan_desc;
 
 typedef struct lsim_plan lsim_plan;

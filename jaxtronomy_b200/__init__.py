@@ -8,3 +8,5 @@ ImageModel.image, ImageLinearFit.likelihood_data_given_model); there is no CPU f
 """
 
 __version__ = "0.1.0"
+
+from jaxtronomy_b200 import config  # noqa: E402,F401

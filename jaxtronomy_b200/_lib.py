@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("LSIM_LIB") or os.path.join(_HERE, "csrc", "liblsim.so
 
 MAX_PARAMS = 12
 MAX_SLOTS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
+PRECISION_F64, PRECISION_F32 = 0, 1
 
 # enum mirrors (include/lsim.h)
 LENS_TYPES = {
@@ -56,7 +57,7 @@ class PlanDesc(C.Structure):
         ("supersampled_conv", C.c_int32), ("kernel_hi_size", C.c_int32), ("kernel_hi", _dp),
         ("kernel_hi_separable", C.c_int32), ("kernel_hi_1d", _dp),
         ("data", _dp), ("cd_data", _dp), ("noise_map2", _dp), ("exposure", _dp), ("background_rms", C.c_double),
-        ("mask", C.POINTER(C.c_uint8)), ("logl_offset", C.c_double),
+        ("mask", C.POINTER(C.c_uint8)), ("logl_offset", C.c_double), ("precision", C.c_int32),
     ]
 
 
@@ -184,6 +185,9 @@ class Plan:
             keep += [xs, ys]
             d.nx, d.ny, d.ss, d.x_sub, d.y_sub = self.nx, self.ny, self.ss, _ptr(xs), _ptr(ys)
             d.image_scale = float(image_scale)
+            from jaxtronomy_b200 import config
+
+            d.precision = PRECISION_F64 if config.read("enable_x64") else PRECISION_F32
             if grid.get("eval_mask") is not None:
                 em = np.ascontiguousarray(np.asarray(grid["eval_mask"]).astype(np.uint8)).ravel()
                 if em.size != self.nx * self.ny:

@@ -8,6 +8,7 @@
 
 #include "../../include/lsim.h"
 #include "lsim_kernels.cuh"
+#include "lsim_f32.cuh"
 
 using namespace lsim;
 
@@ -75,6 +76,7 @@ struct lsim_plan {
   int n_series = 0;
   int sig = -1;  // index of the specialised image kernel for this model, or -1
   bool has_image = false, has_data = false;
+  bool f32 = false;  // LSIM_PRECISION_F32: the image kernel runs in single precision
   size_t image_smem = 0;
   int n_sm = 148;
 
@@ -195,6 +197,8 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
     }
   }
   const bool has_data = has_image && d->data && d->cd_data && (d->noise_map2 || d->exposure);
+  if (d->precision != LSIM_PRECISION_F64 && d->precision != LSIM_PRECISION_F32) return LSIM_E_INVALID;
+  if (d->precision == LSIM_PRECISION_F32 && !f32_supported(d)) return LSIM_E_UNSUPPORTED;
 
   lsim_plan* p = new (std::nothrow) lsim_plan();
   if (!p) return LSIM_E_INVALID;
@@ -230,6 +234,7 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
   p->sig = find_signature(d);
   p->has_image = has_image;
   p->has_data = has_data;
+  p->f32 = d->precision == LSIM_PRECISION_F32;
   if (has_image) {
     D.nx = d->nx;
     D.ny = d->ny;
@@ -264,6 +269,7 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
     }
     p->image_smem = (size_t)d->n_lens * sizeof(LensC) + (size_t)d->n_light * sizeof(LightC) +
                     (size_t)n_series * kMaxSeries * sizeof(double);
+    if (p->f32) p->image_smem += f32_extra_smem(d->n_lens, d->n_light, n_series);
     if (p->image_smem > 48 * 1024) {
       delete p;
       return LSIM_E_UNSUPPORTED;
@@ -447,6 +453,34 @@ int launch_image_ns(const lsim_plan* plan, const double* params, int64_t set0, i
   }
 }
 
+// LSIM_PRECISION_F32: the single-precision image kernel (interpreted profile lists, lock-step rows for ss <= 3)
+template <int NSLOT>
+int launch_image_f32_ns(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
+                        double scale, double* out, cudaStream_t st) {
+  dim3 grid((unsigned)tiles, (unsigned)n);
+  Timed timed(kClsImage, st);
+#define LSIM_F32_LAUNCH(SSV)                                                                                   \
+  k_image_f32<NSLOT, SSV><<<grid, kImageBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, \
+                                                                        plan->n_series, out)
+  switch (plan->dev.ss) {
+    case 1: LSIM_F32_LAUNCH(1); break;
+    case 2: LSIM_F32_LAUNCH(2); break;
+    case 3: LSIM_F32_LAUNCH(3); break;
+    default: LSIM_F32_LAUNCH(0); break;
+  }
+#undef LSIM_F32_LAUNCH
+  return after_launch("k_image_f32");
+}
+
+int launch_image_f32(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
+                     double scale, double* out, cudaStream_t st) {
+  const int ns = plan->dev.n_slots;
+  if (ns <= 1) return launch_image_f32_ns<1>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  if (ns <= 2) return launch_image_f32_ns<2>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  if (ns <= 4) return launch_image_f32_ns<4>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  return launch_image_f32_ns<8>(plan, params, set0, n, ppt, tiles, scale, out, st);
+}
+
 // ray-shoot + light + re-bin for sets [set0, set0+n) -> out[n][n_slots][npix]
 int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, double scale, double* out,
                  double* sub_out, cudaStream_t st) {
@@ -470,6 +504,7 @@ int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int6
   ppt = ((ppt + kImageBlock - 1) / kImageBlock) * kImageBlock;
   tiles = (npix + ppt - 1) / ppt;
   const int ns = plan->dev.n_slots;
+  if (plan->f32) return launch_image_f32(plan, params, set0, n, ppt, tiles, scale, out, st);
   int rc = LSIM_E_UNSUPPORTED;
   switch ((sub_out || plan->dev.eval_list) ? kSigNone : plan->sig) {
     case kSigEplShear_S: rc = launch_image_sig<false, LT_EplShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;

@@ -392,3 +392,49 @@ def test_fp64_peak_microbenchmark_runs():
 
     flops = _lib.measure_fp64_peak(20000)
     assert 1e12 < flops < 1e14
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# opt-in fp32 image kernel (jaxtronomy_b200.config.update("enable_x64", False)): stated looser tolerance
+# ---------------------------------------------------------------------------------------------------------------
+FP32_IMAGE_RTOL, FP32_IMAGE_ATOL_FRAC, FP32_LOGL_RTOL = 2e-4, 2e-5, 2e-4
+
+
+def test_fp32_variant(headline):
+    """fp32 image kernel vs the fp64 path (itself at 1e-10 of the reference) on the headline workload:
+    images |a-b| <= 2e-4 |b| + 2e-5 max|b|, log-likelihood and amplitudes within 2e-4 relative."""
+    import jaxtronomy_b200
+    from bench import build_headline
+    from jaxtronomy_b200 import _lib
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+
+    params = headline["params"][:64]
+    img64 = headline["model"].image_batch(params).cpu().numpy()
+    l64, a64, _ = headline["model"].logL_linear_batch(params)
+    jaxtronomy_b200.config.update("enable_x64", False)
+    try:
+        m32 = build_headline(n_sets=4, seed=77, data_image=headline["data_image"])["model"]
+        img32 = m32.image_batch(params).cpu().numpy()
+        l32, a32, _ = m32.logL_linear_batch(params)
+        # a model outside the fp32 kernel's scope is refused loudly, not run in fp64 behind the caller's back
+        with pytest.raises(_lib.LsimError):
+            from jaxtronomy_b200.Data.imaging_data import ImageData
+            from jaxtronomy_b200.Data.psf import PSF
+            from jaxtronomy_b200.ImSim.image_model import ImageModel
+            from jaxtronomy_b200.LightModel.light_model import LightModel
+
+            st = headline["static"]
+            data = ImageData(image_data=headline["data_image"], **st["kwargs_data"])
+            im = ImageModel(data, PSF(psf_type="NONE"), LensModel(["NFW"]), LightModel(["SERSIC"]), LightModel([]),
+                            kwargs_numerics=dict(supersampling_factor=1))
+            im.image([dict(Rs=1.0, alpha_Rs=1.0, center_x=0.0, center_y=0.0)],
+                     [dict(amp=1.0, R_sersic=0.3, n_sersic=2.0, center_x=0.0, center_y=0.0)], [])
+    finally:
+        jaxtronomy_b200.config.update("enable_x64", True)
+    tol = FP32_IMAGE_RTOL * np.abs(img64) + FP32_IMAGE_ATOL_FRAC * np.abs(img64).max(axis=(1, 2), keepdims=True)
+    err = np.abs(img32 - img64)
+    assert np.all(err <= tol), float(np.max(err / tol))
+    assert not np.array_equal(img32, img64)  # it really is a different arithmetic
+    l64, l32, a64, a32 = l64.cpu().numpy(), l32.cpu().numpy(), a64.cpu().numpy(), a32.cpu().numpy()
+    assert np.max(np.abs(l32 - l64) / np.abs(l64)) <= FP32_LOGL_RTOL
+    assert np.max(np.abs(a32 - a64) / np.abs(a64)) <= FP32_LOGL_RTOL
