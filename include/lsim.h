@@ -215,6 +215,23 @@ int lsim_resize_convolve(const lsim_plan* plan, const double* flux, int64_t n_im
 int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear_solve, int source_marg,
               double* logl, double* amps, double* model, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One particle-swarm iteration AFTER the fitness evaluation, entirely on the device: the loop body
+ * of lenstronomy's ParticleSwarmOptimizer._sample that jaxtronomy/Sampling/Samplers/pso.py:11-66 inherits, i.e.
+ *   global best   <- the particle with the largest fitness if it beats the current one (first wins on ties)
+ *   personal best <- position / fitness where fitness improved
+ *   velocity      <- w v + c1 r1 (pbest - x) + c2 r2 (gbest - x),  w = 0.5 + r0 / 2      (per particle AND dimension)
+ *   position      <- x + velocity
+ * evaluated in exactly that operation order with individually rounded operations (bit-exact against NumPy).
+ *   position, velocity, pbest_pos   device [B, P] (updated in place)
+ *   pbest_fit  device [B]; gbest_pos device [P]; gbest_fit device [1]  (updated in place)
+ *   fitness    device [B]: log-likelihood of `position` (from lsim_logl + the sampler's bound penalties)
+ *   rnd        device [3, B, P]: uniform [0,1) numbers r0, r1, r2 (the caller's generator, as the reference's PSO
+ *              draws them from NumPy's global generator)
+ * No allocation, no synchronisation; two launches on `stream`. */
+int lsim_pso_step(double* position, double* velocity, double* pbest_pos, double* pbest_fit, double* gbest_pos,
+                  double* gbest_fit, const double* fitness, const double* rnd, int64_t B, int32_t P, double c1,
+                  double c2, void* stream);
+
 /* introspection */
 int lsim_abi_version(void);
 const char* lsim_strerror(int code);

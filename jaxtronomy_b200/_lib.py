@@ -71,7 +71,7 @@ _lib = None
 SYMBOLS = [
     "lsim_plan_create", "lsim_plan_destroy", "lsim_ray_shoot", "lsim_surface_brightness", "lsim_workspace_bytes",
     "lsim_image", "lsim_resize_convolve", "lsim_logl", "lsim_abi_version", "lsim_strerror", "lsim_last_cuda_error", "lsim_launch_count",
-    "lsim_measure_fp64_peak", "lsim_timing_enable", "lsim_timing_read",
+    "lsim_measure_fp64_peak", "lsim_timing_enable", "lsim_timing_read", "lsim_pso_step",
 ]
 
 
@@ -109,6 +109,8 @@ def load():
     lib.lsim_launch_count.restype = i64
     lib.lsim_measure_fp64_peak.argtypes = [i64, C.POINTER(C.c_double), vp]
     lib.lsim_measure_fp64_peak.restype = i32
+    lib.lsim_pso_step.argtypes = [vp] * 8 + [i64, i32, C.c_double, C.c_double, vp]
+    lib.lsim_pso_step.restype = i32
     lib.lsim_timing_enable.argtypes = [i32]
     lib.lsim_timing_enable.restype = i32
     lib.lsim_timing_read.argtypes = [C.POINTER(C.c_double * 4), C.POINTER(C.c_int64 * 4)]
@@ -355,6 +357,21 @@ class Plan:
                                       model.data_ptr() if model is not None else None, ws.data_ptr(), ws.numel() * 8,
                                       self._stream()))
         return logl, amps, model
+
+
+def pso_step(position, velocity, pbest_pos, pbest_fit, gbest_pos, gbest_fit, fitness, rnd, c1=1.193, c2=1.193):
+    """In-place particle-swarm iteration on CUDA tensors (lsim_pso_step); rnd: [3, B, P] uniform numbers."""
+    torch = _torch()
+    B, P = position.shape
+    for t, shape in ((position, (B, P)), (velocity, (B, P)), (pbest_pos, (B, P)), (pbest_fit, (B,)), (gbest_pos, (P,)),
+                     (gbest_fit, (1,)), (fitness, (B,)), (rnd, (3, B, P))):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == shape):
+            raise LsimError("pso_step needs contiguous float64 CUDA tensors; got %s %s for expected shape %s"
+                            % (t.dtype, tuple(t.shape), shape))
+    ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    check(load().lsim_pso_step(ptr(position), ptr(velocity), ptr(pbest_pos), ptr(pbest_fit), ptr(gbest_pos),
+                               ptr(gbest_fit), ptr(fitness), ptr(rnd), B, P, float(c1), float(c2),
+                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
 
 def measure_fp64_peak(iters=200000):

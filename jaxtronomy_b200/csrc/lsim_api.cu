@@ -786,6 +786,23 @@ int lsim_timing_read(double ms[4], int64_t count[4]) {
   return LSIM_OK;
 }
 
+int lsim_pso_step(double* position, double* velocity, double* pbest_pos, double* pbest_fit, double* gbest_pos,
+                  double* gbest_fit, const double* fitness, const double* rnd, int64_t B, int32_t P, double c1,
+                  double c2, void* stream) {
+  if (B < 0 || P <= 0) return LSIM_E_INVALID;
+  if (B == 0) return LSIM_OK;
+  if (!position || !velocity || !pbest_pos || !pbest_fit || !gbest_pos || !gbest_fit || !fitness || !rnd)
+    return LSIM_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_pso_best<<<1, kPsoBlock, 0, st>>>(position, fitness, pbest_pos, pbest_fit, gbest_pos, gbest_fit, B, P);
+  int rc = after_launch("k_pso_best");
+  if (rc != LSIM_OK) return rc;
+  const int64_t n = B * P;
+  k_pso_move<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, st>>>(position, velocity, pbest_pos, gbest_pos, rnd,
+                                                                      n, P, c1, c2);
+  return after_launch("k_pso_move");
+}
+
 int lsim_measure_fp64_peak(int64_t iters, double* flops, void* stream) {
   if (!flops || iters <= 0) return LSIM_E_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -689,6 +689,83 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
   }
 }
 
+// ---- particle swarm: best-particle bookkeeping and move ------------------------------------------------------------
+// k_pso_best (one CTA): argmax of fitness (lowest index on ties), global best update, then personal bests.
+constexpr int kPsoBlock = 1024;
+__global__ void __launch_bounds__(kPsoBlock)
+k_pso_best(const double* __restrict__ position, const double* __restrict__ fitness, double* __restrict__ pbest_pos,
+           double* __restrict__ pbest_fit, double* __restrict__ gbest_pos, double* __restrict__ gbest_fit, int64_t B,
+           int P) {
+  __shared__ double s_val[kPsoBlock / 32];
+  __shared__ int64_t s_idx[kPsoBlock / 32];
+  __shared__ int64_t s_best;
+  double best = -HUGE_VAL;
+  int64_t arg = -1;  // -1: nothing beats -inf yet; nan never wins (comparisons are false), like the reference's `<`
+  for (int64_t b = threadIdx.x; b < B; b += kPsoBlock) {
+    const double f = fitness[b];
+    if (f > best) {
+      best = f;
+      arg = b;
+    }
+  }
+  auto better = [](double fa, int64_t ia, double fb, int64_t ib) {  // is (fb, ib) to be preferred over (fa, ia)?
+    if (ib < 0) return false;
+    if (ia < 0) return true;
+    return fb > fa || (fb == fa && ib < ia);
+  };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double of = __shfl_xor_sync(0xffffffffu, best, o);
+    const int64_t oi = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (better(best, arg, of, oi)) {
+      best = of;
+      arg = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_val[threadIdx.x >> 5] = best;
+    s_idx[threadIdx.x >> 5] = arg;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kPsoBlock / 32; ++w)
+      if (better(best, arg, s_val[w], s_idx[w])) {
+        best = s_val[w];
+        arg = s_idx[w];
+      }
+    s_best = (arg >= 0 && gbest_fit[0] < best) ? arg : -1;  // `if self.global_best.fitness < particle.fitness`
+    if (s_best >= 0) gbest_fit[0] = best;
+  }
+  __syncthreads();
+  const int64_t g = s_best;
+  if (g >= 0)
+    for (int k = threadIdx.x; k < P; k += kPsoBlock) gbest_pos[k] = position[g * P + k];
+  for (int64_t b = threadIdx.x; b < B; b += kPsoBlock) {
+    const double f = fitness[b];
+    if (f > pbest_fit[b]) {  // `if particle.fitness > particle.personal_best.fitness`
+      pbest_fit[b] = f;
+      for (int k = 0; k < P; ++k) pbest_pos[b * P + k] = position[b * P + k];
+    }
+  }
+}
+
+// k_pso_move: one thread per (particle, dimension); individually rounded operations in NumPy's order.
+__global__ void __launch_bounds__(kBlock)
+k_pso_move(double* __restrict__ position, double* __restrict__ velocity, const double* __restrict__ pbest_pos,
+           const double* __restrict__ gbest_pos, const double* __restrict__ rnd, int64_t n, int P, double c1,
+           double c2) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const double x = position[i];
+  const double w = __dadd_rn(0.5, __ddiv_rn(rnd[i], 2.0));
+  const double part = __dmul_rn(w, velocity[i]);
+  const double cog = __dmul_rn(__dmul_rn(c1, rnd[n + i]), __dadd_rn(pbest_pos[i], -x));
+  const double soc = __dmul_rn(__dmul_rn(c2, rnd[2 * n + i]), __dadd_rn(gbest_pos[i % P], -x));
+  const double v = __dadd_rn(__dadd_rn(part, cog), soc);
+  velocity[i] = v;
+  position[i] = __dadd_rn(x, v);
+}
+
 // ---- k_fp64_peak ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_fp64_peak(int64_t iters, double* sink) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

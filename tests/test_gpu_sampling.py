@@ -107,3 +107,45 @@ def test_multi_band_likelihood_is_the_sum_of_bands():
     x0 = param.kwargs2args(kl, ks, kll)
     got = like.logL_batch(np.stack([x0, x0]))
     assert abs(got[0] - want) <= 1e-10 * abs(want) and got[0] == got[1]
+
+
+def test_pso_step_is_bit_exact_against_the_oracle():
+    """lsim_pso_step vs oracle/pso.py on the same state and the same uniform numbers: array_equal, including ties
+    (first particle wins), a nan fitness (never wins) and particles that do not improve."""
+    import torch
+
+    from jaxtronomy_b200 import _lib
+    from oracle import pso as opso
+
+    rng = np.random.default_rng(11)
+    for B, P in ((1, 3), (37, 11), (5000, 17)):
+        st = dict(position=rng.normal(0, 1, (B, P)), velocity=rng.normal(0, 0.1, (B, P)),
+                  pbest_pos=rng.normal(0, 1, (B, P)), pbest_fit=rng.normal(-100, 10, B),
+                  gbest_pos=rng.normal(0, 1, P), gbest_fit=np.array([-95.0]))
+        fitness = rng.normal(-100, 10, B)
+        if B > 4:
+            fitness[3] = fitness[1] = fitness.max() + 1.0   # tie for the best: index 1 must win
+            fitness[2] = np.nan
+        rnd = rng.uniform(0, 1, (3, B, P))
+        dev = {k: torch.as_tensor(v.copy(), device="cuda") for k, v in st.items()}
+        for _ in range(2):  # two consecutive iterations on the evolving state
+            opso.pso_step(st["position"], st["velocity"], st["pbest_pos"], st["pbest_fit"], st["gbest_pos"],
+                          st["gbest_fit"], fitness, rnd)
+            _lib.pso_step(dev["position"], dev["velocity"], dev["pbest_pos"], dev["pbest_fit"], dev["gbest_pos"],
+                          dev["gbest_fit"], torch.as_tensor(fitness, device="cuda"), torch.as_tensor(rnd, device="cuda"))
+            for k in st:
+                np.testing.assert_array_equal(dev[k].cpu().numpy(), st[k], err_msg="%s B=%d" % (k, B))
+            fitness = fitness - 1.0  # second pass: nobody improves, only the move changes the state
+
+
+def test_device_pso_improves_the_fit_without_host_round_trips():
+    from jaxtronomy_b200.Sampling.sampler import DeviceParticleSwarmOptimizer
+
+    c, lin, param, like = _setup()
+    x0 = param.kwargs2args(c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"])
+    pso = DeviceParticleSwarmOptimizer(like, x0 - 0.05, x0 + 0.05, particle_count=64, seed=0)
+    best, hist = pso.optimize(max_iter=15)
+    assert best.shape == x0.shape
+    assert np.all(np.diff(hist) >= 0) and hist[-1] > hist[0]
+    assert hist[-1] >= like.logL(x0) - 50.0
+    assert abs(like.logL(best) - hist[-1]) <= 1e-9 * abs(hist[-1])

@@ -238,3 +238,22 @@ def test_pso_runs_on_a_toy_likelihood():
         prepare_logL_func("cpu", None)
     with pytest.raises(ValueError):
         prepare_logL_func("tpu", None)
+
+
+def test_oracle_pso_step_bookkeeping():
+    """oracle/pso.py: first-wins ties, nan never wins, non-improving particles keep their personal best."""
+    from oracle import pso as opso
+
+    B, P = 6, 2
+    pos = np.arange(B * P, dtype=float).reshape(B, P)
+    vel = np.zeros((B, P))
+    pb, pf = pos.copy() + 100, np.full(B, -10.0)
+    gb, gf = np.zeros(P), np.array([-5.0])
+    fit = np.array([-20.0, -1.0, np.nan, -1.0, -9.0, -30.0])
+    rnd = np.zeros((3, B, P))
+    before = pos.copy()
+    opso.pso_step(pos, vel, pb, pf, gb, gf, fit, rnd)
+    assert gf[0] == -1.0 and np.array_equal(gb, before[1])
+    assert np.array_equal(pf, [-10.0, -1.0, -10.0, -1.0, -9.0, -10.0])
+    assert np.array_equal(pb[1], before[1]) and np.array_equal(pb[0], before[0] + 100)
+    assert np.array_equal(vel, np.zeros((B, P))) and np.array_equal(pos, before)  # all draws 0: w v = 0, no pull
