@@ -1,4 +1,7 @@
 // lsim_api.cu -- C ABI (include/lsim.h) over the kernels in lsim_kernels.cuh.  Single translation unit.
+#include <cufft.h>  // types only: the library is dlopen()ed on first use, liblsim.so does not link it
+#include <dlfcn.h>
+
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -69,8 +72,56 @@ const int kLightParams[LSIM_LIGHT_TYPE_COUNT] = {5, 7, 4};
 
 }  // namespace
 
+// ---- FFT convolution for large PSF kernels (zero boundary): cuFFT D2Z / Z2D on zero-padded images -------------------
+struct CufftApi {
+  cufftResult (*PlanMany)(cufftHandle*, int, int*, int*, int, int, int*, int, int, cufftType, int) = nullptr;
+  cufftResult (*ExecD2Z)(cufftHandle, cufftDoubleReal*, cufftDoubleComplex*) = nullptr;
+  cufftResult (*ExecZ2D)(cufftHandle, cufftDoubleComplex*, cufftDoubleReal*) = nullptr;
+  cufftResult (*SetStream)(cufftHandle, cudaStream_t) = nullptr;
+  cufftResult (*Destroy)(cufftHandle) = nullptr;
+  bool ok = false;
+};
+
+static const CufftApi& cufft_api() {
+  static CufftApi api = [] {
+    CufftApi a;
+    void* h = nullptr;
+    for (const char* name : {"libcufft.so.11", "libcufft.so.12", "libcufft.so"}) {
+      h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) return a;
+    a.PlanMany = reinterpret_cast<decltype(a.PlanMany)>(dlsym(h, "cufftPlanMany"));
+    a.ExecD2Z = reinterpret_cast<decltype(a.ExecD2Z)>(dlsym(h, "cufftExecD2Z"));
+    a.ExecZ2D = reinterpret_cast<decltype(a.ExecZ2D)>(dlsym(h, "cufftExecZ2D"));
+    a.SetStream = reinterpret_cast<decltype(a.SetStream)>(dlsym(h, "cufftSetStream"));
+    a.Destroy = reinterpret_cast<decltype(a.Destroy)>(dlsym(h, "cufftDestroy"));
+    a.ok = a.PlanMany && a.ExecD2Z && a.ExecZ2D && a.SetStream && a.Destroy;
+    return a;
+  }();
+  return api;
+}
+
+struct FftConv {
+  int nx = 0, ny = 0, K = 0, PX = 0, PY = 0, nb = 0;
+  cufftHandle fwd = 0, inv = 0;
+  bool have_fwd = false, have_inv = false;
+  double* pad = nullptr;               // [nb][PY][PX]
+  cufftDoubleComplex* spec = nullptr;  // [nb][PY][PX/2+1]
+  cufftDoubleComplex* kspec = nullptr; // [PY][PX/2+1]
+  ~FftConv() {
+    if (have_fwd) cufft_api().Destroy(fwd);
+    if (have_inv) cufft_api().Destroy(inv);
+    cudaFree(pad);
+    cudaFree(spec);
+    cudaFree(kspec);
+  }
+};
+
 struct lsim_plan {
   PlanDev dev;
+  FftConv* fft_lo = nullptr;  // pixel-grid kernel, when it takes the FFT path
+  FftConv* fft_hi = nullptr;  // supersampled kernel, likewise
   std::vector<void*> owned;
   bool full = false;
   int n_series = 0;
@@ -82,6 +133,8 @@ struct lsim_plan {
 
   ~lsim_plan() {
     for (void* p : owned) cudaFree(p);
+    delete fft_lo;
+    delete fft_hi;
   }
   template <class T>
   int upload(const T* host, size_t n, const T** dev_out) {
@@ -117,6 +170,7 @@ int configure_kernels() {
 }
 
 int find_signature(const lsim_plan_desc* d);  // defined with the kernel-variant tables below
+int fft_conv_create(int nx, int ny, int K, const double* kernel, int mode, FftConv** out);  // defined with the convolutions
 
 double series_tol_default() {
   const char* s = getenv("LSIM_SERIES_TOL");
@@ -267,6 +321,10 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
         if (d->kernel_hi_separable) TRY(p->upload(d->kernel_hi_1d, (size_t)d->kernel_hi_size, &D.kernel_hi_1d));
       }
     }
+    if (D.K > 0 && !d->kernel_separable)
+      TRY(fft_conv_create(d->nx, d->ny, d->kernel_size, d->kernel, d->conv_mode, &p->fft_lo));
+    if (D.ss_conv && !d->kernel_hi_separable)
+      TRY(fft_conv_create(d->nx * d->ss, d->ny * d->ss, d->kernel_hi_size, d->kernel_hi, d->conv_mode, &p->fft_hi));
     p->image_smem = (size_t)d->n_lens * sizeof(LensC) + (size_t)d->n_light * sizeof(LightC) +
                     (size_t)n_series * kMaxSeries * sizeof(double);
     if (p->f32) p->image_smem += f32_extra_smem(d->n_lens, d->n_light, n_series);
@@ -529,7 +587,109 @@ struct ConvSpec {
   int mode;
   double scale;
   int accumulate;  // out += scale * conv(in) instead of out = ...
+  const FftConv* fft = nullptr;  // set: take the FFT path
 };
+
+// smallest m >= n of the form 2^a 3^b 5^c 7^d (cuFFT's fast sizes)
+int fft_fast_size(int n) {
+  for (int m = n;; ++m) {
+    int r = m;
+    for (int p : {2, 3, 5, 7})
+      while (r % p == 0) r /= p;
+    if (r == 1) return m;
+  }
+}
+
+// kernels larger than this side take the FFT path (zero boundary only; LSIM_FFT_MIN_K overrides, 0 disables)
+int fft_min_k() {
+  const char* s = getenv("LSIM_FFT_MIN_K");
+  return (s && *s) ? atoi(s) : 33;
+}
+
+// Build the FFT state for "same" convolution of nx x ny images with `kernel` [K,K] (host).  Returns LSIM_OK with
+// *out == nullptr when the FFT path does not apply (small kernel, cuFFT missing): the direct kernels are used.
+int fft_conv_create(int nx, int ny, int K, const double* kernel, int mode, FftConv** out) {
+  *out = nullptr;
+  const int mink = fft_min_k();
+  if (mode != LSIM_CONV_ZERO || mink <= 0 || K < mink || !cufft_api().ok) return LSIM_OK;
+  const CufftApi& api = cufft_api();
+  FftConv* f = new (std::nothrow) FftConv();
+  if (!f) return LSIM_E_INVALID;
+  f->nx = nx; f->ny = ny; f->K = K;
+  f->PX = fft_fast_size(nx + K - 1);
+  f->PY = fft_fast_size(ny + K - 1);
+  const size_t nreal = (size_t)f->PX * f->PY, nspec = (size_t)f->PY * (f->PX / 2 + 1);
+  int64_t nb = (int64_t)((64u << 20) / (nreal * 8 + nspec * 16));
+  f->nb = (int)(nb < 1 ? 1 : (nb > 256 ? 256 : nb));
+#define FFT_TRY(call)                         \
+  do {                                        \
+    if ((call) != cudaSuccess) {              \
+      int rc__ = cuda_fail(cudaGetLastError(), #call); \
+      delete f;                               \
+      return rc__;                            \
+    }                                         \
+  } while (0)
+  FFT_TRY(cudaMalloc(&f->pad, f->nb * nreal * sizeof(double)));
+  FFT_TRY(cudaMalloc(&f->spec, f->nb * nspec * sizeof(cufftDoubleComplex)));
+  FFT_TRY(cudaMalloc(&f->kspec, nspec * sizeof(cufftDoubleComplex)));
+  int dims[2] = {f->PY, f->PX};
+  if (api.PlanMany(&f->fwd, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, f->nb) != CUFFT_SUCCESS) {
+    delete f;
+    return LSIM_E_CUDA;
+  }
+  f->have_fwd = true;
+  if (api.PlanMany(&f->inv, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, f->nb) != CUFFT_SUCCESS) {
+    delete f;
+    return LSIM_E_CUDA;
+  }
+  f->have_inv = true;
+  // kernel spectrum: the kernel sits at the origin of the padded frame, the crop offset (K-1)/2 centres it
+  std::vector<double> kp(nreal, 0.0);
+  for (int i = 0; i < K; ++i)
+    for (int j = 0; j < K; ++j) kp[(size_t)i * f->PX + j] = kernel[(size_t)i * K + j];
+  FFT_TRY(cudaMemset(f->pad, 0, f->nb * nreal * sizeof(double)));
+  FFT_TRY(cudaMemcpy(f->pad, kp.data(), nreal * sizeof(double), cudaMemcpyHostToDevice));
+  api.SetStream(f->fwd, nullptr);
+  if (api.ExecD2Z(f->fwd, f->pad, f->spec) != CUFFT_SUCCESS) {
+    delete f;
+    return LSIM_E_CUDA;
+  }
+  FFT_TRY(cudaMemcpy(f->kspec, f->spec, nspec * sizeof(cufftDoubleComplex), cudaMemcpyDeviceToDevice));
+  FFT_TRY(cudaDeviceSynchronize());
+#undef FFT_TRY
+  *out = f;
+  return LSIM_OK;
+}
+
+// n_images "same" convolutions through the FFT state, nb images per transform batch.  The scratch belongs to the
+// plan: one call in flight per plan (documented in lsim.h).
+int launch_conv_fft(const FftConv& f, const double* in, double* out, int64_t n_images, double scale, int accumulate,
+                    cudaStream_t st) {
+  const CufftApi& api = cufft_api();
+  const size_t nreal = (size_t)f.PX * f.PY, nspec = (size_t)f.PY * (f.PX / 2 + 1), npix = (size_t)f.nx * f.ny;
+  api.SetStream(f.fwd, st);
+  api.SetStream(f.inv, st);
+  const unsigned gx = (unsigned)((nreal + kBlock - 1) / kBlock);
+  for (int64_t i0 = 0; i0 < n_images; i0 += f.nb) {
+    const int64_t n = n_images - i0 < f.nb ? n_images - i0 : f.nb;
+    Timed timed(kClsConv, st);
+    k_fft_pad<<<dim3(gx > 1024 ? 1024 : gx, (unsigned)n), kBlock, 0, st>>>(in + i0 * npix, f.pad, f.nx, f.ny, f.PX, f.PY);
+    int rc = after_launch("k_fft_pad");
+    if (rc != LSIM_OK) return rc;
+    if (api.ExecD2Z(f.fwd, f.pad, f.spec) != CUFFT_SUCCESS) return LSIM_E_CUDA;
+    k_fft_mul<<<dim3(gx > 1024 ? 1024 : gx, (unsigned)n), kBlock, 0, st>>>(
+        reinterpret_cast<double2*>(f.spec), reinterpret_cast<const double2*>(f.kspec), (int)nspec, 1.0 / (double)nreal);
+    rc = after_launch("k_fft_mul");
+    if (rc != LSIM_OK) return rc;
+    if (api.ExecZ2D(f.inv, f.spec, f.pad) != CUFFT_SUCCESS) return LSIM_E_CUDA;
+    k_fft_crop<<<dim3(gx > 1024 ? 1024 : gx, (unsigned)n), kBlock, 0, st>>>(f.pad, out + i0 * npix, f.nx, f.ny, f.PX, f.PY,
+                                                                         (f.K - 1) / 2, scale, accumulate);
+    rc = after_launch("k_fft_crop");
+    if (rc != LSIM_OK) return rc;
+    g_launches.fetch_add(2, std::memory_order_relaxed);  // the two cuFFT executions
+  }
+  return LSIM_OK;
+}
 
 template <int KT, int R, int NW>
 int launch_conv_tiled(const ConvSpec& c, const double* in, double* out, int64_t n_images, cudaStream_t st) {
@@ -562,6 +722,7 @@ int launch_conv_tiled_kt(const ConvSpec& c, const double* in, double* out, int64
 }
 
 int launch_conv_spec(const ConvSpec& c, const double* in, double* out, int64_t n_images, cudaStream_t st) {
+  if (c.fft) return launch_conv_fft(*c.fft, in, out, n_images, c.scale, c.accumulate, st);
   if (!c.kernel_1d && !getenv("LSIM_CONV_GENERIC")) {
     if (c.K <= 7) return launch_conv_tiled_kt<7>(c, in, out, n_images, st);
     if (c.K <= 11) return launch_conv_tiled_kt<11>(c, in, out, n_images, st);
@@ -611,7 +772,7 @@ int launch_rebin(const PlanDev& D, const double* sub, double* out, int64_t n_ima
 // pixel-grid convolution of the plan (regular path): out = image_scale * conv(in)
 int launch_conv(const lsim_plan* plan, const double* in, double* out, int64_t n_images, cudaStream_t st) {
   const PlanDev& D = plan->dev;
-  ConvSpec c{D.nx, D.ny, D.K, D.kernel, D.kernel_1d, D.conv_mode, D.image_scale, 0};
+  ConvSpec c{D.nx, D.ny, D.K, D.kernel, D.kernel_1d, D.conv_mode, D.image_scale, 0, plan->fft_lo};
   return launch_conv_spec(c, in, out, n_images, st);
 }
 
@@ -620,13 +781,13 @@ int launch_conv(const lsim_plan* plan, const double* in, double* out, int64_t n_
 int launch_conv_supersampled(const lsim_plan* plan, const double* sub, double* hsub, const double* low, double* out,
                              int64_t n_images, cudaStream_t st) {
   const PlanDev& D = plan->dev;
-  ConvSpec hi{D.nx * D.ss, D.ny * D.ss, D.K_hi, D.kernel_hi, D.kernel_hi_1d, D.conv_mode, 1.0, 0};
+  ConvSpec hi{D.nx * D.ss, D.ny * D.ss, D.K_hi, D.kernel_hi, D.kernel_hi_1d, D.conv_mode, 1.0, 0, plan->fft_hi};
   int rc = launch_conv_spec(hi, sub, hsub, n_images, st);
   if (rc != LSIM_OK) return rc;
   rc = launch_rebin(D, hsub, out, n_images, D.image_scale, st);
   if (rc != LSIM_OK) return rc;
   if (D.K > 0) {
-    ConvSpec lo{D.nx, D.ny, D.K, D.kernel, D.kernel_1d, D.conv_mode, D.image_scale, 1};
+    ConvSpec lo{D.nx, D.ny, D.K, D.kernel, D.kernel_1d, D.conv_mode, D.image_scale, 1, plan->fft_lo};
     rc = launch_conv_spec(lo, low, out, n_images, st);
   }
   return rc;

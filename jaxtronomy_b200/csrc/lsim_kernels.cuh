@@ -457,6 +457,41 @@ k_conv_separable(const double* __restrict__ in, double* __restrict__ out, int nx
   }
 }
 
+// ---- FFT convolution helpers (large kernels; the transforms themselves are cuFFT) ----------------------------------
+// zero-padded copy [n][ny][nx] -> [n][PY][PX]
+__global__ void __launch_bounds__(kBlock)
+k_fft_pad(const double* __restrict__ in, double* __restrict__ pad, int nx, int ny, int PX, int PY) {
+  const double* src = in + (int64_t)blockIdx.y * nx * ny;
+  double* dst = pad + (int64_t)blockIdx.y * PX * PY;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < PX * PY; i += gridDim.x * kBlock) {
+    const int y = i / PX, x = i - y * PX;
+    dst[i] = (x < nx && y < ny) ? src[(int64_t)y * nx + x] : 0.0;
+  }
+}
+
+// spectrum [n][PY][PXc] *= kernel spectrum [PY][PXc] * norm
+__global__ void __launch_bounds__(kBlock)
+k_fft_mul(double2* __restrict__ spec, const double2* __restrict__ kspec, int n_spec, double norm) {
+  double2* s = spec + (int64_t)blockIdx.y * n_spec;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n_spec; i += gridDim.x * kBlock) {
+    const double2 a = s[i], b = kspec[i];
+    s[i] = make_double2((a.x * b.x - a.y * b.y) * norm, (a.x * b.y + a.y * b.x) * norm);
+  }
+}
+
+// out[n][ny][nx] (+)= scale * full[n][y + r][x + r]   ("same" part of the full linear convolution)
+__global__ void __launch_bounds__(kBlock)
+k_fft_crop(const double* __restrict__ pad, double* __restrict__ out, int nx, int ny, int PX, int PY, int r,
+           double scale, int accumulate) {
+  const double* src = pad + (int64_t)blockIdx.y * PX * PY;
+  double* dst = out + (int64_t)blockIdx.y * nx * ny;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < nx * ny; i += gridDim.x * kBlock) {
+    const int y = i / nx, x = i - y * nx;
+    const double v = src[(int64_t)(y + r) * PX + (x + r)];
+    dst[i] = accumulate ? fma(v, scale, dst[i]) : v * scale;
+  }
+}
+
 // ---- reductions -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -438,3 +438,43 @@ def test_fp32_variant(headline):
     l64, l32, a64, a32 = l64.cpu().numpy(), l32.cpu().numpy(), a64.cpu().numpy(), a32.cpu().numpy()
     assert np.max(np.abs(l32 - l64) / np.abs(l64)) <= FP32_LOGL_RTOL
     assert np.max(np.abs(a32 - a64) / np.abs(a64)) <= FP32_LOGL_RTOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FFT path of the PSF convolution (kernel side >= 33, or forced with LSIM_FFT_MIN_K)
+# ---------------------------------------------------------------------------------------------------------------
+def _numerics_with_pixel_psf(nx, ny, kernel, ss=1, supersampling_convolution=False):
+    from jaxtronomy_b200.Data.pixel_grid import PixelGrid
+    from jaxtronomy_b200.Data.psf import PSF
+    from jaxtronomy_b200.ImSim.Numerics.numerics import Numerics
+
+    pg = PixelGrid(nx, ny, np.array([[0.05, 0.0], [0.0, 0.05]]), -1.0, -1.0)
+    psf = PSF(psf_type="PIXEL", kernel_point_source=kernel, point_source_supersampling_factor=1)
+    return Numerics(pg, psf, supersampling_factor=ss, supersampling_convolution=supersampling_convolution,
+                    convolution_kernel_size=kernel.shape[0])
+
+
+def test_fft_convolution_matches_direct_and_the_oracle(monkeypatch):
+    """A 45 x 45 asymmetric PSF on a non-square 70 x 52 frame takes the cuFFT path; the same kernel with the FFT path
+    disabled takes the direct kernels; both against the oracle's convolution (scipy), zero boundary."""
+    from oracle.imsim import PixelKernelConvolution
+
+    rng = np.random.default_rng(5)
+    nx, ny, K = 70, 52, 45
+    kernel = rng.uniform(0.0, 1.0, (K, K)) * np.exp(-((np.arange(K) - 20.0) ** 2)[:, None] / 60.0)
+    kernel /= kernel.sum()
+    flux = rng.uniform(0, 1, (5, ny * nx))  # 5 images: the transform batch is padded with idle slots
+    want = np.stack([PixelKernelConvolution(kernel).convolution2d(f.reshape(ny, nx)) for f in flux]) * 0.05**2
+    got_fft = _numerics_with_pixel_psf(nx, ny, kernel).re_size_convolve(flux)
+    monkeypatch.setenv("LSIM_FFT_MIN_K", "0")
+    got_direct = _numerics_with_pixel_psf(nx, ny, kernel).re_size_convolve(flux)
+    for got, what in ((got_fft, "fft"), (got_direct, "direct")):
+        assert got.shape == want.shape
+        assert_close(got, want, what=what, **BAR)
+    assert not np.array_equal(got_fft, got_direct)  # two different algorithms really ran
+    # forcing the FFT path on the headline-size kernel agrees with the tiled direct kernel
+    k21 = kernel[12:33, 12:33] / kernel[12:33, 12:33].sum()
+    direct21 = _numerics_with_pixel_psf(nx, ny, k21).re_size_convolve(flux)
+    monkeypatch.setenv("LSIM_FFT_MIN_K", "5")
+    fft21 = _numerics_with_pixel_psf(nx, ny, k21).re_size_convolve(flux)
+    assert_close(fft21, direct21, what="fft vs tiled", **BAR)
