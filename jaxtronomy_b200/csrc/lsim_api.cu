@@ -363,11 +363,25 @@ int lsim_ray_shoot(const lsim_plan* plan, const double* params, int64_t B, const
   if (what == 1 && plan->dev.ray.multi_plane) return LSIM_E_UNSUPPORTED;
   if (B > 65535) return LSIM_E_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid((unsigned)((N + kBlock * kRayItems - 1) / (kBlock * kRayItems)), (unsigned)B);
+  // rays per CTA: one batch for deflector lists that stream through shared memory in several chunks; otherwise enough
+  // that the per-CTA parameter preparation is amortised, while keeping >= 16 waves of CTAs in the grid
+  const int64_t batch = (int64_t)kBlock * kRayItems;
+  int64_t rpc = batch;
+  if (plan->dev.n_lens <= kLensChunk) {
+    const int64_t n_batches = (N + batch - 1) / batch;
+    const int64_t want_ctas = 16 * (int64_t)plan->n_sm * 4;           // per launch
+    int64_t per_set = (want_ctas + B - 1) / B;                        // CTAs per parameter set
+    if (per_set < 1) per_set = 1;
+    int64_t bpc = (n_batches + per_set - 1) / per_set;                // ray batches per CTA
+    if (bpc > 64) bpc = 64;
+    if (bpc < 1) bpc = 1;
+    rpc = bpc * batch;
+  }
+  dim3 grid((unsigned)((N + rpc - 1) / rpc), (unsigned)B);
   if (plan->full)
-    k_ray_shoot<true><<<grid, kBlock, kRaySmem, st>>>(plan->dev, params, x, y, N, coords_batched, out_x, out_y, what);
+    k_ray_shoot<true><<<grid, kBlock, kRaySmem, st>>>(plan->dev, params, x, y, N, coords_batched, out_x, out_y, what, rpc);
   else
-    k_ray_shoot<false><<<grid, kBlock, kRaySmem, st>>>(plan->dev, params, x, y, N, coords_batched, out_x, out_y, what);
+    k_ray_shoot<false><<<grid, kBlock, kRaySmem, st>>>(plan->dev, params, x, y, N, coords_batched, out_x, out_y, what, rpc);
   return after_launch("k_ray_shoot");
 }
 
@@ -391,6 +405,11 @@ namespace {
 
 // Scratch doubles per parameter set.  Regular path: U (unconvolved pixels) [+ C (convolved pixels)].
 // Supersampled convolution: Usub + Hsub (sub-pixel flux and its convolution) + U + C.
+// bytes of the per-set prepared constants block (k_prepare -> k_image), a multiple of 8
+size_t prep_bytes(const lsim_plan* plan) {
+  return prepared_bytes(plan->dev.n_lens, plan->dev.n_light, plan->n_series);
+}
+
 size_t per_set_bytes(const lsim_plan* plan, bool need_conv_out) {
   const PlanDev& D = plan->dev;
   const size_t npix = (size_t)D.nx * D.ny, nsub = npix * D.ss * D.ss;
@@ -398,18 +417,18 @@ size_t per_set_bytes(const lsim_plan* plan, bool need_conv_out) {
   size_t n = npix * D.n_slots;
   if (conv && need_conv_out) n += npix * D.n_slots;
   if (conv && D.ss_conv) n += 2 * nsub * D.n_slots + (need_conv_out ? 0 : npix * D.n_slots);
-  return n * sizeof(double);
+  return n * sizeof(double) + prep_bytes(plan);
 }
 
 int64_t chunk_sets(const lsim_plan* plan) { return (int64_t)plan->n_sm * 8; }
 
 template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = RuntimeTypes>
 int launch_image_k(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
-                   double scale, double* out, double* sub_out, cudaStream_t st) {
+                   double scale, double* out, double* sub_out, cudaStream_t st, const unsigned char* prep) {
   dim3 grid((unsigned)tiles, (unsigned)n);
   Timed timed(kClsImage, st);
   k_image<NSLOT, FULL, SS, LT, GT><<<grid, kImageBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale,
-                                                                                out, sub_out);
+                                                                                out, sub_out, prep, plan->n_series);
   return after_launch("k_image");
 }
 
@@ -455,10 +474,10 @@ int find_signature(const lsim_plan_desc* d) {
 // returns LSIM_E_UNSUPPORTED when (NSLOT, ss) has no specialised instantiation -> caller falls back
 template <bool FULL, class LT, class GT>
 int launch_image_sig(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
-                     double scale, double* out, double* sub_out, cudaStream_t st) {
+                     double scale, double* out, double* sub_out, cudaStream_t st, const unsigned char* prep) {
   const int ns = plan->dev.n_slots, ss = plan->dev.ss;
 #define LSIM_SIG_CASE(NS, SSV) \
-  if (ns == NS && ss == SSV) return launch_image_k<NS, FULL, SSV, LT, GT>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
+  if (ns == NS && ss == SSV) return launch_image_k<NS, FULL, SSV, LT, GT>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep);
   LSIM_SIG_CASE(1, 3)
   LSIM_SIG_CASE(2, 3)
   if (!FULL) {
@@ -476,14 +495,14 @@ int launch_image_sig(const lsim_plan* plan, const double* params, int64_t set0, 
 // variant (runtime supersampling factor, one sub-pixel at a time).
 template <int NSLOT>
 int launch_image_ns(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
-                    double scale, double* out, double* sub_out, cudaStream_t st) {
+                    double scale, double* out, double* sub_out, cudaStream_t st, const unsigned char* prep) {
   if (sub_out) {  // supersampled convolution: the SUB instantiations (runtime supersampling factor)
     dim3 grid((unsigned)tiles, (unsigned)n);
     Timed timed(kClsImage, st);
     const bool masked = plan->dev.eval_list != nullptr;
 #define LSIM_SUB_LAUNCH(FULLV, MASKV)                                                                          \
   k_image<NSLOT, FULLV, 0, RuntimeTypes, RuntimeTypes, true, MASKV><<<grid, kImageBlock, plan->image_smem, st>>>( \
-      plan->dev, params, set0, ppt, scale, out, sub_out)
+      plan->dev, params, set0, ppt, scale, out, sub_out, prep, plan->n_series)
     if (plan->full && masked) LSIM_SUB_LAUNCH(true, true);
     else if (plan->full) LSIM_SUB_LAUNCH(true, false);
     else if (masked) LSIM_SUB_LAUNCH(false, true);
@@ -496,30 +515,30 @@ int launch_image_ns(const lsim_plan* plan, const double* params, int64_t set0, i
     Timed timed(kClsImage, st);
     if (plan->full)
       k_image<NSLOT, true, 0, RuntimeTypes, RuntimeTypes, false, true><<<grid, kImageBlock, plan->image_smem, st>>>(
-          plan->dev, params, set0, ppt, scale, out, sub_out);
+          plan->dev, params, set0, ppt, scale, out, sub_out, prep, plan->n_series);
     else
       k_image<NSLOT, false, 0, RuntimeTypes, RuntimeTypes, false, true><<<grid, kImageBlock, plan->image_smem, st>>>(
-          plan->dev, params, set0, ppt, scale, out, sub_out);
+          plan->dev, params, set0, ppt, scale, out, sub_out, prep, plan->n_series);
     return after_launch("k_image");
   }
-  if (plan->full) return launch_image_k<NSLOT, true, 0>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
+  if (plan->full) return launch_image_k<NSLOT, true, 0>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep);
   switch (plan->dev.ss) {
-    case 1: return launch_image_k<NSLOT, false, 1>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
-    case 2: return launch_image_k<NSLOT, false, 2>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
-    case 3: return launch_image_k<NSLOT, false, 3>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
-    default: return launch_image_k<NSLOT, false, 0>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
+    case 1: return launch_image_k<NSLOT, false, 1>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep);
+    case 2: return launch_image_k<NSLOT, false, 2>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep);
+    case 3: return launch_image_k<NSLOT, false, 3>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep);
+    default: return launch_image_k<NSLOT, false, 0>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep);
   }
 }
 
 // LSIM_PRECISION_F32: the single-precision image kernel (interpreted profile lists, lock-step rows for ss <= 3)
 template <int NSLOT>
 int launch_image_f32_ns(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
-                        double scale, double* out, cudaStream_t st) {
+                        double scale, double* out, cudaStream_t st, const unsigned char* prep) {
   dim3 grid((unsigned)tiles, (unsigned)n);
   Timed timed(kClsImage, st);
 #define LSIM_F32_LAUNCH(SSV)                                                                                   \
   k_image_f32<NSLOT, SSV><<<grid, kImageBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, \
-                                                                        plan->n_series, out)
+                                                                        plan->n_series, out, prep)
   switch (plan->dev.ss) {
     case 1: LSIM_F32_LAUNCH(1); break;
     case 2: LSIM_F32_LAUNCH(2); break;
@@ -531,17 +550,17 @@ int launch_image_f32_ns(const lsim_plan* plan, const double* params, int64_t set
 }
 
 int launch_image_f32(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
-                     double scale, double* out, cudaStream_t st) {
+                     double scale, double* out, cudaStream_t st, const unsigned char* prep) {
   const int ns = plan->dev.n_slots;
-  if (ns <= 1) return launch_image_f32_ns<1>(plan, params, set0, n, ppt, tiles, scale, out, st);
-  if (ns <= 2) return launch_image_f32_ns<2>(plan, params, set0, n, ppt, tiles, scale, out, st);
-  if (ns <= 4) return launch_image_f32_ns<4>(plan, params, set0, n, ppt, tiles, scale, out, st);
-  return launch_image_f32_ns<8>(plan, params, set0, n, ppt, tiles, scale, out, st);
+  if (ns <= 1) return launch_image_f32_ns<1>(plan, params, set0, n, ppt, tiles, scale, out, st, prep);
+  if (ns <= 2) return launch_image_f32_ns<2>(plan, params, set0, n, ppt, tiles, scale, out, st, prep);
+  if (ns <= 4) return launch_image_f32_ns<4>(plan, params, set0, n, ppt, tiles, scale, out, st, prep);
+  return launch_image_f32_ns<8>(plan, params, set0, n, ppt, tiles, scale, out, st, prep);
 }
 
 // ray-shoot + light + re-bin for sets [set0, set0+n) -> out[n][n_slots][npix]
 int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, double scale, double* out,
-                 double* sub_out, cudaStream_t st) {
+                 double* sub_out, cudaStream_t st, const unsigned char* prep) {
   const int npix_all = plan->dev.nx * plan->dev.ny;
   const int npix = plan->dev.n_eval;  // evaluated pixels
   if (npix < npix_all) {              // masked pixels keep zero flux
@@ -552,31 +571,46 @@ int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int6
   }
   // CTAs per set: all CTAs of a launch cost the same, so a grid of w.x "waves" of resident CTAs runs like
   // ceil(w.x) waves (1184 sets x 1 CTA on 148 SMs x 3 resident = 2.67 waves took the time of 3).  Ask for >= 16
-  // waves: the partial last wave then costs at most ~3 %, and the per-CTA parameter preparation stays amortised
-  // over thousands of pixels.
+  // waves (32 by default, LSIM_IMAGE_WAVES): the partial last wave then costs ~1 %; the per-set constants come
+  // from k_prepare, so small CTAs cost nothing extra.
   const int64_t resident = (int64_t)plan->n_sm * LSIM_IMAGE_MIN_BLOCKS;
-  int64_t want = (16 * resident + n - 1) / n;
+  static const int64_t waves = [] {
+    const char* e = getenv("LSIM_IMAGE_WAVES");
+    const int64_t v = (e && *e) ? atoll(e) : 32;
+    return v < 1 ? (int64_t)1 : v;
+  }();
+  int64_t want = (waves * resident + n - 1) / n;
   int max_tiles = (npix + kImageBlock - 1) / kImageBlock;
   int tiles = (int)(want < 1 ? 1 : (want > max_tiles ? max_tiles : want));
   int ppt = (npix + tiles - 1) / tiles;
   ppt = ((ppt + kImageBlock - 1) / kImageBlock) * kImageBlock;
   tiles = (npix + ppt - 1) / ppt;
   const int ns = plan->dev.n_slots;
-  if (plan->f32) return launch_image_f32(plan, params, set0, n, ppt, tiles, scale, out, st);
+  if (prep) {  // per-set constants once per set, not once per CTA
+    const int64_t items = n * (plan->dev.n_lens + plan->dev.n_light);
+    if (items > 0) {
+      Timed timed(kClsOther, st);
+      k_prepare<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(plan->dev, params, set0, n, plan->n_series,
+                                                               const_cast<unsigned char*>(prep));
+      int rcp = after_launch("k_prepare");
+      if (rcp != LSIM_OK) return rcp;
+    }
+  }
+  if (plan->f32) return launch_image_f32(plan, params, set0, n, ppt, tiles, scale, out, st, prep);
   int rc = LSIM_E_UNSUPPORTED;
   switch ((sub_out || plan->dev.eval_list) ? kSigNone : plan->sig) {
-    case kSigEplShear_S: rc = launch_image_sig<false, LT_EplShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
-    case kSigEplShear_SS: rc = launch_image_sig<false, LT_EplShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
-    case kSigNieShear_S: rc = launch_image_sig<false, LT_NieShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
-    case kSigNieShear_SS: rc = launch_image_sig<false, LT_NieShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
-    case kSigEplmShear_SS: rc = launch_image_sig<true, LT_EplmShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st); break;
+    case kSigEplShear_S: rc = launch_image_sig<false, LT_EplShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep); break;
+    case kSigEplShear_SS: rc = launch_image_sig<false, LT_EplShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep); break;
+    case kSigNieShear_S: rc = launch_image_sig<false, LT_NieShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep); break;
+    case kSigNieShear_SS: rc = launch_image_sig<false, LT_NieShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep); break;
+    case kSigEplmShear_SS: rc = launch_image_sig<true, LT_EplmShear, GT_SS>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep); break;
     default: break;
   }
   if (rc != LSIM_E_UNSUPPORTED) return rc;
-  if (ns <= 1) return launch_image_ns<1>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
-  if (ns <= 2) return launch_image_ns<2>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
-  if (ns <= 4) return launch_image_ns<4>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
-  return launch_image_ns<8>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st);
+  if (ns <= 1) return launch_image_ns<1>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep);
+  if (ns <= 2) return launch_image_ns<2>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep);
+  if (ns <= 4) return launch_image_ns<4>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep);
+  return launch_image_ns<8>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep);
 }
 
 // One "same" convolution pass: n_images images of nx x ny with a K x K kernel (or its 1-d factor).
@@ -800,16 +834,19 @@ int run_chunk(const lsim_plan* plan, const double* params, int64_t s0, int64_t n
               double* dst, cudaStream_t st) {
   const PlanDev& D = plan->dev;
   const size_t npix = (size_t)D.nx * D.ny, nsub = npix * D.ss * D.ss, ns = (size_t)D.n_slots;
-  if (D.conv_mode == LSIM_CONV_NONE) return launch_image(plan, params, s0, n, D.image_scale, dst, nullptr, st);
+  // the scratch starts with the prepared-constants blocks of the chunk (none when the caller gave no scratch)
+  const unsigned char* prep = reinterpret_cast<const unsigned char*>(ws);
+  if (ws) ws += (size_t)chunk * prep_bytes(plan) / sizeof(double);
+  if (D.conv_mode == LSIM_CONV_NONE) return launch_image(plan, params, s0, n, D.image_scale, dst, nullptr, st, prep);
   double* U = ws;  // [chunk][ns][npix]
   if (!D.ss_conv) {
-    int rc = launch_image(plan, params, s0, n, 1.0, U, nullptr, st);
+    int rc = launch_image(plan, params, s0, n, 1.0, U, nullptr, st, prep);
     if (rc != LSIM_OK) return rc;
     return launch_conv(plan, U, dst, n * D.n_slots, st);
   }
   double* Usub = ws + (size_t)chunk * ns * npix;
   double* Hsub = Usub + (size_t)chunk * ns * nsub;
-  int rc = launch_image(plan, params, s0, n, 1.0, U, Usub, st);
+  int rc = launch_image(plan, params, s0, n, 1.0, U, Usub, st, prep);
   if (rc != LSIM_OK) return rc;
   return launch_conv_supersampled(plan, Usub, Hsub, U, dst, n * D.n_slots, st);
 }
@@ -855,6 +892,13 @@ int lsim_image(const lsim_plan* plan, const double* params, int64_t B, double* i
     chunk = (int64_t)(workspace_bytes / per_set_bytes(plan, false));
     if (!workspace || chunk < 1) return LSIM_E_WORKSPACE;
     if (chunk > chunk_sets(plan)) chunk = chunk_sets(plan);
+  } else if (workspace && prep_bytes(plan) > 0) {
+    // no PSF: the images go straight to the caller's buffer; scratch (optional) only holds the prepared constants
+    const int64_t fit = (int64_t)(workspace_bytes / prep_bytes(plan));
+    if (fit < 1) workspace = nullptr;
+    else if (fit < chunk) chunk = fit;
+  } else {
+    workspace = nullptr;
   }
   for (int64_t s0 = 0; s0 < B; s0 += chunk) {
     const int64_t n = B - s0 < chunk ? B - s0 : chunk;
@@ -911,7 +955,8 @@ int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear
   const size_t img = (size_t)D.nx * D.ny * D.n_slots, sub = img * D.ss * D.ss;
   // layout: [U | Usub, Hsub (supersampled conv only) | C]; without a PSF the images land in U directly
   double* ws = static_cast<double*>(workspace);
-  double* C = conv ? ws + (size_t)chunk * img + (D.ss_conv ? 2 * (size_t)chunk * sub : 0) : ws;
+  double* main_ws = ws + (size_t)chunk * prep_bytes(plan) / sizeof(double);  // run_chunk skips the same prefix
+  double* C = conv ? main_ws + (size_t)chunk * img + (D.ss_conv ? 2 * (size_t)chunk * sub : 0) : main_ws;
   for (int64_t s0 = 0; s0 < B; s0 += chunk) {
     const int64_t n = B - s0 < chunk ? B - s0 : chunk;
     int rc = run_chunk(plan, params, s0, n, chunk, ws, C, st);

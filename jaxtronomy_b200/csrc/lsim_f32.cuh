@@ -187,7 +187,7 @@ inline size_t f32_extra_smem(int n_lens, int n_light, int n_series) {
 template <int NSLOT, int SS>
 __global__ void __launch_bounds__(kImageBlock, 4)
 k_image_f32(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, double out_scale, int n_series,
-            double* __restrict__ out) {
+            double* __restrict__ out, const unsigned char* __restrict__ prepared) {
   constexpr int J = SS > 0 ? SS : 1;
   extern __shared__ double smem[];
   LensC* L = reinterpret_cast<LensC*>(smem);
@@ -198,8 +198,7 @@ k_image_f32(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt,
   float* poolf = reinterpret_cast<float*>(Gf + P.n_light);
   const int64_t bl = blockIdx.y;
   const double* row = params + (set0 + bl) * P.n_param_cols;
-  stage_lens(P, row, 0, P.n_lens, L, pool);
-  stage_light(P, row, G);
+  load_or_stage(P, row, prepared, bl, n_series, L, G, pool);
   __syncthreads();
   for (int i = threadIdx.x; i < P.n_lens; i += kImageBlock) {
     Lf[i].type = L[i].type;

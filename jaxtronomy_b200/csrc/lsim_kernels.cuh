@@ -75,13 +75,79 @@ __device__ __forceinline__ void stage_light(const PlanDev& P, const double* row,
   for (int i = threadIdx.x; i < P.n_light; i += blockDim.x) light_prepare(P.light[i], row, G[i]);
 }
 
+// ---- k_prepare: per-set constants computed ONCE per parameter set into global memory --------------------------------
+// Block of one set = the shared-memory image k_image works from: [LensC x n_lens][LightC x n_light][coefficient pool].
+// One thread per (set, profile).  The image kernel's CTAs (several per set) then fetch the block with a coalesced
+// copy instead of each recomputing trig, series coefficients and normalisations behind a barrier.
+__host__ __device__ inline size_t prepared_bytes(int n_lens, int n_light, int n_series) {
+  return (size_t)n_lens * sizeof(LensC) + (size_t)n_light * sizeof(LightC) +
+         (size_t)n_series * kMaxSeries * sizeof(double);
+}
+
+__global__ void __launch_bounds__(128)
+k_prepare(PlanDev P, const double* __restrict__ params, int64_t set0, int64_t n_sets, int n_series,
+          unsigned char* __restrict__ prepared) {
+  const int n_items = P.n_lens + P.n_light;
+  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (t >= n_sets * n_items) return;
+  const int64_t bl = t / n_items;
+  const int i = (int)(t - bl * n_items);
+  const double* row = params + (set0 + bl) * P.n_param_cols;
+  unsigned char* base = prepared + bl * prepared_bytes(P.n_lens, P.n_light, n_series);
+  LensC* L = reinterpret_cast<LensC*>(base);
+  LightC* G = reinterpret_cast<LightC*>(L + P.n_lens);
+  double* pool = reinterpret_cast<double*>(G + P.n_light);
+  if (i < P.n_lens) {
+    const lsim_lens_desc& d = P.lens[i];
+    int off = 0;
+    if (lens_type_has_series(d))
+      for (int j = 0; j < i; ++j) off += lens_type_has_series(P.lens[j]) ? 1 : 0;
+    LensC tmp;
+    tmp.coef_off = off * kMaxSeries;
+    lens_prepare(d, row, tmp, pool + off * kMaxSeries, P.series_tol);
+    L[i] = tmp;
+  } else {
+    LightC tmp;
+    light_prepare(P.light[i - P.n_lens], row, tmp);
+    G[i - P.n_lens] = tmp;
+  }
+}
+
+// shared-memory image of one set: copy of the prepared block (if given) or computed in place
+__device__ __forceinline__ void load_or_stage(const PlanDev& P, const double* row, const unsigned char* prepared,
+                                              int64_t bl, int n_series, LensC* L, LightC* G, double* pool) {
+  if (prepared) {
+    const size_t nb = prepared_bytes(P.n_lens, P.n_light, n_series);
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(prepared + bl * nb);
+    uint64_t* dst = reinterpret_cast<uint64_t*>(L);
+    const int head = (int)(((size_t)P.n_lens * sizeof(LensC) + (size_t)P.n_light * sizeof(LightC)) / 8);
+    for (int i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
+    // coefficient pools: only the first 32 entries of every profile unless a longer series is in use
+    for (int s = 0; s < n_series; ++s) {
+      int need = 0;
+      for (int l = 0; l < P.n_lens; ++l) {
+        const LensC* Lg = reinterpret_cast<const LensC*>(src) + l;
+        if (Lg->coef_off == s * kMaxSeries && Lg->n_coef > need) need = Lg->n_coef;
+      }
+      for (int i = threadIdx.x; i < need; i += blockDim.x) pool[s * kMaxSeries + i] = reinterpret_cast<const double*>(src)[head + s * kMaxSeries + i];
+    }
+  } else {
+    stage_lens(P, row, 0, P.n_lens, L, pool);
+    stage_light(P, row, G);
+  }
+}
+
 // ---- k_ray_shoot ---------------------------------------------------------------------------------------------
 constexpr int kRayItems = 2;
 
+// rpc: rays per CTA (a multiple of kBlock * kRayItems).  A model whose deflector list fits one shared-memory chunk
+// is staged ONCE per CTA and the CTA then walks its rays, so the per-set preparation (trig, series coefficients) is
+// amortised over thousands of rays; longer lists (LensModelBulk, 1000 halos) stream chunk by chunk past one ray batch
+// that stays in registers (the host passes rpc = kBlock * kRayItems for those).
 template <bool FULL>
 __global__ void __launch_bounds__(kBlock)
 k_ray_shoot(PlanDev P, const double* __restrict__ params, const double* __restrict__ x, const double* __restrict__ y,
-            int64_t N, int coords_batched, double* __restrict__ ox, double* __restrict__ oy, int what) {
+            int64_t N, int coords_batched, double* __restrict__ ox, double* __restrict__ oy, int what, int64_t rpc) {
   extern __shared__ double smem[];
   LensC* L = reinterpret_cast<LensC*>(smem);
   double* pool = reinterpret_cast<double*>(L + kLensChunk);
@@ -89,36 +155,44 @@ k_ray_shoot(PlanDev P, const double* __restrict__ params, const double* __restri
   const double* row = params + b * P.n_param_cols;
   const double* xb = coords_batched ? x + b * N : x;
   const double* yb = coords_batched ? y + b * N : y;
+  const bool one_chunk = P.n_lens <= kLensChunk;
 
-  stage_math_tables();  // made visible by the __syncthreads() of the first chunk
-  Rays<kRayItems> r;
-  int64_t idx[kRayItems];
+  stage_math_tables();
+  if (one_chunk) stage_lens(P, row, 0, P.n_lens, L, pool);
+  __syncthreads();
+  const int64_t r_end = min(N, ((int64_t)blockIdx.x + 1) * rpc);
+  for (int64_t r0 = (int64_t)blockIdx.x * rpc; r0 < r_end; r0 += kBlock * kRayItems) {
+    Rays<kRayItems> r;
+    int64_t idx[kRayItems];
 #pragma unroll
-  for (int k = 0; k < kRayItems; ++k) {
-    idx[k] = (int64_t)blockIdx.x * (kBlock * kRayItems) + k * kBlock + threadIdx.x;
-    const double x0 = idx[k] < N ? xb[idx[k]] : 0.0;
-    const double y0 = idx[k] < N ? yb[idx[k]] : 0.0;
-    ray_init(P.ray, k, x0, y0, r);
-  }
-  for (int c0 = 0; c0 < P.n_lens; c0 += kLensChunk) {
-    int n_c = min(kLensChunk, P.n_lens - c0);
-    __syncthreads();
-    stage_lens(P, row, c0, n_c, L, pool);
-    __syncthreads();
-    ray_apply<FULL, kRayItems>(P.ray, L, pool, n_c, r);
-  }
-#pragma unroll
-  for (int k = 0; k < kRayItems; ++k) {
-    if (idx[k] < N) {
-      double bx, by;
-      if (what == 1 && !P.ray.multi_plane) {
-        bx = r.ax[k] * P.ray.alpha_scaling;
-        by = r.ay[k] * P.ray.alpha_scaling;
-      } else {
-        ray_finish(P.ray, r, k, bx, by);
+    for (int k = 0; k < kRayItems; ++k) {
+      idx[k] = r0 + k * kBlock + threadIdx.x;
+      const double x0 = idx[k] < N ? xb[idx[k]] : 0.0;
+      const double y0 = idx[k] < N ? yb[idx[k]] : 0.0;
+      ray_init(P.ray, k, x0, y0, r);
+    }
+    for (int c0 = 0; c0 < P.n_lens; c0 += kLensChunk) {
+      const int n_c = min(kLensChunk, P.n_lens - c0);
+      if (!one_chunk) {
+        __syncthreads();
+        stage_lens(P, row, c0, n_c, L, pool);
+        __syncthreads();
       }
-      ox[b * N + idx[k]] = bx;
-      oy[b * N + idx[k]] = by;
+      ray_apply<FULL, kRayItems>(P.ray, L, pool, n_c, r);
+    }
+#pragma unroll
+    for (int k = 0; k < kRayItems; ++k) {
+      if (idx[k] < N) {
+        double bx, by;
+        if (what == 1 && !P.ray.multi_plane) {
+          bx = r.ax[k] * P.ray.alpha_scaling;
+          by = r.ay[k] * P.ray.alpha_scaling;
+        } else {
+          ray_finish(P.ray, r, k, bx, by);
+        }
+        ox[b * N + idx[k]] = bx;
+        oy[b * N + idx[k]] = by;
+      }
     }
   }
 }
@@ -179,7 +253,7 @@ template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = Runt
           bool MASKED = false>
 __global__ void __launch_bounds__(kImageBlock, LSIM_IMAGE_MIN_BLOCKS)
 k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, double out_scale,
-        double* __restrict__ out, double* __restrict__ sub_out) {
+        double* __restrict__ out, double* __restrict__ sub_out, const unsigned char* __restrict__ prepared, int n_series) {
   constexpr int J = SS > 0 ? SS : 1;
   extern __shared__ double smem[];
   LensC* L = reinterpret_cast<LensC*>(smem);
@@ -188,8 +262,7 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
   const int64_t bl = blockIdx.y;
   const double* row = params + (set0 + bl) * P.n_param_cols;
   stage_math_tables();
-  stage_lens(P, row, 0, P.n_lens, L, pool);
-  stage_light(P, row, G);
+  load_or_stage(P, row, prepared, bl, n_series, L, G, pool);
   __syncthreads();
 
   const int npix = P.nx * P.ny;
