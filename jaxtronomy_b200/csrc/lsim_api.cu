@@ -749,8 +749,11 @@ int launch_conv_tiled(const ConvSpec& c, const double* in, double* out, int64_t 
 
 template <int KT>
 int launch_conv_tiled_kt(const ConvSpec& c, const double* in, double* out, int64_t n_images, cudaStream_t st) {
-  // pick the tile height (64 = 8 warps x 8 rows, or 60 = 6 warps x 10 rows) that wastes fewer rows
+  // pick the tile height (64 = 8 warps x 8 rows, or 60 rows) that wastes fewer rows
   const int w64 = ((c.ny + 63) / 64) * 64, w60 = ((c.ny + 59) / 60) * 60;
+  // 60-row tiles: 4 warps x 15 rows measured 3 % faster than 6 x 10 for K <= 21 (more register reuse per loaded
+  // column); the larger kernels keep 10 rows per warp to stay inside the register budget
+  if (w60 < w64 && KT <= 21) return launch_conv_tiled<KT, 15, 4>(c, in, out, n_images, st);
   if (w60 < w64) return launch_conv_tiled<KT, 10, 6>(c, in, out, n_images, st);
   return launch_conv_tiled<KT, 8, 8>(c, in, out, n_images, st);
 }

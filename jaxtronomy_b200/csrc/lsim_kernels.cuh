@@ -256,11 +256,11 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
         double* __restrict__ out, double* __restrict__ sub_out, const unsigned char* __restrict__ prepared, int n_series) {
   constexpr int J = SS > 0 ? SS : 1;
   extern __shared__ double smem[];
+  const int64_t bl = blockIdx.y;
+  const double* row = params + (set0 + bl) * P.n_param_cols;
   LensC* L = reinterpret_cast<LensC*>(smem);
   LightC* G = reinterpret_cast<LightC*>(L + P.n_lens);
   double* pool = reinterpret_cast<double*>(G + P.n_light);
-  const int64_t bl = blockIdx.y;
-  const double* row = params + (set0 + bl) * P.n_param_cols;
   stage_math_tables();
   load_or_stage(P, row, prepared, bl, n_series, L, G, pool);
   __syncthreads();
@@ -437,7 +437,9 @@ k_conv_direct(const double* __restrict__ in, double* __restrict__ out, int nx, i
 // thread pulls its R + KT - 1 input values of that column into registers once and reuses each of them for up
 // to KT of the R x KT FMAs; the KT weights of the column are warp-uniform shared-memory broadcasts.  Shared
 // memory traffic per FMA drops from 2 loads (k_conv_direct) to (R + 2 KT - 1) / (R KT) ~ 0.24 (R = 10, KT = 21),
-// which moves the kernel from shared-memory-bandwidth-bound to fp64-pipe-bound.
+// which moves the kernel from shared-memory-bandwidth-bound to fp64-pipe-bound.  The weight is the operand the DFMAs
+// of a row share (register reuse cache): a DFMA with three fresh register operands issues every 3 cycles instead of
+// 2 on B200 (profiles/r1_dfma_operand_probe.md).
 template <int KT, int R, int NW>
 __global__ void __launch_bounds__(NW * 32, 2)
 k_conv_tiled(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
