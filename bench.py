@@ -321,9 +321,9 @@ def run_gpu(args):
         roof = {"bound": "fp64", "kernel": "k_image (fused ray-shoot + light + re-bin)", "achieved": achieved,
                 "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
                 # dram__bytes_read.sum + dram__bytes_write.sum of one k_image launch of 1184 sets, from the ncu
-                # --set full capture profiles/image_r1e_ncu_summary.txt (7.2 MB + 266.9 MB: the re-binned images,
-                # 1184 x 259 KB = 306.9 MB algorithmic)
-                "traffic": 274.1e6 * sets_per_launch / 1184.0,
+                # --set full capture profiles/image_r1h_ncu_summary.txt (5.7 MB + 255.7 MB: the re-binned images,
+                # 1184 x 259 KB = 306.9 MB algorithmic; the tail of the writes is still in L2 when the kernel ends)
+                "traffic": 261.4e6 * sets_per_launch / 1184.0,
                 "peak_source": "measured DFMA-chain microbenchmark (lsim_measure_fp64_peak); MEASURED_PEAKS.json has "
                                "no fp64 entry; nominal 37.2 TFLOP/s",
                 "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_ms,
