@@ -160,16 +160,40 @@ def cpu_images_per_s(n_images, cores, st=None, data_image=None, ss=3):
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled from a thread every 10 ms (no process
+    start-up latency, so even a 0.2 s region at 8 GPUs gets samples); `nvidia-smi -lms` is the fallback."""
+
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self._stop, self.thread = index, [], None, threading.Event(), None
+        self._nvml = None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except (ValueError, IndexError):
+                pass
+        return self.index
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self._nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._visible_index()), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -178,11 +202,37 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def _poll(self):
+        nv = self._nvml
+        flags = (("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                 ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                 ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        smax = nv.nvmlDeviceGetMaxClockInfo(self._handle, nv.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM)
+                mask = get_reasons(self._handle)
+                self.rows.append([str(sm), str(smax), ""] + ["Active" if mask & bit else "Not Active" for _, bit in flags])
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        self._stop.set()
+        if self._nvml is not None:
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+            try:
+                self._nvml.nvmlShutdown()
+            except Exception:
+                pass
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -205,7 +255,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
