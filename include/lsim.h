@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LSIM_ABI_VERSION 4
+#define LSIM_ABI_VERSION 5
 #define LSIM_MAX_PARAMS 12 /* largest param_names list on the path: EPL_MULTIPOLE_M1M3M4 */
 #define LSIM_MAX_SLOTS 8   /* output / linear-basis images per parameter set */
 
@@ -100,6 +100,21 @@ typedef struct lsim_light_desc {
 
 enum { LSIM_PRECISION_F64 = 0, LSIM_PRECISION_F32 = 1 };
 
+/* One point-source image (PointSource.point_source_list / linear_response_set, PointSource/point_source.py:255-384;
+ * UNLENSED and LENSED_POSITION give positions and amplitudes as parameters).  It is painted with the (supersampled)
+ * PSF kernel shifted to its sub-pixel position by bilinear interpolation and re-binned
+ * (PointSourceRendering.point_source_rendering, ImSim/Numerics/point_source_rendering.py:33-77;
+ * image_util.add_layer2image, Util/image_util.py:9-40), and added to its slot AFTER the PSF convolution of the
+ * extended light (ImageModel.point_source, image_model.py:395-429; linear_response_matrix,
+ * image_linear_solve.py:361-455). */
+typedef struct lsim_point_desc {
+  int32_t col_ra, col_dec, col_amp; /* column of params[B,P], or -1: use the constant below */
+  int32_t slot;                     /* output image (0..n_slots-1), -1: skipped */
+  double cst_ra, cst_dec, cst_amp;
+  int32_t use_amp;                  /* 0: amplitude 1 (one linear basis image per point-source image) */
+  int32_t pad;
+} lsim_point_desc;
+
 /* PSF convolution on the pixel grid (ImSim/Numerics/convolution.py) */
 enum {
   LSIM_CONV_NONE = 0,      /* psf_type NONE or unconvolved=True (numerics.py:170-171) */
@@ -165,6 +180,18 @@ typedef struct lsim_plan_desc {
    * counterpart is running without jax_enable_x64); convolution and likelihood stay fp64.  Refused with
    * LSIM_E_UNSUPPORTED for models outside its scope (see csrc/lsim_f32.cuh) -- never a silent fp64 fallback. */
   int32_t precision;
+
+  /* point sources (optional; needs the evaluation grid).  ps_kernel: the PSF kernel sampled at ps_supersampling
+   * points per pixel (PSF.kernel_point_source_supersampled), or the 3x3 delta of unconvolved=True.
+   * pixel = ps_Ma2pix . (ra, dec) + (ps_x_at_radec_0, ps_y_at_radec_0)  (Util/util.py:86-99).  nx == ny required. */
+  int32_t n_points;
+  const lsim_point_desc* points; /* host array [n_points] */
+  int32_t ps_kernel_size;        /* odd */
+  int32_t ps_supersampling;      /* >= 1 */
+  const double* ps_kernel;       /* host [Kp*Kp] */
+  double ps_x_at_radec_0, ps_y_at_radec_0;
+  double ps_Ma2pix[4];           /* row-major 2x2 */
+  double ps_scale;               /* flux scaling of the point-source image (image_model.py:429) */
 } lsim_plan_desc;
 
 typedef struct lsim_plan lsim_plan;

@@ -54,6 +54,10 @@ class Numerics(object):
         if convolution_type not in ("fft", "fft_static", "grid"):
             raise ValueError("convolution_type %s not supported!" % convolution_type)
         self._pixel_width = pixel_grid.pixel_width
+        # PointSourceRendering(pixel_grid, supersampling_factor=point_source_supersampling_factor, psf)
+        # (numerics.py:141-147, point_source_rendering.py:22-24)
+        self._ps_supersampling = psf.point_source_supersampling_factor if point_source_supersampling_factor is None \
+            else int(point_source_supersampling_factor)
         nx, ny = pixel_grid.num_pixel_axes
         ra0, dec0 = pixel_grid.radec_at_xy_0
         self._nx, self._ny = nx, ny
@@ -137,6 +141,10 @@ class Numerics(object):
         out = self._plans[key].resize_convolve(flat, unconvolved=unconvolved)
         out = out.reshape(lead + (self._ny, self._nx))
         return out if want_torch else out.cpu().numpy()
+
+    @property
+    def point_source_supersampling_factor(self):
+        return self._ps_supersampling
 
     @property
     def grid_supersampling_factor(self):
@@ -256,6 +264,10 @@ class NumericsSubFrame(object):
 
     def re_size_convolve(self, flux_array, unconvolved=False):
         return self._complete_frame(self._numerics_subframe.re_size_convolve(flux_array, unconvolved=unconvolved))
+
+    @property
+    def point_source_supersampling_factor(self):
+        return self._numerics_subframe.point_source_supersampling_factor
 
     @property
     def grid_supersampling_factor(self):

@@ -29,42 +29,54 @@ class ImageLinearFit(ImageModel):
             raise ValueError("at most %d linear components are supported by jaxtronomy_b200, got %d" % (_lib.MAX_SLOTS, n))
         self._n_lin = n
 
-    def _split_plan(self, unconvolved=False):
-        """Every light component in its own slot with amp = 1: source components first, then lens light
-        (linear_response_matrix order, image_linear_solve.py:391-441)."""
-        key = ("split", bool(unconvolved))
+    def _split_plan(self, unconvolved=False, num_images=None):
+        """Every linear component in its own slot with amp = 1: source components first, then lens light, then one
+        slot per point-source image (linear_response_matrix order, image_linear_solve.py:391-453)."""
+        num_images = list(self._num_point_images if num_images is None else num_images)
+        key = ("split", bool(unconvolved), tuple(num_images))
         if key not in self._plans:
-            ns = self.SourceModel._num_func
+            ns, n_light = self.SourceModel._num_func, self._n_lin
+            n_slots = n_light + sum(num_images)
+            if n_slots > _lib.MAX_SLOTS:
+                raise ValueError("at most %d linear components are supported by jaxtronomy_b200, got %d"
+                                 % (_lib.MAX_SLOTS, n_slots))
+            ps = dict(num_images=num_images, slots=[n_light + j for j in range(sum(num_images))], k=None)
             self._plans[key] = self._build_plan(list(range(ns)), [ns + i for i in range(self.LensLightModel._num_func)],
-                                                max(self._n_lin, 1), False, unconvolved)
+                                                max(n_slots, 1), False, unconvolved, ps=ps)
         return self._plans[key]
 
     def num_param_linear(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None, kwargs_ps=None):
-        return self._n_lin
+        n_ps = self.PointSource.num_basis(kwargs_ps) if (kwargs_ps and self._n_ps_models) else sum(self._num_point_images)
+        return self._n_lin + n_ps
 
     # -- batch entry points (CUDA tensors, no Python-side packing) ----------------------------------------------
-    def logL_linear_batch(self, params, source_marg=False, return_model=False, out=None):
-        """[B, P] parameter matrix -> (logL [B], amplitudes [B, n_lin], model [B, ny, nx] or None)."""
-        logl, amps, model = self._split_plan().logl(params, linear_solve=True, source_marg=source_marg,
-                                                    return_model=return_model, out=out)
+    def logL_linear_batch(self, params, source_marg=False, return_model=False, out=None, num_images=None):
+        """[B, P] parameter matrix -> (logL [B], amplitudes [B, n_lin], model [B, ny, nx] or None).  With point
+        sources the matrix carries their columns for ``num_images`` (default: num_point_source_images)."""
+        logl, amps, model = self._split_plan(num_images=num_images).logl(
+            params, linear_solve=True, source_marg=source_marg, return_model=return_model, out=out)
         if model is not None:
             model = self.ImageNumerics.complete_frame(model)
         return logl, amps, model
 
-    def response_batch(self, params, unconvolved=False):
-        """[B, P] -> convolved amp=1 basis images [B, n_lin, ny, nx] (full frame)."""
-        return self.ImageNumerics.complete_frame(self._split_plan(unconvolved).image(params))
+    def response_batch(self, params, unconvolved=False, num_images=None):
+        """[B, P] -> amp=1 basis images [B, n_lin, ny, nx] (full frame): convolved extended components, then the
+        point-source images."""
+        return self.ImageNumerics.complete_frame(self._split_plan(unconvolved, num_images).image(params))
 
     # -- reference API --------------------------------------------------------------------------------------------
     def linear_response_matrix(self, kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps=None,
                                kwargs_extinction=None, kwargs_special=None, unconvolved=False):
         """Response matrix [n_lin, N_d] on the unmasked pixels (image_linear_solve.py:361-455)."""
-        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light)
-        if self._n_lin == 0:
+        counts = self._ps_counts(kwargs_ps)
+        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps, counts)
+        if self._n_lin + sum(counts) == 0:
             return np.zeros(((B,) if batched else ()) + (0, self.num_data_evaluate))
         import torch
 
-        images = torch.nan_to_num(self.response_batch(mat, unconvolved))  # flux scaling is part of image_scale
+        # flux scaling is part of image_scale / ps_scale; point sources keep the PSF kernel also when
+        # unconvolved=True (image_linear_solve.py:444-449 calls point_source_rendering without the flag)
+        images = torch.nan_to_num(self.response_batch(mat, unconvolved, counts))
         A = self.image2array_masked(images)
         return self._finish(A, batched, self._want_torch(kwargs_lens, kwargs_source, kwargs_lens_light))
 
@@ -72,21 +84,22 @@ class ImageLinearFit(ImageModel):
                            kwargs_extinction=None, kwargs_special=None, inv_bool=False):
         """-> (model [ny, nx], model_error, cov_param, param): WLS amplitudes and the model they give
         (image_linear_solve.py:97-181).  ``cov_param`` (M^-1) is only formed when inv_bool is True."""
-        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light)
+        counts = self._ps_counts(kwargs_ps)
+        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps, counts)
         want_torch = self._want_torch(kwargs_lens, kwargs_source, kwargs_lens_light)
-        _, amps, model = self.logL_linear_batch(mat, return_model=True)
+        _, amps, model = self.logL_linear_batch(mat, return_model=True, num_images=counts)
         cov = None
         if inv_bool:
-            cov = self._finish(self._cov_param(mat), batched, want_torch)
+            cov = self._finish(self._cov_param(mat, counts), batched, want_torch)
         model_error = np.zeros(self.Data.num_pixel_axes)
         return (self._finish(model, batched, want_torch), model_error, cov, self._finish(amps, batched, want_torch))
 
-    def _cov_param(self, mat):
+    def _cov_param(self, mat, num_images=None):
         """M^-1 = (A W A^T)^-1 with the cond gate of de_lens.py:26-27 (only for callers that want the covariance;
         the likelihood kernel never forms it)."""
         import torch
 
-        images = torch.nan_to_num(self.response_batch(mat))
+        images = torch.nan_to_num(self.response_batch(mat, num_images=num_images))
         A = self.image2array_masked(images)  # [B, n, N_d]
         w = torch.as_tensor(1.0 / self.image2array_masked(self.Data.C_D), device=A.device)
         M = torch.einsum("bin,n,bjn->bij", A, w, A)
@@ -104,9 +117,10 @@ class ImageLinearFit(ImageModel):
         if linear_prior is not None:
             raise ValueError("linear_prior (d_prior marginalisation, de_lens.py:52-74) is outside the scope of "
                              "jaxtronomy_b200")
-        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light)
+        counts = self._ps_counts(kwargs_ps)
+        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps, counts)
         want_torch = self._want_torch(kwargs_lens, kwargs_source, kwargs_lens_light)
-        logl, amps, _ = self.logL_linear_batch(mat, source_marg=source_marg)
+        logl, amps, _ = self.logL_linear_batch(mat, source_marg=source_marg, num_images=counts)
         return self._finish(logl, batched, want_torch), self._finish(amps, batched, want_torch)
 
     def update_linear_kwargs(self, param, kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps=None):
@@ -114,8 +128,13 @@ class ImageLinearFit(ImageModel):
         i = 0
         kwargs_source, i = self.SourceModel.update_linear(param, i, kwargs_source)
         kwargs_lens_light, i = self.LensLightModel.update_linear(param, i, kwargs_lens_light)
+        if kwargs_ps and self._n_ps_models:
+            kwargs_ps, i = self.PointSource.update_linear(param, i, kwargs_ps, kwargs_lens)
         return kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps
 
     def linear_param_from_kwargs(self, kwargs_source, kwargs_lens_light, kwargs_ps=None):
-        return self.SourceModel.linear_param_from_kwargs(kwargs_source) + \
+        out = self.SourceModel.linear_param_from_kwargs(kwargs_source) + \
             self.LensLightModel.linear_param_from_kwargs(kwargs_lens_light)
+        if kwargs_ps and self._n_ps_models:
+            out = out + self.PointSource.linear_param_from_kwargs(kwargs_ps)
+        return out

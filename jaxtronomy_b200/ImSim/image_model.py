@@ -35,9 +35,17 @@ class ImageModel(object):
         if lens_model_class is None:
             lens_model_class = LensModel(lens_model_list=[])
         self.LensModel = lens_model_class
-        if point_source_class is not None and len(getattr(point_source_class, "point_source_type_list", [])) > 0:
-            raise ValueError("point sources are outside the scope of jaxtronomy_b200 (SURVEY.md 8(f)-3)")
+        if point_source_class is None:
+            from jaxtronomy_b200.PointSource.point_source import PointSource
+
+            point_source_class = PointSource(point_source_type_list=[])
         self.PointSource = point_source_class
+        self._n_ps_models = len(self.PointSource.point_source_type_list)
+        if psf_error_map_bool_list is not None and any(psf_error_map_bool_list):
+            raise ValueError("the PSF error map is outside the scope of jaxtronomy_b200 (SURVEY.md 8(f)-3)")
+        # images per point-source model: fixes the column layout of the batch entry points; the kwargs entry points
+        # read it from the lengths of ra_image
+        self._num_point_images = [0] * self._n_ps_models
         if source_model_class is None:
             source_model_class = LightModel(light_model_list=[])
         self.SourceModel = source_model_class
@@ -57,12 +65,8 @@ class ImageModel(object):
         self._mask1d = util.image2array(self.likelihood_mask)
         if data_class.primary_beam is not None:
             raise ValueError("primary beam not supported in jaxtronomy")
-        # one column per parameter, in the order lens -> source -> lens light (Param.args2kwargs order)
-        self.param_layout = _model.ColumnLayout()
-        self.LensModel.lens_descs(self.param_layout)
-        self.SourceModel.light_descs(self.param_layout, "source", True, [0] * self.SourceModel._num_func, True)
-        self.LensLightModel.light_descs(self.param_layout, "lens_light", False, [0] * self.LensLightModel._num_func,
-                                        True)
+        # one column per parameter, in the order lens -> source -> lens light -> point sources (Param.args2kwargs)
+        self.param_layout = self._full_layout(self._num_point_images)
         self._plans = {}
 
     # ----------------------------------------------------------------------------------------------------
@@ -89,8 +93,49 @@ class ImageModel(object):
         return dict(data=cut(d.data), cd_data=cut(np.asarray(d.C_D)), noise_map2=cut(nm2), exposure=cut(exposure),
                     background_rms=d.background_rms, mask=None if bool(np.all(mask)) else mask, logl_offset=offset)
 
+    # -- point sources ----------------------------------------------------------------------------------------
+    @property
+    def num_point_source_images(self):
+        return list(self._num_point_images)
+
+    @num_point_source_images.setter
+    def num_point_source_images(self, num_images):
+        """Images per point-source model for the [B, P] batch entry points (image_batch, logL_batch, the sampler
+        plans): the parameter matrix then carries ra_image[0..n), dec_image[0..n), point_amp[0..n) per model after
+        the lens, source and lens-light columns."""
+        num_images = [int(n) for n in num_images]
+        if len(num_images) != self._n_ps_models:
+            raise ValueError("%d image counts given for %d point-source models" % (len(num_images), self._n_ps_models))
+        if num_images != self._num_point_images:
+            self._num_point_images = num_images
+            self._plans = {}
+            self.param_layout = self._full_layout(num_images)
+
+    def _full_layout(self, num_images):
+        layout = _model.ColumnLayout()
+        self.LensModel.lens_descs(layout)
+        self.SourceModel.light_descs(layout, "source", True, [0] * self.SourceModel._num_func, True)
+        self.LensLightModel.light_descs(layout, "lens_light", False, [0] * self.LensLightModel._num_func, True)
+        self.PointSource.point_descs(layout, num_images, [0] * sum(num_images), True)
+        return layout
+
+    def _ps_dict(self, unconvolved):
+        """Rendering constants of PointSourceRendering (point_source_rendering.py:13-62)."""
+        if self.ImageNumerics.subframe_calc:
+            raise ValueError("point sources together with flux_evaluate_indexes sub-frames are not supported")
+        ss = self.ImageNumerics.point_source_supersampling_factor
+        if unconvolved:
+            kernel = np.zeros((3, 3))
+            kernel[1, 1] = 1
+        else:
+            kernel = self.PSF.kernel_point_source_supersampled(ss)
+        x0, y0 = self.Data.map_coord2pix(0.0, 0.0)
+        return dict(kernel=kernel, supersampling=ss, x_at_radec_0=x0, y_at_radec_0=y0,
+                    Ma2pix=self.Data.transform_angle2pix, scale=self._flux_scaling)
+
     def _build_plan(self, source_slots, lens_light_slots, n_slots, use_amp, unconvolved, lensed=True,
-                    source_fn=None, n_cols=None):
+                    source_fn=None, n_cols=None, ps=None):
+        """ps: None or dict(num_images, slots (flat over images, -1 = left out), k)"""
         layout = _model.ColumnLayout()
         lens_descs = self.LensModel.lens_descs(layout, source_fn=source_fn)  # always registers the lens columns
         if not lensed:
@@ -99,42 +144,72 @@ class ImageModel(object):
                                              source_fn=source_fn)
         light += self.LensLightModel.light_descs(layout, "lens_light", lensed=False, slots=lens_light_slots,
                                                  use_amp=use_amp, source_fn=source_fn)
+        points = None
+        if ps is not None and sum(ps["num_images"]) > 0:
+            points = self._ps_dict(unconvolved)
+            points["descs"] = self.PointSource.point_descs(layout, ps["num_images"], ps["slots"], use_amp,
+                                                           k=ps.get("k"), source_fn=source_fn)
         return _lib.Plan(layout.n_cols if n_cols is None else n_cols, lens_descs=lens_descs, light_descs=light,
-                         n_slots=n_slots,
+                         n_slots=n_slots, points=points,
                          grid=self.ImageNumerics.grid_dict(), psf=self.ImageNumerics.psf_dict(unconvolved),
                          image_scale=self.ImageNumerics.pixel_area * self._flux_scaling, data=self._data_dict(),
                          **self.LensModel.plan_kwargs())
 
-    def _joint_plan(self, source_bool, lens_light_bool, unconvolved=False, de_lensed=False):
-        """All selected components summed with their amplitudes into one image."""
-        key = ("joint", tuple(source_bool), tuple(lens_light_bool), bool(unconvolved), bool(de_lensed))
+    def _joint_plan(self, source_bool, lens_light_bool, unconvolved=False, de_lensed=False, num_images=None,
+                    ps_add=True, ps_k=None):
+        """All selected components summed with their amplitudes into one image.  The parameter matrix always
+        carries the point-source columns of ``num_images`` (default: the model's current image counts)."""
+        num_images = list(self._num_point_images if num_images is None else num_images)
+        key = ("joint", tuple(source_bool), tuple(lens_light_bool), bool(unconvolved), bool(de_lensed),
+               tuple(num_images), bool(ps_add), ps_k)
         if key not in self._plans:
+            ps = dict(num_images=num_images, slots=[0 if ps_add else -1] * sum(num_images), k=ps_k)
             self._plans[key] = self._build_plan([0 if b else -1 for b in source_bool],
                                                 [0 if b else -1 for b in lens_light_bool], 1, True, unconvolved,
-                                                lensed=not de_lensed)
+                                                lensed=not de_lensed, ps=ps)
         return self._plans[key]
 
     def sampler_plan(self, source_fn, n_cols, linear_solver):
         """Plan for the sampler boundary: ``source_fn`` maps every model parameter to a column of the sampler's
         `positions` matrix or to a constant (Param.args2kwargs, Sampling/likelihood.py:305)."""
         ns, nl = self.SourceModel._num_func, self.LensLightModel._num_func
+        num_images = list(getattr(source_fn, "num_point_images", [0] * self._n_ps_models))
+        if len(num_images) != self._n_ps_models:
+            raise ValueError("the Param class describes %d point-source models, the image model has %d"
+                             % (len(num_images), self._n_ps_models))
+        n_ps = sum(num_images)
         if linear_solver:
-            n_slots = max(ns + nl, 1)
+            n_slots = max(ns + nl + n_ps, 1)
             if n_slots > _lib.MAX_SLOTS:
                 raise ValueError("at most %d linear components are supported" % _lib.MAX_SLOTS)
+            ps = dict(num_images=num_images, slots=[ns + nl + j for j in range(n_ps)], k=None)
             return self._build_plan(list(range(ns)), [ns + i for i in range(nl)], n_slots, False, False,
-                                    source_fn=source_fn, n_cols=n_cols)
-        return self._build_plan([0] * ns, [0] * nl, 1, True, False, source_fn=source_fn, n_cols=n_cols)
+                                    source_fn=source_fn, n_cols=n_cols, ps=ps)
+        ps = dict(num_images=num_images, slots=[0] * n_ps, k=None)
+        return self._build_plan([0] * ns, [0] * nl, 1, True, False, source_fn=source_fn, n_cols=n_cols, ps=ps)
 
     def sampler_plans(self, param_class, n_cols, linear_solver, index_lists=None):
         """List of plans whose log-likelihoods add up to this model's (one entry for a single band)."""
         return [self.sampler_plan(param_class.column_source_fn(index_lists), n_cols, linear_solver)]
 
-    def _pack(self, kwargs_lens, kwargs_source, kwargs_lens_light):
+    def _pack(self, kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps=None, num_images=None):
         values = _model.gather_values(self.LensModel.param_name_list, kwargs_lens or [], "lens")
         values += _model.gather_values(self.SourceModel.param_name_list, kwargs_source or [], "source light")
         values += _model.gather_values(self.LensLightModel.param_name_list, kwargs_lens_light or [], "lens light")
+        if num_images is not None and sum(num_images) > 0:
+            values += self.PointSource.gather_values(kwargs_ps, num_images)
         return _model.pack_columns(values)
+
+    def _ps_counts(self, kwargs_ps):
+        """Images per point-source model of a kwargs call ([] / None: the model has no point sources)."""
+        if self._n_ps_models == 0:
+            return []
+        if not kwargs_ps:
+            raise ValueError("kwargs_ps is required: the model has %d point-source model(s)" % self._n_ps_models)
+        return self.PointSource.num_images(kwargs_ps)
+
+    def _dummy_ps(self, num_images):
+        return [dict(ra_image=np.zeros(n), dec_image=np.zeros(n), point_amp=np.zeros(n)) for n in num_images]
 
     @staticmethod
     def _want_torch(*kwargs_lists):
@@ -160,11 +235,26 @@ class ImageModel(object):
         """Make an image with a realisation of linear parameter values (image_model.py:431-492)."""
         if kwargs_extinction:
             raise ValueError("Extinction is not implemented in JAXtronomy yet")
-        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light)
+        counts = self._ps_counts(kwargs_ps)
+        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps, counts)
         plan = self._joint_plan([bool(source_add)] * self.SourceModel._num_func,
-                                [bool(lens_light_add)] * self.LensLightModel._num_func, unconvolved)
+                                [bool(lens_light_add)] * self.LensLightModel._num_func, unconvolved,
+                                num_images=counts, ps_add=bool(point_source_add))
         out = self.ImageNumerics.complete_frame(plan.image(mat)[:, 0])
         return self._finish(out, batched, self._want_torch(kwargs_lens, kwargs_source, kwargs_lens_light))
+
+    def point_source(self, kwargs_ps, kwargs_lens=None, kwargs_special=None, unconvolved=False, k=None):
+        """Point-source images painted with the PSF at their sub-pixel positions (image_model.py:395-429)."""
+        if kwargs_special:
+            raise ValueError("astrometric displacements (kwargs_special) are outside the scope of jaxtronomy_b200")
+        if self._n_ps_models == 0:
+            return np.zeros(self.Data.num_pixel_axes)
+        counts = self._ps_counts(kwargs_ps)
+        mat, B, batched = self._pack(self._dummy_lens(), self._dummy_source(), self._dummy_lens_light(), kwargs_ps,
+                                     counts)
+        plan = self._joint_plan([False] * self.SourceModel._num_func, [False] * self.LensLightModel._num_func,
+                                unconvolved, num_images=counts, ps_add=True, ps_k=k)
+        return self._finish(plan.image(mat)[:, 0], batched, False)
 
     def source_surface_brightness(self, kwargs_source, kwargs_lens=None, kwargs_extinction=None, kwargs_special=None,
                                   unconvolved=False, de_lensed=False, k=None, update_pixelbased_mapping=True):
@@ -175,14 +265,15 @@ class ImageModel(object):
             raise ValueError("Extinction is not implemented in JAXtronomy yet")
         mat, B, batched = self._pack(kwargs_lens, kwargs_source, self._dummy_lens_light())
         plan = self._joint_plan(self.SourceModel._bool_list(k), [False] * self.LensLightModel._num_func, unconvolved,
-                                de_lensed=de_lensed)
+                                de_lensed=de_lensed, num_images=[0] * self._n_ps_models)
         return self._finish(self.ImageNumerics.complete_frame(plan.image(mat)[:, 0]), batched,
                             self._want_torch(kwargs_lens, kwargs_source))
 
     def lens_surface_brightness(self, kwargs_lens_light, unconvolved=False, k=None):
         """image_model.py:370-393."""
         mat, B, batched = self._pack(self._dummy_lens(), self._dummy_source(), kwargs_lens_light)
-        plan = self._joint_plan([False] * self.SourceModel._num_func, self.LensLightModel._bool_list(k), unconvolved)
+        plan = self._joint_plan([False] * self.SourceModel._num_func, self.LensLightModel._bool_list(k), unconvolved,
+                                num_images=[0] * self._n_ps_models)
         return self._finish(self.ImageNumerics.complete_frame(plan.image(mat)[:, 0]), batched,
                             self._want_torch(kwargs_lens_light))
 
@@ -208,8 +299,13 @@ class ImageModel(object):
         (image_model.py:162-221)."""
         if check_positive_flux:
             raise ValueError("check positive flux is not supported in jaxtronomy")
-        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light)
-        logl = self.logL_batch(mat)
+        if kwargs_special:
+            raise ValueError("kwargs_special is outside the scope of jaxtronomy_b200")
+        counts = self._ps_counts(kwargs_ps)
+        mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps, counts)
+        plan = self._joint_plan([True] * self.SourceModel._num_func, [True] * self.LensLightModel._num_func,
+                                num_images=counts)
+        logl = plan.logl(mat, linear_solve=False)[0]
         return self._finish(logl, batched, self._want_torch(kwargs_lens, kwargs_source, kwargs_lens_light))
 
     def logL_batch(self, params, out=None):

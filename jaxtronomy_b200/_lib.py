@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("LSIM_LIB") or os.path.join(_HERE, "csrc", "liblsim.so
 
 MAX_PARAMS = 12
 MAX_SLOTS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 PRECISION_F64, PRECISION_F32 = 0, 1
 
 # enum mirrors (include/lsim.h)
@@ -45,6 +45,12 @@ class LightDesc(C.Structure):
 _dp = C.POINTER(C.c_double)
 
 
+class PointDesc(C.Structure):
+    _fields_ = [("col_ra", C.c_int32), ("col_dec", C.c_int32), ("col_amp", C.c_int32), ("slot", C.c_int32),
+                ("cst_ra", C.c_double), ("cst_dec", C.c_double), ("cst_amp", C.c_double), ("use_amp", C.c_int32),
+                ("pad", C.c_int32)]
+
+
 class PlanDesc(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("n_param_cols", C.c_int32),
@@ -58,6 +64,9 @@ class PlanDesc(C.Structure):
         ("kernel_hi_separable", C.c_int32), ("kernel_hi_1d", _dp),
         ("data", _dp), ("cd_data", _dp), ("noise_map2", _dp), ("exposure", _dp), ("background_rms", C.c_double),
         ("mask", C.POINTER(C.c_uint8)), ("logl_offset", C.c_double), ("precision", C.c_int32),
+        ("n_points", C.c_int32), ("points", C.POINTER(PointDesc)), ("ps_kernel_size", C.c_int32),
+        ("ps_supersampling", C.c_int32), ("ps_kernel", _dp), ("ps_x_at_radec_0", C.c_double),
+        ("ps_y_at_radec_0", C.c_double), ("ps_Ma2pix", C.c_double * 4), ("ps_scale", C.c_double),
     ]
 
 
@@ -154,11 +163,13 @@ class Plan:
     """Owns one lsim_plan (device copies of the static configuration) on the current CUDA device."""
 
     def __init__(self, n_param_cols, lens_descs=(), light_descs=(), n_slots=1, multi_plane=False, alpha_scaling=1.0,
-                 T_ij_end=0.0, T_z_source=0.0, grid=None, psf=None, image_scale=1.0, data=None):
+                 T_ij_end=0.0, T_z_source=0.0, grid=None, psf=None, image_scale=1.0, data=None, points=None):
         """
         :param grid: None or dict(nx, ny, ss, x_sub, y_sub)
         :param psf: None or dict(mode=CONV_*, kernel=[K,K], kernel_1d=[K] or None)
         :param data: None or dict(data, cd_data, noise_map2 or None, exposure or None, background_rms, mask or None)
+        :param points: None or dict(descs=[PointDesc], kernel=[Kp,Kp], supersampling, x_at_radec_0, y_at_radec_0,
+            Ma2pix=[2,2], scale): point-source images painted into the slot images after the convolution
         """
         torch = _torch()
         lib = load()
@@ -236,6 +247,19 @@ class Plan:
                     assert m.size == npix
                     keep.append(m)
                     d.mask = m.ctypes.data_as(C.POINTER(C.c_uint8))
+        if points is not None and len(points["descs"]) > 0:
+            if grid is None:
+                raise LsimError("point sources need an evaluation grid")
+            pts = (PointDesc * len(points["descs"]))(*points["descs"])
+            pk = _f64(points["kernel"])
+            keep += [pts, pk]
+            d.n_points, d.points = len(points["descs"]), pts
+            d.ps_kernel_size, d.ps_kernel, d.ps_supersampling = pk.shape[0], _ptr(pk), int(points["supersampling"])
+            d.ps_x_at_radec_0, d.ps_y_at_radec_0 = float(points["x_at_radec_0"]), float(points["y_at_radec_0"])
+            m = np.asarray(points["Ma2pix"], dtype=np.float64).ravel()
+            for k in range(4):
+                d.ps_Ma2pix[k] = float(m[k])
+            d.ps_scale = float(points.get("scale", 1.0))
         self.has_data = data is not None
         handle = C.c_void_p()
         with torch.cuda.device(self.device):

@@ -252,6 +252,19 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
   }
   const bool has_data = has_image && d->data && d->cd_data && (d->noise_map2 || d->exposure);
   if (d->precision != LSIM_PRECISION_F64 && d->precision != LSIM_PRECISION_F32) return LSIM_E_INVALID;
+  if (d->n_points < 0 || (d->n_points > 0 && (!d->points || !has_image))) return LSIM_E_INVALID;
+  if (d->n_points > 0) {
+    if (d->ps_kernel_size < 1 || d->ps_kernel_size % 2 == 0 || !d->ps_kernel || d->ps_supersampling < 1)
+      return LSIM_E_INVALID;
+    if (d->nx != d->ny) return LSIM_E_UNSUPPORTED;  // the reference's rendering assumes a square frame
+    if (d->eval_mask) return LSIM_E_UNSUPPORTED;    // sub-frames: the host side cuts the frame, not a pixel list
+    for (int i = 0; i < d->n_points; ++i) {
+      const lsim_point_desc& q = d->points[i];
+      if (q.slot >= d->n_slots || q.col_ra >= d->n_param_cols || q.col_dec >= d->n_param_cols ||
+          q.col_amp >= d->n_param_cols)
+        return LSIM_E_INVALID;
+    }
+  }
   if (d->precision == LSIM_PRECISION_F32 && !f32_supported(d)) return LSIM_E_UNSUPPORTED;
 
   lsim_plan* p = new (std::nothrow) lsim_plan();
@@ -320,6 +333,17 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
         TRY(p->upload(d->kernel_hi, (size_t)d->kernel_hi_size * d->kernel_hi_size, &D.kernel_hi));
         if (d->kernel_hi_separable) TRY(p->upload(d->kernel_hi_1d, (size_t)d->kernel_hi_size, &D.kernel_hi_1d));
       }
+    }
+    if (d->n_points > 0) {
+      D.n_points = d->n_points;
+      D.ps_K = d->ps_kernel_size;
+      D.ps_ss = d->ps_supersampling;
+      TRY(p->upload(d->points, (size_t)d->n_points, &D.points));
+      TRY(p->upload(d->ps_kernel, (size_t)d->ps_kernel_size * d->ps_kernel_size, &D.ps_kernel));
+      D.ps_x0 = d->ps_x_at_radec_0;
+      D.ps_y0 = d->ps_y_at_radec_0;
+      for (int k = 0; k < 4; ++k) D.ps_M[k] = d->ps_Ma2pix[k];
+      D.ps_scale = d->ps_scale;
     }
     if (D.K > 0 && !d->kernel_separable)
       TRY(fft_conv_create(d->nx, d->ny, d->kernel_size, d->kernel, d->conv_mode, &p->fft_lo));
@@ -840,18 +864,24 @@ int run_chunk(const lsim_plan* plan, const double* params, int64_t s0, int64_t n
   // the scratch starts with the prepared-constants blocks of the chunk (none when the caller gave no scratch)
   const unsigned char* prep = reinterpret_cast<const unsigned char*>(ws);
   if (ws) ws += (size_t)chunk * prep_bytes(plan) / sizeof(double);
-  if (D.conv_mode == LSIM_CONV_NONE) return launch_image(plan, params, s0, n, D.image_scale, dst, nullptr, st, prep);
-  double* U = ws;  // [chunk][ns][npix]
-  if (!D.ss_conv) {
-    int rc = launch_image(plan, params, s0, n, 1.0, U, nullptr, st, prep);
-    if (rc != LSIM_OK) return rc;
-    return launch_conv(plan, U, dst, n * D.n_slots, st);
+  int rc;
+  if (D.conv_mode == LSIM_CONV_NONE) {
+    rc = launch_image(plan, params, s0, n, D.image_scale, dst, nullptr, st, prep);
+  } else if (!D.ss_conv) {
+    double* U = ws;  // [chunk][ns][npix]
+    rc = launch_image(plan, params, s0, n, 1.0, U, nullptr, st, prep);
+    if (rc == LSIM_OK) rc = launch_conv(plan, U, dst, n * D.n_slots, st);
+  } else {
+    double* U = ws;
+    double* Usub = ws + (size_t)chunk * ns * npix;
+    double* Hsub = Usub + (size_t)chunk * ns * nsub;
+    rc = launch_image(plan, params, s0, n, 1.0, U, Usub, st, prep);
+    if (rc == LSIM_OK) rc = launch_conv_supersampled(plan, Usub, Hsub, U, dst, n * D.n_slots, st);
   }
-  double* Usub = ws + (size_t)chunk * ns * npix;
-  double* Hsub = Usub + (size_t)chunk * ns * nsub;
-  int rc = launch_image(plan, params, s0, n, 1.0, U, Usub, st, prep);
-  if (rc != LSIM_OK) return rc;
-  return launch_conv_supersampled(plan, Usub, Hsub, U, dst, n * D.n_slots, st);
+  if (rc != LSIM_OK || D.n_points == 0) return rc;
+  Timed timed(kClsOther, st);
+  k_point_sources<<<dim3((unsigned)D.n_slots, (unsigned)n), kBlock, 0, st>>>(D, params, s0, dst);
+  return after_launch("k_point_sources");
 }
 
 int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, int64_t n, int linear, int marg,

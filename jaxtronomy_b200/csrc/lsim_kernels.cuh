@@ -54,6 +54,11 @@ struct PlanDev {
   double bkg2;
   const uint8_t* mask;
   double logl_offset;
+  // point sources
+  int32_t n_points, ps_K, ps_ss;
+  const lsim_point_desc* points;
+  const double* ps_kernel;
+  double ps_x0, ps_y0, ps_M[4], ps_scale;
 };
 
 // ---- shared-memory staging of per-set constants -----------------------------------------------------------
@@ -529,6 +534,63 @@ k_conv_separable(const double* __restrict__ in, double* __restrict__ out, int nx
       double* d = dst + (int64_t)y * nx + x;
       *d = accumulate ? fma(a, scale, *d) : a * scale;
     }
+  }
+}
+
+// ---- k_point_sources: PSF stamps of the point-source images, added to the finished slot images ----------------------
+// grid (n_slots, sets): one CTA owns one output image, walks the point images assigned to it one after the other
+// (no atomics, deterministic order) and its threads share the pixels of each footprint.
+// Pixel value = amp * sum over the ss x ss sub-pixels of the bilinear interpolation of the supersampled kernel at
+//   (row, col) = (r + Kp/2 - y_sub, c + Kp/2 - x_sub),  x_sub = x_pix ss + (ss-1)/2
+// with zeros outside the kernel, neighbour by neighbour (jax.scipy.ndimage.map_coordinates, order 1, mode
+// "constant"), which is add_layer2image + re_size(...) * ss^2 of the reference.
+__device__ __forceinline__ double ps_bilinear(const double* __restrict__ k, int K, double ky, double kx) {
+  const double fy = floor(ky), fx = floor(kx);
+  const double wy1 = ky - fy, wx1 = kx - fx, wy0 = 1.0 - wy1, wx0 = 1.0 - wx1;
+  const int iy = (int)fy, ix = (int)fx;
+  auto at = [&](int y, int x) { return (y >= 0 && y < K && x >= 0 && x < K) ? k[y * K + x] : 0.0; };
+  // order of jax's accumulation: (lower, lower), (lower, upper), (upper, lower), (upper, upper); weight product first
+  double s = (wy0 * wx0) * at(iy, ix);
+  s += (wy0 * wx1) * at(iy, ix + 1);
+  s += (wy1 * wx0) * at(iy + 1, ix);
+  s += (wy1 * wx1) * at(iy + 1, ix + 1);
+  return s;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_point_sources(PlanDev P, const double* __restrict__ params, int64_t set0, double* __restrict__ dst) {
+  const int slot = blockIdx.x;
+  const int64_t bl = blockIdx.y;
+  const double* row = params + (set0 + bl) * P.n_param_cols;
+  double* img = dst + (bl * P.n_slots + slot) * ((int64_t)P.nx * P.ny);
+  const int K = P.ps_K, ss = P.ps_ss, half = K / 2;
+  for (int i = 0; i < P.n_points; ++i) {
+    const lsim_point_desc& d = P.points[i];
+    if (d.slot != slot) continue;
+    const double ra = d.col_ra >= 0 ? row[d.col_ra] : d.cst_ra;
+    const double dec = d.col_dec >= 0 ? row[d.col_dec] : d.cst_dec;
+    const double amp = d.use_amp ? (d.col_amp >= 0 ? row[d.col_amp] : d.cst_amp) : 1.0;
+    const double xp = P.ps_M[0] * ra + P.ps_M[1] * dec + P.ps_x0;
+    const double yp = P.ps_M[2] * ra + P.ps_M[3] * dec + P.ps_y0;
+    const double xs = xp * ss + (ss - 1) / 2.0, ys = yp * ss + (ss - 1) / 2.0;
+    // sub-grid columns with a non-zero contribution: -1 < c + half - xs < K
+    if (!(fabs(xs) < 1e9 && fabs(ys) < 1e9)) continue;  // nan / absurd positions paint nothing
+    const int c_lo = (int)floor(xs - half - 1.0), c_hi = (int)ceil(xs - half + K);
+    const int r_lo = (int)floor(ys - half - 1.0), r_hi = (int)ceil(ys - half + K);
+    const int px_lo = max(0, (int)floor((double)c_lo / ss)), px_hi = min(P.nx - 1, (int)floor((double)c_hi / ss));
+    const int py_lo = max(0, (int)floor((double)r_lo / ss)), py_hi = min(P.ny - 1, (int)floor((double)r_hi / ss));
+    const int w = px_hi - px_lo + 1, h = py_hi - py_lo + 1;
+    if (w > 0 && h > 0) {
+      for (int t = threadIdx.x; t < w * h; t += kBlock) {
+        const int py = py_lo + t / w, px = px_lo + t % w;
+        double acc = 0.0;
+        for (int sy = 0; sy < ss; ++sy)
+          for (int sx = 0; sx < ss; ++sx)
+            acc += ps_bilinear(P.ps_kernel, K, (py * ss + sy) + half - ys, (px * ss + sx) + half - xs);
+        img[(int64_t)py * P.nx + px] += amp * acc * P.ps_scale;
+      }
+    }
+    __syncthreads();  // the next point image may touch the same pixels from other threads
   }
 }
 

@@ -304,12 +304,17 @@ class ImageModel:
 
     def __init__(self, data_class, psf_class, lens_model_list=None, source_model_list=None,
                  lens_light_model_list=None, kwargs_numerics=None, likelihood_mask=None,
-                 lens_profile_kwargs_list=None):
+                 lens_profile_kwargs_list=None, point_source_type_list=None):
+        # point sources: UNLENSED / LENSED_POSITION without fixed magnification -- positions and amplitudes are the
+        # parameters themselves (PointSource/Types/unlensed.py, lensed_position.py)
+        self.point_source_type_list = list(point_source_type_list or [])
+        self._ps_supersampling = (kwargs_numerics or {}).get("point_source_supersampling_factor", 1)
         self.Data = data_class
         self.PSF = psf_class
         self._flux_scaling = getattr(data_class, "flux_scaling", 1)
         self.PSF.set_pixel_size(self.Data.pixel_width)
-        self.ImageNumerics = NumericsSubFrame(pixel_grid=self.Data, psf=self.PSF, **(kwargs_numerics or {}))
+        kwargs_numerics = {k: v for k, v in (kwargs_numerics or {}).items() if k != "point_source_supersampling_factor"}
+        self.ImageNumerics = NumericsSubFrame(pixel_grid=self.Data, psf=self.PSF, **kwargs_numerics)
         self.lens_model_list = list(lens_model_list or [])
         self.lens_profile_kwargs_list = lens_profile_kwargs_list
         self.source_model_list = list(source_model_list or [])
@@ -339,18 +344,39 @@ class ImageModel:
         flux = _light.surface_brightness(self.lens_light_model_list, x, y, kwargs_lens_light or [], k=k)
         return self.ImageNumerics.re_size_convolve(flux, unconvolved=unconvolved) * self._flux_scaling
 
+    # --- point sources: image_model.py:395-429, PointSource/point_source.py:255-284,347-384 ---
+    def _ps_render(self, ra, dec, amp, unconvolved=False):
+        from oracle.point_source import point_source_rendering
+
+        kernel = None if unconvolved else self.PSF.kernel_point_source_supersampled(self._ps_supersampling)
+        return point_source_rendering(self.Data, kernel, self._ps_supersampling, ra, dec, amp, unconvolved=unconvolved)
+
+    def point_source(self, kwargs_ps, unconvolved=False, k=None):
+        image = np.zeros(self.Data.num_pixel_axes)
+        ra, dec, amp = [], [], []
+        for i, kw in enumerate(kwargs_ps or []):
+            if k is None or k == i:
+                ra += list(np.atleast_1d(kw["ra_image"]))
+                dec += list(np.atleast_1d(kw["dec_image"]))
+                amp += list(np.atleast_1d(kw["point_amp"]))
+        image = image + self._ps_render(np.array(ra), np.array(dec), np.array(amp), unconvolved=unconvolved)
+        return image * self._flux_scaling
+
     def image(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None, unconvolved=False,
-              source_add=True, lens_light_add=True):
+              source_add=True, lens_light_add=True, kwargs_ps=None, point_source_add=True):
         model = np.zeros(self.Data.num_pixel_axes)
         if source_add:
             model = model + self.source_surface_brightness(kwargs_source, kwargs_lens, unconvolved=unconvolved)
         if lens_light_add:
             model = model + self.lens_surface_brightness(kwargs_lens_light, unconvolved=unconvolved)
+        if point_source_add and self.point_source_type_list:
+            model = model + self.point_source(kwargs_ps, unconvolved=unconvolved)
         return model
 
-    def likelihood_data_given_model(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None):
+    def likelihood_data_given_model(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None,
+                                    kwargs_ps=None):
         """image_model.py:162-221 (no linear solve)."""
-        im_sim = self.image(kwargs_lens, kwargs_source, kwargs_lens_light)
+        im_sim = self.image(kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps=kwargs_ps)
         model_error = np.zeros(self.Data.num_pixel_axes)
         return self.Data.log_likelihood(im_sim, self.likelihood_mask, model_error)
 
@@ -365,7 +391,8 @@ class ImageModel:
         return array2image(grid1d, nx, ny)
 
     # --- image_linear_solve.py ---
-    def linear_response_matrix(self, kwargs_lens, kwargs_source, kwargs_lens_light, unconvolved=False):
+    def linear_response_matrix(self, kwargs_lens, kwargs_source, kwargs_lens_light, unconvolved=False,
+                               kwargs_ps=None):
         x, y = self.ImageNumerics.coordinates_evaluate
         rows = []
         if len(self.source_model_list) > 0:
@@ -378,11 +405,16 @@ class ImageModel:
         for image in resp:
             image = self.ImageNumerics.re_size_convolve(image, unconvolved=unconvolved)
             rows.append(nan_to_num(self.image2array_masked(image)))
+        for kw in (kwargs_ps or []) if self.point_source_type_list else []:  # one basis image per point-source image
+            for ra, dec in zip(np.atleast_1d(kw["ra_image"]), np.atleast_1d(kw["dec_image"])):
+                image = self._ps_render(np.array([ra]), np.array([dec]), np.array([1.0]))
+                rows.append(nan_to_num(self.image2array_masked(image)))
         A = np.array(rows).reshape(len(rows), self.num_data_evaluate)
         return A * self._flux_scaling
 
-    def image_linear_solve(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None, inv_bool=False):
-        A = self.linear_response_matrix(kwargs_lens, kwargs_source, kwargs_lens_light)
+    def image_linear_solve(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None, inv_bool=False,
+                           kwargs_ps=None):
+        A = self.linear_response_matrix(kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps=kwargs_ps)
         model_error = np.zeros(self.Data.num_pixel_axes)
         C_D_response = self.image2array_masked(self.Data.C_D + model_error)
         d = self.image2array_masked(self.Data.data)
@@ -390,10 +422,10 @@ class ImageModel:
         return self.array_masked2image(wls_model), model_error, cov_param, param
 
     def likelihood_data_given_model_linear(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None,
-                                           source_marg=False):
+                                           source_marg=False, kwargs_ps=None):
         """ImageLinearFit.likelihood_data_given_model, image_linear_solve.py:228-339 -> (logL, param)."""
         model, model_error, cov, param = self.image_linear_solve(kwargs_lens, kwargs_source, kwargs_lens_light,
-                                                                 inv_bool=source_marg)
+                                                                 inv_bool=source_marg, kwargs_ps=kwargs_ps)
         logL = self.Data.log_likelihood(model, self.likelihood_mask, model_error)
         if cov is not None and source_marg:
             logL = logL + marginalisation_const(cov)

@@ -11,6 +11,8 @@ lenstronomy host helpers -- see refshim.py for what is and is not substituted) a
     tests/golden/profiles.npz     deflections of every hot-path lens profile + light profiles + 2F1 sweep
     tests/golden/lens_models.npz  LensModel / LensModelBulk / MultiPlane ray shooting
     tests/golden/imsim.npz        grid bookkeeping, re-bin + convolution, ImageModel, ImageLinearFit
+    tests/golden/point_sources.npz  point-source rendering, ImageModel / ImageLinearFit with point sources
+                                  (python tests/golden/make_golden.py point_sources  regenerates only this file)
 
 Parameter sets follow the reference's own tests (test/test_LensModel/test_Profiles/*.py,
 test/test_ImSim/*.py) plus the clamps/edge cases listed in SURVEY.md 7 "Hard parts".
@@ -437,7 +439,87 @@ def gen_imsim():
     st.save("imsim.npz")
 
 
+def gen_point_sources():
+    """Point sources: PointSourceRendering, ImageModel.point_source / image and ImageLinearFit with
+    UNLENSED + LENSED_POSITION models, after test/test_ImSim/test_Numerics/test_point_source_rendering.py and
+    test/test_ImSim/test_image_model.py (point_source_type_list=["LENSED_POSITION"], 4 images)."""
+    from jaxtronomy.ImSim.Numerics.point_source_rendering import PointSourceRendering
+    from jaxtronomy.PointSource.point_source import PointSource
+
+    st = Store()
+    rng = np.random.default_rng(23)
+    # 1. rendering alone: supersampling 1 and 3, positions inside, on the edge and outside the frame
+    numPix, deltaPix = 24, 0.07
+    kd = sim_util.data_configure_simple(numPix, deltaPix, 100.0, 0.05, inverse=False)
+    pg = PixelGrid(numPix, numPix, kd["transform_pix2angle"], kd["ra_at_xy_0"], kd["dec_at_xy_0"])
+    ra = np.array([0.11, -0.4321, 0.77, -0.83, 1.2])  # the last one lies outside the frame
+    dec = np.array([-0.2, 0.3, 0.79, -0.8299, 0.1])
+    amp = np.array([10.0, 3.0, 7.5, 1.0, 4.0])
+    for ss in (1, 3):
+        K = 7 * ss if (7 * ss) % 2 == 1 else 7 * ss + 1
+        kern = gauss_kernel(K, 1.1 * ss) + 0.02 * rng.uniform(0, 1, (K, K)) / K**2
+        psf = PSF(psf_type="PIXEL", kernel_point_source=kern, point_source_supersampling_factor=ss)
+        psr = PointSourceRendering(pg, supersampling_factor=ss, psf=psf)
+        out = np.asarray(psr.point_source_rendering(ra, dec, amp))
+        outu = np.asarray(psr.point_source_rendering(ra, dec, amp, unconvolved=True))
+        st.add("rendering_ss%d" % ss, dict(ra=ra, dec=dec, amp=amp, kernel=kern, transform_pix2angle=kd["transform_pix2angle"],
+                                         ra_at_xy_0=kd["ra_at_xy_0"], dec_at_xy_0=kd["dec_at_xy_0"]),
+               dict(image=out, image_unconvolved=outu), dict(numPix=numPix, supersampling=ss))
+
+    # 2. ImageModel / ImageLinearFit with a lensed quad and a field star
+    numPix, deltaPix = 40, 0.08
+    kern = gauss_kernel(9, 1.4) + 0.02 * rng.uniform(0, 1, (9, 9)) / 81
+    kd = sim_util.data_configure_simple(numPix, deltaPix, 100.0, 0.05, inverse=False)
+    kw_lens = [dict(theta_E=1.1, gamma=2.0, e1=0.1, e2=-0.05, center_x=0.02, center_y=-0.01),
+               dict(gamma1=0.03, gamma2=-0.01, ra_0=0, dec_0=0)]
+    kw_src = [dict(amp=12.0, R_sersic=0.2, n_sersic=1.5, e1=0.1, e2=0.05, center_x=0.08, center_y=0.03)]
+    kw_ll = [dict(amp=20.0, R_sersic=0.5, n_sersic=3.0, e1=0.05, e2=0.0, center_x=0.02, center_y=-0.01)]
+    kw_ps = [dict(ra_image=np.array([1.013, -0.734, 0.412, -0.551]), dec_image=np.array([0.402, -0.846, -1.002, 0.978]),
+                  point_amp=np.array([30.0, 25.0, 18.0, 12.0])),
+             dict(ra_image=np.array([-1.21]), dec_image=np.array([1.07]), point_amp=np.array([40.0]))]
+    ps_types = ["LENSED_POSITION", "UNLENSED"]
+    psf_kw = dict(psf_type="PIXEL", kernel_point_source=kern)
+    num_kw = dict(supersampling_factor=2, point_source_supersampling_factor=1)
+    lens, src, ll = LensModel(["EPL", "SHEAR"]), LightModel(["SERSIC_ELLIPSE"]), LightModel(["SERSIC_ELLIPSE"])
+    cp = lambda kws: [{k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()} for kw in kws]  # noqa: E731
+    psf = PSF(**psf_kw)
+    ps = PointSource(ps_types, lens_model=lens)
+    data = ImageData(**kd)
+    im = ImageModel(data, psf, lens, src, ll, point_source_class=ps, kwargs_numerics=num_kw)
+    truth = np.asarray(im.image(kw_lens, kw_src, kw_ll, cp(kw_ps)))
+    noisy = truth + rng.normal(0, 0.05, truth.shape) + rng.normal(0, 1, truth.shape) * np.sqrt(np.maximum(truth, 0) / 100.0)
+    kd2 = dict(kd, image_data=noisy)
+    data = ImageData(**kd2)
+    im = ImageModel(data, psf, lens, src, ll, point_source_class=ps, kwargs_numerics=num_kw)
+    lin = ImageLinearFit(data, psf, lens, src, ll, point_source_class=ps, kwargs_numerics=num_kw)
+    kw_ps_p = cp(kw_ps)
+    kw_ps_p[0]["ra_image"] = kw_ps_p[0]["ra_image"] + 0.004  # perturbed: the model differs from the data
+    outs = dict(
+        image=np.asarray(im.image(kw_lens, kw_src, kw_ll, cp(kw_ps_p))),
+        image_unconvolved=np.asarray(im.image(kw_lens, kw_src, kw_ll, cp(kw_ps_p), unconvolved=True)),
+        image_no_ps=np.asarray(im.image(kw_lens, kw_src, kw_ll, cp(kw_ps_p), point_source_add=False)),
+        point_source=np.asarray(im.point_source(cp(kw_ps_p), kw_lens)),
+        point_source_k1=np.asarray(im.point_source(cp(kw_ps_p), kw_lens, k=1)),
+        logL=float(im.likelihood_data_given_model(kw_lens, kw_src, kw_ll, cp(kw_ps_p))),
+        A=np.asarray(lin.linear_response_matrix(kw_lens, cp(kw_src), cp(kw_ll), cp(kw_ps_p))))
+    model, _, _, param = lin.image_linear_solve(kw_lens, cp(kw_src), cp(kw_ll), cp(kw_ps_p))
+    logL_lin, param2 = lin.likelihood_data_given_model(kw_lens, cp(kw_src), cp(kw_ll), cp(kw_ps_p))
+    outs.update(wls_model=np.asarray(model), param=np.asarray(param), logL_linear=float(logL_lin))
+    ins = dict(image_data=noisy, transform_pix2angle=kd["transform_pix2angle"], ra_at_xy_0=kd["ra_at_xy_0"],
+               dec_at_xy_0=kd["dec_at_xy_0"], exposure_time=kd["exposure_time"], background_rms=0.05, kernel=kern)
+    st.add("image_quad_and_star", ins, outs,
+           dict(numPix=numPix, deltaPix=deltaPix, lens_model_list=["EPL", "SHEAR"], kwargs_lens=kw_lens,
+                source_model_list=["SERSIC_ELLIPSE"], kwargs_source=kw_src, lens_light_model_list=["SERSIC_ELLIPSE"],
+                kwargs_lens_light=kw_ll, point_source_type_list=ps_types, kwargs_ps=kw_ps_p,
+                kwargs_psf=dict(psf_type="PIXEL"), kwargs_numerics=num_kw))
+    st.save("point_sources.npz")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["point_sources"]:
+        gen_point_sources()
+        sys.exit(0)
     gen_profiles()
     gen_lens_models()
     gen_imsim()
+    gen_point_sources()

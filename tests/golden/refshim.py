@@ -228,7 +228,15 @@ def _make_jax():
     jsp.special.gammaln = _wrapped(scipy.special.gammaln)
     jsp.special.eval_hermite = _wrapped(scipy.special.eval_hermite)
     jsp.ndimage = types.ModuleType("jax.scipy.ndimage")
-    jsp.ndimage.map_coordinates = _wrapped(scipy.ndimage.map_coordinates)
+    def _map_coordinates(input, coordinates, order, mode="constant", cval=0.0):
+        # jax.scipy.ndimage.map_coordinates (jax/_src/scipy/ndimage.py) replaces every out-of-range NEIGHBOUR by
+        # cval and keeps interpolating: that is scipy's "grid-constant", not scipy's "constant"
+        if mode == "constant":
+            mode = "grid-constant"
+        return scipy.ndimage.map_coordinates(np.asarray(input, dtype=float), [np.asarray(c) for c in coordinates],
+                                             order=order, mode=mode, cval=cval)
+
+    jsp.ndimage.map_coordinates = _map_coordinates
 
     experimental = types.ModuleType("jax.experimental")
     experimental.checkify = types.ModuleType("jax.experimental.checkify")
@@ -246,7 +254,12 @@ def _make_jax():
     jax.config = _Config()
     jax.debug = types.SimpleNamespace(print=lambda *a, **k: None)
     jax.devices = lambda *a: [object()]
+    # imported at module level by the lens-equation solver (PointSource/Types/base_ps.py pulls it in); never called
+    jax.random = types.ModuleType("jax.random")
+    jsp.optimize = types.ModuleType("jax.scipy.optimize")
+    jsp.optimize.minimize = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("minimize not in refshim"))
     mods = {
+        "jax.random": jax.random, "jax.scipy.optimize": jsp.optimize,
         "jax": jax, "jax.numpy": jnp, "jax.numpy.linalg": jnp.linalg, "jax.lax": lax, "jax.tree_util": tree_util,
         "jax.scipy": jsp, "jax.scipy.signal": jsp.signal, "jax.scipy.special": jsp.special,
         "jax.scipy.ndimage": jsp.ndimage, "jax.experimental": experimental,

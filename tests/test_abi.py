@@ -59,17 +59,22 @@ int main(void) {
          offsetof(lsim_plan_desc, mask));
   printf("%zu %zu %zu\\n", offsetof(lsim_plan_desc, eval_mask), offsetof(lsim_plan_desc, kernel_hi),
          offsetof(lsim_plan_desc, logl_offset));
+  printf("%zu %zu %zu %zu\\n", offsetof(lsim_plan_desc, precision), offsetof(lsim_plan_desc, points),
+         offsetof(lsim_plan_desc, ps_Ma2pix), offsetof(lsim_plan_desc, ps_scale));
+  printf("%zu %zu %zu\\n", sizeof(lsim_point_desc), offsetof(lsim_point_desc, cst_ra), offsetof(lsim_point_desc, use_amp));
   return 0;
 }''')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
     out = subprocess.check_output([str(exe)], text=True).split()
     got = [int(v) for v in out]
-    L, G, P = _lib.LensDesc, _lib.LightDesc, _lib.PlanDesc
+    L, G, P, Q = _lib.LensDesc, _lib.LightDesc, _lib.PlanDesc, _lib.PointDesc
     want = [C.sizeof(L), L.cst.offset, L.opt.offset, L.delta_T.offset, L.red2phys.offset,
             C.sizeof(G), G.col.offset, G.cst.offset,
             C.sizeof(P), P.lens.offset, P.light.offset, P.x_sub.offset, P.data.offset, P.mask.offset,
-            P.eval_mask.offset, P.kernel_hi.offset, P.logl_offset.offset]
+            P.eval_mask.offset, P.kernel_hi.offset, P.logl_offset.offset,
+            P.precision.offset, P.points.offset, P.ps_Ma2pix.offset, P.ps_scale.offset,
+            C.sizeof(Q), Q.cst_ra.offset, Q.use_amp.offset]
     assert got == want
 
 

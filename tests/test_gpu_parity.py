@@ -478,3 +478,86 @@ def test_fft_convolution_matches_direct_and_the_oracle(monkeypatch):
     monkeypatch.setenv("LSIM_FFT_MIN_K", "5")
     fft21 = _numerics_with_pixel_psf(nx, ny, k21).re_size_convolve(flux)
     assert_close(fft21, direct21, what="fft vs tiled", **BAR)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# point sources against the reference fixtures
+# ---------------------------------------------------------------------------------------------------------------
+POINTS = load("point_sources.npz")
+
+
+@pytest.mark.parametrize("name", [n for n in POINTS if n.startswith("rendering_")])
+def test_point_source_rendering(name):
+    """PointSourceRendering.point_source_rendering through ImageModel.point_source (k_point_sources): stamps inside,
+    across the edge of and outside the frame, supersampling 1 and 3, convolved and unconvolved."""
+    from jaxtronomy_b200.Data.imaging_data import ImageData
+    from jaxtronomy_b200.Data.psf import PSF
+    from jaxtronomy_b200.ImSim.image_model import ImageModel
+    from jaxtronomy_b200.PointSource.point_source import PointSource
+
+    c = POINTS[name]
+    n, ss = c.meta["numPix"], c.meta["supersampling"]
+    data = ImageData(image_data=np.zeros((n, n)), transform_pix2angle=c.inp["transform_pix2angle"],
+                     ra_at_xy_0=float(c.inp["ra_at_xy_0"]), dec_at_xy_0=float(c.inp["dec_at_xy_0"]),
+                     background_rms=1.0, exposure_time=1.0)
+    psf = PSF(psf_type="PIXEL", kernel_point_source=c.inp["kernel"], point_source_supersampling_factor=ss)
+    im = ImageModel(data, psf, point_source_class=PointSource(["UNLENSED"]),
+                    kwargs_numerics=dict(point_source_supersampling_factor=ss))
+    kps = [dict(ra_image=c.inp["ra"], dec_image=c.inp["dec"], point_amp=c.inp["amp"])]
+    assert_close(im.point_source(kps), c.out["image"], what=name, **BAR)
+    assert_close(im.point_source(kps, unconvolved=True), c.out["image_unconvolved"], what=name + " unconvolved", **BAR)
+    assert_close(im.image(kwargs_ps=kps), c.out["image"], what=name + " via image()", **BAR)
+
+
+def _ps_model(c, linear):
+    from jaxtronomy_b200.Data.imaging_data import ImageData
+    from jaxtronomy_b200.ImSim.image_linear_solve import ImageLinearFit
+    from jaxtronomy_b200.ImSim.image_model import ImageModel
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+    from jaxtronomy_b200.LightModel.light_model import LightModel
+    from jaxtronomy_b200.PointSource.point_source import PointSource
+
+    kd = dict(image_data=c.inp["image_data"], transform_pix2angle=c.inp["transform_pix2angle"],
+              ra_at_xy_0=float(c.inp["ra_at_xy_0"]), dec_at_xy_0=float(c.inp["dec_at_xy_0"]),
+              background_rms=float(c.inp["background_rms"]), exposure_time=float(c.inp["exposure_time"]))
+    lens = LensModel(c.meta["lens_model_list"])
+    cls = ImageLinearFit if linear else ImageModel
+    return cls(ImageData(**kd), _psf(c.meta["kwargs_psf"], c.inp), lens, LightModel(c.meta["source_model_list"]),
+               LightModel(c.meta["lens_light_model_list"]),
+               point_source_class=PointSource(c.meta["point_source_type_list"], lens_model=lens),
+               kwargs_numerics=c.meta["kwargs_numerics"])
+
+
+def test_image_model_with_point_sources():
+    c = POINTS["image_quad_and_star"]
+    kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
+    kps = [{k: np.asarray(v, dtype=float) for k, v in kw.items()} for kw in c.meta["kwargs_ps"]]
+    im = _ps_model(c, linear=False)
+    assert_close(im.image(kl, ks, kll, kps), c.out["image"], what="image", **BAR)
+    assert_close(im.image(kl, ks, kll, kps, unconvolved=True), c.out["image_unconvolved"], what="unconvolved", **BAR)
+    assert_close(im.image(kl, ks, kll, kps, point_source_add=False), c.out["image_no_ps"], what="no ps", **BAR)
+    assert_close(im.point_source(kps, kl), c.out["point_source"], what="point_source", **BAR)
+    assert_close(im.point_source(kps, kl, k=1), c.out["point_source_k1"], what="point_source k=1", **BAR)
+    logL = im.likelihood_data_given_model(kl, ks, kll, kps)
+    assert abs(logL - float(c.out["logL"])) <= 1e-10 * abs(float(c.out["logL"]))
+    lin = _ps_model(c, linear=True)
+    assert lin.num_param_linear(kl, ks, kll, kps) == 7
+    A = lin.linear_response_matrix(kl, ks, kll, kps)
+    assert_close(A, c.out["A"], what="response matrix", **BAR)
+    model, _, _, param = lin.image_linear_solve(kl, ks, kll, kps)
+    assert_close(param, c.out["param"], what="param", rtol=1e-8, atol_frac=1e-10)
+    assert_close(model, c.out["wls_model"], what="wls model", rtol=1e-8, atol_frac=1e-10)
+    logL_lin, param2 = lin.likelihood_data_given_model(kl, ks, kll, kps)
+    assert abs(logL_lin - float(c.out["logL_linear"])) <= 1e-9 * abs(float(c.out["logL_linear"]))
+    # the solved amplitudes land in the kwargs like in the reference (update_linear_kwargs)
+    _, ks2, kll2, kps2 = lin.update_linear_kwargs(param2, kl, [dict(k) for k in ks], [dict(k) for k in kll],
+                                                  [dict(k) for k in kps])
+    assert np.allclose(kps2[0]["point_amp"], param2[2:6]) and np.allclose(kps2[1]["point_amp"], param2[6:7])
+    assert abs(im.likelihood_data_given_model(kl, ks2, kll2, kps2) - logL_lin) <= 1e-9 * abs(logL_lin)
+    # batch entry point: [B, P] matrix with the point-source columns
+    import torch
+
+    lin.num_point_source_images = [4, 1]
+    mat, _, _ = lin._pack(kl, ks, kll, kps, [4, 1])
+    l_b, a_b, _ = lin.logL_linear_batch(torch.as_tensor(np.repeat(mat, 3, axis=0), device="cuda"))
+    assert np.allclose(l_b.cpu().numpy(), logL_lin, rtol=1e-12) and np.allclose(a_b.cpu().numpy()[2], param2, rtol=1e-12)

@@ -200,3 +200,63 @@ def test_degenerate_system_returns_zero_amplitudes():
     im = build_oracle_image_model(c)
     _, _, _, param = im.image_linear_solve(c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"])
     assert np.all(param == 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# point sources: oracle/point_source.py + the point-source branches of oracle/imsim.py
+# ---------------------------------------------------------------------------------------------------------------
+POINTS = load("point_sources.npz")
+
+
+@pytest.mark.parametrize("name", [n for n in POINTS if n.startswith("rendering_")])
+def test_point_source_rendering(name):
+    from oracle.lenstronomy_port import PixelGrid
+    from oracle.point_source import point_source_rendering
+
+    c = POINTS[name]
+    n, ss = c.meta["numPix"], c.meta["supersampling"]
+    pg = PixelGrid(n, n, c.inp["transform_pix2angle"], float(c.inp["ra_at_xy_0"]), float(c.inp["dec_at_xy_0"]))
+    kernel = c.inp["kernel"] / np.sum(c.inp["kernel"])  # PSF(kernel_point_source_normalisation=True)
+    tol = dict(rtol=1e-11, atol_frac=1e-13)
+    got = point_source_rendering(pg, kernel, ss, c.inp["ra"], c.inp["dec"], c.inp["amp"])
+    assert_close(got, c.out["image"], what=name, **tol)
+    gotu = point_source_rendering(pg, kernel, ss, c.inp["ra"], c.inp["dec"], c.inp["amp"], unconvolved=True)
+    assert_close(gotu, c.out["image_unconvolved"], what=name + " unconvolved", **tol)
+    # flux conservation for stamps fully inside the frame: the first image carries amp[0] in total
+    one = point_source_rendering(pg, kernel, ss, c.inp["ra"][:1], c.inp["dec"][:1], c.inp["amp"][:1])
+    assert abs(one.sum() - c.inp["amp"][0]) < 1e-9 * c.inp["amp"][0]
+
+
+def _oracle_ps_model(c):
+    kd = dict(image_data=c.inp["image_data"], transform_pix2angle=c.inp["transform_pix2angle"],
+              ra_at_xy_0=float(c.inp["ra_at_xy_0"]), dec_at_xy_0=float(c.inp["dec_at_xy_0"]),
+              background_rms=float(c.inp["background_rms"]), exposure_time=float(c.inp["exposure_time"]))
+    return imsim.ImageModel(imsim.ImageData(**kd), _psf(c.meta["kwargs_psf"], c.inp), c.meta["lens_model_list"],
+                            c.meta["source_model_list"], c.meta["lens_light_model_list"], c.meta["kwargs_numerics"],
+                            point_source_type_list=c.meta["point_source_type_list"])
+
+
+def _ps_kwargs(c):
+    return [{k: np.asarray(v, dtype=float) for k, v in kw.items()} for kw in c.meta["kwargs_ps"]]
+
+
+def test_image_model_with_point_sources():
+    c = POINTS["image_quad_and_star"]
+    im = _oracle_ps_model(c)
+    kl, ks, kll, kps = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"], _ps_kwargs(c)
+    tol = dict(rtol=1e-11, atol_frac=1e-13)
+    assert_close(im.image(kl, ks, kll, kwargs_ps=kps), c.out["image"], what="image", **tol)
+    assert_close(im.image(kl, ks, kll, kwargs_ps=kps, unconvolved=True), c.out["image_unconvolved"], what="unconv", **tol)
+    assert_close(im.image(kl, ks, kll, kwargs_ps=kps, point_source_add=False), c.out["image_no_ps"], what="no ps", **tol)
+    assert_close(im.point_source(kps), c.out["point_source"], what="point_source", **tol)
+    assert_close(im.point_source(kps, k=1), c.out["point_source_k1"], what="point_source k=1", **tol)
+    logL = im.likelihood_data_given_model(kl, ks, kll, kwargs_ps=kps)
+    assert abs(logL - float(c.out["logL"])) <= 1e-11 * abs(float(c.out["logL"]))
+    A = im.linear_response_matrix(kl, ks, kll, kwargs_ps=kps)
+    assert A.shape == c.out["A"].shape == (7, 1600)  # source, lens light, 4 + 1 point-source images
+    assert_close(A, c.out["A"], what="A", **tol)
+    model, _, _, param = im.image_linear_solve(kl, ks, kll, kwargs_ps=kps)
+    assert_close(param, c.out["param"], what="param", rtol=1e-9, atol_frac=1e-11)
+    assert_close(model, c.out["wls_model"], what="wls model", rtol=1e-9, atol_frac=1e-11)
+    logL_lin, _ = im.likelihood_data_given_model_linear(kl, ks, kll, kwargs_ps=kps)
+    assert abs(logL_lin - float(c.out["logL_linear"])) <= 1e-9 * abs(float(c.out["logL_linear"]))

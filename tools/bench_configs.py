@@ -138,6 +138,24 @@ def c5():
                 band_images_per_s=4 * B / ms * 1e3, sets_per_s=B / ms * 1e3)
 
 
+def mixed():
+    """Headline workload with the default prior box e1, e2 ~ U(-0.5, 0.5) (SURVEY.md 8(d) "mixed-nmax" run): the
+    series length differs from set to set (nmax 10 ... 50), so CTAs of one launch no longer cost the same."""
+    from bench import build_headline
+
+    B = 16384
+    cfg = build_headline(n_sets=B, seed=1234)
+    rng = np.random.default_rng(7)
+    p = cfg["params"].clone()
+    p[:, 2] = torch.as_tensor(rng.uniform(-0.5, 0.5, B), device="cuda")
+    p[:, 3] = torch.as_tensor(rng.uniform(-0.5, 0.5, B), device="cuda")
+    emod = torch.sqrt(p[:, 2] ** 2 + p[:, 3] ** 2).cpu().numpy()
+    nmax = np.select([emod < 0.12, emod < 0.4, emod < 0.6, emod < 0.73], [10, 20, 35, 50], 100)
+    ms = timed(lambda: cfg["model"].logL_linear_batch(p))
+    return dict(config="headline with e1,e2 ~ U(-0.5,0.5) (mixed nmax), 16384 sets", ms=ms, images_per_s=B / ms * 1e3,
+                nmax_histogram={int(k): int((nmax == k).sum()) for k in np.unique(nmax)})
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c3", "c4", "c5"]
     t0 = time.time()
