@@ -36,6 +36,7 @@ class Param(object):
     def __init__(self, kwargs_model, kwargs_fixed_lens=None, kwargs_fixed_source=None, kwargs_fixed_lens_light=None,
                  kwargs_lower_lens=None, kwargs_lower_source=None, kwargs_lower_lens_light=None,
                  kwargs_upper_lens=None, kwargs_upper_source=None, kwargs_upper_lens_light=None, linear_solver=True,
+                 kwargs_fixed_ps=None, kwargs_lower_ps=None, kwargs_upper_ps=None, num_point_source_list=None,
                  **unsupported):
         for k, v in unsupported.items():
             if v:
@@ -73,13 +74,42 @@ class Param(object):
                     if n not in self._fixed[comp][i]:
                         self._index[(comp, i, n)] = len(self._flat_names)
                         self._flat_names.append("%s_%s%d" % (n, label, i))
+        # point sources after the light components (lenstronomy Param order); per model ra_image[0..n),
+        # dec_image[0..n), point_amp[0..n) (PointSourceParam.set_params).  The image count per model is static.
+        self._ps_models = list(kwargs_model.get("point_source_model_list", []))
+        for m in self._ps_models:
+            if m not in ("UNLENSED", "LENSED_POSITION"):
+                raise ValueError("point-source model %s is outside the scope of jaxtronomy_b200" % m)
+        if self._ps_models and (num_point_source_list is None or len(num_point_source_list) != len(self._ps_models)):
+            raise ValueError("num_point_source_list (images per point-source model) is required")
+        self._ps_num = [int(n) for n in (num_point_source_list or [])]
+        fill_ps = lambda lst: [dict(d) for d in lst] if lst is not None else [{} for _ in self._ps_models]  # noqa: E731
+        self._ps_fixed, self._ps_lower, self._ps_upper = fill_ps(kwargs_fixed_ps), fill_ps(kwargs_lower_ps), \
+            fill_ps(kwargs_upper_ps)
+        if linear_solver:
+            for d, n in zip(self._ps_fixed, self._ps_num):
+                d.setdefault("point_amp", np.ones(n))
+        for k, n in enumerate(self._ps_num):
+            for name in ("ra_image", "dec_image", "point_amp"):
+                if name not in self._ps_fixed[k]:
+                    for j in range(n):
+                        self._index[("point_source", k, name, j)] = len(self._flat_names)
+                        self._flat_names.append("%s_%d_point_source%d" % (name, j, k))
 
     def num_param(self):
         return len(self._flat_names), list(self._flat_names)
 
     def param_limits(self):
         lower, upper = np.empty(len(self._flat_names)), np.empty(len(self._flat_names))
-        for (comp, i, n), j in self._index.items():
+        ps_lo, ps_hi = {"ra_image": -100, "dec_image": -100, "point_amp": 0}, \
+            {"ra_image": 100, "dec_image": 100, "point_amp": 100}
+        for key, j in self._index.items():
+            if key[0] == "point_source":
+                _, k, n, e = key
+                lo, hi = self._ps_lower[k].get(n, ps_lo[n]), self._ps_upper[k].get(n, ps_hi[n])
+                lower[j], upper[j] = np.broadcast_to(lo, (self._ps_num[k],))[e], np.broadcast_to(hi, (self._ps_num[k],))[e]
+                continue
+            comp, i, n = key
             lower[j] = self._lower[comp][i].get(n, _DEFAULT_LOWER[n])
             upper[j] = self._upper[comp][i].get(n, _DEFAULT_UPPER[n])
         return lower, upper
@@ -99,14 +129,29 @@ class Param(object):
                         kw[n] = args[..., self._index[(comp, i, n)]]
                 lst.append(kw)
             out[key] = lst
-        out.update(kwargs_ps=[], kwargs_special={}, kwargs_extinction=[], kwargs_tracer_source=[])
+        kwargs_ps = []
+        for k, n in enumerate(self._ps_num):
+            kw = {}
+            for name in ("ra_image", "dec_image", "point_amp"):
+                if name in self._ps_fixed[k]:
+                    kw[name] = np.broadcast_to(np.asarray(self._ps_fixed[k][name], dtype=float), (n,)).copy()
+                else:
+                    cols = [self._index[("point_source", k, name, j)] for j in range(n)]
+                    kw[name] = args[..., cols]
+            kwargs_ps.append(kw)
+        out.update(kwargs_ps=kwargs_ps, kwargs_special={}, kwargs_extinction=[], kwargs_tracer_source=[])
         return out
 
-    def kwargs2args(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None, **unused):
+    def kwargs2args(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None, kwargs_ps=None, **unused):
         given = {"lens": kwargs_lens or [], "source": kwargs_source or [], "lens_light": kwargs_lens_light or []}
         args = np.empty(len(self._flat_names))
-        for (comp, i, n), j in self._index.items():
-            args[j] = given[comp][i][n]
+        for key, j in self._index.items():
+            if key[0] == "point_source":
+                _, k, n, e = key
+                args[j] = np.atleast_1d(kwargs_ps[k][n])[e]
+            else:
+                comp, i, n = key
+                args[j] = given[comp][i][n]
         return args
 
     def column_source_fn(self, index_lists=None):
@@ -114,7 +159,13 @@ class Param(object):
         ``index_lists``: {"lens": [...], "source": [...], "lens_light": [...]} local -> global profile index of a
         band's sub-model (SingleBandMultiModel.select_kwargs); None = identity."""
 
-        def fn(component, i_local, names):
+        def fn(component, i_local, names, element=None):
+            if component == "point_source":  # one parameter (`names`) of image `element` of model i_local
+                fixed = self._ps_fixed[i_local]
+                if names in fixed:
+                    return ("cst", float(np.broadcast_to(np.asarray(fixed[names], dtype=float),
+                                                         (self._ps_num[i_local],))[element]))
+                return ("col", self._index[("point_source", i_local, names, element)])
             idx = (index_lists or {}).get(component)
             i = i_local if idx is None else idx[i_local]
             src = []
@@ -125,4 +176,5 @@ class Param(object):
                     src.append(("col", self._index[(component, i, n)]))
             return src
 
+        fn.num_point_images = list(self._ps_num)
         return fn

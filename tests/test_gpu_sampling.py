@@ -149,3 +149,32 @@ def test_device_pso_improves_the_fit_without_host_round_trips():
     assert np.all(np.diff(hist) >= 0) and hist[-1] > hist[0]
     assert hist[-1] >= like.logL(x0) - 50.0
     assert abs(like.logL(best) - hist[-1]) <= 1e-9 * abs(hist[-1])
+
+
+def test_likelihood_module_with_point_sources():
+    """Sampler boundary with point sources: the image positions are columns of the `positions` matrix, the point
+    amplitudes are solved linearly (one per image) together with the extended light."""
+    from jaxtronomy_b200.Sampling.likelihood import LikelihoodModule
+    from jaxtronomy_b200.Sampling.parameters import Param
+    from tests.test_gpu_parity import POINTS, _ps_model
+
+    c = POINTS["image_quad_and_star"]
+    lin = _ps_model(c, linear=True)
+    km = dict(lens_model_list=c.meta["lens_model_list"], source_light_model_list=c.meta["source_model_list"],
+              lens_light_model_list=c.meta["lens_light_model_list"],
+              point_source_model_list=c.meta["point_source_type_list"])
+    kps = [{k: np.asarray(v, dtype=float) for k, v in kw.items()} for kw in c.meta["kwargs_ps"]]
+    param = Param(km, kwargs_fixed_lens=[{}, {"ra_0": 0.0, "dec_0": 0.0}], num_point_source_list=[4, 1],
+                  kwargs_fixed_ps=[{}, {"ra_image": kps[1]["ra_image"], "dec_image": kps[1]["dec_image"]}])
+    like = LikelihoodModule(lin, param)
+    kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
+    x0 = param.kwargs2args(kl, ks, kll, kwargs_ps=kps)
+    assert abs(like.logL(x0) - float(c.out["logL_linear"])) <= 1e-9 * abs(float(c.out["logL_linear"]))
+    rng = np.random.default_rng(3)
+    pos = x0[None, :] + rng.normal(0, 0.003, (9, x0.size))
+    logl = like.logL_batch(pos)
+    for b in (0, 8):
+        kw = param.args2kwargs(pos[b])
+        want, _ = lin.likelihood_data_given_model(kw["kwargs_lens"], kw["kwargs_source"], kw["kwargs_lens_light"],
+                                                  kw["kwargs_ps"])
+        assert abs(logl[b] - want) <= 1e-11 * abs(want), (b, logl[b], want)
