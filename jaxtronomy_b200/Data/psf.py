@@ -46,19 +46,36 @@ class PSF(object):
                              "jaxtronomy_b200")
         self.psf_variance_map_bool = False
 
+    def _gaussian_kernel(self, supersampling_factor):
+        """Pixelised kernel of a GAUSSIAN PSF (point sources only; the extended light uses GaussianConvolution):
+        lenstronomy.Data.psf.PSF.kernel_point_source / kernel_point_source_supersampled -- a Gaussian of the given
+        fwhm sampled on round(truncation * fwhm / pixel_size * factor) (made odd) points of pixel_size / factor,
+        normalised.  lenstronomy is not under /root/reference: restated from its published behaviour, parity
+        unpinned."""
+        from jaxtronomy_b200.Util import kernel_util
+
+        if self._pixel_size is None:
+            raise ValueError("set_pixel_size() must be called before the kernel of a GAUSSIAN PSF is requested")
+        n = int(round(self._truncation * self._fwhm / self._pixel_size * supersampling_factor))
+        if n % 2 == 0:
+            n += 1
+        k1 = kernel_util.kernel_gaussian_1d(n, self._sigma_gaussian / (self._pixel_size / supersampling_factor))
+        return np.outer(k1, k1)
+
     @property
     def kernel_point_source(self):
         if self.psf_type == "GAUSSIAN":
-            raise ValueError("the pixelised kernel of a GAUSSIAN PSF is only needed for point sources "
-                             "(outside the scope of jaxtronomy_b200)")
+            return self._gaussian_kernel(1)
         return self._kernel_point_source
 
-    def kernel_point_source_supersampled(self, supersampling_factor):
-        """Kernel sampled at `supersampling_factor` points per pixel.  Only available when the PSF was given
-        supersampled at that factor: lenstronomy otherwise interpolates the pixel kernel iteratively
+    def kernel_point_source_supersampled(self, supersampling_factor, updata_cache=True):
+        """Kernel sampled at `supersampling_factor` points per pixel.  For a PIXEL PSF only available when the PSF
+        was given supersampled at that factor: lenstronomy otherwise interpolates the pixel kernel iteratively
         (kernel_util.subgrid_kernel), which is not reproduced here."""
-        if self.psf_type != "PIXEL":
-            raise ValueError("supersampled kernels are defined for PIXEL PSFs")
+        if self.psf_type == "GAUSSIAN":
+            return self._gaussian_kernel(supersampling_factor)
+        if self.psf_type == "NONE":
+            return self._kernel_point_source
         if supersampling_factor == 1:
             return self._kernel_point_source
         if getattr(self, "_kernel_point_source_supersampled", None) is not None and \

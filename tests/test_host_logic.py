@@ -257,3 +257,19 @@ def test_oracle_pso_step_bookkeeping():
     assert np.array_equal(pf, [-10.0, -1.0, -10.0, -1.0, -9.0, -10.0])
     assert np.array_equal(pb[1], before[1]) and np.array_equal(pb[0], before[0] + 100)
     assert np.array_equal(vel, np.zeros((B, P))) and np.array_equal(pos, before)  # all draws 0: w v = 0, no pull
+
+
+def test_gaussian_psf_point_source_kernel():
+    """Pixelised kernel of a GAUSSIAN PSF for point sources: odd size from truncation * fwhm / pixel size, unit sum,
+    second moment = sigma^2 (in pixels) up to the truncation, supersampled version consistent."""
+    from jaxtronomy_b200.Data.psf import PSF
+    from jaxtronomy_b200.Util.util import fwhm2sigma
+
+    psf = PSF(psf_type="GAUSSIAN", fwhm=0.3, truncation=6, pixel_size=0.05)
+    k = psf.kernel_point_source
+    assert k.shape == (37, 37) and abs(k.sum() - 1) < 1e-14 and np.allclose(k, k.T) and np.allclose(k, k[::-1, ::-1])
+    a = np.arange(37) - 18
+    var = (k.sum(0) * a**2).sum()
+    assert abs(var - (fwhm2sigma(0.3) / 0.05) ** 2) < 2e-3 * var
+    k3 = psf.kernel_point_source_supersampled(3)
+    assert k3.shape[0] % 2 == 1 and abs(k3.sum() - 1) < 1e-14 and abs(k3.shape[0] - 3 * 36) <= 1

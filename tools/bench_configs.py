@@ -138,6 +138,57 @@ def c5():
                 band_images_per_s=4 * B / ms * 1e3, sets_per_s=B / ms * 1e3)
 
 
+def c1():
+    """The Einstein-ring notebook's PSO (notebooks/modeling_a_simple_Einstein_ring.ipynb: 256 particles x 200
+    iterations, 100x100 px, EPL+SHEAR, SERSIC_ELLIPSE source + lens light, 4-image point source, Gaussian PSF, ss 1,
+    linear solver; published: lenstronomy 6 min 43 s, JAXtronomy on a CPU node 12 s) with the GPU-resident swarm."""
+    from jaxtronomy_b200.PointSource.point_source import PointSource
+    from jaxtronomy_b200.Sampling.sampler import DeviceParticleSwarmOptimizer
+    from jaxtronomy_b200.Util import simulation_util as sim_util
+
+    rng = np.random.default_rng(5)
+    kd = sim_util.data_configure_simple(100, 0.05, 100.0, 0.5, inverse=False)
+    km = dict(lens_model_list=["EPL", "SHEAR"], source_light_model_list=["SERSIC_ELLIPSE"],
+              lens_light_model_list=["SERSIC_ELLIPSE"], point_source_model_list=["LENSED_POSITION"])
+    lens = LensModel(km["lens_model_list"])
+    psf = PSF(psf_type="GAUSSIAN", fwhm=0.1, truncation=5)
+    kl = [dict(theta_E=1.0, gamma=2.0, e1=0.1, e2=-0.05, center_x=0.0, center_y=0.0),
+          dict(gamma1=0.03, gamma2=-0.01, ra_0=0, dec_0=0)]
+    ks = [dict(amp=16.0, R_sersic=0.1, n_sersic=1.0, e1=0.1, e2=0.1, center_x=0.1, center_y=0.05)]
+    kll = [dict(amp=16.0, R_sersic=0.6, n_sersic=2.0, e1=-0.1, e2=0.1, center_x=0.0, center_y=0.0)]
+    kps = [dict(ra_image=np.array([1.02, -0.71, 0.43, -0.52]), dec_image=np.array([0.41, -0.83, -0.98, 0.95]),
+                point_amp=np.array([100.0, 80.0, 60.0, 40.0]))]
+
+    def make(image):
+        return ImageLinearFit(ImageData(**dict(kd, image_data=image)), psf, lens, LightModel(km["source_light_model_list"]),
+                              LightModel(km["lens_light_model_list"]), point_source_class=PointSource(["LENSED_POSITION"]),
+                              kwargs_numerics=dict(supersampling_factor=1))
+
+    truth = make(np.zeros((100, 100))).image(kl, ks, kll, kps)
+    lin = make(truth + rng.normal(0, 0.5, truth.shape))
+    param = Param(km, kwargs_fixed_lens=[{}, {"ra_0": 0.0, "dec_0": 0.0}], num_point_source_list=[4])
+    like = LikelihoodModule(lin, param)
+    x0 = param.kwargs2args(kl, ks, kll, kwargs_ps=kps)
+    sig = np.full(x0.size, 0.05)
+    n_part, n_iter = 256, 200
+
+    def run():
+        pso = DeviceParticleSwarmOptimizer(like, x0 - sig, x0 + sig, particle_count=n_part, seed=1)
+        best, hist = pso.optimize(max_iter=n_iter)
+        return hist
+
+    run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    hist = run()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return dict(config="C1 notebook PSO: 256 particles x 200 iterations, 100x100, EPL+SHEAR, 2 SERSIC_ELLIPSE, "
+                       "4-image point source, Gaussian PSF, linear solver (n_lin = 6), GPU-resident swarm",
+                wall_s=dt, likelihoods_per_s=n_part * n_iter / dt, logL_first=hist[0], logL_last=hist[-1],
+                logL_truth=like.logL(x0), published="lenstronomy 403 s, JAXtronomy (CPU node) 12 s")
+
+
 def mixed():
     """Headline workload with the default prior box e1, e2 ~ U(-0.5, 0.5) (SURVEY.md 8(d) "mixed-nmax" run): the
     series length differs from set to set (nmax 10 ... 50), so CTAs of one launch no longer cost the same."""
