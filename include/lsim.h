@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LSIM_ABI_VERSION 5
+#define LSIM_ABI_VERSION 6
 #define LSIM_MAX_PARAMS 12 /* largest param_names list on the path: EPL_MULTIPOLE_M1M3M4 */
 #define LSIM_MAX_SLOTS 8   /* output / linear-basis images per parameter set */
 
@@ -112,7 +112,7 @@ typedef struct lsim_point_desc {
   int32_t slot;                     /* output image (0..n_slots-1), -1: skipped */
   double cst_ra, cst_dec, cst_amp;
   int32_t use_amp;                  /* 0: amplitude 1 (one linear basis image per point-source image) */
-  int32_t pad;
+  int32_t error_map;                /* 1: contributes to the PSF error map (psf_error_map_bool_list) */
 } lsim_point_desc;
 
 /* PSF convolution on the pixel grid (ImSim/Numerics/convolution.py) */
@@ -192,6 +192,14 @@ typedef struct lsim_plan_desc {
   double ps_x_at_radec_0, ps_y_at_radec_0;
   double ps_Ma2pix[4];           /* row-major 2x2 */
   double ps_scale;               /* flux scaling of the point-source image (image_model.py:429) */
+  /* PSF error map (ImageModel._error_map_psf, image_model.py:615-648; PointSourceRendering.psf_variance_map,
+   * point_source_rendering.py:79-111; kernel_util.estimate_amp, Util/kernel_util.py:7-47): for every point-source
+   * image flagged error_map, sigma^2 += psf_variance_map * amp_est^2 painted at its pixel position, amp_est =
+   * max(sum of the 5x5 data pixels around it, 0) / ps_mean_kernel (0 within 2 pixels of the frame edge).  The map is
+   * added to C_D in the WLS weights and, as |.|, to C_D(model) in chi^2.  NULL: no error map. */
+  const double* ps_variance_map; /* host [Kv*Kv], pixel resolution */
+  int32_t ps_variance_size;      /* Kv, odd */
+  double ps_mean_kernel;         /* sum of the central 5x5 of the pixel-resolution PSF kernel */
 } lsim_plan_desc;
 
 typedef struct lsim_plan lsim_plan;
@@ -262,6 +270,10 @@ int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear
 int lsim_pso_step(double* position, double* velocity, double* pbest_pos, double* pbest_fit, double* gbest_pos,
                   double* gbest_fit, const double* fitness, const double* rnd, int64_t B, int32_t P, double c1,
                   double c2, void* stream);
+
+/* ImageModel._error_map_psf (image_model.py:615-648): the PSF error map (sigma^2) of each parameter set.
+ *   error_map  device [B, ny, nx]; zeros when the plan has no ps_variance_map */
+int lsim_psf_error_map(const lsim_plan* plan, const double* params, int64_t B, double* error_map, void* stream);
 
 /* introspection */
 int lsim_abi_version(void);

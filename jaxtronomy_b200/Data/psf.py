@@ -41,10 +41,17 @@ class PSF(object):
             self._kernel_point_source = k
         else:
             raise ValueError("psf_type %s not supported!" % psf_type)
+        # variance of the PSF model per kernel pixel, relative to a point source of amplitude 1 (lenstronomy
+        # Data/psf.py: same shape as kernel_point_source); feeds ImageModel._error_map_psf
+        self.psf_variance_map_bool = psf_variance_map is not None
+        self._psf_variance_map = None
         if psf_variance_map is not None:
-            raise ValueError("psf_variance_map is only used with point sources, which are outside the scope of "
-                             "jaxtronomy_b200")
-        self.psf_variance_map_bool = False
+            if psf_type != "PIXEL":
+                raise ValueError("psf_variance_map needs a PIXEL PSF")
+            vm = np.array(psf_variance_map, dtype=float)
+            if vm.shape != self._kernel_point_source.shape:
+                raise ValueError("psf_variance_map must have the shape of the pixel-resolution kernel_point_source")
+            self._psf_variance_map = vm
 
     def _gaussian_kernel(self, supersampling_factor):
         """Pixelised kernel of a GAUSSIAN PSF (point sources only; the extended light uses GaussianConvolution):
@@ -85,6 +92,12 @@ class PSF(object):
             "supersampling_convolution=True needs the PSF at the supersampled resolution: pass "
             "PSF(psf_type='PIXEL', kernel_point_source=<supersampled kernel>, point_source_supersampling_factor=%d)"
             % supersampling_factor)
+
+    @property
+    def psf_variance_map(self):
+        if self._psf_variance_map is None:
+            return np.zeros_like(self.kernel_point_source)
+        return self._psf_variance_map
 
     @property
     def fwhm(self):

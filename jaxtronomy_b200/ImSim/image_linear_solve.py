@@ -91,7 +91,7 @@ class ImageLinearFit(ImageModel):
         cov = None
         if inv_bool:
             cov = self._finish(self._cov_param(mat, counts), batched, want_torch)
-        model_error = np.zeros(self.Data.num_pixel_axes)
+        model_error = self._error_map_model(kwargs_lens, kwargs_ps, kwargs_special)
         return (self._finish(model, batched, want_torch), model_error, cov, self._finish(amps, batched, want_torch))
 
     def _cov_param(self, mat, num_images=None):
@@ -101,8 +101,13 @@ class ImageLinearFit(ImageModel):
 
         images = torch.nan_to_num(self.response_batch(mat, num_images=num_images))
         A = self.image2array_masked(images)  # [B, n, N_d]
-        w = torch.as_tensor(1.0 / self.image2array_masked(self.Data.C_D), device=A.device)
-        M = torch.einsum("bin,n,bjn->bij", A, w, A)
+        cd = torch.as_tensor(self.image2array_masked(self.Data.C_D), device=A.device)
+        if self._psf_error_map and sum(num_images or self._num_point_images) > 0:  # C_D + model error
+            err = self._split_plan(num_images=num_images).psf_error_map(mat)
+            w = 1.0 / (cd[None, :] + self.image2array_masked(err))
+        else:
+            w = (1.0 / cd)[None, :].expand(A.shape[0], -1)
+        M = torch.einsum("bin,bn,bjn->bij", A, w, A)
         stable = torch.linalg.cond(M) < 5 / np.finfo(float).eps
         Minv = torch.linalg.pinv(M)
         return torch.where(stable[:, None, None], torch.nan_to_num(Minv, nan=0.0, posinf=0.0, neginf=0.0),

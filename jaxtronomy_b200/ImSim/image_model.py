@@ -41,8 +41,10 @@ class ImageModel(object):
             point_source_class = PointSource(point_source_type_list=[])
         self.PointSource = point_source_class
         self._n_ps_models = len(self.PointSource.point_source_type_list)
-        if psf_error_map_bool_list is not None and any(psf_error_map_bool_list):
-            raise ValueError("the PSF error map is outside the scope of jaxtronomy_b200 (SURVEY.md 8(f)-3)")
+        if psf_error_map_bool_list is None:
+            psf_error_map_bool_list = [True] * self._n_ps_models
+        self._psf_error_map_bool_list = [bool(b) for b in psf_error_map_bool_list]
+        self._psf_error_map = bool(getattr(self.PSF, "psf_variance_map_bool", False))  # image_model.py:127-132
         # images per point-source model: fixes the column layout of the batch entry points; the kwargs entry points
         # read it from the lengths of ra_image
         self._num_point_images = [0] * self._n_ps_models
@@ -130,8 +132,13 @@ class ImageModel(object):
         else:
             kernel = self.PSF.kernel_point_source_supersampled(ss)
         x0, y0 = self.Data.map_coord2pix(0.0, 0.0)
-        return dict(kernel=kernel, supersampling=ss, x_at_radec_0=x0, y_at_radec_0=y0,
-                    Ma2pix=self.Data.transform_angle2pix, scale=self._flux_scaling)
+        out = dict(kernel=kernel, supersampling=ss, x_at_radec_0=x0, y_at_radec_0=y0,
+                   Ma2pix=self.Data.transform_angle2pix, scale=self._flux_scaling)
+        if self._psf_error_map and any(self._psf_error_map_bool_list):
+            k = np.asarray(self.PSF.kernel_point_source)
+            c = int((len(k) - 0.5) / 2)  # kernel_util.estimate_amp, Util/kernel_util.py:42-44
+            out.update(variance_map=self.PSF.psf_variance_map, mean_kernel=float(np.sum(k[c - 2:c + 3, c - 2:c + 3])))
+        return out
 
     def _build_plan(self, source_slots, lens_light_slots, n_slots, use_amp, unconvolved, lensed=True,
                     source_fn=None, n_cols=None, ps=None):
@@ -147,8 +154,9 @@ class ImageModel(object):
         points = None
         if ps is not None and sum(ps["num_images"]) > 0:
             points = self._ps_dict(unconvolved)
-            points["descs"] = self.PointSource.point_descs(layout, ps["num_images"], ps["slots"], use_amp,
-                                                           k=ps.get("k"), source_fn=source_fn)
+            points["descs"] = self.PointSource.point_descs(
+                layout, ps["num_images"], ps["slots"], use_amp, k=ps.get("k"), source_fn=source_fn,
+                error_map_bool_list=self._psf_error_map_bool_list if self._psf_error_map else None)
         return _lib.Plan(layout.n_cols if n_cols is None else n_cols, lens_descs=lens_descs, light_descs=light,
                          n_slots=n_slots, points=points,
                          grid=self.ImageNumerics.grid_dict(), psf=self.ImageNumerics.psf_dict(unconvolved),
@@ -346,10 +354,24 @@ class ImageModel(object):
     def data_response(self):
         return self.image2array_masked(self.Data.data)
 
+    def _error_map_psf(self, kwargs_lens, kwargs_ps, kwargs_special=None):
+        """sigma^2 expected from inaccuracies of the PSF model at the point-source positions
+        (image_model.py:615-648); zeros without a psf_variance_map."""
+        if not (self._psf_error_map and self._n_ps_models and kwargs_ps):
+            return np.zeros(self.Data.num_pixel_axes)
+        counts = self._ps_counts(kwargs_ps)
+        mat, B, batched = self._pack(self._dummy_lens(), self._dummy_source(), self._dummy_lens_light(), kwargs_ps,
+                                     counts)
+        plan = self._joint_plan([True] * self.SourceModel._num_func, [True] * self.LensLightModel._num_func,
+                                num_images=counts)
+        return self._finish(plan.psf_error_map(mat), batched, False)
+
+    def _error_map_model(self, kwargs_lens, kwargs_ps, kwargs_special=None):
+        return self._error_map_psf(kwargs_lens, kwargs_ps, kwargs_special)
+
     def error_response(self, kwargs_lens, kwargs_ps, kwargs_special):
-        """C_D of the data on the unmasked pixels (+ model error, zero without point sources),
-        image_model.py:576-595."""
-        model_error = np.zeros(self.Data.num_pixel_axes)
+        """C_D of the data on the unmasked pixels + model error (the PSF error map), image_model.py:576-595."""
+        model_error = self._error_map_model(kwargs_lens, kwargs_ps, kwargs_special)
         return self.image2array_masked(self.Data.C_D + model_error), model_error
 
     def update_psf(self, psf_class):

@@ -134,7 +134,7 @@ class PointSource(object):
         return bool(all(np.all(np.asarray(kw["point_amp"]) >= 0) for kw in kwargs_ps if "point_amp" in kw))
 
     # -- kernel descriptors --------------------------------------------------------------------------------------
-    def point_descs(self, layout, num_images, slots, use_amp, k=None, source_fn=None):
+    def point_descs(self, layout, num_images, slots, use_amp, k=None, source_fn=None, error_map_bool_list=None):
         """lsim_point_desc list for a plan.
 
         :param layout: _model.ColumnLayout; 3 n columns are registered per model: ra_image[0..n), dec_image[0..n),
@@ -160,6 +160,8 @@ class PointSource(object):
                 include = (k is None or k == i) and self._flux_from_point_source_list[i]
                 d.slot = int(slots[flat]) if include else -1
                 d.use_amp = 1 if use_amp else 0
+                # ImageModel._error_map_psf loops over ALL models with a True flag (image_model.py:632-647)
+                d.error_map = 1 if (error_map_bool_list is not None and error_map_bool_list[i]) else 0
                 descs.append(d)
                 flat += 1
         return descs

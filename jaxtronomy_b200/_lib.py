@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("LSIM_LIB") or os.path.join(_HERE, "csrc", "liblsim.so
 
 MAX_PARAMS = 12
 MAX_SLOTS = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 PRECISION_F64, PRECISION_F32 = 0, 1
 
 # enum mirrors (include/lsim.h)
@@ -48,7 +48,7 @@ _dp = C.POINTER(C.c_double)
 class PointDesc(C.Structure):
     _fields_ = [("col_ra", C.c_int32), ("col_dec", C.c_int32), ("col_amp", C.c_int32), ("slot", C.c_int32),
                 ("cst_ra", C.c_double), ("cst_dec", C.c_double), ("cst_amp", C.c_double), ("use_amp", C.c_int32),
-                ("pad", C.c_int32)]
+                ("error_map", C.c_int32)]
 
 
 class PlanDesc(C.Structure):
@@ -67,6 +67,7 @@ class PlanDesc(C.Structure):
         ("n_points", C.c_int32), ("points", C.POINTER(PointDesc)), ("ps_kernel_size", C.c_int32),
         ("ps_supersampling", C.c_int32), ("ps_kernel", _dp), ("ps_x_at_radec_0", C.c_double),
         ("ps_y_at_radec_0", C.c_double), ("ps_Ma2pix", C.c_double * 4), ("ps_scale", C.c_double),
+        ("ps_variance_map", _dp), ("ps_variance_size", C.c_int32), ("ps_mean_kernel", C.c_double),
     ]
 
 
@@ -80,7 +81,7 @@ _lib = None
 SYMBOLS = [
     "lsim_plan_create", "lsim_plan_destroy", "lsim_ray_shoot", "lsim_surface_brightness", "lsim_workspace_bytes",
     "lsim_image", "lsim_resize_convolve", "lsim_logl", "lsim_abi_version", "lsim_strerror", "lsim_last_cuda_error", "lsim_launch_count",
-    "lsim_measure_fp64_peak", "lsim_timing_enable", "lsim_timing_read", "lsim_pso_step",
+    "lsim_measure_fp64_peak", "lsim_timing_enable", "lsim_timing_read", "lsim_pso_step", "lsim_psf_error_map",
 ]
 
 
@@ -118,6 +119,8 @@ def load():
     lib.lsim_launch_count.restype = i64
     lib.lsim_measure_fp64_peak.argtypes = [i64, C.POINTER(C.c_double), vp]
     lib.lsim_measure_fp64_peak.restype = i32
+    lib.lsim_psf_error_map.argtypes = [vp, vp, i64, vp, vp]
+    lib.lsim_psf_error_map.restype = i32
     lib.lsim_pso_step.argtypes = [vp] * 8 + [i64, i32, C.c_double, C.c_double, vp]
     lib.lsim_pso_step.restype = i32
     lib.lsim_timing_enable.argtypes = [i32]
@@ -260,6 +263,11 @@ class Plan:
             for k in range(4):
                 d.ps_Ma2pix[k] = float(m[k])
             d.ps_scale = float(points.get("scale", 1.0))
+            if points.get("variance_map") is not None:
+                vm = _f64(points["variance_map"])
+                keep.append(vm)
+                d.ps_variance_map, d.ps_variance_size = _ptr(vm), vm.shape[0]
+                d.ps_mean_kernel = float(points["mean_kernel"])
         self.has_data = data is not None
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -381,6 +389,20 @@ class Plan:
                                       model.data_ptr() if model is not None else None, ws.data_ptr(), ws.numel() * 8,
                                       self._stream()))
         return logl, amps, model
+
+
+def _plan_psf_error_map(self, params):
+    """[B, P] -> PSF error map sigma^2 [B, ny, nx] (lsim_psf_error_map)."""
+    torch = _torch()
+    p = self._params(params)
+    B = p.shape[0]
+    out = torch.empty((B, self.ny, self.nx), dtype=torch.float64, device=self.device)
+    with torch.cuda.device(self.device):
+        check(self._lib.lsim_psf_error_map(self._handle, p.data_ptr(), B, out.data_ptr(), self._stream()))
+    return out
+
+
+Plan.psf_error_map = _plan_psf_error_map
 
 
 def pso_step(position, velocity, pbest_pos, pbest_fit, gbest_pos, gbest_fit, fitness, rnd, c1=1.193, c2=1.193):

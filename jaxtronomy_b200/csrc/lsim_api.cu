@@ -258,6 +258,8 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
       return LSIM_E_INVALID;
     if (d->nx != d->ny) return LSIM_E_UNSUPPORTED;  // the reference's rendering assumes a square frame
     if (d->eval_mask) return LSIM_E_UNSUPPORTED;    // sub-frames: the host side cuts the frame, not a pixel list
+    if (d->ps_variance_map && (d->ps_variance_size < 1 || d->ps_variance_size % 2 == 0 || !(d->ps_mean_kernel > 0)))
+      return LSIM_E_INVALID;
     for (int i = 0; i < d->n_points; ++i) {
       const lsim_point_desc& q = d->points[i];
       if (q.slot >= d->n_slots || q.col_ra >= d->n_param_cols || q.col_dec >= d->n_param_cols ||
@@ -344,6 +346,15 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
       D.ps_y0 = d->ps_y_at_radec_0;
       for (int k = 0; k < 4; ++k) D.ps_M[k] = d->ps_Ma2pix[k];
       D.ps_scale = d->ps_scale;
+      if (d->ps_variance_map && has_data) {
+        bool any = false;
+        for (int i = 0; i < d->n_points; ++i) any = any || d->points[i].error_map;
+        if (any) {
+          TRY(p->upload(d->ps_variance_map, (size_t)d->ps_variance_size * d->ps_variance_size, &D.ps_var));
+          D.ps_var_K = d->ps_variance_size;
+          D.ps_mean_kernel = d->ps_mean_kernel;
+        }
+      }
     }
     if (D.K > 0 && !d->kernel_separable)
       TRY(fft_conv_create(d->nx, d->ny, d->kernel_size, d->kernel, d->conv_mode, &p->fft_lo));
@@ -434,6 +445,12 @@ size_t prep_bytes(const lsim_plan* plan) {
   return prepared_bytes(plan->dev.n_lens, plan->dev.n_light, plan->n_series);
 }
 
+// per-set scratch in front of the image buffers: prepared constants [+ PSF error map]
+size_t prefix_bytes(const lsim_plan* plan) {
+  const PlanDev& D = plan->dev;
+  return prep_bytes(plan) + (D.ps_var ? (size_t)D.nx * D.ny * sizeof(double) : 0);
+}
+
 size_t per_set_bytes(const lsim_plan* plan, bool need_conv_out) {
   const PlanDev& D = plan->dev;
   const size_t npix = (size_t)D.nx * D.ny, nsub = npix * D.ss * D.ss;
@@ -441,7 +458,7 @@ size_t per_set_bytes(const lsim_plan* plan, bool need_conv_out) {
   size_t n = npix * D.n_slots;
   if (conv && need_conv_out) n += npix * D.n_slots;
   if (conv && D.ss_conv) n += 2 * nsub * D.n_slots + (need_conv_out ? 0 : npix * D.n_slots);
-  return n * sizeof(double) + prep_bytes(plan);
+  return n * sizeof(double) + prefix_bytes(plan);
 }
 
 int64_t chunk_sets(const lsim_plan* plan) { return (int64_t)plan->n_sm * 8; }
@@ -863,7 +880,7 @@ int run_chunk(const lsim_plan* plan, const double* params, int64_t s0, int64_t n
   const size_t npix = (size_t)D.nx * D.ny, nsub = npix * D.ss * D.ss, ns = (size_t)D.n_slots;
   // the scratch starts with the prepared-constants blocks of the chunk (none when the caller gave no scratch)
   const unsigned char* prep = reinterpret_cast<const unsigned char*>(ws);
-  if (ws) ws += (size_t)chunk * prep_bytes(plan) / sizeof(double);
+  if (ws) ws += (size_t)chunk * prefix_bytes(plan) / sizeof(double);
   int rc;
   if (D.conv_mode == LSIM_CONV_NONE) {
     rc = launch_image(plan, params, s0, n, D.image_scale, dst, nullptr, st, prep);
@@ -885,18 +902,18 @@ int run_chunk(const lsim_plan* plan, const double* params, int64_t s0, int64_t n
 }
 
 int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, int64_t n, int linear, int marg,
-                      double* logl, double* amps, double* model, cudaStream_t st) {
+                      double* logl, double* amps, double* model, const double* err, cudaStream_t st) {
   const int ns = plan->dev.n_slots;
   dim3 grid((unsigned)n);
   Timed timed(kClsLike, st);
   if (ns <= 1)
-    k_likelihood<1><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model);
+    k_likelihood<1><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else if (ns <= 2)
-    k_likelihood<2><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model);
+    k_likelihood<2><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else if (ns <= 4)
-    k_likelihood<4><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model);
+    k_likelihood<4><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else
-    k_likelihood<8><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model);
+    k_likelihood<8><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   return after_launch("k_likelihood");
 }
 
@@ -927,7 +944,7 @@ int lsim_image(const lsim_plan* plan, const double* params, int64_t B, double* i
     if (chunk > chunk_sets(plan)) chunk = chunk_sets(plan);
   } else if (workspace && prep_bytes(plan) > 0) {
     // no PSF: the images go straight to the caller's buffer; scratch (optional) only holds the prepared constants
-    const int64_t fit = (int64_t)(workspace_bytes / prep_bytes(plan));
+    const int64_t fit = (int64_t)(workspace_bytes / prefix_bytes(plan));
     if (fit < 1) workspace = nullptr;
     else if (fit < chunk) chunk = fit;
   } else {
@@ -988,13 +1005,40 @@ int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear
   const size_t img = (size_t)D.nx * D.ny * D.n_slots, sub = img * D.ss * D.ss;
   // layout: [U | Usub, Hsub (supersampled conv only) | C]; without a PSF the images land in U directly
   double* ws = static_cast<double*>(workspace);
-  double* main_ws = ws + (size_t)chunk * prep_bytes(plan) / sizeof(double);  // run_chunk skips the same prefix
+  double* main_ws = ws + (size_t)chunk * prefix_bytes(plan) / sizeof(double);  // run_chunk skips the same prefix
+  double* err = D.ps_var ? ws + (size_t)chunk * prep_bytes(plan) / sizeof(double) : nullptr;  // [chunk][npix]
   double* C = conv ? main_ws + (size_t)chunk * img + (D.ss_conv ? 2 * (size_t)chunk * sub : 0) : main_ws;
   for (int64_t s0 = 0; s0 < B; s0 += chunk) {
     const int64_t n = B - s0 < chunk ? B - s0 : chunk;
     int rc = run_chunk(plan, params, s0, n, chunk, ws, C, st);
     if (rc != LSIM_OK) return rc;
-    rc = launch_likelihood(plan, C, s0, n, linear_solve, source_marg, logl, amps, model, st);
+    if (err) {
+      Timed timed(kClsOther, st);
+      k_ps_error_map<<<(unsigned)n, kBlock, 0, st>>>(D, params, s0, err);
+      rc = after_launch("k_ps_error_map");
+      if (rc != LSIM_OK) return rc;
+    }
+    rc = launch_likelihood(plan, C, s0, n, linear_solve, source_marg, logl, amps, model, err, st);
+    if (rc != LSIM_OK) return rc;
+  }
+  return LSIM_OK;
+}
+
+int lsim_psf_error_map(const lsim_plan* plan, const double* params, int64_t B, double* error_map, void* stream) {
+  if (!plan || B < 0) return LSIM_E_INVALID;
+  if (!plan->has_image) return LSIM_E_NO_IMAGE;
+  if (B == 0) return LSIM_OK;
+  if (!error_map || (plan->dev.n_param_cols > 0 && !params)) return LSIM_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PlanDev& D = plan->dev;
+  if (!D.ps_var) {
+    LSIM_CUDA(cudaMemsetAsync(error_map, 0, (size_t)B * D.nx * D.ny * sizeof(double), st));
+    return LSIM_OK;
+  }
+  for (int64_t s0 = 0; s0 < B; s0 += 65535) {
+    const int64_t n = B - s0 < 65535 ? B - s0 : 65535;
+    k_ps_error_map<<<(unsigned)n, kBlock, 0, st>>>(D, params, s0, error_map + (size_t)s0 * D.nx * D.ny);
+    int rc = after_launch("k_ps_error_map");
     if (rc != LSIM_OK) return rc;
   }
   return LSIM_OK;

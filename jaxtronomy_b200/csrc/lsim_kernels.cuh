@@ -59,6 +59,9 @@ struct PlanDev {
   const lsim_point_desc* points;
   const double* ps_kernel;
   double ps_x0, ps_y0, ps_M[4], ps_scale;
+  const double* ps_var;  // PSF variance map [ps_var_K^2] or null
+  int32_t ps_var_K;
+  double ps_mean_kernel;
 };
 
 // ---- shared-memory staging of per-set constants -----------------------------------------------------------
@@ -594,6 +597,57 @@ k_point_sources(PlanDev P, const double* __restrict__ params, int64_t set0, doub
   }
 }
 
+// ---- k_ps_error_map: PSF error map of one parameter set (one CTA per set) -------------------------------------------
+// err[set][pixel] = sum over flagged point-source images of bilinear(psf_variance_map) * amp_est^2  (see lsim.h)
+__global__ void __launch_bounds__(kBlock)
+k_ps_error_map(PlanDev P, const double* __restrict__ params, int64_t set0, double* __restrict__ err) {
+  const int64_t bl = blockIdx.x;
+  const double* row = params + (set0 + bl) * P.n_param_cols;
+  double* img = err + bl * ((int64_t)P.nx * P.ny);
+  const int npix = P.nx * P.ny, K = P.ps_var_K, half = K / 2;
+  for (int p = threadIdx.x; p < npix; p += kBlock) img[p] = 0.0;
+  __syncthreads();
+  for (int i = 0; i < P.n_points; ++i) {
+    const lsim_point_desc& d = P.points[i];
+    if (!d.error_map) continue;
+    const double ra = d.col_ra >= 0 ? row[d.col_ra] : d.cst_ra;
+    const double dec = d.col_dec >= 0 ? row[d.col_dec] : d.cst_dec;
+    const double xp = P.ps_M[0] * ra + P.ps_M[1] * dec + P.ps_x0;
+    const double yp = P.ps_M[2] * ra + P.ps_M[3] * dec + P.ps_y0;
+    if (!(fabs(xp) < 1e9 && fabs(yp) < 1e9)) continue;
+    // kernel_util.estimate_amp: the 5 x 5 data pixels around round(pos - 0.49999), nothing near the frame edge
+    const int xi = (int)rint(xp - 0.49999), yi = (int)rint(yp - 0.49999);
+    double amp = 0.0;
+    if (xi > 2 && xi < P.nx - 2 && yi > 2 && yi < P.ny - 2) {  // (numPix_x, numPix_y = shape(data); frame is square)
+      double s = 0.0;
+      for (int a = 0; a < 5; ++a)
+        for (int b = 0; b < 5; ++b) s += P.data[(int64_t)(yi - 2 + a) * P.nx + (xi - 2 + b)];
+      amp = fmax(s, 0.0) / P.ps_mean_kernel;
+    }
+    const double a2 = amp * amp;
+    const int px_lo = max(0, (int)floor(xp - half - 1.0)), px_hi = min(P.nx - 1, (int)ceil(xp - half + K));
+    const int py_lo = max(0, (int)floor(yp - half - 1.0)), py_hi = min(P.ny - 1, (int)ceil(yp - half + K));
+    const int w = px_hi - px_lo + 1, h = py_hi - py_lo + 1;
+    if (w > 0 && h > 0 && a2 != 0.0) {
+      for (int t = threadIdx.x; t < w * h; t += kBlock) {
+        const int py = py_lo + t / w, px = px_lo + t % w;
+        // add_layer2image(variance_map, x, y, psf_variance_map * amp^2): the kernel is scaled first
+        const double fy = floor(py + half - yp), fx = floor(px + half - xp);
+        const double ky = py + half - yp, kx = px + half - xp;
+        const double wy1 = ky - fy, wx1 = kx - fx, wy0 = 1.0 - wy1, wx0 = 1.0 - wx1;
+        const int iy = (int)fy, ix = (int)fx;
+        auto at = [&](int y, int x) { return (y >= 0 && y < K && x >= 0 && x < K) ? P.ps_var[y * K + x] * a2 : 0.0; };
+        double v = (wy0 * wx0) * at(iy, ix);
+        v += (wy0 * wx1) * at(iy, ix + 1);
+        v += (wy1 * wx0) * at(iy + 1, ix);
+        v += (wy1 * wx1) * at(iy + 1, ix + 1);
+        img[(int64_t)py * P.nx + px] += v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- FFT convolution helpers (large kernels; the transforms themselves are cuFFT) ----------------------------------
 // zero-padded copy [n][ny][nx] -> [n][PY][PX]
 __global__ void __launch_bounds__(kBlock)
@@ -741,7 +795,7 @@ constexpr int kLikeUnroll = 4;
 template <int NS>
 __global__ void __launch_bounds__(kBlock)
 k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linear, int marg, double* __restrict__ logl,
-             double* __restrict__ amps, double* __restrict__ model_out) {
+             double* __restrict__ amps, double* __restrict__ model_out, const double* __restrict__ err_map) {
   constexpr int NM = NS * (NS + 1) / 2;
   __shared__ double scratch[(NM + NS + 1) * (kBlock / 32)];
   __shared__ double s_amp[NS];
@@ -750,6 +804,8 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
   const int npix = P.nx * P.ny;
   const int ns = P.n_slots;
   const double* A = conv + bl * ns * (int64_t)npix;
+  // PSF error map of this set (sigma^2, or null): added to C_D(data) in the weights and as |.| to C_D(model) in chi^2
+  const double* E = err_map ? err_map + bl * (int64_t)npix : nullptr;
 
   if (linear) {
     double acc[NM + NS];
@@ -763,6 +819,7 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
         const int p = p0 + u * kBlock;
         const bool use = p < npix && (!P.mask || P.mask[p]);
         wgt[u] = use ? __ldg(P.w_data + p) : 0.0;  // masked / out-of-range pixels get zero weight
+        if (E && use) wgt[u] = 1.0 / (1.0 / wgt[u] + E[p]);  // 1 / (C_D + model_error), image_linear_solve.py:150
         dat[u] = use ? __ldg(P.data + p) : 0.0;
 #pragma unroll
         for (int k = 0; k < NS; ++k) a[u][k] = (use && k < ns) ? A[(int64_t)k * npix + p] : 0.0;
@@ -845,7 +902,8 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
       const int p = p0 + u * kBlock;
       if (model_out && valid[u]) model_out[(set0 + bl) * npix + p] = mdl[u];
       if (use[u]) {
-        const double cd = P.noise_map2 ? aux[u] : fma(fmax(mdl[u], 0.0), aux[u], P.bkg2);
+        double cd = P.noise_map2 ? aux[u] : fma(fmax(mdl[u], 0.0), aux[u], P.bkg2);
+        if (E) cd += fabs(E[p]);  // imaging_data.py:180
         const double d = mdl[u] - dat[u];
         chi[0] += d * d / cd;
       }

@@ -304,10 +304,14 @@ class ImageModel:
 
     def __init__(self, data_class, psf_class, lens_model_list=None, source_model_list=None,
                  lens_light_model_list=None, kwargs_numerics=None, likelihood_mask=None,
-                 lens_profile_kwargs_list=None, point_source_type_list=None):
+                 lens_profile_kwargs_list=None, point_source_type_list=None, psf_variance_map=None,
+                 psf_error_map_bool_list=None):
         # point sources: UNLENSED / LENSED_POSITION without fixed magnification -- positions and amplitudes are the
         # parameters themselves (PointSource/Types/unlensed.py, lensed_position.py)
         self.point_source_type_list = list(point_source_type_list or [])
+        # PSF error map (image_model.py:127-132,615-648): variance per kernel pixel for a unit point source
+        self._psf_variance_map = None if psf_variance_map is None else np.asarray(psf_variance_map, dtype=float)
+        self._psf_error_map_bool_list = psf_error_map_bool_list
         self._ps_supersampling = (kwargs_numerics or {}).get("point_source_supersampling_factor", 1)
         self.Data = data_class
         self.PSF = psf_class
@@ -351,6 +355,21 @@ class ImageModel:
         kernel = None if unconvolved else self.PSF.kernel_point_source_supersampled(self._ps_supersampling)
         return point_source_rendering(self.Data, kernel, self._ps_supersampling, ra, dec, amp, unconvolved=unconvolved)
 
+    def error_map_psf(self, kwargs_ps):
+        """ImageModel._error_map_psf, image_model.py:615-648."""
+        from oracle.point_source import psf_variance_map
+
+        error_map = np.zeros(self.Data.num_pixel_axes)
+        if self._psf_variance_map is None or not self.point_source_type_list or not kwargs_ps:
+            return error_map
+        flags = self._psf_error_map_bool_list or [True] * len(self.point_source_type_list)
+        for k, kw in enumerate(kwargs_ps):
+            if flags[k] and np.size(kw["ra_image"]) > 0:
+                error_map = error_map + psf_variance_map(self.Data, self.PSF.kernel_point_source,
+                                                         self._psf_variance_map, kw["ra_image"], kw["dec_image"],
+                                                         self.Data.data)
+        return error_map
+
     def point_source(self, kwargs_ps, unconvolved=False, k=None):
         image = np.zeros(self.Data.num_pixel_axes)
         ra, dec, amp = [], [], []
@@ -377,7 +396,7 @@ class ImageModel:
                                     kwargs_ps=None):
         """image_model.py:162-221 (no linear solve)."""
         im_sim = self.image(kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps=kwargs_ps)
-        model_error = np.zeros(self.Data.num_pixel_axes)
+        model_error = self.error_map_psf(kwargs_ps)
         return self.Data.log_likelihood(im_sim, self.likelihood_mask, model_error)
 
     # --- masks ---
@@ -415,7 +434,7 @@ class ImageModel:
     def image_linear_solve(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None, inv_bool=False,
                            kwargs_ps=None):
         A = self.linear_response_matrix(kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps=kwargs_ps)
-        model_error = np.zeros(self.Data.num_pixel_axes)
+        model_error = self.error_map_psf(kwargs_ps)
         C_D_response = self.image2array_masked(self.Data.C_D + model_error)
         d = self.image2array_masked(self.Data.data)
         param, cov_param, wls_model = get_param_WLS(A.T, 1 / C_D_response, d, inv_bool=inv_bool)

@@ -73,3 +73,32 @@ def point_source_rendering(pixel_grid, kernel_supersampled, supersampling_factor
     for i in range(len(x_pos)):
         subgrid2d = add_layer2image(subgrid2d, x_sub[i], y_sub[i], amp[i] * kernel)
     return re_size(subgrid2d, subgrid) * subgrid**2
+
+
+def estimate_amp(data, x_pos, y_pos, psf_kernel):
+    """jaxtronomy/Util/kernel_util.py:7-47."""
+    numPix_x, numPix_y = data.shape
+    x_int = int(np.round(x_pos - 0.49999))
+    y_int = int(np.round(y_pos - 0.49999))
+    ok = not (x_int <= 2 or x_int >= numPix_x - 2 or y_int <= 2 or y_int >= numPix_y - 2)
+    if not ok:
+        return 0.0
+    mean_image = max(np.sum(data[y_int - 2:y_int + 3, x_int - 2:x_int + 3]), 0)
+    num = len(psf_kernel)
+    center = int((num - 0.5) / 2)
+    mean_kernel = np.sum(psf_kernel[center - 2:center + 3, center - 2:center + 3])
+    return mean_image / mean_kernel
+
+
+def psf_variance_map(pixel_grid, psf_kernel, variance_kernel, ra_pos, dec_pos, data):
+    """PointSourceRendering.psf_variance_map with fix_psf_variance_map=False
+    (jaxtronomy/ImSim/Numerics/point_source_rendering.py:79-111)."""
+    M = np.asarray(pixel_grid._Ma2pix)
+    ra_pos, dec_pos = np.atleast_1d(ra_pos), np.atleast_1d(dec_pos)
+    x_pos = M[0, 0] * ra_pos + M[0, 1] * dec_pos + pixel_grid._x_at_radec_0
+    y_pos = M[1, 0] * ra_pos + M[1, 1] * dec_pos + pixel_grid._y_at_radec_0
+    out = np.zeros_like(data, dtype=float)
+    for i in range(len(x_pos)):
+        amp = estimate_amp(data, x_pos[i], y_pos[i], psf_kernel)
+        out = add_layer2image(out, x_pos[i], y_pos[i], variance_kernel * amp**2)
+    return out

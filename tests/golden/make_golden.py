@@ -512,6 +512,25 @@ def gen_point_sources():
                 source_model_list=["SERSIC_ELLIPSE"], kwargs_source=kw_src, lens_light_model_list=["SERSIC_ELLIPSE"],
                 kwargs_lens_light=kw_ll, point_source_type_list=ps_types, kwargs_ps=kw_ps_p,
                 kwargs_psf=dict(psf_type="PIXEL"), kwargs_numerics=num_kw))
+    # 3. the same model with a PSF variance map: error map, likelihood and linear solve with C_D + model error
+    var_map = 0.02 * kern**2 / np.max(kern**2) + 1e-4 * rng.uniform(0, 1, kern.shape)
+    psf_v = PSF(psf_type="PIXEL", kernel_point_source=kern, psf_variance_map=var_map)
+    for case, flags in (("error_map_all", None), ("error_map_first_only", [True, False])):
+        im = ImageModel(data, psf_v, lens, src, ll, point_source_class=ps, kwargs_numerics=num_kw,
+                        psf_error_map_bool_list=flags)
+        lin = ImageLinearFit(data, psf_v, lens, src, ll, point_source_class=ps, kwargs_numerics=num_kw,
+                             psf_error_map_bool_list=flags)
+        outs = dict(error_map=np.asarray(im._error_map_psf(kw_lens, cp(kw_ps_p))),
+                    logL=float(im.likelihood_data_given_model(kw_lens, kw_src, kw_ll, cp(kw_ps_p))))
+        model, model_error, _, param = lin.image_linear_solve(kw_lens, cp(kw_src), cp(kw_ll), cp(kw_ps_p))
+        logL_lin, _ = lin.likelihood_data_given_model(kw_lens, cp(kw_src), cp(kw_ll), cp(kw_ps_p))
+        outs.update(wls_model=np.asarray(model), model_error=np.asarray(model_error), param=np.asarray(param),
+                    logL_linear=float(logL_lin))
+        st.add(case, dict(ins, psf_variance_map=var_map), outs,
+               dict(numPix=numPix, deltaPix=deltaPix, lens_model_list=["EPL", "SHEAR"], kwargs_lens=kw_lens,
+                    source_model_list=["SERSIC_ELLIPSE"], kwargs_source=kw_src, lens_light_model_list=["SERSIC_ELLIPSE"],
+                    kwargs_lens_light=kw_ll, point_source_type_list=ps_types, kwargs_ps=kw_ps_p,
+                    kwargs_psf=dict(psf_type="PIXEL"), kwargs_numerics=num_kw, psf_error_map_bool_list=flags))
     st.save("point_sources.npz")
 
 

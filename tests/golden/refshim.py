@@ -425,6 +425,9 @@ def _make_lenstronomy():
                               kernel_point_source_normalisation, point_source_supersampling_factor)
             self.point_source_supersampling_factor = point_source_supersampling_factor
             self.psf_variance_map_bool = psf_variance_map is not None
+            # lenstronomy PSF.psf_variance_map: the given map (shape of kernel_point_source), zeros if none
+            self.psf_variance_map = np.array(psf_variance_map, dtype=float) if psf_variance_map is not None \
+                else np.zeros_like(self.kernel_point_source) if psf_type != "GAUSSIAN" else None
 
         def kernel_point_source_supersampled(self, supersampling_factor, updata_cache=True):
             if self.psf_type == "GAUSSIAN":

@@ -561,3 +561,40 @@ def test_image_model_with_point_sources():
     mat, _, _ = lin._pack(kl, ks, kll, kps, [4, 1])
     l_b, a_b, _ = lin.logL_linear_batch(torch.as_tensor(np.repeat(mat, 3, axis=0), device="cuda"))
     assert np.allclose(l_b.cpu().numpy(), logL_lin, rtol=1e-12) and np.allclose(a_b.cpu().numpy()[2], param2, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["error_map_all", "error_map_first_only"])
+def test_psf_error_map(name):
+    """PSF error map (k_ps_error_map) and its use in k_likelihood: weights 1/(C_D + error), chi^2 on C_D(model) + |error|."""
+    from jaxtronomy_b200.Data.imaging_data import ImageData
+    from jaxtronomy_b200.Data.psf import PSF
+    from jaxtronomy_b200.ImSim.image_linear_solve import ImageLinearFit
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+    from jaxtronomy_b200.LightModel.light_model import LightModel
+    from jaxtronomy_b200.PointSource.point_source import PointSource
+
+    c = POINTS[name]
+    kd = dict(image_data=c.inp["image_data"], transform_pix2angle=c.inp["transform_pix2angle"],
+              ra_at_xy_0=float(c.inp["ra_at_xy_0"]), dec_at_xy_0=float(c.inp["dec_at_xy_0"]),
+              background_rms=float(c.inp["background_rms"]), exposure_time=float(c.inp["exposure_time"]))
+    lens = LensModel(c.meta["lens_model_list"])
+    psf = PSF(psf_type="PIXEL", kernel_point_source=c.inp["kernel"], psf_variance_map=c.inp["psf_variance_map"])
+    lin = ImageLinearFit(ImageData(**kd), psf, lens, LightModel(c.meta["source_model_list"]),
+                         LightModel(c.meta["lens_light_model_list"]),
+                         point_source_class=PointSource(c.meta["point_source_type_list"], lens_model=lens),
+                         kwargs_numerics=c.meta["kwargs_numerics"],
+                         psf_error_map_bool_list=c.meta["psf_error_map_bool_list"])
+    kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
+    kps = [{k: np.asarray(v, dtype=float) for k, v in kw.items()} for kw in c.meta["kwargs_ps"]]
+    assert_close(lin._error_map_psf(kl, kps), c.out["error_map"], what="error map", **BAR)
+    # ImageModel.likelihood_data_given_model (amplitudes from the kwargs) through the parent class
+    from jaxtronomy_b200.ImSim.image_model import ImageModel
+
+    logL = ImageModel.likelihood_data_given_model(lin, kl, ks, kll, kps)
+    assert abs(logL - float(c.out["logL"])) <= 1e-10 * abs(float(c.out["logL"]))
+    model, model_error, _, param = lin.image_linear_solve(kl, ks, kll, kps)
+    assert_close(model_error, c.out["model_error"], what="model error", **BAR)
+    assert_close(param, c.out["param"], what="param", rtol=1e-8, atol_frac=1e-10)
+    assert_close(model, c.out["wls_model"], what="wls model", rtol=1e-8, atol_frac=1e-10)
+    logL_lin, _ = lin.likelihood_data_given_model(kl, ks, kll, kps)
+    assert abs(logL_lin - float(c.out["logL_linear"])) <= 1e-9 * abs(float(c.out["logL_linear"]))

@@ -260,3 +260,28 @@ def test_image_model_with_point_sources():
     assert_close(model, c.out["wls_model"], what="wls model", rtol=1e-9, atol_frac=1e-11)
     logL_lin, _ = im.likelihood_data_given_model_linear(kl, ks, kll, kwargs_ps=kps)
     assert abs(logL_lin - float(c.out["logL_linear"])) <= 1e-9 * abs(float(c.out["logL_linear"]))
+
+
+@pytest.mark.parametrize("name", ["error_map_all", "error_map_first_only"])
+def test_psf_error_map(name):
+    """ImageModel._error_map_psf + its use in the likelihood and the linear solve (C_D + model error)."""
+    c = POINTS[name]
+    kd = dict(image_data=c.inp["image_data"], transform_pix2angle=c.inp["transform_pix2angle"],
+              ra_at_xy_0=float(c.inp["ra_at_xy_0"]), dec_at_xy_0=float(c.inp["dec_at_xy_0"]),
+              background_rms=float(c.inp["background_rms"]), exposure_time=float(c.inp["exposure_time"]))
+    im = imsim.ImageModel(imsim.ImageData(**kd), _psf(c.meta["kwargs_psf"], c.inp), c.meta["lens_model_list"],
+                          c.meta["source_model_list"], c.meta["lens_light_model_list"], c.meta["kwargs_numerics"],
+                          point_source_type_list=c.meta["point_source_type_list"],
+                          psf_variance_map=c.inp["psf_variance_map"],
+                          psf_error_map_bool_list=c.meta["psf_error_map_bool_list"])
+    kl, ks, kll, kps = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"], _ps_kwargs(c)
+    tol = dict(rtol=1e-11, atol_frac=1e-13)
+    assert c.out["error_map"].max() > 0
+    assert_close(im.error_map_psf(kps), c.out["error_map"], what="error map", **tol)
+    logL = im.likelihood_data_given_model(kl, ks, kll, kwargs_ps=kps)
+    assert abs(logL - float(c.out["logL"])) <= 1e-11 * abs(float(c.out["logL"]))
+    model, model_error, _, param = im.image_linear_solve(kl, ks, kll, kwargs_ps=kps)
+    assert_close(model_error, c.out["model_error"], what="model error", **tol)
+    assert_close(param, c.out["param"], what="param", rtol=1e-9, atol_frac=1e-11)
+    logL_lin, _ = im.likelihood_data_given_model_linear(kl, ks, kll, kwargs_ps=kps)
+    assert abs(logL_lin - float(c.out["logL_linear"])) <= 1e-9 * abs(float(c.out["logL_linear"]))
