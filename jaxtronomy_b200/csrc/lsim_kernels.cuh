@@ -1,11 +1,16 @@
 // lsim_kernels.cuh -- the CUDA kernels of the forward-simulation path (sm_100a).
 //
+//   k_prepare              per-set constants (parameter conversion, series coefficients) once per parameter set
 //   k_ray_shoot            LensModel.ray_shooting / SinglePlane.alpha / LensModelBulk / MultiPlane on N points x B sets
 //   k_surface_brightness   LightModel.surface_brightness / functions_split on N points x B sets
 //   k_image                fused ray-shoot + light + ss x ss re-bin: one thread per *pixel*, looping its
 //                          ss^2 sub-pixels in registers, so the supersampled flux never exists in memory
-//   k_conv_*               PSF convolution of the re-binned basis images (direct, shared-memory tiled)
+//                          (k_image_f32 in lsim_f32.cuh: the opt-in single-precision variant)
+//   k_conv_*               PSF convolution of the re-binned basis images (direct, shared-memory tiled);
+//   k_fft_pad/mul/crop     ... and the helpers around cuFFT for kernels of side >= 33
+//   k_point_sources        PSF stamps of the point-source images; k_ps_error_map: the PSF error map
 //   k_likelihood           WLS amplitudes (normal equations reduced per CTA, solved in registers) + chi^2
+//   k_pso_best/k_pso_move  one particle-swarm iteration on the device
 //   k_fp64_peak            DFMA-chain microbenchmark for the roofline denominator
 //
 // Layout: parameter sets are the slow (grid.y / blockIdx) axis, pixels the fast axis; all global stores

@@ -4,7 +4,7 @@
 // arithmetic with g++ and check it against the oracle on a machine without a GPU.  The device build is
 // the product; the host build exists only under tests/.
 //
-// Design rule (measured, profiles/r1_k_image_*.md): the fp64 pipe (64 DFMA lanes / SM / clk on B200) is the
+// Design rule (measured, profiles/image_r1*_ncu_summary.txt, profiles/r1_dfma_operand_probe.md): the fp64 pipe (64 DFMA lanes / SM / clk on B200) is the
 // binding unit of the image kernel, so
 //   * transcendental cores are short FMA chains with no special-case handling in the fast path,
 //   * anything that can run on another pipe does: reciprocal seeds, int<->double conversions and rounding go
@@ -109,6 +109,22 @@ LSIM_HD double rcp_fast(double x) {
 // dozen instructions for that): one compare and a select.
 LSIM_HD double max_nan(double x, double lo) { return (x < lo) ? lo : x; }
 LSIM_HD double min_nan(double x, double hi) { return (x > hi) ? hi : x; }
+
+// sqrt(x) for finite, normal, positive x (no special cases): MUFU.RSQ64H seed (XU pipe), two Newton steps on
+// 1/sqrt(x) and one correction of the root; < 1 ulp.  x = 0 / inf / nan are NOT handled (callers guarantee x > 0).
+LSIM_HD double sqrt_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  const double s = x * y;
+  return fma(0.5 * y, fma(-s, s, x), s);
+#else
+  return sqrt(x);
+#endif
+}
 
 // ---- fast fp64 log2 / exp2 --------------------------------------------------------------------------
 // The hot loop needs pow(x, s) = exp2(s * log2(x)) and exp(-b (k - 1)) for finite positive normal x.
