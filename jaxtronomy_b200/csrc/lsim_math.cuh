@@ -126,6 +126,20 @@ LSIM_HD double sqrt_fast(double x) {
 #endif
 }
 
+// 1/sqrt(x) for finite, normal, positive x: MUFU.RSQ64H seed + two Newton steps (~1 ulp).
+LSIM_HD double rsqrt_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 // ---- fast fp64 log2 / exp2 --------------------------------------------------------------------------
 // The hot loop needs pow(x, s) = exp2(s * log2(x)) and exp(-b (k - 1)) for finite positive normal x.
 // libdevice's log/exp/pow carry special-case branches and long polynomials; on a kernel bound by the fp64 pipe
