@@ -293,6 +293,43 @@ LSIM_HD void multipole_eval(double xs, double ys, int m, double A, double cmp, d
   }
 }
 
+// The m = 1, 3, 4 multipoles of EPL_MULTIPOLE_M1M3M4 at one point, fused: one reciprocal square root, the powers of
+// u = e^{i phi} by complex multiplication, no trigonometric call (epl_multipole_m1m3m4.py:608-678 adds
+// Multipole.derivatives for m = 1, 3, 4; same expressions as multipole_eval above).  L.c[9..18] as prepared.
+LSIM_HD void multipole_m1m3m4_add(const LensC& L, double xs, double ys, double& fx, double& fy) {
+  const double r2 = fma(ys, ys, xs * xs);
+  double c1 = 1.0, s1 = 0.0;  // atan2(0, 0) = 0
+  if (r2 > 0) {
+    const double ir = rsqrt_fast(fmax(r2, 1e-300));
+    c1 = xs * ir;
+    s1 = ys * ir;
+  }
+  const double c2 = fma(c1, c1, -(s1 * s1)), s2 = 2.0 * c1 * s1;
+  const double c3 = fma(c2, c1, -(s2 * s1)), s3 = fma(c2, s1, s2 * c1);
+  const double c4 = fma(c2, c2, -(s2 * s2)), s4 = 2.0 * c2 * s2;
+  double gx = 0.0, gy = 0.0;
+  {  // m = 3: A = c[13], (cos, sin)(3 phi_3) = c[14], c[15]
+    const double cmd = fma(s3, L.c[15], c3 * L.c[14]), smd = fma(s3, L.c[14], -(c3 * L.c[15]));
+    const double a = L.c[13] * cmd, b = 3.0 * L.c[13] * smd;
+    gx += fma(s1, b, c1 * a);
+    gy += fma(-c1, b, s1 * a);
+  }
+  {  // m = 4
+    const double cmd = fma(s4, L.c[18], c4 * L.c[17]), smd = fma(s4, L.c[17], -(c4 * L.c[18]));
+    const double a = L.c[16] * cmd, b = 4.0 * L.c[16] * smd;
+    gx += fma(s1, b, c1 * a);
+    gy += fma(-c1, b, s1 * a);
+  }
+  {  // m = 1: A = c[9], (cos, sin)(phi_1) = c[10], c[11], ln r_E = c[12]
+    const double cmd = fma(s1, L.c[11], c1 * L.c[10]);
+    const double lg = 0.5 * kLn2 * log2_pos(fmax(r2, 1e-12)) - L.c[12];  // r = max(r, 1e-6)
+    gx += L.c[9] * fma(L.c[10], lg, cmd * c1);
+    gy += L.c[9] * fma(L.c[11], lg, cmd * s1);
+  }
+  fx += gx;
+  fy += gy;
+}
+
 // nfw.py:347-365
 LSIM_HD double nfw_g(double X) {
   const double c = 0.000001;
@@ -545,20 +582,10 @@ LSIM_HD void lens_eval1(int type, const LensC& L, const double* coef_pool, doubl
   }
   if (FULL) {
     switch (type) {
-      case LSIM_LENS_EPL_MULTIPOLE_M1M3M4: {
-        double ex, ey, mx, my;
-        epl_eval1(L, coef_pool + L.coef_off, xs, ys, ex, ey);
-        multipole_eval(xs, ys, 3, L.c[13], L.c[14], L.c[15], 0.0, mx, my);
-        ex += mx;
-        ey += my;
-        multipole_eval(xs, ys, 4, L.c[16], L.c[17], L.c[18], 0.0, mx, my);
-        ex += mx;
-        ey += my;
-        multipole_eval(xs, ys, 1, L.c[9], L.c[10], L.c[11], L.c[12], mx, my);
-        fx = ex + mx;
-        fy = ey + my;
+      case LSIM_LENS_EPL_MULTIPOLE_M1M3M4:
+        epl_eval1(L, coef_pool + L.coef_off, xs, ys, fx, fy);
+        multipole_m1m3m4_add(L, xs, ys, fx, fy);
         return;
-      }
       case LSIM_LENS_MULTIPOLE:
         multipole_eval(xs, ys, (int)L.c[2], L.c[3], L.c[4], L.c[5], L.c[6], fx, fy);
         return;
@@ -653,6 +680,22 @@ LSIM_HD void lens_eval(int type, const LensC& L, const double* coef_pool, const 
       ys[j] = y[j] - L.c[1];
     }
     epl_eval<J>(L, coef_pool + L.coef_off, xs, ys, fx, fy);
+    return;
+  }
+  if (FULL && type == LSIM_LENS_EPL_MULTIPOLE_M1M3M4) {
+    double xs[J], ys[J];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < J; ++j) {
+      xs[j] = x[j] - L.c[0];
+      ys[j] = y[j] - L.c[1];
+    }
+    epl_eval<J>(L, coef_pool + L.coef_off, xs, ys, fx, fy);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < J; ++j) multipole_m1m3m4_add(L, xs[j], ys[j], fx[j], fy[j]);
     return;
   }
   if (type == LSIM_LENS_SHEAR) {
