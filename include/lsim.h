@@ -205,7 +205,7 @@ typedef struct lsim_plan_desc {
 typedef struct lsim_plan lsim_plan;
 
 /* Validate a descriptor, upload static data to the current CUDA device and build a plan.
- * PSF kernels with a side of 33 pixels or more (zero boundary, not separable) are convolved by FFT (cuFFT D2Z/Z2D on
+ * PSF kernels with a side of 27 pixels or more (zero boundary, not separable) are convolved by FFT (cuFFT D2Z/Z2D on
  * zero-padded frames, loaded with dlopen on first use; direct convolution is used if cuFFT is absent).  Such a plan
  * owns the FFT scratch, so only ONE image / likelihood call may be in flight per plan (use one plan per stream);
  * all other plans are re-entrant across streams. */

@@ -7,7 +7,7 @@
 //                          ss^2 sub-pixels in registers, so the supersampled flux never exists in memory
 //                          (k_image_f32 in lsim_f32.cuh: the opt-in single-precision variant)
 //   k_conv_*               PSF convolution of the re-binned basis images (direct, shared-memory tiled);
-//   k_fft_pad/mul/crop     ... and the helpers around cuFFT for kernels of side >= 33
+//   k_fft_pad/mul/crop     ... and the helpers around cuFFT for kernels of side >= 27
 //   k_point_sources        PSF stamps of the point-source images; k_ps_error_map: the PSF error map
 //   k_likelihood           WLS amplitudes (normal equations reduced per CTA, solved in registers) + chi^2
 //   k_pso_best/k_pso_move  one particle-swarm iteration on the device

@@ -441,7 +441,7 @@ def test_fp32_variant(headline):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# FFT path of the PSF convolution (kernel side >= 33, or forced with LSIM_FFT_MIN_K)
+# FFT path of the PSF convolution (kernel side >= 27, or forced with LSIM_FFT_MIN_K)
 # ---------------------------------------------------------------------------------------------------------------
 def _numerics_with_pixel_psf(nx, ny, kernel, ss=1, supersampling_convolution=False):
     from jaxtronomy_b200.Data.pixel_grid import PixelGrid
