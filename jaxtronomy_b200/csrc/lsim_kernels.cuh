@@ -446,30 +446,30 @@ k_conv_direct(const double* __restrict__ in, double* __restrict__ out, int nx, i
 }
 
 // Register-tiled direct convolution for K <= KT (the common PSF sizes; the kernel is zero-padded to KT x KT).
-// A warp owns a 32-column x R-row strip, NW warps stack to a 32 x (R NW) tile.  For each kernel column dx a
-// thread pulls its R + KT - 1 input values of that column into registers once and reuses each of them for up
-// to KT of the R x KT FMAs; the KT weights of the column are warp-uniform shared-memory broadcasts.  Shared
-// memory traffic per FMA drops from 2 loads (k_conv_direct) to (R + 2 KT - 1) / (R KT) ~ 0.24 (R = 10, KT = 21),
-// which moves the kernel from shared-memory-bandwidth-bound to fp64-pipe-bound.  The weight is the operand the DFMAs
-// of a row share (register reuse cache): a DFMA with three fresh register operands issues every 3 cycles instead of
-// 2 on B200 (profiles/r1_dfma_operand_probe.md).
+// A warp owns a 32-column x R-row strip, NW warps stack to a 32 x (R NW) tile.  For each kernel column dx a thread
+// reads its R + KT - 1 input values of that column from shared memory and uses each of them for up to KT of the
+// R x KT FMAs.  The weights are passed BY VALUE as a kernel parameter (constant bank, read through uniform
+// registers): every DFMA then has the form  acc[o] += v.reuse * UR  -- one input value held in the operand reuse
+// cache, a uniform-register weight and ONE fresh vector register (the accumulator).  That matters on B200, where a
+// DFMA with three fresh register operands issues every 3 cycles instead of 2 (profiles/r1_dfma_operand_probe.md);
+// with shared-memory weights (the previous version: two fresh registers + reuse) the same tiling ran 19 % slower.
+// wT[dx][dy], flipped (correlation form), zero padded from K to KT.
+template <int KT>
+struct ConvWeights {
+  double w[KT * KT];
+};
+
 template <int KT, int R, int NW>
 __global__ void __launch_bounds__(NW * 32, 2)
-k_conv_tiled(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
-             const double* __restrict__ kernel, int mode, double scale, int accumulate) {
-  constexpr int NT = NW * 32, TH = R * NW, HALO = KT - 1, TWD = 32 + HALO, PITCH = TWD | 1, WS = KT + 1;
+k_conv_tiled_u(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int mode, double scale,
+               int accumulate, const __grid_constant__ ConvWeights<KT> W) {
+  constexpr int NT = NW * 32, TH = R * NW, HALO = KT - 1, TWD = 32 + HALO, PITCH = TWD | 1;
   extern __shared__ double smem[];
-  double* tile = smem;                      // [TH + HALO][PITCH]
-  double* wT = smem + (TH + HALO) * PITCH;  // [KT][WS]: wT[dx][dy], flipped (correlation form), zero padded
-  const int rT = HALO / 2, pad = (KT - K) / 2;
+  double* tile = smem;  // [TH + HALO][PITCH]
+  const int rT = HALO / 2;
   const int tiles_x = (nx + 31) / 32;
   const int tx0 = (blockIdx.x % tiles_x) * 32, ty0 = (blockIdx.x / tiles_x) * TH;
   const double* img = in + (int64_t)blockIdx.y * nx * ny;
-  for (int i = threadIdx.x; i < KT * KT; i += NT) {
-    const int a = i / KT, b = i - a * KT, ka = a - pad, kb = b - pad;
-    const bool inside = ka >= 0 && ka < K && kb >= 0 && kb < K;
-    wT[b * WS + a] = inside ? kernel[(K - 1 - ka) * K + (K - 1 - kb)] : 0.0;
-  }
   for (int i = threadIdx.x; i < (TH + HALO) * TWD; i += NT) {
     const int ly = i / TWD, lx = i - ly * TWD;
     tile[ly * PITCH + lx] = conv_fetch(img, nx, ny, tx0 + lx - rT, ty0 + ly - rT, mode);
@@ -485,10 +485,9 @@ k_conv_tiled(const double* __restrict__ in, double* __restrict__ out, int nx, in
     double v[R + KT - 1];
 #pragma unroll
     for (int i = 0; i < R + KT - 1; ++i) v[i] = tcol[i * PITCH + dx];
-    const double* w = wT + dx * WS;
 #pragma unroll
     for (int dy = 0; dy < KT; ++dy) {
-      const double wv = w[dy];
+      const double wv = W.w[dx * KT + dy];
 #pragma unroll
       for (int o = 0; o < R; ++o) acc[o] = fma(wv, v[o + dy], acc[o]);
     }

@@ -2,7 +2,7 @@
 # Run on the GPU box: gpurun -- 'bash tools/ncu_profile.sh <tag>'; text summaries land in gpurun_out/ (the
 # .ncu-rep files are ~45 MB each and stay on the box).
 TAG=${1:-dev}
-KERNELS=${2:-"k_image k_conv_tiled k_likelihood"}
+KERNELS=${2:-"k_image k_conv_tiled_u k_likelihood"}
 mkdir -p gpurun_out /tmp/ncu
 CMD="python bench.py --steps 1 --warmup 3 --batch 2368 --no-cpu"
 for k in $KERNELS; do
