@@ -794,7 +794,10 @@ __device__ inline bool lu_solve(double* m, double* r, int n) {
 //   logL = -1/2 sum mask (model - data)^2 / C_D(model)                    (imaging_data.py:159-182)
 //          C_D(model) = noise_map^2  or  max(model,0)/t_exp + sigma_bkg^2 (image_noise.py:99-137)
 //   marg != 0: + 1/2 sign log|det M^-1|, -1e15 if singular               (de_lens.py:39-49)
-constexpr int kLikeUnroll = 4;
+#ifndef LSIM_LIKE_UNROLL
+#define LSIM_LIKE_UNROLL 4
+#endif
+constexpr int kLikeUnroll = LSIM_LIKE_UNROLL;
 
 template <int NS>
 __global__ void __launch_bounds__(kBlock)
