@@ -598,3 +598,47 @@ def test_psf_error_map(name):
     assert_close(model, c.out["wls_model"], what="wls model", rtol=1e-8, atol_frac=1e-10)
     logL_lin, _ = lin.likelihood_data_given_model(kl, ks, kll, kps)
     assert abs(logL_lin - float(c.out["logL_linear"])) <= 1e-9 * abs(float(c.out["logL_linear"]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# batch-shape and robustness edge cases of the [B, P] entry points
+# ---------------------------------------------------------------------------------------------------------------
+def test_batch_edge_cases(headline):
+    """Empty batch, one set, a ragged batch that spans several chunks, and rows with wild / nan parameters: the
+    wild rows get finite or nan results of their own and never disturb their neighbours."""
+    import torch
+
+    from bench import oracle_headline_logl
+
+    model, params = headline["model"], headline["params"]
+    empty = params[:0]
+    l0, a0, _ = model.logL_linear_batch(empty)
+    assert l0.shape == (0,) and a0.shape == (0, 1) and model.image_batch(empty).shape == (0, 180, 180)
+    l1, a1, _ = model.logL_linear_batch(params[:1])
+    ref, _ = oracle_headline_logl(headline, 0)
+    assert abs(float(l1[0]) - ref) <= 1e-10 * abs(ref)
+    # ragged: 2 x 1184 + 37 sets (chunk = 8 x 148 SMs) built by tiling the 296 fixture rows
+    big = params.repeat(9, 1)[: 2 * 1184 + 37].contiguous()
+    lb, _, _ = model.logL_linear_batch(big)
+    base, _, _ = model.logL_linear_batch(params)
+    assert torch.equal(lb, base.repeat(9)[: big.shape[0]])
+    # wild rows
+    wild = params[:8].clone()
+    wild[1, 0] = float("nan")      # theta_E
+    wild[2, 11] = 1e-9             # R_sersic far below its clamp (sersic_utils.py: R_sersic >= 1e-4)
+    wild[3, 12] = 0.2              # n_sersic below the usual range: steep profile, exponent clamps
+    wild[4, 2:4] = 0.0             # e1 = e2 = 0: f = 0, the series collapses to its first term
+    wild[5, 0] = 1e6               # absurd Einstein radius
+    wild[6, 1] = 2.999             # gamma at the edge of the power-law range
+    lw, aw, _ = model.logL_linear_batch(wild)
+    clean, _, _ = model.logL_linear_batch(params[:8])
+    for b in (0, 7):
+        assert lw[b] == clean[b]
+    assert all(np.isfinite(float(lw[b])) for b in (2, 3, 4, 5, 6)), lw
+    assert not np.isfinite(float(lw[1])) or abs(float(lw[1])) > 0  # a nan row stays confined to itself
+    # the e = 0 and gamma-edge rows against the oracle
+    headline_w = dict(headline, params_host=wild.cpu().numpy())
+    for b in (4, 6):
+        ref, ramp = oracle_headline_logl(headline_w, b)
+        assert abs(float(lw[b]) - ref) <= 1e-9 * abs(ref), (b, float(lw[b]), ref)
+        np.testing.assert_allclose(aw[b].cpu().numpy(), ramp, rtol=1e-8)
