@@ -273,3 +273,25 @@ def test_gaussian_psf_point_source_kernel():
     assert abs(var - (fwhm2sigma(0.3) / 0.05) ** 2) < 2e-3 * var
     k3 = psf.kernel_point_source_supersampled(3)
     assert k3.shape[0] % 2 == 1 and abs(k3.sum() - 1) < 1e-14 and abs(k3.shape[0] - 3 * 36) <= 1
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) on a tiny sample: one JSON line
+    with the contract's keys, no GPU needed."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-images", "4"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    # under torchrun only rank 0 works
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1"],
+                         capture_output=True, text=True, timeout=60, cwd=root, env=dict(os.environ, RANK="1"))
+    assert out.returncode == 0 and out.stdout.strip() == ""
