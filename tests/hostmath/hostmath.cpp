@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "../../jaxtronomy_b200/csrc/lsim_profiles.cuh"
+#include "../../jaxtronomy_b200/csrc/lsim_grad.cuh"
 
 using namespace lsim;
 
@@ -78,5 +79,46 @@ int hm_epl_terms(const lsim_lens_desc* lens, const double* row, double series_to
   std::vector<double> pool(kMaxSeries);
   lens_prepare(*lens, row, L, pool.data(), series_tol);
   return L.n_coef;
+}
+
+// Dual-number profile arithmetic of the gradient path (lsim_grad.cuh).
+//   ax, ay   [N]: summed deflection;  dax, day [N][n_lens][6]: d(alpha_i)/d(parameter k of profile i)
+int hm_lens_jvp(const lsim_lens_desc* lens, int n_lens, const double* row, const double* x, const double* y, int64_t N,
+                double* ax, double* ay, double* dax, double* day) {
+  std::vector<ad::GLens> L(n_lens);
+  std::vector<double> pool((size_t)(n_lens + 1) * ad::kGradPool);
+  int off = 0;
+  for (int i = 0; i < n_lens; ++i) {
+    L[i].coef_off = off * ad::kGradPool;
+    double* F = pool.data() + (size_t)off * ad::kGradPool;
+    if (!ad::lens_prepare_d(lens[i], row, L[i], F, F + kMaxSeries)) return -2;
+    if (ad::lens_grad_has_series(lens[i])) ++off;
+  }
+  for (int64_t p = 0; p < N; ++p) {
+    ax[p] = ay[p] = 0.0;
+    for (int i = 0; i < n_lens; ++i) {
+      ad::LD fx, fy;
+      ad::lens_eval_d(L[i], pool.data(), x[p], y[p], fx, fy);
+      ax[p] += fx.v;
+      ay[p] += fy.v;
+      for (int k = 0; k < ad::kLensN; ++k) {
+        dax[((size_t)p * n_lens + i) * ad::kLensN + k] = fx.d[k];
+        day[((size_t)p * n_lens + i) * ad::kLensN + k] = fy.d[k];
+      }
+    }
+  }
+  return 0;
+}
+
+//   out [N], dout [N][9]: d/dx, d/dy, then d/d(parameter k)
+int hm_light_jvp(const lsim_light_desc* light, const double* row, const double* x, const double* y, int64_t N,
+                 double* out, double* dout) {
+  if (!ad::light_grad_supported(*light)) return -2;
+  for (int64_t p = 0; p < N; ++p) {
+    const ad::GD v = ad::light_eval_d(*light, row, ad::var<ad::kLightN>(x[p], 0), ad::var<ad::kLightN>(y[p], 1));
+    out[p] = v.v;
+    for (int k = 0; k < ad::kLightN; ++k) dout[(size_t)p * ad::kLightN + k] = v.d[k];
+  }
+  return 0;
 }
 }

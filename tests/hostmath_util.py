@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "hostmath", "hostmath.cpp")
 SO = os.path.join(HERE, "hostmath", "libhostmath.so")
 _DEPS = [SRC] + [os.path.join(HERE, "..", "jaxtronomy_b200", "csrc", f)
-                 for f in ("lsim_profiles.cuh", "lsim_math.cuh", "lsim_cse_tables.h")] + \
+                 for f in ("lsim_profiles.cuh", "lsim_math.cuh", "lsim_cse_tables.h", "lsim_grad.cuh")] + \
     [os.path.join(HERE, "..", "include", "lsim.h")]
 
 _dp = C.POINTER(C.c_double)
@@ -39,6 +39,8 @@ def lib():
         h.hm_exp2.argtypes = [_dp, C.c_int64, _dp]
         h.hm_exp2_neg.argtypes = [_dp, C.c_int64, _dp]
         h.hm_epl_terms.argtypes = [C.POINTER(_lib.LensDesc), _dp, C.c_double]
+        h.hm_lens_jvp.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp]
+        h.hm_light_jvp.argtypes = [C.POINTER(_lib.LightDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp]
         _h = h
     return _h
 
@@ -109,3 +111,34 @@ def exp2_neg(x):
     out = np.empty_like(x)
     lib().hm_exp2_neg(_p(x), x.size, _p(out))
     return out
+
+
+def lens_jvp(lens_model_list, kwargs_list, x, y, profile_kwargs_list=None):
+    """Dual-number deflection of the gradient path: (alpha_x, alpha_y, d alpha_x [N, n_lens, 6], d alpha_y)."""
+    names = [_model.LENS_PARAM_NAMES[n] for n in lens_model_list]
+    row = np.asarray(_model.gather_values(names, kwargs_list), dtype=np.float64)
+    layout = _model.ColumnLayout()
+    descs = [_model.lens_desc(n, layout.add_profile("lens", i, names[i]), (profile_kwargs_list or [{}] * len(names))[i])
+             for i, n in enumerate(lens_model_list)]
+    arr = (_lib.LensDesc * max(1, len(descs)))(*descs)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    ax, ay = np.empty_like(x), np.empty_like(y)
+    dax, day = np.empty((x.size, len(descs), 6)), np.empty((x.size, len(descs), 6))
+    rc = lib().hm_lens_jvp(arr, len(descs), _p(row), _p(x), _p(y), x.size, _p(ax), _p(ay), _p(dax), _p(day))
+    assert rc == 0, rc
+    return ax, ay, dax, day
+
+
+def light_jvp(light_model, kwargs, x, y, use_amp=True):
+    """Dual-number surface brightness: (I [N], dI [N, 9]) with dI[:, 0:2] = d/dx, d/dy and dI[:, 2 + k] = d/d(param k)."""
+    names = [_model.LIGHT_PARAM_NAMES[light_model]]
+    row = np.asarray(_model.gather_values(names, [kwargs], "light"), dtype=np.float64)
+    layout = _model.ColumnLayout()
+    desc = _model.light_desc(light_model, layout.add_profile("light", 0, names[0]), lensed=True, slot=0, use_amp=use_amp)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out, dout = np.empty_like(x), np.empty((x.size, 9))
+    rc = lib().hm_light_jvp(C.byref(desc), _p(row), _p(x), _p(y), x.size, _p(out), _p(dout))
+    assert rc == 0, rc
+    return out, dout

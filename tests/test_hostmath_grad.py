@@ -1,0 +1,116 @@
+"""CPU: the dual-number profile arithmetic of the gradient path (jaxtronomy_b200/csrc/lsim_grad.cuh compiled for the
+host by tests/hostmath) against the oracle.
+
+The reference obtains these derivatives from jax autodiff, which cannot run here (no jax).  The pin is therefore
+(i) values: the dual's value part against the oracle restatement (itself pinned to the reference's fixtures) at the
+1e-10 bar, and (ii) tangents: 4th-order central finite differences of the oracle in every parameter, stated tolerance
+1e-8 of the largest |derivative| of the profile over the test points (the finite-difference error floor, not the
+kernel's: the two agree to ~1e-9 where the profile is smooth)."""
+
+import numpy as np
+import pytest
+
+from oracle import lens_profiles as olp
+from oracle import light_profiles as oli
+from tests import hostmath_util as hm
+
+FD_TOL = 1e-8
+
+
+def fd(fun, p0, i, h):
+    """4th-order central difference of fun(params) in parameter i."""
+    def at(s):
+        p = list(p0)
+        p[i] = p0[i] + s
+        return np.asarray(fun(p))
+    return (8.0 * (at(h) - at(-h)) - (at(2 * h) - at(-2 * h))) / (12.0 * h)
+
+
+def grid(n=9, lim=2.3):
+    g = np.linspace(-lim, lim, n)
+    x, y = np.meshgrid(g + 0.0137, g - 0.0291)
+    return x.ravel(), y.ravel()
+
+
+LENS_CASES = [
+    ("EPL", dict(theta_E=1.2, gamma=2.1, e1=0.21, e2=-0.13, center_x=0.05, center_y=-0.03), None),
+    ("EPL", dict(theta_E=0.9, gamma=1.7, e1=-0.02, e2=0.05, center_x=-0.1, center_y=0.2), None),  # nmax 10
+    ("EPL", dict(theta_E=1.4, gamma=2.4, e1=0.45, e2=0.3, center_x=0.0, center_y=0.0), None),  # f = 0.54: nmax 35
+    ("EPL", dict(theta_E=1.1, gamma=1.9, e1=-0.55, e2=0.5, center_x=0.0, center_y=0.1), None),  # f = 0.74: nmax 100
+    ("SIE", dict(theta_E=1.1, e1=0.15, e2=0.1, center_x=0.02, center_y=0.01), None),
+    ("SIE", dict(theta_E=1.1, e1=0.15, e2=0.1, center_x=0.02, center_y=0.01), {"NIE": False}),
+    ("NIE", dict(theta_E=1.3, e1=-0.2, e2=0.12, s_scale=0.3, center_x=0.0, center_y=0.04), None),
+    ("SIS", dict(theta_E=0.8, center_x=0.1, center_y=-0.2), None),
+    ("SHEAR", dict(gamma1=0.05, gamma2=-0.03, ra_0=0.1, dec_0=0.2), None),
+    ("CONVERGENCE", dict(kappa=0.1, ra_0=-0.1, dec_0=0.3), None),
+]
+
+
+@pytest.mark.parametrize("case", range(len(LENS_CASES)))
+def test_lens_dual_against_oracle(case):
+    name, kw, pk = LENS_CASES[case]
+    names = olp.PARAM_NAMES[name]
+    x, y = grid()
+    ax, ay, dax, day = hm.lens_jvp([name], [kw], x, y, [pk or {}])
+    p0 = [kw[n] for n in names]
+
+    def fun(p):
+        return olp.derivatives(name, x, y, profile_kwargs=pk, **dict(zip(names, p)))
+
+    rx, ry = fun(p0)
+    scale = max(np.abs(rx).max(), np.abs(ry).max())
+    assert np.allclose(ax, rx, rtol=1e-10, atol=1e-12 * scale)
+    assert np.allclose(ay, ry, rtol=1e-10, atol=1e-12 * scale)
+    for i, n in enumerate(names):
+        d = fd(fun, p0, i, 1e-4)
+        ref = np.stack([d[0], d[1]])
+        got = np.stack([dax[:, 0, i], day[:, 0, i]])
+        tol = FD_TOL * max(np.abs(ref).max(), 1e-3)
+        assert np.abs(got - ref).max() <= tol, (name, n, np.abs(got - ref).max(), tol)
+    for i in range(len(names), 6):
+        assert not dax[:, 0, i].any() and not day[:, 0, i].any()
+
+
+def test_lens_dual_sum_and_fixed_parameters():
+    x, y = grid(5)
+    models = ["EPL", "SHEAR", "SIS"]
+    kws = [LENS_CASES[0][1], LENS_CASES[8][1], LENS_CASES[7][1]]
+    ax, ay, dax, day = hm.lens_jvp(models, kws, x, y)
+    rx = sum(olp.derivatives(m, x, y, **k)[0] for m, k in zip(models, kws))
+    ry = sum(olp.derivatives(m, x, y, **k)[1] for m, k in zip(models, kws))
+    assert np.allclose(ax, rx, rtol=1e-10) and np.allclose(ay, ry, rtol=1e-10)
+    # every profile carries the derivatives of its own parameters only
+    _, _, d1, _ = hm.lens_jvp(["SHEAR"], [kws[1]], x, y)
+    assert np.array_equal(dax[:, 1], d1[:, 0])
+
+
+LIGHT_CASES = [
+    ("SERSIC_ELLIPSE", dict(amp=12.0, R_sersic=0.4, n_sersic=2.3, e1=0.2, e2=-0.1, center_x=0.05, center_y=-0.1)),
+    ("SERSIC_ELLIPSE", dict(amp=3.0, R_sersic=1.1, n_sersic=0.9, e1=-0.3, e2=0.25, center_x=0.0, center_y=0.3)),
+    ("SERSIC", dict(amp=5.0, R_sersic=0.7, n_sersic=3.6, center_x=-0.2, center_y=0.1)),
+    ("GAUSSIAN", dict(amp=20.0, sigma=0.6, center_x=0.1, center_y=0.0)),
+]
+
+
+@pytest.mark.parametrize("case", range(len(LIGHT_CASES)))
+def test_light_dual_against_oracle(case):
+    name, kw = LIGHT_CASES[case]
+    names = oli.PARAM_NAMES[name]
+    x, y = grid(9, 1.7)
+    func = oli._FUNCS[name]
+    val, dv = hm.light_jvp(name, kw, x, y)
+    p0 = [kw[n] for n in names]
+    ref = func(x, y, **kw)
+    assert np.allclose(val, ref, rtol=1e-10, atol=1e-12 * np.abs(ref).max())
+    for i, n in enumerate(names):
+        d = fd(lambda p: func(x, y, **dict(zip(names, p))), p0, i, 1e-4 * max(1.0, abs(p0[i])))
+        tol = FD_TOL * max(np.abs(d).max(), 1e-3)
+        assert np.abs(dv[:, 2 + i] - d).max() <= tol, (name, n, np.abs(dv[:, 2 + i] - d).max(), tol)
+    h = 2e-4
+    dx = (8 * (func(x + h, y, **kw) - func(x - h, y, **kw)) - (func(x + 2 * h, y, **kw) - func(x - 2 * h, y, **kw))) / (12 * h)
+    dy = (8 * (func(x, y + h, **kw) - func(x, y - h, **kw)) - (func(x, y + 2 * h, **kw) - func(x, y - 2 * h, **kw))) / (12 * h)
+    tol = FD_TOL * max(np.abs(dx).max(), np.abs(dy).max())
+    assert np.abs(dv[:, 0] - dx).max() <= tol and np.abs(dv[:, 1] - dy).max() <= tol
+    # amplitude solved linearly: amp = 1 and carries no tangent
+    val1, dv1 = hm.light_jvp(name, kw, x, y, use_amp=False)
+    assert np.allclose(val1 * kw["amp"], val, rtol=1e-13) and not dv1[:, 2].any()
