@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LSIM_ABI_VERSION 6
+#define LSIM_ABI_VERSION 7
 #define LSIM_MAX_PARAMS 12 /* largest param_names list on the path: EPL_MULTIPOLE_M1M3M4 */
 #define LSIM_MAX_SLOTS 8   /* output / linear-basis images per parameter set */
 
@@ -253,6 +253,27 @@ int lsim_resize_convolve(const lsim_plan* plan, const double* flux, int64_t n_im
  *   source_marg != 0 adds the marginalisation constant (de_lens.py:39-49) */
 int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear_solve, int source_marg,
               double* logl, double* amps, double* model, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Log-likelihood AND its gradient with respect to the parameter matrix: what
+ * jax.value_and_grad(LikelihoodModule.logL) gives the reference's gradient-descent sampler
+ * (Sampling/Samplers/optax.py:39,91-96 -> Sampling/likelihood.py:293-372 -> ImageLinearFit / ImageModel
+ * likelihood_data_given_model).  Forward pass as lsim_logl; then the adjoint of the likelihood (the WLS amplitude
+ * solve differentiated analytically), the transposed PSF convolution, and one dual-number pass over the supersampled
+ * grid in which every profile carries the derivatives with respect to its own parameters.  Clamps differentiate
+ * like jnp.maximum / jnp.where; the EPL hypergeometric function takes its value from the nmax schedule and its
+ * tangent from the fixed 100-term series in (t, z), as the reference's custom_jvp does (Profiles/epl.py:321-340).
+ *   logl       device [B]
+ *   grad       device [B, P]: d logl[b] / d params[b, :]; columns no profile reads are 0; with linear_solve the
+ *              amplitudes are functions of the other parameters (solved per set), not parameters
+ *   amps       device [B, n_slots] or NULL (linear_solve only)
+ * Scope: single plane; EPL, SIE, NIE, SIS, SHEAR, CONVERGENCE; SERSIC, SERSIC_ELLIPSE, GAUSSIAN; PSF none, pixel
+ * kernel (zero boundary) or separable Gaussian (edge-replicated); regular convolution; no point sources; fp64.
+ * Anything else: LSIM_E_UNSUPPORTED (never a finite-difference or CPU fallback).  Results are bit-reproducible
+ * run to run (fixed reduction order, no atomics).  Workspace: lsim_logl_grad_workspace_bytes (less is accepted,
+ * down to one set). */
+size_t lsim_logl_grad_workspace_bytes(const lsim_plan* plan, int64_t B);
+int lsim_logl_grad(const lsim_plan* plan, const double* params, int64_t B, int linear_solve, double* logl,
+                   double* grad, double* amps, void* workspace, size_t workspace_bytes, void* stream);
 
 /* One particle-swarm iteration AFTER the fitness evaluation, entirely on the device: the loop body
  * of lenstronomy's ParticleSwarmOptimizer._sample that jaxtronomy/Sampling/Samplers/pso.py:11-66 inherits, i.e.

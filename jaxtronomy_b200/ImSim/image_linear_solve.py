@@ -59,6 +59,12 @@ class ImageLinearFit(ImageModel):
             model = self.ImageNumerics.complete_frame(model)
         return logl, amps, model
 
+    def logL_linear_grad_batch(self, params):
+        """[B, P] -> (logL [B], d logL / d params [B, P], amplitudes [B, n_lin]) with the amplitudes solved per set
+        and differentiated through (jax.value_and_grad of ImageLinearFit.likelihood_data_given_model in the
+        reference; lsim_logl_grad).  The `amp` columns of the matrix are not read, their gradient is 0."""
+        return self._split_plan().logl_grad(params, linear_solve=True)
+
     def response_batch(self, params, unconvolved=False, num_images=None):
         """[B, P] -> amp=1 basis images [B, n_lin, ny, nx] (full frame): convolved extended components, then the
         point-source images."""

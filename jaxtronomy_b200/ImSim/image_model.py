@@ -322,6 +322,13 @@ class ImageModel(object):
         plan = self._joint_plan([True] * self.SourceModel._num_func, [True] * self.LensLightModel._num_func)
         return plan.logl(params, linear_solve=False, out=out)[0]
 
+    def logL_grad_batch(self, params):
+        """[B, P] -> (logL [B], d logL / d params [B, P]) as CUDA tensors: what jax.value_and_grad of
+        likelihood_data_given_model gives the reference (lsim_logl_grad; amplitudes are parameters here)."""
+        plan = self._joint_plan([True] * self.SourceModel._num_func, [True] * self.LensLightModel._num_func)
+        logl, grad, _ = plan.logl_grad(params, linear_solve=False)
+        return logl, grad
+
     def image_batch(self, params):
         """[B, P] -> model images [B, ny, nx] (CUDA tensor)."""
         plan = self._joint_plan([True] * self.SourceModel._num_func, [True] * self.LensLightModel._num_func)

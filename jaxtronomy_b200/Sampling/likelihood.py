@@ -66,6 +66,47 @@ class LikelihoodModule(object):
             return out
         return total
 
+    def logL_and_grad_batch_device(self, positions):
+        """positions: [B, n] CUDA tensor -> (logL [B], d logL / d positions [B, n]) on the current stream: the batched
+        counterpart of jax.value_and_grad(LikelihoodModule.logL) (Sampling/Samplers/optax.py:39).  The penalties are
+        constants (jnp.where branches without a parameter dependence): their gradient is 0."""
+        import torch
+
+        if self._source_marg:
+            raise ValueError("the gradient does not cover the source marginalisation constant")
+        total, gtotal = None, None
+        for plan in self._plans:
+            l, g, _ = plan.logl_grad(positions, linear_solve=self._linear_solver)
+            bad = torch.isnan(l)
+            l = torch.where(bad, torch.full_like(l, -(10.0**15)), l)
+            g = torch.where(bad[:, None], torch.zeros_like(g), g)
+            total = l if total is None else total + l
+            gtotal = g if gtotal is None else gtotal + g
+        if self._check_bounds:
+            if self._bounds_dev is None or self._bounds_dev[0].device != positions.device:
+                self._bounds_dev = (torch.as_tensor(self._lower_limit, device=positions.device),
+                                    torch.as_tensor(self._upper_limit, device=positions.device))
+            lo, hi = self._bounds_dev
+            hit = ((positions < lo) | (positions > hi)).any(dim=1)
+            total = torch.where(hit, torch.full_like(total, -(10.0**18)), total)
+            gtotal = torch.where(hit[:, None], torch.zeros_like(gtotal), gtotal)
+        return total, gtotal
+
+    def logL_and_grad_batch(self, positions):
+        """positions: [B, n] NumPy array -> (logL [B], grad [B, n]) NumPy arrays."""
+        import torch
+
+        pos = torch.as_tensor(np.ascontiguousarray(positions, dtype=np.float64)).to("cuda")
+        if pos.ndim != 2 or pos.shape[1] != self._n:
+            raise _lib.LsimError("positions must be [B, %d]" % self._n)
+        l, g = self.logL_and_grad_batch_device(pos)
+        return l.cpu().numpy(), g.cpu().numpy()
+
+    def value_and_grad(self, args):
+        """One parameter vector -> (logL, d logL / d args)."""
+        l, g = self.logL_and_grad_batch(np.asarray(args, dtype=float)[None, :])
+        return float(l[0]), g[0]
+
     def logL_batch(self, positions):
         """positions: [B, n] NumPy array -> logL NumPy array [B] (the `new_logL_func` of prepare_logL_func)."""
         import torch

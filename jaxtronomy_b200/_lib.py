@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("LSIM_LIB") or os.path.join(_HERE, "csrc", "liblsim.so
 
 MAX_PARAMS = 12
 MAX_SLOTS = 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 PRECISION_F64, PRECISION_F32 = 0, 1
 
 # enum mirrors (include/lsim.h)
@@ -82,6 +82,7 @@ SYMBOLS = [
     "lsim_plan_create", "lsim_plan_destroy", "lsim_ray_shoot", "lsim_surface_brightness", "lsim_workspace_bytes",
     "lsim_image", "lsim_resize_convolve", "lsim_logl", "lsim_abi_version", "lsim_strerror", "lsim_last_cuda_error", "lsim_launch_count",
     "lsim_measure_fp64_peak", "lsim_timing_enable", "lsim_timing_read", "lsim_pso_step", "lsim_psf_error_map",
+    "lsim_logl_grad", "lsim_logl_grad_workspace_bytes",
 ]
 
 
@@ -112,6 +113,10 @@ def load():
     lib.lsim_resize_convolve.restype = i32
     lib.lsim_logl.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, C.c_size_t, vp]
     lib.lsim_logl.restype = i32
+    lib.lsim_logl_grad_workspace_bytes.argtypes = [vp, i64]
+    lib.lsim_logl_grad_workspace_bytes.restype = C.c_size_t
+    lib.lsim_logl_grad.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.lsim_logl_grad.restype = i32
     lib.lsim_abi_version.restype = i32
     lib.lsim_strerror.argtypes = [i32]
     lib.lsim_strerror.restype = C.c_char_p
@@ -391,6 +396,27 @@ class Plan:
         return logl, amps, model
 
 
+def _plan_logl_grad(self, params, linear_solve=False):
+    """[B, P] -> (logl [B], grad [B, P] = d logl / d params, amps [B, n_slots] or None)   (lsim_logl_grad)"""
+    torch = _torch()
+    p = self._params(params)
+    B = p.shape[0]
+    logl = torch.empty(B, dtype=torch.float64, device=self.device)
+    grad = torch.empty((B, self.n_param_cols), dtype=torch.float64, device=self.device)
+    amps = torch.empty((B, self.n_slots), dtype=torch.float64, device=self.device) if linear_solve else None
+    need = int(self._lib.lsim_logl_grad_workspace_bytes(self._handle, max(int(B), 1)))
+    if need == 0:
+        check(-2)  # LSIM_E_UNSUPPORTED: the model is outside the gradient's scope (see include/lsim.h)
+    if self._ws is None or self._ws.numel() * 8 < need:
+        self._ws = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+    ws = self._ws
+    with torch.cuda.device(self.device):
+        check(self._lib.lsim_logl_grad(self._handle, p.data_ptr(), B, int(bool(linear_solve)), logl.data_ptr(),
+                                       grad.data_ptr(), amps.data_ptr() if amps is not None else None, ws.data_ptr(),
+                                       ws.numel() * 8, self._stream()))
+    return logl, grad, amps
+
+
 def _plan_psf_error_map(self, params):
     """[B, P] -> PSF error map sigma^2 [B, ny, nx] (lsim_psf_error_map)."""
     torch = _torch()
@@ -403,6 +429,7 @@ def _plan_psf_error_map(self, params):
 
 
 Plan.psf_error_map = _plan_psf_error_map
+Plan.logl_grad = _plan_logl_grad
 
 
 def pso_step(position, velocity, pbest_pos, pbest_fit, gbest_pos, gbest_fit, fitness, rnd, c1=1.193, c2=1.193):

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SOURCES = ["lsim_api.cu"]
 DEPS = ["lsim_api.cu", "lsim_kernels.cuh", "lsim_profiles.cuh", "lsim_math.cuh", "lsim_f32.cuh", "lsim_cse_tables.h",
-        "lsim_math_tables.h",
+        "lsim_math_tables.h", "lsim_grad.cuh", "lsim_grad_kernels.cuh",
         os.path.join(ROOT, "include", "lsim.h")]
 OUT = os.path.join(HERE, "liblsim.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",

@@ -12,6 +12,7 @@
 #include "../../include/lsim.h"
 #include "lsim_kernels.cuh"
 #include "lsim_f32.cuh"
+#include "lsim_grad_kernels.cuh"
 
 using namespace lsim;
 
@@ -131,6 +132,13 @@ struct lsim_plan {
   bool f32 = false;  // LSIM_PRECISION_F32: the image kernel runs in single precision
   size_t image_smem = 0;
   int n_sm = 148;
+  // gradient path (lsim_logl_grad): transposed PSF = the flipped kernel; grad_nl = lens profiles held in registers
+  bool grad_ok = false;
+  int grad_series = 0;
+  size_t grad_smem = 0;
+  const double* kernel_flip = nullptr;
+  const double* kernel_1d_flip = nullptr;
+  std::vector<double> kernel_flip_host;
 
   ~lsim_plan() {
     for (void* p : owned) cudaFree(p);
@@ -163,10 +171,15 @@ int upload_tables() {
 
 constexpr size_t kRaySmem = kLensChunk * sizeof(LensC) + (size_t)kMaxSeriesProfiles * kMaxSeries * sizeof(double);
 constexpr size_t kConvSmemMax = 200 * 1024;
+constexpr size_t kGradSmemMax = 200 * 1024;
 
 int configure_kernels() {
   LSIM_CUDA(cudaFuncSetAttribute(k_conv_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
   LSIM_CUDA(cudaFuncSetAttribute(k_conv_separable, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
   return LSIM_OK;
 }
 
@@ -358,6 +371,31 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
       }
     }
     if (D.K > 0) p->kernel_host.assign(d->kernel, d->kernel + (size_t)d->kernel_size * d->kernel_size);
+    {  // gradient path: scope check, transposed PSF
+      bool ok = !d->multi_plane && !d->supersampled_conv && d->n_points == 0 && !p->f32 &&
+                (d->conv_mode != LSIM_CONV_EDGE || d->kernel_separable);
+      int gs = 0;
+      for (int i = 0; i < d->n_lens; ++i) {
+        ok = ok && ad::lens_grad_supported(d->lens[i]);
+        gs += ad::lens_grad_has_series(d->lens[i]) ? 1 : 0;
+      }
+      for (int i = 0; i < d->n_light; ++i) ok = ok && ad::light_grad_supported(d->light[i]);
+      p->grad_series = gs;
+      p->grad_smem = (size_t)d->n_lens * sizeof(ad::GLens) + (size_t)gs * ad::kGradPool * sizeof(double) +
+                     (size_t)grad_entries(d->n_lens, d->n_light) * kGradBlock * sizeof(double);
+      p->grad_ok = ok && p->grad_smem <= kGradSmemMax;
+      if (p->grad_ok && D.K > 0) {
+        const size_t kk = (size_t)d->kernel_size * d->kernel_size;
+        p->kernel_flip_host.resize(kk);
+        for (size_t i = 0; i < kk; ++i) p->kernel_flip_host[i] = d->kernel[kk - 1 - i];
+        TRY(p->upload(p->kernel_flip_host.data(), kk, &p->kernel_flip));
+        if (d->kernel_separable) {
+          std::vector<double> f1(d->kernel_size);
+          for (int i = 0; i < d->kernel_size; ++i) f1[i] = d->kernel_1d[d->kernel_size - 1 - i];
+          TRY(p->upload(f1.data(), f1.size(), &p->kernel_1d_flip));
+        }
+      }
+    }
     if (D.ss_conv)
       p->kernel_hi_host.assign(d->kernel_hi, d->kernel_hi + (size_t)d->kernel_hi_size * d->kernel_hi_size);
     if (D.K > 0 && !d->kernel_separable)
@@ -938,9 +976,143 @@ int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, i
   return after_launch("k_likelihood");
 }
 
+// ---- gradient path ---------------------------------------------------------------------------------------------------
+int grad_max_tiles(const lsim_plan* plan) { return (plan->dev.n_eval + kGradBlock - 1) / kGradBlock; }
+
+size_t grad_per_set_bytes(const lsim_plan* plan) {
+  const PlanDev& D = plan->dev;
+  const size_t img = (size_t)D.nx * D.ny * D.n_slots;
+  return per_set_bytes(plan, true) + img * sizeof(double) +
+         (size_t)grad_max_tiles(plan) * grad_entries(D.n_lens, D.n_light) * sizeof(double);
+}
+
+template <int NS>
+int launch_like_adjoint_ns(const lsim_plan* plan, const double* conv, int64_t set0, int64_t n, int linear, double* logl,
+                           double* amps, double* abar, cudaStream_t st) {
+  Timed timed(kClsLike, st);
+  k_like_adjoint<NS><<<(unsigned)n, kBlock, 0, st>>>(plan->dev, conv, set0, linear, logl, amps, abar);
+  return after_launch("k_like_adjoint");
+}
+
+int launch_like_adjoint(const lsim_plan* plan, const double* conv, int64_t set0, int64_t n, int linear, double* logl,
+                        double* amps, double* abar, cudaStream_t st) {
+  const int ns = plan->dev.n_slots;
+  if (ns <= 1) return launch_like_adjoint_ns<1>(plan, conv, set0, n, linear, logl, amps, abar, st);
+  if (ns <= 2) return launch_like_adjoint_ns<2>(plan, conv, set0, n, linear, logl, amps, abar, st);
+  if (ns <= 4) return launch_like_adjoint_ns<4>(plan, conv, set0, n, linear, logl, amps, abar, st);
+  return launch_like_adjoint_ns<8>(plan, conv, set0, n, linear, logl, amps, abar, st);
+}
+
+// Ubar = image_scale * psf^T (*) Abar for n_images frames; `tmp` is a second frame buffer (edge mode only)
+int launch_conv_transposed(const lsim_plan* plan, const double* abar, double* tmp, double* ubar, int64_t n_images,
+                           cudaStream_t st) {
+  const PlanDev& D = plan->dev;
+  if (D.conv_mode == LSIM_CONV_ZERO) {
+    ConvSpec c{D.nx, D.ny, D.K, plan->kernel_flip, plan->kernel_1d_flip, LSIM_CONV_ZERO, D.image_scale, 0, nullptr,
+               plan->kernel_flip_host.data()};
+    return launch_conv_spec(c, abar, ubar, n_images, st);
+  }
+  const unsigned tiles = (unsigned)(((size_t)D.nx * D.ny + kBlock - 1) / kBlock);
+  for (int64_t i0 = 0; i0 < n_images; i0 += 65535) {
+    const int64_t ni = n_images - i0 < 65535 ? n_images - i0 : 65535;
+    const size_t off = (size_t)i0 * D.nx * D.ny;
+    for (int axis = 1; axis >= 0; --axis) {  // the forward pass convolves along x, then along y (either order is exact)
+      Timed timed(kClsConv, st);
+      k_conv_adj_edge<<<dim3(tiles, (unsigned)ni), kBlock, 0, st>>>(axis == 1 ? abar + off : tmp + off,
+                                                                    axis == 1 ? tmp + off : ubar + off, D.nx, D.ny, D.K,
+                                                                    D.kernel_1d, axis, axis == 1 ? 1.0 : D.image_scale);
+      int rc = after_launch("k_conv_adj_edge");
+      if (rc != LSIM_OK) return rc;
+    }
+  }
+  return LSIM_OK;
+}
+
+int launch_image_grad(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, const double* ubar,
+                      double wscale, double* partial, double* grad, cudaStream_t st) {
+  const PlanDev& D = plan->dev;
+  const int npix = D.n_eval;
+  const int max_tiles = grad_max_tiles(plan);
+  int64_t want = ((int64_t)plan->n_sm * 8 + n - 1) / n;
+  int tiles = (int)(want < 1 ? 1 : (want > max_tiles ? max_tiles : want));
+  if (tiles < 1) tiles = 1;
+  int ppt = (npix + tiles - 1) / tiles;
+  ppt = ((ppt + kGradBlock - 1) / kGradBlock) * kGradBlock;
+  if (ppt < kGradBlock) ppt = kGradBlock;
+  tiles = npix > 0 ? (npix + ppt - 1) / ppt : 1;
+  for (int64_t i0 = 0; i0 < n; i0 += 65535) {
+    const int64_t ni = n - i0 < 65535 ? n - i0 : 65535;
+    const dim3 grid((unsigned)tiles, (unsigned)ni);
+    const double* ub = ubar + (size_t)i0 * D.n_slots * D.nx * D.ny;
+    double* pt = partial + (size_t)i0 * tiles * grad_entries(D.n_lens, D.n_light);
+    {
+      Timed timed(kClsImage, st);
+      switch (D.n_lens <= 3 ? D.n_lens : 0) {
+        case 1: k_image_grad<1><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); break;
+        case 2: k_image_grad<2><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); break;
+        case 3: k_image_grad<3><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); break;
+        default: k_image_grad<0><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); break;
+      }
+      int rc = after_launch("k_image_grad");
+      if (rc != LSIM_OK) return rc;
+    }
+    Timed timed(kClsOther, st);
+    k_grad_reduce<<<(unsigned)ni, 128, grad_entries(D.n_lens, D.n_light) * sizeof(double), st>>>(D, pt, tiles, set0 + i0,
+                                                                                                 grad);
+    int rc = after_launch("k_grad_reduce");
+    if (rc != LSIM_OK) return rc;
+  }
+  return LSIM_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+size_t lsim_logl_grad_workspace_bytes(const lsim_plan* plan, int64_t B) {
+  if (!plan || !plan->has_image || !plan->grad_ok || B <= 0) return 0;
+  int64_t c = chunk_sets(plan);
+  if (B < c) c = B;
+  return grad_per_set_bytes(plan) * (size_t)c;
+}
+
+int lsim_logl_grad(const lsim_plan* plan, const double* params, int64_t B, int linear_solve, double* logl, double* grad,
+                   double* amps, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!plan || B < 0) return LSIM_E_INVALID;
+  if (!plan->has_image || !plan->has_data) return LSIM_E_NO_IMAGE;
+  if (!plan->grad_ok) return LSIM_E_UNSUPPORTED;
+  if (B == 0) return LSIM_OK;
+  if (!logl || !grad || (plan->dev.n_param_cols > 0 && !params)) return LSIM_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PlanDev& D = plan->dev;
+  const bool conv = D.conv_mode != LSIM_CONV_NONE;
+  int64_t chunk = (int64_t)(workspace_bytes / grad_per_set_bytes(plan));
+  if (!workspace || chunk < 1) return LSIM_E_WORKSPACE;
+  if (chunk > chunk_sets(plan)) chunk = chunk_sets(plan);
+  const size_t img = (size_t)D.nx * D.ny * D.n_slots;
+  // layout: the forward scratch of `chunk` sets [prepared constants | U | C], then Abar, then the per-CTA partials
+  double* ws = static_cast<double*>(workspace);
+  double* U = ws + (size_t)chunk * prefix_bytes(plan) / sizeof(double);
+  double* C = conv ? U + (size_t)chunk * img : U;
+  double* G = ws + (size_t)chunk * per_set_bytes(plan, true) / sizeof(double);
+  double* partial = G + (size_t)chunk * img;
+  for (int64_t s0 = 0; s0 < B; s0 += chunk) {
+    const int64_t n = B - s0 < chunk ? B - s0 : chunk;
+    int rc = run_chunk(plan, params, s0, n, chunk, ws, C, st);
+    if (rc != LSIM_OK) return rc;
+    rc = launch_like_adjoint(plan, C, s0, n, linear_solve, logl, amps, G, st);
+    if (rc != LSIM_OK) return rc;
+    const double* ubar = G;
+    if (conv) {
+      rc = launch_conv_transposed(plan, G, C, U, n * D.n_slots, st);
+      if (rc != LSIM_OK) return rc;
+      ubar = U;
+    }
+    rc = launch_image_grad(plan, params, s0, n, ubar, conv ? 1.0 : D.image_scale, partial, grad, st);
+    if (rc != LSIM_OK) return rc;
+  }
+  return LSIM_OK;
+}
 
 size_t lsim_workspace_bytes(const lsim_plan* plan, int64_t B) {
   if (!plan || !plan->has_image || B <= 0) return 0;

@@ -1,0 +1,382 @@
+// lsim_grad_kernels.cuh -- kernels of lsim_logl_grad: logL and d logL / d params for a batch of parameter sets
+// (the reference gets this from jax.value_and_grad, Sampling/Samplers/optax.py:39,91-96).
+//
+//   k_like_adjoint   logL, WLS amplitudes and Abar = d logL / d C (C: convolved, scaled basis images) per set
+//   k_conv_adj_edge  transposed edge-replicated separable convolution (GaussianConvolution) -- the zero-boundary
+//                    transposes run on the forward convolution kernels with the flipped PSF
+//   k_image_grad     sum over pixels of Ubar * dU/dp: dual-number evaluation of every profile per sub-pixel
+//                    (lsim_grad.cuh), per-thread partial sums in shared memory, one deterministic partial per CTA
+//   k_grad_reduce    partials -> grad[B, P] in a fixed order (bit-reproducible run to run; no atomics)
+#pragma once
+
+#include "lsim_grad.cuh"
+#include "lsim_kernels.cuh"
+
+namespace lsim {
+
+constexpr int kGradBlock = 256;
+constexpr int kGradLightStride = 7;  // entries per light component: its own parameters (SERSIC_ELLIPSE has 7)
+
+__host__ __device__ inline int grad_entries(int n_lens, int n_light) {
+  return ad::kLensN * n_lens + kGradLightStride * n_light;
+}
+
+__host__ __device__ inline int grad_lens_params(int type) {
+  switch (type) {
+    case LSIM_LENS_EPL: return 6;
+    case LSIM_LENS_SIE: return 5;
+    case LSIM_LENS_NIE: return 6;
+    case LSIM_LENS_SIS: return 3;
+    case LSIM_LENS_SHEAR: return 4;
+    case LSIM_LENS_CONVERGENCE: return 3;
+    default: return 0;
+  }
+}
+__host__ __device__ inline int grad_light_params(int type) {
+  switch (type) {
+    case LSIM_LIGHT_SERSIC: return 5;
+    case LSIM_LIGHT_SERSIC_ELLIPSE: return 7;
+    case LSIM_LIGHT_GAUSSIAN: return 4;
+    default: return 0;
+  }
+}
+
+// ---- k_like_adjoint --------------------------------------------------------------------------------------------------
+// One CTA per parameter set; same arithmetic as k_likelihood for logL and the amplitudes, then the adjoint.
+//   m = sum_k a_k A_k (linear: a = M^-1 R, M = A W A^T, R = A W d) or sum_k A_k;  r = m - d
+//   C_D(m) = noise_map^2 or max(m,0)/t_exp + sigma_bkg^2;  logL = -1/2 sum mask r^2 / C_D(m)
+//   g = d logL / d m = -mask (r / C_D - r^2 C_D'(m) / (2 C_D^2)),  C_D' = [m > 0] / t_exp (0 with a noise map)
+//   linear:  h = M^-1 (A g),  q = sum_k h_k A_k,  Abar_k = a_k (g - W q) - h_k W r      (W, g zero off the mask)
+//   else:    Abar_k = g
+// A set whose normal matrix fails the reference's stability gate (amplitudes forced to 0, de_lens.py:91-105) has a
+// constant model: Abar = 0.
+template <int NS>
+__global__ void __launch_bounds__(kBlock)
+k_like_adjoint(PlanDev P, const double* __restrict__ conv, int64_t set0, int linear, double* __restrict__ logl,
+               double* __restrict__ amps, double* __restrict__ abar) {
+  constexpr int NM = NS * (NS + 1) / 2;
+  __shared__ double scratch[(NM + NS + 1) * (kBlock / 32)];
+  __shared__ double s_amp[NS], s_h[NS], s_M[NS * NS];
+  __shared__ int s_ok;
+  const int64_t bl = blockIdx.x;
+  const int npix = P.nx * P.ny;
+  const int ns = P.n_slots;
+  const double* A = conv + bl * ns * (int64_t)npix;
+  double* out = abar + bl * ns * (int64_t)npix;
+
+  if (linear) {
+    double acc[NM + NS];
+#pragma unroll
+    for (int i = 0; i < NM + NS; ++i) acc[i] = 0.0;
+    for (int p = threadIdx.x; p < npix; p += kBlock) {
+      const bool use = !P.mask || P.mask[p];
+      if (!use) continue;
+      const double w = __ldg(P.w_data + p), d = __ldg(P.data + p);
+      double a[NS];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) a[k] = k < ns ? nan_to_num(A[(int64_t)k * npix + p]) : 0.0;
+      int m = 0;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+#pragma unroll
+        for (int j = i; j < NS; ++j) acc[m++] += w * a[i] * a[j];
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) acc[NM + i] += w * d * a[i];
+    }
+    block_sum(acc, scratch);
+    if (threadIdx.x == 0) {
+      double M2[NS * NS], Mw[NS * NS], R[NS], ev[NS];
+      int m = 0;
+      double Mf[NS * NS];
+      for (int i = 0; i < NS; ++i)
+        for (int j = i; j < NS; ++j) {
+          Mf[i * NS + j] = acc[m];
+          Mf[j * NS + i] = acc[m];
+          ++m;
+        }
+      for (int i = 0; i < ns; ++i)
+        for (int j = 0; j < ns; ++j) M2[i * ns + j] = Mf[i * NS + j];
+      for (int i = 0; i < ns * ns; ++i) {
+        Mw[i] = M2[i];
+        s_M[i] = M2[i];
+      }
+      for (int i = 0; i < ns; ++i) R[i] = acc[NM + i];
+      sym_eigenvalues(Mw, ns, ev);
+      double emax = 0.0, emin = HUGE_VAL;
+      for (int i = 0; i < ns; ++i) {
+        emax = fmax(emax, fabs(ev[i]));
+        emin = fmin(emin, fabs(ev[i]));
+      }
+      bool ok = (emax / emin) < 5.0 / DBL_EPSILON && lu_solve(M2, R, ns);
+      if (ok)
+        for (int i = 0; i < ns; ++i) ok = ok && (fabs(R[i]) <= DBL_MAX);
+      for (int i = 0; i < NS; ++i) s_amp[i] = (ok && i < ns) ? R[i] : 0.0;
+      s_ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+  }
+
+  // model, residual and d logL / d model of one pixel
+  auto pixel = [&](int p, bool use, double (&a)[NS], double& r, double& g, double& chi) {
+    double m = 0.0;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      a[k] = 0.0;
+      if (k < ns) {
+        if (linear) {
+          if (use) {
+            a[k] = nan_to_num(A[(int64_t)k * npix + p]);
+            m += s_amp[k] * a[k];
+          }
+        } else {
+          a[k] = A[(int64_t)k * npix + p];
+          m += a[k];
+        }
+      }
+    }
+    r = 0.0;
+    g = 0.0;
+    chi = 0.0;
+    if (use) {
+      double cd, cdp = 0.0;
+      if (P.noise_map2) {
+        cd = __ldg(P.noise_map2 + p);
+      } else {
+        const double ie = __ldg(P.inv_exposure + p);
+        cd = fma(fmax(m, 0.0), ie, P.bkg2);
+        cdp = m > 0.0 ? ie : 0.0;
+      }
+      r = m - __ldg(P.data + p);
+      const double rc = r / cd;
+      chi = r * rc;
+      g = -(rc - 0.5 * rc * rc * cdp);
+    }
+  };
+
+  double red[NS + 1];
+#pragma unroll
+  for (int i = 0; i < NS + 1; ++i) red[i] = 0.0;
+  for (int p = threadIdx.x; p < npix; p += kBlock) {
+    const bool use = !P.mask || P.mask[p];
+    double a[NS], r, g, chi;
+    pixel(p, use, a, r, g, chi);
+    red[0] += chi;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) red[1 + k] += g * a[k];
+  }
+  block_sum(red, scratch);
+  if (threadIdx.x == 0) {
+    logl[set0 + bl] = -red[0] / 2 + P.logl_offset;
+    if (amps && linear)
+      for (int k = 0; k < ns; ++k) amps[(set0 + bl) * ns + k] = s_amp[k];
+    if (linear) {
+      double M2[NS * NS], c[NS];
+      for (int i = 0; i < ns * ns; ++i) M2[i] = s_M[i];
+      for (int i = 0; i < ns; ++i) c[i] = red[1 + i];
+      const bool ok = s_ok && lu_solve(M2, c, ns);
+      for (int i = 0; i < NS; ++i) s_h[i] = (ok && i < ns) ? c[i] : 0.0;
+    }
+  }
+  __syncthreads();
+  const bool dead = linear && !s_ok;
+  for (int p = threadIdx.x; p < npix; p += kBlock) {
+    const bool use = !P.mask || P.mask[p];
+    double a[NS], r, g, chi;
+    pixel(p, use, a, r, g, chi);
+    if (linear) {
+      const double w = use ? __ldg(P.w_data + p) : 0.0;
+      double q = 0.0;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) q += s_h[k] * a[k];
+      const double gq = g - w * q, wr = w * r;
+#pragma unroll
+      for (int k = 0; k < NS; ++k)
+        if (k < ns) out[(int64_t)k * npix + p] = dead ? 0.0 : fma(s_amp[k], gq, -(s_h[k] * wr));
+    } else {
+#pragma unroll
+      for (int k = 0; k < NS; ++k)
+        if (k < ns) out[(int64_t)k * npix + p] = g;
+    }
+  }
+}
+
+// ---- k_conv_adj_edge ----------------------------------------------------------------------------------------------
+// Transpose of ONE 1-D pass of the edge-replicated separable convolution
+//   out[o] = sum_d k1[d + R] in[clamp(o - d)],  d = -R..R        (GaussianConvolution, convolution.py:216-236)
+// along x (axis 0) or y (axis 1):  adj[i] = sum_o out_bar[o] [clamp(o - d) == i] k1[d + R].
+// Interior i collects o = i + d; the two edge pixels also collect every tap that was clamped onto them.
+__global__ void __launch_bounds__(kBlock)
+k_conv_adj_edge(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
+                const double* __restrict__ k1, int axis, double scale) {
+  const int R = (K - 1) / 2;
+  const int64_t frame = (int64_t)blockIdx.y * nx * ny;
+  const int n = axis == 0 ? nx : ny, stride = axis == 0 ? 1 : nx;
+  for (int idx = blockIdx.x * kBlock + threadIdx.x; idx < nx * ny; idx += gridDim.x * kBlock) {
+    const int y = idx / nx, x = idx - y * nx;
+    const int i = axis == 0 ? x : y;
+    const double* line = in + frame + (axis == 0 ? (int64_t)y * nx : (int64_t)x);
+    double acc = 0.0;
+    for (int o = max(0, i - R); o <= min(n - 1, i + R); ++o) {  // unclamped taps: o - d = i
+      acc = fma(k1[o - i + R], line[(int64_t)o * stride], acc);
+    }
+    if (i == 0) {  // taps with o - d < 0, i.e. d > o
+      for (int o = 0; o < min(n, R); ++o) {
+        double t = 0.0;
+        for (int d = o + 1; d <= R; ++d) t += k1[d + R];
+        acc = fma(t, line[(int64_t)o * stride], acc);
+      }
+    }
+    if (i == n - 1) {  // taps with o - d > n - 1, i.e. d < o - (n - 1)
+      for (int o = max(0, n - R); o < n; ++o) {
+        double t = 0.0;
+        for (int d = -R; d < o - (n - 1); ++d) t += k1[d + R];
+        acc = fma(t, line[(int64_t)o * stride], acc);
+      }
+    }
+    out[frame + idx] = acc * scale;
+  }
+}
+
+// ---- k_image_grad ----------------------------------------------------------------------------------------------------
+// grid (tiles, sets).  shared memory: GLens[n_lens] | coefficient pool [n_series][kGradPool] | acc[E][kGradBlock].
+// NL > 0: the model has exactly NL lens profiles; their dual deflections stay in registers between the ray shooting
+// and the lens-parameter update.  NL == 0: any number of profiles, each evaluated twice (value, then tangents).
+template <int NL>
+__global__ void __launch_bounds__(kGradBlock)
+k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, int n_series,
+             const double* __restrict__ ubar, double wscale, double* __restrict__ partial) {
+  using namespace ad;
+  extern __shared__ double smem[];
+  const int64_t bl = blockIdx.y;
+  const double* row = params + (set0 + bl) * P.n_param_cols;
+  GLens* L = reinterpret_cast<GLens*>(smem);
+  double* pool = reinterpret_cast<double*>(L + P.n_lens);
+  double* acc = pool + (size_t)n_series * kGradPool;
+  const int E = grad_entries(P.n_lens, P.n_light);
+  for (int i = threadIdx.x; i < P.n_lens; i += kGradBlock) {
+    int off = 0;
+    for (int j = 0; j < i; ++j) off += lens_grad_has_series(P.lens[j]) ? 1 : 0;
+    L[i].coef_off = off * kGradPool;
+    lens_prepare_d(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries);
+  }
+  double* my = acc + threadIdx.x;
+  for (int e = 0; e < E; ++e) my[e * kGradBlock] = 0.0;
+  __syncthreads();
+
+  const int npix = P.nx * P.ny;
+  const int ss = P.ss;
+  const int64_t sub_stride = (int64_t)P.nx * ss;
+  const double wsub = wscale / ((double)ss * ss);
+  const double as = P.ray.alpha_scaling;
+  // flux_evaluate_indexes: pixels outside the list have zero flux whatever the parameters are
+  const int q_end = min(P.eval_list ? P.n_eval : npix, (int)(blockIdx.x + 1) * ppt);
+  for (int q = blockIdx.x * ppt + threadIdx.x; q < q_end; q += kGradBlock) {
+    const int p = P.eval_list ? __ldg(P.eval_list + q) : q;
+    const int py = p / P.nx, px = p - py * P.nx;
+    for (int i = 0; i < ss; ++i) {
+      const int64_t base = ((int64_t)py * ss + i) * sub_stride + (int64_t)px * ss;
+      for (int j = 0; j < ss; ++j) {
+        const double x = __ldg(P.x_sub + base + j), y = __ldg(P.y_sub + base + j);
+        double ax = 0.0, ay = 0.0;
+        LD fx[NL > 0 ? NL : 1], fy[NL > 0 ? NL : 1];
+        if (NL > 0) {
+#pragma unroll
+          for (int l = 0; l < NL; ++l) {
+            lens_eval_d(L[l], pool, x, y, fx[l], fy[l]);
+            ax += fx[l].v;
+            ay += fy[l].v;
+          }
+        } else {
+          for (int l = 0; l < P.n_lens; ++l) {
+            lens_eval_d(L[l], pool, x, y, fx[0], fy[0]);
+            ax += fx[0].v;
+            ay += fy[0].v;
+          }
+        }
+        const double bx = x - ax * as, by = y - ay * as;
+        double vx = 0.0, vy = 0.0;
+        double* lacc = my + (size_t)kLensN * P.n_lens * kGradBlock;
+        for (int g = 0; g < P.n_light; ++g) {
+          const lsim_light_desc& d = P.light[g];
+          if (d.slot < 0) continue;
+          const double w = __ldg(ubar + (bl * P.n_slots + d.slot) * (int64_t)npix + p) * wsub;
+          const GD I = d.lensed ? light_eval_d(d, row, var<kLightN>(bx, 0), var<kLightN>(by, 1))
+                                : light_eval_d(d, row, cst<kLightN>(x), cst<kLightN>(y));
+          if (d.lensed) {
+            vx = fma(w, I.d[0], vx);
+            vy = fma(w, I.d[1], vy);
+          }
+          double* e = lacc + (size_t)g * kGradLightStride * kGradBlock;
+#pragma unroll
+          for (int k = 0; k < kGradLightStride; ++k) e[k * kGradBlock] = fma(w, I.d[2 + k], e[k * kGradBlock]);
+        }
+        vx *= -as;  // d beta / d p = -alpha_scaling d alpha / d p
+        vy *= -as;
+        if (NL > 0) {
+#pragma unroll
+          for (int l = 0; l < NL; ++l) {
+            double* e = my + (size_t)l * kLensN * kGradBlock;
+#pragma unroll
+            for (int k = 0; k < kLensN; ++k)
+              e[k * kGradBlock] = fma(vx, fx[l].d[k], fma(vy, fy[l].d[k], e[k * kGradBlock]));
+          }
+        } else if (vx != 0.0 || vy != 0.0) {
+          for (int l = 0; l < P.n_lens; ++l) {
+            lens_eval_d(L[l], pool, x, y, fx[0], fy[0]);
+            double* e = my + (size_t)l * kLensN * kGradBlock;
+#pragma unroll
+            for (int k = 0; k < kLensN; ++k)
+              e[k * kGradBlock] = fma(vx, fx[0].d[k], fma(vy, fy[0].d[k], e[k * kGradBlock]));
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // one partial per entry and CTA: warp w reduces entries w, w + 8, ... in a fixed order
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* dst = partial + (bl * gridDim.x + blockIdx.x) * (int64_t)E;
+  for (int e = wid; e < E; e += kGradBlock / 32) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < kGradBlock / 32; ++j) s += acc[e * kGradBlock + lane + 32 * j];
+    s = warp_sum(s);
+    if (lane == 0) dst[e] = s;
+  }
+}
+
+// ---- k_grad_reduce ------------------------------------------------------------------------------------------------
+// One CTA per set: entry sums over the tiles (fixed order), then the entries of each parameter column.
+__global__ void __launch_bounds__(128)
+k_grad_reduce(PlanDev P, const double* __restrict__ partial, int tiles, int64_t set0, double* __restrict__ grad) {
+  extern __shared__ double s_e[];
+  const int64_t bl = blockIdx.x;
+  const int E = grad_entries(P.n_lens, P.n_light);
+  const double* src = partial + bl * tiles * (int64_t)E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    double s = 0.0;
+    for (int t = 0; t < tiles; ++t) s += src[(int64_t)t * E + e];
+    s_e[e] = s;
+  }
+  __syncthreads();
+  double* g = grad + (set0 + bl) * P.n_param_cols;
+  for (int c = threadIdx.x; c < P.n_param_cols; c += blockDim.x) {
+    double s = 0.0;
+    for (int l = 0; l < P.n_lens; ++l) {
+      const int np = grad_lens_params(P.lens[l].type);
+      for (int k = 0; k < np; ++k)
+        if (P.lens[l].col[k] == c) s += s_e[l * ad::kLensN + k];
+    }
+    for (int gi = 0; gi < P.n_light; ++gi) {
+      const lsim_light_desc& d = P.light[gi];
+      if (d.slot < 0) continue;
+      const int np = grad_light_params(d.type);
+      for (int k = 0; k < np; ++k)
+        if (d.col[k] == c && !(k == 0 && !d.use_amp)) s += s_e[ad::kLensN * P.n_lens + gi * kGradLightStride + k];
+    }
+    g[c] = s;
+  }
+}
+
+}  // namespace lsim

@@ -1,0 +1,258 @@
+"""GPU: lsim_logl_grad (log-likelihood and its gradient w.r.t. the parameter matrix) through the
+C ABI against the NumPy oracle.
+
+The reference obtains the gradient from jax autodiff, which cannot run in this environment, so the pin is:
+  * value: logL / amplitudes of the gradient call == the forward call (same kernels) and the oracle at the 1e-10 bar;
+  * gradient: 4th-order central finite differences of the ORACLE's log-likelihood in every parameter.  Stated
+    tolerance: |g - g_fd| <= 1e-6 max|g| (the finite-difference floor of a chi^2 of ~1e3..1e4 terms; the dual-number
+    arithmetic itself agrees with the oracle to ~1e-10 per profile, tests/test_hostmath_grad.py);
+  * at the headline size (180 x 180, ss 3, 21 x 21 PSF): central differences of the GPU forward path itself."""
+
+import numpy as np
+import pytest
+
+from tests.golden_io import load
+
+pytestmark = pytest.mark.gpu
+
+IMSIM = load("imsim.npz")
+GRAD_TOL = 1e-6
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_loaded():
+    from jaxtronomy_b200 import _lib
+
+    _lib.load()
+    import torch
+
+    assert torch.cuda.is_available()
+    before = _lib.launch_count()
+    yield
+    assert _lib.launch_count() > before
+
+
+def _base_row(c, names):
+    kws = {"lens": c.meta["kwargs_lens"], "source": c.meta["kwargs_source"], "lens_light": c.meta["kwargs_lens_light"]}
+    return np.array([kws[comp][i][n] for comp, i, n in names], dtype=float)
+
+
+def _row_to_kwargs(c, names, row):
+    kws = {"lens": [dict() for _ in c.meta["kwargs_lens"]], "source": [dict() for _ in c.meta["kwargs_source"]],
+           "lens_light": [dict() for _ in c.meta["kwargs_lens_light"]]}
+    for j, (comp, i, n) in enumerate(names):
+        kws[comp][i][n] = row[j]
+    return kws["lens"], kws["source"], kws["lens_light"]
+
+
+def _oracle_logl(om, c, names, row, linear):
+    kl, ks, kll = _row_to_kwargs(c, names, row)
+    if linear:
+        return om.likelihood_data_given_model_linear(kl, ks, kll)[0]
+    return om.likelihood_data_given_model(kl, ks, kll)
+
+
+def _fd(fun, row, j, h):
+    def at(s):
+        r = row.copy()
+        r[j] += s
+        return fun(r)
+    return (8.0 * (at(h) - at(-h)) - (at(2 * h) - at(-2 * h))) / (12.0 * h)
+
+
+def _perturbed(base, names, rng, B):
+    mat = np.tile(base, (B, 1))
+    for j, (comp, i, n) in enumerate(names):
+        if n in ("theta_E", "gamma", "R_sersic", "n_sersic"):
+            mat[1:, j] *= 1 + rng.normal(0, 0.02, B - 1)
+        elif n in ("e1", "e2", "gamma1", "gamma2", "center_x", "center_y"):
+            mat[1:, j] += rng.normal(0, 0.01, B - 1)
+    return mat
+
+
+GRAD_CASES = ["headline_epl_shear_pixel", "c1_sie_shear_gauss", "linear_sis_3comp", "subframe_epl_shear"]
+
+
+@pytest.mark.parametrize("linear", [True, False])
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_gradient_matches_oracle_finite_differences(name, linear):
+    import torch
+
+    from tests.test_gpu_parity import build_image_model
+    from tests.test_oracle_golden import build_oracle_image_model
+
+    c = IMSIM[name]
+    lin = build_image_model(c, linear=True)
+    om = build_oracle_image_model(c)
+    names = lin.param_names
+    rng = np.random.default_rng(5)
+    B = 3
+    mat = _perturbed(_base_row(c, names), names, rng, B)
+    t = torch.as_tensor(mat, device="cuda")
+    if linear:
+        logl, grad, amps = lin.logL_linear_grad_batch(t)
+        logl_f, amps_f, _ = lin.logL_linear_batch(t)
+        assert torch.equal(amps, amps_f)
+    else:
+        logl, grad = lin.logL_grad_batch(t)
+        logl_f = lin.logL_batch(t)
+    # the value of the gradient call is the forward path's value
+    np.testing.assert_allclose(logl.cpu().numpy(), logl_f.cpu().numpy(), rtol=1e-13)
+    logl, grad = logl.cpu().numpy(), grad.cpu().numpy()
+    assert np.all(np.isfinite(grad))
+    worst = 0.0
+    for b in (0, B - 1):
+        row = mat[b]
+        ol = _oracle_logl(om, c, names, row, linear)
+        assert abs(logl[b] - ol) <= 1e-9 * abs(ol), (b, logl[b], ol)
+        ref = np.zeros(len(names))
+        for j, (comp, i, n) in enumerate(names):
+            if linear and n == "amp":
+                assert grad[b, j] == 0.0  # solved per set, not a parameter
+                continue
+            h = 1e-4 * max(1.0, abs(row[j]))
+            ref[j] = _fd(lambda r: _oracle_logl(om, c, names, r, linear), row, j, h)
+        scale = np.abs(ref).max()
+        err = np.abs(grad[b] - ref).max() / scale
+        worst = max(worst, err)
+        assert err <= GRAD_TOL, (name, linear, b, err, grad[b], ref)
+    print("gradient vs oracle finite differences: %s linear=%s worst relative error %.2e" % (name, linear, worst))
+
+
+def test_gradient_is_reproducible_and_chunked_batches_agree():
+    import torch
+
+    from tests.test_gpu_parity import build_image_model
+
+    c = IMSIM["headline_epl_shear_pixel"]
+    lin = build_image_model(c, linear=True)
+    names = lin.param_names
+    mat = _perturbed(_base_row(c, names), names, np.random.default_rng(9), 37)
+    t = torch.as_tensor(mat, device="cuda")
+    l1, g1, a1 = lin.logL_linear_grad_batch(t)
+    l2, g2, a2 = lin.logL_linear_grad_batch(t)
+    assert torch.equal(l1, l2) and torch.equal(g1, g2) and torch.equal(a1, a2)  # fixed reduction order, no atomics
+    # a set's gradient does not depend on its position in the batch up to the tile split (different CTA partition)
+    l3, g3, _ = lin.logL_linear_grad_batch(t[5:6])
+    torch.testing.assert_close(g3[0], g1[5], rtol=1e-11, atol=1e-9 * float(g1[5].abs().max()))
+    assert lin.logL_linear_grad_batch(t[:0])[1].shape == (0, len(names))
+
+
+def test_gradient_with_likelihood_mask_and_noise_map():
+    """Masked pixels carry no gradient; a noise map makes C_D independent of the model."""
+    import torch
+
+    from bench import build_headline
+
+    cfg = build_headline(num_pix=48, ss=2, kernel_size=9, n_sets=4, seed=11)
+    from jaxtronomy_b200.Data.imaging_data import ImageData
+    from jaxtronomy_b200.Data.psf import PSF
+    from jaxtronomy_b200.ImSim.image_linear_solve import ImageLinearFit
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+    from jaxtronomy_b200.LightModel.light_model import LightModel
+
+    st = cfg["static"]
+    rng = np.random.default_rng(3)
+    mask = (rng.uniform(size=(48, 48)) > 0.3).astype(float)
+    kd = dict(st["kwargs_data"])
+    kd.pop("exposure_time")
+    kd.pop("background_rms")
+    data = ImageData(image_data=cfg["data_image"], noise_map=0.05 + 0.02 * rng.uniform(size=(48, 48)), **kd)
+    lin = ImageLinearFit(data, PSF(psf_type="PIXEL", kernel_point_source=st["kernel"]), LensModel(["EPL", "SHEAR"]),
+                         LightModel(["SERSIC_ELLIPSE"]), LightModel([]),
+                         kwargs_numerics=dict(supersampling_factor=2), likelihood_mask=mask)
+    t = cfg["params"].clone()
+    t[:, 10] = 15.0
+    for linear in (True, False):
+        def value(m):
+            return (lin.logL_linear_batch(m)[0] if linear else lin.logL_batch(m)).cpu().numpy()
+        grad = (lin.logL_linear_grad_batch(t)[1] if linear else lin.logL_grad_batch(t)[1]).cpu().numpy()
+        for j in (0, 1, 2, 5, 6, 11, 12, 13, 15) + (() if linear else (10,)):
+            h = 1e-4
+            d = torch.zeros_like(t)
+            d[:, j] = h
+            fd = (8 * (value(t + d) - value(t - d)) - (value(t + 2 * d) - value(t - 2 * d))) / (12 * h)
+            scale = np.abs(grad).max(axis=1)
+            assert np.all(np.abs(grad[:, j] - fd) <= GRAD_TOL * scale), (linear, j, grad[:, j], fd)
+
+
+def test_headline_size_gradient_against_gpu_central_differences():
+    """180 x 180, ss 3, 21 x 21 PSF: the gradient against central differences of the forward path on the same device."""
+    import torch
+
+    from bench import build_headline
+
+    cfg = build_headline(n_sets=8, seed=21)
+    lin, t = cfg["model"], cfg["params"]
+    logl, grad, amps = lin.logL_linear_grad_batch(t)
+    logl_f, amps_f, _ = lin.logL_linear_batch(t)
+    assert torch.equal(amps, amps_f)
+    np.testing.assert_allclose(logl.cpu().numpy(), logl_f.cpu().numpy(), rtol=1e-13)
+    grad = grad.cpu().numpy()
+    assert np.all(np.isfinite(grad)) and not grad[:, 10].any()  # amp is solved per set, not a parameter
+    scale = np.abs(grad).max(axis=1)
+    worst = 0.0
+    for j in [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 12, 13, 14, 15, 16]:
+        h = 1e-4
+        d = torch.zeros_like(t)
+        d[:, j] = h
+        v = lambda m: lin.logL_linear_batch(m)[0].cpu().numpy()
+        fd = (8 * (v(t + d) - v(t - d)) - (v(t + 2 * d) - v(t - 2 * d))) / (12 * h)
+        err = np.abs(grad[:, j] - fd) / scale
+        worst = max(worst, err.max())
+        assert np.all(err <= GRAD_TOL), (j, grad[:, j], fd)
+    print("headline-size gradient vs central differences of the forward path: worst relative error %.2e" % worst)
+
+
+def test_models_outside_the_gradient_scope_are_refused():
+    import torch
+
+    from jaxtronomy_b200 import _lib
+    from tests.test_gpu_parity import build_image_model
+
+    for name in ("c3_multipole_noise_map", "ss_conv_sie_shear"):
+        c = IMSIM[name]
+        lin = build_image_model(c, linear=True)
+        row = _base_row(c, lin.param_names)
+        with pytest.raises(_lib.LsimError):
+            lin.logL_linear_grad_batch(torch.as_tensor(row[None, :], device="cuda"))
+
+
+def test_gradient_descent_sampler_recovers_the_truth():
+    """OptaxMinimizer (interface of jaxtronomy/Sampling/Samplers/optax.py) on a 48 x 48 EPL + SHEAR + SERSIC_ELLIPSE
+    fit: every chain starts a few per cent off and must end at a log-likelihood at least as good as the truth's."""
+    import torch
+
+    from bench import TRUTH, build_headline
+    from jaxtronomy_b200.Sampling.likelihood import LikelihoodModule
+    from jaxtronomy_b200.Sampling.parameters import Param
+    from jaxtronomy_b200.Sampling.Samplers.optax import OptaxMinimizer
+
+    cfg = build_headline(num_pix=48, ss=2, kernel_size=9, n_sets=1, seed=1)
+    lin = cfg["model"]
+    kwargs_model = dict(lens_model_list=["EPL", "SHEAR"], source_light_model_list=["SERSIC_ELLIPSE"])
+    fixed_lens = [{}, {"ra_0": 0.0, "dec_0": 0.0}]
+    param = Param(kwargs_model, kwargs_fixed_lens=fixed_lens, kwargs_fixed_source=[{}], linear_solver=True)
+    like = LikelihoodModule(lin, param, check_bounds=True, linear_solver=True)
+    from bench import row_to_kwargs
+
+    kl, ks, _ = row_to_kwargs(TRUTH)
+    truth = np.asarray(param.kwargs2args(kwargs_lens=kl, kwargs_source=ks))
+    l_truth, g_truth = like.value_and_grad(truth)
+    assert np.isfinite(l_truth) and np.all(np.isfinite(g_truth)) and len(g_truth) == len(truth)
+    # gradient of the module == central differences of its own logL
+    for j in range(len(truth)):
+        h = 1e-5
+        e = np.zeros_like(truth)
+        e[j] = h
+        fd = (like.logL(truth + e) - like.logL(truth - e)) / (2 * h)
+        assert abs(g_truth[j] - fd) <= 1e-5 * np.abs(g_truth).max() + 1e-6, (j, g_truth[j], fd)
+    lo, hi = param.param_limits()
+    sigma = 0.02 * np.maximum(np.abs(truth), 0.05)
+    opt = OptaxMinimizer(like, truth, sigma, np.asarray(lo), np.asarray(hi), maxiter=200)
+    best = opt.run(num_chains=4, tol=1e-7, rng_seed=0)
+    l_best = like.logL(best)
+    assert l_best >= l_truth - 1e-6, (l_best, l_truth)
+    assert np.all(opt.final_logL >= l_truth - 0.5), opt.final_logL
+    print("gradient descent: logL(truth) %.4f -> best %.4f in %s iterations (%d batched evaluations)"
+          % (l_truth, l_best, opt.num_iterations, opt.num_evaluations))
