@@ -381,8 +381,7 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
       }
       for (int i = 0; i < d->n_light; ++i) ok = ok && ad::light_grad_supported(d->light[i]);
       p->grad_series = gs;
-      p->grad_smem = (size_t)d->n_lens * sizeof(ad::GLens) + (size_t)gs * ad::kGradPool * sizeof(double) +
-                     (size_t)grad_entries(d->n_lens, d->n_light) * kGradBlock * sizeof(double);
+      p->grad_smem = grad_smem_bytes(d->n_lens, d->n_light, gs);
       p->grad_ok = ok && p->grad_smem <= kGradSmemMax;
       if (p->grad_ok && D.K > 0) {
         const size_t kk = (size_t)d->kernel_size * d->kernel_size;

@@ -35,7 +35,7 @@ namespace ad {
 constexpr int kLensN = 6;    // tangents carried by a lens profile: its own parameters (param_names order)
 constexpr int kLightN = 9;   // light profile: d/d(x), d/d(y) of the evaluation point, then its own parameters
 constexpr int kTanTerms = 100;                      // hyp2f1_slow, epl.py:283
-constexpr int kGradPool = kMaxSeries + kTanTerms;   // per EPL-family profile: F_n [kMaxSeries], dF_n/dt [kTanTerms]
+constexpr int kGradPool = kMaxSeries + 2 * kTanTerms;  // per EPL-family profile: F_n [kMaxSeries], dF_n/dt and (n+1) F_{n+1} [kTanTerms each]
 
 template <int N>
 struct Dual {
@@ -221,7 +221,9 @@ struct GLens {
   int32_t n_val;     // EPL: terms of the value series (nmax schedule), n_tan: terms of the tangent series (<= 100)
   int32_t n_tan;
   int32_t coef_off;  // EPL: offset of this profile's coefficients in the pool
-  LD c[8];
+  LD c[8];           // dual-number evaluation (lens_eval_d)
+  LD p[6];           // EPL hand-derived path: theta_E, t, phi, q, center_x, center_y with their parameter derivatives
+  double k[12];      // EPL hand-derived path: cos phi, sin phi, f, ln b, t log2 b, 2/(1+q), dlnA/dq, df/dq
 };
 
 template <int N>
@@ -253,6 +255,23 @@ LSIM_HD void epl_prepare_d(GLens& L, double* F, double* dF, const LD& theta_E, c
   L.c[5] = theta_E * dsqrt(q);
   L.c[6] = gamma - 1.0;
   const double f = (1.0 - q.v) / (1.0 + q.v);
+  {
+    const double t = gamma.v - 1.0, b = L.c[5].v;
+    L.p[0] = theta_E;
+    L.p[1] = gamma - 1.0;
+    L.p[2] = phi;
+    L.p[3] = q;
+    L.p[4] = cx;
+    L.p[5] = cy;
+    L.k[0] = L.c[2].v;
+    L.k[1] = L.c[3].v;
+    L.k[2] = f;
+    L.k[3] = log(b);
+    L.k[4] = t * log2(b);
+    L.k[5] = 2.0 / (1.0 + q.v);
+    L.k[6] = -1.0 / (1.0 + q.v) + t / (2.0 * q.v);      // d ln A / d q at fixed theta_E, A = 2 b^t / (1+q), b = theta_E sqrt(q)
+    L.k[7] = -2.0 / ((1.0 + q.v) * (1.0 + q.v));        // d f / d q
+  }
   const double wmax = f / (2.0 - f);
   const int nmax = epl_nmax(f);
   int cut = 2;  // first n with n wmax^(n-1) < 1e-22 (beyond it nothing contributes)
@@ -285,6 +304,10 @@ LSIM_HD void epl_prepare_d(GLens& L, double* F, double* dF, const LD& theta_E, c
     ppF = pF;
     pF = nF;
   }
+  // coefficients of dS/dw = sum_m (m+1) F_{m+1} w^m, m < n_tan - 1 (stored behind dF)
+  double* G = dF + kTanTerms;
+  for (int m = 0; m + 1 < n_tan; ++m) G[m] = (m + 1.0) * F[m + 1];
+  G[n_tan - 1] = 0.0;
 }
 
 // EPL deflection at one image-plane point with its derivatives w.r.t. the profile's own parameters
@@ -523,6 +546,299 @@ LSIM_HD GD light_eval_d(const lsim_light_desc& d, const double* row, const GD& x
     }
     default:
       return cst<kLightN>(0.0);
+  }
+}
+
+
+// ---- hand-derived gradients (the fast path of k_image_grad) ------------------------------------------------------
+// Per sub-pixel the kernel needs, for a given 2-vector v (the back-propagated source-plane gradient),
+//   g_k = d(v . alpha)/d(parameter k of the profile).
+// LensPt carries what lens_point() leaves behind for lens_vjp(): for the EPL the Jacobian of the major-axis
+// deflection alpha' w.r.t. (x', y', q, t, theta_E) and alpha' itself; for the profiles evaluated on dual numbers the
+// 2 x 6 tangents.  Either way 12 doubles.
+struct LensPt {
+  double ax, ay;
+  double s[12];
+};
+
+// S = sum_{n<N} c_n w^n for real c_n by the quadratic-factor (Clenshaw) recurrence, three series at once:
+// value coefficients a (na terms), and b, c (nb terms each).
+LSIM_HD void series3(const double* a, int na, const double* b, const double* c, int nb, double wr, double wi,
+                     double (&o)[6]) {
+  const double pp = wr + wr, qq = -fma(wr, wr, wi * wi);
+  double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0, c1 = 0.0, c2 = 0.0;
+  for (int k = na - 1; k >= 1; --k) {
+    const double t = fma(pp, a1, fma(qq, a2, a[k]));
+    a2 = a1;
+    a1 = t;
+  }
+  for (int k = nb - 1; k >= 1; --k) {
+    const double tb = fma(pp, b1, fma(qq, b2, b[k]));
+    const double tc = fma(pp, c1, fma(qq, c2, c[k]));
+    b2 = b1;
+    b1 = tb;
+    c2 = c1;
+    c1 = tc;
+  }
+  o[0] = fma(a1, wr, fma(qq, a2, a[0]));
+  o[1] = a1 * wi;
+  o[2] = fma(b1, wr, fma(qq, b2, b[0]));
+  o[3] = b1 * wi;
+  o[4] = fma(c1, wr, fma(qq, c2, c[0]));
+  o[5] = c1 * wi;
+}
+
+// EPL: alpha' = A R^-t Z H(z, t), A = 2 b^t / (1+q), Z = q x' + i y', R = max(|Z|, 1e-9), z = f Q, Q = -Z^2/|Z|^2,
+// H = u S(w), u = 1/(1 - z/2) = 2|Z|^2 conj(D)/|D|^2, w = z/(z-2) = f Z^2 conj(D)/|D|^2, D = f Z^2 + 2|Z|^2.
+//   d alpha' = pre [ H (dlnA - t dlnR - lnR dt + kappa) + H_t dt + H_z dz ],   pre = A R^-t Z,  kappa = dZ / Z,
+//   dlnR = Re kappa (0 where R is clamped),  dz = df Q + z 2i Im kappa,
+//   H_t = u S_t,  H_z = u^2 (S - u S') / 2   with the 100-term series (the reference's custom_jvp; H itself: nmax terms).
+LSIM_HD void epl_point(const GLens& L, const double* pool, double x, double y, LensPt& o) {
+  const double* F = pool + L.coef_off;
+  const double* dF = F + kMaxSeries;
+  const double* G = dF + kTanTerms;
+  const double cph = L.k[0], sph = L.k[1], f = L.k[2], q = L.p[3].v, t = L.p[1].v;
+  const double xs = x - L.p[4].v, ys = y - L.p[5].v;
+  const double xr = fma(ys, sph, xs * cph), yr = fma(ys, cph, -(xs * sph));
+  const double Zr = q * xr, Zi = yr;
+  const double R2 = fma(Zi, Zi, Zr * Zr);
+  const double z2r = fma(-Zi, Zi, Zr * Zr), z2i = 2.0 * Zr * Zi;
+  const double Dr = fma(f, z2r, R2 + R2), Di = f * z2i;
+  const double inv = rcp_fast(fma(Dr, Dr, Di * Di));
+  const double finv = f * inv;
+  const double wr = fma(z2i, Di, z2r * Dr) * finv, wi = fma(z2i, Dr, -(z2r * Di)) * finv;
+  const double s2 = (R2 + R2) * inv;
+  const double ur = s2 * Dr, ui = -(s2 * Di);
+  double S[6];  // S_val, S', S_t
+  series3(F, L.n_val, G, dF, L.n_tan, wr, wi, S);
+  double Sr = S[0], Si = S[1];  // the 100-term S of the tangent; equals S_val when both series have the same length
+  if (L.n_tan != L.n_val) {
+    double T[6];
+    series3(F, L.n_tan, G, dF, 1, wr, wi, T);
+    Sr = T[0];
+    Si = T[1];
+  }
+  const double Hr = fma(ur, S[0], -(ui * S[1])), Hi = fma(ur, S[1], ui * S[0]);      // H = u S_val
+  const double Htr = fma(ur, S[4], -(ui * S[5])), Hti = fma(ur, S[5], ui * S[4]);    // H_t = u S_t
+  const double usr = fma(ur, S[2], -(ui * S[3])), usi = fma(ur, S[3], ui * S[2]);    // u S'
+  const double ar_ = Sr - usr, ai_ = Si - usi;
+  const double u2r = fma(ur, ur, -(ui * ui)), u2i = 2.0 * ur * ui;
+  const double Hzr = 0.5 * fma(u2r, ar_, -(u2i * ai_)), Hzi = 0.5 * fma(u2r, ai_, u2i * ar_);
+  const double iR2 = rcp_fast(R2);
+  const double Qr = -(z2r * iR2), Qi = -(z2i * iR2);
+  const double Yr = fma(Hzr, Qr, -(Hzi * Qi)), Yi = fma(Hzr, Qi, Hzi * Qr);          // H_z Q
+  const double Yzr = f * Yr, Yzi = f * Yi;                                          // H_z z
+  const double R2c = max_nan(R2, 1e-18);
+  const double lg = log2_pos(R2c);
+  const double P = L.k[5] * exp2_fin(fma(-0.5 * t, lg, L.k[4]));
+  const double lnR = 0.5 * kLn2 * lg;
+  const double teff = (R2 < 1e-18) ? 0.0 : t;
+  const double prr = P * Zr, pri = P * Zi;
+  double ar = fma(prr, Hr, -(pri * Hi)), ai = fma(prr, Hi, pri * Hr);
+  const bool finite = (fabs(ar) <= DBL_MAX) && (fabs(ai) <= DBL_MAX);
+  // kappa of the three directions that move Z: x' (dZ = q), y' (dZ = i), q (dZ = x')
+  const double izr = Zr * iR2, izi = -(Zi * iR2);  // 1 / Z
+  const double kr[3] = {q * izr, -izi, xr * izr};
+  const double ki[3] = {q * izi, izr, xr * izi};
+  const double ex[3] = {0.0, 0.0, L.k[6]};
+  const double df[3] = {0.0, 0.0, L.k[7]};
+  LSIM_UNROLL
+  for (int d = 0; d < 3; ++d) {
+    const double c0 = ex[d] - teff * kr[d];
+    // D = H kappa + c0 H + 2 Im(kappa) i (H_z z) + df (H_z Q)
+    const double Dre = fma(Hr, kr[d], -(Hi * ki[d])) + fma(c0, Hr, fma(-2.0 * ki[d], Yzi, df[d] * Yr));
+    const double Dim = fma(Hr, ki[d], Hi * kr[d]) + fma(c0, Hi, fma(2.0 * ki[d], Yzr, df[d] * Yi));
+    o.s[2 * d] = finite ? fma(prr, Dre, -(pri * Dim)) : 0.0;
+    o.s[2 * d + 1] = finite ? fma(prr, Dim, pri * Dre) : 0.0;
+  }
+  {  // t: D = H (ln b - ln R) + H_t
+    const double c0 = L.k[3] - lnR;
+    const double Dre = fma(c0, Hr, Htr), Dim = fma(c0, Hi, Hti);
+    o.s[6] = finite ? fma(prr, Dre, -(pri * Dim)) : 0.0;
+    o.s[7] = finite ? fma(prr, Dim, pri * Dre) : 0.0;
+  }
+  const double tte = t / L.p[0].v;  // theta_E: alpha' t / theta_E
+  o.s[8] = finite ? ar * tte : 0.0;
+  o.s[9] = finite ? ai * tte : 0.0;
+  ar = nan_to_num(ar, 1e10, -1e10);
+  ai = nan_to_num(ai, 1e10, -1e10);
+  o.s[10] = finite ? ar : 0.0;
+  o.s[11] = finite ? ai : 0.0;
+  o.ax = fma(-ai, sph, ar * cph);
+  o.ay = fma(ai, cph, ar * sph);
+}
+
+LSIM_HD void epl_vjp(const GLens& L, const LensPt& o, double x, double y, double vx, double vy, double (&g)[kLensN]) {
+  const double cph = L.k[0], sph = L.k[1];
+  const double Vr = fma(vy, sph, vx * cph), Vi = fma(vy, cph, -(vx * sph));  // v in the major-axis frame
+  const double sx = fma(Vr, o.s[0], Vi * o.s[1]), sy = fma(Vr, o.s[2], Vi * o.s[3]);
+  const double sq = fma(Vr, o.s[4], Vi * o.s[5]), st = fma(Vr, o.s[6], Vi * o.s[7]);
+  const double sE = fma(Vr, o.s[8], Vi * o.s[9]);
+  const double xs = x - L.p[4].v, ys = y - L.p[5].v;
+  const double xr = fma(ys, sph, xs * cph), yr = fma(ys, cph, -(xs * sph));
+  // phi: x' and y' rotate (dx'/dphi = y', dy'/dphi = -x') and alpha = e^{i phi} alpha' (d/dphi = i alpha)
+  const double sphi = fma(sx, yr, -(sy * xr)) + fma(Vi, o.s[10], -(Vr * o.s[11]));
+  const double scx = fma(sph, sy, -(cph * sx)), scy = -fma(sph, sx, cph * sy);
+  LSIM_UNROLL
+  for (int k = 0; k < kLensN; ++k)
+    g[k] = fma(sE, L.p[0].d[k], fma(st, L.p[1].d[k], fma(sphi, L.p[2].d[k],
+           fma(sq, L.p[3].d[k], fma(scx, L.p[4].d[k], scy * L.p[5].d[k])))));
+}
+
+// value + whatever lens_vjp needs, for any profile in the gradient's scope
+LSIM_HD void lens_point(const GLens& L, const double* pool, double x, double y, LensPt& o) {
+  if (L.type == LSIM_LENS_EPL) {
+    epl_point(L, pool, x, y, o);
+  } else if (L.type == LSIM_LENS_SHEAR) {
+    const double xs = x - L.c[2].v, ys = y - L.c[3].v;
+    o.ax = fma(L.c[1].v, ys, L.c[0].v * xs);
+    o.ay = fma(L.c[1].v, xs, -(L.c[0].v * ys));
+  } else {
+    LD fx, fy;
+    lens_eval_d(L, pool, x, y, fx, fy);
+    o.ax = fx.v;
+    o.ay = fy.v;
+    LSIM_UNROLL
+    for (int k = 0; k < kLensN; ++k) {
+      o.s[k] = fx.d[k];
+      o.s[kLensN + k] = fy.d[k];
+    }
+  }
+}
+
+// g_k = d(vx alpha_x + vy alpha_y) / d(parameter k)
+LSIM_HD void lens_vjp(const GLens& L, const LensPt& o, double x, double y, double vx, double vy, double (&g)[kLensN]) {
+  if (L.type == LSIM_LENS_EPL) {
+    epl_vjp(L, o, x, y, vx, vy, g);
+  } else if (L.type == LSIM_LENS_SHEAR) {  // alpha = (g1 xs + g2 ys, g2 xs - g1 ys)
+    const double xs = x - L.c[2].v, ys = y - L.c[3].v;
+    const double s[4] = {fma(vx, xs, -(vy * ys)), fma(vx, ys, vy * xs), -fma(vx, L.c[0].v, vy * L.c[1].v),
+                         fma(vy, L.c[0].v, -(vx * L.c[1].v))};
+    LSIM_UNROLL
+    for (int k = 0; k < kLensN; ++k)
+      g[k] = fma(s[0], L.c[0].d[k], fma(s[1], L.c[1].d[k], fma(s[2], L.c[2].d[k], s[3] * L.c[3].d[k])));
+  } else {
+    LSIM_UNROLL
+    for (int k = 0; k < kLensN; ++k) g[k] = fma(vx, o.s[k], vy * o.s[kLensN + k]);
+  }
+}
+
+// ---- light, hand-derived -------------------------------------------------------------------------------------------
+constexpr int kLightG = 7;  // own parameters of a light profile (SERSIC_ELLIPSE has 7)
+struct GLight {
+  int32_t type, lensed, slot, pad;
+  double k[20];
+};
+
+// SERSIC / SERSIC_ELLIPSE: k = cx, cy, a11, a12, a22 (the product-average transform), 1/n, log2 Rs_, -bn log2e,
+// min(bn log2e, 1021), (1000 Rs_)^2, amp, bn, [Rs > 1e-4]/Rs_, 1.9992 [bn not clamped], 1/norm, dnorm/de1 / norm,
+// dnorm/de2 / norm, [amp is a parameter]
+LSIM_HD void light_prepare_g(const lsim_light_desc& d, const double* row, GLight& G) {
+  G.type = d.type;
+  G.lensed = d.lensed;
+  G.slot = d.slot;
+  G.pad = 0;
+  auto P = [&](int i) { return param_of(d, row, i); };
+  const double amp = d.use_amp ? P(0) : 1.0;
+  if (d.type == LSIM_LIGHT_SERSIC || d.type == LSIM_LIGHT_SERSIC_ELLIPSE) {
+    const bool ell = d.type == LSIM_LIGHT_SERSIC_ELLIPSE;
+    double Rs = P(1);
+    const double n = P(2);
+    const double e1 = ell ? P(3) : 0.0, e2 = ell ? P(4) : 0.0;
+    bool rs_live = true;
+    if (ell) {
+      rs_live = !(Rs < 0.0);
+      Rs = fmax(0.0, Rs);
+    }
+    rs_live = rs_live && !(Rs < 0.0001);
+    const double arg = 1 - e1 * e1 - e2 * e2;
+    const double ne = sqrt(fabs(arg));
+    const bool n_live = !(ne < 0.000001);
+    const double norm = fmax(ne, 0.000001);
+    const double Rs_ = fmax(0.0001, Rs);
+    const double bnr = 1.9992 * n - 0.3271;
+    const double bn = fmax(bnr, 0.00001);
+    G.k[0] = P(ell ? 5 : 3);
+    G.k[1] = P(ell ? 6 : 4);
+    G.k[2] = (1 - e1) / norm;
+    G.k[3] = -e2 / norm;
+    G.k[4] = (1 + e1) / norm;
+    G.k[5] = 1.0 / n;
+    G.k[6] = log2(Rs_);
+    G.k[7] = -bn * kLog2e;
+    G.k[8] = fmin(bn * kLog2e, 1021.0);
+    G.k[9] = (1000.0 * Rs_) * (1000.0 * Rs_);
+    G.k[10] = amp;
+    G.k[11] = bn;
+    G.k[12] = rs_live ? 1.0 / Rs_ : 0.0;
+    G.k[13] = (bnr < 0.00001) ? 0.0 : 1.9992;
+    G.k[14] = 1.0 / norm;
+    const double sgn = arg < 0 ? -1.0 : 1.0;
+    G.k[15] = (n_live && ne > 0) ? -e1 * sgn / (ne * norm) : 0.0;
+    G.k[16] = (n_live && ne > 0) ? -e2 * sgn / (ne * norm) : 0.0;
+    G.type = ell ? LSIM_LIGHT_SERSIC_ELLIPSE : LSIM_LIGHT_SERSIC;
+  } else if (d.type == LSIM_LIGHT_GAUSSIAN) {
+    const double sigma = P(1);
+    G.k[0] = P(2);
+    G.k[1] = P(3);
+    G.k[2] = -0.5 * kLog2e / (sigma * sigma);
+    G.k[3] = 1.0 / (2 * kPi * sigma * sigma);
+    G.k[4] = 1.0 / (sigma * sigma);
+    G.k[5] = 1.0 / sigma;
+    G.k[10] = amp;
+  } else {
+    G.slot = -1;
+  }
+}
+
+// I, dI/dx, dI/dy and dI/d(own parameter k) (param_names order) of one light component at (x, y)
+LSIM_HD void light_point(const GLight& G, double x, double y, double& I, double& Ix, double& Iy, double (&g)[kLightG]) {
+  LSIM_UNROLL
+  for (int k = 0; k < kLightG; ++k) g[k] = 0.0;
+  I = Ix = Iy = 0.0;
+  if (G.type == LSIM_LIGHT_GAUSSIAN) {
+    const double dx = x - G.k[0], dy = y - G.k[1];
+    const double r2 = fma(dy, dy, dx * dx);
+    const double E = G.k[3] * exp2_fin(G.k[2] * r2);
+    I = G.k[10] * E;
+    const double w = -I * G.k[4];
+    Ix = w * dx;
+    Iy = w * dy;
+    g[0] = E;
+    g[1] = I * G.k[5] * fma(r2, G.k[4], -2.0);
+    g[2] = -Ix;
+    g[3] = -Iy;
+    return;
+  }
+  const bool ell = G.type == LSIM_LIGHT_SERSIC_ELLIPSE;
+  const double xs = x - G.k[0], ys = y - G.k[1];
+  const double x_ = fma(G.k[3], ys, G.k[2] * xs), y_ = fma(G.k[4], ys, G.k[3] * xs);
+  const double R2 = fma(y_, y_, x_ * x_);
+  const bool r_live = !(R2 < 1e-8);
+  const double R2c = max_nan(R2, 1e-8);
+  if (!(R2c <= G.k[9])) return;  // R_frac > max_R_frac: identically zero
+  const double lu = fma(0.5, log2_pos(R2c), -G.k[6]);  // log2(R_/Rs_)
+  const double p = exp2_fin(lu * G.k[5]);
+  const double E = exp2_fin(fma(G.k[7], p, G.k[8]));
+  const double amp = G.k[10], bn = G.k[11], inv_n = G.k[5];
+  I = amp * E;
+  const double bEp = bn * E * p * inv_n * amp;           // amp bn E p / n
+  const double W = r_live ? -bEp * rcp_fast(R2c) : 0.0;  // dI/dR / R
+  const double gx = W * x_, gy = W * y_;
+  Ix = fma(gy, G.k[3], gx * G.k[2]);
+  Iy = fma(gy, G.k[4], gx * G.k[3]);
+  g[0] = E;
+  g[1] = bEp * G.k[12];
+  g[2] = I * fma(bn * p * inv_n * inv_n, lu * kLn2, -(G.k[13] * (p - 1.0)));
+  if (ell) {
+    const double WR2 = W * R2;
+    g[3] = fma(gy, ys, -(gx * xs)) * G.k[14] - WR2 * G.k[15];
+    g[4] = -fma(gx, ys, gy * xs) * G.k[14] - WR2 * G.k[16];
+    g[5] = -Ix;
+    g[6] = -Iy;
+  } else {
+    g[3] = -Ix;
+    g[4] = -Iy;
   }
 }
 

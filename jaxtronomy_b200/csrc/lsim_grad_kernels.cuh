@@ -239,9 +239,19 @@ k_conv_adj_edge(const double* __restrict__ in, double* __restrict__ out, int nx,
 }
 
 // ---- k_image_grad ----------------------------------------------------------------------------------------------------
-// grid (tiles, sets).  shared memory: GLens[n_lens] | coefficient pool [n_series][kGradPool] | acc[E][kGradBlock].
-// NL > 0: the model has exactly NL lens profiles; their dual deflections stay in registers between the ray shooting
-// and the lens-parameter update.  NL == 0: any number of profiles, each evaluated twice (value, then tangents).
+// grid (tiles, sets).  shared memory: GLens[n_lens] | GLight[n_light] | coefficient pool [n_series][kGradPool] |
+// acc[E][kGradBlock].  Per sub-pixel: every lens profile once (value + Jacobian, lens_point), every light component
+// once (value + gradient, light_point), then the lens parameters' contraction with the back-propagated source-plane
+// gradient (lens_vjp).  EPL, SHEAR and the light profiles use closed-form derivatives, the other lens profiles dual
+// numbers (lsim_grad.cuh).
+// NL > 0: the model has exactly NL lens profiles; their point states stay in registers between the ray shooting and
+// the lens-parameter update.  NL == 0: any number of profiles, each evaluated twice.
+__host__ __device__ inline size_t grad_smem_bytes(int n_lens, int n_light, int n_series) {
+  return (size_t)n_lens * sizeof(ad::GLens) + (size_t)n_light * sizeof(ad::GLight) +
+         (size_t)n_series * ad::kGradPool * sizeof(double) +
+         (size_t)grad_entries(n_lens, n_light) * kGradBlock * sizeof(double);
+}
+
 template <int NL>
 __global__ void __launch_bounds__(kGradBlock)
 k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, int n_series,
@@ -251,14 +261,20 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
   const int64_t bl = blockIdx.y;
   const double* row = params + (set0 + bl) * P.n_param_cols;
   GLens* L = reinterpret_cast<GLens*>(smem);
-  double* pool = reinterpret_cast<double*>(L + P.n_lens);
+  GLight* G = reinterpret_cast<GLight*>(L + P.n_lens);
+  double* pool = reinterpret_cast<double*>(G + P.n_light);
   double* acc = pool + (size_t)n_series * kGradPool;
   const int E = grad_entries(P.n_lens, P.n_light);
-  for (int i = threadIdx.x; i < P.n_lens; i += kGradBlock) {
-    int off = 0;
-    for (int j = 0; j < i; ++j) off += lens_grad_has_series(P.lens[j]) ? 1 : 0;
-    L[i].coef_off = off * kGradPool;
-    lens_prepare_d(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries);
+  stage_math_tables();
+  for (int i = threadIdx.x; i < P.n_lens + P.n_light; i += kGradBlock) {
+    if (i < P.n_lens) {
+      int off = 0;
+      for (int j = 0; j < i; ++j) off += lens_grad_has_series(P.lens[j]) ? 1 : 0;
+      L[i].coef_off = off * kGradPool;
+      lens_prepare_d(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries);
+    } else {
+      light_prepare_g(P.light[i - P.n_lens], row, G[i - P.n_lens]);
+    }
   }
   double* my = acc + threadIdx.x;
   for (int e = 0; e < E; ++e) my[e * kGradBlock] = 0.0;
@@ -269,6 +285,7 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
   const int64_t sub_stride = (int64_t)P.nx * ss;
   const double wsub = wscale / ((double)ss * ss);
   const double as = P.ray.alpha_scaling;
+  double* lacc = my + (size_t)kLensN * P.n_lens * kGradBlock;
   // flux_evaluate_indexes: pixels outside the list have zero flux whatever the parameters are
   const int q_end = min(P.eval_list ? P.n_eval : npix, (int)(blockIdx.x + 1) * ppt);
   for (int q = blockIdx.x * ppt + threadIdx.x; q < q_end; q += kGradBlock) {
@@ -279,55 +296,56 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
       for (int j = 0; j < ss; ++j) {
         const double x = __ldg(P.x_sub + base + j), y = __ldg(P.y_sub + base + j);
         double ax = 0.0, ay = 0.0;
-        LD fx[NL > 0 ? NL : 1], fy[NL > 0 ? NL : 1];
+        LensPt pt[NL > 0 ? NL : 1];
         if (NL > 0) {
 #pragma unroll
           for (int l = 0; l < NL; ++l) {
-            lens_eval_d(L[l], pool, x, y, fx[l], fy[l]);
-            ax += fx[l].v;
-            ay += fy[l].v;
+            lens_point(L[l], pool, x, y, pt[l]);
+            ax += pt[l].ax;
+            ay += pt[l].ay;
           }
         } else {
           for (int l = 0; l < P.n_lens; ++l) {
-            lens_eval_d(L[l], pool, x, y, fx[0], fy[0]);
-            ax += fx[0].v;
-            ay += fy[0].v;
+            lens_point(L[l], pool, x, y, pt[0]);
+            ax += pt[0].ax;
+            ay += pt[0].ay;
           }
         }
         const double bx = x - ax * as, by = y - ay * as;
         double vx = 0.0, vy = 0.0;
-        double* lacc = my + (size_t)kLensN * P.n_lens * kGradBlock;
         for (int g = 0; g < P.n_light; ++g) {
-          const lsim_light_desc& d = P.light[g];
-          if (d.slot < 0) continue;
-          const double w = __ldg(ubar + (bl * P.n_slots + d.slot) * (int64_t)npix + p) * wsub;
-          const GD I = d.lensed ? light_eval_d(d, row, var<kLightN>(bx, 0), var<kLightN>(by, 1))
-                                : light_eval_d(d, row, cst<kLightN>(x), cst<kLightN>(y));
-          if (d.lensed) {
-            vx = fma(w, I.d[0], vx);
-            vy = fma(w, I.d[1], vy);
+          const GLight& Gg = G[g];
+          if (Gg.slot < 0) continue;
+          const double w = __ldg(ubar + (bl * P.n_slots + Gg.slot) * (int64_t)npix + p) * wsub;
+          double I, Ix, Iy, gg[kLightG];
+          light_point(Gg, Gg.lensed ? bx : x, Gg.lensed ? by : y, I, Ix, Iy, gg);
+          if (Gg.lensed) {
+            vx = fma(w, Ix, vx);
+            vy = fma(w, Iy, vy);
           }
           double* e = lacc + (size_t)g * kGradLightStride * kGradBlock;
 #pragma unroll
-          for (int k = 0; k < kGradLightStride; ++k) e[k * kGradBlock] = fma(w, I.d[2 + k], e[k * kGradBlock]);
+          for (int k = 0; k < kGradLightStride; ++k) e[k * kGradBlock] = fma(w, gg[k], e[k * kGradBlock]);
         }
         vx *= -as;  // d beta / d p = -alpha_scaling d alpha / d p
         vy *= -as;
         if (NL > 0) {
 #pragma unroll
           for (int l = 0; l < NL; ++l) {
+            double gl[kLensN];
+            lens_vjp(L[l], pt[l], x, y, vx, vy, gl);
             double* e = my + (size_t)l * kLensN * kGradBlock;
 #pragma unroll
-            for (int k = 0; k < kLensN; ++k)
-              e[k * kGradBlock] = fma(vx, fx[l].d[k], fma(vy, fy[l].d[k], e[k * kGradBlock]));
+            for (int k = 0; k < kLensN; ++k) e[k * kGradBlock] += gl[k];
           }
         } else if (vx != 0.0 || vy != 0.0) {
           for (int l = 0; l < P.n_lens; ++l) {
-            lens_eval_d(L[l], pool, x, y, fx[0], fy[0]);
+            lens_point(L[l], pool, x, y, pt[0]);
+            double gl[kLensN];
+            lens_vjp(L[l], pt[0], x, y, vx, vy, gl);
             double* e = my + (size_t)l * kLensN * kGradBlock;
 #pragma unroll
-            for (int k = 0; k < kLensN; ++k)
-              e[k * kGradBlock] = fma(vx, fx[0].d[k], fma(vy, fy[0].d[k], e[k * kGradBlock]));
+            for (int k = 0; k < kLensN; ++k) e[k * kGradBlock] += gl[k];
           }
         }
       }

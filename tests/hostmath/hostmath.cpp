@@ -121,4 +121,48 @@ int hm_light_jvp(const lsim_light_desc* light, const double* row, const double* 
   }
   return 0;
 }
+
+// Hand-derived fast path of the gradient kernel: g [N][n_lens][6] = d(vx alpha_x + vy alpha_y)/d(parameter k).
+int hm_lens_vjp(const lsim_lens_desc* lens, int n_lens, const double* row, const double* x, const double* y, int64_t N,
+                const double* vx, const double* vy, double* ax, double* ay, double* g) {
+  std::vector<ad::GLens> L(n_lens);
+  std::vector<double> pool((size_t)(n_lens + 1) * ad::kGradPool);
+  int off = 0;
+  for (int i = 0; i < n_lens; ++i) {
+    L[i].coef_off = off * ad::kGradPool;
+    double* F = pool.data() + (size_t)off * ad::kGradPool;
+    if (!ad::lens_prepare_d(lens[i], row, L[i], F, F + kMaxSeries)) return -2;
+    if (ad::lens_grad_has_series(lens[i])) ++off;
+  }
+  for (int64_t p = 0; p < N; ++p) {
+    ax[p] = ay[p] = 0.0;
+    for (int i = 0; i < n_lens; ++i) {
+      ad::LensPt o;
+      ad::lens_point(L[i], pool.data(), x[p], y[p], o);
+      ax[p] += o.ax;
+      ay[p] += o.ay;
+      double gg[ad::kLensN];
+      ad::lens_vjp(L[i], o, x[p], y[p], vx[p], vy[p], gg);
+      for (int k = 0; k < ad::kLensN; ++k) g[((size_t)p * n_lens + i) * ad::kLensN + k] = gg[k];
+    }
+  }
+  return 0;
+}
+
+//   out [N], dout [N][9]: d/dx, d/dy, then d/d(parameter k) -- same layout as hm_light_jvp
+int hm_light_point(const lsim_light_desc* light, const double* row, const double* x, const double* y, int64_t N,
+                   double* out, double* dout) {
+  ad::GLight G;
+  ad::light_prepare_g(*light, row, G);
+  if (G.slot < 0) return -2;
+  for (int64_t p = 0; p < N; ++p) {
+    double I, Ix, Iy, g[ad::kLightG];
+    ad::light_point(G, x[p], y[p], I, Ix, Iy, g);
+    out[p] = I;
+    dout[(size_t)p * 9] = Ix;
+    dout[(size_t)p * 9 + 1] = Iy;
+    for (int k = 0; k < ad::kLightG; ++k) dout[(size_t)p * 9 + 2 + k] = g[k];
+  }
+  return 0;
+}
 }

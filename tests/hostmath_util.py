@@ -41,6 +41,8 @@ def lib():
         h.hm_epl_terms.argtypes = [C.POINTER(_lib.LensDesc), _dp, C.c_double]
         h.hm_lens_jvp.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp]
         h.hm_light_jvp.argtypes = [C.POINTER(_lib.LightDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp]
+        h.hm_light_point.argtypes = [C.POINTER(_lib.LightDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp]
+        h.hm_lens_vjp.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp]
         _h = h
     return _h
 
@@ -130,7 +132,23 @@ def lens_jvp(lens_model_list, kwargs_list, x, y, profile_kwargs_list=None):
     return ax, ay, dax, day
 
 
-def light_jvp(light_model, kwargs, x, y, use_amp=True):
+def lens_vjp(lens_model_list, kwargs_list, x, y, vx, vy, profile_kwargs_list=None):
+    """Hand-derived fast path: (alpha_x, alpha_y, g [N, n_lens, 6]) with g = d(vx alpha_x + vy alpha_y)/d(param)."""
+    names = [_model.LENS_PARAM_NAMES[n] for n in lens_model_list]
+    row = np.asarray(_model.gather_values(names, kwargs_list), dtype=np.float64)
+    layout = _model.ColumnLayout()
+    descs = [_model.lens_desc(n, layout.add_profile("lens", i, names[i]), (profile_kwargs_list or [{}] * len(names))[i])
+             for i, n in enumerate(lens_model_list)]
+    arr = (_lib.LensDesc * max(1, len(descs)))(*descs)
+    x, y, vx, vy = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, vx, vy))
+    ax, ay = np.empty_like(x), np.empty_like(y)
+    g = np.empty((x.size, len(descs), 6))
+    rc = lib().hm_lens_vjp(arr, len(descs), _p(row), _p(x), _p(y), x.size, _p(vx), _p(vy), _p(ax), _p(ay), _p(g))
+    assert rc == 0, rc
+    return ax, ay, g
+
+
+def light_jvp(light_model, kwargs, x, y, use_amp=True, fast=False):
     """Dual-number surface brightness: (I [N], dI [N, 9]) with dI[:, 0:2] = d/dx, d/dy and dI[:, 2 + k] = d/d(param k)."""
     names = [_model.LIGHT_PARAM_NAMES[light_model]]
     row = np.asarray(_model.gather_values(names, [kwargs], "light"), dtype=np.float64)
@@ -139,6 +157,7 @@ def light_jvp(light_model, kwargs, x, y, use_amp=True):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)
     out, dout = np.empty_like(x), np.empty((x.size, 9))
-    rc = lib().hm_light_jvp(C.byref(desc), _p(row), _p(x), _p(y), x.size, _p(out), _p(dout))
+    fn = lib().hm_light_point if fast else lib().hm_light_jvp
+    rc = fn(C.byref(desc), _p(row), _p(x), _p(y), x.size, _p(out), _p(dout))
     assert rc == 0, rc
     return out, dout

@@ -114,3 +114,37 @@ def test_light_dual_against_oracle(case):
     # amplitude solved linearly: amp = 1 and carries no tangent
     val1, dv1 = hm.light_jvp(name, kw, x, y, use_amp=False)
     assert np.allclose(val1 * kw["amp"], val, rtol=1e-13) and not dv1[:, 2].any()
+
+
+@pytest.mark.parametrize("case", range(len(LENS_CASES)))
+def test_hand_derived_lens_gradient_equals_the_dual_numbers(case):
+    """The kernel's fast path (closed-form Jacobian of the EPL / shear, lens_point + lens_vjp) against the dual-number
+    evaluation of the same profile: same function, two derivations -- they must agree to round-off."""
+    name, kw, pk = LENS_CASES[case]
+    x, y = grid(11)
+    rng = np.random.default_rng(case)
+    vx, vy = rng.normal(size=x.size), rng.normal(size=x.size)
+    ax, ay, dax, day = hm.lens_jvp([name], [kw], x, y, [pk or {}])
+    bx, by, g = hm.lens_vjp([name], [kw], x, y, vx, vy, [pk or {}])
+    scale = max(np.abs(ax).max(), np.abs(ay).max())
+    assert np.allclose(bx, ax, rtol=1e-12, atol=1e-13 * scale) and np.allclose(by, ay, rtol=1e-12, atol=1e-13 * scale)
+    ref = vx[:, None] * dax[:, 0] + vy[:, None] * day[:, 0]
+    for k in range(6):
+        tol = 1e-11 * max(np.abs(ref[:, k]).max(), 1e-6)
+        assert np.abs(g[:, 0, k] - ref[:, k]).max() <= tol, (name, k, np.abs(g[:, 0, k] - ref[:, k]).max(), tol)
+
+
+@pytest.mark.parametrize("case", range(len(LIGHT_CASES)))
+@pytest.mark.parametrize("use_amp", [True, False])
+def test_hand_derived_light_gradient_equals_the_dual_numbers(case, use_amp):
+    name, kw = LIGHT_CASES[case]
+    x, y = grid(11, 1.9)
+    v0, d0 = hm.light_jvp(name, kw, x, y, use_amp=use_amp)
+    v1, d1 = hm.light_jvp(name, kw, x, y, use_amp=use_amp, fast=True)
+    assert np.allclose(v1, v0, rtol=1e-12, atol=1e-300)
+    n = len(oli.PARAM_NAMES[name])
+    for k in range(2 + n):
+        if k == 2 and not use_amp:
+            continue  # the amplitude is not a parameter then; the kernel never reads that entry
+        tol = 1e-11 * max(np.abs(d0[:, k]).max(), 1e-300)
+        assert np.abs(d1[:, k] - d0[:, k]).max() <= tol, (name, k, np.abs(d1[:, k] - d0[:, k]).max(), tol)
