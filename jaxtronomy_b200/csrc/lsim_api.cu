@@ -134,6 +134,7 @@ struct lsim_plan {
   int n_sm = 148;
   // gradient path (lsim_logl_grad): transposed PSF = the flipped kernel; grad_nl = lens profiles held in registers
   bool grad_ok = false;
+  bool grad_fast = false;  // every lens profile has closed-form derivatives (EPL, SHEAR)
   int grad_series = 0;
   size_t grad_smem = 0;
   const double* kernel_flip = nullptr;
@@ -176,10 +177,14 @@ constexpr size_t kGradSmemMax = 200 * 1024;
 int configure_kernels() {
   LSIM_CUDA(cudaFuncSetAttribute(k_conv_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
   LSIM_CUDA(cudaFuncSetAttribute(k_conv_separable, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
-  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
-  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
-  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
-  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
+#define LSIM_GRAD_ATTR(NL)                                                                                        \
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax)); \
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
+  LSIM_GRAD_ATTR(0)
+  LSIM_GRAD_ATTR(1)
+  LSIM_GRAD_ATTR(2)
+  LSIM_GRAD_ATTR(3)
+#undef LSIM_GRAD_ATTR
   return LSIM_OK;
 }
 
@@ -375,12 +380,15 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
       bool ok = !d->multi_plane && !d->supersampled_conv && d->n_points == 0 && !p->f32 &&
                 (d->conv_mode != LSIM_CONV_EDGE || d->kernel_separable);
       int gs = 0;
+      bool fast = true;
       for (int i = 0; i < d->n_lens; ++i) {
+        fast = fast && ad::lens_grad_closed_form(d->lens[i]);
         ok = ok && ad::lens_grad_supported(d->lens[i]);
         gs += ad::lens_grad_has_series(d->lens[i]) ? 1 : 0;
       }
       for (int i = 0; i < d->n_light; ++i) ok = ok && ad::light_grad_supported(d->light[i]);
       p->grad_series = gs;
+      p->grad_fast = fast;
       p->grad_smem = grad_smem_bytes(d->n_lens, d->n_light, gs);
       p->grad_ok = ok && p->grad_smem <= kGradSmemMax;
       if (p->grad_ok && D.K > 0) {
@@ -1032,7 +1040,7 @@ int launch_image_grad(const lsim_plan* plan, const double* params, int64_t set0,
   const PlanDev& D = plan->dev;
   const int npix = D.n_eval;
   const int max_tiles = grad_max_tiles(plan);
-  int64_t want = ((int64_t)plan->n_sm * 8 + n - 1) / n;
+  int64_t want = ((int64_t)plan->n_sm * 24 + n - 1) / n;  // >= 8 waves of 3 resident CTAs
   int tiles = (int)(want < 1 ? 1 : (want > max_tiles ? max_tiles : want));
   if (tiles < 1) tiles = 1;
   int ppt = (npix + tiles - 1) / tiles;
@@ -1046,12 +1054,18 @@ int launch_image_grad(const lsim_plan* plan, const double* params, int64_t set0,
     double* pt = partial + (size_t)i0 * tiles * grad_entries(D.n_lens, D.n_light);
     {
       Timed timed(kClsImage, st);
+#define LSIM_GRAD_LAUNCH(NL)                                                                                      \
+  if (plan->grad_fast)                                                                                            \
+    k_image_grad<NL, true><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); \
+  else                                                                                                            \
+    k_image_grad<NL, false><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt);
       switch (D.n_lens <= 3 ? D.n_lens : 0) {
-        case 1: k_image_grad<1><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); break;
-        case 2: k_image_grad<2><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); break;
-        case 3: k_image_grad<3><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); break;
-        default: k_image_grad<0><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); break;
+        case 1: LSIM_GRAD_LAUNCH(1) break;
+        case 2: LSIM_GRAD_LAUNCH(2) break;
+        case 3: LSIM_GRAD_LAUNCH(3) break;
+        default: LSIM_GRAD_LAUNCH(0) break;
       }
+#undef LSIM_GRAD_LAUNCH
       int rc = after_launch("k_image_grad");
       if (rc != LSIM_OK) return rc;
     }

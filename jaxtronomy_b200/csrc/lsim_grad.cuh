@@ -35,7 +35,15 @@ namespace ad {
 constexpr int kLensN = 6;    // tangents carried by a lens profile: its own parameters (param_names order)
 constexpr int kLightN = 9;   // light profile: d/d(x), d/d(y) of the evaluation point, then its own parameters
 constexpr int kTanTerms = 100;                      // hyp2f1_slow, epl.py:283
-constexpr int kGradPool = kMaxSeries + 2 * kTanTerms;  // per EPL-family profile: F_n [kMaxSeries], dF_n/dt and (n+1) F_{n+1} [kTanTerms each]
+// per EPL-family profile: F_n [kMaxSeries] | dF_n/dt [kTanTerms] | Coef4 [kTanTerms] (the four series of the fast path,
+// interleaved so that one term is two 128-bit shared-memory loads)
+constexpr int kGradPool = kMaxSeries + 5 * kTanTerms;
+struct alignas(16) Coef4 {
+  double fv;  // F_n for n < n_val, else 0: the value series (nmax schedule) on the tangent series' index range
+  double f;   // F_n: the 100-term S of the tangent
+  double g;   // (n+1) F_{n+1}: dS/dw
+  double d;   // dF_n/dt: dS/dt
+};
 
 template <int N>
 struct Dual {
@@ -304,10 +312,14 @@ LSIM_HD void epl_prepare_d(GLens& L, double* F, double* dF, const LD& theta_E, c
     ppF = pF;
     pF = nF;
   }
-  // coefficients of dS/dw = sum_m (m+1) F_{m+1} w^m, m < n_tan - 1 (stored behind dF)
-  double* G = dF + kTanTerms;
-  for (int m = 0; m + 1 < n_tan; ++m) G[m] = (m + 1.0) * F[m + 1];
-  G[n_tan - 1] = 0.0;
+  // the fast path's interleaved table: value series cut at n_val, S, dS/dw = sum_m (m+1) F_{m+1} w^m, dS/dt
+  Coef4* T = reinterpret_cast<Coef4*>(dF + kTanTerms);
+  for (int n = 0; n < n_tan; ++n) {
+    T[n].fv = n < n_val ? F[n] : 0.0;
+    T[n].f = F[n];
+    T[n].g = n + 1 < n_tan ? (n + 1.0) * F[n + 1] : 0.0;
+    T[n].d = dF[n];
+  }
 }
 
 // EPL deflection at one image-plane point with its derivatives w.r.t. the profile's own parameters
@@ -561,31 +573,43 @@ struct LensPt {
   double s[12];
 };
 
-// S = sum_{n<N} c_n w^n for real c_n by the quadratic-factor (Clenshaw) recurrence, three series at once:
-// value coefficients a (na terms), and b, c (nb terms each).
-LSIM_HD void series3(const double* a, int na, const double* b, const double* c, int nb, double wr, double wi,
-                     double (&o)[6]) {
+// S = sum_n c_n w^n for real c_n by the quadratic-factor (Clenshaw) recurrence  b_k = c_k + 2 Re(w) b_{k+1} -
+// |w|^2 b_{k+2},  S = c_0 + w b_1 - |w|^2 b_2.  Four series in one loop (four independent FMA chains):
+//   F cut at n_val (the value of 2F1, nmax schedule), F (100-term S), (n+1) F_{n+1} (dS/dw), dF_n/dt (dS/dt).
+// A value series longer than the tangent series (nmax = 200, 500) runs its head alone first.
+LSIM_HD void series4(const double* F, int n_val, const Coef4* T, int n_tan, double wr, double wi, double (&o)[8]) {
   const double pp = wr + wr, qq = -fma(wr, wr, wi * wi);
-  double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0, c1 = 0.0, c2 = 0.0;
-  for (int k = na - 1; k >= 1; --k) {
-    const double t = fma(pp, a1, fma(qq, a2, a[k]));
+  double a1 = 0.0, a2 = 0.0, f1 = 0.0, f2 = 0.0, b1 = 0.0, b2 = 0.0, c1 = 0.0, c2 = 0.0;
+  for (int k = n_val - 1; k >= n_tan; --k) {
+    const double t = fma(pp, a1, fma(qq, a2, F[k]));
     a2 = a1;
     a1 = t;
   }
-  for (int k = nb - 1; k >= 1; --k) {
-    const double tb = fma(pp, b1, fma(qq, b2, b[k]));
-    const double tc = fma(pp, c1, fma(qq, c2, c[k]));
+  const bool longv = n_val > n_tan;
+  for (int k = n_tan - 1; k >= 1; --k) {
+    const Coef4 c = T[k];
+    const double ta = fma(pp, a1, fma(qq, a2, longv ? c.f : c.fv));
+    const double tf = fma(pp, f1, fma(qq, f2, c.f));
+    const double tb = fma(pp, b1, fma(qq, b2, c.g));
+    const double tc = fma(pp, c1, fma(qq, c2, c.d));
+    a2 = a1;
+    a1 = ta;
+    f2 = f1;
+    f1 = tf;
     b2 = b1;
     b1 = tb;
     c2 = c1;
     c1 = tc;
   }
-  o[0] = fma(a1, wr, fma(qq, a2, a[0]));
+  const Coef4 c = T[0];
+  o[0] = fma(a1, wr, fma(qq, a2, c.f));
   o[1] = a1 * wi;
-  o[2] = fma(b1, wr, fma(qq, b2, b[0]));
+  o[2] = fma(b1, wr, fma(qq, b2, c.g));
   o[3] = b1 * wi;
-  o[4] = fma(c1, wr, fma(qq, c2, c[0]));
+  o[4] = fma(c1, wr, fma(qq, c2, c.d));
   o[5] = c1 * wi;
+  o[6] = fma(f1, wr, fma(qq, f2, c.f));
+  o[7] = f1 * wi;
 }
 
 // EPL: alpha' = A R^-t Z H(z, t), A = 2 b^t / (1+q), Z = q x' + i y', R = max(|Z|, 1e-9), z = f Q, Q = -Z^2/|Z|^2,
@@ -595,8 +619,7 @@ LSIM_HD void series3(const double* a, int na, const double* b, const double* c, 
 //   H_t = u S_t,  H_z = u^2 (S - u S') / 2   with the 100-term series (the reference's custom_jvp; H itself: nmax terms).
 LSIM_HD void epl_point(const GLens& L, const double* pool, double x, double y, LensPt& o) {
   const double* F = pool + L.coef_off;
-  const double* dF = F + kMaxSeries;
-  const double* G = dF + kTanTerms;
+  const Coef4* T = reinterpret_cast<const Coef4*>(F + kMaxSeries + kTanTerms);
   const double cph = L.k[0], sph = L.k[1], f = L.k[2], q = L.p[3].v, t = L.p[1].v;
   const double xs = x - L.p[4].v, ys = y - L.p[5].v;
   const double xr = fma(ys, sph, xs * cph), yr = fma(ys, cph, -(xs * sph));
@@ -609,15 +632,9 @@ LSIM_HD void epl_point(const GLens& L, const double* pool, double x, double y, L
   const double wr = fma(z2i, Di, z2r * Dr) * finv, wi = fma(z2i, Dr, -(z2r * Di)) * finv;
   const double s2 = (R2 + R2) * inv;
   const double ur = s2 * Dr, ui = -(s2 * Di);
-  double S[6];  // S_val, S', S_t
-  series3(F, L.n_val, G, dF, L.n_tan, wr, wi, S);
-  double Sr = S[0], Si = S[1];  // the 100-term S of the tangent; equals S_val when both series have the same length
-  if (L.n_tan != L.n_val) {
-    double T[6];
-    series3(F, L.n_tan, G, dF, 1, wr, wi, T);
-    Sr = T[0];
-    Si = T[1];
-  }
+  double S[8];  // S_val, S', S_t, S_100
+  series4(F, L.n_val, T, L.n_tan, wr, wi, S);
+  const double Sr = S[6], Si = S[7];
   const double Hr = fma(ur, S[0], -(ui * S[1])), Hi = fma(ur, S[1], ui * S[0]);      // H = u S_val
   const double Htr = fma(ur, S[4], -(ui * S[5])), Hti = fma(ur, S[5], ui * S[4]);    // H_t = u S_t
   const double usr = fma(ur, S[2], -(ui * S[3])), usi = fma(ur, S[3], ui * S[2]);    // u S'
@@ -679,13 +696,18 @@ LSIM_HD void epl_vjp(const GLens& L, const LensPt& o, double x, double y, double
   // phi: x' and y' rotate (dx'/dphi = y', dy'/dphi = -x') and alpha = e^{i phi} alpha' (d/dphi = i alpha)
   const double sphi = fma(sx, yr, -(sy * xr)) + fma(Vi, o.s[10], -(Vr * o.s[11]));
   const double scx = fma(sph, sy, -(cph * sx)), scy = -fma(sph, sx, cph * sy);
-  LSIM_UNROLL
-  for (int k = 0; k < kLensN; ++k)
-    g[k] = fma(sE, L.p[0].d[k], fma(st, L.p[1].d[k], fma(sphi, L.p[2].d[k],
-           fma(sq, L.p[3].d[k], fma(scx, L.p[4].d[k], scy * L.p[5].d[k])))));
+  g[0] = sE;
+  g[1] = st;
+  g[2] = sphi;
+  g[3] = sq;
+  g[4] = scx;
+  g[5] = scy;
 }
 
 // value + whatever lens_vjp needs, for any profile in the gradient's scope
+// FAST: the model holds closed-form profiles only (EPL, SHEAR, NULL) -- the dual-number code is not compiled in, which
+// is what lets that instantiation of k_image_grad run with half the registers.
+template <bool FAST = false>
 LSIM_HD void lens_point(const GLens& L, const double* pool, double x, double y, LensPt& o) {
   if (L.type == LSIM_LENS_EPL) {
     epl_point(L, pool, x, y, o);
@@ -693,6 +715,9 @@ LSIM_HD void lens_point(const GLens& L, const double* pool, double x, double y, 
     const double xs = x - L.c[2].v, ys = y - L.c[3].v;
     o.ax = fma(L.c[1].v, ys, L.c[0].v * xs);
     o.ay = fma(L.c[1].v, xs, -(L.c[0].v * ys));
+  } else if (FAST) {
+    o.ax = 0.0;
+    o.ay = 0.0;
   } else {
     LD fx, fy;
     lens_eval_d(L, pool, x, y, fx, fy);
@@ -706,20 +731,47 @@ LSIM_HD void lens_point(const GLens& L, const double* pool, double x, double y, 
   }
 }
 
-// g_k = d(vx alpha_x + vy alpha_y) / d(parameter k)
+// s_j = d(vx alpha_x + vy alpha_y) / d(primitive j) of the profile.  The primitives are (theta_E, t, phi, q, center_x,
+// center_y) for the EPL, the four parameters for the shear, the parameters themselves otherwise; lens_chain() maps
+// sums of s over any number of points to the parameters (the map is linear and constant per parameter set, so it is
+// applied once per CTA, not once per sub-pixel).
+template <bool FAST = false>
 LSIM_HD void lens_vjp(const GLens& L, const LensPt& o, double x, double y, double vx, double vy, double (&g)[kLensN]) {
   if (L.type == LSIM_LENS_EPL) {
     epl_vjp(L, o, x, y, vx, vy, g);
   } else if (L.type == LSIM_LENS_SHEAR) {  // alpha = (g1 xs + g2 ys, g2 xs - g1 ys)
     const double xs = x - L.c[2].v, ys = y - L.c[3].v;
-    const double s[4] = {fma(vx, xs, -(vy * ys)), fma(vx, ys, vy * xs), -fma(vx, L.c[0].v, vy * L.c[1].v),
-                         fma(vy, L.c[0].v, -(vx * L.c[1].v))};
+    g[0] = fma(vx, xs, -(vy * ys));
+    g[1] = fma(vx, ys, vy * xs);
+    g[2] = -fma(vx, L.c[0].v, vy * L.c[1].v);
+    g[3] = fma(vy, L.c[0].v, -(vx * L.c[1].v));
+    g[4] = 0.0;
+    g[5] = 0.0;
+  } else if (FAST) {
     LSIM_UNROLL
-    for (int k = 0; k < kLensN; ++k)
-      g[k] = fma(s[0], L.c[0].d[k], fma(s[1], L.c[1].d[k], fma(s[2], L.c[2].d[k], s[3] * L.c[3].d[k])));
+    for (int k = 0; k < kLensN; ++k) g[k] = 0.0;
   } else {
     LSIM_UNROLL
     for (int k = 0; k < kLensN; ++k) g[k] = fma(vx, o.s[k], vy * o.s[kLensN + k]);
+  }
+}
+LSIM_HD bool lens_grad_closed_form(const lsim_lens_desc& d) {
+  return d.type == LSIM_LENS_NULL || d.type == LSIM_LENS_SHEAR || lens_grad_has_series(d);
+}
+
+LSIM_HD void lens_chain(const GLens& L, const double (&s)[kLensN], double (&g)[kLensN]) {
+  for (int k = 0; k < kLensN; ++k) {
+    if (L.type == LSIM_LENS_EPL) {
+      double a = 0.0;
+      for (int j = 0; j < 6; ++j) a = fma(s[j], L.p[j].d[k], a);
+      g[k] = a;
+    } else if (L.type == LSIM_LENS_SHEAR) {
+      double a = 0.0;
+      for (int j = 0; j < 4; ++j) a = fma(s[j], L.c[j].d[k], a);
+      g[k] = a;
+    } else {
+      g[k] = s[k];
+    }
   }
 }
 

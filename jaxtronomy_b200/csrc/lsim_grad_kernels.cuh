@@ -14,7 +14,10 @@
 
 namespace lsim {
 
-constexpr int kGradBlock = 256;
+constexpr int kGradBlock = 128;
+#ifndef LSIM_GRAD_FAST_BLOCKS
+#define LSIM_GRAD_FAST_BLOCKS 3  // resident CTAs per SM asked of the closed-form instantiation (register budget 65536 / (128 x this))
+#endif
 constexpr int kGradLightStride = 7;  // entries per light component: its own parameters (SERSIC_ELLIPSE has 7)
 
 __host__ __device__ inline int grad_entries(int n_lens, int n_light) {
@@ -246,14 +249,15 @@ k_conv_adj_edge(const double* __restrict__ in, double* __restrict__ out, int nx,
 // numbers (lsim_grad.cuh).
 // NL > 0: the model has exactly NL lens profiles; their point states stay in registers between the ray shooting and
 // the lens-parameter update.  NL == 0: any number of profiles, each evaluated twice.
+// FAST: every lens profile has closed-form derivatives (EPL, SHEAR): no dual-number code in that instantiation.
 __host__ __device__ inline size_t grad_smem_bytes(int n_lens, int n_light, int n_series) {
   return (size_t)n_lens * sizeof(ad::GLens) + (size_t)n_light * sizeof(ad::GLight) +
          (size_t)n_series * ad::kGradPool * sizeof(double) +
          (size_t)grad_entries(n_lens, n_light) * kGradBlock * sizeof(double);
 }
 
-template <int NL>
-__global__ void __launch_bounds__(kGradBlock)
+template <int NL, bool FAST>
+__global__ void __launch_bounds__(kGradBlock, FAST ? LSIM_GRAD_FAST_BLOCKS : 2)
 k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, int n_series,
              const double* __restrict__ ubar, double wscale, double* __restrict__ partial) {
   using namespace ad;
@@ -300,13 +304,13 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
         if (NL > 0) {
 #pragma unroll
           for (int l = 0; l < NL; ++l) {
-            lens_point(L[l], pool, x, y, pt[l]);
+            lens_point<FAST>(L[l], pool, x, y, pt[l]);
             ax += pt[l].ax;
             ay += pt[l].ay;
           }
         } else {
           for (int l = 0; l < P.n_lens; ++l) {
-            lens_point(L[l], pool, x, y, pt[0]);
+            lens_point<FAST>(L[l], pool, x, y, pt[0]);
             ax += pt[0].ax;
             ay += pt[0].ay;
           }
@@ -333,16 +337,16 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
 #pragma unroll
           for (int l = 0; l < NL; ++l) {
             double gl[kLensN];
-            lens_vjp(L[l], pt[l], x, y, vx, vy, gl);
+            lens_vjp<FAST>(L[l], pt[l], x, y, vx, vy, gl);
             double* e = my + (size_t)l * kLensN * kGradBlock;
 #pragma unroll
             for (int k = 0; k < kLensN; ++k) e[k * kGradBlock] += gl[k];
           }
         } else if (vx != 0.0 || vy != 0.0) {
           for (int l = 0; l < P.n_lens; ++l) {
-            lens_point(L[l], pool, x, y, pt[0]);
+            lens_point<FAST>(L[l], pool, x, y, pt[0]);
             double gl[kLensN];
-            lens_vjp(L[l], pt[0], x, y, vx, vy, gl);
+            lens_vjp<FAST>(L[l], pt[0], x, y, vx, vy, gl);
             double* e = my + (size_t)l * kLensN * kGradBlock;
 #pragma unroll
             for (int k = 0; k < kLensN; ++k) e[k * kGradBlock] += gl[k];
@@ -352,15 +356,36 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
     }
   }
   __syncthreads();
-  // one partial per entry and CTA: warp w reduces entries w, w + 8, ... in a fixed order
+  // one partial per entry and CTA: warp w reduces entries w, w + 8, ... in a fixed order; the lens entries then go
+  // from the profile's primitives to its parameters (lens_chain)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* dst = partial + (bl * gridDim.x + blockIdx.x) * (int64_t)E;
+  double* red = acc;  // entry e lands in acc[e]: the slot of (entry 0, thread e) -- free once entry 0 ... are reduced
+  double sums[52];  // E <= 200 (shared-memory limit checked at plan creation) -> at most 50 entries per warp
+  int n_mine = 0;
   for (int e = wid; e < E; e += kGradBlock / 32) {
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < kGradBlock / 32; ++j) s += acc[e * kGradBlock + lane + 32 * j];
-    s = warp_sum(s);
-    if (lane == 0) dst[e] = s;
+    sums[n_mine++] = warp_sum(s);
+  }
+  __syncthreads();  // every column of acc has been read
+  n_mine = 0;
+  for (int e = wid; e < E; e += kGradBlock / 32) {
+    if (lane == 0) red[e] = sums[n_mine];
+    ++n_mine;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P.n_lens + P.n_light; i += kGradBlock) {
+    if (i < P.n_lens) {
+      double s[kLensN], g[kLensN];
+      for (int k = 0; k < kLensN; ++k) s[k] = red[i * kLensN + k];
+      lens_chain(L[i], s, g);
+      for (int k = 0; k < kLensN; ++k) dst[i * kLensN + k] = g[k];
+    } else {
+      const int o = kLensN * P.n_lens + (i - P.n_lens) * kGradLightStride;
+      for (int k = 0; k < kGradLightStride; ++k) dst[o + k] = red[o + k];
+    }
   }
 }
 

@@ -141,8 +141,9 @@ int hm_lens_vjp(const lsim_lens_desc* lens, int n_lens, const double* row, const
       ad::lens_point(L[i], pool.data(), x[p], y[p], o);
       ax[p] += o.ax;
       ay[p] += o.ay;
-      double gg[ad::kLensN];
-      ad::lens_vjp(L[i], o, x[p], y[p], vx[p], vy[p], gg);
+      double ss[ad::kLensN], gg[ad::kLensN];
+      ad::lens_vjp(L[i], o, x[p], y[p], vx[p], vy[p], ss);
+      ad::lens_chain(L[i], ss, gg);
       for (int k = 0; k < ad::kLensN; ++k) g[((size_t)p * n_lens + i) * ad::kLensN + k] = gg[k];
     }
   }

@@ -37,6 +37,7 @@ LENS_CASES = [
     ("EPL", dict(theta_E=0.9, gamma=1.7, e1=-0.02, e2=0.05, center_x=-0.1, center_y=0.2), None),  # nmax 10
     ("EPL", dict(theta_E=1.4, gamma=2.4, e1=0.45, e2=0.3, center_x=0.0, center_y=0.0), None),  # f = 0.54: nmax 35
     ("EPL", dict(theta_E=1.1, gamma=1.9, e1=-0.55, e2=0.5, center_x=0.0, center_y=0.1), None),  # f = 0.74: nmax 100
+    ("EPL", dict(theta_E=1.0, gamma=2.05, e1=0.7, e2=-0.55, center_x=0.03, center_y=0.0), None),  # f = 0.89: nmax 200
     ("SIE", dict(theta_E=1.1, e1=0.15, e2=0.1, center_x=0.02, center_y=0.01), None),
     ("SIE", dict(theta_E=1.1, e1=0.15, e2=0.1, center_x=0.02, center_y=0.01), {"NIE": False}),
     ("NIE", dict(theta_E=1.3, e1=-0.2, e2=0.12, s_scale=0.3, center_x=0.0, center_y=0.04), None),
@@ -74,7 +75,7 @@ def test_lens_dual_against_oracle(case):
 def test_lens_dual_sum_and_fixed_parameters():
     x, y = grid(5)
     models = ["EPL", "SHEAR", "SIS"]
-    kws = [LENS_CASES[0][1], LENS_CASES[8][1], LENS_CASES[7][1]]
+    kws = [LENS_CASES[0][1], LENS_CASES[9][1], LENS_CASES[8][1]]
     ax, ay, dax, day = hm.lens_jvp(models, kws, x, y)
     rx = sum(olp.derivatives(m, x, y, **k)[0] for m, k in zip(models, kws))
     ry = sum(olp.derivatives(m, x, y, **k)[1] for m, k in zip(models, kws))
