@@ -42,6 +42,20 @@ static ffi::Error LoglImpl(cudaStream_t stream, int64_t plan, int32_t linear, in
                           workspace.element_count() * sizeof(double), stream));
 }
 
+// jax.value_and_grad(LikelihoodModule.logL) (Sampling/Samplers/optax.py:39): logL and d logL / d params; the Python side
+// wraps this handler in a jax.custom_vjp whose backward rule is ct[:, None] * grad
+static ffi::Error LoglGradImpl(cudaStream_t stream, int64_t plan, int32_t linear,
+                               ffi::Buffer<ffi::F64> params,      // [B, P]
+                               ffi::Buffer<ffi::F64> workspace,   // >= lsim_logl_grad_workspace_bytes(plan, 1) / 8
+                               ffi::ResultBuffer<ffi::F64> logl,  // [B]
+                               ffi::ResultBuffer<ffi::F64> grad,  // [B, P]
+                               ffi::ResultBuffer<ffi::F64> amps) {  // [B, n_slots]
+  const int64_t B = params.dimensions()[0];
+  return Status(lsim_logl_grad(Plan(plan), params.typed_data(), B, linear, logl->typed_data(), grad->typed_data(),
+                               linear ? amps->typed_data() : nullptr, workspace.typed_data(),
+                               workspace.element_count() * sizeof(double), stream));
+}
+
 // ImageModel.image / rows of linear_response_matrix (image_model.py:431-492, image_linear_solve.py:361-455)
 static ffi::Error ImageImpl(cudaStream_t stream, int64_t plan, ffi::Buffer<ffi::F64> params,
                             ffi::Buffer<ffi::F64> workspace, ffi::ResultBuffer<ffi::F64> images) {  // [B, n_slots, ny, nx]
@@ -68,6 +82,16 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(LsimLogl, LoglImpl,
                                   .Attr<int32_t>("marg")
                                   .Arg<ffi::Buffer<ffi::F64>>()
                                   .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(LsimLoglGrad, LoglGradImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("plan")
+                                  .Attr<int32_t>("linear")
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
                                   .Ret<ffi::Buffer<ffi::F64>>()
                                   .Ret<ffi::Buffer<ffi::F64>>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(LsimImage, ImageImpl,

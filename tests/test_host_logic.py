@@ -295,3 +295,59 @@ def test_bench_reference_arm_prints_one_json_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1"],
                          capture_output=True, text=True, timeout=60, cwd=root, env=dict(os.environ, RANK="1"))
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# gradient-descent sampler (host logic of Sampling/Samplers/optax.py; the device gradient is tested in test_gpu_grad)
+# ---------------------------------------------------------------------------------------------------------------
+def _rosenbrock_logl(x):
+    f = np.sum(100 * (x[:, 1:] - x[:, :-1] ** 2) ** 2 + (1 - x[:, :-1]) ** 2, axis=1)
+    g = np.zeros_like(x)
+    g[:, :-1] += -400 * x[:, :-1] * (x[:, 1:] - x[:, :-1] ** 2) - 2 * (1 - x[:, :-1])
+    g[:, 1:] += 200 * (x[:, 1:] - x[:, :-1] ** 2)
+    return -f, -g
+
+
+def test_optax_minimizer_batched_lbfgs_converges_inside_the_bounds():
+    from jaxtronomy_b200.Sampling.Samplers.optax import OptaxMinimizer
+
+    n = 5
+    opt = OptaxMinimizer(_rosenbrock_logl, np.zeros(n), np.ones(n), -3 * np.ones(n), 3 * np.ones(n), maxiter=500)
+    best = opt.run(num_chains=6, tol=1e-12, rng_seed=0)
+    np.testing.assert_allclose(best, np.ones(n), atol=1e-5)
+    assert np.all(opt.num_iterations <= 500) and opt.final_logL.shape == (6,)
+    # the chains are advanced together: far fewer batched evaluations than iterations x chains
+    assert opt.num_evaluations < opt.num_iterations.sum()
+    # same seed, same result (NumPy generator, deterministic line search)
+    opt2 = OptaxMinimizer(_rosenbrock_logl, np.zeros(n), np.ones(n), -3 * np.ones(n), 3 * np.ones(n), maxiter=500)
+    np.testing.assert_array_equal(opt2.run(num_chains=6, tol=1e-12, rng_seed=0), best)
+
+
+def test_optax_minimizer_reparametrisation_and_stop_rule():
+    from jaxtronomy_b200.Sampling.Samplers.optax import OptaxMinimizer
+
+    lo, hi = np.array([-1.0, 0.0, 2.0]), np.array([1.0, 10.0, 2.5])
+    opt = OptaxMinimizer(lambda x: (-np.sum((x - 0.3) ** 2, axis=1), -2 * (x - 0.3)), np.zeros(3), np.ones(3), lo, hi,
+                         maxiter=7)
+    x = np.array([[0.2, 3.0, 2.1], [-0.99, 9.99, 2.49]])
+    np.testing.assert_allclose(opt.constrain(opt.unconstrain(x)), x, rtol=1e-12)
+    # every unconstrained point maps inside the box, however far out (numpyro's sigmoid-affine interval transform)
+    far = opt.constrain(np.array([[-800.0, 800.0, 0.0]]))
+    assert np.all(far >= lo) and np.all(far <= hi) and far[0, 2] == 2.25
+    # start points come from the truncated normal: inside the box, reproducible
+    init = opt._draw_init_params(100, 3)
+    assert np.all(init > lo) and np.all(init < hi)
+    np.testing.assert_array_equal(init, opt._draw_init_params(100, 3))
+    # the optimum of the third parameter lies outside its box: the chain walks to the lower edge; maxiter caps the loop
+    u, iters = opt.run_single(opt.unconstrain(np.array([0.0, 5.0, 2.2])), tol=1e-14)
+    assert iters <= 7
+    # loss gradient in the unconstrained space = chain rule through the sigmoid
+    f0, g0 = opt._loss_and_grad(u[None, :])
+    e = 1e-6
+    for j in range(3):
+        d = np.zeros(3)
+        d[j] = e
+        fd = (opt._loss(u + d)[0] - opt._loss(u - d)[0]) / (2 * e)
+        assert abs(g0[0, j] - fd) < 1e-6 * max(1.0, abs(fd))
+    with pytest.raises(ValueError):
+        OptaxMinimizer(_rosenbrock_logl, np.zeros(2), np.ones(2), np.ones(2), np.ones(2))
