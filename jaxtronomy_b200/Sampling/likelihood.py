@@ -1,6 +1,6 @@
 """LikelihoodModule: flat sampler vector -> log-likelihood, jaxtronomy/Sampling/likelihood.py:293-405 and
-Sampling/Likelihoods/image_likelihood.py:56-96 for the imaging likelihood (no priors / position / custom terms:
-out of scope).
+Sampling/Likelihoods/image_likelihood.py:56-96 for the imaging likelihood, plus Gaussian priors on the sampled
+parameters (position / time-delay / flux-ratio / kinematic likelihoods and KDE priors: out of scope).
 
 The reference evaluates ``jit(vmap(logL))`` over the particle axis (Sampling/sampler.py:241-246).  Here the whole
 ``positions[B, n]`` matrix goes to the GPU as is: the plan's column map *is* ``Param.args2kwargs``, the bound check
@@ -15,11 +15,22 @@ __all__ = ["LikelihoodModule"]
 
 
 class LikelihoodModule(object):
-    def __init__(self, image_model, param_class, check_bounds=True, source_marg=False, linear_solver=True):
+    def __init__(self, image_model, param_class, check_bounds=True, source_marg=False, linear_solver=True,
+                 prior_lens=None, prior_source=None, prior_lens_light=None, **unsupported):
         """
         :param image_model: ImageModel / ImageLinearFit / MultiLinear instance (the imaging likelihood)
         :param param_class: jaxtronomy_b200.Sampling.parameters.Param
+        :param prior_lens, prior_source, prior_lens_light: Gaussian priors ``[[index, param_name, mean, sigma], ...]``
+            (the reference forwards them to lenstronomy's PriorLikelihood, Sampling/likelihood.py:155-176, and adds
+            its value to logL, :345-349): logL -= (value - mean)^2 / (2 sigma^2).  Evaluated on the columns of the
+            `positions` matrix on the device; a prior on a fixed parameter is a constant.  lenstronomy is not under
+            /root/reference: the formula is restated (parity unpinned).  KDE / log-normal priors, the position,
+            time-delay, flux-ratio, kinematic and tracer likelihoods are outside the scope: passing
+            them raises.
         """
+        for k, v in unsupported.items():
+            if v:
+                raise ValueError("LikelihoodModule option %s is outside the scope of jaxtronomy_b200" % k)
         self.imSim = image_model
         self.param = param_class
         self._check_bounds = check_bounds
@@ -29,6 +40,40 @@ class LikelihoodModule(object):
         self._n = self.param.num_param()[0]
         self._bounds_dev = None
         self._plans = self.imSim.sampler_plans(self.param, self._n, linear_solver)
+        # Gaussian priors: (column, mean, sigma) of sampled parameters + the constant of priors on fixed ones
+        self._prior_cols, self._prior_const = [], 0.0
+        for comp, priors in (("lens", prior_lens), ("source", prior_source), ("lens_light", prior_lens_light)):
+            for index, name, mean, sigma in (priors or []):
+                key = (comp, int(index), name)
+                if key in self.param._index:
+                    self._prior_cols.append((self.param._index[key], float(mean), float(sigma)))
+                elif name in self.param._fixed[comp][int(index)]:
+                    self._prior_const -= (float(self.param._fixed[comp][int(index)][name]) - mean) ** 2 / sigma**2 / 2
+                else:
+                    raise ValueError("prior on unknown parameter %s of %s model %d" % (name, comp, index))
+        self._prior_dev = None
+
+    def _prior(self, positions, want_grad=False):
+        """Gaussian prior term of every row of `positions` (device tensor) [+ its gradient]."""
+        import torch
+
+        if not self._prior_cols:
+            z = torch.full((positions.shape[0],), self._prior_const, dtype=positions.dtype, device=positions.device)
+            return (z, None) if want_grad else z
+        if self._prior_dev is None or self._prior_dev[0].device != positions.device:
+            cols = torch.as_tensor([c for c, _, _ in self._prior_cols], device=positions.device)
+            mean = torch.as_tensor([m for _, m, _ in self._prior_cols], dtype=positions.dtype, device=positions.device)
+            isig2 = torch.as_tensor([1.0 / s**2 for _, _, s in self._prior_cols], dtype=positions.dtype,
+                                    device=positions.device)
+            self._prior_dev = (cols, mean, isig2)
+        cols, mean, isig2 = self._prior_dev
+        d = positions[:, cols] - mean
+        val = -(d * d * isig2).sum(dim=1) / 2 + self._prior_const
+        if not want_grad:
+            return val
+        grad = torch.zeros_like(positions)
+        grad.index_add_(1, cols, -d * isig2)
+        return val, grad
 
     def __call__(self, a):
         return self.logL(a)
@@ -53,6 +98,8 @@ class LikelihoodModule(object):
             l, _, _ = plan.logl(positions, linear_solve=self._linear_solver, source_marg=self._source_marg)
             l = torch.where(torch.isnan(l), torch.full_like(l, -(10.0**15)), l)  # image_likelihood.py:95
             total = l if total is None else total + l
+        if self._prior_cols or self._prior_const:
+            total = total + self._prior(positions)
         if self._check_bounds:
             if self._bounds_dev is None or self._bounds_dev[0].device != positions.device:
                 self._bounds_dev = (torch.as_tensor(self._lower_limit, device=positions.device),
@@ -82,6 +129,11 @@ class LikelihoodModule(object):
             g = torch.where(bad[:, None], torch.zeros_like(g), g)
             total = l if total is None else total + l
             gtotal = g if gtotal is None else gtotal + g
+        if self._prior_cols or self._prior_const:
+            pv, pg = self._prior(positions, want_grad=True)
+            total = total + pv
+            if pg is not None:
+                gtotal = gtotal + pg
         if self._check_bounds:
             if self._bounds_dev is None or self._bounds_dev[0].device != positions.device:
                 self._bounds_dev = (torch.as_tensor(self._lower_limit, device=positions.device),

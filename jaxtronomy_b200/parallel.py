@@ -60,3 +60,31 @@ def sharded_logl(logl_fn, params, world_size, rank, out=None):
     local = logl_fn(params[lo:hi])
     out[lo:hi] = local
     return all_gather_logl(out, world_size, rank, B)
+
+
+def sharded_logl_grad(logl_grad_fn, params, world_size, rank):
+    """Gradient counterpart of sharded_logl: ``logl_grad_fn(params_slice) -> ([n_local], [n_local, P])`` on this rank's
+    slice, then ONE all-gather of the packed ``[logL | grad]`` rows ((1 + P) x 8 bytes per set) -> ([B], [B, P]) on
+    every rank.  The chains of a gradient-descent run are independent, exactly like the particles of a swarm."""
+    import torch
+
+    B, P = params.shape
+    lo, hi = shard_bounds(B, world_size, rank)
+    logl, grad = logl_grad_fn(params[lo:hi])
+    if world_size == 1:
+        return logl, grad
+    packed = torch.empty((B, P + 1), dtype=torch.float64, device=params.device)
+    packed[lo:hi, 0] = logl
+    packed[lo:hi, 1:] = grad
+    import torch.distributed as dist
+
+    sizes = shard_sizes(B, world_size)
+    m = max(sizes)
+    mine = torch.zeros((m, P + 1), dtype=torch.float64, device=params.device)
+    mine[: hi - lo] = packed[lo:hi]
+    gathered = torch.empty((world_size * m, P + 1), dtype=torch.float64, device=params.device)
+    dist.all_gather_into_tensor(gathered, mine)
+    for r in range(world_size):
+        a, b = shard_bounds(B, world_size, r)
+        packed[a:b] = gathered[r * m: r * m + (b - a)]
+    return packed[:, 0].contiguous(), packed[:, 1:].contiguous()

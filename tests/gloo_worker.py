@@ -14,5 +14,8 @@ full = parallel.sharded_logl(fn, params, world, rank)
 assert torch.equal(full, fn(params)), (rank, full)
 lo, hi = parallel.shard_bounds(n, world, rank)
 assert hi - lo in (n // world, n // world + 1)
+vg = lambda p: ((p**2).sum(dim=1) - 4.0, 2.0 * p)  # noqa: E731
+l, g = parallel.sharded_logl_grad(vg, params, world, rank)
+assert torch.equal(l, fn(params)) and torch.equal(g, 2.0 * params), (rank, l, g)
 dist.destroy_process_group()
 print("OK", rank)

@@ -253,6 +253,16 @@ def test_gradient_descent_sampler_recovers_the_truth():
         e[j] = h
         fd = (like.logL(truth + e) - like.logL(truth - e)) / (2 * h)
         assert abs(g_truth[j] - fd) <= 1e-5 * np.abs(g_truth).max() + 1e-6, (j, g_truth[j], fd)
+    # Gaussian priors add their value and their gradient
+    like_p = LikelihoodModule(lin, param, prior_lens=[[0, "gamma", 2.05, 0.05]], prior_source=[[0, "n_sersic", 2.5, 0.5]])
+    l_p, g_p = like_p.value_and_grad(truth)
+    names = param.num_param()[1]
+    jg, jn = names.index("gamma_lens0"), names.index("n_sersic_source_light0")
+    dl = -(truth[jg] - 2.05) ** 2 / 0.05**2 / 2 - (truth[jn] - 2.5) ** 2 / 0.5**2 / 2
+    assert abs(l_p - (l_truth + dl)) <= 1e-10 * abs(l_truth) and abs(like_p.logL(truth) - l_p) <= 1e-10 * abs(l_p)
+    dg = np.zeros_like(truth)
+    dg[jg], dg[jn] = -(truth[jg] - 2.05) / 0.05**2, -(truth[jn] - 2.5) / 0.5**2
+    np.testing.assert_allclose(g_p, g_truth + dg, rtol=1e-12, atol=1e-12 * np.abs(g_truth).max())
     lo, hi = param.param_limits()
     sigma = 0.02 * np.maximum(np.abs(truth), 0.05)
     opt = OptaxMinimizer(like, truth, sigma, np.asarray(lo), np.asarray(hi), maxiter=200)

@@ -351,3 +351,40 @@ def test_optax_minimizer_reparametrisation_and_stop_rule():
         assert abs(g0[0, j] - fd) < 1e-6 * max(1.0, abs(fd))
     with pytest.raises(ValueError):
         OptaxMinimizer(_rosenbrock_logl, np.zeros(2), np.ones(2), np.ones(2), np.ones(2))
+
+
+def test_likelihood_module_gaussian_priors_value_and_gradient():
+    """Prior term of LikelihoodModule on the columns of the positions matrix (device-agnostic tensor code)."""
+    import torch
+
+    from jaxtronomy_b200.Sampling.likelihood import LikelihoodModule
+    from jaxtronomy_b200.Sampling.parameters import Param
+
+    class NoImage:  # the imaging likelihood needs a GPU; the prior bookkeeping does not
+        def sampler_plans(self, *a, **k):
+            return []
+
+    km = dict(lens_model_list=["EPL", "SHEAR"], source_light_model_list=["SERSIC_ELLIPSE"])
+    param = Param(km, kwargs_fixed_lens=[{"gamma": 2.0}, {"ra_0": 0, "dec_0": 0}])
+    like = LikelihoodModule(NoImage(), param, prior_lens=[[0, "theta_E", 1.2, 0.1], [0, "gamma", 2.1, 0.2],
+                                                          [1, "gamma1", 0.0, 0.05]],
+                            prior_source=[[0, "R_sersic", 0.3, 0.1]])
+    n, names = param.num_param()
+    rng = np.random.default_rng(0)
+    pos = torch.as_tensor(rng.normal(1.0, 0.3, (5, n)))
+    val, grad = like._prior(pos, want_grad=True)
+    j = {nm: i for i, nm in enumerate(names)}
+    x = pos.numpy()
+    want = -((x[:, j["theta_E_lens0"]] - 1.2) ** 2 / 0.1**2 + (x[:, j["gamma1_lens1"]]) ** 2 / 0.05**2
+             + (x[:, j["R_sersic_source_light0"]] - 0.3) ** 2 / 0.1**2) / 2 - (2.0 - 2.1) ** 2 / 0.2**2 / 2
+    np.testing.assert_allclose(val.numpy(), want, rtol=1e-13)
+    g = np.zeros_like(x)
+    g[:, j["theta_E_lens0"]] = -(x[:, j["theta_E_lens0"]] - 1.2) / 0.1**2
+    g[:, j["gamma1_lens1"]] = -x[:, j["gamma1_lens1"]] / 0.05**2
+    g[:, j["R_sersic_source_light0"]] = -(x[:, j["R_sersic_source_light0"]] - 0.3) / 0.1**2
+    np.testing.assert_allclose(grad.numpy(), g, rtol=1e-13)
+    np.testing.assert_array_equal(like._prior(pos).numpy(), val.numpy())
+    with pytest.raises(ValueError):
+        LikelihoodModule(NoImage(), param, prior_lens=[[0, "not_a_parameter", 0.0, 1.0]])
+    with pytest.raises(ValueError):
+        LikelihoodModule(NoImage(), param, time_delay_likelihood=True)
