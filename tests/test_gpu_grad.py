@@ -141,6 +141,48 @@ def test_gradient_is_reproducible_and_chunked_batches_agree():
     assert lin.logL_linear_grad_batch(t[:0])[1].shape == (0, len(names))
 
 
+def test_gradient_batches_larger_than_one_chunk_and_small_workspaces():
+    """The C call walks the batch in chunks of 8 x SMs sets (fewer with a small workspace): rows on both sides of a
+    chunk boundary must equal the same rows evaluated alone, and a workspace for ONE set must give the same numbers."""
+    import ctypes as C
+
+    import torch
+
+    from jaxtronomy_b200 import _lib
+    from tests.test_gpu_parity import build_image_model
+
+    c = IMSIM["subframe_epl_shear"]
+    lin = build_image_model(c, linear=True)
+    names = lin.param_names
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    B = 8 * n_sm + 37
+    mat = _perturbed(_base_row(c, names), names, np.random.default_rng(4), B)
+    t = torch.as_tensor(mat, device="cuda")
+    logl, grad, amps = lin.logL_linear_grad_batch(t)
+    assert torch.isfinite(grad).all()
+    for b in (0, 8 * n_sm - 1, 8 * n_sm, B - 1):
+        l1, g1, a1 = lin.logL_linear_grad_batch(t[b:b + 1])
+        assert torch.equal(l1[0], logl[b]) and torch.equal(a1[0], amps[b])
+        torch.testing.assert_close(g1[0], grad[b], rtol=1e-11, atol=1e-11 * float(grad[b].abs().max()))
+    # the same call through the raw C ABI with the smallest workspace the library accepts (chunks of one set)
+    plan = lin._split_plan()
+    lib = _lib.load()
+    one = int(lib.lsim_logl_grad_workspace_bytes(plan._handle, 1))
+    ws = torch.empty(one // 8 + 1, dtype=torch.float64, device="cuda")
+    n = 5
+    l2 = torch.empty(n, dtype=torch.float64, device="cuda")
+    g2 = torch.empty((n, len(names)), dtype=torch.float64, device="cuda")
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.lsim_logl_grad(plan._handle, t.data_ptr(), n, 1, l2.data_ptr(), g2.data_ptr(), None, ws.data_ptr(), one,
+                            stream)
+    assert rc == 0
+    assert torch.equal(l2, logl[:n])
+    torch.testing.assert_close(g2, grad[:n], rtol=1e-11, atol=1e-11 * float(grad[:n].abs().max()))
+    # too small a workspace is an error code, not a crash
+    assert lib.lsim_logl_grad(plan._handle, t.data_ptr(), n, 1, l2.data_ptr(), g2.data_ptr(), None, ws.data_ptr(),
+                              one // 2, stream) == -4
+
+
 def test_gradient_with_likelihood_mask_and_noise_map():
     """Masked pixels carry no gradient; a noise map makes C_D independent of the model."""
     import torch
