@@ -137,6 +137,8 @@ struct lsim_plan {
   bool grad_fast = false;  // every lens profile has closed-form derivatives (EPL, SHEAR)
   int grad_series = 0;
   size_t grad_smem = 0;
+  const lsim_lens_desc* grad_lens = nullptr;  // device: the gradient's lens list (EPL_MULTIPOLE_M1M3M4 expanded)
+  int n_grad_lens = 0;
   const double* kernel_flip = nullptr;
   const double* kernel_1d_flip = nullptr;
   std::vector<double> kernel_flip_host;
@@ -381,16 +383,21 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
                 (d->conv_mode != LSIM_CONV_EDGE || d->kernel_separable);
       int gs = 0;
       bool fast = true;
-      for (int i = 0; i < d->n_lens; ++i) {
-        fast = fast && ad::lens_grad_closed_form(d->lens[i]);
-        ok = ok && ad::lens_grad_supported(d->lens[i]);
-        gs += ad::lens_grad_has_series(d->lens[i]) ? 1 : 0;
+      std::vector<lsim_lens_desc> gl((size_t)4 * (d->n_lens > 0 ? d->n_lens : 1));
+      const int ngl = ad::expand_grad_lens(d->lens, d->n_lens, gl.data(), (int)gl.size());
+      ok = ok && ngl >= 0;
+      for (int i = 0; ok && i < d->n_lens; ++i) ok = ad::lens_grad_supported(d->lens[i]);
+      for (int i = 0; ok && i < ngl; ++i) {
+        fast = fast && ad::lens_grad_closed_form(gl[i]);
+        gs += ad::lens_grad_has_series(gl[i]) ? 1 : 0;
       }
       for (int i = 0; i < d->n_light; ++i) ok = ok && ad::light_grad_supported(d->light[i]);
       p->grad_series = gs;
       p->grad_fast = fast;
-      p->grad_smem = grad_smem_bytes(d->n_lens, d->n_light, gs);
+      p->n_grad_lens = ok ? ngl : 0;
+      p->grad_smem = grad_smem_bytes(p->n_grad_lens, d->n_light, gs);
       p->grad_ok = ok && p->grad_smem <= kGradSmemMax;
+      if (p->grad_ok && ngl > 0) TRY(p->upload(gl.data(), (size_t)ngl, &p->grad_lens));
       if (p->grad_ok && D.K > 0) {
         const size_t kk = (size_t)d->kernel_size * d->kernel_size;
         p->kernel_flip_host.resize(kk);
@@ -984,13 +991,21 @@ int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, i
 }
 
 // ---- gradient path ---------------------------------------------------------------------------------------------------
+// device view of the plan with the gradient's lens list in place of the forward one
+PlanDev grad_dev(const lsim_plan* plan) {
+  PlanDev G = plan->dev;
+  G.lens = plan->grad_lens;
+  G.n_lens = plan->n_grad_lens;
+  return G;
+}
+
 int grad_max_tiles(const lsim_plan* plan) { return (plan->dev.n_eval + kGradBlock - 1) / kGradBlock; }
 
 size_t grad_per_set_bytes(const lsim_plan* plan) {
   const PlanDev& D = plan->dev;
   const size_t img = (size_t)D.nx * D.ny * D.n_slots;
   return per_set_bytes(plan, true) + img * sizeof(double) +
-         (size_t)grad_max_tiles(plan) * grad_entries(D.n_lens, D.n_light) * sizeof(double);
+         (size_t)grad_max_tiles(plan) * grad_entries(plan->n_grad_lens, D.n_light) * sizeof(double);
 }
 
 template <int NS>
@@ -1037,7 +1052,7 @@ int launch_conv_transposed(const lsim_plan* plan, const double* abar, double* tm
 
 int launch_image_grad(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, const double* ubar,
                       double wscale, double* partial, double* grad, cudaStream_t st) {
-  const PlanDev& D = plan->dev;
+  const PlanDev D = grad_dev(plan);
   const int npix = D.n_eval;
   const int max_tiles = grad_max_tiles(plan);
   int64_t want = ((int64_t)plan->n_sm * 24 + n - 1) / n;  // >= 8 waves of 3 resident CTAs

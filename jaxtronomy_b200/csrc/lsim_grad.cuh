@@ -34,6 +34,11 @@ namespace ad {
 
 constexpr int kLensN = 6;    // tangents carried by a lens profile: its own parameters (param_names order)
 constexpr int kLightN = 9;   // light profile: d/d(x), d/d(y) of the evaluation point, then its own parameters
+constexpr int kLensEntries = 8;  // gradient entries per (pseudo-)profile: 6 tangents + up to 2 closed-form extras
+constexpr int kGradLensMP = 64;  // internal pseudo-profile of the gradient path: ONE multipole (m = 1, 3 or 4) of
+                                 // EPL_MULTIPOLE_M1M3M4 with the parameters (theta_E, e1, e2, center_x, center_y,
+                                 // delta_phi_m, a_m/a): lsim_api.cu expands that 12-parameter profile into an EPL and
+                                 // three of these, whose gradients land in the parent's columns
 constexpr int kTanTerms = 100;                      // hyp2f1_slow, epl.py:283
 // per EPL-family profile: F_n [kMaxSeries] | dF_n/dt [kTanTerms] | Coef4 [kTanTerms] (the four series of the fast path,
 // interleaved so that one term is two 128-bit shared-memory loads)
@@ -413,6 +418,47 @@ LSIM_HD void nie_eval_d(const GLens& L, double x, double y, LD& fx, LD& fy) {
   fy = ar * sph + ai * cph;
 }
 
+// One multipole of EPL_MULTIPOLE_M1M3M4 (epl_multipole_m1m3m4.py:463-535: a_m = a_m/a * theta_E / sqrt(q),
+// phi_m = phi + delta_phi_m, r_E = theta_E for m = 1) at UNIT a_m/a: the deflection is linear in that amplitude, so its
+// derivative is the unit deflection itself and the six tangents go to theta_E, e1, e2, center_x, center_y, delta_phi_m.
+// c[0..4] = cx, cy, theta_E/sqrt(q), phi_m, theta_E;  k[0] = a_m/a;  n_val = m.
+LSIM_HD void mp_prepare_d(GLens& L, int m, const LD& theta_E, const LD& e1, const LD& e2, const LD& cx, const LD& cy,
+                          const LD& delta, double a) {
+  LD phi, q;
+  ellipticity2phi_q_d(e1, e2, phi, q);
+  L.type = kGradLensMP;
+  L.n_val = m;
+  L.c[0] = cx;
+  L.c[1] = cy;
+  L.c[2] = theta_E / dsqrt(q);
+  L.c[3] = phi + delta;
+  L.c[4] = theta_E;
+  L.k[0] = a;
+}
+
+// Multipole.derivatives (multipole.py:72-119) with a_m = c[2]
+LSIM_HD void mp_eval_d(const GLens& L, double x, double y, LD& fx, LD& fy) {
+  const int m = L.n_val;
+  const LD xs = x - L.c[0], ys = y - L.c[1];
+  LD r = dsqrt(xs * xs + ys * ys);
+  const LD phi = datan2(ys, xs);
+  const LD &am = L.c[2], &phim = L.c[3];
+  const LD cphi = dcos(phi), sphi = dsin(phi);
+  if (m == 1) {
+    r = dmax(r, 0.000001);
+    const LD lg = dlog(r / L.c[4]);
+    const LD cd = dcos(phi - phim);
+    fx = am * 0.5 * (dcos(phim) * lg + cd * cphi);
+    fy = am * 0.5 * (dsin(phim) * lg + cd * sphi);
+  } else {
+    const LD A = am / (1.0 - (double)(m * m));
+    const LD arg = (phi - phim) * (double)m;
+    const LD cm = dcos(arg), sm = dsin(arg);
+    fx = cphi * A * cm + sphi * (double)m * A * sm;
+    fy = sphi * A * cm - cphi * (double)m * A * sm;
+  }
+}
+
 // Builds the prepared block of one lens descriptor from the parameter row.  Returns false for a profile outside the
 // gradient's scope.
 LSIM_HD bool lens_prepare_d(const lsim_lens_desc& d, const double* row, GLens& L, double* F, double* dF) {
@@ -437,6 +483,10 @@ LSIM_HD bool lens_prepare_d(const lsim_lens_desc& d, const double* row, GLens& L
       nie_prepare_d(L, lens_var(d, row, 0), lens_var(d, row, 1), lens_var(d, row, 2), lens_var(d, row, 3),
                     lens_var(d, row, 4), lens_var(d, row, 5));
       return true;
+    case kGradLensMP:
+      mp_prepare_d(L, (int)d.opt[0], lens_var(d, row, 0), lens_var(d, row, 1), lens_var(d, row, 2), lens_var(d, row, 3),
+                   lens_var(d, row, 4), lens_var(d, row, 5), param_of(d, row, 6));
+      return true;
     case LSIM_LENS_SIS:
     case LSIM_LENS_SHEAR:
     case LSIM_LENS_CONVERGENCE:
@@ -457,6 +507,8 @@ LSIM_HD bool lens_grad_supported(const lsim_lens_desc& d) {
     case LSIM_LENS_SIS:
     case LSIM_LENS_SHEAR:
     case LSIM_LENS_CONVERGENCE:
+    case LSIM_LENS_EPL_MULTIPOLE_M1M3M4:  // expanded into EPL + three kGradLensMP by the caller
+    case kGradLensMP:
       return true;
     default:
       return false;
@@ -464,6 +516,50 @@ LSIM_HD bool lens_grad_supported(const lsim_lens_desc& d) {
 }
 LSIM_HD bool lens_grad_has_series(const lsim_lens_desc& d) {
   return d.type == LSIM_LENS_EPL || (d.type == LSIM_LENS_SIE && (d.flags & LSIM_FLAG_SIE_NIE_FALSE));
+}
+
+// The gradient path's own lens list: every profile as is, except EPL_MULTIPOLE_M1M3M4 (12 parameters), which becomes an
+// EPL (parameters 0..5) and three kGradLensMP pseudo-profiles (theta_E, e1, e2, center_x, center_y, delta_phi_m,
+// a_m/a) that read the parent's columns / constants -- their gradient entries therefore add up in the parent's columns.
+// Returns the number of descriptors written (<= cap), or -1 if `cap` is too small.
+inline int expand_grad_lens(const lsim_lens_desc* in, int n, lsim_lens_desc* out, int cap) {
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (in[i].type != LSIM_LENS_EPL_MULTIPOLE_M1M3M4) {
+      if (m + 1 > cap) return -1;
+      out[m++] = in[i];
+      continue;
+    }
+    if (m + 4 > cap) return -1;
+    lsim_lens_desc e = in[i];
+    e.type = LSIM_LENS_EPL;
+    for (int k = 6; k < LSIM_MAX_PARAMS; ++k) {
+      e.col[k] = -1;
+      e.cst[k] = 0.0;
+    }
+    out[m++] = e;
+    const int order[3] = {1, 3, 4}, ia[3] = {6, 8, 10}, id[3] = {7, 9, 11};
+    const int src[5] = {0, 2, 3, 4, 5};  // theta_E, e1, e2, center_x, center_y of the parent
+    for (int j = 0; j < 3; ++j) {
+      lsim_lens_desc q = in[i];
+      q.type = kGradLensMP;
+      q.opt[0] = order[j];
+      for (int k = 0; k < LSIM_MAX_PARAMS; ++k) {
+        q.col[k] = -1;
+        q.cst[k] = 0.0;
+      }
+      for (int k = 0; k < 5; ++k) {
+        q.col[k] = in[i].col[src[k]];
+        q.cst[k] = in[i].cst[src[k]];
+      }
+      q.col[5] = in[i].col[id[j]];
+      q.cst[5] = in[i].cst[id[j]];
+      q.col[6] = in[i].col[ia[j]];
+      q.cst[6] = in[i].cst[ia[j]];
+      out[m++] = q;
+    }
+  }
+  return m;
 }
 
 // deflection of one prepared profile at (x, y) with its parameter derivatives
@@ -474,6 +570,11 @@ LSIM_HD void lens_eval_d(const GLens& L, const double* pool, double x, double y,
       break;
     case LSIM_LENS_NIE:
       nie_eval_d(L, x, y, fx, fy);
+      break;
+    case kGradLensMP:
+      mp_eval_d(L, x, y, fx, fy);
+      fx = fx * L.k[0];
+      fy = fy * L.k[0];
       break;
     case LSIM_LENS_SIS: {  // sis.py:35-43: theta_E, center_x, center_y
       const LD xs = x - L.c[1], ys = y - L.c[2];
@@ -571,6 +672,7 @@ LSIM_HD GD light_eval_d(const lsim_light_desc& d, const double* row, const GD& x
 struct LensPt {
   double ax, ay;
   double s[12];
+  double hx, hy;  // kGradLensMP: the unit-amplitude deflection (= d alpha / d amplitude)
 };
 
 // S = sum_n c_n w^n for real c_n by the quadratic-factor (Clenshaw) recurrence  b_k = c_k + 2 Re(w) b_{k+1} -
@@ -685,7 +787,7 @@ LSIM_HD void epl_point(const GLens& L, const double* pool, double x, double y, L
   o.ay = fma(ai, cph, ar * sph);
 }
 
-LSIM_HD void epl_vjp(const GLens& L, const LensPt& o, double x, double y, double vx, double vy, double (&g)[kLensN]) {
+LSIM_HD void epl_vjp(const GLens& L, const LensPt& o, double x, double y, double vx, double vy, double (&g)[kLensEntries]) {
   const double cph = L.k[0], sph = L.k[1];
   const double Vr = fma(vy, sph, vx * cph), Vi = fma(vy, cph, -(vx * sph));  // v in the major-axis frame
   const double sx = fma(Vr, o.s[0], Vi * o.s[1]), sy = fma(Vr, o.s[2], Vi * o.s[3]);
@@ -702,6 +804,8 @@ LSIM_HD void epl_vjp(const GLens& L, const LensPt& o, double x, double y, double
   g[3] = sq;
   g[4] = scx;
   g[5] = scy;
+  g[6] = 0.0;
+  g[7] = 0.0;
 }
 
 // value + whatever lens_vjp needs, for any profile in the gradient's scope
@@ -718,6 +822,18 @@ LSIM_HD void lens_point(const GLens& L, const double* pool, double x, double y, 
   } else if (FAST) {
     o.ax = 0.0;
     o.ay = 0.0;
+  } else if (L.type == kGradLensMP) {
+    LD fx, fy;
+    mp_eval_d(L, x, y, fx, fy);
+    o.hx = fx.v;
+    o.hy = fy.v;
+    o.ax = L.k[0] * fx.v;
+    o.ay = L.k[0] * fy.v;
+    LSIM_UNROLL
+    for (int k = 0; k < kLensN; ++k) {
+      o.s[k] = fx.d[k];
+      o.s[kLensN + k] = fy.d[k];
+    }
   } else {
     LD fx, fy;
     lens_eval_d(L, pool, x, y, fx, fy);
@@ -736,7 +852,10 @@ LSIM_HD void lens_point(const GLens& L, const double* pool, double x, double y, 
 // sums of s over any number of points to the parameters (the map is linear and constant per parameter set, so it is
 // applied once per CTA, not once per sub-pixel).
 template <bool FAST = false>
-LSIM_HD void lens_vjp(const GLens& L, const LensPt& o, double x, double y, double vx, double vy, double (&g)[kLensN]) {
+LSIM_HD void lens_vjp(const GLens& L, const LensPt& o, double x, double y, double vx, double vy,
+                      double (&g)[kLensEntries]) {
+  g[6] = 0.0;
+  g[7] = 0.0;
   if (L.type == LSIM_LENS_EPL) {
     epl_vjp(L, o, x, y, vx, vy, g);
   } else if (L.type == LSIM_LENS_SHEAR) {  // alpha = (g1 xs + g2 ys, g2 xs - g1 ys)
@@ -750,6 +869,10 @@ LSIM_HD void lens_vjp(const GLens& L, const LensPt& o, double x, double y, doubl
   } else if (FAST) {
     LSIM_UNROLL
     for (int k = 0; k < kLensN; ++k) g[k] = 0.0;
+  } else if (L.type == kGradLensMP) {
+    LSIM_UNROLL
+    for (int k = 0; k < kLensN; ++k) g[k] = L.k[0] * fma(vx, o.s[k], vy * o.s[kLensN + k]);
+    g[6] = fma(vx, o.hx, vy * o.hy);
   } else {
     LSIM_UNROLL
     for (int k = 0; k < kLensN; ++k) g[k] = fma(vx, o.s[k], vy * o.s[kLensN + k]);
@@ -759,13 +882,13 @@ LSIM_HD bool lens_grad_closed_form(const lsim_lens_desc& d) {
   return d.type == LSIM_LENS_NULL || d.type == LSIM_LENS_SHEAR || lens_grad_has_series(d);
 }
 
-LSIM_HD void lens_chain(const GLens& L, const double (&s)[kLensN], double (&g)[kLensN]) {
-  for (int k = 0; k < kLensN; ++k) {
-    if (L.type == LSIM_LENS_EPL) {
+LSIM_HD void lens_chain(const GLens& L, const double (&s)[kLensEntries], double (&g)[kLensEntries]) {
+  for (int k = 0; k < kLensEntries; ++k) {
+    if (k < kLensN && L.type == LSIM_LENS_EPL) {
       double a = 0.0;
       for (int j = 0; j < 6; ++j) a = fma(s[j], L.p[j].d[k], a);
       g[k] = a;
-    } else if (L.type == LSIM_LENS_SHEAR) {
+    } else if (k < kLensN && L.type == LSIM_LENS_SHEAR) {
       double a = 0.0;
       for (int j = 0; j < 4; ++j) a = fma(s[j], L.c[j].d[k], a);
       g[k] = a;

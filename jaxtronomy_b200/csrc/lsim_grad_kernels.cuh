@@ -20,8 +20,9 @@ constexpr int kGradBlock = 128;
 #endif
 constexpr int kGradLightStride = 7;  // entries per light component: its own parameters (SERSIC_ELLIPSE has 7)
 
+// n_lens: (pseudo-)profiles of the gradient's own lens list (EPL_MULTIPOLE_M1M3M4 expands into four)
 __host__ __device__ inline int grad_entries(int n_lens, int n_light) {
-  return ad::kLensN * n_lens + kGradLightStride * n_light;
+  return ad::kLensEntries * n_lens + kGradLightStride * n_light;
 }
 
 __host__ __device__ inline int grad_lens_params(int type) {
@@ -32,6 +33,7 @@ __host__ __device__ inline int grad_lens_params(int type) {
     case LSIM_LENS_SIS: return 3;
     case LSIM_LENS_SHEAR: return 4;
     case LSIM_LENS_CONVERGENCE: return 3;
+    case ad::kGradLensMP: return 7;
     default: return 0;
   }
 }
@@ -289,7 +291,7 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
   const int64_t sub_stride = (int64_t)P.nx * ss;
   const double wsub = wscale / ((double)ss * ss);
   const double as = P.ray.alpha_scaling;
-  double* lacc = my + (size_t)kLensN * P.n_lens * kGradBlock;
+  double* lacc = my + (size_t)kLensEntries * P.n_lens * kGradBlock;
   // flux_evaluate_indexes: pixels outside the list have zero flux whatever the parameters are
   const int q_end = min(P.eval_list ? P.n_eval : npix, (int)(blockIdx.x + 1) * ppt);
   for (int q = blockIdx.x * ppt + threadIdx.x; q < q_end; q += kGradBlock) {
@@ -336,20 +338,20 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
         if (NL > 0) {
 #pragma unroll
           for (int l = 0; l < NL; ++l) {
-            double gl[kLensN];
+            double gl[kLensEntries];
             lens_vjp<FAST>(L[l], pt[l], x, y, vx, vy, gl);
-            double* e = my + (size_t)l * kLensN * kGradBlock;
+            double* e = my + (size_t)l * kLensEntries * kGradBlock;
 #pragma unroll
-            for (int k = 0; k < kLensN; ++k) e[k * kGradBlock] += gl[k];
+            for (int k = 0; k < (FAST ? kLensN : kLensEntries); ++k) e[k * kGradBlock] += gl[k];
           }
         } else if (vx != 0.0 || vy != 0.0) {
           for (int l = 0; l < P.n_lens; ++l) {
             lens_point<FAST>(L[l], pool, x, y, pt[0]);
-            double gl[kLensN];
+            double gl[kLensEntries];
             lens_vjp<FAST>(L[l], pt[0], x, y, vx, vy, gl);
-            double* e = my + (size_t)l * kLensN * kGradBlock;
+            double* e = my + (size_t)l * kLensEntries * kGradBlock;
 #pragma unroll
-            for (int k = 0; k < kLensN; ++k) e[k * kGradBlock] += gl[k];
+            for (int k = 0; k < (FAST ? kLensN : kLensEntries); ++k) e[k * kGradBlock] += gl[k];
           }
         }
       }
@@ -378,12 +380,12 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
   __syncthreads();
   for (int i = threadIdx.x; i < P.n_lens + P.n_light; i += kGradBlock) {
     if (i < P.n_lens) {
-      double s[kLensN], g[kLensN];
-      for (int k = 0; k < kLensN; ++k) s[k] = red[i * kLensN + k];
+      double s[kLensEntries], g[kLensEntries];
+      for (int k = 0; k < kLensEntries; ++k) s[k] = red[i * kLensEntries + k];
       lens_chain(L[i], s, g);
-      for (int k = 0; k < kLensN; ++k) dst[i * kLensN + k] = g[k];
+      for (int k = 0; k < kLensEntries; ++k) dst[i * kLensEntries + k] = g[k];
     } else {
-      const int o = kLensN * P.n_lens + (i - P.n_lens) * kGradLightStride;
+      const int o = kLensEntries * P.n_lens + (i - P.n_lens) * kGradLightStride;
       for (int k = 0; k < kGradLightStride; ++k) dst[o + k] = red[o + k];
     }
   }
@@ -409,14 +411,14 @@ k_grad_reduce(PlanDev P, const double* __restrict__ partial, int tiles, int64_t 
     for (int l = 0; l < P.n_lens; ++l) {
       const int np = grad_lens_params(P.lens[l].type);
       for (int k = 0; k < np; ++k)
-        if (P.lens[l].col[k] == c) s += s_e[l * ad::kLensN + k];
+        if (P.lens[l].col[k] == c) s += s_e[l * ad::kLensEntries + k];
     }
     for (int gi = 0; gi < P.n_light; ++gi) {
       const lsim_light_desc& d = P.light[gi];
       if (d.slot < 0) continue;
       const int np = grad_light_params(d.type);
       for (int k = 0; k < np; ++k)
-        if (d.col[k] == c && !(k == 0 && !d.use_amp)) s += s_e[ad::kLensN * P.n_lens + gi * kGradLightStride + k];
+        if (d.col[k] == c && !(k == 0 && !d.use_amp)) s += s_e[ad::kLensEntries * P.n_lens + gi * kGradLightStride + k];
     }
     g[c] = s;
   }

@@ -141,7 +141,7 @@ int hm_lens_vjp(const lsim_lens_desc* lens, int n_lens, const double* row, const
       ad::lens_point(L[i], pool.data(), x[p], y[p], o);
       ax[p] += o.ax;
       ay[p] += o.ay;
-      double ss[ad::kLensN], gg[ad::kLensN];
+      double ss[ad::kLensEntries], gg[ad::kLensEntries];
       ad::lens_vjp(L[i], o, x[p], y[p], vx[p], vy[p], ss);
       ad::lens_chain(L[i], ss, gg);
       for (int k = 0; k < ad::kLensN; ++k) g[((size_t)p * n_lens + i) * ad::kLensN + k] = gg[k];
@@ -163,6 +163,39 @@ int hm_light_point(const lsim_light_desc* light, const double* row, const double
     dout[(size_t)p * 9] = Ix;
     dout[(size_t)p * 9 + 1] = Iy;
     for (int k = 0; k < ad::kLightG; ++k) dout[(size_t)p * 9 + 2 + k] = g[k];
+  }
+  return 0;
+}
+
+// EPL_MULTIPOLE_M1M3M4 through the gradient path's expansion (EPL + three multipole pseudo-profiles):
+//   ax, ay [N]; g [N][12] = d(vx alpha_x + vy alpha_y)/d(parameter k), param_names order
+int hm_eplm_vjp(const lsim_lens_desc* lens, const double* row, const double* x, const double* y, int64_t N,
+                const double* vx, const double* vy, double* ax, double* ay, double* g) {
+  lsim_lens_desc ex[4];
+  const int n = ad::expand_grad_lens(lens, 1, ex, 4);
+  if (n != 4) return -2;
+  std::vector<ad::GLens> L(n);
+  std::vector<double> pool((size_t)2 * ad::kGradPool);
+  for (int i = 0; i < n; ++i) {
+    L[i].coef_off = 0;
+    if (!ad::lens_prepare_d(ex[i], row, L[i], pool.data(), pool.data() + kMaxSeries)) return -2;
+  }
+  for (int64_t p = 0; p < N; ++p) {
+    ax[p] = ay[p] = 0.0;
+    for (int k = 0; k < 12; ++k) g[p * 12 + k] = 0.0;
+    for (int i = 0; i < n; ++i) {
+      ad::LensPt o;
+      ad::lens_point(L[i], pool.data(), x[p], y[p], o);
+      ax[p] += o.ax;
+      ay[p] += o.ay;
+      double ss[ad::kLensEntries], gg[ad::kLensEntries];
+      ad::lens_vjp(L[i], o, x[p], y[p], vx[p], vy[p], ss);
+      ad::lens_chain(L[i], ss, gg);
+      for (int k = 0; k < ad::kLensEntries; ++k) {
+        const int c = ex[i].col[k];  // the harness gives every parent parameter its own column = its index
+        if (k < (i == 0 ? 6 : 7) && c >= 0) g[p * 12 + c] += gg[k];
+      }
+    }
   }
   return 0;
 }

@@ -43,6 +43,7 @@ def lib():
         h.hm_light_jvp.argtypes = [C.POINTER(_lib.LightDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp]
         h.hm_light_point.argtypes = [C.POINTER(_lib.LightDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp]
         h.hm_lens_vjp.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp]
+        h.hm_eplm_vjp.argtypes = [C.POINTER(_lib.LensDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp]
         _h = h
     return _h
 
@@ -161,3 +162,17 @@ def light_jvp(light_model, kwargs, x, y, use_amp=True, fast=False):
     rc = fn(C.byref(desc), _p(row), _p(x), _p(y), x.size, _p(out), _p(dout))
     assert rc == 0, rc
     return out, dout
+
+
+def eplm_vjp(kwargs, x, y, vx, vy):
+    """EPL_MULTIPOLE_M1M3M4 through the gradient path's expansion: (alpha_x, alpha_y, g [N, 12])."""
+    names = [_model.LENS_PARAM_NAMES["EPL_MULTIPOLE_M1M3M4"]]
+    row = np.asarray(_model.gather_values(names, [kwargs]), dtype=np.float64)
+    layout = _model.ColumnLayout()
+    desc = _model.lens_desc("EPL_MULTIPOLE_M1M3M4", layout.add_profile("lens", 0, names[0]), {})
+    x, y, vx, vy = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, vx, vy))
+    ax, ay = np.empty_like(x), np.empty_like(y)
+    g = np.empty((x.size, 12))
+    rc = lib().hm_eplm_vjp(C.byref(desc), _p(row), _p(x), _p(y), x.size, _p(vx), _p(vy), _p(ax), _p(ay), _p(g))
+    assert rc == 0, rc
+    return ax, ay, g

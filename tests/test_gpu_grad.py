@@ -70,12 +70,14 @@ def _perturbed(base, names, rng, B):
     for j, (comp, i, n) in enumerate(names):
         if n in ("theta_E", "gamma", "R_sersic", "n_sersic"):
             mat[1:, j] *= 1 + rng.normal(0, 0.02, B - 1)
-        elif n in ("e1", "e2", "gamma1", "gamma2", "center_x", "center_y"):
+        elif n in ("e1", "e2", "gamma1", "gamma2", "center_x", "center_y", "a1_a", "a3_a", "a4_a", "delta_phi_m1",
+                   "delta_phi_m3", "delta_phi_m4"):
             mat[1:, j] += rng.normal(0, 0.01, B - 1)
     return mat
 
 
-GRAD_CASES = ["headline_epl_shear_pixel", "c1_sie_shear_gauss", "linear_sis_3comp", "subframe_epl_shear"]
+GRAD_CASES = ["headline_epl_shear_pixel", "c1_sie_shear_gauss", "linear_sis_3comp", "subframe_epl_shear",
+              "c3_multipole_noise_map"]
 
 
 @pytest.mark.parametrize("linear", [True, False])
@@ -258,12 +260,28 @@ def test_models_outside_the_gradient_scope_are_refused():
     from jaxtronomy_b200 import _lib
     from tests.test_gpu_parity import build_image_model
 
-    for name in ("c3_multipole_noise_map", "ss_conv_sie_shear"):
-        c = IMSIM[name]
-        lin = build_image_model(c, linear=True)
-        row = _base_row(c, lin.param_names)
-        with pytest.raises(_lib.LsimError):
-            lin.logL_linear_grad_batch(torch.as_tensor(row[None, :], device="cuda"))
+    c = IMSIM["ss_conv_sie_shear"]  # supersampled convolution
+    lin = build_image_model(c, linear=True)
+    row = _base_row(c, lin.param_names)
+    with pytest.raises(_lib.LsimError):
+        lin.logL_linear_grad_batch(torch.as_tensor(row[None, :], device="cuda"))
+    # a lens profile without derivative code (NFW) in an otherwise supported configuration
+    from bench import build_headline
+    from jaxtronomy_b200.Data.imaging_data import ImageData
+    from jaxtronomy_b200.Data.psf import PSF
+    from jaxtronomy_b200.ImSim.image_linear_solve import ImageLinearFit
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+    from jaxtronomy_b200.LightModel.light_model import LightModel
+
+    cfg = build_headline(num_pix=24, ss=1, kernel_size=5, n_sets=1, seed=1)
+    st = cfg["static"]
+    nfw = ImageLinearFit(ImageData(image_data=cfg["data_image"], **st["kwargs_data"]),
+                         PSF(psf_type="PIXEL", kernel_point_source=st["kernel"]), LensModel(["NFW"]),
+                         LightModel(["SERSIC"]), LightModel([]), kwargs_numerics=dict(supersampling_factor=1))
+    row = torch.tensor([[1.0, 0.5, 0.0, 0.0, 1.0, 0.3, 2.0, 0.0, 0.0]], device="cuda", dtype=torch.float64)
+    assert torch.isfinite(nfw.logL_linear_batch(row)[0]).all()
+    with pytest.raises(_lib.LsimError):
+        nfw.logL_linear_grad_batch(row)
 
 
 def test_gradient_descent_sampler_recovers_the_truth():

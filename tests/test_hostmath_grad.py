@@ -149,3 +149,27 @@ def test_hand_derived_light_gradient_equals_the_dual_numbers(case, use_amp):
             continue  # the amplitude is not a parameter then; the kernel never reads that entry
         tol = 1e-11 * max(np.abs(d0[:, k]).max(), 1e-300)
         assert np.abs(d1[:, k] - d0[:, k]).max() <= tol, (name, k, np.abs(d1[:, k] - d0[:, k]).max(), tol)
+
+
+def test_epl_multipole_gradient_through_the_expansion():
+    """EPL_MULTIPOLE_M1M3M4 = EPL (closed form) + three multipole pseudo-profiles (dual numbers, unit amplitude) whose
+    gradients land in the parent's twelve parameters: against finite differences of the oracle."""
+    kw = dict(theta_E=1.15, gamma=2.08, e1=0.18, e2=-0.11, center_x=0.04, center_y=-0.02, a1_a=0.03, delta_phi_m1=0.4,
+              a3_a=-0.02, delta_phi_m3=0.25, a4_a=0.015, delta_phi_m4=-0.3)
+    names = olp.PARAM_NAMES["EPL_MULTIPOLE_M1M3M4"]
+    x, y = grid(9)
+    rng = np.random.default_rng(12)
+    vx, vy = rng.normal(size=x.size), rng.normal(size=x.size)
+    ax, ay, g = hm.eplm_vjp(kw, x, y, vx, vy)
+    p0 = [kw[n] for n in names]
+
+    def fun(p):
+        return olp.derivatives("EPL_MULTIPOLE_M1M3M4", x, y, **dict(zip(names, p)))
+
+    rx, ry = fun(p0)
+    assert np.allclose(ax, rx, rtol=1e-10, atol=1e-12) and np.allclose(ay, ry, rtol=1e-10, atol=1e-12)
+    for i, n in enumerate(names):
+        d = fd(fun, p0, i, 1e-4)
+        ref = vx * d[0] + vy * d[1]
+        tol = FD_TOL * max(np.abs(ref).max(), 1e-3)
+        assert np.abs(g[:, i] - ref).max() <= tol, (n, np.abs(g[:, i] - ref).max(), tol)
