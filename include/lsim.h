@@ -266,7 +266,7 @@ int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear
  *   grad       device [B, P]: d logl[b] / d params[b, :]; columns no profile reads are 0; with linear_solve the
  *              amplitudes are functions of the other parameters (solved per set), not parameters
  *   amps       device [B, n_slots] or NULL (linear_solve only)
- * Scope: single plane; EPL, EPL_MULTIPOLE_M1M3M4, SIE, NIE, SIS, SHEAR, CONVERGENCE; SERSIC, SERSIC_ELLIPSE, GAUSSIAN; PSF none, pixel
+ * Scope: single plane; every lens profile of this header; SERSIC, SERSIC_ELLIPSE, GAUSSIAN; PSF none, pixel
  * kernel (zero boundary) or separable Gaussian (edge-replicated); regular convolution; no point sources; fp64.
  * Anything else: LSIM_E_UNSUPPORTED (never a finite-difference or CPU fallback).  Results are bit-reproducible
  * run to run (fixed reduction order, no atomics).  Workspace: lsim_logl_grad_workspace_bytes (less is accepted,

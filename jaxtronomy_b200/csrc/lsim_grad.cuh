@@ -189,6 +189,13 @@ template <int N>
 LSIM_HD Dual<N> datan(const Dual<N>& a) { return chain(a, atan(a.v), 1.0 / fma(a.v, a.v, 1.0)); }
 template <int N>
 LSIM_HD Dual<N> datanh(const Dual<N>& a) { return chain(a, atanh(a.v), 1.0 / fma(-a.v, a.v, 1.0)); }
+template <int N>
+LSIM_HD Dual<N> dacosh(const Dual<N>& a) {
+  const double r = sqrt(fma(a.v, a.v, -1.0));
+  return chain(a, log(a.v + r), 1.0 / r);
+}
+template <int N>
+LSIM_HD Dual<N> dacos(const Dual<N>& a) { return chain(a, acos(a.v), -1.0 / sqrt(fma(-a.v, a.v, 1.0))); }
 // a^b for a > 0
 template <int N>
 LSIM_HD Dual<N> dpow(const Dual<N>& a, const Dual<N>& b) {
@@ -459,6 +466,146 @@ LSIM_HD void mp_eval_d(const GLens& L, double x, double y, LD& fx, LD& fy) {
   }
 }
 
+// ---- NFW / TNFW / MULTIPOLE / CSE family on dual numbers (literal restatements; nfw.py:88-105,259-279,347-365,
+// tnfw.py:69-87,228-349, multipole.py:72-119, cored_steep_ellipsoid.py:107-132,227-245,434-477,536-564,
+// nfw_ellipse_cse.py:250-280,338-349, hernquist_ellipse_cse.py:151-164,190-202) --------------------------------------
+LSIM_HD LD nfw_g_d(LD X) {
+  if (X.v < 0.000001) X = cst<kLensN>(0.000001);
+  if (X.v < 1) return dlog(X * 0.5) + dacosh(1.0 / X) / dsqrt(1.0 - X * X);
+  if (X.v == 1) return cst<kLensN>(1 + log(0.5));
+  return dlog(X * 0.5) + dacos(1.0 / X) / dsqrt(X * X - 1.0);
+}
+LSIM_HD LD alpha2rho0_d(const LD& alpha_Rs, const LD& Rs) { return alpha_Rs / (4.0 * (Rs * Rs) * (1.0 + log(0.5))); }
+
+// c[0..3] = Rs (clamped), 4 rho0 Rs, cx, cy
+LSIM_HD void nfw_eval_d(const GLens& L, double x, double y, LD& fx, LD& fy) {
+  const LD xs = x - L.c[2], ys = y - L.c[3];
+  const LD R = dmax(dsqrt(xs * xs + ys * ys), 0.00000001);
+  const LD X = R / L.c[0];
+  const LD a = L.c[1] * nfw_g_d(X) / (X * X);
+  fx = a * xs;
+  fy = a * ys;
+}
+
+LSIM_HD LD tnfw_F_d(LD x) {
+  x = dmax(x, 0.001);
+  if (x.v < 1) {
+    const LD r = dsqrt(1.0 - x * x);
+    return datanh(r) / r;
+  }
+  if (x.v > 1) {
+    const LD r = dsqrt(x * x - 1.0);
+    return datan(r) / r;
+  }
+  return x;
+}
+// c[0..4] = Rs, 4 rho0 Rs, tau, cx, cy
+LSIM_HD void tnfw_eval_d(const GLens& L, double x, double y, LD& fx, LD& fy) {
+  const LD &Rs = L.c[0], &tau = L.c[2];
+  const LD xs = x - L.c[3], ys = y - L.c[4];
+  LD R = dsqrt(xs * xs + ys * ys);
+  if (R.v < 0.001 * Rs.v) R = Rs * 0.001;  // jnp.maximum(R, s * Rs): the tangent of the larger argument
+  const LD X = dmax(R / Rs, 0.001);
+  const LD t2 = tau * tau;
+  const LD st = dsqrt(t2 + X * X);
+  const LD Lx = dlog(X / (tau + st));
+  const LD g = t2 / ((t2 + 1.0) * (t2 + 1.0)) *
+               ((t2 + 1.0 + 2.0 * (X * X - 1.0)) * tnfw_F_d(X) + tau * kPi + (t2 - 1.0) * dlog(tau) +
+                st * (Lx * (t2 - 1.0) / tau - kPi));
+  const LD a = L.c[1] * g / (X * X);
+  fx = a * xs;
+  fy = a * ys;
+}
+
+// MULTIPOLE: c[0..4] = cx, cy, a_m, phi_m, r_E; n_val = m (not differentiable)
+// (shares mp_eval_d with the pseudo-profile below: unit scale k[0] = 1)
+
+// CSE major axis / product average at (x, y) in the major-axis frame, generic in the tangent width
+template <int N>
+LSIM_HD void cse_major_d(const Dual<N>& x, const Dual<N>& y, double a, double s, const Dual<N>& q, Dual<N>& fx,
+                         Dual<N>& fy) {
+  const Dual<N> q2 = q * q;
+  const Dual<N> psi = dsqrt(q2 * (x * x + s * s) + y * y);
+  const Dual<N> ps = psi + s;
+  const Dual<N> Phi = ps * ps + (1.0 - q2) * (x * x);
+  const Dual<N> den = a / (s * psi * Phi);
+  fx = q * x * (psi + q2 * s) * den;
+  fy = q * y * ps * den;
+}
+template <int N>
+LSIM_HD void cse_prodavg_d(const Dual<N>& x, const Dual<N>& y, double a, double s, const Dual<N>& q, Dual<N>& fx,
+                           Dual<N>& fy) {
+  const Dual<N> sq = dsqrt(q);
+  Dual<N> gx, gy;
+  cse_major_d(x * sq, y * sq, 1.0, s, q, gx, gy);
+  const Dual<N> f = (a / q) * sq;
+  fx = f * gx;
+  fy = f * gy;
+}
+
+// Sum over a CSE table at (X, Y, q) on Dual<3> (d/dX, d/dY, d/dq), then composed with the six-wide duals of X, Y, q:
+// the 44 / 41 / 16 components are evaluated with 3 tangents instead of 6.
+LSIM_HD void cse_set_d(bool product_avg, const double* A, const double* S, int n, const LD& X, const LD& Y, const LD& q,
+                       LD& fx, LD& fy) {
+  using D3 = Dual<3>;
+  const D3 x3 = var<3>(X.v, 0), y3 = var<3>(Y.v, 1), q3 = var<3>(q.v, 2);
+  D3 sx = cst<3>(0.0), sy = cst<3>(0.0);
+  for (int i = 0; i < n; ++i) {
+    D3 gx, gy;
+    if (product_avg)
+      cse_prodavg_d(x3, y3, A[i], S[i], q3, gx, gy);
+    else
+      cse_major_d(x3, y3, A[i], S[i], q3, gx, gy);
+    sx = sx + gx;
+    sy = sy + gy;
+  }
+  fx.v = sx.v;
+  fy.v = sy.v;
+  LSIM_UNROLL
+  for (int k = 0; k < kLensN; ++k) {
+    fx.d[k] = fma(sx.d[0], X.d[k], fma(sx.d[1], Y.d[k], sx.d[2] * q.d[k]));
+    fy.d[k] = fma(sy.d[0], X.d[k], fma(sy.d[1], Y.d[k], sy.d[2] * q.d[k]));
+  }
+}
+
+// CSE / NFW_ELLIPSE_CSE / HERNQUIST_ELLIPSE_CSE: c[0..6] = cx, cy, cos phi, sin phi, q, 1/Rs (1 for CSE), const;
+// k[0] = a, k[1] = s (CSE); flags as in the descriptor
+LSIM_HD void cse_family_eval_d(const GLens& L, uint32_t flags, double x, double y, LD& fx, LD& fy) {
+  const LD &cph = L.c[2], &sph = L.c[3], &q = L.c[4];
+  const LD xs = x - L.c[0], ys = y - L.c[1];
+  const LD xr = (xs * cph + ys * sph) * L.c[5], yr = (ys * cph - xs * sph) * L.c[5];
+  LD gx, gy;
+  if (L.n_tan == LSIM_LENS_CSE) {
+    // the amplitude and core are parameters here: evaluate directly on the six-wide duals
+    const LD &a = L.c[6], &sc = L.c[7];
+    const bool major = (flags & LSIM_FLAG_CSE_MAJOR) != 0;
+    const LD sq = major ? cst<kLensN>(1.0) : dsqrt(q);
+    const LD X = xr * sq, Y = yr * sq;
+    const LD q2 = q * q;
+    const LD psi = dsqrt(q2 * (X * X + sc * sc) + Y * Y);
+    const LD ps = psi + sc;
+    const LD Phi = ps * ps + (1.0 - q2) * (X * X);
+    const LD amp = major ? a : (a / q) * sq;
+    const LD den = amp / (sc * psi * Phi);
+    gx = q * X * (psi + q2 * sc) * den;
+    gy = q * Y * ps * den;
+  } else if (L.n_tan == LSIM_LENS_NFW_ELLIPSE_CSE) {
+    const bool low = (flags & LSIM_FLAG_CSE_LOW_ACCURACY) != 0;
+    cse_set_d(true, cse_table(low ? 3 : 1), cse_table(low ? 2 : 0), low ? LSIM_NFW_CSE_LOW_S_N : LSIM_NFW_CSE_HIGH_S_N,
+              xr, yr, q, gx, gy);
+    gx = gx * L.c[6];
+    gy = gy * L.c[6];
+  } else {
+    cse_set_d(false, cse_table(5), cse_table(4), LSIM_HERNQUIST_CSE_S_N, xr, yr, q, gx, gy);
+    gx = gx * L.c[6];
+    gy = gy * L.c[6];
+  }
+  fx = gx * cph - gy * sph;
+  fy = gx * sph + gy * cph;
+}
+
+constexpr int kGradLensCSEFamily = 65;  // prepared type of CSE / NFW_ELLIPSE_CSE / HERNQUIST_ELLIPSE_CSE (n_tan = which)
+
 // Builds the prepared block of one lens descriptor from the parameter row.  Returns false for a profile outside the
 // gradient's scope.
 LSIM_HD bool lens_prepare_d(const lsim_lens_desc& d, const double* row, GLens& L, double* F, double* dF) {
@@ -483,7 +630,69 @@ LSIM_HD bool lens_prepare_d(const lsim_lens_desc& d, const double* row, GLens& L
       nie_prepare_d(L, lens_var(d, row, 0), lens_var(d, row, 1), lens_var(d, row, 2), lens_var(d, row, 3),
                     lens_var(d, row, 4), lens_var(d, row, 5));
       return true;
+    case LSIM_LENS_NFW: {
+      const LD Rs0 = lens_var(d, row, 0), aRs = lens_var(d, row, 1);
+      const LD rho0 = alpha2rho0_d(aRs, Rs0);
+      const LD Rs = (Rs0.v < 0.0000001) ? cst<kLensN>(0.0000001) : Rs0;
+      L.type = LSIM_LENS_NFW;
+      L.c[0] = Rs;
+      L.c[1] = 4.0 * rho0 * Rs;
+      L.c[2] = lens_var(d, row, 2);
+      L.c[3] = lens_var(d, row, 3);
+      return true;
+    }
+    case LSIM_LENS_TNFW: {
+      const LD Rs = lens_var(d, row, 0), aRs = lens_var(d, row, 1), rt = lens_var(d, row, 2);
+      L.type = LSIM_LENS_TNFW;
+      L.c[0] = Rs;
+      L.c[1] = 4.0 * alpha2rho0_d(aRs, Rs) * Rs;
+      L.c[2] = rt / Rs;
+      L.c[3] = lens_var(d, row, 3);
+      L.c[4] = lens_var(d, row, 4);
+      return true;
+    }
+    case LSIM_LENS_MULTIPOLE:  // m, a_m, phi_m, center_x, center_y, r_E; m is an integer, not differentiable
+      L.type = kGradLensMP;
+      L.n_val = (int)param_of(d, row, 0);
+      L.c[0] = lens_var(d, row, 3);
+      L.c[1] = lens_var(d, row, 4);
+      L.c[2] = lens_var(d, row, 1);
+      L.c[3] = lens_var(d, row, 2);
+      L.c[4] = lens_var(d, row, 5);
+      L.k[0] = 1.0;
+      L.k[1] = 1.0;  // a plain MULTIPOLE: its tangents are the parameters' own (no amplitude entry)
+      return true;
+    case LSIM_LENS_CSE:
+    case LSIM_LENS_NFW_ELLIPSE_CSE:
+    case LSIM_LENS_HERNQUIST_ELLIPSE_CSE: {
+      LD phi, q;
+      ellipticity2phi_q_d(lens_var(d, row, 2), lens_var(d, row, 3), phi, q);
+      L.type = kGradLensCSEFamily;
+      L.n_tan = d.type;
+      L.n_val = (int)d.flags;
+      L.c[0] = lens_var(d, row, 4);
+      L.c[1] = lens_var(d, row, 5);
+      L.c[2] = dcos(phi);
+      L.c[3] = dsin(phi);
+      L.c[4] = q;
+      if (d.type == LSIM_LENS_CSE) {
+        L.c[5] = cst<kLensN>(1.0);
+        L.c[6] = lens_var(d, row, 0);
+        L.c[7] = lens_var(d, row, 1);
+      } else if (d.type == LSIM_LENS_NFW_ELLIPSE_CSE) {
+        const LD Rs = lens_var(d, row, 0);
+        L.c[5] = 1.0 / Rs;
+        L.c[6] = 4.0 * alpha2rho0_d(lens_var(d, row, 1), Rs) * (Rs * Rs * Rs) / Rs;
+      } else {
+        const LD sigma0 = lens_var(d, row, 0), Rs = lens_var(d, row, 1);
+        const LD rs_ = Rs / dsqrt(q);
+        L.c[5] = 1.0 / Rs;
+        L.c[6] = sigma0 * (rs_ * rs_) / Rs;
+      }
+      return true;
+    }
     case kGradLensMP:
+      L.k[1] = 0.0;
       mp_prepare_d(L, (int)d.opt[0], lens_var(d, row, 0), lens_var(d, row, 1), lens_var(d, row, 2), lens_var(d, row, 3),
                    lens_var(d, row, 4), lens_var(d, row, 5), param_of(d, row, 6));
       return true;
@@ -509,6 +718,12 @@ LSIM_HD bool lens_grad_supported(const lsim_lens_desc& d) {
     case LSIM_LENS_CONVERGENCE:
     case LSIM_LENS_EPL_MULTIPOLE_M1M3M4:  // expanded into EPL + three kGradLensMP by the caller
     case kGradLensMP:
+    case LSIM_LENS_NFW:
+    case LSIM_LENS_TNFW:
+    case LSIM_LENS_MULTIPOLE:
+    case LSIM_LENS_CSE:
+    case LSIM_LENS_NFW_ELLIPSE_CSE:
+    case LSIM_LENS_HERNQUIST_ELLIPSE_CSE:
       return true;
     default:
       return false;
@@ -575,6 +790,15 @@ LSIM_HD void lens_eval_d(const GLens& L, const double* pool, double x, double y,
       mp_eval_d(L, x, y, fx, fy);
       fx = fx * L.k[0];
       fy = fy * L.k[0];
+      break;
+    case LSIM_LENS_NFW:
+      nfw_eval_d(L, x, y, fx, fy);
+      break;
+    case LSIM_LENS_TNFW:
+      tnfw_eval_d(L, x, y, fx, fy);
+      break;
+    case kGradLensCSEFamily:
+      cse_family_eval_d(L, (uint32_t)L.n_val, x, y, fx, fy);
       break;
     case LSIM_LENS_SIS: {  // sis.py:35-43: theta_E, center_x, center_y
       const LD xs = x - L.c[1], ys = y - L.c[2];

@@ -34,6 +34,12 @@ __host__ __device__ inline int grad_lens_params(int type) {
     case LSIM_LENS_SHEAR: return 4;
     case LSIM_LENS_CONVERGENCE: return 3;
     case ad::kGradLensMP: return 7;
+    case LSIM_LENS_NFW: return 4;
+    case LSIM_LENS_TNFW: return 5;
+    case LSIM_LENS_MULTIPOLE:
+    case LSIM_LENS_CSE:
+    case LSIM_LENS_NFW_ELLIPSE_CSE:
+    case LSIM_LENS_HERNQUIST_ELLIPSE_CSE: return 6;
     default: return 0;
   }
 }

@@ -265,7 +265,13 @@ def test_models_outside_the_gradient_scope_are_refused():
     row = _base_row(c, lin.param_names)
     with pytest.raises(_lib.LsimError):
         lin.logL_linear_grad_batch(torch.as_tensor(row[None, :], device="cuda"))
-    # a lens profile without derivative code (NFW) in an otherwise supported configuration
+
+
+def test_dual_number_profiles_on_the_device():
+    """NFW + TNFW + NFW_ELLIPSE_CSE + SHEAR (four lens profiles: the generic instantiation that evaluates every profile
+    twice, all on dual numbers) against central differences of the forward path on the device."""
+    import torch
+
     from bench import build_headline
     from jaxtronomy_b200.Data.imaging_data import ImageData
     from jaxtronomy_b200.Data.psf import PSF
@@ -273,15 +279,38 @@ def test_models_outside_the_gradient_scope_are_refused():
     from jaxtronomy_b200.LensModel.lens_model import LensModel
     from jaxtronomy_b200.LightModel.light_model import LightModel
 
-    cfg = build_headline(num_pix=24, ss=1, kernel_size=5, n_sets=1, seed=1)
+    cfg = build_headline(num_pix=32, ss=2, kernel_size=7, n_sets=1, seed=1)
     st = cfg["static"]
-    nfw = ImageLinearFit(ImageData(image_data=cfg["data_image"], **st["kwargs_data"]),
-                         PSF(psf_type="PIXEL", kernel_point_source=st["kernel"]), LensModel(["NFW"]),
-                         LightModel(["SERSIC"]), LightModel([]), kwargs_numerics=dict(supersampling_factor=1))
-    row = torch.tensor([[1.0, 0.5, 0.0, 0.0, 1.0, 0.3, 2.0, 0.0, 0.0]], device="cuda", dtype=torch.float64)
-    assert torch.isfinite(nfw.logL_linear_batch(row)[0]).all()
-    with pytest.raises(_lib.LsimError):
-        nfw.logL_linear_grad_batch(row)
+    lin = ImageLinearFit(ImageData(image_data=cfg["data_image"], **st["kwargs_data"]),
+                         PSF(psf_type="PIXEL", kernel_point_source=st["kernel"]),
+                         LensModel(["NFW", "TNFW", "NFW_ELLIPSE_CSE", "SHEAR"]),
+                         LightModel(["SERSIC_ELLIPSE"]), LightModel(["GAUSSIAN"]),
+                         kwargs_numerics=dict(supersampling_factor=2))
+    names = lin.param_names
+    vals = {"lens": [dict(Rs=0.6, alpha_Rs=0.5, center_x=0.02, center_y=-0.01),
+                     dict(Rs=0.3, alpha_Rs=0.2, r_trunc=0.9, center_x=0.3, center_y=0.2),
+                     dict(Rs=0.8, alpha_Rs=0.4, e1=0.1, e2=-0.05, center_x=-0.02, center_y=0.03),
+                     dict(gamma1=0.03, gamma2=-0.02, ra_0=0.0, dec_0=0.0)],
+            "source": [dict(amp=1.0, R_sersic=0.25, n_sersic=1.5, e1=0.1, e2=0.05, center_x=0.03, center_y=0.06)],
+            "lens_light": [dict(amp=1.0, sigma=0.3, center_x=0.0, center_y=0.0)]}
+    row = np.array([vals[comp][i][n] for comp, i, n in names])
+    t = torch.as_tensor(np.tile(row, (3, 1)), device="cuda")
+    t[1:] += 0.01 * torch.as_tensor(np.random.default_rng(2).normal(size=(2, len(row))), device="cuda")
+    logl, grad, _ = lin.logL_linear_grad_batch(t)
+    assert torch.isfinite(logl).all() and torch.isfinite(grad).all()
+    grad = grad.cpu().numpy()
+    scale = np.abs(grad).max(axis=1)
+    v = lambda m: lin.logL_linear_batch(m)[0].cpu().numpy()  # noqa: E731
+    for j, (comp, i, n) in enumerate(names):
+        if n == "amp":
+            continue
+        err = np.full(3, np.inf)
+        for h in STEPS:
+            d = torch.zeros_like(t)
+            d[:, j] = h
+            fdv = (8 * (v(t + d) - v(t - d)) - (v(t + 2 * d) - v(t - 2 * d))) / (12 * h)
+            err = np.minimum(err, np.abs(grad[:, j] - fdv) / scale)
+        assert np.all(err <= 1e-6), (comp, i, n, err)
 
 
 def test_gradient_descent_sampler_recovers_the_truth():

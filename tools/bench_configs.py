@@ -92,6 +92,31 @@ def c3():
                 images_per_s=B / ms * 1e3, fp64_TFLOPs_algorithmic=B * flop / ms / 1e9)
 
 
+def c3grad():
+    """C3's model through the gradient path: logL and d logL / d 27 sampled parameters, 1184 sets."""
+    st = static_config()
+    rng = np.random.default_rng(2)
+    data = ImageData(image_data=rng.normal(0, 0.05, (180, 180)) + 0.1, **st["kwargs_data"])
+    psf = PSF(psf_type="PIXEL", kernel_point_source=psf_kernel(21))
+    km = dict(lens_model_list=["EPL_MULTIPOLE_M1M3M4", "SHEAR"], source_light_model_list=["SERSIC_ELLIPSE"],
+              lens_light_model_list=["SERSIC_ELLIPSE"])
+    lin = ImageLinearFit(data, psf, LensModel(km["lens_model_list"]), LightModel(km["source_light_model_list"]),
+                         LightModel(km["lens_light_model_list"]), kwargs_numerics=dict(supersampling_factor=3))
+    param = Param(km, kwargs_fixed_lens=[{}, {"ra_0": 0.0, "dec_0": 0.0}])
+    like = LikelihoodModule(lin, param)
+    B = 1184
+    kl = [dict(theta_E=1.2, gamma=2.0, e1=0.2, e2=-0.1, center_x=0.0, center_y=0.0, a1_a=0.01, delta_phi_m1=0.1,
+               a3_a=0.01, delta_phi_m3=0.1, a4_a=0.01, delta_phi_m4=0.1), dict(gamma1=0.03, gamma2=0.01, ra_0=0, dec_0=0)]
+    ks = [dict(amp=1, R_sersic=0.3, n_sersic=2.0, e1=0.1, e2=0.1, center_x=0.05, center_y=0.0)]
+    kll = [dict(amp=1, R_sersic=0.6, n_sersic=3.0, e1=0.05, e2=0.0, center_x=0.0, center_y=0.0)]
+    x0 = param.kwargs2args(kl, ks, kll)
+    pos = torch.as_tensor(x0[None, :] + rng.normal(0, 0.02, (B, x0.size)), device="cuda")
+    ms = timed(lambda: like.logL_and_grad_batch_device(pos))
+    ms_f = timed(lambda: like.logL_batch_device(pos))
+    return dict(config="C3 model, logL + gradient (%d sampled parameters), %d sets" % (x0.size, B), ms=ms,
+                gradients_per_s=B / ms * 1e3, forward_only_ms=ms_f, grad_over_forward=ms / ms_f)
+
+
 def c4():
     """1 EPL + 1000 TNFW on a 1000x1000 ray grid (substructure notebook shape)."""
     rng = np.random.default_rng(3)
