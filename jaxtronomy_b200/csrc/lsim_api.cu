@@ -179,13 +179,12 @@ constexpr size_t kGradSmemMax = 200 * 1024;
 int configure_kernels() {
   LSIM_CUDA(cudaFuncSetAttribute(k_conv_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
   LSIM_CUDA(cudaFuncSetAttribute(k_conv_separable, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
-#define LSIM_GRAD_ATTR(NL)                                                                                        \
-  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax)); \
-  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
+#define LSIM_GRAD_ATTR(NS)                                                                                        \
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax)); \
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
   LSIM_GRAD_ATTR(0)
   LSIM_GRAD_ATTR(1)
   LSIM_GRAD_ATTR(2)
-  LSIM_GRAD_ATTR(3)
 #undef LSIM_GRAD_ATTR
   return LSIM_OK;
 }
@@ -1069,15 +1068,14 @@ int launch_image_grad(const lsim_plan* plan, const double* params, int64_t set0,
     double* pt = partial + (size_t)i0 * tiles * grad_entries(D.n_lens, D.n_light);
     {
       Timed timed(kClsImage, st);
-#define LSIM_GRAD_LAUNCH(NL)                                                                                      \
+#define LSIM_GRAD_LAUNCH(NS)                                                                                      \
   if (plan->grad_fast)                                                                                            \
-    k_image_grad<NL, true><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); \
+    k_image_grad<NS, true><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); \
   else                                                                                                            \
-    k_image_grad<NL, false><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt);
-      switch (D.n_lens <= 3 ? D.n_lens : 0) {
+    k_image_grad<NS, false><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt);
+      switch (plan->grad_series < 2 ? plan->grad_series : 2) {  // EPL-family profiles kept in registers
         case 1: LSIM_GRAD_LAUNCH(1) break;
         case 2: LSIM_GRAD_LAUNCH(2) break;
-        case 3: LSIM_GRAD_LAUNCH(3) break;
         default: LSIM_GRAD_LAUNCH(0) break;
       }
 #undef LSIM_GRAD_LAUNCH

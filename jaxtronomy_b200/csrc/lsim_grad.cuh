@@ -425,6 +425,8 @@ LSIM_HD void nie_eval_d(const GLens& L, double x, double y, LD& fx, LD& fy) {
   fy = ar * sph + ai * cph;
 }
 
+struct GLens;
+LSIM_HD void mp_constants(GLens& L);
 // One multipole of EPL_MULTIPOLE_M1M3M4 (epl_multipole_m1m3m4.py:463-535: a_m = a_m/a * theta_E / sqrt(q),
 // phi_m = phi + delta_phi_m, r_E = theta_E for m = 1) at UNIT a_m/a: the deflection is linear in that amplitude, so its
 // derivative is the unit deflection itself and the six tangents go to theta_E, e1, e2, center_x, center_y, delta_phi_m.
@@ -441,6 +443,7 @@ LSIM_HD void mp_prepare_d(GLens& L, int m, const LD& theta_E, const LD& e1, cons
   L.c[3] = phi + delta;
   L.c[4] = theta_E;
   L.k[0] = a;
+  mp_constants(L);
 }
 
 // Multipole.derivatives (multipole.py:72-119) with a_m = c[2]
@@ -660,7 +663,7 @@ LSIM_HD bool lens_prepare_d(const lsim_lens_desc& d, const double* row, GLens& L
       L.c[3] = lens_var(d, row, 2);
       L.c[4] = lens_var(d, row, 5);
       L.k[0] = 1.0;
-      L.k[1] = 1.0;  // a plain MULTIPOLE: its tangents are the parameters' own (no amplitude entry)
+      mp_constants(L);
       return true;
     case LSIM_LENS_CSE:
     case LSIM_LENS_NFW_ELLIPSE_CSE:
@@ -692,7 +695,6 @@ LSIM_HD bool lens_prepare_d(const lsim_lens_desc& d, const double* row, GLens& L
       return true;
     }
     case kGradLensMP:
-      L.k[1] = 0.0;
       mp_prepare_d(L, (int)d.opt[0], lens_var(d, row, 0), lens_var(d, row, 1), lens_var(d, row, 2), lens_var(d, row, 3),
                    lens_var(d, row, 4), lens_var(d, row, 5), param_of(d, row, 6));
       return true;
@@ -772,6 +774,18 @@ inline int expand_grad_lens(const lsim_lens_desc* in, int n, lsim_lens_desc* out
       q.col[6] = in[i].col[ia[j]];
       q.cst[6] = in[i].cst[ia[j]];
       out[m++] = q;
+    }
+  }
+  // the profiles whose point state the kernel keeps in registers (the EPL family) go first; the order of the sum of
+  // deflections is internal to the gradient path
+  for (int i = 1; i < m; ++i) {
+    if (!lens_grad_has_series(out[i])) continue;
+    int j = i;
+    while (j > 0 && !lens_grad_has_series(out[j - 1])) {
+      const lsim_lens_desc t = out[j - 1];
+      out[j - 1] = out[j];
+      out[j] = t;
+      --j;
     }
   }
   return m;
@@ -896,7 +910,6 @@ LSIM_HD GD light_eval_d(const lsim_light_desc& d, const double* row, const GD& x
 struct LensPt {
   double ax, ay;
   double s[12];
-  double hx, hy;  // kGradLensMP: the unit-amplitude deflection (= d alpha / d amplitude)
 };
 
 // S = sum_n c_n w^n for real c_n by the quadratic-factor (Clenshaw) recurrence  b_k = c_k + 2 Re(w) b_{k+1} -
@@ -1033,6 +1046,103 @@ LSIM_HD void epl_vjp(const GLens& L, const LensPt& o, double x, double y, double
 }
 
 // value + whatever lens_vjp needs, for any profile in the gradient's scope
+// ---- multipole (kGradLensMP) in closed form ------------------------------------------------------------------------
+// Plain constants next to the duals c[0..4] = cx, cy, rho (= a_m at unit amplitude), phi_m, r_E:
+//   k[0] = amplitude, k[2] = rho, k[3] = 1/(1-m^2) (m != 1), k[4], k[5] = cos, sin(m phi_m), k[6] = ln r_E
+LSIM_HD void mp_constants(GLens& L) {
+  const int m = L.n_val;
+  L.k[2] = L.c[2].v;
+  L.k[3] = m == 1 ? 0.0 : 1.0 / (1.0 - (double)(m * m));
+  L.k[4] = cos(m * L.c[3].v);
+  L.k[5] = sin(m * L.c[3].v);
+  L.k[6] = log(L.c[4].v);
+}
+
+// unit vector of the point, (cos, sin)(m Delta) with Delta = phi - phi_m by complex powers (no trigonometric call), r^2
+LSIM_HD void mp_terms(const GLens& L, double x, double y, double& c1, double& s1, double& cm, double& sm, double& r2) {
+  const int m = L.n_val;
+  const double xs = x - L.c[0].v, ys = y - L.c[1].v;
+  r2 = fma(ys, ys, xs * xs);
+  c1 = 1.0;
+  s1 = 0.0;  // atan2(0, 0) = 0
+  if (r2 > 0) {
+    const double ir = rsqrt_fast(fmax(r2, 1e-300));
+    c1 = xs * ir;
+    s1 = ys * ir;
+  }
+  double ur = c1, ui = s1;
+  for (int k = 1; k < m; ++k) {
+    const double t = fma(ur, c1, -(ui * s1));
+    ui = fma(ur, s1, ui * c1);
+    ur = t;
+  }
+  cm = fma(ui, L.k[5], ur * L.k[4]);  // cos(m phi - m phi_m)
+  sm = fma(ui, L.k[4], -(ur * L.k[5]));
+}
+
+// deflection at unit amplitude (multipole.py:72-119)
+LSIM_HD void mp_value(const GLens& L, double x, double y, double& hx, double& hy) {
+  double c1, s1, cm, sm, r2;
+  mp_terms(L, x, y, c1, s1, cm, sm, r2);
+  const int m = L.n_val;
+  if (m == 1) {
+    const double lg = 0.5 * kLn2 * log2_pos(fmax(r2, 1e-12)) - L.k[6];
+    const double h = 0.5 * L.k[2];
+    hx = h * fma(L.k[4], lg, cm * c1);
+    hy = h * fma(L.k[5], lg, cm * s1);
+  } else {
+    const double A = L.k[2] * L.k[3];
+    hx = A * fma(m * s1, sm, c1 * cm);
+    hy = A * fma(-m * c1, sm, s1 * cm);
+  }
+}
+
+// s_j = d(a v . alpha_hat)/d(primitive j), primitives (rho, phi_m, cx, cy, r_E) in g[0..4]; g[6] = v . alpha_hat
+LSIM_HD void mp_vjp(const GLens& L, double x, double y, double vx, double vy, double (&g)[kLensEntries]) {
+  double c1, s1, cm, sm, r2;
+  mp_terms(L, x, y, c1, s1, cm, sm, r2);
+  const int m = L.n_val;
+  const double a = L.k[0], rho = L.k[2], ar = a * rho;
+  // everything below at unit rho: alpha_hat = rho * h
+  double dpx, dpy;              // d h / d phi (polar angle of the point)
+  double dlx = 0.0, dly = 0.0;  // d h / d ln r   (m = 1 only)
+  double hx, hy, dmx, dmy;      // h, d h / d phi_m
+  if (m == 1) {
+    const bool live = !(r2 < 1e-12);
+    const double lg = 0.5 * kLn2 * log2_pos(fmax(r2, 1e-12)) - L.k[6];
+    hx = 0.5 * fma(L.k[4], lg, cm * c1);
+    hy = 0.5 * fma(L.k[5], lg, cm * s1);
+    dmx = 0.5 * fma(-L.k[5], lg, sm * c1);
+    dmy = 0.5 * fma(L.k[4], lg, sm * s1);
+    dpx = -0.5 * fma(sm, c1, cm * s1);
+    dpy = 0.5 * fma(cm, c1, -(sm * s1));
+    dlx = live ? 0.5 * L.k[4] : 0.0;
+    dly = live ? 0.5 * L.k[5] : 0.0;
+    g[4] = -ar * 0.5 * fma(vx, L.k[4], vy * L.k[5]) / L.c[4].v;  // ln(r / r_E): d/d r_E = -1 / r_E
+  } else {
+    const double A = L.k[3];
+    hx = A * fma(m * s1, sm, c1 * cm);
+    hy = A * fma(-m * c1, sm, s1 * cm);
+    dmx = A * m * fma(c1, sm, -(m * s1 * cm));
+    dmy = A * m * fma(s1, sm, m * c1 * cm);
+    dpx = -cm * s1;  // A (m^2 - 1) cos(m Delta) (sin, -cos)(phi)
+    dpy = cm * c1;
+    g[4] = 0.0;
+  }
+  const double sh = fma(vx, hx, vy * hy);
+  g[6] = rho * sh;
+  g[0] = a * sh;
+  g[1] = ar * fma(vx, dmx, vy * dmy);
+  // position: d phi / d xs = -sin / r, d phi / d ys = cos / r, d ln r / d xs = cos / r, d ln r / d ys = sin / r;
+  // the centre moves the point the other way
+  const double ir = r2 > 0 ? rsqrt_fast(fmax(r2, 1e-300)) : 0.0;
+  const double sp = ar * fma(vx, dpx, vy * dpy) * ir, sl = ar * fma(vx, dlx, vy * dly) * ir;
+  g[2] = -fma(-s1, sp, c1 * sl);
+  g[3] = -fma(c1, sp, s1 * sl);
+  g[5] = 0.0;
+  g[7] = 0.0;
+}
+
 // FAST: the model holds closed-form profiles only (EPL, SHEAR, NULL) -- the dual-number code is not compiled in, which
 // is what lets that instantiation of k_image_grad run with half the registers.
 template <bool FAST = false>
@@ -1043,21 +1153,14 @@ LSIM_HD void lens_point(const GLens& L, const double* pool, double x, double y, 
     const double xs = x - L.c[2].v, ys = y - L.c[3].v;
     o.ax = fma(L.c[1].v, ys, L.c[0].v * xs);
     o.ay = fma(L.c[1].v, xs, -(L.c[0].v * ys));
+  } else if (L.type == kGradLensMP) {
+    double hx, hy;
+    mp_value(L, x, y, hx, hy);
+    o.ax = L.k[0] * hx;
+    o.ay = L.k[0] * hy;
   } else if (FAST) {
     o.ax = 0.0;
     o.ay = 0.0;
-  } else if (L.type == kGradLensMP) {
-    LD fx, fy;
-    mp_eval_d(L, x, y, fx, fy);
-    o.hx = fx.v;
-    o.hy = fy.v;
-    o.ax = L.k[0] * fx.v;
-    o.ay = L.k[0] * fy.v;
-    LSIM_UNROLL
-    for (int k = 0; k < kLensN; ++k) {
-      o.s[k] = fx.d[k];
-      o.s[kLensN + k] = fy.d[k];
-    }
   } else {
     LD fx, fy;
     lens_eval_d(L, pool, x, y, fx, fy);
@@ -1090,20 +1193,46 @@ LSIM_HD void lens_vjp(const GLens& L, const LensPt& o, double x, double y, doubl
     g[3] = fma(vy, L.c[0].v, -(vx * L.c[1].v));
     g[4] = 0.0;
     g[5] = 0.0;
+  } else if (L.type == kGradLensMP) {
+    mp_vjp(L, x, y, vx, vy, g);
   } else if (FAST) {
     LSIM_UNROLL
     for (int k = 0; k < kLensN; ++k) g[k] = 0.0;
-  } else if (L.type == kGradLensMP) {
-    LSIM_UNROLL
-    for (int k = 0; k < kLensN; ++k) g[k] = L.k[0] * fma(vx, o.s[k], vy * o.s[kLensN + k]);
-    g[6] = fma(vx, o.hx, vy * o.hy);
   } else {
     LSIM_UNROLL
     for (int k = 0; k < kLensN; ++k) g[k] = fma(vx, o.s[k], vy * o.s[kLensN + k]);
   }
 }
+// Profiles the kernel does not keep a point state for: the deflection alone in the first pass ...
+template <bool FAST = false>
+LSIM_HD void lens_value(const GLens& L, const double* pool, double x, double y, double& ax, double& ay) {
+  if (L.type == LSIM_LENS_SHEAR) {
+    const double xs = x - L.c[2].v, ys = y - L.c[3].v;
+    ax = fma(L.c[1].v, ys, L.c[0].v * xs);
+    ay = fma(L.c[1].v, xs, -(L.c[0].v * ys));
+  } else if (L.type == kGradLensMP) {
+    double hx, hy;
+    mp_value(L, x, y, hx, hy);
+    ax = L.k[0] * hx;
+    ay = L.k[0] * hy;
+  } else {
+    LensPt o;
+    lens_point<FAST>(L, pool, x, y, o);  // the Jacobian part is dead code here
+    ax = o.ax;
+    ay = o.ay;
+  }
+}
+// ... and the contraction in the second, recomputing what it needs (nothing for the shear and the multipoles)
+template <bool FAST = false>
+LSIM_HD void lens_vjp_recompute(const GLens& L, const double* pool, double x, double y, double vx, double vy,
+                                double (&g)[kLensEntries]) {
+  LensPt o;
+  if (L.type != LSIM_LENS_SHEAR && L.type != kGradLensMP) lens_point<FAST>(L, pool, x, y, o);
+  lens_vjp<FAST>(L, o, x, y, vx, vy, g);
+}
 LSIM_HD bool lens_grad_closed_form(const lsim_lens_desc& d) {
-  return d.type == LSIM_LENS_NULL || d.type == LSIM_LENS_SHEAR || lens_grad_has_series(d);
+  return d.type == LSIM_LENS_NULL || d.type == LSIM_LENS_SHEAR || d.type == kGradLensMP ||
+         d.type == LSIM_LENS_MULTIPOLE || lens_grad_has_series(d);
 }
 
 LSIM_HD void lens_chain(const GLens& L, const double (&s)[kLensEntries], double (&g)[kLensEntries]) {
@@ -1116,6 +1245,9 @@ LSIM_HD void lens_chain(const GLens& L, const double (&s)[kLensEntries], double 
       double a = 0.0;
       for (int j = 0; j < 4; ++j) a = fma(s[j], L.c[j].d[k], a);
       g[k] = a;
+    } else if (k < kLensN && L.type == kGradLensMP) {  // primitives (rho, phi_m, cx, cy, r_E) = c[2], c[3], c[0], c[1], c[4]
+      g[k] = fma(s[0], L.c[2].d[k], fma(s[1], L.c[3].d[k], fma(s[2], L.c[0].d[k], fma(s[3], L.c[1].d[k],
+                                                                                       s[4] * L.c[4].d[k]))));
     } else {
       g[k] = s[k];
     }

@@ -255,16 +255,19 @@ k_conv_adj_edge(const double* __restrict__ in, double* __restrict__ out, int nx,
 // once (value + gradient, light_point), then the lens parameters' contraction with the back-propagated source-plane
 // gradient (lens_vjp).  EPL, SHEAR and the light profiles use closed-form derivatives, the other lens profiles dual
 // numbers (lsim_grad.cuh).
-// NL > 0: the model has exactly NL lens profiles; their point states stay in registers between the ray shooting and
-// the lens-parameter update.  NL == 0: any number of profiles, each evaluated twice.
-// FAST: every lens profile has closed-form derivatives (EPL, SHEAR): no dual-number code in that instantiation.
+// NS: the first NS profiles of the gradient's lens list are EPL-family profiles (expand_grad_lens puts them first)
+// whose point state -- the 2 x 5 Jacobian of the major-axis deflection -- stays in registers between the ray shooting
+// and the lens-parameter update; every other profile is evaluated for its deflection first and contracted later
+// (shear and multipoles need nothing from the first pass; dual-number profiles are evaluated twice).
+// FAST: every lens profile has closed-form derivatives (EPL, SHEAR, multipoles): no dual-number code in that
+// instantiation.
 __host__ __device__ inline size_t grad_smem_bytes(int n_lens, int n_light, int n_series) {
   return (size_t)n_lens * sizeof(ad::GLens) + (size_t)n_light * sizeof(ad::GLight) +
          (size_t)n_series * ad::kGradPool * sizeof(double) +
          (size_t)grad_entries(n_lens, n_light) * kGradBlock * sizeof(double);
 }
 
-template <int NL, bool FAST>
+template <int NS, bool FAST>
 __global__ void __launch_bounds__(kGradBlock, FAST ? LSIM_GRAD_FAST_BLOCKS : 2)
 k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, int n_series,
              const double* __restrict__ ubar, double wscale, double* __restrict__ partial) {
@@ -308,20 +311,18 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
       for (int j = 0; j < ss; ++j) {
         const double x = __ldg(P.x_sub + base + j), y = __ldg(P.y_sub + base + j);
         double ax = 0.0, ay = 0.0;
-        LensPt pt[NL > 0 ? NL : 1];
-        if (NL > 0) {
+        LensPt pt[NS > 0 ? NS : 1];
 #pragma unroll
-          for (int l = 0; l < NL; ++l) {
-            lens_point<FAST>(L[l], pool, x, y, pt[l]);
-            ax += pt[l].ax;
-            ay += pt[l].ay;
-          }
-        } else {
-          for (int l = 0; l < P.n_lens; ++l) {
-            lens_point<FAST>(L[l], pool, x, y, pt[0]);
-            ax += pt[0].ax;
-            ay += pt[0].ay;
-          }
+        for (int l = 0; l < NS; ++l) {
+          lens_point<FAST>(L[l], pool, x, y, pt[l]);
+          ax += pt[l].ax;
+          ay += pt[l].ay;
+        }
+        for (int l = NS; l < P.n_lens; ++l) {
+          double fx, fy;
+          lens_value<FAST>(L[l], pool, x, y, fx, fy);
+          ax += fx;
+          ay += fy;
         }
         const double bx = x - ax * as, by = y - ay * as;
         double vx = 0.0, vy = 0.0;
@@ -341,24 +342,21 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
         }
         vx *= -as;  // d beta / d p = -alpha_scaling d alpha / d p
         vy *= -as;
-        if (NL > 0) {
 #pragma unroll
-          for (int l = 0; l < NL; ++l) {
-            double gl[kLensEntries];
-            lens_vjp<FAST>(L[l], pt[l], x, y, vx, vy, gl);
-            double* e = my + (size_t)l * kLensEntries * kGradBlock;
+        for (int l = 0; l < NS; ++l) {
+          double gl[kLensEntries];
+          lens_vjp<FAST>(L[l], pt[l], x, y, vx, vy, gl);
+          double* e = my + (size_t)l * kLensEntries * kGradBlock;
 #pragma unroll
-            for (int k = 0; k < (FAST ? kLensN : kLensEntries); ++k) e[k * kGradBlock] += gl[k];
-          }
-        } else if (vx != 0.0 || vy != 0.0) {
-          for (int l = 0; l < P.n_lens; ++l) {
-            lens_point<FAST>(L[l], pool, x, y, pt[0]);
-            double gl[kLensEntries];
-            lens_vjp<FAST>(L[l], pt[0], x, y, vx, vy, gl);
-            double* e = my + (size_t)l * kLensEntries * kGradBlock;
-#pragma unroll
-            for (int k = 0; k < (FAST ? kLensN : kLensEntries); ++k) e[k * kGradBlock] += gl[k];
-          }
+          for (int k = 0; k < kLensN; ++k) e[k * kGradBlock] += gl[k];
+        }
+        for (int l = NS; l < P.n_lens; ++l) {
+          double gl[kLensEntries];
+          lens_vjp_recompute<FAST>(L[l], pool, x, y, vx, vy, gl);
+          double* e = my + (size_t)l * kLensEntries * kGradBlock;
+          const int ne = L[l].type == LSIM_LENS_SHEAR ? 4 : kLensN;
+          for (int k = 0; k < ne; ++k) e[k * kGradBlock] += gl[k];
+          if (L[l].type == kGradLensMP) e[6 * kGradBlock] += gl[6];  // the amplitude's entry
         }
       }
     }

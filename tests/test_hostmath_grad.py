@@ -48,6 +48,7 @@ LENS_CASES = [
     ("TNFW", dict(Rs=0.8, alpha_Rs=0.6, r_trunc=2.5, center_x=-0.04, center_y=0.03), None),
     ("MULTIPOLE", dict(m=3, a_m=0.05, phi_m=0.3, center_x=0.02, center_y=0.01, r_E=1.0), None),
     ("MULTIPOLE", dict(m=1, a_m=0.04, phi_m=-0.2, center_x=0.0, center_y=0.05, r_E=1.3), None),
+    ("MULTIPOLE", dict(m=4, a_m=0.0, phi_m=0.1, center_x=0.0, center_y=0.0, r_E=1.0), None),  # zero amplitude
     ("CSE", dict(a=1.3, s=0.4, e1=0.15, e2=-0.1, center_x=0.01, center_y=0.02), None),
     ("CSE", dict(a=0.9, s=0.6, e1=-0.2, e2=0.05, center_x=0.0, center_y=0.0), {"axis": "major"}),
     ("NFW_ELLIPSE_CSE", dict(Rs=1.1, alpha_Rs=0.8, e1=0.2, e2=0.1, center_x=0.03, center_y=-0.01), None),
