@@ -6,7 +6,8 @@ import numpy as np
 
 from jaxtronomy_b200 import parallel
 
-__all__ = ["prepare_logL_func", "ParticleSwarmOptimizer", "DeviceParticleSwarmOptimizer"]
+__all__ = ["prepare_logL_func", "ParticleSwarmOptimizer", "DeviceParticleSwarmOptimizer", "DeviceEnsembleSampler",
+           "mcmc_emcee", "sample_ball_truncated"]
 
 
 def prepare_logL_func(backend, likelihood_module, threadCount=1, world_size=1, rank=0):
@@ -138,3 +139,117 @@ class DeviceParticleSwarmOptimizer(object):
                           self.global_fitness, fitness, rnd, c1, c2)
             history[it] = self.global_fitness[0]
         return self.global_best.cpu().numpy(), history.cpu().numpy().tolist()
+
+
+class DeviceEnsembleSampler(object):
+    """Affine-invariant ensemble sampler with the stretch move (Goodman & Weare 2010; a = 2, the walkers split at
+    random into two halves that are updated in turn against each other): what
+    ``emcee.EnsembleSampler(n_walkers, n_param, logL_func, vectorize=True).run_mcmc`` does behind
+    ``Sampler.mcmc_emcee`` (jaxtronomy/Sampling/sampler.py:112-212), which hands emcee the batched ``logL_func``.
+
+    Here the walkers, the proposals and the accept / reject step stay on the device: a step is two batched likelihood
+    evaluations of n_walkers / 2 proposals each (``LikelihoodModule.logL_batch_device`` on the proposal matrix itself)
+    and a handful of element-wise tensor operations; the chain is read back once at the end.  Per half-ensemble S with
+    complement C:  z = ((a-1) u + 1)^2 / a,  y_k = c_j + z (x_k - c_j) with j uniform in C,  accept if
+    ln u' < (n-1) ln z + logp(y_k) - logp(x_k).
+
+    emcee is not installable here (parity unpinned): same move, same acceptance rule, torch's generator instead of
+    NumPy's.  ``logp_fn`` may be any callable on a [B, n] tensor (the CPU tests sample a Gaussian with it).
+    """
+
+    def __init__(self, logp_fn, n_walkers, n_param, seed=0, a=2.0, device=None):
+        import torch
+
+        if n_walkers < 2 or n_walkers % 2:
+            raise ValueError("the stretch move needs an even number of walkers (>= 2)")
+        self._logp = getattr(logp_fn, "logL_batch_device", logp_fn)
+        self.n_walkers, self.n_param, self.a = int(n_walkers), int(n_param), float(a)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(int(seed))
+        self.chain = None
+        self.log_prob = None
+        self.n_accepted = None
+
+    def run_mcmc(self, initpos, n_steps):
+        """Advance the ensemble by n_steps from ``initpos`` [n_walkers, n_param]; stores chain [n_steps, n_walkers, n_param]
+        and log_prob [n_steps, n_walkers] (device tensors)."""
+        import torch
+
+        dev, W, n = self.device, self.n_walkers, self.n_param
+        x = torch.as_tensor(np.asarray(initpos, dtype=np.float64) if not isinstance(initpos, torch.Tensor) else initpos,
+                            dtype=torch.float64, device=dev).clone().contiguous()
+        if x.shape != (W, n):
+            raise ValueError("initpos must be [%d, %d]" % (W, n))
+        lp = self._logp(x).clone()
+        if torch.isnan(lp).any():
+            raise ValueError("The initial log-probability contains NaN")
+        chain = torch.empty((n_steps, W, n), dtype=torch.float64, device=dev)
+        logp = torch.empty((n_steps, W), dtype=torch.float64, device=dev)
+        accepted = torch.zeros(W, dtype=torch.int64, device=dev)
+        half = W // 2
+        for it in range(n_steps):
+            perm = torch.randperm(W, device=dev, generator=self._gen)
+            for first in (True, False):
+                s_idx = perm[:half] if first else perm[half:]
+                c_idx = perm[half:] if first else perm[:half]
+                s, c = x[s_idx], x[c_idx]
+                u = torch.rand(half, dtype=torch.float64, device=dev, generator=self._gen)
+                zz = ((self.a - 1.0) * u + 1.0) ** 2 / self.a
+                rint = torch.randint(half, (half,), device=dev, generator=self._gen)
+                cj = c[rint]
+                q = cj - (cj - s) * zz[:, None]
+                new_lp = self._logp(q.contiguous())
+                lnpdiff = (n - 1.0) * torch.log(zz) + new_lp - lp[s_idx]
+                acc = torch.log(torch.rand(half, dtype=torch.float64, device=dev, generator=self._gen)) < lnpdiff
+                x[s_idx] = torch.where(acc[:, None], q, s)
+                lp[s_idx] = torch.where(acc, new_lp, lp[s_idx])
+                accepted[s_idx] += acc.to(torch.int64)
+            chain[it] = x
+            logp[it] = lp
+        self.chain, self.log_prob, self.n_accepted = chain, logp, accepted
+        return x, lp
+
+    @property
+    def acceptance_fraction(self):
+        return (self.n_accepted.double() / self.chain.shape[0]).cpu().numpy()
+
+    def get_chain(self, discard=0, thin=1, flat=False):
+        c = self.chain[discard::thin]
+        return (c.reshape(-1, self.n_param) if flat else c).cpu().numpy()
+
+    def get_log_prob(self, discard=0, thin=1, flat=False):
+        lp = self.log_prob[discard::thin]
+        return (lp.reshape(-1) if flat else lp).cpu().numpy()
+
+
+def sample_ball_truncated(mean, sigma, lower_limit, upper_limit, size, seed=None):
+    """Start positions of the walkers: independent normals around ``mean`` truncated to the prior box (lenstronomy's
+    sampling_util.sample_ball_truncated, used at sampler.py:185-191; restated -- parity unpinned)."""
+    from scipy.stats import truncnorm
+
+    mean, sigma = np.asarray(mean, dtype=float), np.asarray(sigma, dtype=float)
+    a, b = (np.asarray(lower_limit) - mean) / sigma, (np.asarray(upper_limit) - mean) / sigma
+    return truncnorm.rvs(a, b, loc=mean, scale=sigma, size=(size, mean.size), random_state=seed)
+
+
+def mcmc_emcee(likelihood_module, n_walkers, n_run, n_burn, mean_start, sigma_start, initpos=None, seed=0,
+               mpi=False, progress=False, threadCount=1, backend_filename=None, start_from_backend=False):
+    """Sampler.mcmc_emcee (jaxtronomy/Sampling/sampler.py:112-212) on the device-resident ensemble sampler:
+    -> (flat samples [n_run * n_walkers, n_param], their log-probabilities), burn-in discarded."""
+    if mpi:
+        raise ValueError("mpi must be False in JAXtronomy, since parallelization is done through JAX")
+    if start_from_backend:
+        raise ValueError("start_from_backend must be False in JAXtronomy")
+    if backend_filename is not None:
+        raise ValueError("backend_filename not supported in JAXtronomy")
+    if n_walkers % 2:
+        n_walkers += 1
+    lower, upper = likelihood_module.param.param_limits()
+    num_param = likelihood_module.param.num_param()[0]
+    if initpos is None:
+        initpos = sample_ball_truncated(mean_start, sigma_start, lower, upper, size=n_walkers, seed=seed)
+    sampler = DeviceEnsembleSampler(likelihood_module, n_walkers, num_param, seed=seed)
+    sampler.run_mcmc(initpos, n_burn + n_run)
+    mcmc_emcee.last_sampler = sampler
+    return sampler.get_chain(discard=n_burn, flat=True), sampler.get_log_prob(discard=n_burn, flat=True)

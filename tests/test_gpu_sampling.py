@@ -178,3 +178,28 @@ def test_likelihood_module_with_point_sources():
         want, _ = lin.likelihood_data_given_model(kw["kwargs_lens"], kw["kwargs_source"], kw["kwargs_lens_light"],
                                                   kw["kwargs_ps"])
         assert abs(logl[b] - want) <= 1e-11 * abs(want), (b, logl[b], want)
+
+
+def test_device_ensemble_sampler_on_the_image_likelihood():
+    """Sampler.mcmc_emcee's boundary (sampler.py:112-212): walkers on the device, two batched likelihood calls per
+    step; the chain must stay inside the prior box, keep its stored log-probabilities consistent with the likelihood
+    and move (acceptance fraction) while improving on a deliberately offset start."""
+    import torch
+
+    from jaxtronomy_b200.Sampling.sampler import mcmc_emcee
+
+    c, lin, param, like = _setup()
+    x0 = np.asarray(param.kwargs2args(c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]))
+    lo, hi = param.param_limits()
+    n_walkers, n_run, n_burn = 32, 30, 10
+    samples, dist = mcmc_emcee(like, n_walkers, n_run, n_burn, x0, 1e-3 * np.maximum(np.abs(x0), 0.1), seed=4)
+    assert samples.shape == (n_walkers * n_run, x0.size) and dist.shape == (n_walkers * n_run,)
+    assert np.all(samples >= lo) and np.all(samples <= hi) and np.all(np.isfinite(dist))
+    s = mcmc_emcee.last_sampler
+    acc = s.acceptance_fraction
+    assert 0.05 < acc.mean() < 0.95, acc.mean()
+    # stored log-probabilities == the likelihood of the stored positions
+    last = torch.as_tensor(s.get_chain()[-1], device="cuda")
+    np.testing.assert_allclose(s.get_log_prob()[-1], like.logL_batch_device(last).cpu().numpy(), rtol=1e-12)
+    with pytest.raises(ValueError):
+        mcmc_emcee(like, 8, 2, 0, x0, 1e-3 * np.ones_like(x0), mpi=True)

@@ -388,3 +388,42 @@ def test_likelihood_module_gaussian_priors_value_and_gradient():
         LikelihoodModule(NoImage(), param, prior_lens=[[0, "not_a_parameter", 0.0, 1.0]])
     with pytest.raises(ValueError):
         LikelihoodModule(NoImage(), param, time_delay_likelihood=True)
+
+
+def test_device_ensemble_sampler_samples_a_correlated_gaussian():
+    """The stretch-move sampler (the emcee call behind Sampler.mcmc_emcee) on CPU tensors: a 3-d correlated Gaussian."""
+    import torch
+
+    from jaxtronomy_b200.Sampling.sampler import DeviceEnsembleSampler, sample_ball_truncated
+
+    mu = torch.tensor([0.5, -1.0, 2.0], dtype=torch.float64)
+    cov = torch.tensor([[1.0, 0.6, 0.0], [0.6, 2.0, -0.5], [0.0, -0.5, 0.5]], dtype=torch.float64)
+    icov = torch.linalg.inv(cov)
+    calls = []
+
+    def logp(x):
+        calls.append(x.shape[0])
+        d = x - mu
+        return -0.5 * torch.einsum("bi,ij,bj->b", d, icov, d)
+
+    W = 64
+    init = sample_ball_truncated(mu.numpy(), np.ones(3), -10 * np.ones(3), 10 * np.ones(3), size=W, seed=1)
+    assert init.shape == (W, 3) and np.all(np.abs(init) < 10)
+    s = DeviceEnsembleSampler(logp, W, 3, seed=2, device="cpu")
+    s.run_mcmc(init, 1500)
+    assert calls[0] == W and set(calls[1:]) == {W // 2} and len(calls) == 1 + 2 * 1500  # two half-ensembles per step
+    flat = s.get_chain(discard=300, flat=True)
+    assert flat.shape == (1200 * W, 3) and s.get_log_prob(discard=300, flat=True).shape == (1200 * W,)
+    np.testing.assert_allclose(flat.mean(axis=0), mu.numpy(), atol=0.06)
+    np.testing.assert_allclose(np.cov(flat.T), cov.numpy(), atol=0.12)
+    acc = s.acceptance_fraction
+    assert acc.shape == (W,) and 0.3 < acc.mean() < 0.9
+    # the stored log-probabilities belong to the stored positions
+    last = torch.as_tensor(s.get_chain()[-1])
+    np.testing.assert_allclose(s.get_log_prob()[-1], logp(last).numpy(), rtol=1e-12)
+    # deterministic for a given seed
+    s2 = DeviceEnsembleSampler(logp, W, 3, seed=2, device="cpu")
+    s2.run_mcmc(init, 20)
+    np.testing.assert_array_equal(s2.get_chain(), s.get_chain()[:20])
+    with pytest.raises(ValueError):
+        DeviceEnsembleSampler(logp, 7, 3, device="cpu")

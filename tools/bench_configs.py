@@ -163,7 +163,7 @@ def c5():
                 band_images_per_s=4 * B / ms * 1e3, sets_per_s=B / ms * 1e3)
 
 
-def c1():
+def c1(mcmc=False):
     """The Einstein-ring notebook's PSO (notebooks/modeling_a_simple_Einstein_ring.ipynb: 256 particles x 200
     iterations, 100x100 px, EPL+SHEAR, SERSIC_ELLIPSE source + lens light, 4-image point source, Gaussian PSF, ss 1,
     linear solver; published: lenstronomy 6 min 43 s, JAXtronomy on a CPU node 12 s) with the GPU-resident swarm."""
@@ -195,6 +195,8 @@ def c1():
     like = LikelihoodModule(lin, param)
     x0 = param.kwargs2args(kl, ks, kll, kwargs_ps=kps)
     sig = np.full(x0.size, 0.05)
+    if mcmc:
+        return _c1_mcmc(like, x0)
     n_part, n_iter = 256, 200
 
     def run():
@@ -212,6 +214,35 @@ def c1():
                        "4-image point source, Gaussian PSF, linear solver (n_lin = 6), GPU-resident swarm",
                 wall_s=dt, likelihoods_per_s=n_part * n_iter / dt, logL_first=hist[0], logL_last=hist[-1],
                 logL_truth=like.logL(x0), published="lenstronomy 403 s, JAXtronomy (CPU node) 12 s")
+
+
+def _c1_mcmc(like, x0):
+    """The same notebook's MCMC: 256 walkers x 100 steps (published: lenstronomy 211.1 s, JAXtronomy on a CPU node
+    8.59 s) with the device-resident stretch-move sampler."""
+    from jaxtronomy_b200.Sampling.sampler import mcmc_emcee
+
+    n_walkers, n_run = 256, 100
+    sig = np.full(x0.size, 0.005)
+
+    def run():
+        return mcmc_emcee(like, n_walkers, n_run, 0, x0, sig, seed=3)
+
+    run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    samples, dist = run()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    acc = float(mcmc_emcee.last_sampler.acceptance_fraction.mean())
+    return dict(config="C1 notebook MCMC: 256 walkers x 100 steps (2 half-ensemble likelihood batches per step), "
+                       "same model as the PSO run, device-resident stretch move",
+                wall_s=dt, likelihoods_per_s=n_walkers * n_run / dt, acceptance_fraction=acc,
+                logL_max=float(dist.max()), logL_truth=like.logL(x0), samples=list(samples.shape),
+                published="lenstronomy 211.1 s, JAXtronomy (CPU node) 8.59 s")
+
+
+def c1mcmc():
+    return c1(mcmc=True)
 
 
 def mixed():
