@@ -124,6 +124,30 @@ def test_gradient_matches_oracle_finite_differences(name, linear):
     print("gradient vs oracle finite differences: %s linear=%s worst relative error %.2e" % (name, linear, worst))
 
 
+def test_gradient_of_a_gated_linear_solve_is_zero():
+    """A degenerate basis (two identical source components) fails the reference's stability gate: the amplitudes are
+    forced to 0 (de_lens.py:91-105), the model is identically 0 and so is the gradient (jnp.where passes the tangent
+    of the selected, constant branch)."""
+    import torch
+
+    from tests.test_gpu_parity import build_image_model
+    from tests.test_oracle_golden import build_oracle_image_model
+
+    c = IMSIM["linear_degenerate"]
+    lin = build_image_model(c, linear=True)
+    names = lin.param_names
+    row = _base_row(c, names)
+    logl, grad, amps = lin.logL_linear_grad_batch(torch.as_tensor(row[None, :], device="cuda"))
+    assert not amps.any() and not grad.any() and torch.isfinite(logl).all()
+    om = build_oracle_image_model(c)
+    ol = _oracle_logl(om, c, names, row, True)
+    assert abs(float(logl[0]) - ol) <= 1e-10 * abs(ol)
+    bumped = np.tile(row, (2, 1))
+    bumped[1, 0] += 1e-3  # the likelihood is flat there: the forward path agrees with the zero gradient
+    lb = lin.logL_linear_batch(torch.as_tensor(bumped, device="cuda"))[0]
+    assert float(lb[0]) == float(lb[1]) == float(logl[0])
+
+
 def test_gradient_is_reproducible_and_chunked_batches_agree():
     import torch
 
