@@ -6,7 +6,7 @@ import numpy as np
 
 from jaxtronomy_b200 import parallel
 
-__all__ = ["prepare_logL_func", "ParticleSwarmOptimizer", "DeviceParticleSwarmOptimizer", "DeviceEnsembleSampler",
+__all__ = ["Sampler", "prepare_logL_func", "ParticleSwarmOptimizer", "DeviceParticleSwarmOptimizer", "DeviceEnsembleSampler",
            "mcmc_emcee", "sample_ball_truncated"]
 
 
@@ -131,6 +131,7 @@ class DeviceParticleSwarmOptimizer(object):
         from jaxtronomy_b200 import _lib
 
         history = torch.empty(max_iter, dtype=torch.float64, device=self.position.device)
+        best_pos = torch.empty((max_iter, self.param_count), dtype=torch.float64, device=self.position.device)
         rnd = torch.empty((3, self.particleCount, self.param_count), dtype=torch.float64, device=self.position.device)
         for it in range(max_iter):
             fitness = self._get_fitness()
@@ -138,6 +139,8 @@ class DeviceParticleSwarmOptimizer(object):
             _lib.pso_step(self.position, self.velocity, self.personal_best, self.personal_fitness, self.global_best,
                           self.global_fitness, fitness, rnd, c1, c2)
             history[it] = self.global_fitness[0]
+            best_pos[it] = self.global_best
+        self.best_position_history = best_pos  # [max_iter, n] device tensor: the global best after every iteration
         return self.global_best.cpu().numpy(), history.cpu().numpy().tolist()
 
 
@@ -253,3 +256,41 @@ def mcmc_emcee(likelihood_module, n_walkers, n_run, n_burn, mean_start, sigma_st
     sampler.run_mcmc(initpos, n_burn + n_run)
     mcmc_emcee.last_sampler = sampler
     return sampler.get_chain(discard=n_burn, flat=True), sampler.get_log_prob(discard=n_burn, flat=True)
+
+
+class Sampler(object):
+    """The sampler front end of the reference (jaxtronomy/Sampling/sampler.py:16-212, a lenstronomy ``Sampler`` whose
+    ``pso`` and ``mcmc_emcee`` are re-routed to the batched likelihood): same constructor and method signatures, with
+    the swarm / the walkers resident on the device (DeviceParticleSwarmOptimizer, DeviceEnsembleSampler)."""
+
+    def __init__(self, likelihoodModule):
+        self.chain = likelihoodModule
+        self.lower_limit, self.upper_limit = self.chain.param.param_limits()
+
+    def pso(self, n_particles, n_iterations, lower_start=None, upper_start=None, threadCount=1, init_pos=None, mpi=False,
+            print_key="PSO", verbose=False, seed=0):
+        """-> (best-fit argument vector, [logL of the global best per iteration, its position per iteration, []])
+        (sampler.py:20-110; the reference's third list holds velocities, which stay on the device here)."""
+        if mpi:
+            raise ValueError("mpi must be False in JAXtronomy since parallelization is done through JAX")
+        if lower_start is None or upper_start is None:
+            lower_start, upper_start = np.array(self.lower_limit), np.array(self.upper_limit)
+        else:
+            lower_start = np.maximum(lower_start, self.lower_limit)
+            upper_start = np.minimum(upper_start, self.upper_limit)
+        pso = DeviceParticleSwarmOptimizer(self.chain, lower_start, upper_start, n_particles, seed=seed)
+        if init_pos is None:
+            init_pos = (upper_start - lower_start) / 2 + lower_start
+        pso.set_global_best(init_pos, [0] * len(init_pos), self.chain.logL(init_pos))
+        result, log_likelihood_list = pso.optimize(n_iterations, verbose=verbose)
+        pos_list = pso.best_position_history.cpu().numpy().tolist()
+        if verbose:
+            print(log_likelihood_list[-1], "log likelihood of the best position (%s)" % print_key)
+        return result, [log_likelihood_list, pos_list, []]
+
+    def mcmc_emcee(self, n_walkers, n_run, n_burn, mean_start, sigma_start, mpi=False, progress=False, threadCount=1,
+                   initpos=None, backend_filename=None, start_from_backend=False, seed=0):
+        """-> (flat samples, their log-probabilities)   (sampler.py:112-212)"""
+        return mcmc_emcee(self.chain, n_walkers, n_run, n_burn, mean_start, sigma_start, initpos=initpos, seed=seed,
+                          mpi=mpi, progress=progress, threadCount=threadCount, backend_filename=backend_filename,
+                          start_from_backend=start_from_backend)

@@ -203,3 +203,24 @@ def test_device_ensemble_sampler_on_the_image_likelihood():
     np.testing.assert_allclose(s.get_log_prob()[-1], like.logL_batch_device(last).cpu().numpy(), rtol=1e-12)
     with pytest.raises(ValueError):
         mcmc_emcee(like, 8, 2, 0, x0, 1e-3 * np.ones_like(x0), mpi=True)
+
+
+def test_sampler_front_end_pso_then_mcmc():
+    """Sampler(likelihoodModule).pso / .mcmc_emcee with the reference's signatures (sampler.py:16-212)."""
+    from jaxtronomy_b200.Sampling.sampler import Sampler
+
+    c, lin, param, like = _setup()
+    x0 = np.asarray(param.kwargs2args(c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]))
+    sampler = Sampler(like)
+    sig = 0.02 * np.maximum(np.abs(x0), 0.1)
+    start = x0 + 0.5 * sig
+    result, (logl_list, pos_list, vel_list) = sampler.pso(32, 25, lower_start=x0 - sig, upper_start=x0 + sig,
+                                                           init_pos=start, seed=2)
+    assert result.shape == x0.shape and len(logl_list) == 25 and len(pos_list) == 25 and vel_list == []
+    assert all(b >= a for a, b in zip(logl_list[:-1], logl_list[1:]))  # the global best never gets worse
+    assert logl_list[-1] >= like.logL(start) and abs(like.logL(np.asarray(pos_list[-1])) - logl_list[-1]) <= 1e-9 * abs(logl_list[-1])
+    np.testing.assert_array_equal(np.asarray(pos_list[-1]), result)
+    samples, dist = sampler.mcmc_emcee(16, 10, 5, result, 1e-3 * np.maximum(np.abs(result), 0.1), seed=1)
+    assert samples.shape == (160, x0.size) and np.all(np.isfinite(dist))
+    with pytest.raises(ValueError):
+        sampler.pso(8, 2, mpi=True)
