@@ -107,6 +107,18 @@ def test_multi_band_likelihood_is_the_sum_of_bands():
     x0 = param.kwargs2args(kl, ks, kll)
     got = like.logL_batch(np.stack([x0, x0]))
     assert abs(got[0] - want) <= 1e-10 * abs(want) and got[0] == got[1]
+    # the gradient of the multi-band likelihood is the sum of the bands' gradients (pixel PSF band + Gaussian PSF band)
+    val, grad = like.value_and_grad(x0)
+    assert abs(val - want) <= 1e-10 * abs(want) and np.all(np.isfinite(grad))
+    scale = np.abs(grad).max()
+    for j in range(len(x0)):
+        best = np.inf
+        for h in (1e-4, 1e-5, 1e-6):
+            e = np.zeros_like(x0)
+            e[j] = h
+            fd = (8 * (like.logL(x0 + e) - like.logL(x0 - e)) - (like.logL(x0 + 2 * e) - like.logL(x0 - 2 * e))) / (12 * h)
+            best = min(best, abs(grad[j] - fd))
+        assert best <= 1e-6 * scale, (j, grad[j], best)
 
 
 def test_pso_step_is_bit_exact_against_the_oracle():
