@@ -720,7 +720,6 @@ struct ConvSpec {
   int accumulate;  // out += scale * conv(in) instead of out = ...
   const FftConv* fft = nullptr;  // set: take the FFT path
   const double* kernel_host = nullptr;  // host copy of `kernel` (weights passed by value to k_conv_tiled_u)
-  ConvFuse fuse{nullptr, nullptr, nullptr, nullptr};  // partial != null: also reduce the n_lin = 1 normal equations
 };
 
 // smallest m >= n of the form 2^a 3^b 5^c 7^d (cuFFT's fast sizes)
@@ -849,21 +848,8 @@ int launch_conv_tiled_u(const ConvSpec& c, const double* in, double* out, int64_
     const int64_t ni = n_images - i0 < 65535 ? n_images - i0 : 65535;
     const size_t off = (size_t)i0 * c.nx * c.ny;
     Timed timed(kClsConv, st);
-    if (c.fuse.partial) {
-      static bool configured_f = false;
-      if (!configured_f) {
-        LSIM_CUDA(cudaFuncSetAttribute(k_conv_tiled_u<KT, R, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-        configured_f = true;
-      }
-      ConvFuse f = c.fuse;
-      f.partial += (size_t)i0 * tiles * 2;
-      k_conv_tiled_u<KT, R, NW, true><<<dim3((unsigned)tiles, (unsigned)ni), NW * 32, smem, st>>>(
-          in + off, out + off, c.nx, c.ny, c.mode, c.scale, c.accumulate, W, f);
-    } else {
-      k_conv_tiled_u<KT, R, NW, false><<<dim3((unsigned)tiles, (unsigned)ni), NW * 32, smem, st>>>(
-          in + off, out + off, c.nx, c.ny, c.mode, c.scale, c.accumulate, W, c.fuse);
-    }
+    k_conv_tiled_u<KT, R, NW><<<dim3((unsigned)tiles, (unsigned)ni), NW * 32, smem, st>>>(
+        in + off, out + off, c.nx, c.ny, c.mode, c.scale, c.accumulate, W);
     int rc = after_launch("k_conv_tiled_u");
     if (rc != LSIM_OK) return rc;
   }
@@ -932,25 +918,11 @@ int launch_rebin(const PlanDev& D, const double* sub, double* out, int64_t n_ima
 }
 
 // pixel-grid convolution of the plan (regular path): out = image_scale * conv(in)
-int launch_conv(const lsim_plan* plan, const double* in, double* out, int64_t n_images, cudaStream_t st,
-                double* fuse_partial = nullptr) {
+int launch_conv(const lsim_plan* plan, const double* in, double* out, int64_t n_images, cudaStream_t st) {
   const PlanDev& D = plan->dev;
   ConvSpec c{D.nx, D.ny, D.K, D.kernel, D.kernel_1d, D.conv_mode, D.image_scale, 0, plan->fft_lo,
              plan->kernel_host.empty() ? nullptr : plan->kernel_host.data()};
-  if (fuse_partial) c.fuse = ConvFuse{D.w_data, D.data, D.mask, fuse_partial};
   return launch_conv_spec(c, in, out, n_images, st);
-}
-
-// Tiles per image of the register-tiled convolution when the plan's pixel-grid PSF takes that path (the conditions
-// and the tile height of launch_conv_spec / launch_conv_tiled_kt), else 0.
-int conv_tiled_tiles(const lsim_plan* plan) {
-  const PlanDev& D = plan->dev;
-  if (D.conv_mode == LSIM_CONV_NONE || D.ss_conv || plan->fft_lo || D.kernel_1d || plan->kernel_host.empty() ||
-      D.K > 31 || getenv("LSIM_CONV_GENERIC"))
-    return 0;
-  const int w64 = ((D.ny + 63) / 64) * 64, w60 = ((D.ny + 59) / 60) * 60;
-  const int th = w60 < w64 ? 60 : 64;
-  return ((D.nx + 31) / 32) * ((D.ny + th - 1) / th);
 }
 
 // supersampled convolution (SubgridKernelConvolution.re_size_convolve, convolution.py:153-166):
@@ -976,7 +948,7 @@ int launch_conv_supersampled(const lsim_plan* plan, const double* sub, double* h
 //   ws   : scratch, laid out for `chunk` sets
 //   dst  : where the final (convolved, scaled) basis images [n][n_slots][npix] go
 int run_chunk(const lsim_plan* plan, const double* params, int64_t s0, int64_t n, int64_t chunk, double* ws,
-              double* dst, cudaStream_t st, double* fuse_partial = nullptr) {
+              double* dst, cudaStream_t st) {
   const PlanDev& D = plan->dev;
   const size_t npix = (size_t)D.nx * D.ny, nsub = npix * D.ss * D.ss, ns = (size_t)D.n_slots;
   // the scratch starts with the prepared-constants blocks of the chunk (none when the caller gave no scratch)
@@ -988,7 +960,7 @@ int run_chunk(const lsim_plan* plan, const double* params, int64_t s0, int64_t n
   } else if (!D.ss_conv) {
     double* U = ws;  // [chunk][ns][npix]
     rc = launch_image(plan, params, s0, n, 1.0, U, nullptr, st, prep);
-    if (rc == LSIM_OK) rc = launch_conv(plan, U, dst, n * D.n_slots, st, fuse_partial);
+    if (rc == LSIM_OK) rc = launch_conv(plan, U, dst, n * D.n_slots, st);
   } else {
     double* U = ws;
     double* Usub = ws + (size_t)chunk * ns * npix;
@@ -1005,12 +977,8 @@ int run_chunk(const lsim_plan* plan, const double* params, int64_t s0, int64_t n
 #ifndef LSIM_LIKE_RESIDENT_DEFAULT
 #define LSIM_LIKE_RESIDENT_DEFAULT 0  // k_likelihood_res for n_lin = 1 (see lsim_kernels.cuh)
 #endif
-#ifndef LSIM_LIKE_FUSE_DEFAULT
-#define LSIM_LIKE_FUSE_DEFAULT 0  // n_lin = 1: normal equations reduced in the convolution's epilogue (ConvFuse)
-#endif
 int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, int64_t n, int linear, int marg,
-                      double* logl, double* amps, double* model, const double* err, cudaStream_t st,
-                      const double* fused = nullptr, int n_tiles = 0) {
+                      double* logl, double* amps, double* model, const double* err, cudaStream_t st) {
   const int ns = plan->dev.n_slots;
   dim3 grid((unsigned)n);
   Timed timed(kClsLike, st);
@@ -1022,8 +990,7 @@ int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, i
     return after_launch("k_likelihood_res");
   }
   if (ns <= 1)
-    k_likelihood<1><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err, fused,
-                                             n_tiles);
+    k_likelihood<1><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else if (ns <= 2)
     k_likelihood<2><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else if (ns <= 4)
@@ -1271,22 +1238,10 @@ int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear
   double* main_ws = ws + (size_t)chunk * prefix_bytes(plan) / sizeof(double);  // run_chunk skips the same prefix
   double* err = D.ps_var ? ws + (size_t)chunk * prep_bytes(plan) / sizeof(double) : nullptr;  // [chunk][npix]
   double* C = conv ? main_ws + (size_t)chunk * img + (D.ss_conv ? 2 * (size_t)chunk * sub : 0) : main_ws;
-  // n_lin = 1: let the convolution's epilogue reduce the normal equations (the per-tile partials take the place of
-  // the prepared-constants blocks, which are dead once k_image has run).  LSIM_LIKE_FUSE=0/1 overrides the default.
-  const char* fenv = getenv("LSIM_LIKE_FUSE");
-  const bool want_fuse = (fenv && *fenv) ? (*fenv != '0') : (LSIM_LIKE_FUSE_DEFAULT != 0);
-  const int ftiles = conv_tiled_tiles(plan);
-  const bool fuse = want_fuse && linear_solve && D.n_slots == 1 && !err && D.n_points == 0 && ftiles > 0 &&
-                    (size_t)ftiles * 2 * sizeof(double) <= prefix_bytes(plan);
   for (int64_t s0 = 0; s0 < B; s0 += chunk) {
     const int64_t n = B - s0 < chunk ? B - s0 : chunk;
-    int rc = run_chunk(plan, params, s0, n, chunk, ws, C, st, fuse ? ws : nullptr);
+    int rc = run_chunk(plan, params, s0, n, chunk, ws, C, st);
     if (rc != LSIM_OK) return rc;
-    if (fuse) {
-      rc = launch_likelihood(plan, C, s0, n, linear_solve, source_marg, logl, amps, model, nullptr, st, ws, ftiles);
-      if (rc != LSIM_OK) return rc;
-      continue;
-    }
     if (err) {
       Timed timed(kClsOther, st);
       k_ps_error_map<<<(unsigned)n, kBlock, 0, st>>>(D, params, s0, err);

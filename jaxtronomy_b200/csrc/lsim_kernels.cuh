@@ -393,7 +393,6 @@ k_rebin(const double* __restrict__ flux, double* __restrict__ out, int nx, int n
 // One CTA computes a kConvT x kConvT output tile of one image; thread (tx, ty) produces kConvR rows.
 // mode ZERO: out = sum_{i,j} in[y - i + r, x - j + r] k[i,j] with zeros outside (fftconvolve "same",
 // convolution.py:73-96); mode EDGE: the image is edge-replicated (convolution.py:216-236).
-__device__ __forceinline__ double warp_sum(double v);
 constexpr int kConvT = 32;
 constexpr int kConvR = 4;  // rows per thread: 256 threads = 32 x 8, 8*4 = 32 rows
 
@@ -462,21 +461,10 @@ struct ConvWeights {
   double w[KT * KT];
 };
 
-// FUSE: the epilogue also reduces this tile's share of the WLS normal equations of a ONE-component linear model,
-//   M += w v^2,  R += (w d) v   (v = nan_to_num of the stored pixel, w = 1/C_D(data), zero off the likelihood mask),
-// into partial[image][tile][2] -- k_likelihood<1> then skips its first pass over the convolved image (one 259 KB read
-// per set less).  4 FMAs next to the 2 K^2 of the convolution itself.
-struct ConvFuse {
-  const double* w;
-  const double* d;
-  const unsigned char* mask;
-  double* partial;
-};
-
-template <int KT, int R, int NW, bool FUSE = false>
+template <int KT, int R, int NW>
 __global__ void __launch_bounds__(NW * 32, 2)
 k_conv_tiled_u(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int mode, double scale,
-               int accumulate, const __grid_constant__ ConvWeights<KT> W, ConvFuse F) {
+               int accumulate, const __grid_constant__ ConvWeights<KT> W) {
   constexpr int NT = NW * 32, TH = R * NW, HALO = KT - 1, TWD = 32 + HALO, PITCH = TWD | 1;
   extern __shared__ double smem[];
   double* tile = smem;  // [TH + HALO][PITCH]
@@ -508,42 +496,12 @@ k_conv_tiled_u(const double* __restrict__ in, double* __restrict__ out, int nx, 
   }
   double* dst = out + (int64_t)blockIdx.y * nx * ny;
   const int x = tx0 + lane;
-  double fm = 0.0, fr = 0.0;
 #pragma unroll
   for (int o = 0; o < R; ++o) {
     const int y = ty0 + warp * R + o;
     if (x < nx && y < ny) {
       double* d = dst + (int64_t)y * nx + x;
-      const double v = accumulate ? fma(acc[o], scale, *d) : acc[o] * scale;
-      *d = v;
-      if (FUSE) {
-        const int p = y * nx + x;
-        if (!F.mask || F.mask[p]) {
-          const double vs = nan_to_num(v), w = __ldg(F.w + p);
-          fm += w * vs * vs;
-          fr += (w * __ldg(F.d + p)) * vs;
-        }
-      }
-    }
-  }
-  if (FUSE) {
-    fm = warp_sum(fm);
-    fr = warp_sum(fr);
-    __syncthreads();  // the input tile is no longer needed: its first 2 NW doubles carry the warp sums
-    if (lane == 0) {
-      tile[2 * warp] = fm;
-      tile[2 * warp + 1] = fr;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double m = 0.0, r = 0.0;
-      for (int w = 0; w < NW; ++w) {
-        m += tile[2 * w];
-        r += tile[2 * w + 1];
-      }
-      double* dp = F.partial + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
-      dp[0] = m;
-      dp[1] = r;
+      *d = accumulate ? fma(acc[o], scale, *d) : acc[o] * scale;
     }
   }
 }
@@ -846,8 +804,7 @@ constexpr int kLikeUnroll = LSIM_LIKE_UNROLL;
 template <int NS>
 __global__ void __launch_bounds__(kBlock)
 k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linear, int marg, double* __restrict__ logl,
-             double* __restrict__ amps, double* __restrict__ model_out, const double* __restrict__ err_map,
-             const double* __restrict__ fused = nullptr, int n_tiles = 0) {
+             double* __restrict__ amps, double* __restrict__ model_out, const double* __restrict__ err_map) {
   constexpr int NM = NS * (NS + 1) / 2;
   __shared__ double scratch[(NM + NS + 1) * (kBlock / 32)];
   __shared__ double s_amp[NS];
@@ -863,16 +820,6 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
     double acc[NM + NS];
 #pragma unroll
     for (int i = 0; i < NM + NS; ++i) acc[i] = 0.0;
-    if (NS == 1 && fused) {
-      // the normal equations were reduced per tile by the convolution's epilogue (ConvFuse): add the tiles in order
-      if (threadIdx.x == 0) {
-        const double* f = fused + bl * n_tiles * 2;
-        for (int t = 0; t < n_tiles; ++t) {
-          acc[0] += f[2 * t];
-          acc[NM] += f[2 * t + 1];
-        }
-      }
-    } else {
     // 4 pixels per thread per trip: all loads of a trip are issued before any arithmetic (latency hiding)
     for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kBlock) {
       double a[kLikeUnroll][NS], wgt[kLikeUnroll], dat[kLikeUnroll];
@@ -902,7 +849,6 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
       }
     }
     block_sum(acc, scratch);
-    }
     if (threadIdx.x == 0) {
       double M[NS * NS], M2[NS * NS], R[NS], ev[NS];
       int m = 0;

@@ -438,60 +438,6 @@ def test_resident_likelihood_kernel_matches_the_generic_one(headline, monkeypatc
     assert abs(float(l_res[4]) - ol) <= 1e-10 * abs(ol) and abs(float(a_res[4, 0]) - op[0]) <= 1e-10 * abs(op[0])
 
 
-def test_normal_equations_fused_into_the_convolution_match(headline, monkeypatch):
-    """n_lin = 1: LSIM_LIKE_FUSE=1 lets the PSF convolution's epilogue reduce M = A W A^T, R = A W d per tile and
-    k_likelihood<1> skip its first pass.  Same per-pixel arithmetic, tile-wise summation order."""
-    import torch
-
-    from jaxtronomy_b200.Data.imaging_data import ImageData
-    from jaxtronomy_b200.Data.psf import PSF
-    from jaxtronomy_b200.ImSim.image_linear_solve import ImageLinearFit
-    from jaxtronomy_b200.LensModel.lens_model import LensModel
-    from jaxtronomy_b200.LightModel.light_model import LightModel
-
-    def both(model, params, **kw):
-        out = []
-        for flag in ("1", "0"):
-            monkeypatch.setenv("LSIM_LIKE_FUSE", flag)
-            l, a, m = model.logL_linear_batch(params, **kw)
-            torch.cuda.synchronize()
-            out.append((l.clone(), a.clone(), None if m is None else m.clone()))
-        return out
-
-    lin = headline["model"]
-    t = headline["params"].clone()  # 296 sets: more than one launch wave, a single chunk
-    t[3, 15] = 1e6                  # all-zero basis image -> M = 0 -> amplitude 0
-    for kw in (dict(), dict(source_marg=True), dict(return_model=True)):
-        (l1, a1, m1), (l0, a0, m0) = both(lin, t, **kw)
-        torch.testing.assert_close(l1, l0, rtol=1e-13, atol=0)
-        torch.testing.assert_close(a1, a0, rtol=1e-13, atol=0)
-        if m1 is not None:
-            torch.testing.assert_close(m1, m0, rtol=1e-13, atol=0)
-        assert float(a1[3, 0]) == 0.0
-    # several chunks (8 x SMs sets each) and a likelihood mask + noise map
-    st = headline["static"]
-    rng = np.random.default_rng(8)
-    kd = {k: v for k, v in st["kwargs_data"].items() if k not in ("exposure_time", "background_rms")}
-    data = ImageData(image_data=headline["data_image"], noise_map=0.05 + 0.02 * rng.uniform(size=(180, 180)), **kd)
-    mask = (rng.uniform(size=(180, 180)) > 0.25).astype(float)
-    lin2 = ImageLinearFit(data, PSF(psf_type="PIXEL", kernel_point_source=st["kernel"]), LensModel(["EPL", "SHEAR"]),
-                          LightModel(["SERSIC_ELLIPSE"]), LightModel([]),
-                          kwargs_numerics=dict(supersampling_factor=3), likelihood_mask=mask)
-    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
-    big = t[torch.arange(8 * n_sm + 50, device="cuda") % t.shape[0]].contiguous()
-    (l1, a1, _), (l0, a0, _) = both(lin2, big)
-    torch.testing.assert_close(l1, l0, rtol=1e-13, atol=0)
-    torch.testing.assert_close(a1, a0, rtol=1e-13, atol=0)
-    # small frame, other PSF size (other tile shape), and the oracle
-    from bench import build_headline, oracle_headline_logl
-
-    small = build_headline(num_pix=70, ss=2, kernel_size=9, n_sets=5, seed=5)
-    (l1, a1, _), (l0, a0, _) = both(small["model"], small["params"])
-    torch.testing.assert_close(l1, l0, rtol=1e-13, atol=0)
-    ol, op = oracle_headline_logl(small, 4)
-    assert abs(float(l1[4]) - ol) <= 1e-10 * abs(ol) and abs(float(a1[4, 0]) - op[0]) <= 1e-10 * abs(op[0])
-
-
 def test_fp64_peak_microbenchmark_runs():
     from jaxtronomy_b200 import _lib
 
