@@ -134,8 +134,9 @@ struct lsim_plan {
   int n_sm = 148;
   // gradient path (lsim_logl_grad): transposed PSF = the flipped kernel; grad_nl = lens profiles held in registers
   bool grad_ok = false;
-  bool grad_fast = false;  // every lens profile has closed-form derivatives (EPL, SHEAR)
+  int grad_tier = 2;  // code tier of k_image_grad this model needs (lsim_grad.cuh: lens_grad_tier)
   int grad_series = 0;
+  int grad_stateful = 0;  // leading profiles of the gradient's lens list with a register-resident point state
   size_t grad_smem = 0;
   const lsim_lens_desc* grad_lens = nullptr;  // device: the gradient's lens list (EPL_MULTIPOLE_M1M3M4 expanded)
   int n_grad_lens = 0;
@@ -181,8 +182,9 @@ int configure_kernels() {
   LSIM_CUDA(cudaFuncSetAttribute(k_conv_separable, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
   LSIM_CUDA(cudaFuncSetAttribute(k_likelihood_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLikeResSmem));
 #define LSIM_GRAD_ATTR(NS)                                                                                        \
-  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax)); \
-  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax)); \
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax)); \
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
   LSIM_GRAD_ATTR(0)
   LSIM_GRAD_ATTR(1)
   LSIM_GRAD_ATTR(2)
@@ -382,18 +384,19 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
       bool ok = !d->multi_plane && !d->supersampled_conv && d->n_points == 0 && !p->f32 &&
                 (d->conv_mode != LSIM_CONV_EDGE || d->kernel_separable);
       int gs = 0;
-      bool fast = true;
+      int tier = 0;
       std::vector<lsim_lens_desc> gl((size_t)4 * (d->n_lens > 0 ? d->n_lens : 1));
       const int ngl = ad::expand_grad_lens(d->lens, d->n_lens, gl.data(), (int)gl.size());
       ok = ok && ngl >= 0;
       for (int i = 0; ok && i < d->n_lens; ++i) ok = ad::lens_grad_supported(d->lens[i]);
       for (int i = 0; ok && i < ngl; ++i) {
-        fast = fast && ad::lens_grad_closed_form(gl[i]);
+        tier = ad::lens_grad_tier(gl[i]) > tier ? ad::lens_grad_tier(gl[i]) : tier;
         gs += ad::lens_grad_has_series(gl[i]) ? 1 : 0;
+        p->grad_stateful += ad::lens_grad_stateful(gl[i]) ? 1 : 0;
       }
       for (int i = 0; i < d->n_light; ++i) ok = ok && ad::light_grad_supported(d->light[i]);
       p->grad_series = gs;
-      p->grad_fast = fast;
+      p->grad_tier = tier;
       p->n_grad_lens = ok ? ngl : 0;
       p->grad_smem = grad_smem_bytes(p->n_grad_lens, d->n_light, gs);
       p->grad_ok = ok && p->grad_smem <= kGradSmemMax;
@@ -1080,11 +1083,13 @@ int launch_image_grad(const lsim_plan* plan, const double* params, int64_t set0,
     {
       Timed timed(kClsImage, st);
 #define LSIM_GRAD_LAUNCH(NS)                                                                                      \
-  if (plan->grad_fast)                                                                                            \
-    k_image_grad<NS, true><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); \
+  if (plan->grad_tier == 0)                                                                                       \
+    k_image_grad<NS, 0><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); \
+  else if (plan->grad_tier == 1)                                                                                  \
+    k_image_grad<NS, 1><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); \
   else                                                                                                            \
-    k_image_grad<NS, false><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt);
-      switch (plan->grad_series < 2 ? plan->grad_series : 2) {  // EPL-family profiles kept in registers
+    k_image_grad<NS, 2><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt);
+      switch (plan->grad_stateful < 2 ? plan->grad_stateful : 2) {  // EPL-family / NIE profiles kept in registers
         case 1: LSIM_GRAD_LAUNCH(1) break;
         case 2: LSIM_GRAD_LAUNCH(2) break;
         default: LSIM_GRAD_LAUNCH(0) break;

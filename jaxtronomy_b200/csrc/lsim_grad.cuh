@@ -731,6 +731,10 @@ LSIM_HD bool lens_grad_supported(const lsim_lens_desc& d) {
       return false;
   }
 }
+// profiles whose point state (a 2 x 5 Jacobian) the kernel keeps in registers: the EPL family and NIE / SIE
+LSIM_HD bool lens_grad_stateful(const lsim_lens_desc& d) {
+  return d.type == LSIM_LENS_EPL || d.type == LSIM_LENS_SIE || d.type == LSIM_LENS_NIE;
+}
 LSIM_HD bool lens_grad_has_series(const lsim_lens_desc& d) {
   return d.type == LSIM_LENS_EPL || (d.type == LSIM_LENS_SIE && (d.flags & LSIM_FLAG_SIE_NIE_FALSE));
 }
@@ -776,12 +780,12 @@ inline int expand_grad_lens(const lsim_lens_desc* in, int n, lsim_lens_desc* out
       out[m++] = q;
     }
   }
-  // the profiles whose point state the kernel keeps in registers (the EPL family) go first; the order of the sum of
+  // the profiles whose point state the kernel keeps in registers (the EPL family, NIE / SIE) go first; the order of the sum of
   // deflections is internal to the gradient path
   for (int i = 1; i < m; ++i) {
-    if (!lens_grad_has_series(out[i])) continue;
+    if (!lens_grad_stateful(out[i])) continue;
     int j = i;
-    while (j > 0 && !lens_grad_has_series(out[j - 1])) {
+    while (j > 0 && !lens_grad_stateful(out[j - 1])) {
       const lsim_lens_desc t = out[j - 1];
       out[j - 1] = out[j];
       out[j] = t;
@@ -1143,9 +1147,72 @@ LSIM_HD void mp_vjp(const GLens& L, double x, double y, double vx, double vy, do
   g[7] = 0.0;
 }
 
-// FAST: the model holds closed-form profiles only (EPL, SHEAR, NULL) -- the dual-number code is not compiled in, which
-// is what lets that instantiation of k_image_grad run with half the registers.
-template <bool FAST = false>
+// ---- NIE / SIE in closed form ----------------------------------------------------------------------------------------
+// Major-axis deflection (nie.py:280-294,333-342):  psi = sqrt(q^2 (s^2 + x^2) + y^2),  e = sqrt(1 - q^2),
+//   alpha_x = (b/e) atan(e x / (psi + s)),   alpha_y = (b/e) atanh(e y / (psi + q^2 s)).
+// Jacobian w.r.t. the primitives (x', y', q, b, s) in o.s[0..9], alpha' in o.s[10..11]; the prepared duals give the map
+// to the parameters: c[0..6] = cx, cy, cos phi, sin phi, q (clamped), b, s.
+LSIM_HD void nie_point(const GLens& L, double x, double y, LensPt& o) {
+  const double cph = L.c[2].v, sph = L.c[3].v, q = L.c[4].v, b = L.c[5].v, s = L.c[6].v;
+  const double xs = x - L.c[0].v, ys = y - L.c[1].v;
+  const double xr = fma(ys, sph, xs * cph), yr = fma(ys, cph, -(xs * sph));
+  const double q2 = q * q;
+  const double psi = sqrt(fma(q2, fma(xr, xr, s * s), yr * yr));
+  const double e2 = 1.0 - q2, e = sqrt(e2), be = b / e;
+  const double dA = psi + s, dB = fma(q2, s, psi);
+  const double iA = 1.0 / dA, iB = 1.0 / dB;
+  const double A = e * xr * iA, B = e * yr * iB;
+  const double tA = atan(A), tB = atanh(B);
+  const double ax = be * tA, ay = be * tB;
+  const double Dx = be / fma(A, A, 1.0), Dy = be / fma(-B, B, 1.0);  // be d atan / dA, be d atanh / dB
+  const double ipsi = psi > 0 ? 1.0 / psi : 0.0;
+  // d psi / d(x, y, q, s)
+  const double px = q2 * xr * ipsi, py = yr * ipsi, pq = q * fma(xr, xr, s * s) * ipsi, ps = q2 * s * ipsi;
+  const double de_q = -q / e;              // d e / d q
+  const double dbe_q = b * q / (e * e2);   // d (b/e) / d q
+  // dA = de x/(psi+s) + e dx/(psi+s) - e x (dpsi + ds)/(psi+s)^2, likewise dB with (psi + q^2 s)
+  const double Ax = e * iA - A * iA * px, Ay = -A * iA * py;
+  const double Aq = de_q * xr * iA - A * iA * pq, As = -A * iA * (ps + 1.0);
+  const double Bx = -B * iB * px, By = e * iB - B * iB * py;
+  const double Bq = de_q * yr * iB - B * iB * fma(2.0 * q, s, pq), Bs = -B * iB * (ps + q2);
+  o.s[0] = Dx * Ax;
+  o.s[1] = Dy * Bx;
+  o.s[2] = Dx * Ay;
+  o.s[3] = Dy * By;
+  o.s[4] = fma(dbe_q, tA, Dx * Aq);
+  o.s[5] = fma(dbe_q, tB, Dy * Bq);
+  o.s[6] = tA / e;  // d / d b
+  o.s[7] = tB / e;
+  o.s[8] = Dx * As;
+  o.s[9] = Dy * Bs;
+  o.s[10] = ax;
+  o.s[11] = ay;
+  o.ax = fma(-ay, sph, ax * cph);
+  o.ay = fma(ay, cph, ax * sph);
+}
+
+// primitives: g = d(v . alpha)/d(b, q, s, phi, cx, cy)
+LSIM_HD void nie_vjp(const GLens& L, const LensPt& o, double x, double y, double vx, double vy,
+                     double (&g)[kLensEntries]) {
+  const double cph = L.c[2].v, sph = L.c[3].v;
+  const double Vr = fma(vy, sph, vx * cph), Vi = fma(vy, cph, -(vx * sph));
+  const double sx = fma(Vr, o.s[0], Vi * o.s[1]), sy = fma(Vr, o.s[2], Vi * o.s[3]);
+  const double xs = x - L.c[0].v, ys = y - L.c[1].v;
+  const double xr = fma(ys, sph, xs * cph), yr = fma(ys, cph, -(xs * sph));
+  g[0] = fma(Vr, o.s[6], Vi * o.s[7]);
+  g[1] = fma(Vr, o.s[4], Vi * o.s[5]);
+  g[2] = fma(Vr, o.s[8], Vi * o.s[9]);
+  g[3] = fma(sx, yr, -(sy * xr)) + fma(Vi, o.s[10], -(Vr * o.s[11]));
+  g[4] = fma(sph, sy, -(cph * sx));
+  g[5] = -fma(sph, sx, cph * sy);
+  g[6] = 0.0;
+  g[7] = 0.0;
+}
+
+// TIER: what is compiled into an instantiation of k_image_grad.  0: EPL family + SHEAR (+ NULL) only -- the headline
+// models; 1: also the closed-form multipoles and NIE / SIE; 2: everything, including the dual-number profiles.  Lower
+// tiers carry less code and fewer registers (140 vs 212), so the headline model never pays for profiles it does not use.
+template <int TIER = 2>
 LSIM_HD void lens_point(const GLens& L, const double* pool, double x, double y, LensPt& o) {
   if (L.type == LSIM_LENS_EPL) {
     epl_point(L, pool, x, y, o);
@@ -1153,12 +1220,14 @@ LSIM_HD void lens_point(const GLens& L, const double* pool, double x, double y, 
     const double xs = x - L.c[2].v, ys = y - L.c[3].v;
     o.ax = fma(L.c[1].v, ys, L.c[0].v * xs);
     o.ay = fma(L.c[1].v, xs, -(L.c[0].v * ys));
-  } else if (L.type == kGradLensMP) {
+  } else if (TIER >= 1 && L.type == kGradLensMP) {
     double hx, hy;
     mp_value(L, x, y, hx, hy);
     o.ax = L.k[0] * hx;
     o.ay = L.k[0] * hy;
-  } else if (FAST) {
+  } else if (TIER >= 1 && L.type == LSIM_LENS_NIE) {
+    nie_point(L, x, y, o);
+  } else if (TIER < 2) {
     o.ax = 0.0;
     o.ay = 0.0;
   } else {
@@ -1178,7 +1247,7 @@ LSIM_HD void lens_point(const GLens& L, const double* pool, double x, double y, 
 // center_y) for the EPL, the four parameters for the shear, the parameters themselves otherwise; lens_chain() maps
 // sums of s over any number of points to the parameters (the map is linear and constant per parameter set, so it is
 // applied once per CTA, not once per sub-pixel).
-template <bool FAST = false>
+template <int TIER = 2>
 LSIM_HD void lens_vjp(const GLens& L, const LensPt& o, double x, double y, double vx, double vy,
                       double (&g)[kLensEntries]) {
   g[6] = 0.0;
@@ -1193,9 +1262,11 @@ LSIM_HD void lens_vjp(const GLens& L, const LensPt& o, double x, double y, doubl
     g[3] = fma(vy, L.c[0].v, -(vx * L.c[1].v));
     g[4] = 0.0;
     g[5] = 0.0;
-  } else if (L.type == kGradLensMP) {
+  } else if (TIER >= 1 && L.type == kGradLensMP) {
     mp_vjp(L, x, y, vx, vy, g);
-  } else if (FAST) {
+  } else if (TIER >= 1 && L.type == LSIM_LENS_NIE) {
+    nie_vjp(L, o, x, y, vx, vy, g);
+  } else if (TIER < 2) {
     LSIM_UNROLL
     for (int k = 0; k < kLensN; ++k) g[k] = 0.0;
   } else {
@@ -1204,35 +1275,41 @@ LSIM_HD void lens_vjp(const GLens& L, const LensPt& o, double x, double y, doubl
   }
 }
 // Profiles the kernel does not keep a point state for: the deflection alone in the first pass ...
-template <bool FAST = false>
+template <int TIER = 2>
 LSIM_HD void lens_value(const GLens& L, const double* pool, double x, double y, double& ax, double& ay) {
   if (L.type == LSIM_LENS_SHEAR) {
     const double xs = x - L.c[2].v, ys = y - L.c[3].v;
     ax = fma(L.c[1].v, ys, L.c[0].v * xs);
     ay = fma(L.c[1].v, xs, -(L.c[0].v * ys));
-  } else if (L.type == kGradLensMP) {
+  } else if (TIER >= 1 && L.type == kGradLensMP) {
     double hx, hy;
     mp_value(L, x, y, hx, hy);
     ax = L.k[0] * hx;
     ay = L.k[0] * hy;
   } else {
     LensPt o;
-    lens_point<FAST>(L, pool, x, y, o);  // the Jacobian part is dead code here
+    lens_point<TIER>(L, pool, x, y, o);  // the Jacobian part is dead code here
     ax = o.ax;
     ay = o.ay;
   }
 }
 // ... and the contraction in the second, recomputing what it needs (nothing for the shear and the multipoles)
-template <bool FAST = false>
+template <int TIER = 2>
 LSIM_HD void lens_vjp_recompute(const GLens& L, const double* pool, double x, double y, double vx, double vy,
                                 double (&g)[kLensEntries]) {
   LensPt o;
-  if (L.type != LSIM_LENS_SHEAR && L.type != kGradLensMP) lens_point<FAST>(L, pool, x, y, o);
-  lens_vjp<FAST>(L, o, x, y, vx, vy, g);
+  if (L.type != LSIM_LENS_SHEAR && L.type != kGradLensMP) lens_point<TIER>(L, pool, x, y, o);
+  lens_vjp<TIER>(L, o, x, y, vx, vy, g);
+}
+LSIM_HD int lens_grad_tier(const lsim_lens_desc& d) {
+  if (d.type == LSIM_LENS_NULL || d.type == LSIM_LENS_SHEAR || lens_grad_has_series(d)) return 0;
+  if (d.type == kGradLensMP || d.type == LSIM_LENS_MULTIPOLE || d.type == LSIM_LENS_NIE || d.type == LSIM_LENS_SIE) return 1;
+  return 2;
 }
 LSIM_HD bool lens_grad_closed_form(const lsim_lens_desc& d) {
   return d.type == LSIM_LENS_NULL || d.type == LSIM_LENS_SHEAR || d.type == kGradLensMP ||
-         d.type == LSIM_LENS_MULTIPOLE || lens_grad_has_series(d);
+         d.type == LSIM_LENS_MULTIPOLE || d.type == LSIM_LENS_NIE || d.type == LSIM_LENS_SIE ||
+         lens_grad_has_series(d);
 }
 
 LSIM_HD void lens_chain(const GLens& L, const double (&s)[kLensEntries], double (&g)[kLensEntries]) {
@@ -1245,6 +1322,10 @@ LSIM_HD void lens_chain(const GLens& L, const double (&s)[kLensEntries], double 
       double a = 0.0;
       for (int j = 0; j < 4; ++j) a = fma(s[j], L.c[j].d[k], a);
       g[k] = a;
+    } else if (k < kLensN && L.type == LSIM_LENS_NIE) {  // primitives (b, q, s, phi, cx, cy); d phi = cos d(sin) - sin d(cos)
+      const double dphi = fma(L.c[2].v, L.c[3].d[k], -(L.c[3].v * L.c[2].d[k]));
+      g[k] = fma(s[0], L.c[5].d[k], fma(s[1], L.c[4].d[k], fma(s[2], L.c[6].d[k], fma(s[3], dphi,
+                                                                 fma(s[4], L.c[0].d[k], s[5] * L.c[1].d[k])))));
     } else if (k < kLensN && L.type == kGradLensMP) {  // primitives (rho, phi_m, cx, cy, r_E) = c[2], c[3], c[0], c[1], c[4]
       g[k] = fma(s[0], L.c[2].d[k], fma(s[1], L.c[3].d[k], fma(s[2], L.c[0].d[k], fma(s[3], L.c[1].d[k],
                                                                                        s[4] * L.c[4].d[k]))));

@@ -259,16 +259,15 @@ k_conv_adj_edge(const double* __restrict__ in, double* __restrict__ out, int nx,
 // whose point state -- the 2 x 5 Jacobian of the major-axis deflection -- stays in registers between the ray shooting
 // and the lens-parameter update; every other profile is evaluated for its deflection first and contracted later
 // (shear and multipoles need nothing from the first pass; dual-number profiles are evaluated twice).
-// FAST: every lens profile has closed-form derivatives (EPL, SHEAR, multipoles): no dual-number code in that
-// instantiation.
+// TIER (lsim_grad.cuh): 0 = EPL family + SHEAR only, 1 = + closed-form multipoles and NIE / SIE, 2 = + dual numbers.
 __host__ __device__ inline size_t grad_smem_bytes(int n_lens, int n_light, int n_series) {
   return (size_t)n_lens * sizeof(ad::GLens) + (size_t)n_light * sizeof(ad::GLight) +
          (size_t)n_series * ad::kGradPool * sizeof(double) +
          (size_t)grad_entries(n_lens, n_light) * kGradBlock * sizeof(double);
 }
 
-template <int NS, bool FAST>
-__global__ void __launch_bounds__(kGradBlock, FAST ? LSIM_GRAD_FAST_BLOCKS : 2)
+template <int NS, int TIER>
+__global__ void __launch_bounds__(kGradBlock, TIER < 2 ? LSIM_GRAD_FAST_BLOCKS : 2)
 k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, int n_series,
              const double* __restrict__ ubar, double wscale, double* __restrict__ partial) {
   using namespace ad;
@@ -314,13 +313,13 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
         LensPt pt[NS > 0 ? NS : 1];
 #pragma unroll
         for (int l = 0; l < NS; ++l) {
-          lens_point<FAST>(L[l], pool, x, y, pt[l]);
+          lens_point<TIER>(L[l], pool, x, y, pt[l]);
           ax += pt[l].ax;
           ay += pt[l].ay;
         }
         for (int l = NS; l < P.n_lens; ++l) {
           double fx, fy;
-          lens_value<FAST>(L[l], pool, x, y, fx, fy);
+          lens_value<TIER>(L[l], pool, x, y, fx, fy);
           ax += fx;
           ay += fy;
         }
@@ -345,14 +344,14 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
 #pragma unroll
         for (int l = 0; l < NS; ++l) {
           double gl[kLensEntries];
-          lens_vjp<FAST>(L[l], pt[l], x, y, vx, vy, gl);
+          lens_vjp<TIER>(L[l], pt[l], x, y, vx, vy, gl);
           double* e = my + (size_t)l * kLensEntries * kGradBlock;
 #pragma unroll
           for (int k = 0; k < kLensN; ++k) e[k * kGradBlock] += gl[k];
         }
         for (int l = NS; l < P.n_lens; ++l) {
           double gl[kLensEntries];
-          lens_vjp_recompute<FAST>(L[l], pool, x, y, vx, vy, gl);
+          lens_vjp_recompute<TIER>(L[l], pool, x, y, vx, vy, gl);
           double* e = my + (size_t)l * kLensEntries * kGradBlock;
           const int ne = L[l].type == LSIM_LENS_SHEAR ? 4 : kLensN;
           for (int k = 0; k < ne; ++k) e[k * kGradBlock] += gl[k];
