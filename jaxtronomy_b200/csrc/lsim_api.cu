@@ -180,7 +180,6 @@ constexpr size_t kGradSmemMax = 200 * 1024;
 int configure_kernels() {
   LSIM_CUDA(cudaFuncSetAttribute(k_conv_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
   LSIM_CUDA(cudaFuncSetAttribute(k_conv_separable, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
-  LSIM_CUDA(cudaFuncSetAttribute(k_likelihood_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLikeResSmem));
 #define LSIM_GRAD_ATTR(NS)                                                                                        \
   LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax)); \
   LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax)); \
@@ -977,21 +976,11 @@ int run_chunk(const lsim_plan* plan, const double* params, int64_t s0, int64_t n
   return after_launch("k_point_sources");
 }
 
-#ifndef LSIM_LIKE_RESIDENT_DEFAULT
-#define LSIM_LIKE_RESIDENT_DEFAULT 0  // k_likelihood_res for n_lin = 1 (see lsim_kernels.cuh)
-#endif
 int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, int64_t n, int linear, int marg,
                       double* logl, double* amps, double* model, const double* err, cudaStream_t st) {
   const int ns = plan->dev.n_slots;
   dim3 grid((unsigned)n);
   Timed timed(kClsLike, st);
-  // LSIM_LIKE_RESIDENT=0/1 overrides the default choice (read per call: a test toggles it)
-  const char* env = getenv("LSIM_LIKE_RESIDENT");
-  const bool resident = (env && *env) ? (*env != '0') : (LSIM_LIKE_RESIDENT_DEFAULT != 0);
-  if (ns == 1 && linear && !model && !err && plan->dev.nx * plan->dev.ny <= kLikeResBlock * kLikeResPix && resident) {
-    k_likelihood_res<<<grid, kLikeResBlock, kLikeResSmem, st>>>(plan->dev, conv, set0, marg, logl, amps);
-    return after_launch("k_likelihood_res");
-  }
   if (ns <= 1)
     k_likelihood<1><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else if (ns <= 2)

@@ -1298,6 +1298,7 @@ template <int TIER = 2>
 LSIM_HD void lens_vjp_recompute(const GLens& L, const double* pool, double x, double y, double vx, double vy,
                                 double (&g)[kLensEntries]) {
   LensPt o;
+  o.ax = o.ay = 0.0;
   if (L.type != LSIM_LENS_SHEAR && L.type != kGradLensMP) lens_point<TIER>(L, pool, x, y, o);
   lens_vjp<TIER>(L, o, x, y, vx, vy, g);
 }

@@ -10,8 +10,6 @@
 //   k_fft_pad/mul/crop     ... and the helpers around cuFFT for kernels of side >= 27
 //   k_point_sources        PSF stamps of the point-source images; k_ps_error_map: the PSF error map
 //   k_likelihood           WLS amplitudes (normal equations reduced per CTA, solved in registers) + chi^2
-//   k_likelihood_res       ... for one linear component: the image stays on the SM (shared memory + registers),
-//                          one pass over HBM
 //   k_pso_best/k_pso_move  one particle-swarm iteration on the device
 //   k_fp64_peak            DFMA-chain microbenchmark for the roofline denominator
 //
@@ -925,92 +923,6 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
     logl[set0 + bl] = l;
     if (amps && linear)
       for (int k = 0; k < ns; ++k) amps[(set0 + bl) * ns + k] = s_amp[k];
-  }
-}
-
-// ---- k_likelihood_res: one linear component, the convolved image resident on the SM ---------------------------------
-// The headline case (n_lin = 1, no model output, no PSF error map): k_likelihood reads the convolved image twice
-// (normal equations, then chi^2 once the amplitude is known) -- 2 x 259 KB per set from HBM, the whole cost of the
-// kernel.  A 180 x 180 fp64 image is 259 KB: more than the shared memory of an SM (227 KB) and exactly its whole
-// register file, so one CTA of 1024 threads keeps 25 pixels per thread in shared memory (200 KB, [pixel slot][thread]:
-// conflict-free) and up to 7 more in registers across the solve, and the image crosses HBM once.  Same arithmetic per
-// pixel as k_likelihood<1>; only the order of the block reduction differs (results agree to round-off).
-constexpr int kLikeResBlock = 1024;
-constexpr int kLikeResSmemPix = 25;  // per thread, in shared memory
-constexpr int kLikeResRegPix = 7;    // per thread, in registers
-constexpr int kLikeResPix = kLikeResSmemPix + kLikeResRegPix;
-constexpr size_t kLikeResSmem = (size_t)kLikeResSmemPix * kLikeResBlock * sizeof(double);
-
-__device__ __forceinline__ double block_sum_1024(double v, double* scratch /* [32] */) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  v = warp_sum(v);
-  __syncthreads();  // scratch may still be read from the previous reduction
-  if (lane == 0) scratch[wid] = v;
-  __syncthreads();
-  double s = 0.0;
-  if (threadIdx.x == 0)
-    for (int w = 0; w < kLikeResBlock / 32; ++w) s += scratch[w];
-  return s;  // valid in thread 0
-}
-
-__global__ void __launch_bounds__(kLikeResBlock, 1)
-k_likelihood_res(PlanDev P, const double* __restrict__ conv, int64_t set0, int marg, double* __restrict__ logl,
-                 double* __restrict__ amps) {
-  extern __shared__ double img[];  // [kLikeResSmemPix][kLikeResBlock]
-  __shared__ double scratch[kLikeResBlock / 32];
-  __shared__ double s_amp, s_marg;
-  const int64_t bl = blockIdx.x;
-  const int npix = P.nx * P.ny;
-  const double* A = conv + bl * (int64_t)npix;
-  double ar[kLikeResRegPix];
-  unsigned use = 0;
-  double m_acc = 0.0, r_acc = 0.0;
-#pragma unroll
-  for (int u = 0; u < kLikeResPix; ++u) {
-    const int p = threadIdx.x + u * kLikeResBlock;
-    const bool on = p < npix && (!P.mask || P.mask[p]);
-    use |= on ? (1u << u) : 0u;
-    const double v = on ? nan_to_num(A[p]) : 0.0;
-    const double w = on ? __ldg(P.w_data + p) : 0.0, d = on ? __ldg(P.data + p) : 0.0;
-    m_acc += w * v * v;
-    r_acc += (w * d) * v;
-    if (u < kLikeResSmemPix)
-      img[u * kLikeResBlock + threadIdx.x] = v;
-    else
-      ar[u - kLikeResSmemPix] = v;
-  }
-  const double M = block_sum_1024(m_acc, scratch);
-  const double R = block_sum_1024(r_acc, scratch);
-  if (threadIdx.x == 0) {
-    const double e = fabs(M);
-    const bool stable = (e / e) < 5.0 / DBL_EPSILON;  // cond2 of a 1 x 1 matrix; 0/0 and inf/inf compare false
-    bool ok = stable && e > 0.0;
-    const double amp = R / M;
-    ok = ok && (fabs(amp) <= DBL_MAX);
-    s_amp = ok ? amp : 0.0;
-    const double sign = M > 0 ? 1.0 : (M < 0 ? -1.0 : 0.0), logdet = log(e);
-    s_marg = (stable && sign != 0.0 && (logdet == logdet)) ? sign * (-logdet) / 2 : -1e15;
-  }
-  __syncthreads();
-  const double amp = s_amp;
-  double chi = 0.0;
-#pragma unroll
-  for (int u = 0; u < kLikeResPix; ++u) {
-    const int p = threadIdx.x + u * kLikeResBlock;
-    if ((use >> u) & 1u) {
-      const double v = u < kLikeResSmemPix ? img[u * kLikeResBlock + threadIdx.x] : ar[u < kLikeResSmemPix ? 0 : u - kLikeResSmemPix];
-      const double m = amp * v;
-      const double cd = P.noise_map2 ? __ldg(P.noise_map2 + p) : fma(fmax(m, 0.0), __ldg(P.inv_exposure + p), P.bkg2);
-      const double d = m - __ldg(P.data + p);
-      chi += d * d / cd;
-    }
-  }
-  chi = block_sum_1024(chi, scratch);
-  if (threadIdx.x == 0) {
-    double l = -chi / 2 + P.logl_offset;
-    if (marg) l += s_marg;
-    logl[set0 + bl] = l;
-    if (amps) amps[set0 + bl] = amp;
   }
 }
 

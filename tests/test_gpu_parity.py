@@ -387,57 +387,6 @@ def test_headline_properties(headline):
     assert torch.equal(l_again, l_all)
 
 
-def test_resident_likelihood_kernel_matches_the_generic_one(headline, monkeypatch):
-    """n_lin = 1 without a model output can take k_likelihood_res (image resident on the SM, one pass over HBM) instead
-    of k_likelihood<1> (LSIM_LIKE_RESIDENT picks).  Same arithmetic per pixel, different reduction order."""
-    import torch
-
-    from jaxtronomy_b200 import _lib
-    from jaxtronomy_b200.Data.imaging_data import ImageData
-    from jaxtronomy_b200.Data.psf import PSF
-    from jaxtronomy_b200.ImSim.image_linear_solve import ImageLinearFit
-    from jaxtronomy_b200.LensModel.lens_model import LensModel
-    from jaxtronomy_b200.LightModel.light_model import LightModel
-
-    def both(model, params, **kw):
-        out = []
-        for flag in ("1", "0"):
-            monkeypatch.setenv("LSIM_LIKE_RESIDENT", flag)
-            n0 = _lib.launch_count()
-            l, a, _ = model.logL_linear_batch(params, **kw)
-            torch.cuda.synchronize()
-            out.append((l.clone(), a.clone(), _lib.launch_count() - n0))
-        return out
-
-    lin, t = headline["model"], headline["params"][:64].clone()
-    t[3, 15] = 1e6  # source centre far outside R_frac <= 1000: an all-zero basis image -> M = 0 -> amplitude 0
-    for marg in (False, True):
-        (l_res, a_res, _), (l_gen, a_gen, _) = both(lin, t, source_marg=marg)
-        torch.testing.assert_close(l_res, l_gen, rtol=1e-13, atol=0)
-        torch.testing.assert_close(a_res, a_gen, rtol=1e-13, atol=0)
-        assert float(a_res[3, 0]) == 0.0 and torch.isfinite(l_res).all()
-    # likelihood mask + noise map
-    st = headline["static"]
-    rng = np.random.default_rng(8)
-    kd = {k: v for k, v in st["kwargs_data"].items() if k not in ("exposure_time", "background_rms")}
-    data = ImageData(image_data=headline["data_image"], noise_map=0.05 + 0.02 * rng.uniform(size=(180, 180)), **kd)
-    mask = (rng.uniform(size=(180, 180)) > 0.25).astype(float)
-    lin2 = ImageLinearFit(data, PSF(psf_type="PIXEL", kernel_point_source=st["kernel"]), LensModel(["EPL", "SHEAR"]),
-                          LightModel(["SERSIC_ELLIPSE"]), LightModel([]),
-                          kwargs_numerics=dict(supersampling_factor=3), likelihood_mask=mask)
-    (l_res, a_res, _), (l_gen, a_gen, _) = both(lin2, t[:8])
-    torch.testing.assert_close(l_res, l_gen, rtol=1e-13, atol=0)
-    torch.testing.assert_close(a_res, a_gen, rtol=1e-13, atol=0)
-    # a small frame (one pixel slot per thread is enough) and the oracle
-    from bench import build_headline, oracle_headline_logl
-
-    small = build_headline(num_pix=40, ss=2, kernel_size=7, n_sets=5, seed=5)
-    (l_res, a_res, _), (l_gen, a_gen, _) = both(small["model"], small["params"])
-    torch.testing.assert_close(l_res, l_gen, rtol=1e-13, atol=0)
-    ol, op = oracle_headline_logl(small, 4)
-    assert abs(float(l_res[4]) - ol) <= 1e-10 * abs(ol) and abs(float(a_res[4, 0]) - op[0]) <= 1e-10 * abs(op[0])
-
-
 def test_fp64_peak_microbenchmark_runs():
     from jaxtronomy_b200 import _lib
 
