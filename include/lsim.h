@@ -220,6 +220,15 @@ void lsim_plan_destroy(lsim_plan* plan);
 int lsim_ray_shoot(const lsim_plan* plan, const double* params, int64_t B, const double* x, const double* y,
                    int64_t N, int coords_batched, double* out_x, double* out_y, int what, void* stream);
 
+/* LensModel.hessian with diff=None (LensModel/lens_model.py:384-414 -> SinglePlane.hessian,
+ * LensModel/single_plane.py:142-180), batched over B parameter sets; single plane, fp64 plans only
+ * (LSIM_E_UNSUPPORTED otherwise -- the reference's multi-plane Hessian is a finite difference of ray_shooting,
+ * which the caller forms from lsim_ray_shoot).
+ *   x, y       device [N] (shared by all sets) or [B,N] when coords_batched != 0
+ *   out        device [B,4,N]: f_xx, f_xy, f_yx, f_yy (times the plan's alpha_scaling) */
+int lsim_hessian(const lsim_plan* plan, const double* params, int64_t B, const double* x, const double* y, int64_t N,
+                 int coords_batched, double* out, void* stream);
+
 /* LightModel.surface_brightness / functions_split on arbitrary points (no lensing applied here).
  *   out        device [B, n_slots, N] */
 int lsim_surface_brightness(const lsim_plan* plan, const double* params, int64_t B, const double* x,

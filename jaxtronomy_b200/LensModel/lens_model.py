@@ -169,3 +169,77 @@ class LensModel(object):
         if self.multi_plane:
             raise ValueError("alpha() in multi-plane mode is outside the scope of jaxtronomy_b200; use ray_shooting")
         return self._run(x, y, kwargs, k, what=1)
+
+    # -- second derivatives (lens_model.py:384-527) ------------------------------------------------------------
+    def hessian(self, x, y, kwargs, k=None, diff=None, diff_method="square"):
+        """Hessian of the lensing potential (f_xx, f_xy, f_yx, f_yy), lens_model.py:384-414.
+
+        ``diff=None``: the exact differentials, one `lsim_hessian` launch (single plane; the reference sums the
+        profiles' own ``hessian`` functions, single_plane.py:142-180).  With ``diff`` set, the finite differences
+        of the deflection field on a square or a cross around (x, y), lens_model.py:617-700 -- four `alpha`
+        launches.  Like `alpha`, the deflection scaling of the model is applied for every ``k``."""
+        if diff is None:
+            if self.multi_plane:
+                raise ValueError("hessian() in multi-plane mode is outside the scope of jaxtronomy_b200: form it from "
+                                 "ray_shooting differences")
+            xf, yf, shape, want_torch = _arrays.flatten_coords(x, y)
+            values = _model.gather_values(self.param_name_list, kwargs, "lens")
+            mat, B, batched = _model.pack_columns(values)
+            h = self._plan(k).hessian(mat, xf, yf)
+            return tuple(_arrays.finish(h[:, i], shape, batched, want_torch) for i in range(4))
+        if diff_method == "square":
+            return self._hessian_differential_square(x, y, kwargs, k=k, diff=diff)
+        if diff_method == "cross":
+            return self._hessian_differential_cross(x, y, kwargs, k=k, diff=diff)
+        raise ValueError('diff_method %s not supported. Chose among "square" or "cross".' % diff_method)
+
+    def _hessian_differential_cross(self, x, y, kwargs, k=None, diff=0.00001):
+        """Differentials of alpha along the cross centred at (x, y), lens_model.py:617-649."""
+        x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
+        x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
+        h = diff / 2
+        ax_dx, ay_dx = self.alpha(x + h, y, kwargs, k=k)
+        ax_dy, ay_dy = self.alpha(x, y + h, kwargs, k=k)
+        ax_dx_, ay_dx_ = self.alpha(x - h, y, kwargs, k=k)
+        ax_dy_, ay_dy_ = self.alpha(x, y - h, kwargs, k=k)
+        f_xx = (ax_dx - ax_dx_) / diff
+        f_xy = (ax_dy - ax_dy_) / diff
+        f_yx = (ay_dx - ay_dx_) / diff
+        f_yy = (ay_dy - ay_dy_) / diff
+        return f_xx, f_xy, f_yx, f_yy
+
+    def _hessian_differential_square(self, x, y, kwargs, k=None, diff=0.00001):
+        """Differentials of alpha on the square around (x, y) (minimises the curl), lens_model.py:651-688."""
+        x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
+        x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
+        h = diff / 2
+        ax_pp, ay_pp = self.alpha(x + h, y + h, kwargs, k=k)
+        ax_pn, ay_pn = self.alpha(x + h, y - h, kwargs, k=k)
+        ax_np, ay_np = self.alpha(x - h, y + h, kwargs, k=k)
+        ax_nn, ay_nn = self.alpha(x - h, y - h, kwargs, k=k)
+        f_xx = (ax_pp - ax_np + ax_pn - ax_nn) / diff / 2
+        f_xy = (ax_pp - ax_pn + ax_np - ax_nn) / diff / 2
+        f_yx = (ay_pp - ay_np + ay_pn - ay_nn) / diff / 2
+        f_yy = (ay_pp - ay_pn + ay_np - ay_nn) / diff / 2
+        return f_xx, f_xy, f_yx, f_yy
+
+    def kappa(self, x, y, kwargs, k=None, diff=None, diff_method="square"):
+        """Convergence 1/2 (f_xx + f_yy), lens_model.py:416-441."""
+        f_xx, f_xy, f_yx, f_yy = self.hessian(x, y, kwargs, k=k, diff=diff, diff_method=diff_method)
+        return 1.0 / 2 * (f_xx + f_yy)
+
+    def curl(self, x, y, kwargs, k=None, diff=None, diff_method="square"):
+        """f_xy - f_yx, lens_model.py:443-467."""
+        f_xx, f_xy, f_yx, f_yy = self.hessian(x, y, kwargs, k=k, diff=diff, diff_method=diff_method)
+        return f_xy - f_yx
+
+    def gamma(self, x, y, kwargs, k=None, diff=None, diff_method="square"):
+        """Shear (1/2 (f_xx - f_yy), f_xy), lens_model.py:469-497."""
+        f_xx, f_xy, f_yx, f_yy = self.hessian(x, y, kwargs, k=k, diff=diff, diff_method=diff_method)
+        return 1.0 / 2 * (f_xx - f_yy), f_xy
+
+    def magnification(self, x, y, kwargs, k=None, diff=None, diff_method="square"):
+        """1 / det(1 - Hessian), lens_model.py:499-526 (no guard against det = 0, like the reference)."""
+        f_xx, f_xy, f_yx, f_yy = self.hessian(x, y, kwargs, k=k, diff=diff, diff_method=diff_method)
+        det_A = (1 - f_xx) * (1 - f_yy) - f_xy * f_yx
+        return 1.0 / det_A

@@ -82,7 +82,7 @@ SYMBOLS = [
     "lsim_plan_create", "lsim_plan_destroy", "lsim_ray_shoot", "lsim_surface_brightness", "lsim_workspace_bytes",
     "lsim_image", "lsim_resize_convolve", "lsim_logl", "lsim_abi_version", "lsim_strerror", "lsim_last_cuda_error", "lsim_launch_count",
     "lsim_measure_fp64_peak", "lsim_timing_enable", "lsim_timing_read", "lsim_pso_step", "lsim_psf_error_map",
-    "lsim_logl_grad", "lsim_logl_grad_workspace_bytes",
+    "lsim_logl_grad", "lsim_logl_grad_workspace_bytes", "lsim_hessian",
 ]
 
 
@@ -103,6 +103,8 @@ def load():
     lib.lsim_plan_destroy.restype = None
     lib.lsim_ray_shoot.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp, vp, i32, vp]
     lib.lsim_ray_shoot.restype = i32
+    lib.lsim_hessian.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp, vp]
+    lib.lsim_hessian.restype = i32
     lib.lsim_surface_brightness.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp, vp]
     lib.lsim_surface_brightness.restype = i32
     lib.lsim_workspace_bytes.argtypes = [vp, i64]
@@ -338,6 +340,24 @@ class Plan:
             check(self._lib.lsim_ray_shoot(self._handle, p.data_ptr(), B, xt.data_ptr(), yt.data_ptr(), N, batched,
                                            ox.data_ptr(), oy.data_ptr(), int(what), self._stream()))
         return ox, oy
+
+    def hessian(self, params, x, y):
+        """-> [B, 4, N]: f_xx, f_xy, f_yx, f_yy (lsim_hessian; single-plane fp64 plans)."""
+        torch = _torch()
+        p = self._params(params)
+        B = p.shape[0]
+        xt, yt = self._coords(x, B), self._coords(y, B)
+        if xt.shape != yt.shape:
+            raise LsimError("x and y must have the same shape")
+        batched = 1 if (xt.ndim == 2) else 0
+        if batched and xt.shape[0] != B:
+            raise LsimError("batched coordinates must be [B, N]")
+        N = xt.shape[-1] if xt.ndim else 1
+        out = torch.empty((B, 4, N), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.lsim_hessian(self._handle, p.data_ptr(), B, xt.data_ptr(), yt.data_ptr(), N, batched,
+                                         out.data_ptr(), self._stream()))
+        return out
 
     def surface_brightness(self, params, x, y):
         torch = _torch()

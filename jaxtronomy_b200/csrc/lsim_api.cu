@@ -140,6 +140,11 @@ struct lsim_plan {
   size_t grad_smem = 0;
   const lsim_lens_desc* grad_lens = nullptr;  // device: the gradient's lens list (EPL_MULTIPOLE_M1M3M4 expanded)
   int n_grad_lens = 0;
+  const lsim_lens_desc* hess_lens = nullptr;  // device: the Hessian's lens list (same expansion; any single-plane fp64 plan)
+  int n_hess_lens = 0;
+  int hess_series = 0;
+  size_t hess_smem = 0;
+  bool hess_ok = false;
   const double* kernel_flip = nullptr;
   const double* kernel_1d_flip = nullptr;
   std::vector<double> kernel_flip_host;
@@ -184,6 +189,7 @@ int configure_kernels() {
   LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax)); \
   LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax)); \
   LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
+  LSIM_CUDA(cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
   LSIM_GRAD_ATTR(0)
   LSIM_GRAD_ATTR(1)
   LSIM_GRAD_ATTR(2)
@@ -326,6 +332,19 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
   p->has_image = has_image;
   p->has_data = has_data;
   p->f32 = d->precision == LSIM_PRECISION_F32;
+  {  // Hessian path (lsim_hessian): single plane, fp64, every profile within the dual-number scope
+    std::vector<lsim_lens_desc> gl((size_t)4 * (d->n_lens > 0 ? d->n_lens : 1));
+    const int ngl = ad::expand_grad_lens(d->lens, d->n_lens, gl.data(), (int)gl.size());
+    bool hok = !d->multi_plane && !p->f32 && ngl >= 0;
+    for (int i = 0; hok && i < d->n_lens; ++i) hok = ad::lens_grad_supported(d->lens[i]);
+    int hs = 0;
+    for (int i = 0; hok && i < ngl; ++i) hs += ad::lens_grad_has_series(gl[i]) ? 1 : 0;
+    p->hess_series = hs;
+    p->n_hess_lens = hok ? ngl : 0;
+    p->hess_smem = hess_smem_bytes(p->n_hess_lens, hs);
+    p->hess_ok = hok && p->hess_smem <= kGradSmemMax;
+    if (p->hess_ok && ngl > 0) TRY(p->upload(gl.data(), (size_t)ngl, &p->hess_lens));
+  }
   if (has_image) {
     D.nx = d->nx;
     D.ny = d->ny;
@@ -476,6 +495,28 @@ int lsim_ray_shoot(const lsim_plan* plan, const double* params, int64_t B, const
   else
     k_ray_shoot<false><<<grid, kBlock, kRaySmem, st>>>(plan->dev, params, x, y, N, coords_batched, out_x, out_y, what, rpc);
   return after_launch("k_ray_shoot");
+}
+
+int lsim_hessian(const lsim_plan* plan, const double* params, int64_t B, const double* x, const double* y, int64_t N,
+                 int coords_batched, double* out, void* stream) {
+  if (!plan || B < 0 || N < 0) return LSIM_E_INVALID;
+  if (!plan->hess_ok) return LSIM_E_UNSUPPORTED;
+  if (B == 0 || N == 0) return LSIM_OK;
+  if (!x || !y || !out || (plan->dev.n_param_cols > 0 && !params)) return LSIM_E_INVALID;
+  if (B > 65535) return LSIM_E_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PlanDev H = plan->dev;
+  H.lens = plan->hess_lens;
+  H.n_lens = plan->n_hess_lens;
+  // enough CTAs per set to fill the machine at small B, few enough that the per-CTA preparation stays amortised
+  int64_t bx = (N + kGradBlock - 1) / kGradBlock;
+  int64_t cap = (8 * (int64_t)plan->n_sm + B - 1) / B;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, (unsigned)B);
+  k_hessian<<<grid, kGradBlock, plan->hess_smem, st>>>(H, params, x, y, N, coords_batched, plan->hess_series,
+                                                        plan->dev.ray.alpha_scaling, out);
+  return after_launch("k_hessian");
 }
 
 int lsim_surface_brightness(const lsim_plan* plan, const double* params, int64_t B, const double* x,

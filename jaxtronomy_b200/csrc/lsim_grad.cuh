@@ -844,6 +844,55 @@ LSIM_HD void lens_eval_d(const GLens& L, const double* pool, double x, double y,
   }
 }
 
+// ---- Hessian of the lens potential (SinglePlane.hessian, LensModel/single_plane.py:142-180) ---------------------
+// Every profile on the path depends on the position only through (x - center_x, y - center_y) (SHEAR / CONVERGENCE:
+// ra_0, dec_0), so  f_xx = -d alpha_x / d center_x,  f_xy = -d alpha_x / d center_y,  f_yx = -d alpha_y / d center_x,
+// f_yy = -d alpha_y / d center_y  -- the tangents lens_eval_d already carries.  For the EPL family these run through
+// the 100-term tangent series (the reference's custom_jvp), which agrees with the reference's closed-form
+// kappa / alpha identities (Profiles/epl.py: EPLMajorAxis.hessian) far inside the 1e-10 bar.
+
+// tangent slots of (center_x, center_y) in a descriptor of the gradient's lens list; false: no position dependence
+LSIM_HD bool lens_center_slots(const lsim_lens_desc& d, int& ix, int& iy) {
+  switch (d.type) {
+    case LSIM_LENS_EPL:
+    case LSIM_LENS_NIE:
+    case LSIM_LENS_CSE:
+    case LSIM_LENS_NFW_ELLIPSE_CSE:
+    case LSIM_LENS_HERNQUIST_ELLIPSE_CSE: ix = 4; iy = 5; return true;
+    case LSIM_LENS_SIE:
+    case LSIM_LENS_TNFW:
+    case LSIM_LENS_MULTIPOLE:
+    case kGradLensMP: ix = 3; iy = 4; return true;
+    case LSIM_LENS_SHEAR:
+    case LSIM_LENS_NFW: ix = 2; iy = 3; return true;
+    case LSIM_LENS_SIS:
+    case LSIM_LENS_CONVERGENCE: ix = 1; iy = 2; return true;
+    default: ix = iy = 0; return false;
+  }
+}
+
+// lens_prepare_d with EVERY parameter carried as an independent variable (a fixed centre still needs its tangent):
+// the descriptor is re-pointed at a private row that holds the resolved parameter values.
+LSIM_HD bool lens_prepare_hess(const lsim_lens_desc& d, const double* row, GLens& L, double* F, double* dF) {
+  lsim_lens_desc dd = d;
+  double r2[LSIM_MAX_PARAMS];
+  for (int k = 0; k < LSIM_MAX_PARAMS; ++k) {
+    r2[k] = param_of(d, row, k);
+    dd.col[k] = k;
+  }
+  return lens_prepare_d(dd, r2, L, F, dF);
+}
+
+// h[0..3] += (f_xx, f_xy, f_yx, f_yy) of one prepared profile
+LSIM_HD void lens_hessian_add(const GLens& L, const double* pool, int ix, int iy, double x, double y, double (&h)[4]) {
+  LD fx, fy;
+  lens_eval_d(L, pool, x, y, fx, fy);
+  h[0] -= fx.d[ix];
+  h[1] -= fx.d[iy];
+  h[2] -= fy.d[ix];
+  h[3] -= fy.d[iy];
+}
+
 // ---- light ------------------------------------------------------------------------------------------------------
 using GD = Dual<kLightN>;
 

@@ -394,6 +394,50 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
   }
 }
 
+// ---- k_hessian: LensModel.hessian (LensModel/lens_model.py:384-414, single_plane.py:142-180) -------------------------
+// grid = (point tiles, sets); one thread per point, the prepared dual-number profiles of the set in shared memory.
+//   out [B, 4, N] = f_xx, f_xy, f_yx, f_yy, times alpha_scaling
+__host__ __device__ inline size_t hess_smem_bytes(int n_lens, int n_series) {
+  return (size_t)n_lens * (sizeof(ad::GLens) + 2 * sizeof(int)) + (size_t)n_series * ad::kGradPool * sizeof(double);
+}
+
+__global__ void __launch_bounds__(kGradBlock)
+k_hessian(PlanDev P, const double* __restrict__ params, const double* __restrict__ x, const double* __restrict__ y,
+          int64_t N, int coords_batched, int n_series, double scale, double* __restrict__ out) {
+  using namespace ad;
+  extern __shared__ double smem[];
+  const int64_t b = blockIdx.y;
+  const double* row = params + b * P.n_param_cols;
+  GLens* L = reinterpret_cast<GLens*>(smem);
+  double* pool = reinterpret_cast<double*>(L + P.n_lens);
+  int* slot = reinterpret_cast<int*>(pool + (size_t)n_series * kGradPool);
+  stage_math_tables();
+  for (int i = threadIdx.x; i < P.n_lens; i += kGradBlock) {
+    int off = 0;
+    for (int j = 0; j < i; ++j) off += lens_grad_has_series(P.lens[j]) ? 1 : 0;
+    L[i].coef_off = off * kGradPool;
+    lens_prepare_hess(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries);
+    int ix, iy;
+    if (!lens_center_slots(P.lens[i], ix, iy)) ix = iy = -1;
+    slot[2 * i] = ix;
+    slot[2 * i + 1] = iy;
+  }
+  __syncthreads();
+  const double* xb = coords_batched ? x + b * N : x;
+  const double* yb = coords_batched ? y + b * N : y;
+  double* o = out + b * 4 * N;
+  for (int64_t i = (int64_t)blockIdx.x * kGradBlock + threadIdx.x; i < N; i += (int64_t)gridDim.x * kGradBlock) {
+    const double xx = xb[i], yy = yb[i];
+    double h[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int l = 0; l < P.n_lens; ++l)
+      if (slot[2 * l] >= 0) lens_hessian_add(L[l], pool, slot[2 * l], slot[2 * l + 1], xx, yy, h);
+    o[i] = h[0] * scale;
+    o[N + i] = h[1] * scale;
+    o[2 * N + i] = h[2] * scale;
+    o[3 * N + i] = h[3] * scale;
+  }
+}
+
 // ---- k_grad_reduce ------------------------------------------------------------------------------------------------
 // One CTA per set: entry sums over the tiles (fixed order), then the entries of each parameter column.
 __global__ void __launch_bounds__(128)

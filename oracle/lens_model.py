@@ -115,3 +115,29 @@ def ray_shooting_multi_plane(
     x = x + alpha_x * T_ij_end
     y = y + alpha_y * T_ij_end
     return x / T_z_source, y / T_z_source
+
+
+def hessian_differential(lens_model_list, x, y, kwargs, k=None, profile_kwargs_list=None, alpha_scaling=1, h=2e-3):
+    """Second derivatives of the potential as a 4th-order central difference of the restated deflection `alpha`.
+
+    NOT a restatement of the reference's per-profile ``hessian`` functions (LensModel/single_plane.py:142-180 sums
+    them; most are closed forms, NIE/SIE a forward difference with step 1e-10, Profiles/nie.py:298-312): the closed
+    forms are pinned directly on fixtures produced by the unmodified reference (tests/golden/hessians.npz).  This
+    numerical derivative is the independent check that the Hessian IS the derivative of the deflection the oracle
+    already pins; it is good to ~1e-9 of the profile's scale where the profile is smooth.
+    -> (f_xx, f_xy, f_yx, f_yy)"""
+    x = np.asarray(x, dtype=float)
+    y = np.asarray(y, dtype=float)
+
+    def a(dx, dy):
+        return alpha(lens_model_list, x + dx, y + dy, kwargs, k=k, profile_kwargs_list=profile_kwargs_list,
+                     alpha_scaling=alpha_scaling)
+
+    def d(axis):
+        s = (h, 0.0) if axis == 0 else (0.0, h)
+        p1, m1 = a(*s), a(-s[0], -s[1])
+        p2, m2 = a(2 * s[0], 2 * s[1]), a(-2 * s[0], -2 * s[1])
+        return [(8.0 * (p1[c] - m1[c]) - (p2[c] - m2[c])) / (12.0 * h) for c in (0, 1)]
+
+    (f_xx, f_yx), (f_xy, f_yy) = d(0), d(1)
+    return f_xx, f_xy, f_yx, f_yy

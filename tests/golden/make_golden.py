@@ -534,7 +534,88 @@ def gen_point_sources():
     st.save("point_sources.npz")
 
 
+# ------------------------------------------------------------------------------------------------
+def hessian_cases():
+    """(case, profile, kwargs, profile_kwargs) of the Hessian fixtures: the deflection fixtures' parameter sets."""
+    cases = []
+    for n, (emod, ang, gamma) in enumerate([(0.0, 0.0, 2.0), (0.05, 0.3, 1.9), (0.12, 1.0, 2.0), (0.25, 0.7, 2.1),
+                                            (0.399, 2.5, 2.5), (0.45, -0.4, 1.7), (0.65, 1.9, 2.2), (0.8, 0.1, 2.0)]):
+        e1, e2 = e_from(emod, ang)
+        cases.append(("epl_%02d" % n, "EPL", dict(theta_E=1.3, gamma=gamma, e1=e1, e2=e2, center_x=0.1, center_y=-0.2), {}))
+    for i, (e1, e2) in enumerate([(0.1, -0.05), (-0.4, 0.3), (0.7, 0.7)]):
+        cases.append(("sie_%d" % i, "SIE", dict(theta_E=1.1, e1=e1, e2=e2, center_x=-0.1, center_y=0.3), {}))
+        cases.append(("nie_%d" % i, "NIE", dict(theta_E=0.9, e1=e1, e2=e2, s_scale=0.1 + 0.2 * i, center_x=0.2,
+                                               center_y=0.0), {}))
+    cases.append(("sie_epl", "SIE", dict(theta_E=1.1, e1=0.2, e2=0.1, center_x=0.0, center_y=0.0), dict(NIE=False, gamma=2)))
+    cases.append(("sis_0", "SIS", dict(theta_E=0.7, center_x=0.3, center_y=-0.6), {}))
+    cases.append(("shear_0", "SHEAR", dict(gamma1=-0.2, gamma2=0.4, ra_0=0.5, dec_0=-1.0), {}))
+    cases.append(("convergence_0", "CONVERGENCE", dict(kappa=0.12, ra_0=0.1, dec_0=0.2), {}))
+    cases.append(("nfw_0", "NFW", dict(Rs=2.4, alpha_Rs=1.5, center_x=0.0, center_y=0.0), {}))
+    cases.append(("nfw_1", "NFW", dict(Rs=0.3, alpha_Rs=0.7, center_x=1.0, center_y=2.0), {}))
+    cases.append(("tnfw_0", "TNFW", dict(Rs=1.4, alpha_Rs=3.5, r_trunc=3.2, center_x=0.0, center_y=0.0), {}))
+    cases.append(("tnfw_1", "TNFW", dict(Rs=2.4, alpha_Rs=1.5, r_trunc=1.2, center_x=1.0, center_y=2.0), {}))
+    for m in (1, 2, 3, 4):
+        cases.append(("multipole_m%d" % m, "MULTIPOLE",
+                      dict(m=m, a_m=0.05, phi_m=0.3 * m, center_x=0.1, center_y=-0.1, r_E=1.2), {}))
+    for i, (emod, ang) in enumerate([(0.2, 0.4), (0.0, 0.0), (0.45, -1.0)]):
+        e1, e2 = e_from(emod, ang)
+        cases.append(("epl_m1m3m4_%d" % i, "EPL_MULTIPOLE_M1M3M4",
+                      dict(theta_E=1.2, gamma=2.05, e1=e1, e2=e2, center_x=0.05, center_y=0.02, a1_a=0.02,
+                           delta_phi_m1=0.5, a3_a=-0.01, delta_phi_m3=0.2, a4_a=0.015, delta_phi_m4=-0.1), {}))
+    for axis in ("product_avg", "major"):
+        cases.append(("cse_%s" % axis, "CSE", dict(a=1.3, s=0.4, e1=0.15, e2=-0.2, center_x=0.1, center_y=0.0),
+                      dict(axis=axis)))
+    for hi in (True, False):
+        cases.append(("nfw_ellipse_cse_%d" % hi, "NFW_ELLIPSE_CSE",
+                      dict(Rs=1.7, alpha_Rs=1.1, e1=0.12, e2=0.08, center_x=-0.05, center_y=0.1), dict(high_accuracy=hi)))
+    cases.append(("hernquist_ellipse_cse", "HERNQUIST_ELLIPSE_CSE",
+                  dict(sigma0=0.9, Rs=1.2, e1=-0.1, e2=0.2, center_x=0.0, center_y=0.05), {}))
+    return cases
+
+
+def gen_hessians():
+    """LensModel.hessian / kappa / gamma / magnification (lens_model.py:384-527) of the unmodified reference."""
+    st = Store()
+    rng = np.random.default_rng(11)
+    x, y = points(rng, n=61)
+    skipped = []
+    for case, name, kw, pk in hessian_cases():
+        try:
+            lm = LensModel([name], profile_kwargs_list=[pk])
+            h = lm.hessian(x, y, [kw])
+        except Exception as e:  # a profile whose reference hessian needs something the shim lacks
+            skipped.append((case, repr(e)))
+            continue
+        st.add(case, dict(x=x, y=y, **kw), dict(zip(("f_xx", "f_xy", "f_yx", "f_yy"), (np.asarray(a) for a in h))),
+               dict(profile=name, profile_kwargs=pk))
+    names = ["EPL", "SHEAR", "SIS", "NFW"]
+    kw = [dict(theta_E=1.2, gamma=2.1, e1=0.2, e2=-0.1, center_x=0.05, center_y=-0.02),
+          dict(gamma1=0.03, gamma2=-0.02, ra_0=0.0, dec_0=0.0),
+          dict(theta_E=0.2, center_x=0.8, center_y=0.5),
+          dict(Rs=0.5, alpha_Rs=0.1, center_x=-0.7, center_y=0.3)]
+    lm = LensModel(names)
+    for k in (None, 0, (0, 2), [True, True, False, True]):
+        h = lm.hessian(x, y, kw, k=k)
+        g1, g2 = lm.gamma(x, y, kw, k=k)
+        outs = dict(zip(("f_xx", "f_xy", "f_yx", "f_yy"), (np.asarray(a) for a in h)))
+        outs.update(kappa=np.asarray(lm.kappa(x, y, kw, k=k)), gamma1=np.asarray(g1), gamma2=np.asarray(g2),
+                    magnification=np.asarray(lm.magnification(x, y, kw, k=k)), curl=np.asarray(lm.curl(x, y, kw, k=k)))
+        st.add("model_k%s" % json.dumps(k).replace(" ", ""), dict(x=x, y=y), outs,
+               dict(lens_model_list=names, kwargs=kw, k=k))
+    for method in ("square", "cross"):
+        h = lm.hessian(x, y, kw, diff=1e-4, diff_method=method)
+        st.add("model_diff_%s" % method, dict(x=x, y=y),
+               dict(zip(("f_xx", "f_xy", "f_yx", "f_yy"), (np.asarray(a) for a in h))),
+               dict(lens_model_list=names, kwargs=kw, k=None, diff=1e-4, diff_method=method))
+    st.save("hessians.npz")
+    for c in skipped:
+        print("skipped", c)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["hessians"]:
+        gen_hessians()
+        sys.exit(0)
     if sys.argv[1:] == ["point_sources"]:
         gen_point_sources()
         sys.exit(0)
@@ -542,3 +623,4 @@ if __name__ == "__main__":
     gen_lens_models()
     gen_imsim()
     gen_point_sources()
+    gen_hessians()

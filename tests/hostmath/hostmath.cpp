@@ -122,6 +122,35 @@ int hm_light_jvp(const lsim_light_desc* light, const double* row, const double* 
   return 0;
 }
 
+// Hessian of the lens potential through the kernel's own per-point code (k_hessian): the descriptor list is expanded
+// like lsim_plan_create does.   h [4][N] = f_xx, f_xy, f_yx, f_yy (unscaled)
+int hm_lens_hessian(const lsim_lens_desc* lens, int n_lens, const double* row, const double* x, const double* y,
+                    int64_t N, double* h) {
+  std::vector<lsim_lens_desc> gl((size_t)4 * (n_lens > 0 ? n_lens : 1));
+  const int ngl = ad::expand_grad_lens(lens, n_lens, gl.data(), (int)gl.size());
+  if (ngl < 0) return -2;
+  for (int i = 0; i < n_lens; ++i)
+    if (!ad::lens_grad_supported(lens[i])) return -2;
+  std::vector<ad::GLens> L(ngl > 0 ? ngl : 1);
+  std::vector<int> slot(2 * (size_t)(ngl > 0 ? ngl : 1));
+  std::vector<double> pool((size_t)(ngl + 1) * ad::kGradPool);
+  int off = 0;
+  for (int i = 0; i < ngl; ++i) {
+    L[i].coef_off = off * ad::kGradPool;
+    double* F = pool.data() + (size_t)off * ad::kGradPool;
+    if (!ad::lens_prepare_hess(gl[i], row, L[i], F, F + kMaxSeries)) return -2;
+    if (ad::lens_grad_has_series(gl[i])) ++off;
+    if (!ad::lens_center_slots(gl[i], slot[2 * i], slot[2 * i + 1])) slot[2 * i] = slot[2 * i + 1] = -1;
+  }
+  for (int64_t p = 0; p < N; ++p) {
+    double hh[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = 0; i < ngl; ++i)
+      if (slot[2 * i] >= 0) ad::lens_hessian_add(L[i], pool.data(), slot[2 * i], slot[2 * i + 1], x[p], y[p], hh);
+    for (int k = 0; k < 4; ++k) h[(size_t)k * N + p] = hh[k];
+  }
+  return 0;
+}
+
 // Hand-derived fast path of the gradient kernel: g [N][n_lens][6] = d(vx alpha_x + vy alpha_y)/d(parameter k).
 int hm_lens_vjp(const lsim_lens_desc* lens, int n_lens, const double* row, const double* x, const double* y, int64_t N,
                 const double* vx, const double* vy, double* ax, double* ay, double* g) {

@@ -44,6 +44,7 @@ def lib():
         h.hm_light_point.argtypes = [C.POINTER(_lib.LightDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp]
         h.hm_lens_vjp.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp]
         h.hm_eplm_vjp.argtypes = [C.POINTER(_lib.LensDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp]
+        h.hm_lens_hessian.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int64, _dp]
         _h = h
     return _h
 
@@ -131,6 +132,22 @@ def lens_jvp(lens_model_list, kwargs_list, x, y, profile_kwargs_list=None):
     rc = lib().hm_lens_jvp(arr, len(descs), _p(row), _p(x), _p(y), x.size, _p(ax), _p(ay), _p(dax), _p(day))
     assert rc == 0, rc
     return ax, ay, dax, day
+
+
+def lens_hessian(lens_model_list, kwargs_list, x, y, profile_kwargs_list=None):
+    """k_hessian's per-point code on the host: (f_xx, f_xy, f_yx, f_yy), unscaled."""
+    names = [_model.LENS_PARAM_NAMES[n] for n in lens_model_list]
+    row = np.asarray(_model.gather_values(names, kwargs_list), dtype=np.float64)
+    layout = _model.ColumnLayout()
+    descs = [_model.lens_desc(n, layout.add_profile("lens", i, names[i]), (profile_kwargs_list or [{}] * len(names))[i])
+             for i, n in enumerate(lens_model_list)]
+    arr = (_lib.LensDesc * max(1, len(descs)))(*descs)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    h = np.empty((4, x.size))
+    rc = lib().hm_lens_hessian(arr, len(descs), _p(row), _p(x), _p(y), x.size, _p(h))
+    assert rc == 0, rc
+    return tuple(h[k].reshape(x.shape) for k in range(4))
 
 
 def lens_vjp(lens_model_list, kwargs_list, x, y, vx, vy, profile_kwargs_list=None):
