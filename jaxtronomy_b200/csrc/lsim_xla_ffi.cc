@@ -74,6 +74,15 @@ static ffi::Error RayShootImpl(cudaStream_t stream, int64_t plan, int32_t what, 
                                stream));
 }
 
+// LensModel.hessian, diff=None (lens_model.py:384-414, single_plane.py:142-180); x, y: [N] shared or [B, N]
+static ffi::Error HessianImpl(cudaStream_t stream, int64_t plan, ffi::Buffer<ffi::F64> params, ffi::Buffer<ffi::F64> x,
+                              ffi::Buffer<ffi::F64> y, ffi::ResultBuffer<ffi::F64> out) {  // [B, 4, N]
+  const bool batched = x.dimensions().size() == 2;
+  const int64_t N = x.dimensions()[batched ? 1 : 0];
+  return Status(lsim_hessian(Plan(plan), params.typed_data(), params.dimensions()[0], x.typed_data(), y.typed_data(),
+                             N, batched ? 1 : 0, out->typed_data(), stream));
+}
+
 XLA_FFI_DEFINE_HANDLER_SYMBOL(LsimLogl, LoglImpl,
                               ffi::Ffi::Bind()
                                   .Ctx<ffi::PlatformStream<cudaStream_t>>()
@@ -110,6 +119,14 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(LsimRayShoot, RayShootImpl,
                                   .Arg<ffi::Buffer<ffi::F64>>()
                                   .Arg<ffi::Buffer<ffi::F64>>()
                                   .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(LsimHessian, HessianImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("plan")
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
                                   .Ret<ffi::Buffer<ffi::F64>>());
 #else
 // jax headers absent: nothing to build.  The symbol below lets a build script detect the empty shim.

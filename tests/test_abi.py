@@ -90,6 +90,7 @@ def test_null_arguments_are_rejected_without_a_gpu(lib):
     assert lib.lsim_workspace_bytes(None, 10) == 0
     assert lib.lsim_ray_shoot(None, None, 1, None, None, 1, 0, None, None, 0, None) == -1
     assert lib.lsim_logl(None, None, 1, 0, 0, None, None, None, None, 0, None) == -1
+    assert lib.lsim_hessian(None, None, 1, None, None, 1, 0, None, None) == -1
 
 
 def test_product_has_no_cpu_fallback():
@@ -125,5 +126,5 @@ def test_xla_ffi_shim_is_header_gated(tmp_path):
     h = C.CDLL(so)
     assert h.lsim_xla_ffi_unavailable() == 1
     text = open(src).read()
-    for handler in ("LsimLogl", "LsimLoglGrad", "LsimImage", "LsimRayShoot"):
+    for handler in ("LsimLogl", "LsimLoglGrad", "LsimImage", "LsimRayShoot", "LsimHessian"):
         assert "XLA_FFI_DEFINE_HANDLER_SYMBOL(%s" % handler in text
