@@ -229,6 +229,16 @@ int lsim_ray_shoot(const lsim_plan* plan, const double* params, int64_t B, const
 int lsim_hessian(const lsim_plan* plan, const double* params, int64_t B, const double* x, const double* y, int64_t N,
                  int coords_batched, double* out, void* stream);
 
+/* PositionLikelihood.source_position_likelihood for ONE LENSED_POSITION point-source model
+ * (Sampling/Likelihoods/position_likelihood.py:214-283, penalty :296-352; source position = mean of the ray-shot image
+ * positions, PointSource/Types/lensed_position.py:65-90), batched over B parameter sets; single plane, fp64 plans.
+ *   x, y            device [n_img] (shared) or [B,n_img] when coords_batched != 0: the image positions
+ *   sigma           image-plane position uncertainty (> 0);  hard_bound_rms < 0: no hard bound
+ *   logl            device [B]: minus the sum of the per-image penalties (overwritten) */
+int lsim_source_position_logl(const lsim_plan* plan, const double* params, int64_t B, const double* x, const double* y,
+                              int n_img, int coords_batched, double sigma, double hard_bound_rms, double* logl,
+                              void* stream);
+
 /* LightModel.surface_brightness / functions_split on arbitrary points (no lensing applied here).
  *   out        device [B, n_slots, N] */
 int lsim_surface_brightness(const lsim_plan* plan, const double* params, int64_t B, const double* x,

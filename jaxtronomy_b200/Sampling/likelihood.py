@@ -16,7 +16,10 @@ __all__ = ["LikelihoodModule"]
 
 class LikelihoodModule(object):
     def __init__(self, image_model, param_class, check_bounds=True, source_marg=False, linear_solver=True,
-                 prior_lens=None, prior_source=None, prior_lens_light=None, **unsupported):
+                 prior_lens=None, prior_source=None, prior_lens_light=None, image_position_uncertainty=0.005,
+                 astrometric_likelihood=False, image_position_likelihood=False, ra_image_list=None, dec_image_list=None,
+                 source_position_likelihood=None, source_position_tolerance=None, source_position_sigma=0.001,
+                 force_no_add_image=False, restrict_image_number=False, max_num_images=None, **unsupported):
         """
         :param image_model: ImageModel / ImageLinearFit / MultiLinear instance (the imaging likelihood)
         :param param_class: jaxtronomy_b200.Sampling.parameters.Param
@@ -24,9 +27,13 @@ class LikelihoodModule(object):
             (the reference forwards them to lenstronomy's PriorLikelihood, Sampling/likelihood.py:155-176, and adds
             its value to logL, :345-349): logL -= (value - mean)^2 / (2 sigma^2).  Evaluated on the columns of the
             `positions` matrix on the device; a prior on a fixed parameter is a constant.  lenstronomy is not under
-            /root/reference: the formula is restated (parity unpinned).  KDE / log-normal priors, the position,
+            /root/reference: the formula is restated (parity unpinned).  KDE / log-normal priors, the
             time-delay, flux-ratio, kinematic and tracer likelihoods are outside the scope: passing
             them raises.
+        :param image_position_uncertainty ... max_num_images: the reference's ``kwargs_position`` (likelihood.py:196-214),
+            forwarded to PositionLikelihood.  As in the reference the source-position penalty is ON by default when the
+            model has a LENSED_POSITION point source (position_likelihood.py:62-66).  ``astrometric_likelihood`` needs
+            ``kwargs_special`` (delta_x_image), which Param does not sample: raises.
         """
         for k, v in unsupported.items():
             if v:
@@ -52,6 +59,76 @@ class LikelihoodModule(object):
                 else:
                     raise ValueError("prior on unknown parameter %s of %s model %d" % (name, comp, index))
         self._prior_dev = None
+        # position likelihood (likelihood.py:286-288, 366-368)
+        if astrometric_likelihood:
+            raise ValueError("astrometric_likelihood needs kwargs_special, which is outside the scope of jaxtronomy_b200's "
+                             "Param; use PositionLikelihood.astrometric_likelihood on kwargs")
+        self._position_likelihood, self._pos_models, self._pos_plan, self._pos_dev = None, [], None, None
+        ps = getattr(image_model, "PointSource", None)
+        if ps is not None and len(ps.point_source_type_list) > 0:
+            from jaxtronomy_b200.Sampling.Likelihoods.position_likelihood import PositionLikelihood
+
+            pl = PositionLikelihood(ps, image_position_uncertainty=image_position_uncertainty,
+                                    image_position_likelihood=image_position_likelihood, ra_image_list=ra_image_list,
+                                    dec_image_list=dec_image_list, source_position_likelihood=source_position_likelihood,
+                                    source_position_tolerance=source_position_tolerance,
+                                    source_position_sigma=source_position_sigma, force_no_add_image=force_no_add_image,
+                                    restrict_image_number=restrict_image_number, max_num_images=max_num_images)
+            self._position_likelihood = pl
+            fn = self.param.column_source_fn()
+            for k, n in enumerate(fn.num_point_images):
+                src = [[fn("point_source", k, name, element=j) for j in range(n)] for name in ("ra_image", "dec_image")]
+                self._pos_models.append((ps.point_source_type_list[k], n, src))
+            if pl._source_position_likelihood and "LENSED_POSITION" in ps.point_source_type_list:
+                lm = ps._lens_model
+                self._pos_plan = _lib.Plan(self._n, lens_descs=lm.lens_descs(None, source_fn=fn), **lm.plan_kwargs())
+        elif source_position_likelihood or image_position_likelihood:
+            raise ValueError("position likelihoods need an image model with a point-source class")
+
+    def _image_positions(self, positions):
+        """Per point-source model: (ra [B, n], dec [B, n]) device tensors, columns of `positions` or fixed constants."""
+        import torch
+
+        if self._pos_dev is None or self._pos_dev[0][0][0].device != positions.device:
+            dev = []
+            for _, n, src in self._pos_models:
+                per = []
+                for lst in src:
+                    idx = torch.as_tensor([v if kind == "col" else 0 for kind, v in lst], dtype=torch.long,
+                                          device=positions.device)
+                    is_col = torch.as_tensor([kind == "col" for kind, _ in lst], device=positions.device)
+                    cst = torch.as_tensor([0.0 if kind == "col" else v for kind, v in lst], dtype=positions.dtype,
+                                          device=positions.device)
+                    per.append((idx, is_col, cst))
+                dev.append(per)
+            self._pos_dev = dev
+        out = []
+        for per in self._pos_dev:
+            out.append(tuple(torch.where(is_col, positions[:, idx], cst).contiguous() for idx, is_col, cst in per))
+        return out
+
+    def _position_logl(self, positions):
+        """PositionLikelihood.logL over the rows of `positions` (device tensor) -> [B] or None."""
+        pl = self._position_likelihood
+        if pl is None or not self._pos_models or not (self._pos_plan is not None or pl._image_position_likelihood):
+            return None
+        total = None
+        coords = self._image_positions(positions)
+        for k, (kind, n, _) in enumerate(self._pos_models):
+            ra, dec = coords[k]
+            if self._pos_plan is not None and kind == "LENSED_POSITION" and n > 0:
+                l = self._pos_plan.source_position_logl(positions, ra, dec, pl._source_position_sigma,
+                                                        pl._bound_source_position_tolerance)
+                total = l if total is None else total + l
+            if pl._image_position_likelihood:  # position_likelihood.py:214-247 on the columns themselves
+                import torch
+
+                m = min(len(pl._ra_image_list[k]), n)
+                ra0 = torch.as_tensor(pl._ra_image_list[k][:m], dtype=positions.dtype, device=positions.device)
+                dec0 = torch.as_tensor(pl._dec_image_list[k][:m], dtype=positions.dtype, device=positions.device)
+                l = -(((ra[:, :m] - ra0) ** 2 + (dec[:, :m] - dec0) ** 2) / pl._image_position_sigma**2 / 2).sum(dim=1)
+                total = l if total is None else total + l
+        return total
 
     def _prior(self, positions, want_grad=False):
         """Gaussian prior term of every row of `positions` (device tensor) [+ its gradient]."""
@@ -100,6 +177,9 @@ class LikelihoodModule(object):
             total = l if total is None else total + l
         if self._prior_cols or self._prior_const:
             total = total + self._prior(positions)
+        pos_l = self._position_logl(positions)
+        if pos_l is not None:
+            total = total + pos_l
         if self._check_bounds:
             if self._bounds_dev is None or self._bounds_dev[0].device != positions.device:
                 self._bounds_dev = (torch.as_tensor(self._lower_limit, device=positions.device),
@@ -121,6 +201,9 @@ class LikelihoodModule(object):
 
         if self._source_marg:
             raise ValueError("the gradient does not cover the source marginalisation constant")
+        pl = self._position_likelihood
+        if pl is not None and (self._pos_plan is not None or pl._image_position_likelihood):
+            raise ValueError("the gradient does not cover the position likelihood: pass source_position_likelihood=False")
         total, gtotal = None, None
         for plan in self._plans:
             l, g, _ = plan.logl_grad(positions, linear_solve=self._linear_solver)

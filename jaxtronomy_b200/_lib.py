@@ -82,7 +82,7 @@ SYMBOLS = [
     "lsim_plan_create", "lsim_plan_destroy", "lsim_ray_shoot", "lsim_surface_brightness", "lsim_workspace_bytes",
     "lsim_image", "lsim_resize_convolve", "lsim_logl", "lsim_abi_version", "lsim_strerror", "lsim_last_cuda_error", "lsim_launch_count",
     "lsim_measure_fp64_peak", "lsim_timing_enable", "lsim_timing_read", "lsim_pso_step", "lsim_psf_error_map",
-    "lsim_logl_grad", "lsim_logl_grad_workspace_bytes", "lsim_hessian",
+    "lsim_logl_grad", "lsim_logl_grad_workspace_bytes", "lsim_hessian", "lsim_source_position_logl",
 ]
 
 
@@ -105,6 +105,8 @@ def load():
     lib.lsim_ray_shoot.restype = i32
     lib.lsim_hessian.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp, vp]
     lib.lsim_hessian.restype = i32
+    lib.lsim_source_position_logl.argtypes = [vp, vp, i64, vp, vp, i32, i32, C.c_double, C.c_double, vp, vp]
+    lib.lsim_source_position_logl.restype = i32
     lib.lsim_surface_brightness.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp, vp]
     lib.lsim_surface_brightness.restype = i32
     lib.lsim_workspace_bytes.argtypes = [vp, i64]
@@ -357,6 +359,25 @@ class Plan:
         with torch.cuda.device(self.device):
             check(self._lib.lsim_hessian(self._handle, p.data_ptr(), B, xt.data_ptr(), yt.data_ptr(), N, batched,
                                          out.data_ptr(), self._stream()))
+        return out
+
+    def source_position_logl(self, params, x, y, sigma, hard_bound_rms=None):
+        """-> logL [B] of PositionLikelihood.source_position_likelihood for one LENSED_POSITION model
+        (lsim_source_position_logl); x, y: image positions [n_img] (shared) or [B, n_img]."""
+        torch = _torch()
+        p = self._params(params)
+        B = p.shape[0]
+        xt, yt = self._coords(x, B), self._coords(y, B)
+        if xt.shape != yt.shape or xt.ndim not in (1, 2):
+            raise LsimError("image positions must be [n_img] or [B, n_img], the same for x and y")
+        batched = 1 if (xt.ndim == 2) else 0
+        if batched and xt.shape[0] != B:
+            raise LsimError("batched image positions must be [B, n_img]")
+        out = torch.empty((B,), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.lsim_source_position_logl(
+                self._handle, p.data_ptr(), B, xt.data_ptr(), yt.data_ptr(), int(xt.shape[-1]), batched, float(sigma),
+                -1.0 if hard_bound_rms is None else float(hard_bound_rms), out.data_ptr(), self._stream()))
         return out
 
     def surface_brightness(self, params, x, y):

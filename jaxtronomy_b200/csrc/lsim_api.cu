@@ -190,6 +190,7 @@ int configure_kernels() {
   LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax)); \
   LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<NS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
   LSIM_CUDA(cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
+  LSIM_CUDA(cudaFuncSetAttribute(k_source_position, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
   LSIM_GRAD_ATTR(0)
   LSIM_GRAD_ATTR(1)
   LSIM_GRAD_ATTR(2)
@@ -517,6 +518,28 @@ int lsim_hessian(const lsim_plan* plan, const double* params, int64_t B, const d
   k_hessian<<<grid, kGradBlock, plan->hess_smem, st>>>(H, params, x, y, N, coords_batched, plan->hess_series,
                                                         plan->dev.ray.alpha_scaling, out);
   return after_launch("k_hessian");
+}
+
+int lsim_source_position_logl(const lsim_plan* plan, const double* params, int64_t B, const double* x, const double* y,
+                              int n_img, int coords_batched, double sigma, double hard_bound_rms, double* logl,
+                              void* stream) {
+  if (!plan || B < 0 || n_img < 0 || n_img > 1024 || !(sigma > 0.0)) return LSIM_E_INVALID;
+  if (!plan->hess_ok) return LSIM_E_UNSUPPORTED;
+  if (B == 0) return LSIM_OK;
+  if (!logl || (n_img > 0 && (!x || !y)) || (plan->dev.n_param_cols > 0 && !params)) return LSIM_E_INVALID;
+  const size_t smem = srcpos_smem_bytes(plan->n_hess_lens, plan->hess_series, n_img);
+  if (smem > kGradSmemMax) return LSIM_E_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_img == 0) {  // no images: the sum over images is empty
+    LSIM_CUDA(cudaMemsetAsync(logl, 0, (size_t)B * sizeof(double), st));
+    return LSIM_OK;
+  }
+  PlanDev H = plan->dev;
+  H.lens = plan->hess_lens;
+  H.n_lens = plan->n_hess_lens;
+  k_source_position<<<(unsigned)B, 32, smem, st>>>(H, params, x, y, n_img, coords_batched, plan->hess_series,
+                                                   plan->dev.ray.alpha_scaling, sigma, hard_bound_rms, logl);
+  return after_launch("k_source_position");
 }
 
 int lsim_surface_brightness(const lsim_plan* plan, const double* params, int64_t B, const double* x,

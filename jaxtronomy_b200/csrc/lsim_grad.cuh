@@ -893,6 +893,38 @@ LSIM_HD void lens_hessian_add(const GLens& L, const double* pool, int ix, int iy
   h[3] -= fy.d[iy];
 }
 
+// value and Hessian of one prepared profile from ONE dual-number evaluation: a += alpha, h += (f_xx, f_xy, f_yx, f_yy)
+LSIM_HD void lens_value_hessian_add(const GLens& L, const double* pool, int ix, int iy, double x, double y, double& ax,
+                                    double& ay, double (&h)[4]) {
+  LD fx, fy;
+  lens_eval_d(L, pool, x, y, fx, fy);
+  ax += fx.v;
+  ay += fy.v;
+  if (ix >= 0) {
+    h[0] -= fx.d[ix];
+    h[1] -= fx.d[iy];
+    h[2] -= fy.d[ix];
+    h[3] -= fy.d[iy];
+  }
+}
+
+// _compute_penalty, Sampling/Likelihoods/position_likelihood.py:296-352: h = Hessian at the image, (d0, d1) = mean
+// source position minus this image's source position.  A = 1 - h; Sigma_beta = (A^T Sigma_theta) A with
+// Sigma_theta = sigma^2 1 (the reference's matmul order); penalty = d^T adj(Sigma_beta) d / (2 det Sigma_beta), 1e15 where
+// det == 0; + 1e3 where |d|^2 > hard_bound_rms^2 (hard_bound_rms < 0: no bound).
+LSIM_HD double source_position_penalty(const double (&h)[4], double d0, double d1, double sigma, double hard_bound_rms) {
+  const double a00 = 1.0 - h[0], a01 = -h[1], a10 = -h[2], a11 = 1.0 - h[3];
+  const double s2 = sigma * sigma;
+  const double t00 = a00 * s2, t01 = a10 * s2, t10 = a01 * s2, t11 = a11 * s2;
+  const double sa = t00 * a00 + t01 * a10, sb = t00 * a01 + t01 * a11, sc = t10 * a00 + t11 * a10,
+               sd = t10 * a01 + t11 * a11;
+  const double det = sa * sd - sb * sc;
+  const double q = d0 * (sd * d0 - sb * d1) + d1 * (-sc * d0 + sa * d1);
+  double pen = (det == 0.0) ? 1e15 : q / (2.0 * det);
+  if (hard_bound_rms >= 0.0 && d0 * d0 + d1 * d1 > hard_bound_rms * hard_bound_rms) pen += 1e3;
+  return pen;
+}
+
 // ---- light ------------------------------------------------------------------------------------------------------
 using GD = Dual<kLightN>;
 

@@ -438,6 +438,72 @@ k_hessian(PlanDev P, const double* __restrict__ params, const double* __restrict
   }
 }
 
+// ---- k_source_position: PositionLikelihood.source_position_likelihood ------------------------------------------------
+// (Sampling/Likelihoods/position_likelihood.py:214-283 and _compute_penalty :296-352; LENSED_POSITION.source_position,
+// PointSource/Types/lensed_position.py:65-90.)  One warp per parameter set; a lane per image:
+//   beta_i = theta_i - alpha(theta_i),  H_i = Hessian(theta_i)      one dual-number evaluation gives both
+//   beta_avg = mean_i beta_i;  delta_i = beta_avg - beta_i
+//   A = 1 - H_i;  Sigma_beta = A^T (sigma^2 1) A;  penalty_i = delta^T adj(Sigma_beta) delta / (2 det Sigma_beta)
+//   (det == 0: 1e15;  |delta|^2 > hard_bound_rms^2: + 1e3);   logl = - sum_i penalty_i      (sums in image order)
+__host__ __device__ inline size_t srcpos_smem_bytes(int n_lens, int n_series, int n_img) {
+  return hess_smem_bytes(n_lens, n_series) + (size_t)7 * n_img * sizeof(double);
+}
+
+__global__ void __launch_bounds__(32)
+k_source_position(PlanDev P, const double* __restrict__ params, const double* __restrict__ x,
+                  const double* __restrict__ y, int n_img, int coords_batched, int n_series, double scale, double sigma,
+                  double hard_bound_rms, double* __restrict__ logl) {
+  using namespace ad;
+  extern __shared__ double smem[];
+  const int64_t b = blockIdx.x;
+  const double* row = params + b * P.n_param_cols;
+  GLens* L = reinterpret_cast<GLens*>(smem);
+  double* pool = reinterpret_cast<double*>(L + P.n_lens);
+  double* w = pool + (size_t)n_series * kGradPool;  // [7][n_img]: beta_x, beta_y, f_xx, f_xy, f_yx, f_yy, penalty
+  int* slot = reinterpret_cast<int*>(w + (size_t)7 * n_img);
+  stage_math_tables();
+  for (int i = threadIdx.x; i < P.n_lens; i += 32) {
+    int off = 0;
+    for (int j = 0; j < i; ++j) off += lens_grad_has_series(P.lens[j]) ? 1 : 0;
+    L[i].coef_off = off * kGradPool;
+    lens_prepare_hess(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries);
+    int ix, iy;
+    if (!lens_center_slots(P.lens[i], ix, iy)) ix = iy = -1;
+    slot[2 * i] = ix;
+    slot[2 * i + 1] = iy;
+  }
+  __syncthreads();
+  const double* xb = coords_batched ? x + b * n_img : x;
+  const double* yb = coords_batched ? y + b * n_img : y;
+  for (int i = threadIdx.x; i < n_img; i += 32) {
+    const double xx = xb[i], yy = yb[i];
+    double ax = 0.0, ay = 0.0, h[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int l = 0; l < P.n_lens; ++l)
+      lens_value_hessian_add(L[l], pool, slot[2 * l], slot[2 * l + 1], xx, yy, ax, ay, h);
+    w[i] = xx - ax * scale;
+    w[n_img + i] = yy - ay * scale;
+    for (int k = 0; k < 4; ++k) w[(2 + k) * n_img + i] = h[k] * scale;
+  }
+  __syncthreads();
+  double sx = 0.0, sy = 0.0;
+  for (int i = 0; i < n_img; ++i) {
+    sx += w[i];
+    sy += w[n_img + i];
+  }
+  const double mx = sx / n_img, my = sy / n_img;
+  for (int i = threadIdx.x; i < n_img; i += 32) {
+    const double h[4] = {w[2 * n_img + i], w[3 * n_img + i], w[4 * n_img + i], w[5 * n_img + i]};
+    const double pen = source_position_penalty(h, mx - w[i], my - w[n_img + i], sigma, hard_bound_rms);
+    w[6 * n_img + i] = pen;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n_img; ++i) s += w[6 * n_img + i];
+    logl[b] = -s;
+  }
+}
+
 // ---- k_grad_reduce ------------------------------------------------------------------------------------------------
 // One CTA per set: entry sums over the tiles (fixed order), then the entries of each parameter column.
 __global__ void __launch_bounds__(128)

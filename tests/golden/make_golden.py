@@ -612,7 +612,64 @@ def gen_hessians():
         print("skipped", c)
 
 
+def gen_position_likelihood():
+    """PositionLikelihood (Sampling/Likelihoods/position_likelihood.py) of the unmodified reference: source-position
+    penalty (with and without the hard bound), image-position likelihood, astrometric likelihood, their sum."""
+    from jaxtronomy.PointSource.point_source import PointSource
+    from jaxtronomy.Sampling.Likelihoods.position_likelihood import PositionLikelihood
+
+    st = Store()
+    kw_epl = dict(theta_E=1.1, gamma=2.0, e1=0.1, e2=-0.05, center_x=0.02, center_y=-0.01)
+    kw_shear = dict(gamma1=0.03, gamma2=-0.01, ra_0=0, dec_0=0)
+    quad = dict(ra_image=np.array([1.013, -0.734, 0.412, -0.551]), dec_image=np.array([0.402, -0.846, -1.002, 0.978]),
+                point_amp=np.array([30.0, 25.0, 18.0, 12.0]))
+    star = dict(ra_image=np.array([-1.21]), dec_image=np.array([1.07]), point_amp=np.array([40.0]))
+    double = dict(ra_image=np.array([0.93, -0.61]), dec_image=np.array([0.81, -0.52]), point_amp=np.array([9.0, 4.0]))
+    cases = [
+        ("quad", ["EPL", "SHEAR"], [kw_epl, kw_shear], ["LENSED_POSITION"], [quad], dict()),
+        ("quad_hard_bound", ["EPL", "SHEAR"], [kw_epl, kw_shear], ["LENSED_POSITION"], [quad],
+         dict(source_position_tolerance=0.05, source_position_sigma=0.003)),
+        ("quad_star_double", ["EPL", "SHEAR"], [kw_epl, kw_shear], ["LENSED_POSITION", "UNLENSED", "LENSED_POSITION"],
+         [quad, star, double], dict(source_position_sigma=0.002)),
+        ("quad_m1m3m4", ["EPL_MULTIPOLE_M1M3M4", "SHEAR", "SIS"],
+         [dict(kw_epl, a1_a=0.01, delta_phi_m1=0.3, a3_a=0.005, delta_phi_m3=-0.2, a4_a=0.01, delta_phi_m4=0.1), kw_shear,
+          dict(theta_E=0.1, center_x=0.9, center_y=-0.7)], ["LENSED_POSITION"], [quad], dict()),
+        ("quad_image_positions", ["EPL", "SHEAR"], [kw_epl, kw_shear], ["LENSED_POSITION"], [quad],
+         dict(image_position_likelihood=True, image_position_uncertainty=0.004,
+              ra_image_list=[[1.01, -0.73, 0.41, -0.55]], dec_image_list=[[0.40, -0.85, -1.00, 0.98]])),
+        # SIS, theta_E = 1, source at (0.1, 0): exact images (1.1, 0) and (-0.9, 0), perturbed by ~1e-3
+        ("sis_double_near", ["SIS"], [dict(theta_E=1.0, center_x=0.0, center_y=0.0)], ["LENSED_POSITION"],
+         [dict(ra_image=np.array([1.1008, -0.9003]), dec_image=np.array([0.0005, -0.0002]), point_amp=np.array([1.0, 1.0]))],
+         dict(source_position_tolerance=0.001)),
+        ("sis_double_near_bound_hit", ["SIS"], [dict(theta_E=1.0, center_x=0.0, center_y=0.0)], ["LENSED_POSITION"],
+         [dict(ra_image=np.array([1.1008, -0.9003]), dec_image=np.array([0.0005, -0.0002]), point_amp=np.array([1.0, 1.0]))],
+         dict(source_position_tolerance=0.0001)),
+        ("star_only", ["EPL", "SHEAR"], [kw_epl, kw_shear], ["UNLENSED"], [star], dict()),
+    ]
+    cp = lambda kws: [{k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()} for kw in kws]  # noqa: E731
+    for case, names, kw_lens, types, kw_ps, opts in cases:
+        lens = LensModel(names)
+        ps = PointSource(types, lens_model=lens)
+        pl = PositionLikelihood(ps, **opts)
+        outs = dict(logL=float(pl.logL(kw_lens, cp(kw_ps), {})))
+        if "LENSED_POSITION" in types:
+            outs["logL_source_position"] = float(pl.source_position_likelihood(
+                kw_lens, cp(kw_ps), opts.get("source_position_sigma", 0.001),
+                hard_bound_rms=opts.get("source_position_tolerance")))
+        st.add(case, dict(), outs, dict(lens_model_list=names, kwargs_lens=kw_lens, point_source_type_list=types,
+                                        kwargs_ps=[{k: np.asarray(v).tolist() for k, v in kw.items()} for kw in kw_ps],
+                                        options=opts))
+    # astrometric likelihood (static): kwargs_special offsets
+    special = dict(delta_x_image=[0.002, -0.001, 0.0005, 0.003], delta_y_image=[-0.0015, 0.0, 0.002, -0.0005])
+    st.add("astrometric", dict(), dict(logL=float(PositionLikelihood.astrometric_likelihood([quad], special, 0.004))),
+           dict(kwargs_special=special, sigma=0.004))
+    st.save("position_likelihood.npz")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["position_likelihood"]:
+        gen_position_likelihood()
+        sys.exit(0)
     if sys.argv[1:] == ["hessians"]:
         gen_hessians()
         sys.exit(0)
@@ -624,3 +681,4 @@ if __name__ == "__main__":
     gen_imsim()
     gen_point_sources()
     gen_hessians()
+    gen_position_likelihood()

@@ -250,7 +250,7 @@ def _make_jax():
     jax.custom_jvp = _CustomJvp
     jax.jvp = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("jvp not available in refshim"))
     jax.grad = jax.jvp
-    jax.vmap = lambda f, *a, **k: f
+    jax.vmap = _vmap
     jax.config = _Config()
     jax.debug = types.SimpleNamespace(print=lambda *a, **k: None)
     jax.devices = lambda *a: [object()]
@@ -519,6 +519,20 @@ def _make_lenstronomy():
 
 
 _installed = False
+
+
+def _vmap(f, in_axes=0, out_axes=0):
+    """jax.vmap for positional arguments: a Python loop over the mapped axis (in_axes: int or a tuple with None for
+    broadcast arguments); outputs (array or tuple of arrays) are stacked along axis 0."""
+    def mapped(*args):
+        axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+        n = next(np.shape(a)[ax] for a, ax in zip(args, axes) if ax is not None)
+        outs = [f(*[a if ax is None else np.take(np.asarray(a), i, axis=ax) for a, ax in zip(args, axes)])
+                for i in range(n)]
+        if isinstance(outs[0], tuple):
+            return tuple(_wrap(np.stack([np.asarray(o[j]) for o in outs])) for j in range(len(outs[0])))
+        return _wrap(np.stack([np.asarray(o) for o in outs]))
+    return mapped
 
 
 def install():

@@ -151,6 +151,47 @@ int hm_lens_hessian(const lsim_lens_desc* lens, int n_lens, const double* row, c
   return 0;
 }
 
+// k_source_position's per-set arithmetic on the host (same helper functions, same order of the sums).
+int hm_source_position_logl(const lsim_lens_desc* lens, int n_lens, const double* row, const double* x, const double* y,
+                            int n_img, double scale, double sigma, double hard_bound_rms, double* logl) {
+  std::vector<lsim_lens_desc> gl((size_t)4 * (n_lens > 0 ? n_lens : 1));
+  const int ngl = ad::expand_grad_lens(lens, n_lens, gl.data(), (int)gl.size());
+  if (ngl < 0) return -2;
+  std::vector<ad::GLens> L(ngl > 0 ? ngl : 1);
+  std::vector<int> slot(2 * (size_t)(ngl > 0 ? ngl : 1));
+  std::vector<double> pool((size_t)(ngl + 1) * ad::kGradPool);
+  int off = 0;
+  for (int i = 0; i < ngl; ++i) {
+    L[i].coef_off = off * ad::kGradPool;
+    double* F = pool.data() + (size_t)off * ad::kGradPool;
+    if (!ad::lens_prepare_hess(gl[i], row, L[i], F, F + kMaxSeries)) return -2;
+    if (ad::lens_grad_has_series(gl[i])) ++off;
+    if (!ad::lens_center_slots(gl[i], slot[2 * i], slot[2 * i + 1])) slot[2 * i] = slot[2 * i + 1] = -1;
+  }
+  std::vector<double> w((size_t)6 * n_img);
+  for (int i = 0; i < n_img; ++i) {
+    double ax = 0.0, ay = 0.0, h[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int l = 0; l < ngl; ++l)
+      ad::lens_value_hessian_add(L[l], pool.data(), slot[2 * l], slot[2 * l + 1], x[i], y[i], ax, ay, h);
+    w[i] = x[i] - ax * scale;
+    w[n_img + i] = y[i] - ay * scale;
+    for (int k = 0; k < 4; ++k) w[(2 + k) * n_img + i] = h[k] * scale;
+  }
+  double sx = 0.0, sy = 0.0;
+  for (int i = 0; i < n_img; ++i) {
+    sx += w[i];
+    sy += w[n_img + i];
+  }
+  const double mx = sx / n_img, my = sy / n_img;
+  double s = 0.0;
+  for (int i = 0; i < n_img; ++i) {
+    const double h[4] = {w[2 * n_img + i], w[3 * n_img + i], w[4 * n_img + i], w[5 * n_img + i]};
+    s += ad::source_position_penalty(h, mx - w[i], my - w[n_img + i], sigma, hard_bound_rms);
+  }
+  *logl = -s;
+  return 0;
+}
+
 // Hand-derived fast path of the gradient kernel: g [N][n_lens][6] = d(vx alpha_x + vy alpha_y)/d(parameter k).
 int hm_lens_vjp(const lsim_lens_desc* lens, int n_lens, const double* row, const double* x, const double* y, int64_t N,
                 const double* vx, const double* vy, double* ax, double* ay, double* g) {

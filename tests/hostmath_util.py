@@ -45,6 +45,8 @@ def lib():
         h.hm_lens_vjp.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp]
         h.hm_eplm_vjp.argtypes = [C.POINTER(_lib.LensDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp]
         h.hm_lens_hessian.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int64, _dp]
+        h.hm_source_position_logl.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int, C.c_double,
+                                              C.c_double, C.c_double, _dp]
         _h = h
     return _h
 
@@ -148,6 +150,23 @@ def lens_hessian(lens_model_list, kwargs_list, x, y, profile_kwargs_list=None):
     rc = lib().hm_lens_hessian(arr, len(descs), _p(row), _p(x), _p(y), x.size, _p(h))
     assert rc == 0, rc
     return tuple(h[k].reshape(x.shape) for k in range(4))
+
+
+def source_position_logl(lens_model_list, kwargs_list, ra, dec, sigma, hard_bound_rms=None, profile_kwargs_list=None):
+    """k_source_position's per-set arithmetic on the host -> logL (float)."""
+    names = [_model.LENS_PARAM_NAMES[n] for n in lens_model_list]
+    row = np.asarray(_model.gather_values(names, kwargs_list), dtype=np.float64)
+    layout = _model.ColumnLayout()
+    descs = [_model.lens_desc(n, layout.add_profile("lens", i, names[i]), (profile_kwargs_list or [{}] * len(names))[i])
+             for i, n in enumerate(lens_model_list)]
+    arr = (_lib.LensDesc * max(1, len(descs)))(*descs)
+    ra = np.ascontiguousarray(ra, dtype=np.float64)
+    dec = np.ascontiguousarray(dec, dtype=np.float64)
+    out = np.zeros(1)
+    rc = lib().hm_source_position_logl(arr, len(descs), _p(row), _p(ra), _p(dec), ra.size, 1.0, float(sigma),
+                                       -1.0 if hard_bound_rms is None else float(hard_bound_rms), _p(out))
+    assert rc == 0, rc
+    return float(out[0])
 
 
 def lens_vjp(lens_model_list, kwargs_list, x, y, vx, vy, profile_kwargs_list=None):

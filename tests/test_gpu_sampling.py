@@ -178,7 +178,9 @@ def test_likelihood_module_with_point_sources():
     kps = [{k: np.asarray(v, dtype=float) for k, v in kw.items()} for kw in c.meta["kwargs_ps"]]
     param = Param(km, kwargs_fixed_lens=[{}, {"ra_0": 0.0, "dec_0": 0.0}], num_point_source_list=[4, 1],
                   kwargs_fixed_ps=[{}, {"ra_image": kps[1]["ra_image"], "dec_image": kps[1]["dec_image"]}])
-    like = LikelihoodModule(lin, param)
+    # imaging likelihood alone (the reference turns the source-position penalty on by default for LENSED_POSITION
+    # models, position_likelihood.py:62-66; that term is covered by tests/test_gpu_zposition.py)
+    like = LikelihoodModule(lin, param, source_position_likelihood=False)
     kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
     x0 = param.kwargs2args(kl, ks, kll, kwargs_ps=kps)
     assert abs(like.logL(x0) - float(c.out["logL_linear"])) <= 1e-9 * abs(float(c.out["logL_linear"]))
