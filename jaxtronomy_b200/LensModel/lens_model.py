@@ -243,3 +243,18 @@ class LensModel(object):
         f_xx, f_xy, f_yx, f_yy = self.hessian(x, y, kwargs, k=k, diff=diff, diff_method=diff_method)
         det_A = (1 - f_xx) * (1 - f_yy) - f_xy * f_yx
         return 1.0 / det_A
+
+    def flexion(self, x, y, kwargs, k=None, diff=0.0001, hessian_diff=False):
+        """Third derivatives (f_xxx, f_xxy, f_xyy, f_yyy) as central differences of the Hessian over ``diff``,
+        lens_model.py:529-570; ``hessian_diff=True`` also differences the Hessian itself (step diff / 4)."""
+        x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
+        hd = diff / 4 if hessian_diff else None
+        f_xx_dx, f_xy_dx, f_yx_dx, f_yy_dx = self.hessian(x + diff / 2, y, kwargs, k=k, diff=hd)
+        f_xx_dy, f_xy_dy, f_yx_dy, f_yy_dy = self.hessian(x, y + diff / 2, kwargs, k=k, diff=hd)
+        f_xx_dx_, f_xy_dx_, f_yx_dx_, f_yy_dx_ = self.hessian(x - diff / 2, y, kwargs, k=k, diff=hd)
+        f_xx_dy_, f_xy_dy_, f_yx_dy_, f_yy_dy_ = self.hessian(x, y - diff / 2, kwargs, k=k, diff=hd)
+        f_xxx = (f_xx_dx - f_xx_dx_) / diff
+        f_xxy = (f_xx_dy - f_xx_dy_) / diff
+        f_xyy = (f_xy_dy - f_xy_dy_) / diff
+        f_yyy = (f_yy_dy - f_yy_dy_) / diff
+        return f_xxx, f_xxy, f_xyy, f_yyy

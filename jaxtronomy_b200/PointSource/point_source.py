@@ -63,8 +63,23 @@ class PointSource(object):
         return xs, ys
 
     def source_position(self, kwargs_ps, kwargs_lens=None):
-        raise ValueError("source positions need ray shooting of the image positions: use "
-                         "LensModel.ray_shooting(ra_image, dec_image, kwargs_lens)")
+        """Intrinsic source positions, point_source.py:188-202: LENSED_POSITION = mean of the ray-shot image positions
+        (Types/lensed_position.py:65-90, one `lsim_ray_shoot` launch per model), UNLENSED = the positions themselves
+        (Types/unlensed.py).  -> (list of x_source, list of y_source)"""
+        xs, ys = [], []
+        for i, model in enumerate(self.point_source_type_list):
+            ra = np.atleast_1d(np.asarray(kwargs_ps[i]["ra_image"], dtype=float))
+            dec = np.atleast_1d(np.asarray(kwargs_ps[i]["dec_image"], dtype=float))
+            if model == "LENSED_POSITION":
+                if self._lens_model is None:
+                    raise ValueError("LENSED_POSITION source positions need the lens model (lens_model=...)")
+                bx, by = self._lens_model.ray_shooting(ra, dec, kwargs_lens)
+                xs.append(np.mean(bx, axis=-1))
+                ys.append(np.mean(by, axis=-1))
+            else:
+                xs.append(ra)
+                ys.append(dec)
+        return xs, ys
 
     def image_amplitude(self, kwargs_ps, kwargs_lens=None, k=None):
         """point_source.py:304-326"""

@@ -607,6 +607,11 @@ def gen_hessians():
         st.add("model_diff_%s" % method, dict(x=x, y=y),
                dict(zip(("f_xx", "f_xy", "f_yx", "f_yy"), (np.asarray(a) for a in h))),
                dict(lens_model_list=names, kwargs=kw, k=None, diff=1e-4, diff_method=method))
+    for hd in (False, True):
+        f = lm.flexion(x, y, kw, diff=1e-4, hessian_diff=hd)
+        st.add("model_flexion_%d" % hd, dict(x=x, y=y),
+               dict(zip(("f_xxx", "f_xxy", "f_xyy", "f_yyy"), (np.asarray(a) for a in f))),
+               dict(lens_model_list=names, kwargs=kw, diff=1e-4, hessian_diff=hd))
     st.save("hessians.npz")
     for c in skipped:
         print("skipped", c)
@@ -656,6 +661,9 @@ def gen_position_likelihood():
             outs["logL_source_position"] = float(pl.source_position_likelihood(
                 kw_lens, cp(kw_ps), opts.get("source_position_sigma", 0.001),
                 hard_bound_rms=opts.get("source_position_tolerance")))
+        sx, sy = ps.source_position(cp(kw_ps), kw_lens)
+        for i in range(len(types)):
+            outs["x_source_%d" % i], outs["y_source_%d" % i] = np.asarray(sx[i], dtype=float), np.asarray(sy[i], dtype=float)
         st.add(case, dict(), outs, dict(lens_model_list=names, kwargs_lens=kw_lens, point_source_type_list=types,
                                         kwargs_ps=[{k: np.asarray(v).tolist() for k, v in kw.items()} for kw in kw_ps],
                                         options=opts))

@@ -23,6 +23,7 @@ from tests.golden_io import load
 HESSIANS = load("hessians.npz")
 PROFILE_CASES = [n for n, c in HESSIANS.items() if "profile" in c.meta]
 MODEL_CASES = [n for n in HESSIANS if n.startswith("model_k")]
+FLEXION_CASES = [n for n in HESSIANS if n.startswith("model_flexion")]
 KEYS = ("f_xx", "f_xy", "f_yx", "f_yy")
 CLAMP_RADIUS = 1e-3
 NIE_ATOL = 2e-2  # of the fixture's scale; reference forward-difference noise, see above (worst case e = 0.99)

@@ -91,6 +91,7 @@ def test_null_arguments_are_rejected_without_a_gpu(lib):
     assert lib.lsim_ray_shoot(None, None, 1, None, None, 1, 0, None, None, 0, None) == -1
     assert lib.lsim_logl(None, None, 1, 0, 0, None, None, None, None, 0, None) == -1
     assert lib.lsim_hessian(None, None, 1, None, None, 1, 0, None, None) == -1
+    assert lib.lsim_source_position_logl(None, None, 1, None, None, 4, 0, 0.001, -1.0, None, None) == -1
 
 
 def test_product_has_no_cpu_fallback():

@@ -5,7 +5,7 @@ two reference facts behind them (NIE forward difference, core clamps): tests/hes
 import numpy as np
 import pytest
 
-from tests.hessian_cases import HESSIANS, KEYS, MODEL_CASES, PROFILE_CASES, check_profile, keep_mask, profile_case
+from tests.hessian_cases import FLEXION_CASES, HESSIANS, KEYS, MODEL_CASES, PROFILE_CASES, check_profile, keep_mask, profile_case
 
 pytestmark = pytest.mark.gpu
 
@@ -83,6 +83,26 @@ def test_differential_hessian(method):
         assert np.max(np.abs(g - c.out[q])[keep]) <= tol, (method, q)
     with pytest.raises(ValueError):
         lm.hessian(x, y, kw, diff=1e-4, diff_method="circle")
+
+
+@pytest.mark.parametrize("name", FLEXION_CASES)
+def test_flexion(name):
+    """lens_model.py:529-570: central differences of the Hessian over diff = 1e-4 (and of alpha over diff / 4 with
+    hessian_diff).  The stencil divides the Hessian's rounding by diff (and alpha's by diff^2 / 4 with hessian_diff):
+    the bar is 1e-10 of the Hessian scale / diff, resp. 1e-10 |alpha| / (diff^2 / 4)."""
+    c = HESSIANS[name]
+    names, kw, diff = c.meta["lens_model_list"], c.meta["kwargs"], c.meta["diff"]
+    x, y = c.inp["x"], c.inp["y"]
+    keep = keep_mask(x, y, kw)
+    lm = _LensModel()(names)
+    got = lm.flexion(x, y, kw, diff=diff, hessian_diff=c.meta["hessian_diff"])
+    h = lm.hessian(x, y, kw)
+    ax, ay = lm.alpha(x, y, kw)
+    hs = max(np.max(np.abs(a[keep])) for a in h)
+    tol = 1e-10 * (max(np.max(np.abs(ax[keep])), np.max(np.abs(ay[keep]))) / (diff * diff / 4)
+                   if c.meta["hessian_diff"] else hs / diff)
+    for g, q in zip(got, ("f_xxx", "f_xxy", "f_xyy", "f_yyy")):
+        assert np.max(np.abs(g - c.out[q])[keep]) <= tol, (name, q, np.max(np.abs(g - c.out[q])[keep]), tol)
 
 
 def test_batched_parameter_sets_torch_io_and_oracle_difference():

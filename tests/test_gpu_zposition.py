@@ -34,6 +34,20 @@ def test_position_likelihood_matches_the_reference(name):
         assert abs(got - want) <= 1e-10 * conditioning(c) * abs(want), (name, got, want)
 
 
+@pytest.mark.parametrize("name", [n for n in POS if n != "astrometric"])
+def test_point_source_source_position(name):
+    """PointSource.source_position (point_source.py:188-202): mean of the ray-shot images / the positions themselves."""
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+    from jaxtronomy_b200.PointSource.point_source import PointSource
+
+    c = POS[name]
+    ps = PointSource(c.meta["point_source_type_list"], lens_model=LensModel(c.meta["lens_model_list"]))
+    xs, ys = ps.source_position(c.meta["kwargs_ps"], c.meta["kwargs_lens"])
+    for i in range(len(xs)):
+        np.testing.assert_allclose(xs[i], c.out["x_source_%d" % i], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(ys[i], c.out["y_source_%d" % i], rtol=1e-10, atol=1e-12)
+
+
 def test_astrometric_likelihood_and_scope():
     from jaxtronomy_b200.Sampling.Likelihoods.position_likelihood import PositionLikelihood
 
