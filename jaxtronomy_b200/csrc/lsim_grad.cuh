@@ -871,9 +871,51 @@ LSIM_HD bool lens_center_slots(const lsim_lens_desc& d, int& ix, int& iy) {
   }
 }
 
-// lens_prepare_d with EVERY parameter carried as an independent variable (a fixed centre still needs its tangent):
-// the descriptor is re-pointed at a private row that holds the resolved parameter values.
-LSIM_HD bool lens_prepare_hess(const lsim_lens_desc& d, const double* row, GLens& L, double* F, double* dF) {
+// EPL family on the Hessian path: closed form from the FORWARD kernel's deflection.  Profiles/epl.py:398-435
+// (Tessore & Metcalf eq. 2 and 17, corrigendum): kappa = (2 - t)/2 (b/R)^t and, with alpha = alpha_x + i alpha_y and
+// u = e^{i phi} of the centred position in the SKY frame (the reference forms the same expression in the major-axis
+// frame and rotates the shear by 2 phi_G, :224-232 -- identical up to rounding),
+//   gamma_1 + i gamma_2 = (1 - t) alpha u / r - kappa u^2;   f_xx = kappa + gamma_1, f_yy = kappa - gamma_1, f_xy = gamma_2.
+// The prepared block is the forward path's LensC (lens_prepare / epl_eval1 of lsim_profiles.cuh), stored inside the
+// GLens slot, so the deflection is bit-identical to lsim_ray_shoot's and costs one nmax-term series per point instead
+// of the 100-term Dual<6> evaluation.
+constexpr int kHessLensEPL = 66;  // GLens.type of an EPL-family profile prepared for the Hessian path
+static_assert(sizeof(LensC) <= sizeof(GLens) - 16, "LensC must fit into the GLens payload");
+LSIM_HD LensC& hess_forward(GLens& L) { return *reinterpret_cast<LensC*>(L.c); }
+LSIM_HD const LensC& hess_forward(const GLens& L) { return *reinterpret_cast<const LensC*>(L.c); }
+
+LSIM_HD void epl_value_hessian(const LensC& C, const double* coef, double x, double y, double& ax, double& ay,
+                               double (&h)[4]) {
+  const double xs = x - C.c[0], ys = y - C.c[1];
+  epl_eval1(C, coef, xs, ys, ax, ay);
+  const double cph = C.c[2], sph = C.c[3], q = C.c[4], t = -2.0 * C.c[6];
+  const double xr = fma(ys, sph, xs * cph), c = fma(ys, cph, -(xs * sph)), a = q * xr;
+  const double R2c = max_nan(fma(c, c, a * a), 1e-16);  // R = max(R, 1e-8), epl.py:411
+  double kappa = (2.0 - t) / 2.0 * exp2_fin(fma(C.c[6], log2_pos(R2c), C.c[7]));
+  kappa = nan_to_num(kappa, 1e10, -1e10);
+  const double r = sqrt(fma(ys, ys, xs * xs));
+  const double ux = xs / r, uy = ys / r;
+  const double u2r = ux * ux * 2.0 - 1.0, u2i = uy * ux * 2.0;
+  double g1 = (1.0 - t) * (ax * ux - ay * uy) / r - kappa * u2r;
+  double g2 = (1.0 - t) * (ay * ux + ax * uy) / r - kappa * u2i;
+  g1 = nan_to_num(g1, 1e10, -1e10);
+  g2 = nan_to_num(g2, 1e10, -1e10);
+  h[0] = kappa + g1;
+  h[1] = g2;
+  h[2] = g2;
+  h[3] = kappa - g1;
+}
+
+// Preparation for the Hessian path.  EPL family: the forward block (above).  Everything else: lens_prepare_d with
+// EVERY parameter carried as an independent variable (a fixed centre still needs its tangent) -- the descriptor is
+// re-pointed at a private row that holds the resolved parameter values.
+LSIM_HD bool lens_prepare_hess(const lsim_lens_desc& d, const double* row, GLens& L, double* F, double* dF,
+                               double series_tol) {
+  if (lens_grad_has_series(d)) {
+    lens_prepare(d, row, hess_forward(L), F, series_tol);
+    L.type = kHessLensEPL;
+    return true;
+  }
   lsim_lens_desc dd = d;
   double r2[LSIM_MAX_PARAMS];
   for (int k = 0; k < LSIM_MAX_PARAMS; ++k) {
@@ -885,6 +927,12 @@ LSIM_HD bool lens_prepare_hess(const lsim_lens_desc& d, const double* row, GLens
 
 // h[0..3] += (f_xx, f_xy, f_yx, f_yy) of one prepared profile
 LSIM_HD void lens_hessian_add(const GLens& L, const double* pool, int ix, int iy, double x, double y, double (&h)[4]) {
+  if (L.type == kHessLensEPL) {
+    double ax, ay, e[4];
+    epl_value_hessian(hess_forward(L), pool + L.coef_off, x, y, ax, ay, e);
+    for (int k = 0; k < 4; ++k) h[k] += e[k];
+    return;
+  }
   LD fx, fy;
   lens_eval_d(L, pool, x, y, fx, fy);
   h[0] -= fx.d[ix];
@@ -896,6 +944,14 @@ LSIM_HD void lens_hessian_add(const GLens& L, const double* pool, int ix, int iy
 // value and Hessian of one prepared profile from ONE dual-number evaluation: a += alpha, h += (f_xx, f_xy, f_yx, f_yy)
 LSIM_HD void lens_value_hessian_add(const GLens& L, const double* pool, int ix, int iy, double x, double y, double& ax,
                                     double& ay, double (&h)[4]) {
+  if (L.type == kHessLensEPL) {
+    double ex, ey, e[4];
+    epl_value_hessian(hess_forward(L), pool + L.coef_off, x, y, ex, ey, e);
+    ax += ex;
+    ay += ey;
+    for (int k = 0; k < 4; ++k) h[k] += e[k];
+    return;
+  }
   LD fx, fy;
   lens_eval_d(L, pool, x, y, fx, fy);
   ax += fx.v;

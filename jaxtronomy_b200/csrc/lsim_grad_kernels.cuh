@@ -416,7 +416,8 @@ k_hessian(PlanDev P, const double* __restrict__ params, const double* __restrict
     int off = 0;
     for (int j = 0; j < i; ++j) off += lens_grad_has_series(P.lens[j]) ? 1 : 0;
     L[i].coef_off = off * kGradPool;
-    lens_prepare_hess(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries);
+    lens_prepare_hess(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries,
+                      P.series_tol);
     int ix, iy;
     if (!lens_center_slots(P.lens[i], ix, iy)) ix = iy = -1;
     slot[2 * i] = ix;
@@ -466,7 +467,8 @@ k_source_position(PlanDev P, const double* __restrict__ params, const double* __
     int off = 0;
     for (int j = 0; j < i; ++j) off += lens_grad_has_series(P.lens[j]) ? 1 : 0;
     L[i].coef_off = off * kGradPool;
-    lens_prepare_hess(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries);
+    lens_prepare_hess(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries,
+                      P.series_tol);
     int ix, iy;
     if (!lens_center_slots(P.lens[i], ix, iy)) ix = iy = -1;
     slot[2 * i] = ix;

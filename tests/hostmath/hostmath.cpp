@@ -138,7 +138,7 @@ int hm_lens_hessian(const lsim_lens_desc* lens, int n_lens, const double* row, c
   for (int i = 0; i < ngl; ++i) {
     L[i].coef_off = off * ad::kGradPool;
     double* F = pool.data() + (size_t)off * ad::kGradPool;
-    if (!ad::lens_prepare_hess(gl[i], row, L[i], F, F + kMaxSeries)) return -2;
+    if (!ad::lens_prepare_hess(gl[i], row, L[i], F, F + kMaxSeries, 1e-14)) return -2;
     if (ad::lens_grad_has_series(gl[i])) ++off;
     if (!ad::lens_center_slots(gl[i], slot[2 * i], slot[2 * i + 1])) slot[2 * i] = slot[2 * i + 1] = -1;
   }
@@ -164,7 +164,7 @@ int hm_source_position_logl(const lsim_lens_desc* lens, int n_lens, const double
   for (int i = 0; i < ngl; ++i) {
     L[i].coef_off = off * ad::kGradPool;
     double* F = pool.data() + (size_t)off * ad::kGradPool;
-    if (!ad::lens_prepare_hess(gl[i], row, L[i], F, F + kMaxSeries)) return -2;
+    if (!ad::lens_prepare_hess(gl[i], row, L[i], F, F + kMaxSeries, 1e-14)) return -2;
     if (ad::lens_grad_has_series(gl[i])) ++off;
     if (!ad::lens_center_slots(gl[i], slot[2 * i], slot[2 * i + 1])) slot[2 * i] = slot[2 * i + 1] = -1;
   }
