@@ -390,6 +390,57 @@ def test_likelihood_module_gaussian_priors_value_and_gradient():
         LikelihoodModule(NoImage(), param, time_delay_likelihood=True)
 
 
+def test_likelihood_module_image_position_term_on_the_columns():
+    """Position-likelihood wiring of LikelihoodModule that needs no GPU: the image positions are gathered from the
+    columns of `positions` (sampled model) or from fixed constants, and the image-position term
+    (position_likelihood.py:214-247) is formed on them; checked against the oracle row by row.  The source-position
+    term needs the kernel (tests/test_gpu_zposition.py)."""
+    import torch
+
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+    from jaxtronomy_b200.PointSource.point_source import PointSource
+    from jaxtronomy_b200.Sampling.likelihood import LikelihoodModule
+    from jaxtronomy_b200.Sampling.parameters import Param
+    from oracle import position_likelihood as opl
+
+    lens = LensModel(["SIS"])
+
+    class NoImage:
+        def sampler_plans(self, *a, **k):
+            return []
+
+    img = NoImage()
+    img.PointSource = PointSource(["LENSED_POSITION", "UNLENSED"], lens_model=lens)
+    km = dict(lens_model_list=["SIS"], point_source_model_list=["LENSED_POSITION", "UNLENSED"])
+    star = dict(ra_image=np.array([-1.21]), dec_image=np.array([1.07]))
+    param = Param(km, num_point_source_list=[3, 1], kwargs_fixed_ps=[{}, star])
+    ra_data = [[1.0, -0.7, 0.4, 9.9], [-1.2]]       # one measured position more than the model has images: truncated
+    dec_data = [[0.4, -0.8, -1.0, 9.9], [1.1]]
+    like = LikelihoodModule(img, param, source_position_likelihood=False, image_position_likelihood=True,
+                            image_position_uncertainty=0.01, ra_image_list=ra_data, dec_image_list=dec_data)
+    n = param.num_param()[0]
+    rng = np.random.default_rng(2)
+    pos = rng.normal(0.5, 0.4, (6, n))
+    got = like._position_logl(torch.as_tensor(pos)).numpy()
+    for b in range(6):
+        kw = param.args2kwargs(pos[b])
+        want = opl.image_position_likelihood(kw["kwargs_ps"], ra_data, dec_data, 0.01)
+        assert abs(got[b] - want) <= 1e-12 * abs(want)
+    # the kwargs-level class gives the same number, and counts the data like the reference (num_data, :285-296)
+    pl = like._position_likelihood
+    kw = param.args2kwargs(pos[0])
+    assert abs(pl.image_position_likelihood(kw["kwargs_ps"], None, 0.01) - got[0]) <= 1e-12 * abs(got[0])
+    assert pl.num_data == 10
+    # no position term at all -> None; the reference's unsupported switches raise
+    assert LikelihoodModule(img, param, source_position_likelihood=False)._position_logl(torch.as_tensor(pos)) is None
+    with pytest.raises(ValueError):
+        LikelihoodModule(img, param, source_position_likelihood=False, force_no_add_image=True)
+    with pytest.raises(ValueError):
+        LikelihoodModule(img, param, source_position_likelihood=False, astrometric_likelihood=True)
+    with pytest.raises(ValueError):
+        LikelihoodModule(NoImage(), Param(dict(lens_model_list=["SIS"])), image_position_likelihood=True)
+
+
 def test_device_ensemble_sampler_samples_a_correlated_gaussian():
     """The stretch-move sampler (the emcee call behind Sampler.mcmc_emcee) on CPU tensors: a 3-d correlated Gaussian."""
     import torch
