@@ -96,6 +96,8 @@ class PositionLikelihood(object):
         if len(kwargs_ps) < 1:
             return 0
         lm = self._lensModel
+        if lm is None:
+            raise ValueError("the source-position likelihood needs the lens model: build PointSource with lens_model=...")
         values = _model.gather_values(lm.param_name_list, kwargs_lens, "lens")
         mat, B, batched = _model.pack_columns(values)
         plan = lm._plan(None)

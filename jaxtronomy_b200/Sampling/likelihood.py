@@ -80,7 +80,12 @@ class LikelihoodModule(object):
                 src = [[fn("point_source", k, name, element=j) for j in range(n)] for name in ("ra_image", "dec_image")]
                 self._pos_models.append((ps.point_source_type_list[k], n, src))
             if pl._source_position_likelihood and "LENSED_POSITION" in ps.point_source_type_list:
-                lm = ps._lens_model
+                # the reference's class_creator always hands the lens model to PointSource; a PointSource built without
+                # one falls back to the image model's
+                lm = ps._lens_model if ps._lens_model is not None else getattr(image_model, "LensModel", None)
+                if lm is None:
+                    raise ValueError("the source-position likelihood needs the lens model: build PointSource with "
+                                     "lens_model=..., or pass source_position_likelihood=False")
                 self._pos_plan = _lib.Plan(self._n, lens_descs=lm.lens_descs(None, source_fn=fn), **lm.plan_kwargs())
         elif source_position_likelihood or image_position_likelihood:
             raise ValueError("position likelihoods need an image model with a point-source class")

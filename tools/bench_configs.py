@@ -186,7 +186,7 @@ def c1(mcmc=False):
 
     def make(image):
         return ImageLinearFit(ImageData(**dict(kd, image_data=image)), psf, lens, LightModel(km["source_light_model_list"]),
-                              LightModel(km["lens_light_model_list"]), point_source_class=PointSource(["LENSED_POSITION"]),
+                              LightModel(km["lens_light_model_list"]), point_source_class=PointSource(["LENSED_POSITION"], lens_model=lens),
                               kwargs_numerics=dict(supersampling_factor=1))
 
     truth = make(np.zeros((100, 100))).image(kl, ks, kll, kps)
