@@ -141,3 +141,30 @@ def hessian_differential(lens_model_list, x, y, kwargs, k=None, profile_kwargs_l
 
     (f_xx, f_yx), (f_xy, f_yy) = d(0), d(1)
     return f_xx, f_xy, f_yx, f_yy
+
+
+def hessian(lens_model_list, x, y, kwargs, k=None, profile_kwargs_list=None, alpha_scaling=1):
+    """SinglePlane.hessian, single_plane.py:142-180: sum of the profiles' Hessians (an int ``k`` returns that profile's
+    own, unscaled).  Profiles whose closed form is restated (EPL family, SIS, SHEAR, CONVERGENCE) use it; the others fall
+    back to `hessian_differential` of that profile alone."""
+    x = np.asarray(x, dtype=float)
+    y = np.asarray(y, dtype=float)
+    if profile_kwargs_list is None:
+        profile_kwargs_list = [{} for _ in lens_model_list]
+
+    def one(i):
+        h = lens_profiles.hessian(lens_model_list[i], x, y, profile_kwargs_list[i], **kwargs[i])
+        if h is None:
+            h = hessian_differential([lens_model_list[i]], x, y, [kwargs[i]], profile_kwargs_list=[profile_kwargs_list[i]],
+                                     h=1e-3)
+        return h
+
+    if isinstance(k, (int, np.integer)) and not isinstance(k, bool):
+        return one(k)
+    bl = _bool_list(len(lens_model_list), k)
+    out = [np.zeros_like(x) for _ in range(4)]
+    for i in range(len(lens_model_list)):
+        if bl[i]:
+            for o, h in zip(out, one(i)):
+                o += h
+    return tuple(o * alpha_scaling for o in out)

@@ -356,3 +356,75 @@ def derivatives(profile, x, y, profile_kwargs=None, **kwargs):
     (profile_list_base.py:161-232), ``kwargs`` the ``param_names`` values."""
     opts = dict(profile_kwargs or {})
     return _FUNCS[profile](x, y, **kwargs, **opts)
+
+
+# --- Hessians (closed forms of the reference; the remaining profiles are covered by the numerical derivative of the
+# --- deflection, oracle/lens_model.py: hessian_differential, and directly by tests/golden/hessians.npz) -----------
+def epl_major_axis_hessian(x, y, b, t, q):
+    """EPLMajorAxis.hessian, epl.py:398-435."""
+    x = np.asarray(x, dtype=float)
+    y = np.asarray(y, dtype=float)
+    with np.errstate(all="ignore"):
+        R = np.maximum(np.hypot(q * x, y), 0.00000001)
+        r = np.hypot(x, y)
+        cos, sin = x / r, y / r
+        cos2, sin2 = cos * cos * 2 - 1, sin * cos * 2
+        kappa = nan_to_num((2 - t) / 2 * (b / R) ** t, posinf=10**10, neginf=-(10**10))
+        alpha_x, alpha_y = epl_major_axis(x, y, b, t, q)
+        gamma_1 = (1 - t) * (alpha_x * cos - alpha_y * sin) / r - kappa * cos2
+        gamma_2 = (1 - t) * (alpha_y * cos + alpha_x * sin) / r - kappa * sin2
+        gamma_1 = nan_to_num(gamma_1, posinf=10**10, neginf=-(10**10))
+        gamma_2 = nan_to_num(gamma_2, posinf=10**10, neginf=-(10**10))
+    return kappa + gamma_1, gamma_2, gamma_2, kappa - gamma_1
+
+
+def epl_hessian(x, y, theta_E, gamma, e1, e2, center_x=0, center_y=0):
+    """EPL.hessian, epl.py:203-232: major-axis Hessian, shear rotated back by 2 phi_G."""
+    t = gamma - 1
+    phi_G, q = ellipticity2phi_q(e1, e2)
+    b = theta_E * np.sqrt(q)
+    x_, y_ = shift_center(x, y, center_x, center_y)
+    x_, y_ = rotate(x_, y_, phi_G)
+    f__xx, f__xy, _, f__yy = epl_major_axis_hessian(x_, y_, b, t, q)
+    kappa = 1.0 / 2 * (f__xx + f__yy)
+    gamma1__ = 1.0 / 2 * (f__xx - f__yy)
+    gamma2__ = f__xy
+    gamma1 = np.cos(2 * phi_G) * gamma1__ - np.sin(2 * phi_G) * gamma2__
+    gamma2 = np.sin(2 * phi_G) * gamma1__ + np.cos(2 * phi_G) * gamma2__
+    return kappa + gamma1, gamma2, gamma2, kappa - gamma1
+
+
+def sis_hessian(x, y, theta_E, center_x=0, center_y=0):
+    """SIS.hessian, sis.py:47-57."""
+    eps = 0.000001
+    x_, y_ = shift_center(x, y, center_x, center_y)
+    R = (x_**2 + y_**2) ** (3.0 / 2)
+    R = np.where(R < eps, eps, R)
+    prefac = theta_E / np.maximum(eps, R)
+    return y_ * y_ * prefac, -x_ * y_ * prefac, -x_ * y_ * prefac, x_ * x_ * prefac
+
+
+def shear_hessian(x, y, gamma1, gamma2, ra_0=0, dec_0=0):
+    """Shear.hessian, shear.py:57-74."""
+    o = np.ones_like(np.asarray(x, dtype=float))
+    return gamma1 * o, gamma2 * o, gamma2 * o, -gamma1 * o
+
+
+def convergence_hessian(x, y, kappa, ra_0=0, dec_0=0):
+    """Convergence.hessian, convergence.py:50-66."""
+    o = np.ones_like(np.asarray(x, dtype=float))
+    return kappa * o, 0 * o, 0 * o, kappa * o
+
+
+_HESSIANS = {"EPL": epl_hessian, "SIS": sis_hessian, "SHEAR": shear_hessian, "CONVERGENCE": convergence_hessian}
+
+
+def hessian(profile, x, y, profile_kwargs=None, **kwargs):
+    """Closed-form Hessian of one named profile, or None where only the numerical derivative is restated."""
+    opts = dict(profile_kwargs or {})
+    if profile == "SIE" and opts.get("NIE") is False:
+        return epl_hessian(x, y, kwargs["theta_E"], opts.get("gamma", 2), kwargs["e1"], kwargs["e2"],
+                           kwargs.get("center_x", 0), kwargs.get("center_y", 0))
+    if profile not in _HESSIANS:
+        return None
+    return _HESSIANS[profile](x, y, **kwargs)

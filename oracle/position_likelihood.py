@@ -9,10 +9,10 @@ Follows
   jaxtronomy/Sampling/Likelihoods/position_likelihood.py:296-352  image2source_covariance, _compute_penalty
   jaxtronomy/PointSource/Types/lensed_position.py:65-90           source position = mean of the ray-shot images
 
-Pinned on tests/golden/position_likelihood.npz (outputs of the unmodified reference).  The Hessian inside is the
-oracle's 4th-order difference of its own deflection (oracle/lens_model.py: hessian_differential) unless the caller
-passes one, so the oracle agrees with the reference to ~1e-8 relative, not 1e-10; the 1e-10 pin of the product is the
-fixture itself.
+Pinned on tests/golden/position_likelihood.npz (outputs of the unmodified reference).  The Hessian inside is
+oracle/lens_model.py: hessian -- the restated closed forms for the EPL family, SIS, SHEAR and CONVERGENCE (1e-10 against
+the fixtures), the 4th-order difference of the restated deflection for the other profiles (~1e-8; of the fixture cases
+only quad_m1m3m4 needs it).
 """
 
 import numpy as np
@@ -43,8 +43,7 @@ def source_position_likelihood(lens_model_list, kwargs_lens, point_source_type_l
             continue
         x, y = np.asarray(kw["ra_image"], dtype=float), np.asarray(kw["dec_image"], dtype=float)
         xs, ys = lens_model.ray_shooting(lens_model_list, x, y, kwargs_lens)
-        h = hessian(x, y) if hessian is not None else lens_model.hessian_differential(lens_model_list, x, y, kwargs_lens,
-                                                                                      h=1e-3)
+        h = hessian(x, y) if hessian is not None else lens_model.hessian(lens_model_list, x, y, kwargs_lens)
         for i in range(x.size):
             logL -= compute_penalty(h[0][i], h[1][i], h[2][i], h[3][i], np.mean(xs), np.mean(ys), xs[i], ys[i], sigma,
                                     hard_bound_rms)

@@ -285,3 +285,44 @@ def test_psf_error_map(name):
     assert_close(param, c.out["param"], what="param", rtol=1e-9, atol_frac=1e-11)
     logL_lin, _ = im.likelihood_data_given_model_linear(kl, ks, kll, kwargs_ps=kps)
     assert abs(logL_lin - float(c.out["logL_linear"])) <= 1e-9 * abs(float(c.out["logL_linear"]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Hessians: the restated closed forms (EPL family, SIS, SHEAR, CONVERGENCE) against the reference's fixtures,
+# INCLUDING the points inside the core clamps (the closed forms reproduce the reference there)
+# ---------------------------------------------------------------------------------------------------------------
+def _hessian_cases():
+    from tests.hessian_cases import HESSIANS
+
+    return [n for n, c in HESSIANS.items()
+            if c.meta.get("profile") in ("EPL", "SIS", "SHEAR", "CONVERGENCE")
+            or (c.meta.get("profile") == "SIE" and c.meta["profile_kwargs"].get("NIE") is False)]
+
+
+@pytest.mark.parametrize("name", _hessian_cases())
+def test_closed_form_hessians(name):
+    from oracle import lens_profiles as olp
+    from tests.hessian_cases import KEYS, profile_case
+
+    c, prof, kw, pk = profile_case(name)
+    got = olp.hessian(prof, c.inp["x"], c.inp["y"], pk, **kw)
+    scale = max(np.max(np.abs(c.out[k][np.isfinite(c.out[k])])) for k in KEYS)
+    for g, k in zip(got, KEYS):
+        assert np.all(np.abs(g - c.out[k]) <= 1e-10 * np.abs(c.out[k]) + 1e-12 * scale), (name, k)
+
+
+def test_model_hessian_sum_and_selection():
+    from oracle import lens_model as olm
+    from tests.hessian_cases import HESSIANS, KEYS, MODEL_CASES, keep_mask
+
+    for name in MODEL_CASES:
+        c = HESSIANS[name]
+        k = c.meta["k"]
+        if isinstance(k, list) and not isinstance(k[0], bool):
+            k = tuple(k)
+        got = olm.hessian(c.meta["lens_model_list"], c.inp["x"], c.inp["y"], c.meta["kwargs"], k=k)
+        # NFW enters through the numerical derivative: 1e-8 of the scale, away from the centres
+        keep = keep_mask(c.inp["x"], c.inp["y"], c.meta["kwargs"]) & (np.hypot(c.inp["x"] + 0.7, c.inp["y"] - 0.3) > 0.3)
+        scale = max(np.max(np.abs(c.out[q][keep])) for q in KEYS)
+        for g, q in zip(got, KEYS):
+            assert np.max(np.abs(g - c.out[q])[keep]) <= 1e-8 * scale, (name, q)
