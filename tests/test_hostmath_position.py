@@ -70,3 +70,17 @@ def test_oracle_image_position_and_astrometric_terms():
     assert opl.astrometric_likelihood(quad, a.meta["kwargs_special"], a.meta["sigma"]) == pytest.approx(
         float(a.out["logL"]), rel=1e-13)
     assert float(POS["star_only"].out["logL"]) == 0.0
+
+
+def test_image_on_the_critical_curve_takes_the_singular_branch():
+    """det(Sigma_beta) == 0 exactly (SIS image at r = theta_E: A = diag(1, 0)): penalty 1e15 (position_likelihood.py:338-342),
+    kernel arithmetic (host build) against the oracle restatement."""
+    kw = [dict(theta_E=1.0, center_x=0.0, center_y=0.0)]
+    ra, dec = [1.0, -0.9], [0.0, 0.0]
+    got = hm.source_position_logl(["SIS"], kw, ra, dec, 0.001)
+    want = opl.source_position_likelihood(["SIS"], kw, ["LENSED_POSITION"], [dict(ra_image=ra, dec_image=dec)], 0.001)
+    assert want < -0.9e15 and abs(got - want) <= 1e-12 * abs(want)
+    # hard bound: + 1e3 per image beyond the tolerance, none within
+    far = hm.source_position_logl(["SIS"], kw, [1.1, -0.7], dec, 0.01, 0.05)
+    near = hm.source_position_logl(["SIS"], kw, [1.1, -0.7], dec, 0.01, 0.5)
+    assert abs((near - far) - 2e3) <= 1e-9 * abs(far)
