@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("LSIM_LIB") or os.path.join(_HERE, "csrc", "liblsim.so
 
 MAX_PARAMS = 12
 MAX_SLOTS = 8
-ABI_VERSION = 7
+ABI_VERSION = 8
 PRECISION_F64, PRECISION_F32 = 0, 1
 
 # enum mirrors (include/lsim.h)

@@ -524,7 +524,7 @@ int lsim_source_position_logl(const lsim_plan* plan, const double* params, int64
                               int n_img, int coords_batched, double sigma, double hard_bound_rms, double* logl,
                               void* stream) {
   if (!plan || B < 0 || n_img < 0 || n_img > 1024 || !(sigma > 0.0)) return LSIM_E_INVALID;
-  if (!plan->hess_ok) return LSIM_E_UNSUPPORTED;
+  if (!plan->hess_ok || B > 2147483647LL) return LSIM_E_UNSUPPORTED;  // one CTA per set in grid.x
   if (B == 0) return LSIM_OK;
   if (!logl || (n_img > 0 && (!x || !y)) || (plan->dev.n_param_cols > 0 && !params)) return LSIM_E_INVALID;
   const size_t smem = srcpos_smem_bytes(plan->n_hess_lens, plan->hess_series, n_img);
