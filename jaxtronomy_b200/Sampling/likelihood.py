@@ -79,6 +79,10 @@ class LikelihoodModule(object):
             for k, n in enumerate(fn.num_point_images):
                 src = [[fn("point_source", k, name, element=j) for j in range(n)] for name in ("ra_image", "dec_image")]
                 self._pos_models.append((ps.point_source_type_list[k], n, src))
+            if pl._image_position_likelihood and (len(pl._ra_image_list) < len(self._pos_models)
+                                                  or len(pl._dec_image_list) < len(self._pos_models)):
+                raise ValueError("image_position_likelihood needs ra_image_list / dec_image_list with one entry per "
+                                 "point-source model")
             if pl._source_position_likelihood and "LENSED_POSITION" in ps.point_source_type_list:
                 # the reference's class_creator always hands the lens model to PointSource; a PointSource built without
                 # one falls back to the image model's

@@ -439,6 +439,8 @@ def test_likelihood_module_image_position_term_on_the_columns():
         LikelihoodModule(img, param, source_position_likelihood=False, astrometric_likelihood=True)
     with pytest.raises(ValueError):
         LikelihoodModule(NoImage(), Param(dict(lens_model_list=["SIS"])), image_position_likelihood=True)
+    with pytest.raises(ValueError):
+        LikelihoodModule(img, param, source_position_likelihood=False, image_position_likelihood=True)  # no data lists
 
 
 def test_device_ensemble_sampler_samples_a_correlated_gaussian():
