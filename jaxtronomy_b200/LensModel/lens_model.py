@@ -166,8 +166,10 @@ class LensModel(object):
 
     def alpha(self, x, y, kwargs, k=None):
         """Deflection angles, lens_model.py (alpha) / single_plane.py:112-139."""
-        if self.multi_plane:
-            raise ValueError("alpha() in multi-plane mode is outside the scope of jaxtronomy_b200; use ray_shooting")
+        if self.multi_plane:  # reduced deflection theta - beta, MultiPlane/multi_plane.py:512-534
+            x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
+            bx, by = self._run(x, y, kwargs, k, what=0)
+            return x - bx, y - by
         return self._run(x, y, kwargs, k, what=1)
 
     # -- second derivatives (lens_model.py:384-527) ------------------------------------------------------------
@@ -177,11 +179,11 @@ class LensModel(object):
         ``diff=None``: the exact differentials, one `lsim_hessian` launch (single plane; the reference sums the
         profiles' own ``hessian`` functions, single_plane.py:142-180).  With ``diff`` set, the finite differences
         of the deflection field on a square or a cross around (x, y), lens_model.py:617-700 -- four `alpha`
-        launches.  Like `alpha`, the deflection scaling of the model is applied for every ``k``."""
+        launches.  Like `alpha`, the deflection scaling of the model is applied for every ``k``.  Multi-plane models
+        have no exact form: ``diff=None`` is the reference's forward difference with 1e-8 (`_hessian_multi_plane`)."""
         if diff is None:
             if self.multi_plane:
-                raise ValueError("hessian() in multi-plane mode is outside the scope of jaxtronomy_b200: form it from "
-                                 "ray_shooting differences")
+                return self._hessian_multi_plane(x, y, kwargs, k=k)
             xf, yf, shape, want_torch = _arrays.flatten_coords(x, y)
             values = _model.gather_values(self.param_name_list, kwargs, "lens")
             mat, B, batched = _model.pack_columns(values)
@@ -192,6 +194,20 @@ class LensModel(object):
         if diff_method == "cross":
             return self._hessian_differential_cross(x, y, kwargs, k=k, diff=diff)
         raise ValueError('diff_method %s not supported. Chose among "square" or "cross".' % diff_method)
+
+    def _hessian_multi_plane(self, x, y, kwargs, k=None, diff=0.00000001):
+        """MultiPlane.hessian, MultiPlane/multi_plane.py:537-589: FORWARD differences of alpha = theta - beta with
+        diff = 1e-8 (three ray-shooting launches).  As the reference notes, the result carries the rounding of the ray
+        shooting divided by diff (~1e-7); pass ``diff`` to `hessian` for the centred stencils."""
+        x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
+        ax, ay = self.alpha(x, y, kwargs, k=k)
+        ax_dx, ay_dx = self.alpha(x + diff, y, kwargs, k=k)
+        ax_dy, ay_dy = self.alpha(x, y + diff, kwargs, k=k)
+        f_xx = (ax_dx - ax) / diff
+        f_xy = (ax_dy - ax) / diff
+        f_yx = (ay_dx - ay) / diff
+        f_yy = (ay_dy - ay) / diff
+        return f_xx, f_xy, f_yx, f_yy
 
     def _hessian_differential_cross(self, x, y, kwargs, k=None, diff=0.00001):
         """Differentials of alpha along the cross centred at (x, y), lens_model.py:617-649."""

@@ -612,6 +612,27 @@ def gen_hessians():
         st.add("model_flexion_%d" % hd, dict(x=x, y=y),
                dict(zip(("f_xxx", "f_xxy", "f_xyy", "f_yyy"), (np.asarray(a) for a in f))),
                dict(lens_model_list=names, kwargs=kw, diff=1e-4, hessian_diff=hd))
+    # multi-plane (same system as lens_models.npz "multi_plane"): alpha = theta - beta (multi_plane.py:512-534), the
+    # Hessian as the reference's forward difference of alpha with diff = 1e-8 (multi_plane.py:537-589), and the
+    # square stencil with diff = 1e-4 through LensModel.hessian
+    mp_names = ["EPL", "NFW_ELLIPSE_CSE", "SIS", "SHEAR"]
+    mp_z = [0.5, 0.5, 0.2, 0.8]
+    mp_kw = [kw[0], dict(Rs=1.5, alpha_Rs=0.3, e1=0.1, e2=0.05, center_x=0.0, center_y=0.1),
+             dict(theta_E=0.15, center_x=0.6, center_y=-0.4), kw[1]]
+    lmm = LensModel(mp_names, z_source=1.5, lens_redshift_list=mp_z, multi_plane=True)
+    mp = lmm.lens_model
+    base = mp.multi_plane_base
+    ax, ay = lmm.alpha(x, y, mp_kw)
+    h8 = lmm.hessian(x, y, mp_kw)
+    h4 = lmm.hessian(x, y, mp_kw, diff=1e-4, diff_method="square")
+    outs = dict(alpha_x=np.asarray(ax), alpha_y=np.asarray(ay), magnification=np.asarray(lmm.magnification(x, y, mp_kw)))
+    outs.update({"d8_" + q: np.asarray(a) for q, a in zip(("f_xx", "f_xy", "f_yx", "f_yy"), h8)})
+    outs.update({"d4_" + q: np.asarray(a) for q, a in zip(("f_xx", "f_xy", "f_yx", "f_yy"), h4)})
+    st.add("multi_plane", dict(x=x, y=y, sorted_index=np.asarray(base.sorted_redshift_index),
+                               T_ij_list=np.asarray(base.T_ij_list, dtype=float), T_z_list=np.asarray(base.T_z_list, dtype=float),
+                               reduced2physical=np.asarray(base._reduced2physical_factor, dtype=float),
+                               T_ij_stop=float(mp.T_ij_stop), T_z_source=float(mp._T_z_source)), outs,
+           dict(lens_model_list=mp_names, lens_redshift_list=mp_z, z_source=1.5, kwargs=mp_kw))
     st.save("hessians.npz")
     for c in skipped:
         print("skipped", c)

@@ -133,13 +133,35 @@ def test_batched_parameter_sets_torch_io_and_oracle_difference():
             assert np.max(np.abs(o - w)) <= 1e-8 * scale
 
 
+def test_multi_plane_alpha_and_hessian():
+    """Multi-plane: alpha = theta - beta (multi_plane.py:512-534) at 1e-10 of |theta|; the Hessian is the reference's
+    forward difference of alpha with diff = 1e-8 (multi_plane.py:537-589), whose rounding noise is eps |theta| / diff on
+    BOTH sides (measured 1.5e-7 on the host build of the kernel arithmetic, tests/test_hostmath_hessian.py): bar
+    64 eps max(|theta|, 1) / diff per point; the diff = 1e-4 square stencil at 64 eps max(|theta|, 1) / 1e-4."""
+    c = HESSIANS["multi_plane"]
+    lm = _LensModel()(c.meta["lens_model_list"], z_source=c.meta["z_source"],
+                      lens_redshift_list=c.meta["lens_redshift_list"], multi_plane=True)
+    assert lm._sorted_redshift_index == [int(i) for i in c.inp["sorted_index"]]
+    lm.set_multi_plane_constants(c.inp["T_ij_list"], c.inp["T_z_list"], c.inp["reduced2physical"],
+                                 float(c.inp["T_ij_stop"]), float(c.inp["T_z_source"]))
+    x, y, kw = c.inp["x"], c.inp["y"], c.meta["kwargs"]
+    theta = np.maximum(np.maximum(np.abs(x), np.abs(y)), 1.0)
+    ax, ay = lm.alpha(x, y, kw)
+    assert np.all(np.abs(ax - c.out["alpha_x"]) <= 1e-10 * theta) and np.all(np.abs(ay - c.out["alpha_y"]) <= 1e-10 * theta)
+    eps = np.finfo(float).eps
+    for tag, got, diff in (("d8_", lm.hessian(x, y, kw), 1e-8),
+                           ("d4_", lm.hessian(x, y, kw, diff=1e-4, diff_method="square"), 1e-4)):
+        for g, q in zip(got, KEYS):
+            assert np.all(np.abs(g - c.out[tag + q]) <= 64 * eps * theta / diff), (tag, q)
+    with pytest.raises(ValueError):
+        lm.hessian(x, y, kw, k=0)          # no subset selection in multi-plane mode, like the reference
+
+
 def test_scope_errors_and_alpha_scaling():
     LensModel = _LensModel()
     x, y = np.array([0.7, -1.1]), np.array([0.4, 0.9])
     kw = [dict(theta_E=1.0, center_x=0.0, center_y=0.0)]
     mp = LensModel(["SIS"], z_source=1.5, lens_redshift_list=[0.5], multi_plane=True)
-    with pytest.raises(ValueError):
-        mp.hessian(x, y, kw)
     # empty input, and the raw C ABI on a multi-plane plan
     lm = LensModel(["SIS"])
     assert all(h.shape == (0,) for h in lm.hessian(np.zeros(0), np.zeros(0), kw))

@@ -43,3 +43,31 @@ def test_model_hessian_sums_the_profiles():
     scale = max(np.max(np.abs(c.out[k][keep])) for k in KEYS)
     for g, k in zip(got, KEYS):
         assert np.max(np.abs(g - c.out[k])[keep]) <= 1e-10 * scale, k
+
+
+def test_multi_plane_forward_difference_noise_is_inside_the_stated_bar():
+    """The multi-plane Hessian of the reference is a forward difference of alpha = theta - beta with diff = 1e-8
+    (multi_plane.py:537-589).  The same stencil on the kernel's host-compiled ray shooting agrees with the reference
+    fixture to the rounding of the ray shooting over diff: bar 64 eps max(|theta|, 1) / diff (tests/test_gpu_zhessian.py
+    uses the same bar for the device)."""
+    c = HESSIANS["multi_plane"]
+    order = [int(i) for i in c.inp["sorted_index"]]
+    names = [c.meta["lens_model_list"][i] for i in order]
+    kws = [c.meta["kwargs"][i] for i in order]
+    mp = dict(delta_T=c.inp["T_ij_list"], T_z=c.inp["T_z_list"], red2phys=c.inp["reduced2physical"],
+              T_ij_end=float(c.inp["T_ij_stop"]), T_z_source=float(c.inp["T_z_source"]))
+    x, y = c.inp["x"], c.inp["y"]
+
+    def alpha(xx, yy):
+        bx, by = hm.ray_shoot(names, kws, xx, yy, multi_plane=mp)
+        return xx - bx, yy - by
+
+    theta = np.maximum(np.maximum(np.abs(x), np.abs(y)), 1.0)
+    ax, ay = alpha(x, y)
+    assert np.all(np.abs(ax - c.out["alpha_x"]) <= 1e-10 * theta) and np.all(np.abs(ay - c.out["alpha_y"]) <= 1e-10 * theta)
+    d = 1e-8
+    axd, ayd = alpha(x + d, y)
+    axe, aye = alpha(x, y + d)
+    eps = np.finfo(float).eps
+    for g, q in zip(((axd - ax) / d, (axe - ax) / d, (ayd - ay) / d, (aye - ay) / d), KEYS):
+        assert np.all(np.abs(g - c.out["d8_" + q]) <= 64 * eps * theta / d), q
