@@ -71,3 +71,40 @@ def test_multi_plane_forward_difference_noise_is_inside_the_stated_bar():
     eps = np.finfo(float).eps
     for g, q in zip(((axd - ax) / d, (axe - ax) / d, (ayd - ay) / d, (aye - ay) / d), KEYS):
         assert np.all(np.abs(g - c.out["d8_" + q]) <= 64 * eps * theta / d), q
+
+
+def test_multi_plane_facade_arithmetic_on_the_host_ray_shooting(monkeypatch):
+    """LensModel.alpha / hessian / magnification of a multi-plane model are façade arithmetic over ray shooting.  With
+    `_run` (the one GPU launch inside) replaced by the host build of the same kernel code, the whole façade path runs on
+    the CPU against the reference fixture -- same bars as the GPU test."""
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+
+    c = HESSIANS["multi_plane"]
+    order = [int(i) for i in c.inp["sorted_index"]]
+    names = [c.meta["lens_model_list"][i] for i in order]
+    mp = dict(delta_T=c.inp["T_ij_list"], T_z=c.inp["T_z_list"], red2phys=c.inp["reduced2physical"],
+              T_ij_end=float(c.inp["T_ij_stop"]), T_z_source=float(c.inp["T_z_source"]))
+
+    def host_run(self, x, y, kwargs, k, what):
+        assert what == 0 and k is None
+        return hm.ray_shoot(names, [kwargs[i] for i in order], np.asarray(x, dtype=float), np.asarray(y, dtype=float),
+                            multi_plane=mp)
+
+    monkeypatch.setattr(LensModel, "_run", host_run)
+    lm = LensModel(c.meta["lens_model_list"], z_source=c.meta["z_source"],
+                   lens_redshift_list=c.meta["lens_redshift_list"], multi_plane=True)
+    x, y, kw = c.inp["x"], c.inp["y"], c.meta["kwargs"]
+    theta = np.maximum(np.maximum(np.abs(x), np.abs(y)), 1.0)
+    eps = np.finfo(float).eps
+    ax, ay = lm.alpha(x, y, kw)
+    assert np.all(np.abs(ax - c.out["alpha_x"]) <= 1e-10 * theta)
+    for tag, got, diff in (("d8_", lm.hessian(x, y, kw), 1e-8),
+                           ("d4_", lm.hessian(x, y, kw, diff=1e-4, diff_method="square"), 1e-4)):
+        for g, q in zip(got, KEYS):
+            assert np.all(np.abs(g - c.out[tag + q]) <= 64 * eps * theta / diff), (tag, q)
+    # mu = 1 / det A from the noisy forward difference: relative agreement degrades with |mu| (d mu = mu^2 d det)
+    mu = lm.magnification(x, y, kw)
+    want = c.out["magnification"]
+    assert np.all(np.abs(mu - want) <= 4 * 64 * eps * theta / 1e-8 * want**2 * 20 + 1e-9 * np.abs(want))
+    f = lm.flexion(x, y, kw, diff=1e-2, hessian_diff=True)   # runs through hessian(diff=...) -> alpha: shapes only
+    assert all(np.shape(a) == np.shape(x) for a in f)
