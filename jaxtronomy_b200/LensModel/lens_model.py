@@ -274,3 +274,14 @@ class LensModel(object):
         f_xyy = (f_xy_dy - f_xy_dy_) / diff
         f_yyy = (f_yy_dy - f_yy_dy_) / diff
         return f_xxx, f_xxy, f_xyy, f_yyy
+
+    def set_static(self, kwargs):
+        """lens_model.py:572-581.  The reference's profiles keep no static cache under jit (profile_list_base.py:246-254
+        forwards to no-op `set_static`s); here every call prepares its parameter set on the device anyway: returns the
+        keyword arguments unchanged."""
+        self.check_parameters(kwargs)
+        return kwargs
+
+    def set_dynamic(self):
+        """lens_model.py:583-592: nothing is cached, nothing to free."""
+        return None
