@@ -18,7 +18,13 @@ import sys
 import threading
 import time
 
-import numpy as np
+# The CPU arm runs ONE process per host core; every BLAS / OpenMP pool inside a worker must therefore be a single
+# thread, and that has to be decided before NumPy / OpenBLAS initialise (round 1 set it after the fork: no effect,
+# 16 processes x 16 spinning BLAS threads ran the port 3-4x below what the host can do).
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -104,6 +110,25 @@ def build_headline(num_pix=180, ss=3, kernel_size=21, n_sets=1024, seed=1234, da
                 static=st, data_image=data_image, num_pix=num_pix, ss=ss)
 
 
+SAMPLED_COLUMNS = [0, 1, 2, 3, 4, 5, 6, 7, 11, 12, 13, 14, 15, 16]  # ra_0, dec_0 fixed at 0; amp solved linearly
+
+
+def headline_likelihood_module(model, e_bound=0.5):
+    """The reference's batch boundary for the headline model: LikelihoodModule(ImageLinearFit, Param) with the shear
+    origin fixed and the amplitude solved linearly -> 14 sampled parameters.  Returns (module, positions_of) where
+    positions_of maps the [B, 17] rows of `sample_params` to the sampler's [B, 14] `positions`."""
+    from jaxtronomy_b200.Sampling.likelihood import LikelihoodModule
+    from jaxtronomy_b200.Sampling.parameters import Param
+
+    km = dict(lens_model_list=LENS_LIST, source_light_model_list=SOURCE_LIST, lens_light_model_list=[])
+    param = Param(km, kwargs_fixed_lens=[{}, {"ra_0": 0.0, "dec_0": 0.0}],
+                  kwargs_lower_lens=[{"e1": -e_bound, "e2": -e_bound}, {}],
+                  kwargs_upper_lens=[{"e1": e_bound, "e2": e_bound}, {}])
+    like = LikelihoodModule(model, param)
+    assert param.num_param()[0] == len(SAMPLED_COLUMNS)
+    return like, lambda rows: np.ascontiguousarray(np.asarray(rows)[:, SAMPLED_COLUMNS])
+
+
 def build_oracle(st, data_image, ss):
     from oracle import imsim
     from oracle.lenstronomy_port import PSF as OPSF
@@ -126,7 +151,12 @@ _W = {}
 
 
 def _cpu_init(st, data_image, ss):
-    os.environ["OMP_NUM_THREADS"] = "1"
+    try:  # belt and braces: the environment at the top of this file already pins the pools to one thread
+        from threadpoolctl import threadpool_limits
+
+        _W["limits"] = threadpool_limits(1)
+    except Exception:
+        pass
     _W["om"] = build_oracle(st, data_image, ss)
 
 
@@ -259,32 +289,64 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+WORKLOAD = ("headline: EPL+SHEAR, SERSIC_ELLIPSE source, 180x180, ss=3, 21x21 pixel PSF, ImageLinearFit likelihood")
+COUNTERS_FILE = os.path.join(ROOT, "profiles", "k_image_counters.json")
+
+
+def cpu_block(value, cores, n, dt):
+    return {"value": value, "unit": "images/s", "cores": cores, "images_per_s_per_core": value / cores, "kind": "port",
+            "blas_threads_per_process": int(os.environ.get("OMP_NUM_THREADS", "0") or 0),
+            "sample": "%d parameter sets of the same workload, NumPy oracle restatement (jax + lenstronomy are not "
+                      "installable offline), one single-threaded process per core, %.1f s" % (n, dt)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = args.cpu_images if args.cpu_images else 8 * cores
-    vals = []
+    n = args.cpu_images if args.cpu_images else 16 * cores
+    vals, dts = [], []
     for _ in range(args.warmup):
         cpu_images_per_s(cores, cores)
     for _ in range(args.steps):
         v, dt = cpu_images_per_s(n, cores)
         vals.append(v)
+        dts.append(dt)
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / value, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "headline: EPL+SHEAR, SERSIC_ELLIPSE source, 180x180, ss=3, 21x21 pixel PSF, "
-                               "ImageLinearFit likelihood", "sample_images_per_step": n},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "%d parameter sets per step, NumPy oracle restatement (jax + lenstronomy are not "
-                                   "installable offline), one process per core" % n},
+        "config": {"workload": WORKLOAD, "sample_images_per_step": n},
+        "cpu_baseline": cpu_block(value, cores, n, float(np.mean(dts))),
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def load_counters():
+    """Executed fp64 thread-instructions per sub-pixel and DRAM bytes per set of k_image, from the committed ncu
+    --set full capture of THIS build's kernel (profiles/k_image_counters.json names the capture)."""
+    try:
+        with open(COUNTERS_FILE) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
+def secondary_configs():
+    """BASELINE.json's other configurations + the mixed-nmax headline, a few steps each (tools/bench_configs.py)."""
+    from tools import bench_configs as bc
+
+    out = {}
+    for name in ("c2", "c3", "c4", "c5", "mixed"):
+        try:
+            out[name] = bc.CONFIGS[name]()
+        except Exception as e:  # a secondary line must never take the headline down
+            out[name] = {"error": repr(e)}
+    return out
 
 
 def run_gpu(args):
@@ -292,6 +354,7 @@ def run_gpu(args):
     import torch.distributed as dist
 
     from jaxtronomy_b200 import _lib, parallel
+    from jaxtronomy_b200.Sampling.sampler import prepare_logL_func
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -308,9 +371,12 @@ def run_gpu(args):
     model = cfg["model"]
     lo, hi = parallel.shard_bounds(B, world, rank)
     shard = cfg["params"][lo:hi].contiguous()
-    host_params = torch.as_tensor(cfg["params_host"][lo:hi]).pin_memory()
     logl_all = torch.empty(B, dtype=torch.float64, device="cuda")
-    host_logl = torch.empty(B, dtype=torch.float64).pin_memory()
+    # the reference's batch boundary (Sampling/sampler.py:215-251): pageable NumPy positions in, NumPy logL out
+    like, positions_of = headline_likelihood_module(model)
+    logl_func = prepare_logL_func("gpu", like, world_size=world, rank=rank)
+    positions = positions_of(cfg["params_host"])
+    e2e_out = {}
 
     def step_device():
         logl, _, _ = model.logL_linear_batch(shard, out=logl_all[lo:hi])
@@ -318,10 +384,8 @@ def run_gpu(args):
         return logl
 
     def step_e2e():
-        dev = host_params.to("cuda", non_blocking=True)
-        model.logL_linear_batch(dev, out=logl_all[lo:hi])
-        parallel.all_gather_logl(logl_all, world, rank, B)
-        host_logl.copy_(logl_all, non_blocking=True)
+        logl = logl_func(positions)              # np.ndarray[B, 14] -> np.ndarray[B], blocking
+        e2e_out["best"] = float(logl.max())      # the sampler's use of the result, on the host
 
     def barrier():
         if world > 1:
@@ -341,7 +405,8 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         step_device()
     launches0 = _lib.launch_count()
     with ClockSampler(local_rank) as clk:
@@ -352,9 +417,11 @@ def run_gpu(args):
     ms_e2e = timed(step_e2e, args.steps)
     value = B * args.steps / (ms_total * 1e-3)
     e2e_value = B * args.steps / (ms_e2e * 1e-3)
+    # the boundary call and the resident call agree on the numbers they return
+    check = np.abs(logl_func(positions) - logl_all.cpu().numpy()).max()
 
     # roofline of the dominant kernel (k_image), timed live with CUDA events on the launch stream
-    roof, cpu = None, None
+    roof, cpu, secondary = None, None, None
     if rank == 0:
         peak = _lib.measure_fp64_peak(400000)
         _lib.set_timing(True)
@@ -364,42 +431,63 @@ def run_gpu(args):
         _lib.set_timing(False)
         n_img_launch = max(tm["image"]["count"], 1)
         sets_per_launch = (hi - lo) / n_img_launch
-        flop_per_launch = sets_per_launch * N_SUB_PER_IMAGE * FLOP_PER_SUPERPIXEL
+        subpix_per_launch = sets_per_launch * N_SUB_PER_IMAGE
         avg_ms = tm["image"]["ms"] / n_img_launch
-        achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12
+        model_tflops = subpix_per_launch * FLOP_PER_SUPERPIXEL / (avg_ms * 1e-3) / 1e12
         total_ms = sum(v["ms"] for v in tm.values())
-        roof = {"bound": "fp64", "kernel": "k_image (fused ray-shoot + light + re-bin)", "achieved": achieved,
-                "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
-                # dram__bytes_read.sum + dram__bytes_write.sum of one k_image launch of 1184 sets, from the ncu
-                # --set full capture profiles/image_r1h_ncu_summary.txt (5.7 MB + 255.7 MB: the re-binned images,
-                # 1184 x 259 KB = 306.9 MB algorithmic; the tail of the writes is still in L2 when the kernel ends)
-                "traffic": 261.4e6 * sets_per_launch / 1184.0,
-                "peak_source": "measured DFMA-chain microbenchmark (lsim_measure_fp64_peak); MEASURED_PEAKS.json has "
-                               "no fp64 entry; nominal 37.2 TFLOP/s",
-                "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_ms,
-                "kernel_share_of_step": {k: v["ms"] / total_ms for k, v in tm.items()},
-                "whole_step_frac": value / world * FLOP_PER_IMAGE / peak}
+        cnt = load_counters()
+        nominal = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 DFMA lanes x 2 flop x 1.965 GHz = 37.2 TFLOP/s
+        roof = {"bound": "fp64", "kernel": "k_image (fused ray-shoot + light + re-bin)", "unit": "TFLOP/s",
+                "peak": peak / 1e12, "peak_nominal": nominal,
+                "peak_source": "measured DFMA-chain microbenchmark in this run (lsim_measure_fp64_peak); "
+                               "MEASURED_PEAKS.json has no fp64 entry; nominal printed beside it",
+                "avg_launch_ms": avg_ms, "sets_per_launch": sets_per_launch,
+                "model_flop_per_subpixel": FLOP_PER_SUPERPIXEL, "model_achieved": model_tflops,
+                "model_frac": model_tflops / (peak / 1e12),
+                "model_note": "SURVEY 8(d) weights (pow = 82, exp = 36, div = 16 ...) charge more flop than the "
+                              "kernel executes; model_frac may exceed 1 and is NOT the roofline fraction",
+                "kernel_share_of_step": {k: v["ms"] / total_ms for k, v in tm.items()}}
+        if cnt is not None:
+            # executed instructions: one fp64 pipe issue slot per DFMA / DMUL / DADD thread-instruction; the measured
+            # peak is a pure-DFMA issue rate of peak/2 instructions/s
+            inst = cnt["dfma_per_subpixel"] + cnt["dmul_per_subpixel"] + cnt["dadd_per_subpixel"]
+            flop = 2 * cnt["dfma_per_subpixel"] + cnt["dmul_per_subpixel"] + cnt["dadd_per_subpixel"]
+            issue_rate = inst * subpix_per_launch / (avg_ms * 1e-3)
+            roof.update({"achieved": flop * subpix_per_launch / (avg_ms * 1e-3) / 1e12,
+                         "frac": issue_rate / (peak / 2.0),
+                         "frac_of_nominal": issue_rate / (nominal * 1e12 / 2.0),
+                         "frac_definition": "executed fp64 thread-instructions (DFMA+DMUL+DADD per sub-pixel from the "
+                                            "ncu capture) x sub-pixels / launch time / measured DFMA issue rate",
+                         "executed_fp64_inst_per_subpixel": inst, "executed_flop_per_subpixel": flop,
+                         "traffic": (cnt["dram_read_bytes_per_set"] + cnt["dram_write_bytes_per_set"]) * sets_per_launch,
+                         "algorithmic_bytes": sets_per_launch * 180 * 180 * 8,
+                         "counters_from": cnt["capture"]})
+        else:
+            roof.update({"achieved": None, "frac": None, "traffic": None, "counters_from": None})
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             n = args.cpu_images if args.cpu_images else 16 * cores
             v, dt = cpu_images_per_s(n, cores)
-            cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                   "sample": "%d parameter sets of the same workload, NumPy oracle restatement, one process per core, "
-                             "%.1f s" % (n, dt)}
+            cpu = cpu_block(v, cores, n, dt)
+        if world == 1 and not args.no_secondary:
+            secondary = secondary_configs()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "headline: EPL+SHEAR, SERSIC_ELLIPSE source, 180x180, ss=3, 21x21 pixel PSF, "
-                                   "ImageLinearFit likelihood", "particles": B, "parallelism": "particle shards x%d, "
+            "config": {"workload": WORKLOAD, "particles": B, "parallelism": "particle shards x%d, "
                        "NCCL all-gather of logL" % world,
                        "l2": "no flush: each step streams %.1f GB of scratch images per GPU (>> 126 MB L2); the only "
                              "reused inputs are the 4.7 MB grid and the parameter matrix" %
                              ((hi - lo) * 2 * 180 * 180 * 8 / 1e9)},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(host_params.numel() * 8),
-                    "d2h_bytes_per_step": int(B * 8)},
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int((hi - lo) * positions.shape[1] * 8), "d2h_bytes_per_step": int(B * 8),
+                    "api": "prepare_logL_func('gpu', LikelihoodModule(ImageLinearFit, Param))(positions: np.ndarray"
+                           "[B,14], pageable) -> np.ndarray[B]; best = logL.max() on the host every step",
+                    "max_abs_diff_vs_resident_call": float(check)},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "secondary": secondary,
         }
         print(json.dumps(line))
     if world > 1:
@@ -415,6 +503,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-images", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
                     help="f32: the opt-in single-precision image kernel (NOT the headline; dtype is reported)")
     args = ap.parse_args()

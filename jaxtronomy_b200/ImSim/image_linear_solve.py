@@ -36,18 +36,19 @@ class ImageLinearFit(ImageModel):
         key = ("split", bool(unconvolved), tuple(num_images))
         if key not in self._plans:
             ns, n_light = self.SourceModel._num_func, self._n_lin
-            n_slots = n_light + sum(num_images)
+            ps_slots, n_ps = self.PointSource.linear_slots(num_images, n_light)
+            n_slots = n_light + n_ps
             if n_slots > _lib.MAX_SLOTS:
                 raise ValueError("at most %d linear components are supported by jaxtronomy_b200, got %d"
                                  % (_lib.MAX_SLOTS, n_slots))
-            ps = dict(num_images=num_images, slots=[n_light + j for j in range(sum(num_images))], k=None)
+            ps = dict(num_images=num_images, slots=ps_slots, k=None)
             self._plans[key] = self._build_plan(list(range(ns)), [ns + i for i in range(self.LensLightModel._num_func)],
                                                 max(n_slots, 1), False, unconvolved, ps=ps)
         return self._plans[key]
 
     def num_param_linear(self, kwargs_lens=None, kwargs_source=None, kwargs_lens_light=None, kwargs_ps=None):
-        n_ps = self.PointSource.num_basis(kwargs_ps) if (kwargs_ps and self._n_ps_models) else sum(self._num_point_images)
-        return self._n_lin + n_ps
+        counts = self.PointSource.num_images(kwargs_ps) if (kwargs_ps and self._n_ps_models) else self._num_point_images
+        return self._n_lin + self.PointSource.linear_slots(counts, 0)[1]
 
     # -- batch entry points (CUDA tensors, no Python-side packing) ----------------------------------------------
     def logL_linear_batch(self, params, source_marg=False, return_model=False, out=None, num_images=None):
@@ -76,7 +77,7 @@ class ImageLinearFit(ImageModel):
         """Response matrix [n_lin, N_d] on the unmasked pixels (image_linear_solve.py:361-455)."""
         counts = self._ps_counts(kwargs_ps)
         mat, B, batched = self._pack(kwargs_lens, kwargs_source, kwargs_lens_light, kwargs_ps, counts)
-        if self._n_lin + sum(counts) == 0:
+        if self._n_lin + self.PointSource.linear_slots(counts, 0)[1] == 0:
             return np.zeros(((B,) if batched else ()) + (0, self.num_data_evaluate))
         import torch
 

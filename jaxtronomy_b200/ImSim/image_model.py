@@ -187,10 +187,11 @@ class ImageModel(object):
                              % (len(num_images), self._n_ps_models))
         n_ps = sum(num_images)
         if linear_solver:
-            n_slots = max(ns + nl + n_ps, 1)
+            ps_slots, n_ps_lin = self.PointSource.linear_slots(num_images, ns + nl)
+            n_slots = max(ns + nl + n_ps_lin, 1)
             if n_slots > _lib.MAX_SLOTS:
                 raise ValueError("at most %d linear components are supported" % _lib.MAX_SLOTS)
-            ps = dict(num_images=num_images, slots=[ns + nl + j for j in range(n_ps)], k=None)
+            ps = dict(num_images=num_images, slots=ps_slots, k=None)
             return self._build_plan(list(range(ns)), [ns + i for i in range(nl)], n_slots, False, False,
                                     source_fn=source_fn, n_cols=n_cols, ps=ps)
         ps = dict(num_images=num_images, slots=[0] * n_ps, k=None)

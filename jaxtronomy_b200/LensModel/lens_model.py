@@ -169,6 +169,8 @@ class LensModel(object):
         if self.multi_plane:  # reduced deflection theta - beta, MultiPlane/multi_plane.py:512-534
             x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
             bx, by = self._run(x, y, kwargs, k, what=0)
+            if _arrays.is_torch(bx):  # a CPU tensor in, a CUDA tensor out: subtract on the result's device
+                x, y = (v.to(bx.device) if _arrays.is_torch(v) else v for v in (x, y))
             return x - bx, y - by
         return self._run(x, y, kwargs, k, what=1)
 
@@ -212,7 +214,6 @@ class LensModel(object):
     def _hessian_differential_cross(self, x, y, kwargs, k=None, diff=0.00001):
         """Differentials of alpha along the cross centred at (x, y), lens_model.py:617-649."""
         x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
-        x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
         h = diff / 2
         ax_dx, ay_dx = self.alpha(x + h, y, kwargs, k=k)
         ax_dy, ay_dy = self.alpha(x, y + h, kwargs, k=k)
@@ -226,7 +227,6 @@ class LensModel(object):
 
     def _hessian_differential_square(self, x, y, kwargs, k=None, diff=0.00001):
         """Differentials of alpha on the square around (x, y) (minimises the curl), lens_model.py:651-688."""
-        x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
         x, y = (v if _arrays.is_torch(v) else np.asarray(v, dtype=np.float64) for v in (x, y))
         h = diff / 2
         ax_pp, ay_pp = self.alpha(x + h, y + h, kwargs, k=k)

@@ -100,6 +100,20 @@ class PointSource(object):
     def num_images(self, kwargs_ps):
         return [int(np.size(kw["ra_image"])) for kw in kwargs_ps]
 
+    def linear_slots(self, num_images, first_slot):
+        """Output slot per image, flat over (model, image): a running index from `first_slot` over the images of
+        the models whose flux is part of the linear solve, -1 for the others (they own no basis image:
+        point_source.py:296,361,398 skip them).  -> (slots, number of slots used)"""
+        slots, used = [], 0
+        for n, f in zip(num_images, self._flux_from_point_source_list):
+            for _ in range(int(n)):
+                if f:
+                    slots.append(first_slot + used)
+                    used += 1
+                else:
+                    slots.append(-1)
+        return slots, used
+
     def num_basis(self, kwargs_ps, kwargs_lens=None):
         """point_source.py:286-302"""
         return sum(n for n, f in zip(self.num_images(kwargs_ps), self._flux_from_point_source_list) if f)

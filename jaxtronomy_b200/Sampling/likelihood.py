@@ -90,6 +90,11 @@ class LikelihoodModule(object):
                 if lm is None:
                     raise ValueError("the source-position likelihood needs the lens model: build PointSource with "
                                      "lens_model=..., or pass source_position_likelihood=False")
+                if getattr(lm, "multi_plane", False):
+                    # the penalty needs the lensing Jacobian at every image; lsim_source_position_logl has it for
+                    # single-plane models only (the reference differences MultiPlane.alpha, multi_plane.py:537-589)
+                    raise ValueError("the source-position likelihood of a multi-plane lens model is not supported: "
+                                     "pass source_position_likelihood=False")
                 self._pos_plan = _lib.Plan(self._n, lens_descs=lm.lens_descs(None, source_fn=fn), **lm.plan_kwargs())
         elif source_position_likelihood or image_position_likelihood:
             raise ValueError("position likelihoods need an image model with a point-source class")

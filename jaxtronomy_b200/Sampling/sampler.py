@@ -25,10 +25,17 @@ def prepare_logL_func(backend, likelihood_module, threadCount=1, world_size=1, r
     def new_logL_func(args):
         import torch
 
-        pos = torch.as_tensor(np.ascontiguousarray(args, dtype=np.float64)).to("cuda")
+        args = np.ascontiguousarray(args, dtype=np.float64)
         if world_size == 1:
+            pos = torch.as_tensor(args).to("cuda")
             return likelihood_module.logL_batch_device(pos).cpu().numpy().flatten()
-        full = parallel.sharded_logl(likelihood_module.logL_batch_device, pos, world_size, rank)
+        # only this rank's rows cross PCIe; the all-gather returns every particle's logL to every rank
+        B = args.shape[0]
+        lo, hi = parallel.shard_bounds(B, world_size, rank)
+        full = torch.empty(B, dtype=torch.float64, device="cuda")
+        if hi > lo:
+            full[lo:hi] = likelihood_module.logL_batch_device(torch.as_tensor(args[lo:hi]).to("cuda"))
+        parallel.all_gather_logl(full, world_size, rank, B)
         return full.cpu().numpy().flatten()
 
     return new_logL_func

@@ -305,7 +305,10 @@ class ImageModel:
     def __init__(self, data_class, psf_class, lens_model_list=None, source_model_list=None,
                  lens_light_model_list=None, kwargs_numerics=None, likelihood_mask=None,
                  lens_profile_kwargs_list=None, point_source_type_list=None, psf_variance_map=None,
-                 psf_error_map_bool_list=None):
+                 psf_error_map_bool_list=None, multi_plane=None):
+        # multi_plane: None, or the host constants of MultiPlane (sorted_index, T_ij_list, T_z_list, reduced2physical,
+        # T_ij_stop, T_z_source) -- LensModel(multi_plane=True) inside the image model, multi_plane.py:236-275
+        self._multi_plane = multi_plane
         # point sources: UNLENSED / LENSED_POSITION without fixed magnification -- positions and amplitudes are the
         # parameters themselves (PointSource/Types/unlensed.py, lensed_position.py)
         self.point_source_type_list = list(point_source_type_list or [])
@@ -331,6 +334,12 @@ class ImageModel:
 
     # --- image_model.py:223-393 ---
     def _ray_shoot(self, x, y, kwargs_lens):
+        if self._multi_plane is not None:
+            mp = self._multi_plane
+            return _lens.ray_shooting_multi_plane(
+                self.lens_model_list, x, y, kwargs_lens, [int(i) for i in mp["sorted_index"]], mp["T_ij_list"],
+                mp["T_z_list"], mp["reduced2physical"], float(mp["T_ij_stop"]), float(mp["T_z_source"]),
+                profile_kwargs_list=self.lens_profile_kwargs_list)
         return _lens.ray_shooting(self.lens_model_list, x, y, kwargs_lens or [],
                                   profile_kwargs_list=self.lens_profile_kwargs_list)
 

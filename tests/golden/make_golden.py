@@ -695,7 +695,158 @@ def gen_position_likelihood():
     st.save("position_likelihood.npz")
 
 
+# ------------------------------------------------------------------------------------------------
+def gen_baseline_shapes():
+    """Fixtures at the BASELINE.json shapes themselves (not shrunk), from the unmodified reference:
+    headline (EPL+SHEAR, SERSIC_ELLIPSE, 180x180, ss 3, 21x21 pixel PSF, ImageLinearFit) for parameter sets in every
+    nmax bracket of epl.py:308-319; C3 (EPL_MULTIPOLE_M1M3M4+SHEAR, n_lin 2); C4 (1 EPL + 1,000 TNFW, 10^4 rays of
+    the 1000x1000 grid); C5 (multi-plane EPL / NFW_ELLIPSE_CSE / SIS inside MultiLinear over 4 bands).
+    The static inputs are the ones bench.py / tools/bench_configs.py use, so the instantiations checked are the ones timed."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from bench import LENS_LIST, SOURCE_LIST, TRUTH, psf_kernel, row_to_kwargs, sample_params, static_config
+    from jaxtronomy.ImSim.MultiBand.multi_linear import MultiLinear
+
+    st = Store()
+    cp = lambda kws: [dict(k) for k in kws]  # noqa: E731
+    sc = static_config()
+    psf = PSF(psf_type="PIXEL", kernel_point_source=sc["kernel"])
+    num_kw = dict(supersampling_factor=3, supersampling_convolution=False)
+
+    # ---- headline: 10 parameter sets, |e| chosen per nmax bracket (10, 10, 20, 20, 20, 35, 35, 50, 50, 100 terms)
+    lens, src, none = LensModel(LENS_LIST), LightModel(SOURCE_LIST), LightModel([])
+    im0 = ImageModel(ImageData(image_data=np.zeros((180, 180)), **sc["kwargs_data"]), psf, lens, src, none,
+                     kwargs_numerics=num_kw)
+    truth = np.asarray(im0.image(*row_to_kwargs(TRUTH)))
+    rng = np.random.default_rng(0)
+    noisy = truth + rng.normal(0, 0.05, truth.shape) + rng.normal(0, 1, truth.shape) * np.sqrt(np.maximum(truth, 0) / 100.0)
+    data = ImageData(image_data=noisy, **sc["kwargs_data"])
+    im = ImageModel(data, psf, lens, src, none, kwargs_numerics=num_kw)
+    lin = ImageLinearFit(data, psf, lens, src, none, kwargs_numerics=num_kw)
+    rows = sample_params(10, seed=2026)
+    emods = [0.05, 0.11, 0.2, 0.3, 0.39, 0.45, 0.55, 0.65, 0.72, 0.8]
+    ang = np.random.default_rng(5).uniform(0, 2 * np.pi, 10)
+    rows[:, 2], rows[:, 3] = emods * np.cos(ang), emods * np.sin(ang)
+    st.add("headline_static", dict(image_data=noisy, kernel=sc["kernel"], rows=rows, truth_row=TRUTH), dict(truth=truth),
+           dict(lens_model_list=LENS_LIST, source_model_list=SOURCE_LIST, kwargs_numerics=num_kw, e_moduli=emods))
+    for b, row in enumerate(rows):
+        kl, ks, kll = row_to_kwargs(row)
+        outs = dict(image_unconvolved=np.asarray(im.image(kl, ks, kll, unconvolved=True)),
+                    A=np.asarray(lin.linear_response_matrix(kl, cp(ks), cp(kll), None)),
+                    logL=float(im.likelihood_data_given_model(kl, ks, kll)))
+        model, _, _, param = lin.image_linear_solve(kl, cp(ks), cp(kll))
+        logL_lin, _ = lin.likelihood_data_given_model(kl, cp(ks), cp(kll))
+        outs.update(param=np.asarray(param), logL_linear=float(logL_lin))
+        if b in (0, 7):
+            outs.update(wls_model=np.asarray(model), image=np.asarray(im.image(kl, ks, kll)))
+        st.add("headline_%02d" % b, dict(row=row), outs)
+
+    # ---- C3: EPL_MULTIPOLE_M1M3M4 + SHEAR, SERSIC_ELLIPSE source + lens light (n_lin 2), same frame / PSF
+    lens3, ll3 = LensModel(["EPL_MULTIPOLE_M1M3M4", "SHEAR"]), LightModel(["SERSIC_ELLIPSE"])
+    kl3 = [dict(theta_E=1.2, gamma=2.0, e1=0.2, e2=-0.1, center_x=0.0, center_y=0.0, a1_a=0.01, delta_phi_m1=0.1,
+                a3_a=0.01, delta_phi_m3=0.1, a4_a=0.01, delta_phi_m4=0.1), dict(gamma1=0.03, gamma2=0.01, ra_0=0, dec_0=0)]
+    ks3 = [dict(amp=1.0, R_sersic=0.3, n_sersic=2.0, e1=0.1, e2=0.1, center_x=0.05, center_y=0.0)]
+    kll3 = [dict(amp=1.0, R_sersic=0.6, n_sersic=3.0, e1=0.05, e2=0.0, center_x=0.0, center_y=0.0)]
+    im0 = ImageModel(ImageData(image_data=np.zeros((180, 180)), **sc["kwargs_data"]), psf, lens3, src, ll3,
+                     kwargs_numerics=num_kw)
+    truth3 = np.asarray(im0.image(kl3, [dict(ks3[0], amp=20.0)], [dict(kll3[0], amp=30.0)]))
+    noisy3 = truth3 + rng.normal(0, 0.05, truth3.shape) + rng.normal(0, 1, truth3.shape) * np.sqrt(np.maximum(truth3, 0) / 100.0)
+    data3 = ImageData(image_data=noisy3, **sc["kwargs_data"])
+    lin3 = ImageLinearFit(data3, psf, lens3, src, ll3, kwargs_numerics=num_kw)
+    im3 = ImageModel(data3, psf, lens3, src, ll3, kwargs_numerics=num_kw)
+    st.add("c3_static", dict(image_data=noisy3, kernel=sc["kernel"]), dict(),
+           dict(lens_model_list=["EPL_MULTIPOLE_M1M3M4", "SHEAR"], source_model_list=["SERSIC_ELLIPSE"],
+                lens_light_model_list=["SERSIC_ELLIPSE"], kwargs_numerics=num_kw))
+    rng3 = np.random.default_rng(33)
+    for b in range(3):
+        kl = [dict(kl3[0]), dict(kl3[1])]
+        for k, s in (("theta_E", 0.03), ("gamma", 0.05), ("e1", 0.1), ("e2", 0.1), ("a1_a", 0.01), ("a3_a", 0.01),
+                     ("a4_a", 0.01), ("delta_phi_m1", 0.3), ("delta_phi_m3", 0.3), ("delta_phi_m4", 0.3),
+                     ("center_x", 0.02), ("center_y", 0.02)):
+            kl[0][k] = float(kl[0][k] + s * rng3.normal())
+        ks = [dict(ks3[0], R_sersic=float(0.3 + 0.05 * rng3.normal()), n_sersic=float(2.0 + 0.3 * rng3.normal()))]
+        kll = [dict(kll3[0], R_sersic=float(0.6 + 0.05 * rng3.normal()), e1=float(0.05 + 0.05 * rng3.normal()))]
+        model, _, _, param = lin3.image_linear_solve(kl, cp(ks), cp(kll))
+        logL_lin, _ = lin3.likelihood_data_given_model(kl, cp(ks), cp(kll))
+        st.add("c3_%02d" % b, dict(), dict(A=np.asarray(lin3.linear_response_matrix(kl, cp(ks), cp(kll), None)),
+                                          image_unconvolved=np.asarray(im3.image(kl, ks, kll, unconvolved=True)),
+                                          param=np.asarray(param), logL_linear=float(logL_lin)),
+               dict(kwargs_lens=kl, kwargs_source=ks, kwargs_lens_light=kll))
+
+    # ---- C4: 1 EPL + 1,000 TNFW, every 10th row / column of the 1000 x 1000 ray grid (10^4 rays)
+    rng4 = np.random.default_rng(3)
+    nh = 1000
+    names = ["EPL"] + ["TNFW"] * nh
+    kws = [dict(theta_E=1.0, gamma=2.0, e1=0.1, e2=0.1, center_x=0.0, center_y=0.0)]
+    kws += [dict(Rs=float(rng4.uniform(0.01, 0.1)), alpha_Rs=float(rng4.uniform(1e-4, 5e-3)),
+                 r_trunc=float(rng4.uniform(0.05, 0.5)), center_x=float(rng4.uniform(-2, 2)),
+                 center_y=float(rng4.uniform(-2, 2))) for _ in range(nh)]
+    g = np.linspace(-2, 2, 1000)[5::10]
+    xx, yy = np.meshgrid(g, g)
+    lmb = LensModelBulk(["EPL", "TNFW"], multi_plane=False)
+    rs_kw = lmb.prepare_ray_shooting_kwargs(names, kws)
+    bx, by = lmb.ray_shooting(xx.ravel(), yy.ravel(), rs_kw)
+    st.add("c4_substructure", dict(x=xx.ravel(), y=yy.ravel(), index_list=rs_kw["index_list"],
+                                   **{"kw_" + k: v for k, v in rs_kw["all_kwargs"].items()}),
+           dict(beta_x=np.asarray(bx), beta_y=np.asarray(by)),
+           dict(unique_lens_model_list=["EPL", "TNFW"], n_halos=nh, kwargs_epl=kws[0]))
+
+    # ---- C5: multi-plane (EPL z=0.5, NFW_ELLIPSE_CSE z=0.3, SIS z=0.8; source z=1.5) inside MultiLinear, 4 bands
+    rng5 = np.random.default_rng(4)
+    km = dict(lens_model_list=["EPL", "NFW_ELLIPSE_CSE", "SIS"], lens_redshift_list=[0.5, 0.3, 0.8], z_source=1.5,
+              multi_plane=True, source_light_model_list=["SERSIC_ELLIPSE"], lens_light_model_list=["SERSIC_ELLIPSE"])
+    kl5 = [dict(theta_E=1.1, gamma=2.0, e1=0.1, e2=-0.1, center_x=0.0, center_y=0.0),
+           dict(Rs=1.5, alpha_Rs=0.2, e1=0.05, e2=0.05, center_x=0.3, center_y=-0.2),
+           dict(theta_E=0.1, center_x=-0.5, center_y=0.4)]
+    ks5 = [dict(amp=1.0, R_sersic=0.3, n_sersic=2.0, e1=0.1, e2=0.1, center_x=0.05, center_y=0.0)]
+    kll5 = [dict(amp=1.0, R_sersic=0.6, n_sersic=3.0, e1=0.05, e2=0.0, center_x=0.0, center_y=0.0)]
+    band_kernels = [psf_kernel(11, 1.5 + 0.2 * b) for b in range(4)]
+    band_num = [dict(supersampling_factor=1), dict(supersampling_factor=1), dict(supersampling_factor=2),
+                dict(supersampling_factor=1)]
+
+    def bands_for(images):
+        return [[dict(sc["kwargs_data"], image_data=images[b]), dict(psf_type="PIXEL", kernel_point_source=band_kernels[b]),
+                 band_num[b]] for b in range(4)]
+
+    ml0 = MultiLinear(bands_for([np.zeros((180, 180))] * 4), km)
+    images = []
+    for b in range(4):
+        t = np.asarray(ml0._imageModel_list[b].image(kl5, [dict(ks5[0], amp=15.0 + 3 * b)], [dict(kll5[0], amp=25.0 - 2 * b)]))
+        images.append(t + rng5.normal(0, 0.05, t.shape) + rng5.normal(0, 1, t.shape) * np.sqrt(np.maximum(t, 0) / 100.0))
+    ml = MultiLinear(bands_for(images), km)
+    base = ml._imageModel_list[0].LensModel.lens_model.multi_plane_base
+    mp = ml._imageModel_list[0].LensModel.lens_model
+    ins = dict(sorted_index=np.asarray(base.sorted_redshift_index), T_ij_list=np.asarray(base.T_ij_list, dtype=float),
+               T_z_list=np.asarray(base.T_z_list, dtype=float),
+               reduced2physical=np.asarray(base._reduced2physical_factor, dtype=float),
+               T_ij_stop=float(mp.T_ij_stop), T_z_source=float(mp._T_z_source))
+    for b in range(4):
+        ins["image_data_%d" % b], ins["kernel_%d" % b] = images[b], band_kernels[b]
+    st.add("c5_static", ins, dict(), dict(kwargs_model=km, band_numerics=band_num))
+    for s in range(3):
+        kl = [dict(k) for k in kl5]
+        for i, k, sig in ((0, "theta_E", 0.02), (0, "gamma", 0.05), (0, "e1", 0.05), (0, "center_x", 0.01),
+                          (1, "alpha_Rs", 0.02), (1, "Rs", 0.1), (1, "e2", 0.03), (2, "theta_E", 0.02), (2, "center_y", 0.05)):
+            kl[i][k] = float(kl[i][k] + sig * rng5.normal())
+        ks = [dict(ks5[0], R_sersic=float(0.3 + 0.03 * rng5.normal()), center_x=float(0.05 + 0.02 * rng5.normal()))]
+        logL, params = ml.likelihood_data_given_model(kl, cp(ks), cp(kll5))
+        outs = dict(logL=float(logL))
+        for b in range(4):
+            outs["param_%d" % b] = np.asarray(params[b])
+            lb, _ = ml._imageModel_list[b].likelihood_data_given_model(kl, cp(ks), cp(kll5))
+            outs["logL_%d" % b] = float(lb)
+        if s == 0:
+            for b in range(4):
+                outs["A_%d" % b] = np.asarray(ml._imageModel_list[b].linear_response_matrix(kl, cp(ks), cp(kll5), None))
+        else:
+            outs["A_2"] = np.asarray(ml._imageModel_list[2].linear_response_matrix(kl, cp(ks), cp(kll5), None))
+        st.add("c5_%02d" % s, dict(), outs, dict(kwargs_lens=kl, kwargs_source=ks, kwargs_lens_light=kll5))
+    st.save("baseline_shapes.npz")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["baseline_shapes"]:
+        gen_baseline_shapes()
+        sys.exit(0)
     if sys.argv[1:] == ["position_likelihood"]:
         gen_position_likelihood()
         sys.exit(0)
@@ -711,3 +862,4 @@ if __name__ == "__main__":
     gen_point_sources()
     gen_hessians()
     gen_position_likelihood()
+    gen_baseline_shapes()

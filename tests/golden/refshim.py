@@ -455,8 +455,12 @@ def _make_lenstronomy():
             return self._light_model.functions_split(bx, by, kwargs_source)
 
     class DifferentialExtinction(object):
-        def __init__(self, optical_depth_model=None, tau0_index=0):
+        def __init__(self, optical_depth_model=None, tau0_index=0, **kwargs):
             pass
+
+        @property
+        def compute_bool(self):  # image_model.py consults this; no extinction model on the path
+            return False
 
     class Background(object):
         """lenstronomy.Cosmo.background.Background for a flat LCDM (matter + Lambda) stand-in cosmology.

@@ -137,7 +137,9 @@ def c4():
 
 
 def c5():
-    """3 planes (EPL, NFW_ELLIPSE_CSE, SIS), 4 bands of 180x180 (ss 1), 4096 sets, multi-band linear likelihood."""
+    """3 planes (EPL, NFW_ELLIPSE_CSE, SIS), 4 bands of 180x180 (ss 1, 1, 2, 1), 4096 sets, multi-band linear
+    likelihood; model, redshifts, PSFs and numerics are the ones of the reference fixture c5_* (parity:
+    tests/test_gpu_baseline_shapes.py)."""
     rng = np.random.default_rng(4)
     km = dict(lens_model_list=["EPL", "NFW_ELLIPSE_CSE", "SIS"], lens_redshift_list=[0.5, 0.3, 0.8], z_source=1.5,
               multi_plane=True, source_light_model_list=["SERSIC_ELLIPSE"], lens_light_model_list=["SERSIC_ELLIPSE"])
@@ -145,8 +147,9 @@ def c5():
     bands = []
     for b in range(4):
         kd = dict(st["kwargs_data"], image_data=rng.normal(0, 0.05, (180, 180)) + 0.1)
+        # numerics per band as in tests/golden/baseline_shapes.npz (c5_static): band 2 is supersampled
         bands.append([kd, dict(psf_type="PIXEL", kernel_point_source=psf_kernel(11, 1.5 + 0.2 * b)),
-                      dict(supersampling_factor=1)])
+                      dict(supersampling_factor=2 if b == 2 else 1)])
     ml = MultiLinear(bands, km)
     param = Param(km)
     like = LikelihoodModule(ml, param)
@@ -159,7 +162,7 @@ def c5():
     B = 4096
     pos = torch.as_tensor(x0[None, :] + rng.normal(0, 0.01, (B, x0.size)), device="cuda")
     ms = timed(lambda: like.logL_batch_device(pos), steps=2, warmup=1)
-    return dict(config="C5 multi-plane EPL+NFW_ELLIPSE_CSE+SIS, 4 bands 180x180 ss1, 4096 sets", ms=ms,
+    return dict(config="C5 multi-plane EPL+NFW_ELLIPSE_CSE+SIS, 4 bands 180x180 ss 1/1/2/1, 4096 sets", ms=ms,
                 band_images_per_s=4 * B / ms * 1e3, sets_per_s=B / ms * 1e3)
 
 
@@ -261,6 +264,9 @@ def mixed():
     ms = timed(lambda: cfg["model"].logL_linear_batch(p))
     return dict(config="headline with e1,e2 ~ U(-0.5,0.5) (mixed nmax), 16384 sets", ms=ms, images_per_s=B / ms * 1e3,
                 nmax_histogram={int(k): int((nmax == k).sum()) for k in np.unique(nmax)})
+
+
+CONFIGS = {"c2": c2, "c3": c3, "c4": c4, "c5": c5, "mixed": mixed}  # what bench.py reports under "secondary"
 
 
 if __name__ == "__main__":
