@@ -291,33 +291,44 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
     double acc[NSLOT];
 #pragma unroll
     for (int k = 0; k < NSLOT; ++k) acc[k] = 0.0;
-    for (int i = 0; i < ss; ++i) {
+    // coordinates of the pixel's first sub-pixel; one row further per i (no index arithmetic inside the loops)
+    const int64_t base0 = ((int64_t)py * ss) * sub_stride + (int64_t)px * ss;
+    const double* xrow = P.x_sub + base0;
+    const double* yrow = P.y_sub + base0;
+    for (int i = 0; i < ss; ++i, xrow += sub_stride, yrow += sub_stride) {
       double racc[NSLOT];
 #pragma unroll
       for (int k = 0; k < NSLOT; ++k) racc[k] = 0.0;
-      const int64_t base = ((int64_t)py * ss + i) * sub_stride + (int64_t)px * ss;
+      const int64_t base = base0 + i * sub_stride;  // (only the sub-pixel outputs of SUB use it)
       for (int j0 = 0; j0 < ss; j0 += J) {
         constexpr bool kSingle = LT::N >= 0;  // specialised kernels are single-plane
         double x[J], y[J], bx[J], by[J], v[J];
         Rays<J> r;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-          x[j] = __ldg(P.x_sub + base + j0 + j);
-          y[j] = __ldg(P.y_sub + base + j0 + j);
+          x[j] = __ldg(xrow + j0 + j);
+          y[j] = __ldg(yrow + j0 + j);
           ray_init<J, kSingle>(P.ray, j, x[j], y[j], r);
         }
-        ray_apply<FULL, J, LT>(P.ray, L, pool, P.n_lens, r);
         if (kSingle) {
-          // the image-plane coordinates are needed again only now (beta = theta - alpha, unlensed light): read them
-          // a second time (L1 hit) instead of keeping 4 J registers alive across the deflector evaluation
+          // the image-plane coordinates are needed again only after the series (cheap profiles, beta = theta - alpha,
+          // unlensed light): read them a second time (L1 hit) instead of keeping 4 J registers alive across it
+          ray_apply_head<FULL, J, LT>(L, pool, r);
 #pragma unroll
           for (int j = 0; j < J; ++j) {
-            x[j] = ldg_again(P.x_sub + base + j0 + j);
-            y[j] = ldg_again(P.y_sub + base + j0 + j);
-            bx[j] = x[j] - r.ax[j] * P.ray.alpha_scaling;
-            by[j] = y[j] - r.ay[j] * P.ray.alpha_scaling;
+            x[j] = ldg_again(xrow + j0 + j);
+            y[j] = ldg_again(yrow + j0 + j);
+            r.x[j] = x[j];
+            r.y[j] = y[j];
+          }
+          ray_apply_tail<FULL, J, LT>(L, pool, r);
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            bx[j] = fma(-r.ax[j], P.ray.alpha_scaling, x[j]);
+            by[j] = fma(-r.ay[j], P.ray.alpha_scaling, y[j]);
           }
         } else {
+          ray_apply<FULL, J, LT>(P.ray, L, pool, P.n_lens, r);
 #pragma unroll
           for (int j = 0; j < J; ++j) ray_finish(P.ray, r, j, bx[j], by[j]);
         }
@@ -325,11 +336,23 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
         auto one_light = [&](int type, const LightC& Gg) {
           const int slot = Gg.slot;
           if (slot < 0) return;
+          if (!SUB) {  // the amplitude and the sum over the J sub-pixels ride on the accumulation FMAs
+            double vs = 0.0;
+            if (Gg.lensed)
+              light_accum<J>(type, Gg, bx, by, NSLOT == 1 ? racc[0] : vs);
+            else
+              light_accum<J>(type, Gg, x, y, NSLOT == 1 ? racc[0] : vs);
+            if (NSLOT > 1) {
+#pragma unroll
+              for (int k = 0; k < NSLOT; ++k) racc[k] += (slot == k) ? vs : 0.0;
+            }
+            return;
+          }
           if (Gg.lensed)
             light_eval<J>(type, Gg, bx, by, v);
           else
             light_eval<J>(type, Gg, x, y, v);
-          if (SUB) {  // supersampled convolution: keep the sub-pixel fluxes [set][slot][ny ss][nx ss]
+          {  // supersampled convolution: keep the sub-pixel fluxes [set][slot][ny ss][nx ss]
             double* dsub = sub_out + (bl * P.n_slots + slot) * ((int64_t)npix * ss * ss) + base + j0;
 #pragma unroll
             for (int j = 0; j < J; ++j) dsub[j] = ((written >> slot) & 1u) ? dsub[j] + v[j] : v[j];

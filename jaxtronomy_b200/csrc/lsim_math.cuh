@@ -89,17 +89,16 @@ LSIM_HD double nan_to_num(double v, double p, double n) {
 }
 LSIM_HD double nan_to_num(double v) { return nan_to_num(v, DBL_MAX, -DBL_MAX); }
 
-// 1/x for finite, normal, non-zero x (no special cases): MUFU.RCP64H seed (XU pipe) + two Newton steps.
-// x = 0 gives +-inf / nan exactly like a true division would for the callers' purposes (nan_to_num follows).
+// 1/x for finite, normal, non-zero x (no special cases): MUFU.RCP64H seed (XU pipe, relative error <= 2^-23) and ONE
+// third-order step r (1 + e + e^2), e = 1 - x r: 3 DFMA instead of the 4 of two Newton steps, error e^3 ~ 2^-69 before
+// the final rounding.  x = 0 gives +-inf / nan exactly like a true division would for the callers' purposes
+// (nan_to_num follows).
 LSIM_HD double rcp_fast(double x) {
 #if defined(__CUDA_ARCH__)
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
 #else
   return 1.0 / x;
 #endif
@@ -213,6 +212,52 @@ LSIM_HD double exp2_neg(double x) {
   const uint32_t hx = (uint32_t)((uint64_t)d2i(x) >> 32);
   const bool low = (uint32_t)(hx - 0xC08FF000u) <= (0xFFF00000u - 0xC08FF000u);  // -inf <= x <= -1022, not nan
   return exp2_core(low ? -1022.0 : x);
+}
+
+// ---- exp2 of a PRE-SCALED argument: y = 256 x -------------------------------------------------------------------
+// The hot profiles compute their exponents with one FMA from prepared constants; folding the factor 256 of the table
+// index into those constants removes the multiplication at the head of exp2_core, and the reduced argument becomes a
+// subtraction: k = rint(y), r' = y - k (exact), 2^x = 2^(k>>8) T[k&255] (1 + r' P'(r')) with the coefficients of P'
+// scaled by powers of 256 (exact), so the result is bit-identical to exp2_core(y / 256).  6 fp64 instructions.
+LSIM_TABLE kExp2S[4] = {kLn2 * kLn2 * kLn2 * kLn2 / 24.0 / 4294967296.0, kLn2 * kLn2 * kLn2 / 6.0 / 16777216.0,
+                        kLn2 * kLn2 / 2.0 / 65536.0, kLn2 / 256.0};
+
+LSIM_HD double exp2_core_s(double y) {
+#if !defined(__CUDA_ARCH__)
+  if (y != y) return y;
+#endif
+  const double kf = rint(y);
+  const int ki = (int)kf;
+  const double r = y - kf;  // exact: |r| <= 1/2 and both are multiples of ulp(y)
+  double p = fma(kExp2S[0], r, kExp2S[1]);
+  p = fma(p, r, kExp2S[2]);
+  p = fma(p, r, kExp2S[3]);
+#if defined(__CUDA_ARCH__)
+  const double T = s_exp2_tab[ki & (LSIM_EXP2_N - 1)];
+#else
+  const double T = h_exp2_tab[ki & (LSIM_EXP2_N - 1)];
+#endif
+  const double t = fma(T * r, p, T);
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(t) + ((ki >> 8) << 20), __double2loint(t));
+#else
+  return i2d(d2i(t) + ((int64_t)(ki >> 8) << 52));
+#endif
+}
+
+// 256 * 1022 = 261632.0 = 0x410FF000_00000000 (same mantissa as 1022: the clamps still compare the high word only)
+LSIM_HD double exp2_fin_s(double y) {
+  const int64_t iy = d2i(y);
+  const uint32_t hy = (uint32_t)((uint64_t)iy >> 32), ay = hy & 0x7fffffffu;
+  const bool big = (uint32_t)(ay - 0x410FF000u) <= (0x7ff00000u - 0x410FF000u);  // 1022 <= |y|/256 <= inf, not nan
+  const double yc = big ? i2d((int64_t)(((uint64_t)((hy & 0x80000000u) | 0x410FF000u)) << 32)) : y;
+  return exp2_core_s(yc);
+}
+
+LSIM_HD double exp2_neg_s(double y) {
+  const uint32_t hy = (uint32_t)((uint64_t)d2i(y) >> 32);
+  const bool low = (uint32_t)(hy - 0xC10FF000u) <= (0xFFF00000u - 0xC10FF000u);  // -inf <= y/256 <= -1022, not nan
+  return exp2_core_s(low ? -261632.0 : y);
 }
 
 }  // namespace lsim

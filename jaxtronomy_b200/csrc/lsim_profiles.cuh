@@ -38,7 +38,7 @@ struct LensC {
   int32_t n_coef;    // EPL family: number of series coefficients actually used
   int32_t coef_off;  // EPL family: offset of this profile's coefficients in the coefficient pool
   double delta_T, inv_T_z, red2phys;  // multi-plane stepping
-  double c[24];
+  double c[30];
 };
 
 struct LightC {
@@ -46,7 +46,7 @@ struct LightC {
   int32_t lensed;
   int32_t slot;
   int32_t pad;
-  double c[12];
+  double c[14];
 };
 
 // ---- CSE tables: device copies live in constant memory, host copies are the header arrays -------------
@@ -108,7 +108,8 @@ LSIM_HD int epl_nmax(double f) {
   return 500;
 }
 
-// EPL family constants.  c[0..8]: cx, cy, cos(phi), sin(phi), q, f, -t/2, t*log2(b), 2/(1+q).
+// EPL family constants.  c[0..8]: cx, cy, cos(phi), sin(phi), q, f, -t/2, t*log2(b), 2/(1+q) (the closed-form Hessian
+// and the fp32 variant read these); c[19..28]: the folded constants epl_core works from (see there).
 // The reference evaluates 2F1(1, t/2; 2 - t/2; z) with the Lopez-Temme series truncated at nmax terms:
 //   2F1 = (1 - z/2)^-1 * sum_{n<nmax} F_n w^n,  w = z/(z-2),
 //   F_0 = 1, F_1 = 1 - 2b/c, F_n = ((n-1) F_{n-2} - (2b-c) F_{n-1}) / (c+n-1)   (hyp2f1_util.py:152-176, a = 1)
@@ -131,6 +132,18 @@ LSIM_HD void epl_prepare(LensC& L, double* coef, double theta_E, double gamma, d
   L.c[6] = -0.5 * t;
   L.c[7] = t * log2(b);
   L.c[8] = 2.0 / (1.0 + q);
+  // epl_core: Z = a + i c with a = q x', c = y' straight from the sky coordinates (shift and rotation folded)
+  const double fe = f > 1e-150 ? f : 1e-150;  // q = 1: every f-dependent term vanishes like f; keep the ratios finite
+  L.c[19] = q * L.c[2];
+  L.c[20] = q * L.c[3];
+  L.c[21] = -(L.c[19] * cx + L.c[20] * cy);
+  L.c[22] = L.c[3] * cx - L.c[2] * cy;
+  L.c[23] = 0.5 * fe;
+  L.c[24] = (4.0 - f * f) / (4.0 * fe);
+  L.c[25] = -0.25 * fe;
+  L.c[26] = (2.0 - f) / (2.0 + f);
+  L.c[27] = 256.0 * L.c[6];
+  L.c[28] = 256.0 * (L.c[7] + log2((2.0 + f) / (fe * (1.0 + q))));
   int nmax = epl_nmax(f);
   double B = t / 2.0, C = 2.0 - B;
   coef[0] = 1.0;
@@ -156,48 +169,44 @@ LSIM_HD void epl_prepare(LensC& L, double* coef, double theta_E, double gamma, d
   L.n_coef = n_used;
 }
 
-// Deflection of the EPL for J points at once (already shifted by the centre).  J independent points are
-// evaluated in lock step so that the series coefficients are read from shared memory once per J points and
-// the compiler can interleave J independent FMA chains.
+// Deflection of the EPL for J points at once.  J independent points are evaluated in lock step so that the series
+// coefficients are read from shared memory once per J points and the compiler can interleave J independent FMA chains.
 //
-// Tessore & Metcalf eq. 22/23 reorganised so that the only non-FMA work per point is one reciprocal, one
-// log2 and one exp2:  with Z = q x' + i y', R2 = |Z|^2, D = f Z^2 + 2 R2:
-//   w = f Z^2 conj(D)/|D|^2,  (1 - z/2)^-1 = 2 R2 conj(D)/|D|^2,  (b/R)^t = exp2(t log2 b - t/2 log2 R2)
-// The series S = sum_n F_n w^n has REAL coefficients, so it is summed with the quadratic-factor (Goertzel /
-// Clenshaw) recurrence  b_k = F_k + p b_{k+1} - |w|^2 b_{k+2},  p = 2 Re w,  S = F_0 - |w|^2 b_2 + b_1 w:
-// two real FMAs per term instead of the four of a complex Horner step.  |w| <= f/(2-f) < 1, so the
-// recurrence is contractive (its characteristic roots are w and conj(w)).
+// Tessore & Metcalf eq. 22/23, reorganised.  With Z = a + i c (a = q x', c = y'), R2 = |Z|^2, U = Z^2 and the series
+// argument w = z/(z-2), z = -f Z/conj(Z):
+//   w = f (f R2 + 2 U)/E,  E = (4 + f^2) R2 + 4 f Re U  (>= (2-f)^2 R2),  |w|^2 = f^2 R2/E,
+//   Z (1 - z/2)^-1 = (2 R2/E) ((2+f) a + i (2-f) c),
+// so one reciprocal (of E/4f), one log2 and one exp2 are the only non-FMA work per point:
+//   n = Re U + (f/2) R2,  Et = n + ((4-f^2)/4f) R2 = E/4f,  iE = 1/Et,
+//   2 Re w = n iE,  Im w = a c iE,  h = R2 iE,  -|w|^2 = -(f/4) h,
+//   alpha' = s (a S_r - rho c S_i, a S_i + rho c S_r),  rho = (2-f)/(2+f),
+//   s = h exp2(-t/2 log2 R2 + t log2 b + log2((2+f)/(f (1+q))))        [= 2/(1+q) (b/R)^t 2 R2 (2+f)/E]
+// (every constant factor of the power law lives in the exponent).  The series S = sum_n F_n w^n has REAL
+// coefficients and is summed with the quadratic-factor (Goertzel / Clenshaw) recurrence
+// b_k = F_k + p b_{k+1} - |w|^2 b_{k+2}, p = 2 Re w, S = F_0 - |w|^2 b_2 + b_1 w: two real FMAs per term instead of the
+// four of a complex Horner step; |w| <= f/(2-f) < 1, so the recurrence is contractive.
+// Output: the deflection in the sky frame is  s[j] * (u1[j], u2[j])  (the caller folds s into its accumulation FMA).
+// Non-finite results (Z = 0) follow the reference: nan_to_num(posinf=1e10, neginf=-1e10) on the major-axis
+// components (epl.py:391-392), one test for all J points; then s = 1 and (u1, u2) is the rotated, cleaned deflection.
 template <int J>
-LSIM_HD void epl_eval(const LensC& L, const double* coef, const double (&xs)[J], const double (&ys)[J],
-                      double (&ax)[J], double (&ay)[J]) {
-  const double cph = L.c[2], sph = L.c[3], q = L.c[4], f = L.c[5];
-  // Only seven values per point stay live across the series loop: everything that multiplies the series
-  // (Z, (1 - z/2)^-1, the radial power law) is folded into one complex prefactor G beforehand.
-  double wi[J], gr[J], gi[J], pp[J], qq[J], b1[J], b2[J];
+LSIM_HD void epl_core(const LensC& L, const double* coef, const double (&a)[J], const double (&c)[J], double (&s)[J],
+                      double (&u1)[J], double (&u2)[J]) {
+  // seven values per point stay live across the series loop besides the recurrence state: a, c, s, Im w, p, -|w|^2
+  double wi[J], pp[J], qq[J], b1[J], b2[J];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int j = 0; j < J; ++j) {
-    const double xr = fma(ys[j], sph, xs[j] * cph);
-    const double c = fma(ys[j], cph, -(xs[j] * sph));
-    const double a = q * xr;
-    const double aa = a * a;
-    const double R2 = fma(c, c, aa);
-    const double z2r = fma(-c, c, aa), z2i = 2.0 * a * c;
-    const double R2x2 = R2 + R2;
-    const double Dr = fma(f, z2r, R2x2), Di = f * z2i;
-    const double inv = rcp_fast(fma(Dr, Dr, Di * Di));
-    const double finv = f * inv;
-    const double wr = fma(z2i, Di, z2r * Dr) * finv;  // Re(Z^2 conj D) f / |D|^2
-    wi[j] = fma(z2i, Dr, -(z2r * Di)) * finv;
+    const double aa = a[j] * a[j];
+    const double R2 = fma(c[j], c[j], aa);
+    const double n = fma(L.c[23], R2, fma(-c[j], c[j], aa));
+    const double iE = rcp_fast(fma(L.c[24], R2, n));
+    pp[j] = n * iE;
+    wi[j] = (a[j] * c[j]) * iE;
+    const double h = R2 * iE;
+    qq[j] = L.c[25] * h;
     const double R2c = max_nan(R2, 1e-18);  // R = max(|Z|, 1e-9)
-    const double P = L.c[8] * exp2_fin(fma(L.c[6], log2_pos(R2c), L.c[7]));
-    const double s2 = R2x2 * inv * P;
-    const double pr = s2 * Dr, pi = -(s2 * Di);  // P 2 R2 conj(D) / |D|^2
-    gr[j] = fma(a, pr, -(c * pi));               // ... times Z
-    gi[j] = fma(a, pi, c * pr);
-    pp[j] = wr + wr;
-    qq[j] = -fma(wr, wr, wi[j] * wi[j]);
+    s[j] = h * exp2_fin_s(fma(L.c[27], log2_pos(R2c), L.c[28]));
     b1[j] = 0.0;
     b2[j] = 0.0;
   }
@@ -212,37 +221,86 @@ LSIM_HD void epl_eval(const LensC& L, const double* coef, const double (&xs)[J],
       b1[j] = t;
     }
   }
-  const double c0 = coef[0];
-  double fr[J], fi[J];
-  uint32_t worst = 0;  // largest |high word| of the results: >= 0x7ff00000 <=> some component is inf / nan
+  const double c0 = coef[0], cph = L.c[2], sph = L.c[3], rho = L.c[26];
+  double tr[J], ti[J];
+  uint32_t worst = 0;  // largest |high word| of the factors: >= 0x7ff00000 <=> some factor is inf / nan
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int j = 0; j < J; ++j) {
     const double Sr = fma(b1[j], 0.5 * pp[j], fma(qq[j], b2[j], c0)), Si = b1[j] * wi[j];
-    // R_omega * (b/R)^t 2/(1+q) = G * S
-    fr[j] = fma(gr[j], Sr, -(gi[j] * Si));
-    fi[j] = fma(gr[j], Si, gi[j] * Sr);
-    const uint32_t hr = (uint32_t)((uint64_t)d2i(fr[j]) >> 32) & 0x7fffffffu;
-    const uint32_t hi = (uint32_t)((uint64_t)d2i(fi[j]) >> 32) & 0x7fffffffu;
-    worst = worst > hr ? worst : hr;
-    worst = worst > hi ? worst : hi;
+    const double cr = rho * c[j];
+    tr[j] = fma(a[j], Sr, -(cr * Si));
+    ti[j] = fma(a[j], Si, cr * Sr);
+    const uint32_t h0 = (uint32_t)((uint64_t)d2i(tr[j]) >> 32) & 0x7fffffffu;
+    const uint32_t h1 = (uint32_t)((uint64_t)d2i(ti[j]) >> 32) & 0x7fffffffu;
+    const uint32_t h2 = (uint32_t)((uint64_t)d2i(s[j]) >> 32) & 0x7fffffffu;
+    worst = worst > h0 ? worst : h0;
+    worst = worst > h1 ? worst : h1;
+    worst = worst > h2 ? worst : h2;
   }
-  if (worst >= 0x7ff00000u) {  // rare; one test for all J points: nan_to_num(posinf=1e10, neginf=-1e10), epl.py:391-392
+  if (worst >= 0x7ff00000u) {  // rare
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int j = 0; j < J; ++j) {
-      fr[j] = nan_to_num(fr[j], 1e10, -1e10);
-      fi[j] = nan_to_num(fi[j], 1e10, -1e10);
+      tr[j] = nan_to_num(s[j] * tr[j], 1e10, -1e10);
+      ti[j] = nan_to_num(s[j] * ti[j], 1e10, -1e10);
+      s[j] = 1.0;
     }
   }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int j = 0; j < J; ++j) {
-    ax[j] = fma(-fi[j], sph, fr[j] * cph);  // rotate(f, -phi)
-    ay[j] = fma(fi[j], cph, fr[j] * sph);
+    u1[j] = fma(-ti[j], sph, tr[j] * cph);  // rotate(f, -phi)
+    u2[j] = fma(ti[j], cph, tr[j] * sph);
+  }
+}
+
+// acc += w * alpha(x, y) for J sky positions.  UNIT: w == 1 at compile time (single-plane lensing).
+template <int J, bool UNIT>
+LSIM_HD void epl_accum(const LensC& L, const double* coef, const double (&x)[J], const double (&y)[J], double w,
+                       double (&accx)[J], double (&accy)[J]) {
+  double a[J], c[J], s[J], u1[J], u2[J];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    a[j] = fma(L.c[19], x[j], fma(L.c[20], y[j], L.c[21]));
+    c[j] = fma(L.c[2], y[j], fma(-L.c[3], x[j], L.c[22]));
+  }
+  epl_core<J>(L, coef, a, c, s, u1, u2);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    const double sw = UNIT ? s[j] : s[j] * w;
+    accx[j] = fma(sw, u1[j], accx[j]);
+    accy[j] = fma(sw, u2[j], accy[j]);
+  }
+}
+
+// Deflection at J points given relative to the profile centre (the form the closed-form Hessian and the multipole
+// variant use).
+template <int J>
+LSIM_HD void epl_eval(const LensC& L, const double* coef, const double (&xs)[J], const double (&ys)[J],
+                      double (&ax)[J], double (&ay)[J]) {
+  double a[J], c[J], s[J], u1[J], u2[J];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    a[j] = fma(L.c[19], xs[j], L.c[20] * ys[j]);
+    c[j] = fma(L.c[2], ys[j], -(L.c[3] * xs[j]));
+  }
+  epl_core<J>(L, coef, a, c, s, u1, u2);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    ax[j] = s[j] * u1[j];
+    ay[j] = s[j] * u2[j];
   }
 }
 
@@ -460,6 +518,8 @@ LSIM_HD void lens_prepare(const lsim_lens_desc& d, const double* row, LensC& L, 
       L.c[1] = P(3);
       L.c[2] = P(0);
       L.c[3] = P(1);
+      L.c[4] = -(L.c[2] * L.c[0] + L.c[3] * L.c[1]);  // alpha = (g1 x + g2 y + c4, g2 x - g1 y + c5)
+      L.c[5] = -(L.c[3] * L.c[0] - L.c[2] * L.c[1]);
       break;
     case LSIM_LENS_CONVERGENCE:
       L.c[0] = P(1);
@@ -716,6 +776,39 @@ LSIM_HD void lens_eval(int type, const LensC& L, const double* coef_pool, const 
   for (int j = 0; j < J; ++j) lens_eval1<FULL>(type, L, coef_pool, x[j], y[j], fx[j], fy[j]);
 }
 
+// acc += w * (reduced deflection of one profile) for J points.  UNIT: w == 1 at compile time.  The hot profiles fold
+// the weighted sum into their last FMAs; everything else goes through lens_eval.
+// CONST_DONE: the position-independent part of the profile (SHEAR: its origin term) is in the accumulators already.
+template <bool FULL, int J, bool UNIT, bool CONST_DONE = false>
+LSIM_HD void lens_accum(int type, const LensC& L, const double* coef_pool, const double (&x)[J], const double (&y)[J],
+                        double w, double (&accx)[J], double (&accy)[J]) {
+  if (type == LSIM_LENS_EPL) {
+    epl_accum<J, UNIT>(L, coef_pool + L.coef_off, x, y, w, accx, accy);
+    return;
+  }
+  if (type == LSIM_LENS_SHEAR) {
+    const double g1 = UNIT ? L.c[2] : L.c[2] * w, g2 = UNIT ? L.c[3] : L.c[3] * w;
+    const double kx = UNIT ? L.c[4] : L.c[4] * w, ky = UNIT ? L.c[5] : L.c[5] * w;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < J; ++j) {
+      accx[j] = fma(g1, x[j], fma(g2, y[j], CONST_DONE ? accx[j] : accx[j] + kx));
+      accy[j] = fma(g2, x[j], fma(-g1, y[j], CONST_DONE ? accy[j] : accy[j] + ky));
+    }
+    return;
+  }
+  double fx[J], fy[J];
+  lens_eval<FULL, J>(type, L, coef_pool, x, y, fx, fy);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    accx[j] = UNIT ? accx[j] + fx[j] : fma(w, fx[j], accx[j]);
+    accy[j] = UNIT ? accy[j] + fy[j] : fma(w, fy[j], accy[j]);
+  }
+}
+
 // Compile-time list of effective profile types (LensC::type / LightC::type after *_prepare).  N < 0 means
 // "not known at compile time": loops run over the runtime count and dispatch on the prepared type.
 template <int... T>
@@ -767,37 +860,59 @@ struct Rays {
   double ax[J], ay[J];  // single plane: accumulated deflection; multi plane: current angle
 };
 
+LSIM_HD constexpr bool lens_type_is_series(int type) {
+  return type == LSIM_LENS_EPL || type == LSIM_LENS_EPL_MULTIPOLE_M1M3M4;
+}
+
+// Compile-time profile list (single plane), first half: the position-independent terms of the cheap profiles
+// (per-set constants: no register lives across the series), then the series profiles, whose last FMA accumulates.
+template <bool FULL, int J, class LT>
+LSIM_HD void ray_apply_head(const LensC* L, const double* pool, Rays<J>& r) {
+  double kx = 0.0, ky = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int l = 0; l < LT::N; ++l)
+    if (LT::at(l) == LSIM_LENS_SHEAR) {
+      kx += L[l].c[4];
+      ky += L[l].c[5];
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    r.ax[j] += kx;
+    r.ay[j] += ky;
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int l = 0; l < LT::N; ++l)
+    if (lens_type_is_series(LT::at(l))) lens_accum<FULL, J, true>(LT::at(l), L[l], pool, r.x, r.y, 1.0, r.ax, r.ay);
+}
+
+// ... second half: the position-dependent part of the cheap profiles.  r.x / r.y may have been re-read in between
+// (the image kernel does, instead of keeping them in registers across the series).  A sum of two terms does not
+// depend on the order; beyond that the order moves the last bit only.
+template <bool FULL, int J, class LT>
+LSIM_HD void ray_apply_tail(const LensC* L, const double* pool, Rays<J>& r) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int l = 0; l < LT::N; ++l)
+    if (!lens_type_is_series(LT::at(l)))
+      lens_accum<FULL, J, true, true>(LT::at(l), L[l], pool, r.x, r.y, 1.0, r.ax, r.ay);
+}
+
 template <bool FULL, int J, class LT = RuntimeTypes>
 LSIM_HD void ray_apply(const RayCfg& P, const LensC* L, const double* pool, int n_c, Rays<J>& r) {
-  double fx[J], fy[J];
-  if (LT::N >= 0) {
-    // single plane, profile list known at compile time: fully unrolled, no dispatch
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int l = 0; l < LT::N; ++l) {
-      lens_eval<FULL, J>(LT::at(l), L[l], pool, r.x, r.y, fx, fy);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int j = 0; j < J; ++j) {
-        r.ax[j] += fx[j];
-        r.ay[j] += fy[j];
-      }
-    }
+  if (LT::N >= 0) {  // single plane, profile list known at compile time: fully unrolled, no dispatch
+    ray_apply_head<FULL, J, LT>(L, pool, r);
+    ray_apply_tail<FULL, J, LT>(L, pool, r);
     return;
   }
   if (!P.multi_plane) {
-    for (int l = 0; l < n_c; ++l) {
-      lens_eval<FULL, J>(L[l].type, L[l], pool, r.x, r.y, fx, fy);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int j = 0; j < J; ++j) {
-        r.ax[j] += fx[j];
-        r.ay[j] += fy[j];
-      }
-    }
+    for (int l = 0; l < n_c; ++l) lens_accum<FULL, J, true>(L[l].type, L[l], pool, r.x, r.y, 1.0, r.ax, r.ay);
   } else {
     // MultiPlaneBase.ray_shooting_partial_comoving (multi_plane_base.py:195-233)
     double tx[J], ty[J];
@@ -811,14 +926,7 @@ LSIM_HD void ray_apply(const RayCfg& P, const LensC* L, const double* pool, int 
         tx[j] = r.x[j] * L[l].inv_T_z;
         ty[j] = r.y[j] * L[l].inv_T_z;
       }
-      lens_eval<FULL, J>(L[l].type, L[l], pool, tx, ty, fx, fy);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int j = 0; j < J; ++j) {
-        r.ax[j] -= fx[j] * L[l].red2phys;
-        r.ay[j] -= fy[j] * L[l].red2phys;
-      }
+      lens_accum<FULL, J, false>(L[l].type, L[l], pool, tx, ty, -L[l].red2phys, r.ax, r.ay);
     }
   }
 }
@@ -853,7 +961,8 @@ LSIM_HD void ray_finish(const RayCfg& P, const Rays<J>& r, int j, double& bx, do
 
 // ---- light -----------------------------------------------------------------------------------------------
 // c[0..1] centre; SERSIC family: c[2..4] = product-average transform rows / norm, c[5] = 1/(2n),
-// c[6] = -log2(Rs_)/n, c[7] = -bn log2(e), c[8] = bn log2(e), c[9] = (max_R_frac Rs_)^2, c[10] = amp
+// c[6] = -log2(Rs_)/n, c[7] = -bn log2(e), c[8] = bn log2(e) (c[5..8] times 256: exp2_*_s), c[9] = (max_R_frac Rs_)^2,
+// c[10] = amp, c[11..12] = the transform of -centre
 LSIM_HD void light_prepare(const lsim_light_desc& d, const double* row, LightC& G) {
   G.type = d.type;
   G.lensed = d.lensed;
@@ -889,6 +998,13 @@ LSIM_HD void light_prepare(const lsim_light_desc& d, const double* row, LightC& 
       G.c[8] = fmin(bn * kLog2e, 1021.0);  // exp(bn) overflows beyond (n_sersic > 354): saturate
       G.c[9] = (1000.0 * Rs_) * (1000.0 * Rs_);
       G.c[10] = amp;
+      G.c[11] = -(G.c[2] * cx + G.c[3] * cy);  // shift folded into the product-average transform
+      G.c[12] = -(G.c[3] * cx + G.c[4] * cy);
+      // exponents pre-scaled by 256 for exp2_*_s
+      G.c[5] *= 256.0;
+      G.c[6] *= 256.0;
+      G.c[7] *= 256.0;
+      G.c[8] *= 256.0;
       G.type = LSIM_LIGHT_SERSIC_ELLIPSE;
       break;
     }
@@ -907,34 +1023,56 @@ LSIM_HD void light_prepare(const lsim_light_desc& d, const double* row, LightC& 
 }
 
 // J points at once (sersic_utils.py:247-267 with R^2 in place of R: no square root is needed because
-// (R/Rs)^(1/n) = exp2(log2(R^2)/(2n) - log2(Rs)/n)).
+// (R/Rs)^(1/n) = exp2(log2(R^2)/(2n) - log2(Rs)/n)).  -> e[j] = the profile at amp = 1
 template <int J>
-LSIM_HD void light_eval(int type, const LightC& G, const double (&x)[J], const double (&y)[J], double (&v)[J]) {
+LSIM_HD void light_unit(int type, const LightC& G, const double (&x)[J], const double (&y)[J], double (&e)[J]) {
   if (type == LSIM_LIGHT_SERSIC_ELLIPSE) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int j = 0; j < J; ++j) {
-      const double xs = x[j] - G.c[0], ys = y[j] - G.c[1];
-      const double xt = fma(G.c[3], ys, G.c[2] * xs);
-      const double yt = fma(G.c[4], ys, G.c[3] * xs);
+      const double xt = fma(G.c[2], x[j], fma(G.c[3], y[j], G.c[11]));
+      const double yt = fma(G.c[3], x[j], fma(G.c[4], y[j], G.c[12]));
       const double R2c = max_nan(fma(yt, yt, xt * xt), 1e-8);  // R_ = max(1e-4, R)
-      const double k = exp2_fin(fma(G.c[5], log2_pos(R2c), G.c[6]));
-      double e = exp2_neg(fma(G.c[7], k, G.c[8]));  // k >= 0, c[7] <= 0: the argument is at most c[8] <= 1021
-      e = (R2c <= G.c[9]) ? e : 0.0;  // R_/Rs_ <= max_R_frac
-      e = (e == e) ? e : 0.0;         // nan_to_num (the exponent is bounded above, so no +inf)
-      v[j] = G.c[10] * e;
+      const double k = exp2_fin_s(fma(G.c[5], log2_pos(R2c), G.c[6]));
+      double v = exp2_neg_s(fma(G.c[7], k, G.c[8]));  // k >= 0, c[7] <= 0: the argument is at most c[8] <= 256 * 1021
+      v = (R2c <= G.c[9]) ? v : 0.0;  // R_/Rs_ <= max_R_frac
+      e[j] = (v == v) ? v : 0.0;      // nan_to_num (the exponent is bounded above, so no +inf)
     }
     return;
   }
-  // GAUSSIAN
+  // GAUSSIAN (amplitude normalisation c[3] applied by the callers through G.c[10] ... no: c[3] IS its amplitude)
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int j = 0; j < J; ++j) {
     const double xs = x[j] - G.c[0], ys = y[j] - G.c[1];
-    v[j] = G.c[3] * exp2_fin(G.c[2] * fma(ys, ys, xs * xs));
+    e[j] = exp2_fin(G.c[2] * fma(ys, ys, xs * xs));
   }
+}
+
+LSIM_HD double light_amp(int type, const LightC& G) { return type == LSIM_LIGHT_SERSIC_ELLIPSE ? G.c[10] : G.c[3]; }
+
+template <int J>
+LSIM_HD void light_eval(int type, const LightC& G, const double (&x)[J], const double (&y)[J], double (&v)[J]) {
+  light_unit<J>(type, G, x, y, v);
+  const double amp = light_amp(type, G);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) v[j] = amp * v[j];
+}
+
+// acc += sum_j amp * profile(x_j, y_j): the amplitude rides on the accumulation FMA
+template <int J>
+LSIM_HD void light_accum(int type, const LightC& G, const double (&x)[J], const double (&y)[J], double& acc) {
+  double e[J];
+  light_unit<J>(type, G, x, y, e);
+  const double amp = light_amp(type, G);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) acc = fma(amp, e[j], acc);
 }
 
 LSIM_HD double light_eval(const LightC& G, double x, double y) {

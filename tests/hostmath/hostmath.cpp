@@ -51,6 +51,35 @@ int hm_ray_shoot(const lsim_lens_desc* lens, int n_lens, int multi_plane, double
   return 0;
 }
 
+// The compile-time profile-list path of the specialised image kernels (k_image<..., TypeList<EPL, SHEAR>, ...>):
+// ray_apply_head / re-read coordinates / ray_apply_tail / beta, three points in lock step, tail padded.
+int hm_ray_shoot_epl_shear(const lsim_lens_desc* lens, double alpha_scaling, const double* row, const double* x,
+                           const double* y, int64_t N, double* ox, double* oy, double series_tol) {
+  using LT = TypeList<LSIM_LENS_EPL, LSIM_LENS_SHEAR>;
+  LensC L[2];
+  std::vector<double> pool(2 * kMaxSeries);
+  L[0].coef_off = 0;
+  lens_prepare(lens[0], row, L[0], pool.data(), series_tol);
+  L[1].coef_off = kMaxSeries;
+  lens_prepare(lens[1], row, L[1], pool.data() + kMaxSeries, series_tol);
+  if (L[0].type != LSIM_LENS_EPL || L[1].type != LSIM_LENS_SHEAR) return 1;
+  RayCfg cfg{0, alpha_scaling, 0.0, 0.0};
+  for (int64_t i = 0; i < N; i += 3) {
+    Rays<3> r;
+    for (int j = 0; j < 3; ++j) {
+      const int64_t k = i + j < N ? i + j : N - 1;
+      ray_init<3, true>(cfg, j, x[k], y[k], r);
+    }
+    ray_apply_head<false, 3, LT>(L, pool.data(), r);
+    ray_apply_tail<false, 3, LT>(L, pool.data(), r);
+    for (int j = 0; j < 3 && i + j < N; ++j) {
+      ox[i + j] = fma(-r.ax[j], cfg.alpha_scaling, r.x[j]);
+      oy[i + j] = fma(-r.ay[j], cfg.alpha_scaling, r.y[j]);
+    }
+  }
+  return 0;
+}
+
 int hm_surface_brightness(const lsim_light_desc* light, int n_light, int n_slots, const double* row, const double* x,
                           const double* y, int64_t N, double* out) {
   std::vector<LightC> G(n_light);

@@ -34,6 +34,8 @@ def lib():
         h = C.CDLL(build())
         h.hm_ray_shoot.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp,
                                    _dp, _dp, C.c_int64, _dp, _dp, C.c_int, C.c_double]
+        h.hm_ray_shoot_epl_shear.argtypes = [C.POINTER(_lib.LensDesc), C.c_double, _dp, _dp, _dp, C.c_int64, _dp, _dp,
+                                             C.c_double]
         h.hm_surface_brightness.argtypes = [C.POINTER(_lib.LightDesc), C.c_int, C.c_int, _dp, _dp, _dp, C.c_int64, _dp]
         h.hm_log2.argtypes = [_dp, C.c_int64, _dp]
         h.hm_exp2.argtypes = [_dp, C.c_int64, _dp]
@@ -77,6 +79,21 @@ def ray_shoot(lens_model_list, kwargs_list, x, y, what=0, profile_kwargs_list=No
     lib().hm_ray_shoot(arr, len(descs), int(mp), alpha_scaling, multi_plane["T_ij_end"] if mp else 0.0,
                        multi_plane["T_z_source"] if mp else 0.0, _p(row), _p(x), _p(y), x.size, _p(ox), _p(oy), what,
                        series_tol)
+    return ox, oy
+
+
+def ray_shoot_epl_shear(kwargs_list, x, y, alpha_scaling=1.0, series_tol=1e-14):
+    """beta through the compile-time TypeList<EPL, SHEAR> path of the specialised image kernels."""
+    names = [_model.LENS_PARAM_NAMES[n] for n in ("EPL", "SHEAR")]
+    row = np.asarray(_model.gather_values(names, kwargs_list), dtype=np.float64)
+    layout = _model.ColumnLayout()
+    descs = [_model.lens_desc(n, layout.add_profile("lens", i, names[i]), {}) for i, n in enumerate(("EPL", "SHEAR"))]
+    arr = (_lib.LensDesc * 2)(*descs)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    ox, oy = np.empty_like(x), np.empty_like(y)
+    rc = lib().hm_ray_shoot_epl_shear(arr, alpha_scaling, _p(row), _p(x), _p(y), x.size, _p(ox), _p(oy), series_tol)
+    assert rc == 0, rc
     return ox, oy
 
 

@@ -135,7 +135,7 @@ def test_headline_through_the_sampler_boundary(headline):
     from jaxtronomy_b200.Sampling.sampler import prepare_logL_func
 
     s = CASES["headline_static"]
-    like, positions_of = headline_likelihood_module(headline["lin"])
+    like, positions_of = headline_likelihood_module(headline["lin"], e_bound=0.95)  # the fixture rows reach |e| = 0.8
     f = prepare_logL_func("gpu", like)
     pos = positions_of(headline["rows"])
     out = f(pos)

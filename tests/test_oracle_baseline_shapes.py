@@ -150,7 +150,10 @@ def test_hostmath_headline_unconvolved_per_pixel(b):
     om = oracle_headline()
     x, y = om.ImageNumerics.coordinates_evaluate
     bx, by = hm.ray_shoot(LENS_LIST, kl, x, y)
-    flux = hm.surface_brightness(SOURCE_LIST, ks, bx, by)[0]
+    # the specialised kernels' compile-time profile list (constant terms, series, linear terms) sums in another order
+    sx, sy = hm.ray_shoot_epl_shear(kl, x, y)
+    assert np.max(np.abs(sx - bx)) <= 1e-14 and np.max(np.abs(sy - by)) <= 1e-14
+    flux = hm.surface_brightness(SOURCE_LIST, ks, sx, sy)[0]
     st = static_config()
     # the reference's flattened sub-pixel order -> re-binned [ny, nx] (oracle grid bookkeeping, pinned bit-exact)
     low, _ = om.ImageNumerics._numerics._grid.flux_array2image_low_high(flux)
