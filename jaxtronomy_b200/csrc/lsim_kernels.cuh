@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kImageBlock, LSIM_IMAGE_MIN_BLOCKS)
 k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, double out_scale,
         double* __restrict__ out, double* __restrict__ sub_out, const unsigned char* __restrict__ prepared, int n_series) {
   constexpr int J = SS > 0 ? SS : 1;
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int64_t bl = blockIdx.y;
   const double* row = params + (set0 + bl) * P.n_param_cols;
   LensC* L = reinterpret_cast<LensC*>(smem);
@@ -285,7 +285,13 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
   // flux_evaluate_indexes: only the listed pixels are visited (the others were zero-filled by the host side),
   // so masked pixels cost nothing and warps stay full
   const int q_end = min(MASKED ? P.n_eval : npix, (int)(blockIdx.x + 1) * ppt);
-  for (int q = blockIdx.x * ppt + threadIdx.x; q < q_end; q += kImageBlock) {
+  // The pixel loop is WARP-UNIFORM: every thread of the CTA makes the same number of trips (a thread past the end
+  // re-evaluates the last pixel and skips the store).  Inside a loop whose trip count depends on the thread the
+  // compiler keeps the polynomial coefficients of the kernel parameters in vector registers; in uniform control flow
+  // they live in uniform registers, and a DFMA with a uniform operand reads two vector registers instead of three.
+  for (int q0 = blockIdx.x * ppt; q0 < q_end; q0 += kImageBlock) {
+    const int q = min(q0 + (int)threadIdx.x, q_end - 1);
+    const bool live = q0 + (int)threadIdx.x < q_end;
     const int p = MASKED ? __ldg(P.eval_list + q) : q;
     const int py = p / P.nx, px = p - py * P.nx;
     double acc[NSLOT];
@@ -313,7 +319,7 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
         if (kSingle) {
           // the image-plane coordinates are needed again only after the series (cheap profiles, beta = theta - alpha,
           // unlensed light): read them a second time (L1 hit) instead of keeping 4 J registers alive across it
-          ray_apply_head<FULL, J, LT>(L, pool, r);
+          ray_apply_head<FULL, J, LT>(P.ray, L, pool, r);
 #pragma unroll
           for (int j = 0; j < J; ++j) {
             x[j] = ldg_again(xrow + j0 + j);
@@ -321,7 +327,7 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
             r.x[j] = x[j];
             r.y[j] = y[j];
           }
-          ray_apply_tail<FULL, J, LT>(L, pool, r);
+          ray_apply_tail<FULL, J, LT>(P.ray, L, pool, r);
 #pragma unroll
           for (int j = 0; j < J; ++j) {
             bx[j] = fma(-r.ax[j], P.ray.alpha_scaling, x[j]);
@@ -339,9 +345,9 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
           if (!SUB) {  // the amplitude and the sum over the J sub-pixels ride on the accumulation FMAs
             double vs = 0.0;
             if (Gg.lensed)
-              light_accum<J>(type, Gg, bx, by, NSLOT == 1 ? racc[0] : vs);
+              light_accum<J>(type, Gg, bx, by, NSLOT == 1 ? racc[0] : vs, P.ray.mk);
             else
-              light_accum<J>(type, Gg, x, y, NSLOT == 1 ? racc[0] : vs);
+              light_accum<J>(type, Gg, x, y, NSLOT == 1 ? racc[0] : vs, P.ray.mk);
             if (NSLOT > 1) {
 #pragma unroll
               for (int k = 0; k < NSLOT; ++k) racc[k] += (slot == k) ? vs : 0.0;
@@ -355,7 +361,8 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
           {  // supersampled convolution: keep the sub-pixel fluxes [set][slot][ny ss][nx ss]
             double* dsub = sub_out + (bl * P.n_slots + slot) * ((int64_t)npix * ss * ss) + base + j0;
 #pragma unroll
-            for (int j = 0; j < J; ++j) dsub[j] = ((written >> slot) & 1u) ? dsub[j] + v[j] : v[j];
+            for (int j = 0; j < J; ++j)
+              if (live) dsub[j] = ((written >> slot) & 1u) ? dsub[j] + v[j] : v[j];
             written |= 1u << slot;
           }
           double vs = v[0];
@@ -375,7 +382,8 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
             if ((written >> k) & 1u) continue;  // a slot without any component is an all-zero image
             double* dsub = sub_out + (bl * P.n_slots + k) * ((int64_t)npix * ss * ss) + base + j0;
 #pragma unroll
-            for (int j = 0; j < J; ++j) dsub[j] = 0.0;
+            for (int j = 0; j < J; ++j)
+              if (live) dsub[j] = 0.0;
           }
         }
       }
@@ -384,7 +392,7 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
     }
 #pragma unroll
     for (int k = 0; k < NSLOT; ++k) {
-      if (k < P.n_slots && (!SUB || out)) out[(bl * P.n_slots + k) * npix + p] = acc[k] * inv_ss * out_scale;
+      if (live && k < P.n_slots && (!SUB || out)) out[(bl * P.n_slots + k) * npix + p] = acc[k] * inv_ss * out_scale;
     }
   }
 }

@@ -38,18 +38,16 @@ constexpr double kLn2 = 0.69314718055994530942;
 
 // log2(1+u)/u = (1/ln2) (1 - u/2 + u^2/3 - ...): coefficients (-1)^(k+1)/(k ln2), k = 6..1, highest first
 LSIM_TABLE kLog2C[6] = {-kLog2e / 6.0, kLog2e / 5.0, -kLog2e / 4.0, kLog2e / 3.0, -kLog2e / 2.0, kLog2e};
-// (2^r - 1)/r = ln2 + ln2^2 r/2 + ...: coefficients ln2^k/k!, k = 4..1, highest first
-LSIM_TABLE kExp2C[4] = {kLn2 * kLn2 * kLn2 * kLn2 / 24.0, kLn2 * kLn2 * kLn2 / 6.0, kLn2 * kLn2 / 2.0, kLn2};
 
-// Lookup tables (tools/gen_math_tables.py): exp2 T[j] = 2^(j/256); log2 {R[i], L[i]} = {~1/c_i, -log2 R[i]} for
-// the 128 bins of the mantissa (2 KB each).  The index differs from lane to lane, which constant memory would
-// serialise, so every kernel that evaluates profiles copies the tables from global into SHARED memory once per CTA
-// (stage_math_tables): a lookup is then one LDS at a 32-bit offset (no 64-bit address arithmetic, lower latency
-// than an L1 hit).
+// Lookup tables (tools/gen_math_tables.py): exp2 T[j] = 2^(j/256) (stored as bit patterns with j << 12 subtracted
+// from the high word, see exp2_core_s); log2 {R[i], L[i]} = {~1/c_i, -log2 R[i]} for the 128 bins of the mantissa
+// (2 KB each).  The index differs from lane to lane, which constant memory would serialise, so every kernel that
+// evaluates profiles copies the tables from global into SHARED memory once per CTA (stage_math_tables): a lookup is
+// then one LDS at a 32-bit offset (no 64-bit address arithmetic, lower latency than an L1 hit).
 #if defined(__CUDACC__)
-__device__ double d_exp2_tab[LSIM_EXP2_N] = LSIM_EXP2_TABLE;
+__device__ unsigned long long d_exp2_tab[LSIM_EXP2_N] = LSIM_EXP2_TABLE;
 __device__ double d_log2_tab[2 * LSIM_LOG2_N] = LSIM_LOG2_TABLE;
-__shared__ double s_exp2_tab[LSIM_EXP2_N];
+__shared__ unsigned long long s_exp2_tab[LSIM_EXP2_N];
 __shared__ double2 s_log2_tab[LSIM_LOG2_N];
 // call at kernel entry, followed by a __syncthreads() before the first log2_pos / exp2_*
 __device__ __forceinline__ void stage_math_tables() {
@@ -58,8 +56,32 @@ __device__ __forceinline__ void stage_math_tables() {
     s_log2_tab[i] = reinterpret_cast<const double2*>(d_log2_tab)[i];
 }
 #endif
-static const double h_exp2_tab[LSIM_EXP2_N] = LSIM_EXP2_TABLE;
+static const unsigned long long h_exp2_tab[LSIM_EXP2_N] = LSIM_EXP2_TABLE;
 static const double h_log2_tab[2 * LSIM_LOG2_N] = LSIM_LOG2_TABLE;
+
+// The polynomial coefficients again, as a plain struct: the image kernels carry it in their kernel parameters
+// (PlanDev.ray.mk), where the compiler reads it through uniform registers -- a DFMA with a uniform-register operand
+// reads two vector registers and issues at full rate, one whose coefficient sits in a vector register (which is what
+// the compiler does with __constant__ data it uses more than once) reads three and takes 3 cycles instead of 2
+// (profiles/r1_dfma_operand_probe.md).
+struct MathK {
+  double l[6];  // kLog2C
+  double e[4];  // kExp2S
+};
+LSIM_HD MathK math_k() {
+  MathK k;
+  k.l[0] = -kLog2e / 6.0;
+  k.l[1] = kLog2e / 5.0;
+  k.l[2] = -kLog2e / 4.0;
+  k.l[3] = kLog2e / 3.0;
+  k.l[4] = -kLog2e / 2.0;
+  k.l[5] = kLog2e;
+  k.e[0] = kLn2 * kLn2 * kLn2 * kLn2 / 24.0 / 4294967296.0;
+  k.e[1] = kLn2 * kLn2 * kLn2 / 6.0 / 16777216.0;
+  k.e[2] = kLn2 * kLn2 / 2.0 / 65536.0;
+  k.e[3] = kLn2 / 256.0;
+  return k;
+}
 
 LSIM_HD int64_t d2i(double x) {
 #if defined(__CUDA_ARCH__)
@@ -146,118 +168,87 @@ LSIM_HD double rsqrt_fast(double x) {
 // so both functions are table-driven and BRANCH-FREE here:
 //   log2_pos(x): x positive, finite, normal.  8 fp64 instructions.  |abs err| < 3e-16 max(1, |log2 x|)
 //                (the result feeds exponents, where absolute accuracy is what matters).
-//   exp2_fin(x): any x; 7 fp64 instructions; |rel err| < 4e-16.  The argument is clamped to [-1022, 1022] with
-//                integer instructions, i.e. results saturate at 2^-1022 (2.2e-308, instead of denormals / 0) and
-//                2^1022 (instead of +inf); nan propagates.
-//   exp2_neg(x): the same for arguments known to stay below 1022 (only the lower clamp).
+//   exp2_fin(x): any x; 7 fp64 instructions (6 for a pre-scaled argument, exp2_fin_s); |rel err| < 4e-16.  Results
+//                saturate at 2^-1022 (2.2e-308, instead of denormals / 0) and 2^1023 (instead of +inf) through one
+//                integer clamp of the table index; nan propagates, +-inf gives nan.
+//   exp2_neg(x): kept as a name for call sites whose argument is bounded above; the same function.
 
 // x = 2^e m, m in [1,2); bin i = top 7 mantissa bits; u = m R_i - 1, |u| <= 1/256;
 // log2 x = e + L_i + log2(1 + u)
-LSIM_HD double log2_pos(double x) {
+template <class CoefT>
+LSIM_HD double log2_pos_c(double x, const CoefT& C) {
   const int64_t ix = d2i(x);
-  const int e = (int)(ix >> 52) - 1023;
+  const uint32_t hx = (uint32_t)((uint64_t)ix >> 32);
+  const int e = (int)(hx >> 20) - 1023;
   const double m = i2d((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-  const int i = (int)(ix >> 45) & (LSIM_LOG2_N - 1);
 #if defined(__CUDA_ARCH__)
-  const double2 rl = s_log2_tab[i];
+  // byte offset of the bin's {R, L} pair: (top 7 mantissa bits) * 16 in one shift and one mask
+  const double2 rl = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(s_log2_tab) + ((hx >> 9) & 0x7f0u));
   const double R = rl.x, L = rl.y;
 #else
+  const int i = (int)(hx >> 13) & (LSIM_LOG2_N - 1);
   const double R = h_log2_tab[2 * i], L = h_log2_tab[2 * i + 1];
 #endif
   const double u = fma(m, R, -1.0);
-  double p = fma(kLog2C[0], u, kLog2C[1]);
-  p = fma(p, u, kLog2C[2]);
-  p = fma(p, u, kLog2C[3]);
-  p = fma(p, u, kLog2C[4]);
-  p = fma(p, u, kLog2C[5]);
+  double p = fma(C[0], u, C[1]);
+  p = fma(p, u, C[2]);
+  p = fma(p, u, C[3]);
+  p = fma(p, u, C[4]);
+  p = fma(p, u, C[5]);
   return (double)e + fma(u, p, L);
 }
+LSIM_HD double log2_pos(double x) { return log2_pos_c(x, kLog2C); }
+LSIM_HD double log2_pos(double x, const MathK& K) { return log2_pos_c(x, K.l); }
 
-// x = k/256 + r, k = rint(256 x), |r| <= 1/512: 2^x = 2^(k>>8) T[k&255] (1 + r P(r)).  |x| <= 1022 or nan.
-LSIM_HD double exp2_core(double x) {
-#if !defined(__CUDA_ARCH__)
-  if (x != x) return x;  // (int)nan is undefined on the host; the device conversion gives 0 and nan flows through r
-#endif
-  const double kf = rint(x * 256.0);
-  const int ki = (int)kf;
-  const double r = fma(kf, -0.00390625, x);  // exact
-  double p = fma(kExp2C[0], r, kExp2C[1]);
-  p = fma(p, r, kExp2C[2]);
-  p = fma(p, r, kExp2C[3]);
-#if defined(__CUDA_ARCH__)
-  const double T = s_exp2_tab[ki & (LSIM_EXP2_N - 1)];
-#else
-  const double T = h_exp2_tab[ki & (LSIM_EXP2_N - 1)];
-#endif
-  const double t = fma(T * r, p, T);  // in [0.9986, 1.9974]
-  // scale by 2^(k>>8): |k>>8| <= 1022 and (k>>8 = -1022 => t >= 1), so the result stays normal and the exponent
-  // can be added to the high word alone
-#if defined(__CUDA_ARCH__)
-  return __hiloint2double(__double2hiint(t) + ((ki >> 8) << 20), __double2loint(t));
-#else
-  return i2d(d2i(t) + ((int64_t)(ki >> 8) << 52));
-#endif
-}
-
-// 1022.0 = 0x408FF000_00000000: the clamps compare the high word only (exact, the low word of the bound is zero)
-LSIM_HD double exp2_fin(double x) {
-  const int64_t ix = d2i(x);
-  const uint32_t hx = (uint32_t)((uint64_t)ix >> 32), ax = hx & 0x7fffffffu;
-  const bool big = (uint32_t)(ax - 0x408FF000u) <= (0x7ff00000u - 0x408FF000u);  // 1022 <= |x| <= inf, not nan
-  const double xc = big ? i2d((int64_t)(((uint64_t)((hx & 0x80000000u) | 0x408FF000u)) << 32)) : x;
-  return exp2_core(xc);
-}
-
-LSIM_HD double exp2_neg(double x) {
-  const uint32_t hx = (uint32_t)((uint64_t)d2i(x) >> 32);
-  const bool low = (uint32_t)(hx - 0xC08FF000u) <= (0xFFF00000u - 0xC08FF000u);  // -inf <= x <= -1022, not nan
-  return exp2_core(low ? -1022.0 : x);
-}
-
-// ---- exp2 of a PRE-SCALED argument: y = 256 x -------------------------------------------------------------------
-// The hot profiles compute their exponents with one FMA from prepared constants; folding the factor 256 of the table
-// index into those constants removes the multiplication at the head of exp2_core, and the reduced argument becomes a
-// subtraction: k = rint(y), r' = y - k (exact), 2^x = 2^(k>>8) T[k&255] (1 + r' P'(r')) with the coefficients of P'
-// scaled by powers of 256 (exact), so the result is bit-identical to exp2_core(y / 256).  6 fp64 instructions.
+// ---- exp2 ------------------------------------------------------------------------------------------------------------
+// Core, for a PRE-SCALED argument y = 256 x (the hot profiles compute their exponents with one FMA from prepared
+// constants, which carry the factor 256): k = rint(y), r = y - k (exact), k clamped to [-1022*256, 1022*256 + 255] with
+// ONE integer min/max, j = k & 255, E = k >> 8:
+//   2^x = (2^E T[j]) (1 + r P(r)),
+// where 2^E T[j] costs one integer multiply-add on the high word of the table entry (the table stores T[j] with
+// j << 12 subtracted from its high word, so hi + (k << 12) = hi(T[j]) + (E << 20)).  P's coefficients are those of
+// (2^r - 1)/r scaled by powers of 256 (exact).  6 fp64 instructions; the result saturates at 2^-1022 / 2^1023 for finite
+// arguments out of range (the reduced argument stays |r| <= 1/2 whatever the clamp does), nan and +-inf give nan.
 LSIM_TABLE kExp2S[4] = {kLn2 * kLn2 * kLn2 * kLn2 / 24.0 / 4294967296.0, kLn2 * kLn2 * kLn2 / 6.0 / 16777216.0,
                         kLn2 * kLn2 / 2.0 / 65536.0, kLn2 / 256.0};
 
-LSIM_HD double exp2_core_s(double y) {
+template <class CoefT>
+LSIM_HD double exp2_core_s(double y, const CoefT& C) {
 #if !defined(__CUDA_ARCH__)
-  if (y != y) return y;
+  if (!(y - y == 0.0)) return y - y;  // nan, +-inf -> nan (the device conversion saturates and r = y - k is nan)
+  if (y > 4e9) y = 4e9;               // (int) of an out-of-range double is undefined on the host; k is clamped anyway
+  if (y < -4e9) y = -4e9;
 #endif
   const double kf = rint(y);
-  const int ki = (int)kf;
+  int ki = (int)(long long)kf;
+#if !defined(__CUDA_ARCH__)
+  if (kf > 2e9) ki = 2000000000;
+  if (kf < -2e9) ki = -2000000000;
+#endif
   const double r = y - kf;  // exact: |r| <= 1/2 and both are multiples of ulp(y)
-  double p = fma(kExp2S[0], r, kExp2S[1]);
-  p = fma(p, r, kExp2S[2]);
-  p = fma(p, r, kExp2S[3]);
+  ki = ki < -261632 ? -261632 : (ki > 261887 ? 261887 : ki);
+  double p = fma(C[0], r, C[1]);
+  p = fma(p, r, C[2]);
+  p = fma(p, r, C[3]);
 #if defined(__CUDA_ARCH__)
-  const double T = s_exp2_tab[ki & (LSIM_EXP2_N - 1)];
+  const unsigned long long tb = s_exp2_tab[ki & (LSIM_EXP2_N - 1)];
+  const double T = __hiloint2double((int)((uint32_t)(tb >> 32) + ((uint32_t)ki << 12)), (int)(uint32_t)tb);
 #else
-  const double T = h_exp2_tab[ki & (LSIM_EXP2_N - 1)];
+  const unsigned long long tb = h_exp2_tab[ki & (LSIM_EXP2_N - 1)];
+  const double T = i2d((int64_t)(tb + ((unsigned long long)((uint32_t)ki << 12) << 32)));
 #endif
-  const double t = fma(T * r, p, T);
-#if defined(__CUDA_ARCH__)
-  return __hiloint2double(__double2hiint(t) + ((ki >> 8) << 20), __double2loint(t));
-#else
-  return i2d(d2i(t) + ((int64_t)(ki >> 8) << 52));
-#endif
+  return fma(T * r, p, T);
 }
 
-// 256 * 1022 = 261632.0 = 0x410FF000_00000000 (same mantissa as 1022: the clamps still compare the high word only)
-LSIM_HD double exp2_fin_s(double y) {
-  const int64_t iy = d2i(y);
-  const uint32_t hy = (uint32_t)((uint64_t)iy >> 32), ay = hy & 0x7fffffffu;
-  const bool big = (uint32_t)(ay - 0x410FF000u) <= (0x7ff00000u - 0x410FF000u);  // 1022 <= |y|/256 <= inf, not nan
-  const double yc = big ? i2d((int64_t)(((uint64_t)((hy & 0x80000000u) | 0x410FF000u)) << 32)) : y;
-  return exp2_core_s(yc);
-}
-
-LSIM_HD double exp2_neg_s(double y) {
-  const uint32_t hy = (uint32_t)((uint64_t)d2i(y) >> 32);
-  const bool low = (uint32_t)(hy - 0xC10FF000u) <= (0xFFF00000u - 0xC10FF000u);  // -inf <= y/256 <= -1022, not nan
-  return exp2_core_s(low ? -261632.0 : y);
-}
+LSIM_HD double exp2_fin_s(double y) { return exp2_core_s(y, kExp2S); }
+LSIM_HD double exp2_fin_s(double y, const MathK& K) { return exp2_core_s(y, K.e); }
+LSIM_HD double exp2_neg_s(double y) { return exp2_core_s(y, kExp2S); }
+// "coefficients from the __constant__ tables" as a type, for code templated on where the coefficients come from
+struct TableK {};
+LSIM_HD double log2_pos(double x, const TableK&) { return log2_pos_c(x, kLog2C); }
+LSIM_HD double exp2_fin_s(double y, const TableK&) { return exp2_core_s(y, kExp2S); }
+// unscaled arguments (everything off the hot path)
+LSIM_HD double exp2_fin(double x) { return exp2_core_s(x * 256.0, kExp2S); }
+LSIM_HD double exp2_neg(double x) { return exp2_core_s(x * 256.0, kExp2S); }
 
 }  // namespace lsim

@@ -38,7 +38,7 @@ struct LensC {
   int32_t n_coef;    // EPL family: number of series coefficients actually used
   int32_t coef_off;  // EPL family: offset of this profile's coefficients in the coefficient pool
   double delta_T, inv_T_z, red2phys;  // multi-plane stepping
-  double c[30];
+  double c[31];  // (an odd count keeps sizeof(LensC) a multiple of 16: the coefficient pools behind stay 16-byte aligned)
 };
 
 struct LightC {
@@ -188,9 +188,9 @@ LSIM_HD void epl_prepare(LensC& L, double* coef, double theta_E, double gamma, d
 // Output: the deflection in the sky frame is  s[j] * (u1[j], u2[j])  (the caller folds s into its accumulation FMA).
 // Non-finite results (Z = 0) follow the reference: nan_to_num(posinf=1e10, neginf=-1e10) on the major-axis
 // components (epl.py:391-392), one test for all J points; then s = 1 and (u1, u2) is the rotated, cleaned deflection.
-template <int J>
+template <int J, class KT>
 LSIM_HD void epl_core(const LensC& L, const double* coef, const double (&a)[J], const double (&c)[J], double (&s)[J],
-                      double (&u1)[J], double (&u2)[J]) {
+                      double (&u1)[J], double (&u2)[J], const KT& K) {
   // seven values per point stay live across the series loop besides the recurrence state: a, c, s, Im w, p, -|w|^2
   double wi[J], pp[J], qq[J], b1[J], b2[J];
 #if defined(__CUDA_ARCH__)
@@ -206,29 +206,49 @@ LSIM_HD void epl_core(const LensC& L, const double* coef, const double (&a)[J], 
     const double h = R2 * iE;
     qq[j] = L.c[25] * h;
     const double R2c = max_nan(R2, 1e-18);  // R = max(|Z|, 1e-9)
-    s[j] = h * exp2_fin_s(fma(L.c[27], log2_pos(R2c), L.c[28]));
-    b1[j] = 0.0;
+    s[j] = h * exp2_fin_s(fma(L.c[27], log2_pos(R2c, K), L.c[28]), K);
+  }
+  // Clenshaw over the terms k = n_coef-1 ... 1, two per trip with the roles of b1 / b2 swapping (no register moves);
+  // an even count peels its first term, whose step is just b1 = F_k (b1 = b2 = 0 before it).  Term 1 is taken
+  // together with the closing step below.  The pairs (F_{k-1}, F_k), k odd, are 16-byte aligned: one LDS.128.
+  int k = L.n_coef - 1;
+  const bool peel = k >= 1 && (k & 1) == 0;
+  const double ctop = peel ? coef[k] : 0.0;
+  k -= peel ? 1 : 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    b1[j] = ctop;
     b2[j] = 0.0;
   }
-  for (int k = L.n_coef - 1; k >= 1; --k) {
-    const double ck = coef[k];
+  for (; k >= 3; k -= 2) {
+#if defined(__CUDA_ARCH__)
+    const double2 cc = *reinterpret_cast<const double2*>(coef + k - 1);
+    const double ck = cc.y, ckm = cc.x;
+#else
+    const double ck = coef[k], ckm = coef[k - 1];
+#endif
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int j = 0; j < J; ++j) {
-      const double t = fma(pp[j], b1[j], fma(qq[j], b2[j], ck));
-      b2[j] = b1[j];
-      b1[j] = t;
+      b2[j] = fma(pp[j], b1[j], fma(qq[j], b2[j], ck));
+      b1[j] = fma(pp[j], b2[j], fma(qq[j], b1[j], ckm));
     }
   }
-  const double c0 = coef[0], cph = L.c[2], sph = L.c[3], rho = L.c[26];
+  const double c0 = coef[0], c1 = k == 1 ? coef[1] : 0.0, cph = L.c[2], sph = L.c[3], rho = L.c[26];
+  const bool last = k == 1;
   double tr[J], ti[J];
   uint32_t worst = 0;  // largest |high word| of the factors: >= 0x7ff00000 <=> some factor is inf / nan
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int j = 0; j < J; ++j) {
-    const double Sr = fma(b1[j], 0.5 * pp[j], fma(qq[j], b2[j], c0)), Si = b1[j] * wi[j];
+    // term 1 (if any): (b1, b2) <- (F_1 + p b1 + q b2, b1); then S = F_0 + w b1 + q b2 with Re w = p/2
+    const double bn = last ? fma(pp[j], b1[j], fma(qq[j], b2[j], c1)) : b1[j];
+    const double bo = last ? b1[j] : b2[j];
+    const double Sr = fma(bn, 0.5 * pp[j], fma(qq[j], bo, c0)), Si = bn * wi[j];
     const double cr = rho * c[j];
     tr[j] = fma(a[j], Sr, -(cr * Si));
     ti[j] = fma(a[j], Si, cr * Sr);
@@ -259,9 +279,9 @@ LSIM_HD void epl_core(const LensC& L, const double* coef, const double (&a)[J], 
 }
 
 // acc += w * alpha(x, y) for J sky positions.  UNIT: w == 1 at compile time (single-plane lensing).
-template <int J, bool UNIT>
+template <int J, bool UNIT, class KT>
 LSIM_HD void epl_accum(const LensC& L, const double* coef, const double (&x)[J], const double (&y)[J], double w,
-                       double (&accx)[J], double (&accy)[J]) {
+                       double (&accx)[J], double (&accy)[J], const KT& K) {
   double a[J], c[J], s[J], u1[J], u2[J];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -270,7 +290,7 @@ LSIM_HD void epl_accum(const LensC& L, const double* coef, const double (&x)[J],
     a[j] = fma(L.c[19], x[j], fma(L.c[20], y[j], L.c[21]));
     c[j] = fma(L.c[2], y[j], fma(-L.c[3], x[j], L.c[22]));
   }
-  epl_core<J>(L, coef, a, c, s, u1, u2);
+  epl_core<J>(L, coef, a, c, s, u1, u2, K);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -294,7 +314,7 @@ LSIM_HD void epl_eval(const LensC& L, const double* coef, const double (&xs)[J],
     a[j] = fma(L.c[19], xs[j], L.c[20] * ys[j]);
     c[j] = fma(L.c[2], ys[j], -(L.c[3] * xs[j]));
   }
-  epl_core<J>(L, coef, a, c, s, u1, u2);
+  epl_core<J>(L, coef, a, c, s, u1, u2, TableK());
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -779,11 +799,11 @@ LSIM_HD void lens_eval(int type, const LensC& L, const double* coef_pool, const 
 // acc += w * (reduced deflection of one profile) for J points.  UNIT: w == 1 at compile time.  The hot profiles fold
 // the weighted sum into their last FMAs; everything else goes through lens_eval.
 // CONST_DONE: the position-independent part of the profile (SHEAR: its origin term) is in the accumulators already.
-template <bool FULL, int J, bool UNIT, bool CONST_DONE = false>
+template <bool FULL, int J, bool UNIT, bool CONST_DONE = false, class KT = TableK>
 LSIM_HD void lens_accum(int type, const LensC& L, const double* coef_pool, const double (&x)[J], const double (&y)[J],
-                        double w, double (&accx)[J], double (&accy)[J]) {
+                        double w, double (&accx)[J], double (&accy)[J], const KT& K = KT()) {
   if (type == LSIM_LENS_EPL) {
-    epl_accum<J, UNIT>(L, coef_pool + L.coef_off, x, y, w, accx, accy);
+    epl_accum<J, UNIT>(L, coef_pool + L.coef_off, x, y, w, accx, accy, K);
     return;
   }
   if (type == LSIM_LENS_SHEAR) {
@@ -851,6 +871,7 @@ LSIM_HD bool lens_type_has_series(const lsim_lens_desc& d) {
 struct RayCfg {
   int32_t multi_plane;
   double alpha_scaling, T_ij_end, inv_T_z_source;
+  MathK mk;  // polynomial coefficients of log2 / exp2 as kernel parameters (uniform-register operands)
 };
 
 // State of J rays while they are pushed through the deflector list.
@@ -867,7 +888,7 @@ LSIM_HD constexpr bool lens_type_is_series(int type) {
 // Compile-time profile list (single plane), first half: the position-independent terms of the cheap profiles
 // (per-set constants: no register lives across the series), then the series profiles, whose last FMA accumulates.
 template <bool FULL, int J, class LT>
-LSIM_HD void ray_apply_head(const LensC* L, const double* pool, Rays<J>& r) {
+LSIM_HD void ray_apply_head(const RayCfg& P, const LensC* L, const double* pool, Rays<J>& r) {
   double kx = 0.0, ky = 0.0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -888,31 +909,33 @@ LSIM_HD void ray_apply_head(const LensC* L, const double* pool, Rays<J>& r) {
 #pragma unroll
 #endif
   for (int l = 0; l < LT::N; ++l)
-    if (lens_type_is_series(LT::at(l))) lens_accum<FULL, J, true>(LT::at(l), L[l], pool, r.x, r.y, 1.0, r.ax, r.ay);
+    if (lens_type_is_series(LT::at(l)))
+      lens_accum<FULL, J, true, false, MathK>(LT::at(l), L[l], pool, r.x, r.y, 1.0, r.ax, r.ay, P.mk);
 }
 
 // ... second half: the position-dependent part of the cheap profiles.  r.x / r.y may have been re-read in between
 // (the image kernel does, instead of keeping them in registers across the series).  A sum of two terms does not
 // depend on the order; beyond that the order moves the last bit only.
 template <bool FULL, int J, class LT>
-LSIM_HD void ray_apply_tail(const LensC* L, const double* pool, Rays<J>& r) {
+LSIM_HD void ray_apply_tail(const RayCfg& P, const LensC* L, const double* pool, Rays<J>& r) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int l = 0; l < LT::N; ++l)
     if (!lens_type_is_series(LT::at(l)))
-      lens_accum<FULL, J, true, true>(LT::at(l), L[l], pool, r.x, r.y, 1.0, r.ax, r.ay);
+      lens_accum<FULL, J, true, true, MathK>(LT::at(l), L[l], pool, r.x, r.y, 1.0, r.ax, r.ay, P.mk);
 }
 
 template <bool FULL, int J, class LT = RuntimeTypes>
 LSIM_HD void ray_apply(const RayCfg& P, const LensC* L, const double* pool, int n_c, Rays<J>& r) {
   if (LT::N >= 0) {  // single plane, profile list known at compile time: fully unrolled, no dispatch
-    ray_apply_head<FULL, J, LT>(L, pool, r);
-    ray_apply_tail<FULL, J, LT>(L, pool, r);
+    ray_apply_head<FULL, J, LT>(P, L, pool, r);
+    ray_apply_tail<FULL, J, LT>(P, L, pool, r);
     return;
   }
   if (!P.multi_plane) {
-    for (int l = 0; l < n_c; ++l) lens_accum<FULL, J, true>(L[l].type, L[l], pool, r.x, r.y, 1.0, r.ax, r.ay);
+    for (int l = 0; l < n_c; ++l)
+      lens_accum<FULL, J, true, false, MathK>(L[l].type, L[l], pool, r.x, r.y, 1.0, r.ax, r.ay, P.mk);
   } else {
     // MultiPlaneBase.ray_shooting_partial_comoving (multi_plane_base.py:195-233)
     double tx[J], ty[J];
@@ -926,7 +949,7 @@ LSIM_HD void ray_apply(const RayCfg& P, const LensC* L, const double* pool, int 
         tx[j] = r.x[j] * L[l].inv_T_z;
         ty[j] = r.y[j] * L[l].inv_T_z;
       }
-      lens_accum<FULL, J, false>(L[l].type, L[l], pool, tx, ty, -L[l].red2phys, r.ax, r.ay);
+      lens_accum<FULL, J, false, false, MathK>(L[l].type, L[l], pool, tx, ty, -L[l].red2phys, r.ax, r.ay, P.mk);
     }
   }
 }
@@ -1024,8 +1047,9 @@ LSIM_HD void light_prepare(const lsim_light_desc& d, const double* row, LightC& 
 
 // J points at once (sersic_utils.py:247-267 with R^2 in place of R: no square root is needed because
 // (R/Rs)^(1/n) = exp2(log2(R^2)/(2n) - log2(Rs)/n)).  -> e[j] = the profile at amp = 1
-template <int J>
-LSIM_HD void light_unit(int type, const LightC& G, const double (&x)[J], const double (&y)[J], double (&e)[J]) {
+template <int J, class KT>
+LSIM_HD void light_unit(int type, const LightC& G, const double (&x)[J], const double (&y)[J], double (&e)[J],
+                        const KT& K) {
   if (type == LSIM_LIGHT_SERSIC_ELLIPSE) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -1034,8 +1058,8 @@ LSIM_HD void light_unit(int type, const LightC& G, const double (&x)[J], const d
       const double xt = fma(G.c[2], x[j], fma(G.c[3], y[j], G.c[11]));
       const double yt = fma(G.c[3], x[j], fma(G.c[4], y[j], G.c[12]));
       const double R2c = max_nan(fma(yt, yt, xt * xt), 1e-8);  // R_ = max(1e-4, R)
-      const double k = exp2_fin_s(fma(G.c[5], log2_pos(R2c), G.c[6]));
-      double v = exp2_neg_s(fma(G.c[7], k, G.c[8]));  // k >= 0, c[7] <= 0: the argument is at most c[8] <= 256 * 1021
+      const double k = exp2_fin_s(fma(G.c[5], log2_pos(R2c, K), G.c[6]), K);
+      double v = exp2_fin_s(fma(G.c[7], k, G.c[8]), K);  // k >= 0, c[7] <= 0: the argument is at most c[8] <= 256 * 1021
       v = (R2c <= G.c[9]) ? v : 0.0;  // R_/Rs_ <= max_R_frac
       e[j] = (v == v) ? v : 0.0;      // nan_to_num (the exponent is bounded above, so no +inf)
     }
@@ -1055,7 +1079,7 @@ LSIM_HD double light_amp(int type, const LightC& G) { return type == LSIM_LIGHT_
 
 template <int J>
 LSIM_HD void light_eval(int type, const LightC& G, const double (&x)[J], const double (&y)[J], double (&v)[J]) {
-  light_unit<J>(type, G, x, y, v);
+  light_unit<J>(type, G, x, y, v, TableK());
   const double amp = light_amp(type, G);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -1064,10 +1088,11 @@ LSIM_HD void light_eval(int type, const LightC& G, const double (&x)[J], const d
 }
 
 // acc += sum_j amp * profile(x_j, y_j): the amplitude rides on the accumulation FMA
-template <int J>
-LSIM_HD void light_accum(int type, const LightC& G, const double (&x)[J], const double (&y)[J], double& acc) {
+template <int J, class KT>
+LSIM_HD void light_accum(int type, const LightC& G, const double (&x)[J], const double (&y)[J], double& acc,
+                         const KT& K) {
   double e[J];
-  light_unit<J>(type, G, x, y, e);
+  light_unit<J>(type, G, x, y, e, K);
   const double amp = light_amp(type, G);
 #if defined(__CUDA_ARCH__)
 #pragma unroll

@@ -21,7 +21,7 @@ int hm_ray_shoot(const lsim_lens_desc* lens, int n_lens, int multi_plane, double
     lens_prepare(lens[i], row, L[i], pool.data() + (size_t)off * kMaxSeries, series_tol);
     if (lens_type_has_series(lens[i])) ++off;
   }
-  RayCfg cfg{multi_plane, multi_plane ? 1.0 : alpha_scaling, T_ij_end, multi_plane ? 1.0 / T_z_source : 0.0};
+  RayCfg cfg{multi_plane, multi_plane ? 1.0 : alpha_scaling, T_ij_end, multi_plane ? 1.0 / T_z_source : 0.0, math_k()};
   // points go through the same J-batched code path the kernels use (J = 3), tail with J = 1
   int64_t i = 0;
   for (; i + 3 <= N; i += 3) {
@@ -63,15 +63,15 @@ int hm_ray_shoot_epl_shear(const lsim_lens_desc* lens, double alpha_scaling, con
   L[1].coef_off = kMaxSeries;
   lens_prepare(lens[1], row, L[1], pool.data() + kMaxSeries, series_tol);
   if (L[0].type != LSIM_LENS_EPL || L[1].type != LSIM_LENS_SHEAR) return 1;
-  RayCfg cfg{0, alpha_scaling, 0.0, 0.0};
+  RayCfg cfg{0, alpha_scaling, 0.0, 0.0, math_k()};
   for (int64_t i = 0; i < N; i += 3) {
     Rays<3> r;
     for (int j = 0; j < 3; ++j) {
       const int64_t k = i + j < N ? i + j : N - 1;
       ray_init<3, true>(cfg, j, x[k], y[k], r);
     }
-    ray_apply_head<false, 3, LT>(L, pool.data(), r);
-    ray_apply_tail<false, 3, LT>(L, pool.data(), r);
+    ray_apply_head<false, 3, LT>(cfg, L, pool.data(), r);
+    ray_apply_tail<false, 3, LT>(cfg, L, pool.data(), r);
     for (int j = 0; j < 3 && i + j < N; ++j) {
       ox[i + j] = fma(-r.ax[j], cfg.alpha_scaling, r.x[j]);
       oy[i + j] = fma(-r.ay[j], cfg.alpha_scaling, r.y[j]);
@@ -99,6 +99,10 @@ void hm_log2(const double* x, int64_t n, double* out) {
 }
 void hm_exp2(const double* x, int64_t n, double* out) {
   for (int64_t i = 0; i < n; ++i) out[i] = exp2_fin(x[i]);
+}
+void hm_exp2_s(const double* y, int64_t n, double* out) {
+  const MathK K = math_k();
+  for (int64_t i = 0; i < n; ++i) out[i] = exp2_fin_s(y[i], K);
 }
 void hm_exp2_neg(const double* x, int64_t n, double* out) {
   for (int64_t i = 0; i < n; ++i) out[i] = exp2_neg(x[i]);

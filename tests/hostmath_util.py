@@ -40,6 +40,7 @@ def lib():
         h.hm_log2.argtypes = [_dp, C.c_int64, _dp]
         h.hm_exp2.argtypes = [_dp, C.c_int64, _dp]
         h.hm_exp2_neg.argtypes = [_dp, C.c_int64, _dp]
+        h.hm_exp2_s.argtypes = [_dp, C.c_int64, _dp]
         h.hm_epl_terms.argtypes = [C.POINTER(_lib.LensDesc), _dp, C.c_double]
         h.hm_lens_jvp.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp]
         h.hm_light_jvp.argtypes = [C.POINTER(_lib.LightDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp]
@@ -126,6 +127,14 @@ def exp2(x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty_like(x)
     lib().hm_exp2(_p(x), x.size, _p(out))
+    return out
+
+
+def exp2_s(y):
+    """exp2 of a pre-scaled argument y = 256 x with the kernel-parameter coefficients (MathK)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.empty_like(y)
+    lib().hm_exp2_s(_p(y), y.size, _p(out))
     return out
 
 
