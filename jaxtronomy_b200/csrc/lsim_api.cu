@@ -1104,13 +1104,13 @@ int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, i
   dim3 grid((unsigned)n);
   Timed timed(kClsLike, st);
   if (ns <= 1)
-    k_likelihood<1><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
+    k_likelihood<1><<<grid, kLikeBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else if (ns <= 2)
-    k_likelihood<2><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
+    k_likelihood<2><<<grid, kLikeBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else if (ns <= 4)
-    k_likelihood<4><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
+    k_likelihood<4><<<grid, kLikeBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else
-    k_likelihood<8><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
+    k_likelihood<8><<<grid, kLikeBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   return after_launch("k_likelihood");
 }
 

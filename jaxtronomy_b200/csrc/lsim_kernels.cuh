@@ -725,21 +725,21 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Sum `n` per-thread values over the CTA; result valid in thread 0's vals[]. scratch: [n][kBlock/32] doubles.
-template <int N>
+// Sum `n` per-thread values over a CTA of BLK threads; result valid in thread 0's vals[]. scratch: [n][BLK/32] doubles.
+template <int N, int BLK = kBlock>
 __device__ __forceinline__ void block_sum(double (&vals)[N], double* scratch) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     double v = warp_sum(vals[i]);
-    if (lane == 0) scratch[i * (kBlock / 32) + wid] = v;
+    if (lane == 0) scratch[i * (BLK / 32) + wid] = v;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       double s = 0.0;
-      for (int w = 0; w < kBlock / 32; ++w) s += scratch[i * (kBlock / 32) + w];
+      for (int w = 0; w < BLK / 32; ++w) s += scratch[i * (BLK / 32) + w];
       vals[i] = s;
     }
   }
@@ -825,17 +825,26 @@ __device__ inline bool lu_solve(double* m, double* r, int n) {
 //   logL = -1/2 sum mask (model - data)^2 / C_D(model)                    (imaging_data.py:159-182)
 //          C_D(model) = noise_map^2  or  max(model,0)/t_exp + sigma_bkg^2 (image_noise.py:99-137)
 //   marg != 0: + 1/2 sign log|det M^-1|, -1e15 if singular               (de_lens.py:39-49)
-#ifndef LSIM_LIKE_UNROLL
-#define LSIM_LIKE_UNROLL 4
-#endif
-constexpr int kLikeUnroll = LSIM_LIKE_UNROLL;
+// CTA shape: 64 threads at <= 64 registers = 4,096 registers, exactly what three k_image CTAs (256 threads x 80
+// registers) leave free on an SM.  lsim_logl launches the likelihood of one buffer on a side stream while the image
+// kernel fills the other; with this shape its CTAs co-reside with the image kernel's (one per SM at a time) and its
+// memory stalls hide behind the image kernel's arithmetic.  Running alone, 16 such CTAs per SM with 6 pixels (n_lin = 1:
+// 18 independent loads) per thread and trip keep > 64 KB in flight per SM, enough for the HBM / L2 pipe.
+// The same shape is used whether or not the call overlaps, so results do not depend on the batch size.
+constexpr int kLikeBlock = 64;
+template <int NS>
+struct LikeUnroll {
+  static constexpr int value = NS <= 1 ? 6 : (NS <= 4 ? 4 : 2);
+  static constexpr int min_blocks = NS <= 2 ? 16 : (NS <= 4 ? 8 : 4);  // 64 / 128 / 255 registers per thread
+};
 
 template <int NS>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kLikeBlock, LikeUnroll<NS>::min_blocks)
 k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linear, int marg, double* __restrict__ logl,
              double* __restrict__ amps, double* __restrict__ model_out, const double* __restrict__ err_map) {
   constexpr int NM = NS * (NS + 1) / 2;
-  __shared__ double scratch[(NM + NS + 1) * (kBlock / 32)];
+  constexpr int kLikeUnroll = LikeUnroll<NS>::value;
+  __shared__ double scratch[(NM + NS + 1) * (kLikeBlock / 32)];
   __shared__ double s_amp[NS];
   __shared__ double s_marg;
   const int64_t bl = blockIdx.x;
@@ -850,11 +859,11 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
 #pragma unroll
     for (int i = 0; i < NM + NS; ++i) acc[i] = 0.0;
     // 4 pixels per thread per trip: all loads of a trip are issued before any arithmetic (latency hiding)
-    for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kBlock) {
+    for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kLikeBlock) {
       double a[kLikeUnroll][NS], wgt[kLikeUnroll], dat[kLikeUnroll];
 #pragma unroll
       for (int u = 0; u < kLikeUnroll; ++u) {
-        const int p = p0 + u * kBlock;
+        const int p = p0 + u * kLikeBlock;
         const bool use = p < npix && (!P.mask || P.mask[p]);
         wgt[u] = use ? __ldg(P.w_data + p) : 0.0;  // masked / out-of-range pixels get zero weight
         if (E && use) wgt[u] = 1.0 / (1.0 / wgt[u] + E[p]);  // 1 / (C_D + model_error), image_linear_solve.py:150
@@ -877,7 +886,7 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
         for (int i = 0; i < NS; ++i) acc[NM + i] += wd * a[u][i];
       }
     }
-    block_sum(acc, scratch);
+    block_sum<NM + NS, kLikeBlock>(acc, scratch);
     if (threadIdx.x == 0) {
       double M[NS * NS], M2[NS * NS], R[NS], ev[NS];
       int m = 0;
@@ -915,12 +924,12 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
   }
 
   double chi[1] = {0.0};
-  for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kBlock) {
+  for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kLikeBlock) {
     double mdl[kLikeUnroll], dat[kLikeUnroll], aux[kLikeUnroll];
     bool use[kLikeUnroll], valid[kLikeUnroll];
 #pragma unroll
     for (int u = 0; u < kLikeUnroll; ++u) {
-      const int p = p0 + u * kBlock;
+      const int p = p0 + u * kLikeBlock;
       valid[u] = p < npix;
       use[u] = valid[u] && (!P.mask || P.mask[p]);
       dat[u] = use[u] ? __ldg(P.data + p) : 0.0;
@@ -937,7 +946,7 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
     }
 #pragma unroll
     for (int u = 0; u < kLikeUnroll; ++u) {
-      const int p = p0 + u * kBlock;
+      const int p = p0 + u * kLikeBlock;
       if (model_out && valid[u]) model_out[(set0 + bl) * npix + p] = mdl[u];
       if (use[u]) {
         double cd = P.noise_map2 ? aux[u] : fma(fmax(mdl[u], 0.0), aux[u], P.bkg2);
@@ -947,7 +956,7 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
       }
     }
   }
-  block_sum(chi, scratch);
+  block_sum<1, kLikeBlock>(chi, scratch);
   if (threadIdx.x == 0) {
     double l = -chi[0] / 2 + P.logl_offset;
     if (linear && marg) l += s_marg;

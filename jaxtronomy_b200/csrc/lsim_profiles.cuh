@@ -237,7 +237,8 @@ LSIM_HD void epl_core(const LensC& L, const double* coef, const double (&a)[J], 
       b1[j] = fma(pp[j], b2[j], fma(qq[j], b1[j], ckm));
     }
   }
-  const double c0 = coef[0], c1 = k == 1 ? coef[1] : 0.0, cph = L.c[2], sph = L.c[3], rho = L.c[26];
+  // F_0 = 1 for every parameter set (hyp2f1_util.py:152): an immediate operand, not a register
+  const double c0 = 1.0, c1 = k == 1 ? coef[1] : 0.0, cph = L.c[2], sph = L.c[3], rho = L.c[26];
   const bool last = k == 1;
   double tr[J], ti[J];
   uint32_t worst = 0;  // largest |high word| of the factors: >= 0x7ff00000 <=> some factor is inf / nan

@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+for f in build_variants/*.so; do echo "== $f"; LSIM_LIB=$PWD/$f python bench.py --no-cpu --no-secondary --steps 3 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['avg_launch_ms'], d['roofline']['kernel_share_of_step'])"; done 2>&1 | tee gpurun_out/r2_variants.txt
