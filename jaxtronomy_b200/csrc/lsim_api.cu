@@ -119,25 +119,8 @@ struct FftConv {
   }
 };
 
-// Side stream + events of one lsim_logl call in flight: the likelihood of chunk i (HBM / L2-bound) runs on `side`
-// while the image and convolution kernels of chunk i+1 (fp64-bound) run on the caller's stream.
-struct Overlap {
-  cudaStream_t side = nullptr;
-  cudaEvent_t ready[2] = {nullptr, nullptr};  // images of buffer b are complete (recorded on the caller's stream)
-  cudaEvent_t done[2] = {nullptr, nullptr};   // the likelihood has consumed buffer b (recorded on `side`)
-  ~Overlap() {
-    for (int b = 0; b < 2; ++b) {
-      if (ready[b]) cudaEventDestroy(ready[b]);
-      if (done[b]) cudaEventDestroy(done[b]);
-    }
-    if (side) cudaStreamDestroy(side);
-  }
-};
-
 struct lsim_plan {
   PlanDev dev;
-  mutable std::mutex overlap_mu;
-  mutable std::vector<Overlap*> overlap_pool;  // idle contexts; one is taken per call, so calls stay re-entrant
   std::vector<double> kernel_host, kernel_hi_host;  // host copies: the tiled convolution takes its weights by value
   FftConv* fft_lo = nullptr;  // pixel-grid kernel, when it takes the FFT path
   FftConv* fft_hi = nullptr;  // supersampled kernel, likewise
@@ -167,7 +150,6 @@ struct lsim_plan {
   std::vector<double> kernel_flip_host;
 
   ~lsim_plan() {
-    for (Overlap* o : overlap_pool) delete o;
     for (void* p : owned) cudaFree(p);
     delete fft_lo;
     delete fft_hi;
@@ -602,8 +584,7 @@ size_t per_set_bytes(const lsim_plan* plan, bool need_conv_out) {
   return n * sizeof(double) + prefix_bytes(plan);
 }
 
-// sets per workspace: lsim_logl splits it into two buffers of 8 x SMs sets (likelihood of one overlaps the other)
-int64_t chunk_sets(const lsim_plan* plan) { return (int64_t)plan->n_sm * 16; }
+int64_t chunk_sets(const lsim_plan* plan) { return (int64_t)plan->n_sm * 8; }
 
 template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = RuntimeTypes>
 int launch_image_k(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
@@ -1060,57 +1041,22 @@ int run_chunk(const lsim_plan* plan, const double* params, int64_t s0, int64_t n
   return after_launch("k_point_sources");
 }
 
-Overlap* overlap_acquire(const lsim_plan* plan) {
-  {
-    std::lock_guard<std::mutex> lk(plan->overlap_mu);
-    if (!plan->overlap_pool.empty()) {
-      Overlap* o = plan->overlap_pool.back();
-      plan->overlap_pool.pop_back();
-      return o;
-    }
-  }
-  Overlap* o = new (std::nothrow) Overlap();
-  if (!o) return nullptr;
-  int least = 0, greatest = 0;
-  cudaDeviceGetStreamPriorityRange(&least, &greatest);
-  bool ok = cudaStreamCreateWithPriority(&o->side, cudaStreamNonBlocking, greatest) == cudaSuccess;
-  for (int b = 0; b < 2 && ok; ++b)
-    ok = cudaEventCreateWithFlags(&o->ready[b], cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&o->done[b], cudaEventDisableTiming) == cudaSuccess;
-  if (!ok) {
-    cudaGetLastError();
-    delete o;
-    return nullptr;
-  }
-  return o;
-}
-
-void overlap_release(const lsim_plan* plan, Overlap* o) {
-  std::lock_guard<std::mutex> lk(plan->overlap_mu);
-  plan->overlap_pool.push_back(o);
-}
-
-bool overlap_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("LSIM_NO_OVERLAP");
-    return !(e && *e && *e != '0');
-  }();
-  return on;
-}
-
 int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, int64_t n, int linear, int marg,
                       double* logl, double* amps, double* model, const double* err, cudaStream_t st) {
   const int ns = plan->dev.n_slots;
-  dim3 grid((unsigned)n);
   Timed timed(kClsLike, st);
+#define LSIM_LIKE_LAUNCH(NS)                                                                                          \
+  k_likelihood<NS, LikeSets<NS>::value><<<(unsigned)((n + LikeSets<NS>::value - 1) / LikeSets<NS>::value), kBlock, 0, st>>>( \
+      plan->dev, conv, set0, (int)n, linear, marg, logl, amps, model, err)
   if (ns <= 1)
-    k_likelihood<1><<<grid, kLikeBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
+    LSIM_LIKE_LAUNCH(1);
   else if (ns <= 2)
-    k_likelihood<2><<<grid, kLikeBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
+    LSIM_LIKE_LAUNCH(2);
   else if (ns <= 4)
-    k_likelihood<4><<<grid, kLikeBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
+    LSIM_LIKE_LAUNCH(4);
   else
-    k_likelihood<8><<<grid, kLikeBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
+    LSIM_LIKE_LAUNCH(8);
+#undef LSIM_LIKE_LAUNCH
   return after_launch("k_likelihood");
 }
 
@@ -1349,51 +1295,27 @@ int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear
   if (!workspace || chunk < 1) return LSIM_E_WORKSPACE;
   if (chunk > chunk_sets(plan)) chunk = chunk_sets(plan);
   const size_t img = (size_t)D.nx * D.ny * D.n_slots, sub = img * D.ss * D.ss;
-  // Two half-size buffers when the batch spans more than one of them: the likelihood of one buffer (HBM / L2-bound,
-  // 5-6 % of the step when serialised) runs on a high-priority side stream while the fp64-bound kernels fill the
-  // other.  All work is ordered after everything already on `st`, and `st` waits for the side stream before returning.
-  Overlap* ov = nullptr;
-  if (overlap_enabled() && chunk >= 2 && B > chunk / 2) ov = overlap_acquire(plan);
-  const int nbuf = ov ? 2 : 1;
-  chunk /= nbuf;
-  double* ws0 = static_cast<double*>(workspace);
-  const size_t buf_doubles = (size_t)chunk * per / sizeof(double);
-  int rc = LSIM_OK;
-  int64_t i = 0;
-  for (int64_t s0 = 0; s0 < B && rc == LSIM_OK; s0 += chunk, ++i) {
-    const int b = (int)(i % nbuf);
+  // layout: [prepared constants | PSF error map] [U | Usub, Hsub (supersampled conv only) | C]; without a PSF the images
+  // land in U directly.  (Running the likelihood of one half buffer on a side stream while the fp64-bound kernels fill
+  // the other was measured twice in round 2 and bought nothing: DESIGN.md 4.)
+  double* ws = static_cast<double*>(workspace);
+  double* main_ws = ws + (size_t)chunk * prefix_bytes(plan) / sizeof(double);  // run_chunk skips the same prefix
+  double* err = D.ps_var ? ws + (size_t)chunk * prep_bytes(plan) / sizeof(double) : nullptr;  // [chunk][npix]
+  double* C = conv ? main_ws + (size_t)chunk * img + (D.ss_conv ? 2 * (size_t)chunk * sub : 0) : main_ws;
+  for (int64_t s0 = 0; s0 < B; s0 += chunk) {
     const int64_t n = B - s0 < chunk ? B - s0 : chunk;
-    // layout of a buffer: [prepared constants | PSF error map] [U | Usub, Hsub (supersampled conv only) | C];
-    // without a PSF the images land in U directly
-    double* ws = ws0 + (size_t)b * buf_doubles;
-    double* main_ws = ws + (size_t)chunk * prefix_bytes(plan) / sizeof(double);  // run_chunk skips the same prefix
-    double* err = D.ps_var ? ws + (size_t)chunk * prep_bytes(plan) / sizeof(double) : nullptr;  // [chunk][npix]
-    double* C = conv ? main_ws + (size_t)chunk * img + (D.ss_conv ? 2 * (size_t)chunk * sub : 0) : main_ws;
-    if (ov && i >= 2 && cudaStreamWaitEvent(st, ov->done[b], 0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "wait done");
-    if (rc == LSIM_OK) rc = run_chunk(plan, params, s0, n, chunk, ws, C, st);
-    if (rc == LSIM_OK && err) {
+    int rc = run_chunk(plan, params, s0, n, chunk, ws, C, st);
+    if (rc != LSIM_OK) return rc;
+    if (err) {
       Timed timed(kClsOther, st);
       k_ps_error_map<<<(unsigned)n, kBlock, 0, st>>>(D, params, s0, err);
       rc = after_launch("k_ps_error_map");
+      if (rc != LSIM_OK) return rc;
     }
-    cudaStream_t ls = st;
-    if (rc == LSIM_OK && ov) {
-      if (cudaEventRecord(ov->ready[b], st) != cudaSuccess || cudaStreamWaitEvent(ov->side, ov->ready[b], 0) != cudaSuccess)
-        rc = cuda_fail(cudaGetLastError(), "record ready");
-      ls = ov->side;
-    }
-    if (rc == LSIM_OK) rc = launch_likelihood(plan, C, s0, n, linear_solve, source_marg, logl, amps, model, err, ls);
-    if (rc == LSIM_OK && ov && cudaEventRecord(ov->done[b], ov->side) != cudaSuccess)
-      rc = cuda_fail(cudaGetLastError(), "record done");
+    rc = launch_likelihood(plan, C, s0, n, linear_solve, source_marg, logl, amps, model, err, st);
+    if (rc != LSIM_OK) return rc;
   }
-  if (ov) {
-    // join: the caller's stream continues only after the side stream has finished (also on the error path, so that
-    // the buffers are not reused while a likelihood still reads them)
-    for (int b = 0; b < 2 && b < i; ++b)
-      if (cudaStreamWaitEvent(st, ov->done[b], 0) != cudaSuccess && rc == LSIM_OK) rc = cuda_fail(cudaGetLastError(), "join");
-    overlap_release(plan, ov);
-  }
-  return rc;
+  return LSIM_OK;
 }
 
 int lsim_psf_error_map(const lsim_plan* plan, const double* params, int64_t B, double* error_map, void* stream) {

@@ -825,144 +825,184 @@ __device__ inline bool lu_solve(double* m, double* r, int n) {
 //   logL = -1/2 sum mask (model - data)^2 / C_D(model)                    (imaging_data.py:159-182)
 //          C_D(model) = noise_map^2  or  max(model,0)/t_exp + sigma_bkg^2 (image_noise.py:99-137)
 //   marg != 0: + 1/2 sign log|det M^-1|, -1e15 if singular               (de_lens.py:39-49)
-// CTA shape: 64 threads at <= 64 registers = 4,096 registers, exactly what three k_image CTAs (256 threads x 80
-// registers) leave free on an SM.  lsim_logl launches the likelihood of one buffer on a side stream while the image
-// kernel fills the other; with this shape its CTAs co-reside with the image kernel's (one per SM at a time) and its
-// memory stalls hide behind the image kernel's arithmetic.  Running alone, 16 such CTAs per SM with 6 pixels (n_lin = 1:
-// 18 independent loads) per thread and trip keep > 64 KB in flight per SM, enough for the HBM / L2 pipe.
-// The same shape is used whether or not the call overlaps, so results do not depend on the batch size.
-constexpr int kLikeBlock = 64;
+#ifndef LSIM_LIKE_UNROLL
+#define LSIM_LIKE_UNROLL 4
+#endif
+constexpr int kLikeUnroll = LSIM_LIKE_UNROLL;
+
+// Sets per CTA.  Every pixel of a set needs three plan-constant values besides its own basis images (1/C_D(data),
+// data, 1/t_exp or noise_map^2): with one set per CTA those re-reads are two thirds of the kernel's L2 traffic
+// (4 x 259 KB of constants against 2 x 259 KB of images per set at n_lin = 1; ncu likelihood_r1n: 6.7 TB/s of L2 reads
+// behind 2.2 TB/s of DRAM reads).  A CTA that walks SPC sets together loads each constant once per SPC sets.  The
+// per-set accumulators, the pixel -> thread map and the reduction tree do not depend on SPC, so a set's result is
+// bit-identical however the batch is grouped.
 template <int NS>
-struct LikeUnroll {
-  static constexpr int value = NS <= 1 ? 6 : (NS <= 4 ? 4 : 2);
-  static constexpr int min_blocks = NS <= 2 ? 16 : (NS <= 4 ? 8 : 4);  // 64 / 128 / 255 registers per thread
+struct LikeSets {
+  static constexpr int value = NS <= 1 ? 4 : (NS <= 2 ? 2 : 1);
 };
 
-template <int NS>
-__global__ void __launch_bounds__(kLikeBlock, LikeUnroll<NS>::min_blocks)
-k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linear, int marg, double* __restrict__ logl,
-             double* __restrict__ amps, double* __restrict__ model_out, const double* __restrict__ err_map) {
-  constexpr int NM = NS * (NS + 1) / 2;
-  constexpr int kLikeUnroll = LikeUnroll<NS>::value;
-  __shared__ double scratch[(NM + NS + 1) * (kLikeBlock / 32)];
-  __shared__ double s_amp[NS];
-  __shared__ double s_marg;
-  const int64_t bl = blockIdx.x;
+template <int NS, int SPC>
+__global__ void __launch_bounds__(kBlock)
+k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int n_sets, int linear, int marg,
+             double* __restrict__ logl, double* __restrict__ amps, double* __restrict__ model_out,
+             const double* __restrict__ err_map) {
+  constexpr int NM = NS * (NS + 1) / 2, NA = NM + NS;
+  __shared__ double scratch[(SPC * NA + 1) * (kBlock / 32)];
+  __shared__ double s_amp[SPC][NS];
+  __shared__ double s_marg[SPC];
   const int npix = P.nx * P.ny;
   const int ns = P.n_slots;
-  const double* A = conv + bl * ns * (int64_t)npix;
-  // PSF error map of this set (sigma^2, or null): added to C_D(data) in the weights and as |.| to C_D(model) in chi^2
-  const double* E = err_map ? err_map + bl * (int64_t)npix : nullptr;
+  const int64_t bl0 = (int64_t)blockIdx.x * SPC;
+  // sets past the end of the batch alias the last one: they are computed and thrown away
+  const double* A[SPC];
+  const double* E[SPC];  // PSF error map of the set (sigma^2, or null): added to C_D(data) in the weights and as |.| to
+                         // C_D(model) in chi^2
+  bool live[SPC];
+#pragma unroll
+  for (int i = 0; i < SPC; ++i) {
+    live[i] = bl0 + i < n_sets;
+    const int64_t bl = live[i] ? bl0 + i : (int64_t)n_sets - 1;
+    A[i] = conv + bl * ns * (int64_t)npix;
+    E[i] = err_map ? err_map + bl * (int64_t)npix : nullptr;
+  }
 
   if (linear) {
-    double acc[NM + NS];
+    double acc[SPC][NA];
 #pragma unroll
-    for (int i = 0; i < NM + NS; ++i) acc[i] = 0.0;
+    for (int i = 0; i < SPC; ++i)
+#pragma unroll
+      for (int m = 0; m < NA; ++m) acc[i][m] = 0.0;
     // 4 pixels per thread per trip: all loads of a trip are issued before any arithmetic (latency hiding)
-    for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kLikeBlock) {
-      double a[kLikeUnroll][NS], wgt[kLikeUnroll], dat[kLikeUnroll];
+    for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kBlock) {
+      double a[SPC][kLikeUnroll][NS], w0[kLikeUnroll], dat[kLikeUnroll];
+      bool use[kLikeUnroll];
 #pragma unroll
       for (int u = 0; u < kLikeUnroll; ++u) {
-        const int p = p0 + u * kLikeBlock;
-        const bool use = p < npix && (!P.mask || P.mask[p]);
-        wgt[u] = use ? __ldg(P.w_data + p) : 0.0;  // masked / out-of-range pixels get zero weight
-        if (E && use) wgt[u] = 1.0 / (1.0 / wgt[u] + E[p]);  // 1 / (C_D + model_error), image_linear_solve.py:150
-        dat[u] = use ? __ldg(P.data + p) : 0.0;
+        const int p = p0 + u * kBlock;
+        use[u] = p < npix && (!P.mask || P.mask[p]);
+        w0[u] = use[u] ? __ldg(P.w_data + p) : 0.0;  // masked / out-of-range pixels get zero weight
+        dat[u] = use[u] ? __ldg(P.data + p) : 0.0;
 #pragma unroll
-        for (int k = 0; k < NS; ++k) a[u][k] = (use && k < ns) ? A[(int64_t)k * npix + p] : 0.0;
+        for (int i = 0; i < SPC; ++i)
+#pragma unroll
+          for (int k = 0; k < NS; ++k) a[i][u][k] = (use[u] && k < ns) ? A[i][(int64_t)k * npix + p] : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < kLikeUnroll; ++u) {
+      for (int i = 0; i < SPC; ++i) {
 #pragma unroll
-        for (int k = 0; k < NS; ++k) a[u][k] = nan_to_num(a[u][k]);
-        const double wd = wgt[u] * dat[u];
-        int m = 0;
+        for (int u = 0; u < kLikeUnroll; ++u) {
+          double wgt = w0[u];
+          if (E[i] && use[u]) wgt = 1.0 / (1.0 / wgt + E[i][p0 + u * kBlock]);  // 1 / (C_D + model_error), image_linear_solve.py:150
 #pragma unroll
-        for (int i = 0; i < NS; ++i) {
+          for (int k = 0; k < NS; ++k) a[i][u][k] = nan_to_num(a[i][u][k]);
+          const double wd = wgt * dat[u];
+          int m = 0;
 #pragma unroll
-          for (int j = i; j < NS; ++j) acc[m++] += wgt[u] * a[u][i] * a[u][j];
+          for (int r = 0; r < NS; ++r) {
+#pragma unroll
+            for (int c = r; c < NS; ++c) acc[i][m++] += wgt * a[i][u][r] * a[i][u][c];
+          }
+#pragma unroll
+          for (int r = 0; r < NS; ++r) acc[i][NM + r] += wd * a[i][u][r];
         }
-#pragma unroll
-        for (int i = 0; i < NS; ++i) acc[NM + i] += wd * a[u][i];
       }
     }
-    block_sum<NM + NS, kLikeBlock>(acc, scratch);
+#pragma unroll
+    for (int i = 0; i < SPC; ++i) block_sum(acc[i], scratch + i * NA * (kBlock / 32));
     if (threadIdx.x == 0) {
-      double M[NS * NS], M2[NS * NS], R[NS], ev[NS];
-      int m = 0;
-      for (int i = 0; i < NS; ++i)
-        for (int j = i; j < NS; ++j) {
-          M[i * NS + j] = acc[m];
-          M[j * NS + i] = acc[m];
-          ++m;
+      for (int i = 0; i < SPC; ++i) {
+        double M[NS * NS], M2[NS * NS], R[NS], ev[NS];
+        int m = 0;
+        for (int r = 0; r < NS; ++r)
+          for (int c = r; c < NS; ++c) {
+            M[r * NS + c] = acc[i][m];
+            M[c * NS + r] = acc[i][m];
+            ++m;
+          }
+        // work on the leading ns x ns block, repacked contiguously
+        for (int r = 0; r < ns; ++r)
+          for (int c = 0; c < ns; ++c) M2[r * ns + c] = M[r * NS + c];
+        for (int r = 0; r < ns; ++r) R[r] = acc[i][NM + r];
+        double Mw[NS * NS];
+        for (int r = 0; r < ns * ns; ++r) Mw[r] = M2[r];
+        sym_eigenvalues(Mw, ns, ev);
+        double emax = 0.0, emin = HUGE_VAL, logdet = 0.0, sign = 1.0;
+        for (int r = 0; r < ns; ++r) {
+          double e = fabs(ev[r]);
+          emax = fmax(emax, e);
+          emin = fmin(emin, e);
+          logdet += log(e);
+          if (ev[r] < 0) sign = -sign;
+          if (ev[r] == 0) sign = 0.0;
         }
-      // work on the leading ns x ns block, repacked contiguously
-      for (int i = 0; i < ns; ++i)
-        for (int j = 0; j < ns; ++j) M2[i * ns + j] = M[i * NS + j];
-      for (int i = 0; i < ns; ++i) R[i] = acc[NM + i];
-      double Mw[NS * NS];
-      for (int i = 0; i < ns * ns; ++i) Mw[i] = M2[i];
-      sym_eigenvalues(Mw, ns, ev);
-      double emax = 0.0, emin = HUGE_VAL, logdet = 0.0, sign = 1.0;
-      for (int i = 0; i < ns; ++i) {
-        double e = fabs(ev[i]);
-        emax = fmax(emax, e);
-        emin = fmin(emin, e);
-        logdet += log(e);
-        if (ev[i] < 0) sign = -sign;
-        if (ev[i] == 0) sign = 0.0;
+        bool stable = (emax / emin) < 5.0 / DBL_EPSILON;  // NaN compares false, like jnp
+        bool ok = stable && lu_solve(M2, R, ns);
+        if (ok)
+          for (int r = 0; r < ns; ++r) ok = ok && (fabs(R[r]) <= DBL_MAX);
+        for (int r = 0; r < NS; ++r) s_amp[i][r] = (ok && r < ns) ? R[r] : 0.0;
+        // log det(M_inv) = -log det(M); M_inv = 0 (unstable) -> sign 0 -> -1e15
+        s_marg[i] = (stable && sign != 0.0 && (logdet == logdet)) ? sign * (-logdet) / 2 : -1e15;
       }
-      bool stable = (emax / emin) < 5.0 / DBL_EPSILON;  // NaN compares false, like jnp
-      bool ok = stable && lu_solve(M2, R, ns);
-      if (ok)
-        for (int i = 0; i < ns; ++i) ok = ok && (fabs(R[i]) <= DBL_MAX);
-      for (int i = 0; i < NS; ++i) s_amp[i] = (ok && i < ns) ? R[i] : 0.0;
-      // log det(M_inv) = -log det(M); M_inv = 0 (unstable) -> sign 0 -> -1e15
-      s_marg = (stable && sign != 0.0 && (logdet == logdet)) ? sign * (-logdet) / 2 : -1e15;
     }
     __syncthreads();
   }
 
-  double chi[1] = {0.0};
-  for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kLikeBlock) {
-    double mdl[kLikeUnroll], dat[kLikeUnroll], aux[kLikeUnroll];
+  double chi[SPC];
+#pragma unroll
+  for (int i = 0; i < SPC; ++i) chi[i] = 0.0;
+  for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kBlock) {
+    double mdl[SPC][kLikeUnroll], dat[kLikeUnroll], aux[kLikeUnroll];
     bool use[kLikeUnroll], valid[kLikeUnroll];
 #pragma unroll
     for (int u = 0; u < kLikeUnroll; ++u) {
-      const int p = p0 + u * kLikeBlock;
+      const int p = p0 + u * kBlock;
       valid[u] = p < npix;
       use[u] = valid[u] && (!P.mask || P.mask[p]);
       dat[u] = use[u] ? __ldg(P.data + p) : 0.0;
       aux[u] = use[u] ? (P.noise_map2 ? __ldg(P.noise_map2 + p) : __ldg(P.inv_exposure + p)) : 1.0;
-      double m = 0.0;
-      if (linear) {
 #pragma unroll
-        for (int k = 0; k < NS; ++k)
-          if (k < ns && use[u]) m += s_amp[k] * nan_to_num(A[(int64_t)k * npix + p]);
-      } else if (valid[u]) {
-        for (int k = 0; k < ns; ++k) m += A[(int64_t)k * npix + p];
+      for (int i = 0; i < SPC; ++i) {
+        double m = 0.0;
+        if (linear) {
+#pragma unroll
+          for (int k = 0; k < NS; ++k)
+            if (k < ns && use[u]) m += s_amp[i][k] * nan_to_num(A[i][(int64_t)k * npix + p]);
+        } else if (valid[u]) {
+          for (int k = 0; k < ns; ++k) m += A[i][(int64_t)k * npix + p];
+        }
+        mdl[i][u] = m;
       }
-      mdl[u] = m;
     }
 #pragma unroll
-    for (int u = 0; u < kLikeUnroll; ++u) {
-      const int p = p0 + u * kLikeBlock;
-      if (model_out && valid[u]) model_out[(set0 + bl) * npix + p] = mdl[u];
-      if (use[u]) {
-        double cd = P.noise_map2 ? aux[u] : fma(fmax(mdl[u], 0.0), aux[u], P.bkg2);
-        if (E) cd += fabs(E[p]);  // imaging_data.py:180
-        const double d = mdl[u] - dat[u];
-        chi[0] += d * d / cd;
+    for (int i = 0; i < SPC; ++i) {
+#pragma unroll
+      for (int u = 0; u < kLikeUnroll; ++u) {
+        const int p = p0 + u * kBlock;
+        if (model_out && valid[u] && live[i]) model_out[(set0 + bl0 + i) * npix + p] = mdl[i][u];
+        if (use[u]) {
+          double cd = P.noise_map2 ? aux[u] : fma(fmax(mdl[i][u], 0.0), aux[u], P.bkg2);
+          if (E[i]) cd += fabs(E[i][p]);  // imaging_data.py:180
+          const double d = mdl[i][u] - dat[u];
+          chi[i] += d * d / cd;
+        }
       }
     }
   }
-  block_sum<1, kLikeBlock>(chi, scratch);
+#pragma unroll
+  for (int i = 0; i < SPC; ++i) {
+    double c1[1] = {chi[i]};
+    block_sum(c1, scratch);
+    chi[i] = c1[0];
+  }
   if (threadIdx.x == 0) {
-    double l = -chi[0] / 2 + P.logl_offset;
-    if (linear && marg) l += s_marg;
-    logl[set0 + bl] = l;
-    if (amps && linear)
-      for (int k = 0; k < ns; ++k) amps[(set0 + bl) * ns + k] = s_amp[k];
+    for (int i = 0; i < SPC; ++i) {
+      if (!live[i]) continue;
+      double l = -chi[i] / 2 + P.logl_offset;
+      if (linear && marg) l += s_marg[i];
+      logl[set0 + bl0 + i] = l;
+      if (amps && linear)
+        for (int k = 0; k < ns; ++k) amps[(set0 + bl0 + i) * ns + k] = s_amp[i][k];
+    }
   }
 }
 
