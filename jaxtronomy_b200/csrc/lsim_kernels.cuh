@@ -830,15 +830,15 @@ __device__ inline bool lu_solve(double* m, double* r, int n) {
 #endif
 constexpr int kLikeUnroll = LSIM_LIKE_UNROLL;
 
-// Sets per CTA.  Every pixel of a set needs three plan-constant values besides its own basis images (1/C_D(data),
-// data, 1/t_exp or noise_map^2): with one set per CTA those re-reads are two thirds of the kernel's L2 traffic
-// (4 x 259 KB of constants against 2 x 259 KB of images per set at n_lin = 1; ncu likelihood_r1n: 6.7 TB/s of L2 reads
-// behind 2.2 TB/s of DRAM reads).  A CTA that walks SPC sets together loads each constant once per SPC sets.  The
-// per-set accumulators, the pixel -> thread map and the reduction tree do not depend on SPC, so a set's result is
-// bit-identical however the batch is grouped.
+// Sets per CTA (SPC).  Every pixel of a set needs three plan-constant values besides its own basis images (1/C_D(data),
+// data, 1/t_exp or noise_map^2): with one set per CTA those re-reads are two thirds of the kernel's L2 traffic (4 x 259 KB
+// of constants against 2 x 259 KB of images per set at n_lin = 1).  A CTA that walks SPC sets together loads each
+// constant once per SPC sets -- measured in round 2 (profiles/r2_likelihood.md): SPC = 4 halves the L2 traffic but leaves
+// 2 CTAs per SM, and the kernel, which lives on memory-level parallelism (long_scoreboard is its top stall), went from
+// 273 to 418 us per 1184 sets.  SPC = 1 (8 CTAs per SM) stays; the template parameter is kept for the record.
 template <int NS>
 struct LikeSets {
-  static constexpr int value = NS <= 1 ? 4 : (NS <= 2 ? 2 : 1);
+  static constexpr int value = 1;
 };
 
 template <int NS, int SPC>
