@@ -128,6 +128,7 @@ struct lsim_plan {
   bool full = false;
   int n_series = 0;
   int sig = -1;  // index of the specialised image kernel for this model, or -1
+  bool fold = false;  // the model and the grid are inside k_image_fold's scope (lsim_kernels.cuh)
   bool has_image = false, has_data = false;
   bool f32 = false;  // LSIM_PRECISION_F32: the image kernel runs in single precision
   size_t image_smem = 0;
@@ -199,6 +200,8 @@ int configure_kernels() {
 }
 
 int find_signature(const lsim_plan_desc* d);  // defined with the kernel-variant tables below
+int effective_lens_type(const lsim_lens_desc& d);
+int effective_light_type(const lsim_light_desc& d);
 int fft_conv_create(int nx, int ny, int K, const double* kernel, int mode, FftConv** out);  // defined with the convolutions
 
 double series_tol_default() {
@@ -354,6 +357,34 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
     const size_t nsub = (size_t)d->nx * d->ny * d->ss * d->ss, npix = (size_t)d->nx * d->ny;
     TRY(p->upload(d->x_sub, nsub, &D.x_sub));
     TRY(p->upload(d->y_sub, nsub, &D.y_sub));
+    {  // are the coordinates affine in the (row, column) indices of the supersampled grid?  (every RegularGrid is)
+      const int64_t W = (int64_t)d->nx * d->ss, H = (int64_t)d->ny * d->ss;
+      const double* c2[2] = {d->x_sub, d->y_sub};
+      double g[2][3];
+      bool ok = true;
+      for (int k = 0; k < 2 && ok; ++k) {
+        const double* v = c2[k];
+        g[k][0] = v[0];
+        g[k][1] = H > 1 ? (v[(H - 1) * W] - v[0]) / (double)(H - 1) : 0.0;
+        g[k][2] = W > 1 ? (v[W - 1] - v[0]) / (double)(W - 1) : 0.0;
+        double vmax = 0.0;
+        for (int64_t i = 0; i < H * W; ++i) vmax = fabs(v[i]) > vmax ? fabs(v[i]) : vmax;
+        const double tol = 16.0 * DBL_EPSILON * (vmax > 0 ? vmax : 1.0);
+        for (int64_t r = 0; r < H && ok; ++r)
+          for (int64_t c = 0; c < W; ++c)
+            if (!(fabs(fma((double)r, g[k][1], fma((double)c, g[k][2], g[k][0])) - v[r * W + c]) <= tol)) {
+              ok = false;
+              break;
+            }
+      }
+      D.grid_affine = ok ? 1 : 0;
+      D.gx0 = g[0][0];
+      D.gxi = g[0][1];
+      D.gxj = g[0][2];
+      D.gy0 = g[1][0];
+      D.gyi = g[1][1];
+      D.gyj = g[1][2];
+    }
     D.n_eval = (int32_t)npix;
     if (d->eval_mask) {
       std::vector<int32_t> list;
@@ -367,6 +398,19 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
     D.conv_mode = d->conv_mode;
     D.K = (d->conv_mode != LSIM_CONV_NONE && d->kernel) ? d->kernel_size : 0;
     D.image_scale = d->image_scale;
+    {  // k_image_fold: one EPL + SHEAR / CONVERGENCE, one or two Sersic components, affine grid, no sub-frame
+      int n_epl = 0;
+      bool ok = !d->multi_plane && !p->f32 && D.grid_affine && !D.eval_list && D.n_eval == (int32_t)npix &&
+                !d->supersampled_conv && d->ss >= 1 && d->ss <= 3 && d->n_light >= 1 && d->n_light <= 2 &&
+                d->n_slots <= d->n_light && !getenv("LSIM_NO_FOLD");
+      for (int i = 0; ok && i < d->n_lens; ++i) {
+        const int t = effective_lens_type(d->lens[i]);
+        if (t == LSIM_LENS_EPL) ++n_epl;
+        else if (t != LSIM_LENS_SHEAR && t != LSIM_LENS_CONVERGENCE) ok = false;
+      }
+      for (int i = 0; ok && i < d->n_light; ++i) ok = effective_light_type(d->light[i]) == LSIM_LIGHT_SERSIC_ELLIPSE;
+      p->fold = ok && n_epl == 1;
+    }
     if (d->conv_mode != LSIM_CONV_NONE) {
       if (d->kernel) {
         TRY(p->upload(d->kernel, (size_t)d->kernel_size * d->kernel_size, &D.kernel));
@@ -737,7 +781,7 @@ int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int6
   // ceil(w.x) waves (1184 sets x 1 CTA on 148 SMs x 3 resident = 2.67 waves took the time of 3).  Ask for >= 16
   // waves (32 by default, LSIM_IMAGE_WAVES): the partial last wave then costs ~1 %; the per-set constants come
   // from k_prepare, so small CTAs cost nothing extra.
-  const int64_t resident = (int64_t)plan->n_sm * LSIM_IMAGE_MIN_BLOCKS;
+  const int64_t resident = (int64_t)plan->n_sm * ((plan->fold && !sub_out) ? LSIM_FOLD_MIN_BLOCKS : LSIM_IMAGE_MIN_BLOCKS);
   static const int64_t waves = [] {
     const char* e = getenv("LSIM_IMAGE_WAVES");
     const int64_t v = (e && *e) ? atoll(e) : 32;
@@ -761,6 +805,21 @@ int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int6
     }
   }
   if (plan->f32) return launch_image_f32(plan, params, set0, n, ppt, tiles, scale, out, st, prep);
+  if (plan->fold && !sub_out) {
+    const int nl = plan->dev.n_light, ss = plan->dev.ss;
+    dim3 grid((unsigned)tiles, (unsigned)n);
+    Timed timed(kClsImage, st);
+#define LSIM_FOLD_CASE(NSV, SSV, NLV)                                                                               \
+  if (ns == NSV && ss == SSV && nl == NLV) {                                                                        \
+    k_image_fold<NSV, SSV, NLV><<<grid, kImageBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out, \
+                                                                             prep, plan->n_series);                 \
+    return after_launch("k_image_fold");                                                                            \
+  }
+    LSIM_FOLD_CASE(1, 3, 1) LSIM_FOLD_CASE(1, 3, 2) LSIM_FOLD_CASE(2, 3, 2)
+    LSIM_FOLD_CASE(1, 2, 1) LSIM_FOLD_CASE(1, 2, 2) LSIM_FOLD_CASE(2, 2, 2)
+    LSIM_FOLD_CASE(1, 1, 1) LSIM_FOLD_CASE(1, 1, 2) LSIM_FOLD_CASE(2, 1, 2)
+#undef LSIM_FOLD_CASE
+  }
   int rc = LSIM_E_UNSUPPORTED;
   switch ((sub_out || plan->dev.eval_list) ? kSigNone : plan->sig) {
     case kSigEplShear_S: rc = launch_image_sig<false, LT_EplShear, GT_S>(plan, params, set0, n, ppt, tiles, scale, out, sub_out, st, prep); break;
@@ -1044,19 +1103,16 @@ int run_chunk(const lsim_plan* plan, const double* params, int64_t s0, int64_t n
 int launch_likelihood(const lsim_plan* plan, const double* conv, int64_t set0, int64_t n, int linear, int marg,
                       double* logl, double* amps, double* model, const double* err, cudaStream_t st) {
   const int ns = plan->dev.n_slots;
+  dim3 grid((unsigned)n);
   Timed timed(kClsLike, st);
-#define LSIM_LIKE_LAUNCH(NS)                                                                                          \
-  k_likelihood<NS, LikeSets<NS>::value><<<(unsigned)((n + LikeSets<NS>::value - 1) / LikeSets<NS>::value), kBlock, 0, st>>>( \
-      plan->dev, conv, set0, (int)n, linear, marg, logl, amps, model, err)
   if (ns <= 1)
-    LSIM_LIKE_LAUNCH(1);
+    k_likelihood<1><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else if (ns <= 2)
-    LSIM_LIKE_LAUNCH(2);
+    k_likelihood<2><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else if (ns <= 4)
-    LSIM_LIKE_LAUNCH(4);
+    k_likelihood<4><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   else
-    LSIM_LIKE_LAUNCH(8);
-#undef LSIM_LIKE_LAUNCH
+    k_likelihood<8><<<grid, kBlock, 0, st>>>(plan->dev, conv, set0, linear, marg, logl, amps, model, err);
   return after_launch("k_likelihood");
 }
 

@@ -43,6 +43,10 @@ struct PlanDev {
   int32_t nx, ny, ss;
   const double* x_sub;
   const double* y_sub;
+  // x_sub[r][c] = gx0 + r gxi + c gxj (and likewise y) to a few ulp, r / c = row / column of the supersampled grid:
+  // set at plan creation when the coordinate arrays are affine in the grid indices (every RegularGrid is)
+  int32_t grid_affine;
+  double gx0, gxi, gxj, gy0, gyi, gyj;
   const int32_t* eval_list;  // [n_eval] indices of the pixels that are evaluated, or null = all of them
   int32_t n_eval;            // number of evaluated pixels (= nx*ny without a mask)
   int32_t conv_mode, K;
@@ -394,6 +398,194 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
     for (int k = 0; k < NSLOT; ++k) {
       if (live && k < P.n_slots && (!SUB || out)) out[(bl * P.n_slots + k) * npix + p] = acc[k] * inv_ss * out_scale;
     }
+  }
+}
+
+// ---- k_image_fold: the image kernel for "one EPL + linear profiles -> Sersic light" on an affine grid ----------------
+// Everything that is LINEAR in the sky position is composed once per parameter set (by the CTA, from the prepared
+// block) instead of being evaluated per sub-pixel:
+//   * SHEAR / CONVERGENCE are linear maps: beta = M x + m0 - scal alpha_EPL(x), M = 1 - scal Gamma;
+//   * the EPL's major-axis coordinates a = q x', c = y' and every Sersic's product-average coordinates
+//     (xt, yt) = T (beta - centre) are affine in x, hence -- on a grid whose coordinates are affine in the sub-pixel
+//     indices (PlanDev.grid_affine) -- affine in (row, column): they are carried along by ADDITIONS, one per sub-pixel
+//     and quantity, and the coordinate arrays are never read;
+//   * the rotation of the EPL deflection back to the sky frame, the deflection scaling and T compose into one 2 x 2
+//     matrix Q per lensed light profile: (xt, yt) = affine(row, col) - s Q (t_r, t_i), with (s, t_r, t_i) straight out
+//     of the series (epl_core<ROT = false>).
+// Per sub-pixel this replaces 4 loads, 2 DMUL and 18 three-register DFMA by ~4 DADD, 2 DMUL and 4 DFMA.  The
+// arithmetic differs from k_image's in the last bits only (the affine coordinates agree with the arrays to a few ulp:
+// checked at plan creation).  Scope: single plane, exactly one EPL (or SIE evaluated as EPL) and any number of SHEAR /
+// CONVERGENCE, NL <= 2 SERSIC / SERSIC_ELLIPSE components, SS in {1, 2, 3}, no sub-frame mask, no supersampled
+// convolution; anything else runs k_image.
+struct FoldLight {
+  double X0, Xi, Xj, Xj2, Y0, Yi, Yj, Yj2, Q00, Q01, Q10, Q11;
+};
+template <int NL>
+struct FoldC {
+  double A0, Ai, Aj, Aj2, C0, Ci, Cj, Cj2;
+  FoldLight g[NL];
+  int32_t epl, pad;
+};
+
+// 2 CTAs of 256 threads per SM at up to 128 registers: measured +2 % over 3 CTAs at 80 registers with spills
+// (gpurun_out/r2_variants2.txt); the kernel is bound by operand delivery to the fp64 pipe, not by occupancy
+#ifndef LSIM_FOLD_MIN_BLOCKS
+#define LSIM_FOLD_MIN_BLOCKS 2
+#endif
+template <int NSLOT, int SS, int NL>
+__global__ void __launch_bounds__(kImageBlock, LSIM_FOLD_MIN_BLOCKS)
+k_image_fold(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, double out_scale,
+             double* __restrict__ out, const unsigned char* __restrict__ prepared, int n_series) {
+  constexpr int J = SS;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ FoldC<NL> F;
+  const int64_t bl = blockIdx.y;
+  const double* row = params + (set0 + bl) * P.n_param_cols;
+  LensC* L = reinterpret_cast<LensC*>(smem);
+  LightC* G = reinterpret_cast<LightC*>(L + P.n_lens);
+  double* pool = reinterpret_cast<double*>(G + P.n_light);
+  stage_math_tables();
+  load_or_stage(P, row, prepared, bl, n_series, L, G, pool);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double sc = P.ray.alpha_scaling;
+    double g00 = 0, g01 = 0, g10 = 0, g11 = 0, kx = 0, ky = 0;
+    int e = 0;
+    for (int l = 0; l < P.n_lens; ++l) {
+      if (L[l].type == LSIM_LENS_EPL) e = l;
+      if (L[l].type == LSIM_LENS_SHEAR) {  // alpha = (g1 x + g2 y + c4, g2 x - g1 y + c5)
+        g00 += L[l].c[2];
+        g01 += L[l].c[3];
+        g10 += L[l].c[3];
+        g11 -= L[l].c[2];
+        kx += L[l].c[4];
+        ky += L[l].c[5];
+      }
+      if (L[l].type == LSIM_LENS_CONVERGENCE) {  // alpha = kappa (x - ra_0, y - dec_0)
+        g00 += L[l].c[2];
+        g11 += L[l].c[2];
+        kx -= L[l].c[2] * L[l].c[0];
+        ky -= L[l].c[2] * L[l].c[1];
+      }
+    }
+    const double m00 = 1.0 - sc * g00, m01 = -sc * g01, m10 = -sc * g10, m11 = 1.0 - sc * g11;
+    const double m0x = -sc * kx, m0y = -sc * ky;
+    const LensC& E = L[e];
+    F.epl = e;
+    F.A0 = E.c[19] * P.gx0 + E.c[20] * P.gy0 + E.c[21];
+    F.Ai = E.c[19] * P.gxi + E.c[20] * P.gyi;
+    F.Aj = E.c[19] * P.gxj + E.c[20] * P.gyj;
+    F.Aj2 = 2.0 * F.Aj;
+    F.C0 = E.c[2] * P.gy0 - E.c[3] * P.gx0 + E.c[22];
+    F.Ci = E.c[2] * P.gyi - E.c[3] * P.gxi;
+    F.Cj = E.c[2] * P.gyj - E.c[3] * P.gxj;
+    F.Cj2 = 2.0 * F.Cj;
+    const double cph = E.c[2], sph = E.c[3];
+    for (int g = 0; g < NL; ++g) {
+      const double t00 = G[g].c[2], t01 = G[g].c[3], t11 = G[g].c[4];
+      double p00 = t00, p01 = t01, p10 = t01, p11 = t11, p0x = G[g].c[11], p0y = G[g].c[12];
+      FoldLight& f = F.g[g];
+      f.Q00 = f.Q01 = f.Q10 = f.Q11 = 0.0;
+      if (G[g].lensed) {
+        p00 = t00 * m00 + t01 * m10;
+        p01 = t00 * m01 + t01 * m11;
+        p10 = t01 * m00 + t11 * m10;
+        p11 = t01 * m01 + t11 * m11;
+        p0x += t00 * m0x + t01 * m0y;
+        p0y += t01 * m0x + t11 * m0y;
+        // alpha_EPL = s Rot (t_r, t_i), Rot = [[cos, -sin], [sin, cos]]:  Q = scal T Rot
+        f.Q00 = sc * (t00 * cph + t01 * sph);
+        f.Q01 = sc * (t01 * cph - t00 * sph);
+        f.Q10 = sc * (t01 * cph + t11 * sph);
+        f.Q11 = sc * (t11 * cph - t01 * sph);
+      }
+      f.X0 = p00 * P.gx0 + p01 * P.gy0 + p0x;
+      f.Xi = p00 * P.gxi + p01 * P.gyi;
+      f.Xj = p00 * P.gxj + p01 * P.gyj;
+      f.Xj2 = 2.0 * f.Xj;
+      f.Y0 = p10 * P.gx0 + p11 * P.gy0 + p0y;
+      f.Yi = p10 * P.gxi + p11 * P.gyi;
+      f.Yj = p10 * P.gxj + p11 * P.gyj;
+      f.Yj2 = 2.0 * f.Yj;
+    }
+  }
+  __syncthreads();
+
+  const int npix = P.nx * P.ny;
+  const double inv_ss = 1.0 / SS;
+  const LensC& E = L[F.epl];
+  const double* coef = pool + E.coef_off;
+  const int q_end = min(npix, (int)(blockIdx.x + 1) * ppt);
+  for (int q0 = blockIdx.x * ppt; q0 < q_end; q0 += kImageBlock) {  // warp-uniform trip count, like k_image
+    const int p = min(q0 + (int)threadIdx.x, q_end - 1);
+    const bool live = q0 + (int)threadIdx.x < q_end;
+    const int py = p / P.nx, px = p - py * P.nx;
+    const double rd = (double)(py * SS), cd = (double)(px * SS);
+    // the affine quantities at the pixel's first sub-pixel; one addition per row and per column from there
+    double ra = fma(rd, F.Ai, fma(cd, F.Aj, F.A0)), rc = fma(rd, F.Ci, fma(cd, F.Cj, F.C0));
+    double rx[NL], ry[NL];
+#pragma unroll
+    for (int g = 0; g < NL; ++g) {
+      rx[g] = fma(rd, F.g[g].Xi, fma(cd, F.g[g].Xj, F.g[g].X0));
+      ry[g] = fma(rd, F.g[g].Yi, fma(cd, F.g[g].Yj, F.g[g].Y0));
+    }
+    double acc[NSLOT];
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) acc[k] = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < SS; ++i) {
+      double racc[NSLOT];
+#pragma unroll
+      for (int k = 0; k < NSLOT; ++k) racc[k] = 0.0;
+      double a[J], c[J], s[J], tr[J], ti[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        a[j] = j == 0 ? ra : (j == 1 ? ra + F.Aj : ra + F.Aj2);
+        c[j] = j == 0 ? rc : (j == 1 ? rc + F.Cj : rc + F.Cj2);
+      }
+      epl_core<J, MathK, false>(E, coef, a, c, s, tr, ti, P.ray.mk);
+#pragma unroll
+      for (int g = 0; g < NL; ++g) {
+        const FoldLight& f = F.g[g];
+        double xt[J], yt[J], e[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          xt[j] = j == 0 ? rx[g] : (j == 1 ? rx[g] + f.Xj : rx[g] + f.Xj2);
+          yt[j] = j == 0 ? ry[g] : (j == 1 ? ry[g] + f.Yj : ry[g] + f.Yj2);
+        }
+        if (G[g].lensed) {
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            xt[j] = fma(-s[j], fma(f.Q00, tr[j], f.Q01 * ti[j]), xt[j]);
+            yt[j] = fma(-s[j], fma(f.Q10, tr[j], f.Q11 * ti[j]), yt[j]);
+          }
+        }
+        sersic_core<J>(G[g], xt, yt, e, P.ray.mk);
+        const double amp = G[g].c[10];
+        const int slot = G[g].slot;
+        if (slot >= 0) {  // the amplitude and the sum over the row ride on the accumulation FMAs
+          if (NSLOT == 1) {
+#pragma unroll
+            for (int j = 0; j < J; ++j) racc[0] = fma(amp, e[j], racc[0]);
+          } else {
+            double vs = 0.0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) vs = fma(amp, e[j], vs);
+#pragma unroll
+            for (int k = 0; k < NSLOT; ++k) racc[k] += (slot == k) ? vs : 0.0;
+          }
+        }
+        rx[g] += f.Xi;
+        ry[g] += f.Yi;
+      }
+      ra += F.Ai;
+      rc += F.Ci;
+#pragma unroll
+      for (int k = 0; k < NSLOT; ++k) acc[k] += racc[k] * inv_ss;
+    }
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k)
+      if (live && k < P.n_slots) out[(bl * P.n_slots + k) * npix + p] = acc[k] * inv_ss * out_scale;
   }
 }
 
@@ -825,133 +1017,101 @@ __device__ inline bool lu_solve(double* m, double* r, int n) {
 //   logL = -1/2 sum mask (model - data)^2 / C_D(model)                    (imaging_data.py:159-182)
 //          C_D(model) = noise_map^2  or  max(model,0)/t_exp + sigma_bkg^2 (image_noise.py:99-137)
 //   marg != 0: + 1/2 sign log|det M^-1|, -1e15 if singular               (de_lens.py:39-49)
+// Round 2 tried three other shapes of this kernel (64-thread CTAs that fit beside k_image on a side stream, four sets
+// per CTA sharing the plan-constant reads, and a plain side-stream overlap): all slower or no faster,
+// profiles/r2_likelihood.md.
 #ifndef LSIM_LIKE_UNROLL
 #define LSIM_LIKE_UNROLL 4
 #endif
 constexpr int kLikeUnroll = LSIM_LIKE_UNROLL;
 
-// Sets per CTA (SPC).  Every pixel of a set needs three plan-constant values besides its own basis images (1/C_D(data),
-// data, 1/t_exp or noise_map^2): with one set per CTA those re-reads are two thirds of the kernel's L2 traffic (4 x 259 KB
-// of constants against 2 x 259 KB of images per set at n_lin = 1).  A CTA that walks SPC sets together loads each
-// constant once per SPC sets -- measured in round 2 (profiles/r2_likelihood.md): SPC = 4 halves the L2 traffic but leaves
-// 2 CTAs per SM, and the kernel, which lives on memory-level parallelism (long_scoreboard is its top stall), went from
-// 273 to 418 us per 1184 sets.  SPC = 1 (8 CTAs per SM) stays; the template parameter is kept for the record.
 template <int NS>
-struct LikeSets {
-  static constexpr int value = 1;
-};
-
-template <int NS, int SPC>
 __global__ void __launch_bounds__(kBlock)
-k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int n_sets, int linear, int marg,
-             double* __restrict__ logl, double* __restrict__ amps, double* __restrict__ model_out,
-             const double* __restrict__ err_map) {
-  constexpr int NM = NS * (NS + 1) / 2, NA = NM + NS;
-  __shared__ double scratch[(SPC * NA + 1) * (kBlock / 32)];
-  __shared__ double s_amp[SPC][NS];
-  __shared__ double s_marg[SPC];
+k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linear, int marg, double* __restrict__ logl,
+             double* __restrict__ amps, double* __restrict__ model_out, const double* __restrict__ err_map) {
+  constexpr int NM = NS * (NS + 1) / 2;
+  __shared__ double scratch[(NM + NS + 1) * (kBlock / 32)];
+  __shared__ double s_amp[NS];
+  __shared__ double s_marg;
+  const int64_t bl = blockIdx.x;
   const int npix = P.nx * P.ny;
   const int ns = P.n_slots;
-  const int64_t bl0 = (int64_t)blockIdx.x * SPC;
-  // sets past the end of the batch alias the last one: they are computed and thrown away
-  const double* A[SPC];
-  const double* E[SPC];  // PSF error map of the set (sigma^2, or null): added to C_D(data) in the weights and as |.| to
-                         // C_D(model) in chi^2
-  bool live[SPC];
-#pragma unroll
-  for (int i = 0; i < SPC; ++i) {
-    live[i] = bl0 + i < n_sets;
-    const int64_t bl = live[i] ? bl0 + i : (int64_t)n_sets - 1;
-    A[i] = conv + bl * ns * (int64_t)npix;
-    E[i] = err_map ? err_map + bl * (int64_t)npix : nullptr;
-  }
+  const double* A = conv + bl * ns * (int64_t)npix;
+  // PSF error map of this set (sigma^2, or null): added to C_D(data) in the weights and as |.| to C_D(model) in chi^2
+  const double* E = err_map ? err_map + bl * (int64_t)npix : nullptr;
 
   if (linear) {
-    double acc[SPC][NA];
+    double acc[NM + NS];
 #pragma unroll
-    for (int i = 0; i < SPC; ++i)
-#pragma unroll
-      for (int m = 0; m < NA; ++m) acc[i][m] = 0.0;
+    for (int i = 0; i < NM + NS; ++i) acc[i] = 0.0;
     // 4 pixels per thread per trip: all loads of a trip are issued before any arithmetic (latency hiding)
     for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kBlock) {
-      double a[SPC][kLikeUnroll][NS], w0[kLikeUnroll], dat[kLikeUnroll];
-      bool use[kLikeUnroll];
+      double a[kLikeUnroll][NS], wgt[kLikeUnroll], dat[kLikeUnroll];
 #pragma unroll
       for (int u = 0; u < kLikeUnroll; ++u) {
         const int p = p0 + u * kBlock;
-        use[u] = p < npix && (!P.mask || P.mask[p]);
-        w0[u] = use[u] ? __ldg(P.w_data + p) : 0.0;  // masked / out-of-range pixels get zero weight
-        dat[u] = use[u] ? __ldg(P.data + p) : 0.0;
+        const bool use = p < npix && (!P.mask || P.mask[p]);
+        wgt[u] = use ? __ldg(P.w_data + p) : 0.0;  // masked / out-of-range pixels get zero weight
+        if (E && use) wgt[u] = 1.0 / (1.0 / wgt[u] + E[p]);  // 1 / (C_D + model_error), image_linear_solve.py:150
+        dat[u] = use ? __ldg(P.data + p) : 0.0;
 #pragma unroll
-        for (int i = 0; i < SPC; ++i)
-#pragma unroll
-          for (int k = 0; k < NS; ++k) a[i][u][k] = (use[u] && k < ns) ? A[i][(int64_t)k * npix + p] : 0.0;
+        for (int k = 0; k < NS; ++k) a[u][k] = (use && k < ns) ? A[(int64_t)k * npix + p] : 0.0;
       }
 #pragma unroll
-      for (int i = 0; i < SPC; ++i) {
+      for (int u = 0; u < kLikeUnroll; ++u) {
 #pragma unroll
-        for (int u = 0; u < kLikeUnroll; ++u) {
-          double wgt = w0[u];
-          if (E[i] && use[u]) wgt = 1.0 / (1.0 / wgt + E[i][p0 + u * kBlock]);  // 1 / (C_D + model_error), image_linear_solve.py:150
+        for (int k = 0; k < NS; ++k) a[u][k] = nan_to_num(a[u][k]);
+        const double wd = wgt[u] * dat[u];
+        int m = 0;
 #pragma unroll
-          for (int k = 0; k < NS; ++k) a[i][u][k] = nan_to_num(a[i][u][k]);
-          const double wd = wgt * dat[u];
-          int m = 0;
+        for (int i = 0; i < NS; ++i) {
 #pragma unroll
-          for (int r = 0; r < NS; ++r) {
-#pragma unroll
-            for (int c = r; c < NS; ++c) acc[i][m++] += wgt * a[i][u][r] * a[i][u][c];
-          }
-#pragma unroll
-          for (int r = 0; r < NS; ++r) acc[i][NM + r] += wd * a[i][u][r];
+          for (int j = i; j < NS; ++j) acc[m++] += wgt[u] * a[u][i] * a[u][j];
         }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) acc[NM + i] += wd * a[u][i];
       }
     }
-#pragma unroll
-    for (int i = 0; i < SPC; ++i) block_sum(acc[i], scratch + i * NA * (kBlock / 32));
+    block_sum(acc, scratch);
     if (threadIdx.x == 0) {
-      for (int i = 0; i < SPC; ++i) {
-        double M[NS * NS], M2[NS * NS], R[NS], ev[NS];
-        int m = 0;
-        for (int r = 0; r < NS; ++r)
-          for (int c = r; c < NS; ++c) {
-            M[r * NS + c] = acc[i][m];
-            M[c * NS + r] = acc[i][m];
-            ++m;
-          }
-        // work on the leading ns x ns block, repacked contiguously
-        for (int r = 0; r < ns; ++r)
-          for (int c = 0; c < ns; ++c) M2[r * ns + c] = M[r * NS + c];
-        for (int r = 0; r < ns; ++r) R[r] = acc[i][NM + r];
-        double Mw[NS * NS];
-        for (int r = 0; r < ns * ns; ++r) Mw[r] = M2[r];
-        sym_eigenvalues(Mw, ns, ev);
-        double emax = 0.0, emin = HUGE_VAL, logdet = 0.0, sign = 1.0;
-        for (int r = 0; r < ns; ++r) {
-          double e = fabs(ev[r]);
-          emax = fmax(emax, e);
-          emin = fmin(emin, e);
-          logdet += log(e);
-          if (ev[r] < 0) sign = -sign;
-          if (ev[r] == 0) sign = 0.0;
+      double M[NS * NS], M2[NS * NS], R[NS], ev[NS];
+      int m = 0;
+      for (int i = 0; i < NS; ++i)
+        for (int j = i; j < NS; ++j) {
+          M[i * NS + j] = acc[m];
+          M[j * NS + i] = acc[m];
+          ++m;
         }
-        bool stable = (emax / emin) < 5.0 / DBL_EPSILON;  // NaN compares false, like jnp
-        bool ok = stable && lu_solve(M2, R, ns);
-        if (ok)
-          for (int r = 0; r < ns; ++r) ok = ok && (fabs(R[r]) <= DBL_MAX);
-        for (int r = 0; r < NS; ++r) s_amp[i][r] = (ok && r < ns) ? R[r] : 0.0;
-        // log det(M_inv) = -log det(M); M_inv = 0 (unstable) -> sign 0 -> -1e15
-        s_marg[i] = (stable && sign != 0.0 && (logdet == logdet)) ? sign * (-logdet) / 2 : -1e15;
+      // work on the leading ns x ns block, repacked contiguously
+      for (int i = 0; i < ns; ++i)
+        for (int j = 0; j < ns; ++j) M2[i * ns + j] = M[i * NS + j];
+      for (int i = 0; i < ns; ++i) R[i] = acc[NM + i];
+      double Mw[NS * NS];
+      for (int i = 0; i < ns * ns; ++i) Mw[i] = M2[i];
+      sym_eigenvalues(Mw, ns, ev);
+      double emax = 0.0, emin = HUGE_VAL, logdet = 0.0, sign = 1.0;
+      for (int i = 0; i < ns; ++i) {
+        double e = fabs(ev[i]);
+        emax = fmax(emax, e);
+        emin = fmin(emin, e);
+        logdet += log(e);
+        if (ev[i] < 0) sign = -sign;
+        if (ev[i] == 0) sign = 0.0;
       }
+      bool stable = (emax / emin) < 5.0 / DBL_EPSILON;  // NaN compares false, like jnp
+      bool ok = stable && lu_solve(M2, R, ns);
+      if (ok)
+        for (int i = 0; i < ns; ++i) ok = ok && (fabs(R[i]) <= DBL_MAX);
+      for (int i = 0; i < NS; ++i) s_amp[i] = (ok && i < ns) ? R[i] : 0.0;
+      // log det(M_inv) = -log det(M); M_inv = 0 (unstable) -> sign 0 -> -1e15
+      s_marg = (stable && sign != 0.0 && (logdet == logdet)) ? sign * (-logdet) / 2 : -1e15;
     }
     __syncthreads();
   }
 
-  double chi[SPC];
-#pragma unroll
-  for (int i = 0; i < SPC; ++i) chi[i] = 0.0;
+  double chi[1] = {0.0};
   for (int p0 = threadIdx.x; p0 < npix; p0 += kLikeUnroll * kBlock) {
-    double mdl[SPC][kLikeUnroll], dat[kLikeUnroll], aux[kLikeUnroll];
+    double mdl[kLikeUnroll], dat[kLikeUnroll], aux[kLikeUnroll];
     bool use[kLikeUnroll], valid[kLikeUnroll];
 #pragma unroll
     for (int u = 0; u < kLikeUnroll; ++u) {
@@ -960,49 +1120,35 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int n_set
       use[u] = valid[u] && (!P.mask || P.mask[p]);
       dat[u] = use[u] ? __ldg(P.data + p) : 0.0;
       aux[u] = use[u] ? (P.noise_map2 ? __ldg(P.noise_map2 + p) : __ldg(P.inv_exposure + p)) : 1.0;
+      double m = 0.0;
+      if (linear) {
 #pragma unroll
-      for (int i = 0; i < SPC; ++i) {
-        double m = 0.0;
-        if (linear) {
-#pragma unroll
-          for (int k = 0; k < NS; ++k)
-            if (k < ns && use[u]) m += s_amp[i][k] * nan_to_num(A[i][(int64_t)k * npix + p]);
-        } else if (valid[u]) {
-          for (int k = 0; k < ns; ++k) m += A[i][(int64_t)k * npix + p];
-        }
-        mdl[i][u] = m;
+        for (int k = 0; k < NS; ++k)
+          if (k < ns && use[u]) m += s_amp[k] * nan_to_num(A[(int64_t)k * npix + p]);
+      } else if (valid[u]) {
+        for (int k = 0; k < ns; ++k) m += A[(int64_t)k * npix + p];
       }
+      mdl[u] = m;
     }
 #pragma unroll
-    for (int i = 0; i < SPC; ++i) {
-#pragma unroll
-      for (int u = 0; u < kLikeUnroll; ++u) {
-        const int p = p0 + u * kBlock;
-        if (model_out && valid[u] && live[i]) model_out[(set0 + bl0 + i) * npix + p] = mdl[i][u];
-        if (use[u]) {
-          double cd = P.noise_map2 ? aux[u] : fma(fmax(mdl[i][u], 0.0), aux[u], P.bkg2);
-          if (E[i]) cd += fabs(E[i][p]);  // imaging_data.py:180
-          const double d = mdl[i][u] - dat[u];
-          chi[i] += d * d / cd;
-        }
+    for (int u = 0; u < kLikeUnroll; ++u) {
+      const int p = p0 + u * kBlock;
+      if (model_out && valid[u]) model_out[(set0 + bl) * npix + p] = mdl[u];
+      if (use[u]) {
+        double cd = P.noise_map2 ? aux[u] : fma(fmax(mdl[u], 0.0), aux[u], P.bkg2);
+        if (E) cd += fabs(E[p]);  // imaging_data.py:180
+        const double d = mdl[u] - dat[u];
+        chi[0] += d * d / cd;
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < SPC; ++i) {
-    double c1[1] = {chi[i]};
-    block_sum(c1, scratch);
-    chi[i] = c1[0];
-  }
+  block_sum(chi, scratch);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SPC; ++i) {
-      if (!live[i]) continue;
-      double l = -chi[i] / 2 + P.logl_offset;
-      if (linear && marg) l += s_marg[i];
-      logl[set0 + bl0 + i] = l;
-      if (amps && linear)
-        for (int k = 0; k < ns; ++k) amps[(set0 + bl0 + i) * ns + k] = s_amp[i][k];
-    }
+    double l = -chi[0] / 2 + P.logl_offset;
+    if (linear && marg) l += s_marg;
+    logl[set0 + bl] = l;
+    if (amps && linear)
+      for (int k = 0; k < ns; ++k) amps[(set0 + bl) * ns + k] = s_amp[k];
   }
 }
 

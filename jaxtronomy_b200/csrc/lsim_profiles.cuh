@@ -188,7 +188,9 @@ LSIM_HD void epl_prepare(LensC& L, double* coef, double theta_E, double gamma, d
 // Output: the deflection in the sky frame is  s[j] * (u1[j], u2[j])  (the caller folds s into its accumulation FMA).
 // Non-finite results (Z = 0) follow the reference: nan_to_num(posinf=1e10, neginf=-1e10) on the major-axis
 // components (epl.py:391-392), one test for all J points; then s = 1 and (u1, u2) is the rotated, cleaned deflection.
-template <int J, class KT>
+// ROT = false: (u1, u2) stay in the major-axis frame (the folded image kernel composes the rotation with the
+// light profile's own transform).
+template <int J, class KT, bool ROT = true>
 LSIM_HD void epl_core(const LensC& L, const double* coef, const double (&a)[J], const double (&c)[J], double (&s)[J],
                       double (&u1)[J], double (&u2)[J], const KT& K) {
   // seven values per point stay live across the series loop besides the recurrence state: a, c, s, Im w, p, -|w|^2
@@ -274,8 +276,8 @@ LSIM_HD void epl_core(const LensC& L, const double* coef, const double (&a)[J], 
 #pragma unroll
 #endif
   for (int j = 0; j < J; ++j) {
-    u1[j] = fma(-ti[j], sph, tr[j] * cph);  // rotate(f, -phi)
-    u2[j] = fma(ti[j], cph, tr[j] * sph);
+    u1[j] = ROT ? fma(-ti[j], sph, tr[j] * cph) : tr[j];  // rotate(f, -phi)
+    u2[j] = ROT ? fma(ti[j], cph, tr[j] * sph) : ti[j];
   }
 }
 
@@ -1048,6 +1050,21 @@ LSIM_HD void light_prepare(const lsim_light_desc& d, const double* row, LightC& 
 
 // J points at once (sersic_utils.py:247-267 with R^2 in place of R: no square root is needed because
 // (R/Rs)^(1/n) = exp2(log2(R^2)/(2n) - log2(Rs)/n)).  -> e[j] = the profile at amp = 1
+// SERSIC(_ELLIPSE) at amp = 1 from the product-average coordinates (xt, yt) of J points
+template <int J, class KT>
+LSIM_HD void sersic_core(const LightC& G, const double (&xt)[J], const double (&yt)[J], double (&e)[J], const KT& K) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < J; ++j) {
+    const double R2c = max_nan(fma(yt[j], yt[j], xt[j] * xt[j]), 1e-8);  // R_ = max(1e-4, R)
+    const double k = exp2_fin_s(fma(G.c[5], log2_pos(R2c, K), G.c[6]), K);
+    double v = exp2_fin_s(fma(G.c[7], k, G.c[8]), K);  // k >= 0, c[7] <= 0: the argument is at most c[8] <= 256 * 1021
+    v = (R2c <= G.c[9]) ? v : 0.0;  // R_/Rs_ <= max_R_frac
+    e[j] = (v == v) ? v : 0.0;      // nan_to_num (the exponent is bounded above, so no +inf)
+  }
+}
+
 template <int J, class KT>
 LSIM_HD void light_unit(int type, const LightC& G, const double (&x)[J], const double (&y)[J], double (&e)[J],
                         const KT& K) {

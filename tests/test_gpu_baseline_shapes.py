@@ -262,3 +262,57 @@ def test_c5_batched_through_the_likelihood_module():
     for n in range(3):
         assert_close(out[n], CASES["c5_%02d" % n].out["logL"], what="logL %d" % n, rtol=1e-9, atol_frac=0)
     np.testing.assert_array_equal(out, np.tile(out[:3], 50))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# k_image_fold (linear profiles and light transforms composed per set, affine grid) against the plain k_image
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["headline", "epl_shear_convergence_two_lights_ss2", "sie_as_epl_ss1"])
+def test_folded_image_kernel_matches_the_plain_one(case, monkeypatch):
+    """The same plan built with and without LSIM_NO_FOLD: basis images per pixel at 1e-12 of the peak (the two kernels
+    differ in operation order only), logL and amplitudes at 1e-11; the headline case is also pinned to the reference
+    by the tests above, which run the folded kernel."""
+    import torch
+
+    from jaxtronomy_b200.Data.imaging_data import ImageData
+    from jaxtronomy_b200.Data.psf import PSF
+    from jaxtronomy_b200.ImSim.image_linear_solve import ImageLinearFit
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+    from jaxtronomy_b200.LightModel.light_model import LightModel
+
+    s = CASES["headline_static"]
+    rng = np.random.default_rng(17)
+    kd = _static()["kwargs_data"]
+    if case == "headline":
+        lens, pk, src, ll, ss, n = ["EPL", "SHEAR"], None, ["SERSIC_ELLIPSE"], [], 3, 64
+    elif case == "epl_shear_convergence_two_lights_ss2":
+        lens, pk, src, ll, ss, n = ["SHEAR", "EPL", "CONVERGENCE"], None, ["SERSIC_ELLIPSE"], ["SERSIC"], 2, 16
+    else:
+        lens, pk, src, ll, ss, n = ["SIE", "SHEAR"], [dict(NIE=False, gamma=2.0), {}], ["SERSIC"], [], 1, 16
+
+    def build():
+        return ImageLinearFit(ImageData(image_data=s.inp["image_data"], **kd),
+                              PSF(psf_type="PIXEL", kernel_point_source=s.inp["kernel"]),
+                              LensModel(lens, profile_kwargs_list=pk), LightModel(src), LightModel(ll),
+                              kwargs_numerics=dict(supersampling_factor=ss))
+
+    folded = build()
+    names = folded.param_names
+    lo = dict(theta_E=0.8, gamma=1.7, e1=-0.3, e2=-0.3, center_x=-0.1, center_y=-0.1, gamma1=-0.08, gamma2=-0.08,
+              ra_0=-0.2, dec_0=-0.2, kappa=-0.05, amp=1.0, R_sersic=0.1, n_sersic=1.0)
+    hi = dict(theta_E=1.6, gamma=2.3, e1=0.3, e2=0.3, center_x=0.1, center_y=0.1, gamma1=0.08, gamma2=0.08,
+              ra_0=0.2, dec_0=0.2, kappa=0.05, amp=1.0, R_sersic=0.5, n_sersic=4.0)
+    mat = np.stack([rng.uniform(lo[nm], hi[nm], n) for _, _, nm in names], axis=1)
+    params = torch.as_tensor(mat, device="cuda")
+    img_f = folded.response_batch(params).cpu().numpy()
+    l_f, a_f, _ = folded.logL_linear_batch(params)
+    monkeypatch.setenv("LSIM_NO_FOLD", "1")
+    plain = build()
+    img_p = plain.response_batch(params).cpu().numpy()
+    l_p, a_p, _ = plain.logL_linear_batch(params)
+    assert not np.array_equal(img_f, img_p), "both plans ran the same kernel"
+    scale = np.abs(img_p).max(axis=(2, 3), keepdims=True)
+    assert np.all(np.abs(img_f - img_p) <= 1e-11 * np.abs(img_p) + 1e-12 * scale), \
+        float(np.max(np.abs(img_f - img_p) / scale))
+    np.testing.assert_allclose(l_f.cpu().numpy(), l_p.cpu().numpy(), rtol=1e-10)
+    np.testing.assert_allclose(a_f.cpu().numpy(), a_p.cpu().numpy(), rtol=1e-9)
