@@ -437,7 +437,7 @@ def run_gpu(args):
         total_ms = sum(v["ms"] for v in tm.values())
         cnt = load_counters()
         nominal = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 DFMA lanes x 2 flop x 1.965 GHz = 37.2 TFLOP/s
-        roof = {"bound": "fp64", "kernel": "k_image (fused ray-shoot + light + re-bin)", "unit": "TFLOP/s",
+        roof = {"bound": "fp64", "kernel": "k_image_fold (fused ray-shoot + light + re-bin)", "unit": "TFLOP/s",
                 "peak": peak / 1e12, "peak_nominal": nominal,
                 "peak_source": "measured DFMA-chain microbenchmark in this run (lsim_measure_fp64_peak); "
                                "MEASURED_PEAKS.json has no fp64 entry; nominal printed beside it",

@@ -41,7 +41,7 @@ def main():
 
     out = {
         "capture": os.path.relpath(path, ROOT),
-        "kernel": "k_image (headline instantiation)", "sets_in_launch": sets, "subpixels_per_set": sub_per_set,
+        "kernel": "k_image_fold<1, 3, 1> (headline instantiation)", "sets_in_launch": sets, "subpixels_per_set": sub_per_set,
         "gpu_time_ms": m.get("gpu__time_duration.sum"),
         "dfma_per_subpixel": per("dfma"), "dmul_per_subpixel": per("dmul"), "dadd_per_subpixel": per("dadd"),
         "pipe_fp64_cycles_active_pct": m.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"),
