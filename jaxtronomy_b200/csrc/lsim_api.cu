@@ -138,6 +138,7 @@ struct lsim_plan {
   int grad_tier = 2;  // code tier of k_image_grad this model needs (lsim_grad.cuh: lens_grad_tier)
   int grad_series = 0;
   int grad_stateful = 0;  // leading profiles of the gradient's lens list with a register-resident point state
+  bool grad_mp = false;   // multi-plane: k_image_grad<0, 2, true> (reverse sweep over the planes)
   size_t grad_smem = 0;
   const lsim_lens_desc* grad_lens = nullptr;  // device: the gradient's lens list (EPL_MULTIPOLE_M1M3M4 expanded)
   int n_grad_lens = 0;
@@ -196,6 +197,7 @@ int configure_kernels() {
   LSIM_GRAD_ATTR(1)
   LSIM_GRAD_ATTR(2)
 #undef LSIM_GRAD_ATTR
+  LSIM_CUDA(cudaFuncSetAttribute(k_image_grad<0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemMax));
   return LSIM_OK;
 }
 
@@ -445,13 +447,15 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
     }
     if (D.K > 0) p->kernel_host.assign(d->kernel, d->kernel + (size_t)d->kernel_size * d->kernel_size);
     {  // gradient path: scope check, transposed PSF
-      bool ok = !d->multi_plane && !d->supersampled_conv && d->n_points == 0 && !p->f32 &&
+      bool ok = !d->supersampled_conv && d->n_points == 0 && !p->f32 &&
                 (d->conv_mode != LSIM_CONV_EDGE || d->kernel_separable);
       int gs = 0;
       int tier = 0;
       std::vector<lsim_lens_desc> gl((size_t)4 * (d->n_lens > 0 ? d->n_lens : 1));
-      const int ngl = ad::expand_grad_lens(d->lens, d->n_lens, gl.data(), (int)gl.size());
-      ok = ok && ngl >= 0;
+      // multi-plane: the list stays in plane order and runs the dual-number tier with the reverse sweep over the planes
+      const int ngl = ad::expand_grad_lens(d->lens, d->n_lens, gl.data(), (int)gl.size(), d->multi_plane != 0);
+      ok = ok && ngl >= 0 && (!d->multi_plane || ngl <= ad::kMaxGradPlanes);
+      p->grad_mp = d->multi_plane != 0;
       for (int i = 0; ok && i < d->n_lens; ++i) ok = ad::lens_grad_supported(d->lens[i]);
       for (int i = 0; ok && i < ngl; ++i) {
         tier = ad::lens_grad_tier(gl[i]) > tier ? ad::lens_grad_tier(gl[i]) : tier;
@@ -1202,10 +1206,15 @@ int launch_image_grad(const lsim_plan* plan, const double* params, int64_t set0,
     k_image_grad<NS, 1><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt); \
   else                                                                                                            \
     k_image_grad<NS, 2><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series, ub, wscale, pt);
-      switch (plan->grad_stateful < 2 ? plan->grad_stateful : 2) {  // EPL-family / NIE profiles kept in registers
-        case 1: LSIM_GRAD_LAUNCH(1) break;
-        case 2: LSIM_GRAD_LAUNCH(2) break;
-        default: LSIM_GRAD_LAUNCH(0) break;
+      if (plan->grad_mp) {
+        k_image_grad<0, 2, true><<<grid, kGradBlock, plan->grad_smem, st>>>(D, params, set0 + i0, ppt, plan->grad_series,
+                                                                            ub, wscale, pt);
+      } else {
+        switch (plan->grad_stateful < 2 ? plan->grad_stateful : 2) {  // EPL-family / NIE profiles kept in registers
+          case 1: LSIM_GRAD_LAUNCH(1) break;
+          case 2: LSIM_GRAD_LAUNCH(2) break;
+          default: LSIM_GRAD_LAUNCH(0) break;
+        }
       }
 #undef LSIM_GRAD_LAUNCH
       int rc = after_launch("k_image_grad");

@@ -743,7 +743,7 @@ LSIM_HD bool lens_grad_has_series(const lsim_lens_desc& d) {
 // EPL (parameters 0..5) and three kGradLensMP pseudo-profiles (theta_E, e1, e2, center_x, center_y, delta_phi_m,
 // a_m/a) that read the parent's columns / constants -- their gradient entries therefore add up in the parent's columns.
 // Returns the number of descriptors written (<= cap), or -1 if `cap` is too small.
-inline int expand_grad_lens(const lsim_lens_desc* in, int n, lsim_lens_desc* out, int cap) {
+inline int expand_grad_lens(const lsim_lens_desc* in, int n, lsim_lens_desc* out, int cap, bool keep_order = false) {
   int m = 0;
   for (int i = 0; i < n; ++i) {
     if (in[i].type != LSIM_LENS_EPL_MULTIPOLE_M1M3M4) {
@@ -777,12 +777,13 @@ inline int expand_grad_lens(const lsim_lens_desc* in, int n, lsim_lens_desc* out
       q.cst[5] = in[i].cst[id[j]];
       q.col[6] = in[i].col[ia[j]];
       q.cst[6] = in[i].cst[ia[j]];
+      q.delta_T = 0.0;  // multi-plane: the pseudo-profiles sit on their parent's plane (no step between them)
       out[m++] = q;
     }
   }
   // the profiles whose point state the kernel keeps in registers (the EPL family, NIE / SIE) go first; the order of the sum of
-  // deflections is internal to the gradient path
-  for (int i = 1; i < m; ++i) {
+  // deflections is internal to the gradient path (single plane only: a multi-plane list stays in plane order)
+  for (int i = 1; i < m && !keep_order; ++i) {
     if (!lens_grad_stateful(out[i])) continue;
     int j = i;
     while (j > 0 && !lens_grad_stateful(out[j - 1])) {
@@ -1439,6 +1440,81 @@ LSIM_HD void lens_vjp_recompute(const GLens& L, const double* pool, double x, do
   if (L.type != LSIM_LENS_SHEAR && L.type != kGradLensMP) lens_point<TIER>(L, pool, x, y, o);
   lens_vjp<TIER>(L, o, x, y, vx, vy, g);
 }
+// ---- multi-plane ray shooting and its reverse sweep (MultiPlaneBase.ray_shooting_partial_comoving,
+// multi_plane_base.py:159-233; jax differentiates the same recursion) --------------------------------------------------
+// Forward, per profile l in plane order:  X += a dT_l;  theta_l = X / T_z_l;  a -= red_l alpha_l(theta_l);
+//          beta = (X + a T_end) / T_z_source      (X comoving position, a angle; a starts as the image position)
+// Reverse, given v = dL/dbeta:  Xb = v / T_z_source,  ab = v T_end / T_z_source;  for l = n-1 ... 0:
+//          w = -red_l ab;  parameter entries of l += d(w . alpha_l)/dp;  Xb += d(w . alpha_l)/dtheta / T_z_l;  ab += Xb dT_l.
+// Every profile depends on the position through (theta - centre) only, so d/dtheta = -d/d(centre): the entries the
+// parameter contraction (lens_vjp) produces anyway -- no second set of derivatives.
+constexpr int kMaxGradPlanes = 8;
+struct MpPlane {
+  double dT, iTz, r2p;
+  int32_t ix, iy;  // entries of lens_vjp's output that hold d/d(centre_x), d/d(centre_y)
+};
+
+// entries of d/d(centre) in lens_vjp's output for a PREPARED profile (closed forms work in their own primitives)
+LSIM_HD void vjp_center_slots(const GLens& L, const lsim_lens_desc& d, int& ix, int& iy) {
+  if (L.type == LSIM_LENS_EPL || L.type == LSIM_LENS_NIE) {
+    ix = 4;
+    iy = 5;
+  } else if (L.type == LSIM_LENS_SHEAR || L.type == kGradLensMP) {
+    ix = 2;
+    iy = 3;
+  } else if (!lens_center_slots(d, ix, iy)) {
+    ix = iy = -1;
+  }
+}
+
+// lens_prepare_d with EVERY parameter carried as an independent variable (a fixed centre still needs its tangent for
+// the reverse sweep); the entries of fixed parameters are dropped when the entries are mapped to columns.
+LSIM_HD bool lens_prepare_all_vars(const lsim_lens_desc& d, const double* row, GLens& L, double* F, double* dF) {
+  lsim_lens_desc dd = d;
+  double r2[LSIM_MAX_PARAMS];
+  for (int k = 0; k < LSIM_MAX_PARAMS; ++k) {
+    r2[k] = param_of(d, row, k);
+    dd.col[k] = k;
+  }
+  return lens_prepare_d(dd, r2, L, F, dF);
+}
+
+template <int TIER>
+LSIM_HD void mp_ray_forward(const GLens* L, const MpPlane* pl, int n, const double* pool, double T_end, double iTzs,
+                            double x, double y, double* tx, double* ty, double& bx, double& by) {
+  double X = 0.0, Y = 0.0, ax = x, ay = y;
+  for (int l = 0; l < n; ++l) {
+    X = fma(ax, pl[l].dT, X);
+    Y = fma(ay, pl[l].dT, Y);
+    tx[l] = X * pl[l].iTz;
+    ty[l] = Y * pl[l].iTz;
+    double fx, fy;
+    lens_value<TIER>(L[l], pool, tx[l], ty[l], fx, fy);
+    ax = fma(-fx, pl[l].r2p, ax);
+    ay = fma(-fy, pl[l].r2p, ay);
+  }
+  bx = fma(ax, T_end, X) * iTzs;
+  by = fma(ay, T_end, Y) * iTzs;
+}
+
+// acc(l, g): add the kLensEntries entries g of profile l
+template <int TIER, class Acc>
+LSIM_HD void mp_ray_reverse(const GLens* L, const MpPlane* pl, int n, const double* pool, double T_end, double iTzs,
+                            const double* tx, const double* ty, double vx, double vy, Acc&& acc) {
+  double Xbx = vx * iTzs, Xby = vy * iTzs, abx = vx * T_end * iTzs, aby = vy * T_end * iTzs;
+  for (int l = n - 1; l >= 0; --l) {
+    double g[kLensEntries];
+    lens_vjp_recompute<TIER>(L[l], pool, tx[l], ty[l], -pl[l].r2p * abx, -pl[l].r2p * aby, g);
+    acc(l, g);
+    if (pl[l].ix >= 0) {
+      Xbx = fma(-g[pl[l].ix], pl[l].iTz, Xbx);
+      Xby = fma(-g[pl[l].iy], pl[l].iTz, Xby);
+    }
+    abx = fma(Xbx, pl[l].dT, abx);
+    aby = fma(Xby, pl[l].dT, aby);
+  }
+}
+
 LSIM_HD int lens_grad_tier(const lsim_lens_desc& d) {
   if (d.type == LSIM_LENS_NULL || d.type == LSIM_LENS_SHEAR || lens_grad_has_series(d)) return 0;
   if (d.type == kGradLensMP || d.type == LSIM_LENS_MULTIPOLE || d.type == LSIM_LENS_NIE || d.type == LSIM_LENS_SIE) return 1;

@@ -266,12 +266,16 @@ __host__ __device__ inline size_t grad_smem_bytes(int n_lens, int n_light, int n
          (size_t)grad_entries(n_lens, n_light) * kGradBlock * sizeof(double);
 }
 
-template <int NS, int TIER>
+// MP: multi-plane lensing (NS = 0, TIER = 2): the rays go through the planes in order (mp_ray_forward), the
+// source-plane gradient comes back through them in reverse (mp_ray_reverse, lsim_grad.cuh); every profile is prepared
+// with all of its parameters as independent variables so that a fixed centre still yields d alpha / d theta.
+template <int NS, int TIER, bool MP = false>
 __global__ void __launch_bounds__(kGradBlock, TIER < 2 ? LSIM_GRAD_FAST_BLOCKS : 2)
 k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, int n_series,
              const double* __restrict__ ubar, double wscale, double* __restrict__ partial) {
   using namespace ad;
   extern __shared__ double smem[];
+  __shared__ MpPlane s_pl[MP ? kMaxGradPlanes : 1];
   const int64_t bl = blockIdx.y;
   const double* row = params + (set0 + bl) * P.n_param_cols;
   GLens* L = reinterpret_cast<GLens*>(smem);
@@ -285,7 +289,18 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
       int off = 0;
       for (int j = 0; j < i; ++j) off += lens_grad_has_series(P.lens[j]) ? 1 : 0;
       L[i].coef_off = off * kGradPool;
-      lens_prepare_d(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries);
+      if (MP) {
+        lens_prepare_all_vars(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries);
+        s_pl[i].dT = P.lens[i].delta_T;
+        s_pl[i].iTz = P.lens[i].T_z != 0 ? 1.0 / P.lens[i].T_z : 0.0;
+        s_pl[i].r2p = P.lens[i].red2phys;
+        int ix, iy;
+        vjp_center_slots(L[i], P.lens[i], ix, iy);
+        s_pl[i].ix = ix;
+        s_pl[i].iy = iy;
+      } else {
+        lens_prepare_d(P.lens[i], row, L[i], pool + off * kGradPool, pool + off * kGradPool + kMaxSeries);
+      }
     } else {
       light_prepare_g(P.light[i - P.n_lens], row, G[i - P.n_lens]);
     }
@@ -309,20 +324,33 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
       const int64_t base = ((int64_t)py * ss + i) * sub_stride + (int64_t)px * ss;
       for (int j = 0; j < ss; ++j) {
         const double x = __ldg(P.x_sub + base + j), y = __ldg(P.y_sub + base + j);
+        if (MP) {
+          double tx[kMaxGradPlanes], ty[kMaxGradPlanes], bx, by;
+          mp_ray_forward<TIER>(L, s_pl, P.n_lens, pool, P.ray.T_ij_end, P.ray.inv_T_z_source, x, y, tx, ty, bx, by);
+          double vx = 0.0, vy = 0.0;
+          for (int g = 0; g < P.n_light; ++g) {
+            const GLight& Gg = G[g];
+            if (Gg.slot < 0) continue;
+            const double w = __ldg(ubar + (bl * P.n_slots + Gg.slot) * (int64_t)npix + p) * wsub;
+            double I, Ix, Iy, gg[kLightG];
+            light_point(Gg, Gg.lensed ? bx : x, Gg.lensed ? by : y, I, Ix, Iy, gg);
+            if (Gg.lensed) {
+              vx = fma(w, Ix, vx);
+              vy = fma(w, Iy, vy);
+            }
+            double* e = lacc + (size_t)g * kGradLightStride * kGradBlock;
+#pragma unroll
+            for (int k = 0; k < kGradLightStride; ++k) e[k * kGradBlock] = fma(w, gg[k], e[k * kGradBlock]);
+          }
+          mp_ray_reverse<TIER>(L, s_pl, P.n_lens, pool, P.ray.T_ij_end, P.ray.inv_T_z_source, tx, ty, vx, vy,
+                               [&](int l, const double (&gl)[kLensEntries]) {
+                                 double* e = my + (size_t)l * kLensEntries * kGradBlock;
+                                 for (int k = 0; k < kLensEntries; ++k) e[k * kGradBlock] += gl[k];
+                               });
+          continue;
+        }
         double ax = 0.0, ay = 0.0;
         LensPt pt[NS > 0 ? NS : 1];
-#pragma unroll
-        for (int l = 0; l < NS; ++l) {
-          lens_point<TIER>(L[l], pool, x, y, pt[l]);
-          ax += pt[l].ax;
-          ay += pt[l].ay;
-        }
-        for (int l = NS; l < P.n_lens; ++l) {
-          double fx, fy;
-          lens_value<TIER>(L[l], pool, x, y, fx, fy);
-          ax += fx;
-          ay += fy;
-        }
         const double bx = x - ax * as, by = y - ay * as;
         double vx = 0.0, vy = 0.0;
         for (int g = 0; g < P.n_light; ++g) {

@@ -253,6 +253,43 @@ int hm_lens_vjp(const lsim_lens_desc* lens, int n_lens, const double* row, const
   return 0;
 }
 
+// Multi-plane ray shooting with its reverse sweep (the per-point code of k_image_grad<0, 2, true>): beta at N image
+// positions and g[p][l][k] = d(vx beta_x + vy beta_y)/d(parameter k of profile l) (descriptor order, after lens_chain).
+int hm_mp_ray_vjp(const lsim_lens_desc* lens, int n_lens, double T_ij_end, double T_z_source, const double* row,
+                  const double* x, const double* y, int64_t N, const double* vx, const double* vy, double* bx, double* by,
+                  double* g) {
+  if (n_lens > ad::kMaxGradPlanes) return -1;
+  std::vector<ad::GLens> L(n_lens);
+  std::vector<ad::MpPlane> pl(n_lens);
+  std::vector<double> pool((size_t)(n_lens + 1) * ad::kGradPool);
+  int off = 0;
+  for (int i = 0; i < n_lens; ++i) {
+    L[i].coef_off = off * ad::kGradPool;
+    double* F = pool.data() + (size_t)off * ad::kGradPool;
+    if (!ad::lens_prepare_all_vars(lens[i], row, L[i], F, F + kMaxSeries)) return -2;
+    if (ad::lens_grad_has_series(lens[i])) ++off;
+    pl[i].dT = lens[i].delta_T;
+    pl[i].iTz = 1.0 / lens[i].T_z;
+    pl[i].r2p = lens[i].red2phys;
+    int ix, iy;
+    ad::vjp_center_slots(L[i], lens[i], ix, iy);
+    pl[i].ix = ix;
+    pl[i].iy = iy;
+  }
+  for (int64_t p = 0; p < N; ++p) {
+    double tx[ad::kMaxGradPlanes], ty[ad::kMaxGradPlanes];
+    ad::mp_ray_forward<2>(L.data(), pl.data(), n_lens, pool.data(), T_ij_end, 1.0 / T_z_source, x[p], y[p], tx, ty, bx[p],
+                          by[p]);
+    ad::mp_ray_reverse<2>(L.data(), pl.data(), n_lens, pool.data(), T_ij_end, 1.0 / T_z_source, tx, ty, vx[p], vy[p],
+                          [&](int l, const double (&s)[ad::kLensEntries]) {
+                            double gg[ad::kLensEntries];
+                            ad::lens_chain(L[l], s, gg);
+                            for (int k = 0; k < ad::kLensN; ++k) g[((size_t)p * n_lens + l) * ad::kLensN + k] = gg[k];
+                          });
+  }
+  return 0;
+}
+
 //   out [N], dout [N][9]: d/dx, d/dy, then d/d(parameter k) -- same layout as hm_light_jvp
 int hm_light_point(const lsim_light_desc* light, const double* row, const double* x, const double* y, int64_t N,
                    double* out, double* dout) {

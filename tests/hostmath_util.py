@@ -46,6 +46,8 @@ def lib():
         h.hm_light_jvp.argtypes = [C.POINTER(_lib.LightDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp]
         h.hm_light_point.argtypes = [C.POINTER(_lib.LightDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp]
         h.hm_lens_vjp.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp]
+        h.hm_mp_ray_vjp.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, C.c_int64, _dp,
+                                    _dp, _dp, _dp, _dp]
         h.hm_eplm_vjp.argtypes = [C.POINTER(_lib.LensDesc), _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp]
         h.hm_lens_hessian.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int64, _dp]
         h.hm_source_position_logl.argtypes = [C.POINTER(_lib.LensDesc), C.c_int, _dp, _dp, _dp, C.c_int, C.c_double,
@@ -209,6 +211,25 @@ def lens_vjp(lens_model_list, kwargs_list, x, y, vx, vy, profile_kwargs_list=Non
     rc = lib().hm_lens_vjp(arr, len(descs), _p(row), _p(x), _p(y), x.size, _p(vx), _p(vy), _p(ax), _p(ay), _p(g))
     assert rc == 0, rc
     return ax, ay, g
+
+
+def mp_ray_vjp(lens_model_list, kwargs_list, x, y, vx, vy, multi_plane, profile_kwargs_list=None):
+    """Multi-plane ray shooting + reverse sweep of the gradient path: (beta_x, beta_y, g [N, n_lens, 6]) with
+    g = d(vx beta_x + vy beta_y)/d(parameter), profiles given in plane order with their (delta_T, T_z, red2phys)."""
+    names = [_model.LENS_PARAM_NAMES[n] for n in lens_model_list]
+    row = np.asarray(_model.gather_values(names, kwargs_list), dtype=np.float64)
+    layout = _model.ColumnLayout()
+    descs = [_model.lens_desc(n, layout.add_profile("lens", i, names[i]), (profile_kwargs_list or [{}] * len(names))[i],
+                              delta_T=multi_plane["delta_T"][i], T_z=multi_plane["T_z"][i],
+                              red2phys=multi_plane["red2phys"][i]) for i, n in enumerate(lens_model_list)]
+    arr = (_lib.LensDesc * len(descs))(*descs)
+    x, y, vx, vy = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, vx, vy))
+    bx, by = np.empty_like(x), np.empty_like(y)
+    g = np.zeros((x.size, len(descs), 6))
+    rc = lib().hm_mp_ray_vjp(arr, len(descs), multi_plane["T_ij_end"], multi_plane["T_z_source"], _p(row), _p(x), _p(y),
+                             x.size, _p(vx), _p(vy), _p(bx), _p(by), _p(g))
+    assert rc == 0, rc
+    return bx, by, g
 
 
 def light_jvp(light_model, kwargs, x, y, use_amp=True, fast=False):

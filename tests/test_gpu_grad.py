@@ -385,3 +385,81 @@ def test_gradient_descent_sampler_recovers_the_truth():
     assert np.all(opt.final_logL >= l_truth - 0.5), opt.final_logL
     print("gradient descent: logL(truth) %.4f -> best %.4f in %s iterations (%d batched evaluations)"
           % (l_truth, l_best, opt.num_iterations, opt.num_evaluations))
+
+
+def test_multi_plane_gradient_against_the_oracle_and_the_forward_path():
+    """Multi-plane lensing (EPL z = 0.5, NFW_ELLIPSE_CSE z = 0.3, SIS z = 0.8; source z = 1.5 -- BASELINE config 5's
+    lens, with the reference fixture's cosmological constants) inside ImageLinearFit on a 32 x 32 frame, ss 2, pixel
+    PSF: the gradient of logL through k_image_grad<0, 2, true> (reverse sweep over the planes) against 4th-order central
+    differences of (a) the NumPy oracle's multi-plane likelihood and (b) the device forward path."""
+    import torch
+
+    from jaxtronomy_b200.Data.imaging_data import ImageData
+    from jaxtronomy_b200.Data.psf import PSF
+    from jaxtronomy_b200.ImSim.image_linear_solve import ImageLinearFit
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+    from jaxtronomy_b200.LightModel.light_model import LightModel
+    from oracle import imsim
+    from oracle.lenstronomy_port import PSF as OPSF
+    from tests.golden_io import load
+
+    s = load("baseline_shapes.npz")["c5_static"]
+    c = load("baseline_shapes.npz")["c5_00"]
+    km = s.meta["kwargs_model"]
+    n, dp = 32, 0.12
+    half = dp * (n - 1) / 2.0
+    kd = dict(exposure_time=100.0, background_rms=0.05, ra_at_xy_0=-half, dec_at_xy_0=-half,
+              transform_pix2angle=np.array([[dp, 0.0], [0.0, dp]]))
+    kernel = s.inp["kernel_0"]
+    rng = np.random.default_rng(8)
+    kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
+
+    def make(image):
+        lens = LensModel(km["lens_model_list"], z_source=km["z_source"], lens_redshift_list=km["lens_redshift_list"],
+                         multi_plane=True)
+        lens.set_multi_plane_constants(s.inp["T_ij_list"], s.inp["T_z_list"], s.inp["reduced2physical"],
+                                       float(s.inp["T_ij_stop"]), float(s.inp["T_z_source"]))
+        return ImageLinearFit(ImageData(image_data=image, **kd), PSF(psf_type="PIXEL", kernel_point_source=kernel), lens,
+                              LightModel(km["source_light_model_list"]), LightModel(km["lens_light_model_list"]),
+                              kwargs_numerics=dict(supersampling_factor=2))
+
+    truth = make(np.zeros((n, n))).image(kl, [dict(ks[0], amp=15.0)], [dict(kll[0], amp=25.0)])
+    image = truth + rng.normal(0, 0.05, truth.shape)
+    lin = make(image)
+    om = imsim.ImageModel(imsim.ImageData(image_data=image, **kd), OPSF(psf_type="PIXEL", kernel_point_source=kernel),
+                          km["lens_model_list"], km["source_light_model_list"], km["lens_light_model_list"],
+                          dict(supersampling_factor=2), multi_plane=s.inp)
+    names = lin.param_names
+    row = np.array([{"lens": kl, "source": ks, "lens_light": kll}[comp][i][nm] for comp, i, nm in names], dtype=float)
+    row[[j for j, (_, _, nm) in enumerate(names) if nm == "theta_E"][0]] *= 1.03  # off the truth: a non-trivial gradient
+    t = torch.as_tensor(row[None, :], device="cuda")
+    logl, grad, amps = lin.logL_linear_grad_batch(t)
+    logl_f, amps_f, _ = lin.logL_linear_batch(t)
+    np.testing.assert_allclose(logl.cpu().numpy(), logl_f.cpu().numpy(), rtol=1e-12)
+    grad = grad.cpu().numpy()[0]
+    assert np.all(np.isfinite(grad))
+
+    def oracle_logl(r):
+        kws = {"lens": [dict() for _ in kl], "source": [dict() for _ in ks], "lens_light": [dict() for _ in kll]}
+        for j, (comp, i, nm) in enumerate(names):
+            kws[comp][i][nm] = r[j]
+        return om.likelihood_data_given_model_linear(kws["lens"], kws["source"], kws["lens_light"])[0]
+
+    def device_logl(r):
+        return float(lin.logL_linear_batch(torch.as_tensor(r[None, :], device="cuda"))[0][0])
+
+    assert abs(oracle_logl(row) - float(logl[0])) <= 1e-9 * abs(float(logl[0]))
+    gscale = np.abs(grad).max()
+    checked = 0
+    for j, (comp, i, nm) in enumerate(names):
+        if nm == "amp":
+            assert grad[j] == 0.0  # solved linearly
+            continue
+        h = 1e-5 * max(1.0, abs(row[j]))
+        fd_dev = _fd(device_logl, row, j, h)
+        assert abs(grad[j] - fd_dev) <= 2e-6 * gscale, (comp, i, nm, grad[j], fd_dev)
+        if comp == "lens":  # the oracle costs ~0.1 s per evaluation: the lens parameters are the ones the sweep touches
+            fd_or = _fd(oracle_logl, row, j, h)
+            assert abs(grad[j] - fd_or) <= 2e-6 * gscale, (comp, i, nm, grad[j], fd_or)
+        checked += 1
+    assert checked >= 20
