@@ -351,6 +351,18 @@ k_image_grad(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
         }
         double ax = 0.0, ay = 0.0;
         LensPt pt[NS > 0 ? NS : 1];
+#pragma unroll
+        for (int l = 0; l < NS; ++l) {
+          lens_point<TIER>(L[l], pool, x, y, pt[l]);
+          ax += pt[l].ax;
+          ay += pt[l].ay;
+        }
+        for (int l = NS; l < P.n_lens; ++l) {
+          double fx, fy;
+          lens_value<TIER>(L[l], pool, x, y, fx, fy);
+          ax += fx;
+          ay += fy;
+        }
         const double bx = x - ax * as, by = y - ay * as;
         double vx = 0.0, vy = 0.0;
         for (int g = 0; g < P.n_light; ++g) {
