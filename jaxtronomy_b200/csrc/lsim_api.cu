@@ -447,7 +447,8 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
     }
     if (D.K > 0) p->kernel_host.assign(d->kernel, d->kernel + (size_t)d->kernel_size * d->kernel_size);
     {  // gradient path: scope check, transposed PSF
-      bool ok = !d->supersampled_conv && d->n_points == 0 && !p->f32 &&
+      // point sources: positions and amplitudes are differentiated (k_point_sources_grad); the PSF error map is not
+      bool ok = !d->supersampled_conv && !(d->n_points > 0 && D.ps_var) && !p->f32 &&
                 (d->conv_mode != LSIM_CONV_EDGE || d->kernel_separable);
       int gs = 0;
       int tier = 0;
@@ -1274,6 +1275,16 @@ int lsim_logl_grad(const lsim_plan* plan, const double* params, int64_t B, int l
     }
     rc = launch_image_grad(plan, params, s0, n, ubar, conv ? 1.0 : D.image_scale, partial, grad, st);
     if (rc != LSIM_OK) return rc;
+    if (D.n_points > 0) {  // after k_grad_reduce has written grad[s0 ... s0 + n): the stamps' own parameters
+      for (int64_t i0 = 0; i0 < n; i0 += 65535) {
+        const int64_t ni = n - i0 < 65535 ? n - i0 : 65535;
+        Timed timed(kClsOther, st);
+        k_point_sources_grad<<<dim3((unsigned)D.n_points, (unsigned)ni), kBlock, 0, st>>>(
+            D, params, s0 + i0, G + (size_t)i0 * img, grad);
+        rc = after_launch("k_point_sources_grad");
+        if (rc != LSIM_OK) return rc;
+      }
+    }
   }
   return LSIM_OK;
 }

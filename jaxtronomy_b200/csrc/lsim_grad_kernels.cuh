@@ -546,6 +546,78 @@ k_source_position(PlanDev P, const double* __restrict__ params, const double* __
   }
 }
 
+// ---- k_point_sources_grad: positions and amplitudes of the point-source images -------------------------------------------
+// grid (n_points, sets).  The stamp of image i lands in slot image `slot` AFTER the PSF convolution (k_point_sources), so
+// its parameters see Abar = dlogL/dC directly:  with S(xs, ys) = sum over the footprint of Abar[pixel] x (sum over the
+// ss x ss sub-pixels of the bilinear interpolant of the PSF kernel at (r + K/2 - ys, c + K/2 - xs)),
+//   dlogL/d(amp) = scale S,   dlogL/d(xs) = amp scale dS/dxs,   (xs, ys) = ss (M (ra, dec) + x0) + (ss - 1)/2
+// and dS/dxs is the sum of the interpolant's own slope -- piecewise constant in x, the derivative jax takes of
+// map_coordinates(order = 1) (ImSim/Numerics/point_source_rendering.py:33-77).  Entries are ADDED to grad[B, P] after
+// k_grad_reduce has written it; every (set, column) is touched by one CTA, so the result is reproducible run to run.
+__device__ __forceinline__ void ps_bilinear_d(const double* __restrict__ k, int K, double ky, double kx, double& v,
+                                              double& dky, double& dkx) {
+  const double fy = floor(ky), fx = floor(kx);
+  const double wy1 = ky - fy, wx1 = kx - fx, wy0 = 1.0 - wy1, wx0 = 1.0 - wx1;
+  const int iy = (int)fy, ix = (int)fx;
+  auto at = [&](int y, int x) { return (y >= 0 && y < K && x >= 0 && x < K) ? k[y * K + x] : 0.0; };
+  const double k00 = at(iy, ix), k01 = at(iy, ix + 1), k10 = at(iy + 1, ix), k11 = at(iy + 1, ix + 1);
+  v = (wy0 * wx0) * k00 + (wy0 * wx1) * k01 + (wy1 * wx0) * k10 + (wy1 * wx1) * k11;
+  dkx = wy0 * (k01 - k00) + wy1 * (k11 - k10);
+  dky = wx0 * (k10 - k00) + wx1 * (k11 - k01);
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_point_sources_grad(PlanDev P, const double* __restrict__ params, int64_t set0, const double* __restrict__ abar,
+                     double* __restrict__ grad) {
+  __shared__ double scratch[3 * (kBlock / 32)];
+  const lsim_point_desc& d = P.points[blockIdx.x];
+  const int64_t bl = blockIdx.y;
+  if (d.slot < 0 || (d.col_ra < 0 && d.col_dec < 0 && !(d.use_amp && d.col_amp >= 0))) return;
+  const double* row = params + (set0 + bl) * P.n_param_cols;
+  const double* A = abar + (bl * P.n_slots + d.slot) * ((int64_t)P.nx * P.ny);
+  const int K = P.ps_K, ss = P.ps_ss, half = K / 2;
+  const double ra = d.col_ra >= 0 ? row[d.col_ra] : d.cst_ra;
+  const double dec = d.col_dec >= 0 ? row[d.col_dec] : d.cst_dec;
+  const double amp = d.use_amp ? (d.col_amp >= 0 ? row[d.col_amp] : d.cst_amp) : 1.0;
+  const double xp = P.ps_M[0] * ra + P.ps_M[1] * dec + P.ps_x0;
+  const double yp = P.ps_M[2] * ra + P.ps_M[3] * dec + P.ps_y0;
+  const double xs = xp * ss + (ss - 1) / 2.0, ys = yp * ss + (ss - 1) / 2.0;
+  double sums[3] = {0.0, 0.0, 0.0};  // S, dS/dxs, dS/dys
+  if (fabs(xs) < 1e9 && fabs(ys) < 1e9) {
+    const int c_lo = (int)floor(xs - half - 1.0), c_hi = (int)ceil(xs - half + K);
+    const int r_lo = (int)floor(ys - half - 1.0), r_hi = (int)ceil(ys - half + K);
+    const int px_lo = max(0, (int)floor((double)c_lo / ss)), px_hi = min(P.nx - 1, (int)floor((double)c_hi / ss));
+    const int py_lo = max(0, (int)floor((double)r_lo / ss)), py_hi = min(P.ny - 1, (int)floor((double)r_hi / ss));
+    const int w = px_hi - px_lo + 1, h = py_hi - py_lo + 1;
+    if (w > 0 && h > 0) {
+      for (int t = threadIdx.x; t < w * h; t += kBlock) {
+        const int py = py_lo + t / w, px = px_lo + t % w;
+        double v = 0.0, gy = 0.0, gx = 0.0;
+        for (int sy = 0; sy < ss; ++sy)
+          for (int sx = 0; sx < ss; ++sx) {
+            double a, dky, dkx;
+            ps_bilinear_d(P.ps_kernel, K, (py * ss + sy) + half - ys, (px * ss + sx) + half - xs, a, dky, dkx);
+            v += a;
+            gy -= dky;  // ky = r + K/2 - ys
+            gx -= dkx;
+          }
+        const double ab = A[(int64_t)py * P.nx + px];
+        sums[0] = fma(ab, v, sums[0]);
+        sums[1] = fma(ab, gx, sums[1]);
+        sums[2] = fma(ab, gy, sums[2]);
+      }
+    }
+  }
+  block_sum(sums, scratch);
+  if (threadIdx.x == 0) {
+    double* g = grad + (set0 + bl) * P.n_param_cols;
+    const double f = amp * P.ps_scale * ss;
+    if (d.col_ra >= 0) atomicAdd(g + d.col_ra, f * (P.ps_M[0] * sums[1] + P.ps_M[2] * sums[2]));
+    if (d.col_dec >= 0) atomicAdd(g + d.col_dec, f * (P.ps_M[1] * sums[1] + P.ps_M[3] * sums[2]));
+    if (d.use_amp && d.col_amp >= 0) atomicAdd(g + d.col_amp, P.ps_scale * sums[0]);
+  }
+}
+
 // ---- k_grad_reduce ------------------------------------------------------------------------------------------------
 // One CTA per set: entry sums over the tiles (fixed order), then the entries of each parameter column.
 __global__ void __launch_bounds__(128)

@@ -463,3 +463,67 @@ def test_multi_plane_gradient_against_the_oracle_and_the_forward_path():
             assert abs(grad[j] - fd_or) <= 2e-6 * gscale, (comp, i, nm, grad[j], fd_or)
         checked += 1
     assert checked >= 20
+
+
+@pytest.mark.parametrize("linear", [True, False])
+def test_point_source_gradient(linear):
+    """EPL + SHEAR, two Sersic components, a lensed quad and a field star (the reference fixture `image_quad_and_star`,
+    40 x 40, ss 2, 9 x 9 pixel PSF): d logL / d(ra_image, dec_image[, point_amp]) from k_point_sources_grad and every
+    other column from the extended-light path, against 4th-order central differences of the device forward path and, for
+    the point-source columns, of the NumPy oracle.  The stamps are bilinear interpolations of the PSF kernel
+    (point_source_rendering.py:33-77): logL is piecewise smooth in the positions, the step stays far inside a cell."""
+    import torch
+
+    from tests.golden_io import load
+    from tests.test_gpu_parity import _ps_model
+    from tests.test_oracle_golden import _oracle_ps_model
+
+    c = load("point_sources.npz")["image_quad_and_star"]
+    kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
+    kps = [{k: np.asarray(v, dtype=float) for k, v in kw.items()} for kw in c.meta["kwargs_ps"]]
+    lin = _ps_model(c, linear=True)
+    lin.num_point_source_images = [4, 1]
+    om = _oracle_ps_model(c)
+    mat, _, _ = lin._pack(kl, ks, kll, kps, [4, 1])
+    row = np.array(mat[0], dtype=float)
+    names = lin.param_names
+    t = torch.as_tensor(row[None, :], device="cuda")
+    if linear:
+        logl, grad, _ = lin.logL_linear_grad_batch(t)
+        fwd = lambda r: float(lin.logL_linear_batch(torch.as_tensor(r[None, :], device="cuda"))[0][0])  # noqa: E731
+    else:
+        logl, grad = lin.logL_grad_batch(t)
+        fwd = lambda r: float(lin.logL_batch(torch.as_tensor(r[None, :], device="cuda"))[0])  # noqa: E731
+    assert abs(float(logl[0]) - fwd(row)) <= 1e-12 * abs(fwd(row))
+    grad = grad.cpu().numpy()[0]
+    assert np.all(np.isfinite(grad))
+
+    def oracle(r):
+        kws = {"lens": [dict() for _ in kl], "source": [dict() for _ in ks], "lens_light": [dict() for _ in kll]}
+        ps = [dict(ra_image=np.zeros(4), dec_image=np.zeros(4), point_amp=np.zeros(4)),
+              dict(ra_image=np.zeros(1), dec_image=np.zeros(1), point_amp=np.zeros(1))]
+        for j, (comp, i, nm) in enumerate(names):
+            if comp == "point_source":
+                base, e = nm.split("[")
+                ps[i][base][int(e[:-1])] = r[j]
+            else:
+                kws[comp][i][nm] = r[j]
+        if linear:
+            return om.likelihood_data_given_model_linear(kws["lens"], kws["source"], kws["lens_light"], kwargs_ps=ps)[0]
+        return om.likelihood_data_given_model(kws["lens"], kws["source"], kws["lens_light"], kwargs_ps=ps)
+
+    assert abs(oracle(row) - float(logl[0])) <= 1e-9 * abs(float(logl[0]))
+    gscale = np.abs(grad).max()
+    n_ps = 0
+    for j, (comp, i, nm) in enumerate(names):
+        if linear and (nm == "amp" or nm.startswith("point_amp")):
+            assert grad[j] == 0.0  # solved linearly
+            continue
+        h = 1e-6 * max(1.0, abs(row[j]))
+        fd = _fd(fwd, row, j, h)
+        assert abs(grad[j] - fd) <= 5e-6 * gscale, (comp, i, nm, grad[j], fd)
+        if comp == "point_source":
+            fo = _fd(oracle, row, j, h)
+            assert abs(grad[j] - fo) <= 5e-6 * gscale, (comp, i, nm, grad[j], fo)
+            n_ps += 1
+    assert n_ps == (10 if linear else 15)
