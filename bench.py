@@ -341,7 +341,7 @@ def secondary_configs():
     from tools import bench_configs as bc
 
     out = {}
-    for name in ("c2", "c3", "c4", "c5", "mixed"):
+    for name in ("c1_pso", "c1_lbfgs", "c2", "c3", "c4", "c5", "mixed"):
         try:
             out[name] = bc.CONFIGS[name]()
         except Exception as e:  # a secondary line must never take the headline down

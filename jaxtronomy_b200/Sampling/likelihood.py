@@ -216,8 +216,11 @@ class LikelihoodModule(object):
         if self._source_marg:
             raise ValueError("the gradient does not cover the source marginalisation constant")
         pl = self._position_likelihood
-        if pl is not None and (self._pos_plan is not None or pl._image_position_likelihood):
-            raise ValueError("the gradient does not cover the position likelihood: pass source_position_likelihood=False")
+        if pl is not None and self._pos_plan is not None:
+            # the penalty is built on the lensing Jacobian at the images: its gradient needs third derivatives of the
+            # potential, which no kernel here carries (the imaging likelihood's gradient does cover the positions)
+            raise ValueError("the gradient does not cover the source-position penalty of the position likelihood: "
+                             "pass source_position_likelihood=False")
         total, gtotal = None, None
         for plan in self._plans:
             l, g, _ = plan.logl_grad(positions, linear_solve=self._linear_solver)
@@ -231,6 +234,19 @@ class LikelihoodModule(object):
             total = total + pv
             if pg is not None:
                 gtotal = gtotal + pg
+        if pl is not None and pl._image_position_likelihood and self._pos_models:
+            # image-position term (position_likelihood.py:214-247): a quadratic form of the sampled columns themselves
+            for k, (kind, n, src) in enumerate(self._pos_models):
+                m = min(len(pl._ra_image_list[k]), n)
+                for lst, ref in ((src[0], pl._ra_image_list[k]), (src[1], pl._dec_image_list[k])):
+                    for e in range(m):
+                        kind_e, v = lst[e]
+                        if kind_e == "col":
+                            d = positions[:, v] - float(ref[e])
+                            total = total - d * d / pl._image_position_sigma**2 / 2
+                            gtotal[:, v] -= d / pl._image_position_sigma**2
+                        else:
+                            total = total - (v - float(ref[e])) ** 2 / pl._image_position_sigma**2 / 2
         if self._check_bounds:
             if self._bounds_dev is None or self._bounds_dev[0].device != positions.device:
                 self._bounds_dev = (torch.as_tensor(self._lower_limit, device=positions.device),

@@ -527,3 +527,39 @@ def test_point_source_gradient(linear):
             assert abs(grad[j] - fo) <= 5e-6 * gscale, (comp, i, nm, grad[j], fo)
             n_ps += 1
     assert n_ps == (10 if linear else 15)
+
+
+def test_likelihood_module_gradient_with_point_sources_and_image_position_term():
+    """LikelihoodModule.logL_and_grad_batch for the Einstein-ring notebook's model class (EPL + SHEAR, two Sersic
+    components, a 4-image LENSED_POSITION point source) with the image-position likelihood on and the source-position
+    penalty off: value == logL_batch, gradient == central differences of logL_batch; with the penalty on it raises."""
+    from tests.golden_io import load
+    from tests.test_gpu_parity import _ps_model
+    from jaxtronomy_b200.Sampling.likelihood import LikelihoodModule
+    from jaxtronomy_b200.Sampling.parameters import Param
+
+    c = load("point_sources.npz")["image_quad_and_star"]
+    kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
+    kps = [{k: np.asarray(v, dtype=float) for k, v in kw.items()} for kw in c.meta["kwargs_ps"]]
+    lin = _ps_model(c, linear=True)
+    km = dict(lens_model_list=c.meta["lens_model_list"], source_light_model_list=c.meta["source_model_list"],
+              lens_light_model_list=c.meta["lens_light_model_list"], point_source_model_list=c.meta["point_source_type_list"])
+    param = Param(km, kwargs_fixed_lens=[{}, {"ra_0": 0.0, "dec_0": 0.0}], num_point_source_list=[4, 1])
+    ra_list = [list(kps[0]["ra_image"] + 0.002), list(kps[1]["ra_image"])]
+    dec_list = [list(kps[0]["dec_image"] - 0.001), list(kps[1]["dec_image"])]
+    like = LikelihoodModule(lin, param, source_position_likelihood=False, image_position_likelihood=True,
+                            image_position_uncertainty=0.004, ra_image_list=ra_list, dec_image_list=dec_list)
+    x0 = param.kwargs2args(kl, ks, kll, kwargs_ps=kps)
+    pos = np.stack([x0, x0 * (1 + 1e-3)])
+    l, g = like.logL_and_grad_batch(pos)
+    np.testing.assert_allclose(l, like.logL_batch(pos), rtol=1e-12)
+    assert np.all(np.isfinite(g)) and g.shape == pos.shape
+    gs = np.abs(g[0]).max()
+    for j in range(len(x0)):
+        h = 1e-6 * max(1.0, abs(x0[j]))
+        e = np.zeros_like(x0)
+        e[j] = h
+        fd = (8 * (like.logL(x0 + e) - like.logL(x0 - e)) - (like.logL(x0 + 2 * e) - like.logL(x0 - 2 * e))) / (12 * h)
+        assert abs(g[0, j] - fd) <= 5e-6 * gs, (j, param.num_param()[1][j], g[0, j], fd)
+    with pytest.raises(ValueError):
+        LikelihoodModule(lin, param).logL_and_grad_batch(pos)  # source-position penalty on (the default): value only
