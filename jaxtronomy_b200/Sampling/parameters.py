@@ -7,7 +7,8 @@ solved linearly instead (LightParam / LinearBasis.add_fixed_linear, linear_basis
 
 Beyond the reference: ``column_source_fn()`` turns the same bookkeeping into the per-parameter column / constant
 map of a kernel plan, so that a batch of sampler positions is consumed by the GPU without any per-particle Python.
-Joint-parameter links, point sources and special parameters are outside the scope.
+Point sources (UNLENSED / LENSED_POSITION: ra_image, dec_image, point_amp per image, after the light components) are
+sampled too; joint-parameter links and special parameters are outside the scope.
 """
 
 import numpy as np
