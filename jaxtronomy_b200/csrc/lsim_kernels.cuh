@@ -416,7 +416,9 @@ k_image(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt, dou
 // arithmetic differs from k_image's in the last bits only (the affine coordinates agree with the arrays to a few ulp:
 // checked at plan creation).  Scope: single plane, exactly one EPL (or SIE evaluated as EPL) and any number of SHEAR /
 // CONVERGENCE, NL <= 2 SERSIC / SERSIC_ELLIPSE components, SS in {1, 2, 3}, no sub-frame mask, no supersampled
-// convolution; anything else runs k_image.
+// convolution; anything else runs k_image.  (An EPL_MULTIPOLE_M1M3M4 variant -- multipoles evaluated from the affine
+// centred position, folded into the light coordinates through scal T -- was measured on BASELINE config 3 and was SLOWER
+// than the specialised k_image, 74.6 vs 65.3 ms per 8192 sets, gpurun_out/r2_variants3.txt: not kept.)
 struct FoldLight {
   double X0, Xi, Xj, Xj2, Y0, Yi, Yj, Yj2, Q00, Q01, Q10, Q11;
 };
@@ -682,6 +684,7 @@ struct ConvWeights {
   double w[KT * KT];
 };
 
+// (2 resident CTAs per SM; 3 measured the same to 0.2 %, gpurun_out/r2_variants3.txt)
 template <int KT, int R, int NW>
 __global__ void __launch_bounds__(NW * 32, 2)
 k_conv_tiled_u(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int mode, double scale,
