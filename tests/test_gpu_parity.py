@@ -642,3 +642,43 @@ def test_batch_edge_cases(headline):
         ref, ramp = oracle_headline_logl(headline_w, b)
         assert abs(float(lw[b]) - ref) <= 1e-9 * abs(ref), (b, float(lw[b]), ref)
         np.testing.assert_allclose(aw[b].cpu().numpy(), ramp, rtol=1e-8)
+
+
+def test_point_source_model_without_linear_flux_keeps_the_solve_intact():
+    """flux_from_point_source_list=[False]: the model's images own no basis image (point_source.py:296,361,398) -- the
+    linear system, its amplitudes and logL are those of the same model without point sources (round-1 advisor finding:
+    the empty slots used to zero every amplitude through the conditioning gate)."""
+    from jaxtronomy_b200.Data.imaging_data import ImageData
+    from jaxtronomy_b200.ImSim.image_linear_solve import ImageLinearFit
+    from jaxtronomy_b200.LensModel.lens_model import LensModel
+    from jaxtronomy_b200.LightModel.light_model import LightModel
+    from jaxtronomy_b200.PointSource.point_source import PointSource
+
+    c = POINTS["image_quad_and_star"]
+    kl, ks, kll = c.meta["kwargs_lens"], c.meta["kwargs_source"], c.meta["kwargs_lens_light"]
+    kps = [{k: np.asarray(v, dtype=float) for k, v in kw.items()} for kw in c.meta["kwargs_ps"]]
+    kd = dict(image_data=c.inp["image_data"], transform_pix2angle=c.inp["transform_pix2angle"],
+              ra_at_xy_0=float(c.inp["ra_at_xy_0"]), dec_at_xy_0=float(c.inp["dec_at_xy_0"]),
+              background_rms=float(c.inp["background_rms"]), exposure_time=float(c.inp["exposure_time"]))
+    lens = LensModel(c.meta["lens_model_list"])
+
+    def build(ps):
+        return ImageLinearFit(ImageData(**kd), _psf(c.meta["kwargs_psf"], c.inp), lens,
+                              LightModel(c.meta["source_model_list"]), LightModel(c.meta["lens_light_model_list"]),
+                              point_source_class=ps, kwargs_numerics=c.meta["kwargs_numerics"])
+
+    plain = build(None)
+    l0, p0 = plain.likelihood_data_given_model(kl, ks, kll)
+    off = build(PointSource(c.meta["point_source_type_list"], lens_model=lens, flux_from_point_source_list=[False, False]))
+    assert off.num_param_linear(kl, ks, kll, kps) == 2
+    l1, p1 = off.likelihood_data_given_model(kl, ks, kll, kps)
+    assert p1.shape == p0.shape == (2,) and np.all(p1 != 0)
+    np.testing.assert_allclose(p1, p0, rtol=1e-12)
+    assert abs(l1 - l0) <= 1e-12 * abs(l0)
+    # one model in, one out: the quad's four images are the only point-source basis images
+    mixed = build(PointSource(c.meta["point_source_type_list"], lens_model=lens, flux_from_point_source_list=[True, False]))
+    assert mixed.num_param_linear(kl, ks, kll, kps) == 6
+    A = mixed.linear_response_matrix(kl, ks, kll, kps)
+    assert A.shape[0] == 6 and np.all(np.abs(A).sum(axis=1) > 0)
+    l2, p2 = mixed.likelihood_data_given_model(kl, ks, kll, kps)
+    assert p2.shape == (6,) and np.all(p2 != 0) and np.isfinite(l2)
