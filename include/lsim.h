@@ -285,10 +285,13 @@ int lsim_logl(const lsim_plan* plan, const double* params, int64_t B, int linear
  *   grad       device [B, P]: d logl[b] / d params[b, :]; columns no profile reads are 0; with linear_solve the
  *              amplitudes are functions of the other parameters (solved per set), not parameters
  *   amps       device [B, n_slots] or NULL (linear_solve only)
- * Scope: single plane; every lens profile of this header; SERSIC, SERSIC_ELLIPSE, GAUSSIAN; PSF none, pixel
- * kernel (zero boundary) or separable Gaussian (edge-replicated); regular convolution; no point sources; fp64.
- * Anything else: LSIM_E_UNSUPPORTED (never a finite-difference or CPU fallback).  Results are bit-reproducible
- * run to run (fixed reduction order, no atomics).  Workspace: lsim_logl_grad_workspace_bytes (less is accepted,
+ * Scope: single plane and multi plane (reverse sweep over the planes, at most 8 profiles after expanding
+ * EPL_MULTIPOLE_M1M3M4; MultiPlaneBase.ray_shooting_partial_comoving, multi_plane_base.py:159-233); every lens profile
+ * of this header; SERSIC, SERSIC_ELLIPSE, GAUSSIAN; point-source images (ra, dec and, without linear_solve, amp: the
+ * slope of the bilinear PSF stamp, point_source_rendering.py:33-77); PSF none, pixel kernel (zero boundary) or separable
+ * Gaussian (edge-replicated); regular convolution; fp64.  Anything else (supersampled convolution, PSF error map,
+ * fp32): LSIM_E_UNSUPPORTED (never a finite-difference or CPU fallback).  Results are reproducible run to run (fixed
+ * reduction order; the point-source entries are added by one CTA per (set, column)).  Workspace: lsim_logl_grad_workspace_bytes (less is accepted,
  * down to one set). */
 size_t lsim_logl_grad_workspace_bytes(const lsim_plan* plan, int64_t B);
 int lsim_logl_grad(const lsim_plan* plan, const double* params, int64_t B, int linear_solve, double* logl,
