@@ -161,6 +161,20 @@ LSIM_HD double rsqrt_fast(double x) {
 #endif
 }
 
+// 1/sqrt(x) for finite, normal, positive x: MUFU.RSQ64H seed (relative error <= 2^-22) and ONE third-order step
+// y (1 + e/2 + 3 e^2/8), e = 1 - x y^2: 5 fp64 instructions, error ~e^3 before rounding (a couple of ulp at most).
+// For consumers whose own accuracy bar is far above the last bit (the 44-term CSE sums: x y gives the square root).
+LSIM_HD double rsqrt_fast3(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(x * y), y, 1.0);
+  return fma(y, e * fma(0.375, e, 0.5), y);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 // ---- fast fp64 log2 / exp2 --------------------------------------------------------------------------
 // The hot loop needs pow(x, s) = exp2(s * log2(x)) and exp(-b (k - 1)) for finite positive normal x.
 // libdevice's log/exp/pow carry special-case branches and long polynomials; on a kernel bound by the fp64 pipe
