@@ -14,6 +14,11 @@
 #include "lsim_f32.cuh"
 #include "lsim_grad_kernels.cuh"
 
+// the headline kernels are compiled in lsim_hot.cu
+#define LSIM_HOT extern template
+#include "lsim_hot_list.h"
+#undef LSIM_HOT
+
 using namespace lsim;
 
 namespace {

@@ -217,7 +217,7 @@ k_like_adjoint(PlanDev P, const double* __restrict__ conv, int64_t set0, int lin
 //   out[o] = sum_d k1[d + R] in[clamp(o - d)],  d = -R..R        (GaussianConvolution, convolution.py:216-236)
 // along x (axis 0) or y (axis 1):  adj[i] = sum_o out_bar[o] [clamp(o - d) == i] k1[d + R].
 // Interior i collects o = i + d; the two edge pixels also collect every tap that was clamped onto them.
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_conv_adj_edge(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
                 const double* __restrict__ k1, int axis, double scale) {
   const int R = (K - 1) / 2;
@@ -441,7 +441,7 @@ __host__ __device__ inline size_t hess_smem_bytes(int n_lens, int n_series) {
   return (size_t)n_lens * (sizeof(ad::GLens) + 2 * sizeof(int)) + (size_t)n_series * ad::kGradPool * sizeof(double);
 }
 
-__global__ void __launch_bounds__(kGradBlock)
+static __global__ void __launch_bounds__(kGradBlock)
 k_hessian(PlanDev P, const double* __restrict__ params, const double* __restrict__ x, const double* __restrict__ y,
           int64_t N, int coords_batched, int n_series, double scale, double* __restrict__ out) {
   using namespace ad;
@@ -490,7 +490,7 @@ __host__ __device__ inline size_t srcpos_smem_bytes(int n_lens, int n_series, in
   return hess_smem_bytes(n_lens, n_series) + (size_t)7 * n_img * sizeof(double);
 }
 
-__global__ void __launch_bounds__(32)
+static __global__ void __launch_bounds__(32)
 k_source_position(PlanDev P, const double* __restrict__ params, const double* __restrict__ x,
                   const double* __restrict__ y, int n_img, int coords_batched, int n_series, double scale, double sigma,
                   double hard_bound_rms, double* __restrict__ logl) {
@@ -566,7 +566,7 @@ __device__ __forceinline__ void ps_bilinear_d(const double* __restrict__ k, int 
   dky = wx0 * (k10 - k00) + wx1 * (k11 - k01);
 }
 
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_point_sources_grad(PlanDev P, const double* __restrict__ params, int64_t set0, const double* __restrict__ abar,
                      double* __restrict__ grad) {
   __shared__ double scratch[3 * (kBlock / 32)];
@@ -620,7 +620,7 @@ k_point_sources_grad(PlanDev P, const double* __restrict__ params, int64_t set0,
 
 // ---- k_grad_reduce ------------------------------------------------------------------------------------------------
 // One CTA per set: entry sums over the tiles (fixed order), then the entries of each parameter column.
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_grad_reduce(PlanDev P, const double* __restrict__ partial, int tiles, int64_t set0, double* __restrict__ grad) {
   extern __shared__ double s_e[];
   const int64_t bl = blockIdx.x;

@@ -101,7 +101,7 @@ __host__ __device__ inline size_t prepared_bytes(int n_lens, int n_light, int n_
          (size_t)n_series * kMaxSeries * sizeof(double);
 }
 
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_prepare(PlanDev P, const double* __restrict__ params, int64_t set0, int64_t n_sets, int n_series,
           unsigned char* __restrict__ prepared) {
   const int n_items = P.n_lens + P.n_light;
@@ -215,7 +215,7 @@ k_ray_shoot(PlanDev P, const double* __restrict__ params, const double* __restri
 }
 
 // ---- k_surface_brightness ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_surface_brightness(PlanDev P, const double* __restrict__ params, const double* __restrict__ x,
                      const double* __restrict__ y, int64_t N, int coords_batched, double* __restrict__ out) {
   __shared__ LightC G[kMaxLight];
@@ -534,7 +534,9 @@ k_image_fold(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
     double acc[NSLOT];
 #pragma unroll
     for (int k = 0; k < NSLOT; ++k) acc[k] = 0.0;
-#pragma unroll 1
+    // rows unrolled: with a rolled loop the compiler spills a handful of per-set constants inside it
+    // (+4 % measured, gpurun_out/r2_variants4.txt)
+#pragma unroll
     for (int i = 0; i < SS; ++i) {
       double racc[NSLOT];
 #pragma unroll
@@ -593,7 +595,7 @@ k_image_fold(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt
 
 // ---- k_rebin: Numerics.re_size_convolve for a caller-supplied supersampled flux ------------------------------
 // flux [n_img][ny*ss][nx*ss] -> out [n_img][ny][nx] = block mean (* scale)  (grid.py:101-117, image_util.py:78-98)
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_rebin(const double* __restrict__ flux, double* __restrict__ out, int nx, int ny, int ss, double scale) {
   const int npix = nx * ny;
   const int64_t nsub = (int64_t)npix * ss * ss;
@@ -628,7 +630,7 @@ __device__ __forceinline__ double conv_fetch(const double* img, int nx, int ny, 
   return (x >= 0 && x < nx && y >= 0 && y < ny) ? img[(int64_t)y * nx + x] : 0.0;
 }
 
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_conv_direct(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
               const double* __restrict__ kernel, int mode, double scale, int accumulate) {
   extern __shared__ double smem[];
@@ -731,7 +733,7 @@ k_conv_tiled_u(const double* __restrict__ in, double* __restrict__ out, int nx, 
 }
 
 // Separable variant (kernel == outer(k1, k1), e.g. the Gaussian PSF): row pass into shared memory, column pass out.
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_conv_separable(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,
                  const double* __restrict__ k1, int mode, double scale, int accumulate) {
   extern __shared__ double smem[];
@@ -790,7 +792,7 @@ __device__ __forceinline__ double ps_bilinear(const double* __restrict__ k, int 
   return s;
 }
 
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_point_sources(PlanDev P, const double* __restrict__ params, int64_t set0, double* __restrict__ dst) {
   const int slot = blockIdx.x;
   const int64_t bl = blockIdx.y;
@@ -829,7 +831,7 @@ k_point_sources(PlanDev P, const double* __restrict__ params, int64_t set0, doub
 
 // ---- k_ps_error_map: PSF error map of one parameter set (one CTA per set) -------------------------------------------
 // err[set][pixel] = sum over flagged point-source images of bilinear(psf_variance_map) * amp_est^2  (see lsim.h)
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_ps_error_map(PlanDev P, const double* __restrict__ params, int64_t set0, double* __restrict__ err) {
   const int64_t bl = blockIdx.x;
   const double* row = params + (set0 + bl) * P.n_param_cols;
@@ -880,7 +882,7 @@ k_ps_error_map(PlanDev P, const double* __restrict__ params, int64_t set0, doubl
 
 // ---- FFT convolution helpers (large kernels; the transforms themselves are cuFFT) ----------------------------------
 // zero-padded copy [n][ny][nx] -> [n][PY][PX]
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_fft_pad(const double* __restrict__ in, double* __restrict__ pad, int nx, int ny, int PX, int PY) {
   const double* src = in + (int64_t)blockIdx.y * nx * ny;
   double* dst = pad + (int64_t)blockIdx.y * PX * PY;
@@ -891,7 +893,7 @@ k_fft_pad(const double* __restrict__ in, double* __restrict__ pad, int nx, int n
 }
 
 // spectrum [n][PY][PXc] *= kernel spectrum [PY][PXc] * norm
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_fft_mul(double2* __restrict__ spec, const double2* __restrict__ kspec, int n_spec, double norm) {
   double2* s = spec + (int64_t)blockIdx.y * n_spec;
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n_spec; i += gridDim.x * kBlock) {
@@ -901,7 +903,7 @@ k_fft_mul(double2* __restrict__ spec, const double2* __restrict__ kspec, int n_s
 }
 
 // out[n][ny][nx] (+)= scale * full[n][y + r][x + r]   ("same" part of the full linear convolution)
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_fft_crop(const double* __restrict__ pad, double* __restrict__ out, int nx, int ny, int PX, int PY, int r,
            double scale, int accumulate) {
   const double* src = pad + (int64_t)blockIdx.y * PX * PY;
@@ -1158,7 +1160,7 @@ k_likelihood(PlanDev P, const double* __restrict__ conv, int64_t set0, int linea
 // ---- particle swarm: best-particle bookkeeping and move ------------------------------------------------------------
 // k_pso_best (one CTA): argmax of fitness (lowest index on ties), global best update, then personal bests.
 constexpr int kPsoBlock = 1024;
-__global__ void __launch_bounds__(kPsoBlock)
+static __global__ void __launch_bounds__(kPsoBlock)
 k_pso_best(const double* __restrict__ position, const double* __restrict__ fitness, double* __restrict__ pbest_pos,
            double* __restrict__ pbest_fit, double* __restrict__ gbest_pos, double* __restrict__ gbest_fit, int64_t B,
            int P) {
@@ -1216,7 +1218,7 @@ k_pso_best(const double* __restrict__ position, const double* __restrict__ fitne
 }
 
 // k_pso_move: one thread per (particle, dimension); individually rounded operations in NumPy's order.
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_pso_move(double* __restrict__ position, double* __restrict__ velocity, const double* __restrict__ pbest_pos,
            const double* __restrict__ gbest_pos, const double* __restrict__ rnd, int64_t n, int P, double c1,
            double c2) {
@@ -1233,7 +1235,7 @@ k_pso_move(double* __restrict__ position, double* __restrict__ velocity, const d
 }
 
 // ---- k_fp64_peak ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_fp64_peak(int64_t iters, double* sink) {
+static __global__ void __launch_bounds__(kBlock) k_fp64_peak(int64_t iters, double* sink) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 0.999999, c = 1e-7;
   for (int64_t i = 0; i < iters; ++i) {

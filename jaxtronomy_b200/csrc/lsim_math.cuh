@@ -23,7 +23,7 @@
 #if defined(__CUDACC__)
 #define LSIM_HD __host__ __device__ __forceinline__
 #define LSIM_D __device__ __forceinline__
-#define LSIM_TABLE __constant__ double
+#define LSIM_TABLE static __constant__ double
 #else
 #define LSIM_HD inline
 #define LSIM_D inline
@@ -45,8 +45,9 @@ LSIM_TABLE kLog2C[6] = {-kLog2e / 6.0, kLog2e / 5.0, -kLog2e / 4.0, kLog2e / 3.0
 // evaluates profiles copies the tables from global into SHARED memory once per CTA (stage_math_tables): a lookup is
 // then one LDS at a 32-bit offset (no 64-bit address arithmetic, lower latency than an L1 hit).
 #if defined(__CUDACC__)
-__device__ unsigned long long d_exp2_tab[LSIM_EXP2_N] = LSIM_EXP2_TABLE;
-__device__ double d_log2_tab[2 * LSIM_LOG2_N] = LSIM_LOG2_TABLE;
+// (static: liblsim.so is built from two translation units, each with its own copy)
+static __device__ unsigned long long d_exp2_tab[LSIM_EXP2_N] = LSIM_EXP2_TABLE;
+static __device__ double d_log2_tab[2 * LSIM_LOG2_N] = LSIM_LOG2_TABLE;
 __shared__ unsigned long long s_exp2_tab[LSIM_EXP2_N];
 __shared__ double2 s_log2_tab[LSIM_LOG2_N];
 // call at kernel entry, followed by a __syncthreads() before the first log2_pos / exp2_*

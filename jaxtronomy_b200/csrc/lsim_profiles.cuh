@@ -50,13 +50,15 @@ struct LightC {
 };
 
 // ---- CSE tables: device copies live in constant memory, host copies are the header arrays -------------
+// (static + uploaded by lsim_api.cu's upload_tables(): only kernels of THAT translation unit may read them; the
+// kernels instantiated in lsim_hot.cu -- k_image_fold, k_likelihood, k_conv_tiled_u -- do not)
 #if defined(__CUDACC__)
-__constant__ double d_nfw_cse_high_s[LSIM_NFW_CSE_HIGH_S_N];
-__constant__ double d_nfw_cse_high_a[LSIM_NFW_CSE_HIGH_A_N];
-__constant__ double d_nfw_cse_low_s[LSIM_NFW_CSE_LOW_S_N];
-__constant__ double d_nfw_cse_low_a[LSIM_NFW_CSE_LOW_A_N];
-__constant__ double d_hernquist_cse_s[LSIM_HERNQUIST_CSE_S_N];
-__constant__ double d_hernquist_cse_a[LSIM_HERNQUIST_CSE_A_N];
+static __constant__ double d_nfw_cse_high_s[LSIM_NFW_CSE_HIGH_S_N];
+static __constant__ double d_nfw_cse_high_a[LSIM_NFW_CSE_HIGH_A_N];
+static __constant__ double d_nfw_cse_low_s[LSIM_NFW_CSE_LOW_S_N];
+static __constant__ double d_nfw_cse_low_a[LSIM_NFW_CSE_LOW_A_N];
+static __constant__ double d_hernquist_cse_s[LSIM_HERNQUIST_CSE_S_N];
+static __constant__ double d_hernquist_cse_a[LSIM_HERNQUIST_CSE_A_N];
 #endif
 
 LSIM_HD const double* cse_table(int which) {

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x 2>&1 | tail -6
-python tools/bench_configs.py c2 c3 c4 c5 2>&1 | tail -5 | cut -c1-330 | tee gpurun_out/r2_configs_n.txt
+for f in jaxtronomy_b200/csrc/liblsim.so build_variants/*.so jaxtronomy_b200/csrc/liblsim.so; do echo "== $f"; LSIM_LIB=$PWD/$f python bench.py --no-cpu --no-secondary --steps 3 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['avg_launch_ms'], d['roofline']['kernel_share_of_step'])"; done 2>&1 | tee gpurun_out/r2_variants4.txt
