@@ -134,6 +134,7 @@ struct lsim_plan {
   int n_series = 0;
   int sig = -1;  // index of the specialised image kernel for this model, or -1
   bool fold = false;  // the model and the grid are inside k_image_fold's scope (lsim_kernels.cuh)
+  bool ray_epl_shear = false;  // single-plane EPL + SHEAR: k_ray_shoot with the compile-time profile list
   bool has_image = false, has_data = false;
   bool f32 = false;  // LSIM_PRECISION_F32: the image kernel runs in single precision
   size_t image_smem = 0;
@@ -341,6 +342,8 @@ int lsim_plan_create(const lsim_plan_desc* d, lsim_plan** out) {
   p->full = full;
   p->n_series = n_series;
   p->sig = find_signature(d);
+  p->ray_epl_shear = !d->multi_plane && d->n_lens == 2 && effective_lens_type(d->lens[0]) == LSIM_LENS_EPL &&
+                     effective_lens_type(d->lens[1]) == LSIM_LENS_SHEAR && !getenv("LSIM_NO_SPECIALISE");
   p->has_image = has_image;
   p->has_data = has_data;
   p->f32 = d->precision == LSIM_PRECISION_F32;
@@ -546,7 +549,10 @@ int lsim_ray_shoot(const lsim_plan* plan, const double* params, int64_t B, const
     rpc = bpc * batch;
   }
   dim3 grid((unsigned)((N + rpc - 1) / rpc), (unsigned)B);
-  if (plan->full)
+  if (plan->ray_epl_shear)
+    k_ray_shoot<false, TypeList<LSIM_LENS_EPL, LSIM_LENS_SHEAR>><<<grid, kBlock, kRaySmem, st>>>(
+        plan->dev, params, x, y, N, coords_batched, out_x, out_y, what, rpc);
+  else if (plan->full)
     k_ray_shoot<true><<<grid, kBlock, kRaySmem, st>>>(plan->dev, params, x, y, N, coords_batched, out_x, out_y, what, rpc);
   else
     k_ray_shoot<false><<<grid, kBlock, kRaySmem, st>>>(plan->dev, params, x, y, N, coords_batched, out_x, out_y, what, rpc);

@@ -155,13 +155,18 @@ __device__ __forceinline__ void load_or_stage(const PlanDev& P, const double* ro
 }
 
 // ---- k_ray_shoot ---------------------------------------------------------------------------------------------
-constexpr int kRayItems = 2;
+// rays per thread in lock step: 3 measured +3.5 % (C2) / +2.7 % (C4) over 2; 4 spills in the 1,000-halo loop
+#ifndef LSIM_RAY_ITEMS
+#define LSIM_RAY_ITEMS 3
+#endif
+constexpr int kRayItems = LSIM_RAY_ITEMS;
 
 // rpc: rays per CTA (a multiple of kBlock * kRayItems).  A model whose deflector list fits one shared-memory chunk
 // is staged ONCE per CTA and the CTA then walks its rays, so the per-set preparation (trig, series coefficients) is
 // amortised over thousands of rays; longer lists (LensModelBulk, 1000 halos) stream chunk by chunk past one ray batch
 // that stays in registers (the host passes rpc = kBlock * kRayItems for those).
-template <bool FULL>
+// LT: compile-time list of the prepared profile types (single plane; lsim_api.cu registers EPL + SHEAR), or RuntimeTypes
+template <bool FULL, class LT = RuntimeTypes>
 __global__ void __launch_bounds__(kBlock)
 k_ray_shoot(PlanDev P, const double* __restrict__ params, const double* __restrict__ x, const double* __restrict__ y,
             int64_t N, int coords_batched, double* __restrict__ ox, double* __restrict__ oy, int what, int64_t rpc) {
@@ -195,7 +200,7 @@ k_ray_shoot(PlanDev P, const double* __restrict__ params, const double* __restri
         stage_lens(P, row, c0, n_c, L, pool);
         __syncthreads();
       }
-      ray_apply<FULL, kRayItems>(P.ray, L, pool, n_c, r);
+      ray_apply<FULL, kRayItems, LT>(P.ray, L, pool, n_c, r);
     }
 #pragma unroll
     for (int k = 0; k < kRayItems; ++k) {
