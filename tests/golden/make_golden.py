@@ -11,6 +11,7 @@ lenstronomy host helpers -- see refshim.py for what is and is not substituted) a
     tests/golden/profiles.npz     deflections of every hot-path lens profile + light profiles + 2F1 sweep
     tests/golden/lens_models.npz  LensModel / LensModelBulk / MultiPlane ray shooting
     tests/golden/imsim.npz        grid bookkeeping, re-bin + convolution, ImageModel, ImageLinearFit
+    tests/golden/gradients.npz    central differences of the reference log-likelihood (python ... make_golden.py gradients)
     tests/golden/point_sources.npz  point-source rendering, ImageModel / ImageLinearFit with point sources
                                   (python tests/golden/make_golden.py point_sources  regenerates only this file)
 
@@ -842,8 +843,152 @@ def gen_baseline_shapes():
         st.add("c5_%02d" % s, dict(), outs, dict(kwargs_lens=kl, kwargs_source=ks, kwargs_lens_light=kll5))
     st.save("baseline_shapes.npz")
 
+# ------------------------------------------------------------------------------------------------
+def gen_gradients():
+    """Gradient pins: 4th-order central differences of the UNMODIFIED reference's log-likelihood
+    (ImageModel.likelihood_data_given_model and ImageLinearFit.likelihood_data_given_model under refshim) in every
+    non-linear parameter, at the steps 1e-4, 1e-5, 1e-6 (x max(1, |value|)), for
+      * epl_shear_sersic: EPL + SHEAR, SERSIC_ELLIPSE source and lens light, 40 x 40, ss 2, 9 x 9 pixel PSF;
+      * quad_and_star: the same plus a 4-image LENSED_POSITION point source and an UNLENSED star (the class of the
+        Einstein-ring notebook's L-BFGS model, image_model.py:395-429, point_source_rendering.py:33-77);
+      * multi_plane: BASELINE config 5's lens (EPL z=0.5, NFW_ELLIPSE_CSE z=0.3, SIS z=0.8, source z=1.5) on 32 x 32.
+    jax autodiff itself cannot run here (no jax); the finite difference of the reference's own forward value is the
+    closest pin available, and it is independent of the oracle.  tests/test_gpu_grad.py compares lsim_logl_grad with
+    the closest of the three steps."""
+    from jaxtronomy.PointSource.point_source import PointSource
+
+    st = Store()
+    steps = (1e-4, 1e-5, 1e-6)
+    gk = lambda n, s: gauss_kernel(n, s)  # noqa: E731
+
+    def run_case(case, kd, kern, num_kw, lens, lens_meta, src_names, ll_names, kw0, ps_types, truth_amp, seed, extra_in):
+        rng = np.random.default_rng(seed)
+        src, ll = LightModel(src_names), LightModel(ll_names)
+        psf = PSF(psf_type="PIXEL", kernel_point_source=kern)
+        ps = PointSource(ps_types, lens_model=lens) if ps_types else None
+        n = kd["transform_pix2angle"].shape[0] and int(kd["numPix"])
+        kdd = {k: v for k, v in kd.items() if k != "numPix"}
+        cp = lambda kws: [{k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()} for kw in kws]  # noqa: E731
+        kl, ks, kll, kps = kw0
+        mk = lambda cls, image: cls(ImageData(image_data=image, **kdd), psf, lens, src, ll, point_source_class=ps,  # noqa: E731
+                                    kwargs_numerics=num_kw)
+        ks_t = [dict(k, amp=a) for k, a in zip(ks, truth_amp["source"])]
+        kll_t = [dict(k, amp=a) for k, a in zip(kll, truth_amp["lens_light"])]
+        truth = np.asarray(mk(ImageModel, np.zeros((n, n))).image(cp(kl), ks_t, kll_t, cp(kps) if kps else None))
+        noisy = truth + rng.normal(0, 0.05, truth.shape) + rng.normal(0, 1, truth.shape) * np.sqrt(np.maximum(truth, 0) / 100.0)
+        im, lin = mk(ImageModel, noisy), mk(ImageLinearFit, noisy)
+        # the parameter vector, in the order lens / source / lens_light / point_source; the evaluation point is a few
+        # per cent off the truth so that no gradient component vanishes
+        names, row = [], []
+        for comp, kws in (("lens", kl), ("source", ks_t), ("lens_light", kll_t)):
+            for i, kw in enumerate(kws):
+                for k, v in kw.items():
+                    if comp == "lens" and k in ("ra_0", "dec_0"):
+                        continue
+                    names.append([comp, i, k])
+                    row.append(float(v))
+        for i, kw in enumerate(kps or []):
+            for k in ("ra_image", "dec_image", "point_amp"):
+                for e, v in enumerate(np.atleast_1d(kw[k])):
+                    names.append(["point_source", i, "%s[%d]" % (k, e)])
+                    row.append(float(v))
+        row = np.array(row)
+        for j, (comp, i, k) in enumerate(names):
+            if k in ("theta_E", "gamma", "R_sersic", "n_sersic", "Rs", "alpha_Rs"):
+                row[j] *= 1 + 0.02 * rng.normal()
+            elif k in ("e1", "e2", "gamma1", "gamma2", "center_x", "center_y") or k.startswith(("ra_image", "dec_image")):
+                row[j] += 0.004 * rng.normal()
+
+        def kwargs_of(r):
+            out = {"lens": [dict() for _ in kl], "source": [dict() for _ in ks], "lens_light": [dict() for _ in kll]}
+            for i, kw in enumerate(kl):
+                for k in ("ra_0", "dec_0"):
+                    if k in kw:
+                        out["lens"][i][k] = kw[k]
+            pso = [{k: np.zeros(len(np.atleast_1d(kw[k]))) for k in ("ra_image", "dec_image", "point_amp")} for kw in (kps or [])]
+            for j, (comp, i, k) in enumerate(names):
+                if comp == "point_source":
+                    base, e = k.split("[")
+                    pso[i][base][int(e[:-1])] = r[j]
+                else:
+                    out[comp][i][k] = float(r[j])
+            return out["lens"], out["source"], out["lens_light"], (pso if kps else None)
+
+        f_non = lambda r: float(im.likelihood_data_given_model(*kwargs_of(r)))  # noqa: E731
+        f_lin = lambda r: float(lin.likelihood_data_given_model(*kwargs_of(r))[0])  # noqa: E731
+
+        def fd(fun, j, h):
+            def at(s):
+                r = row.copy()
+                r[j] += s
+                return fun(r)
+            return (8.0 * (at(h) - at(-h)) - (at(2 * h) - at(-2 * h))) / (12.0 * h)
+
+        P = len(row)
+        fd_non, fd_lin = np.full((len(steps), P), np.nan), np.full((len(steps), P), np.nan)
+        for j, (comp, i, k) in enumerate(names):
+            linear_col = k == "amp" or k.startswith("point_amp")
+            for a, h0 in enumerate(steps):
+                h = h0 * max(1.0, abs(row[j]))
+                fd_non[a, j] = fd(f_non, j, h)
+                if not linear_col:
+                    fd_lin[a, j] = fd(f_lin, j, h)
+        ins = dict(image_data=noisy, kernel=kern, row=row, steps=np.array(steps), **kdd, **extra_in)
+        st.add(case, ins, dict(fd_nonlinear=fd_non, fd_linear=fd_lin, logL=f_non(row), logL_linear=f_lin(row)),
+               dict(names=names, lens_meta=lens_meta, source_model_list=src_names, lens_light_model_list=ll_names,
+                    point_source_type_list=ps_types, num_point_source_images=[len(np.atleast_1d(kw["ra_image"])) for kw in (kps or [])],
+                    kwargs_numerics=num_kw, fixed_lens=[{k: kw[k] for k in ("ra_0", "dec_0") if k in kw} for kw in kl]))
+        print(case, "P =", P, "logL", f_non(row), f_lin(row))
+
+    numPix, deltaPix = 40, 0.08
+    kd = sim_util.data_configure_simple(numPix, deltaPix, 100.0, 0.05, inverse=False)
+    kd = dict(numPix=numPix, transform_pix2angle=kd["transform_pix2angle"], ra_at_xy_0=kd["ra_at_xy_0"],
+              dec_at_xy_0=kd["dec_at_xy_0"], exposure_time=100.0, background_rms=0.05)
+    rngk = np.random.default_rng(31)
+    kern = gk(9, 1.4) + 0.02 * rngk.uniform(0, 1, (9, 9)) / 81
+    kl = [dict(theta_E=1.1, gamma=2.0, e1=0.1, e2=-0.05, center_x=0.02, center_y=-0.01),
+          dict(gamma1=0.03, gamma2=-0.01, ra_0=0, dec_0=0)]
+    ks = [dict(amp=12.0, R_sersic=0.2, n_sersic=1.5, e1=0.1, e2=0.05, center_x=0.08, center_y=0.03)]
+    kll = [dict(amp=20.0, R_sersic=0.5, n_sersic=3.0, e1=0.05, e2=0.0, center_x=0.02, center_y=-0.01)]
+    kps = [dict(ra_image=np.array([1.013, -0.734, 0.412, -0.551]), dec_image=np.array([0.402, -0.846, -1.002, 0.978]),
+                point_amp=np.array([30.0, 25.0, 18.0, 12.0])),
+           dict(ra_image=np.array([-1.21]), dec_image=np.array([1.07]), point_amp=np.array([40.0]))]
+    amps = dict(source=[12.0], lens_light=[20.0])
+    num_kw = dict(supersampling_factor=2, point_source_supersampling_factor=1)
+    lens = LensModel(["EPL", "SHEAR"])
+    run_case("epl_shear_sersic", kd, kern, dict(supersampling_factor=2), lens, dict(lens_model_list=["EPL", "SHEAR"]),
+             ["SERSIC_ELLIPSE"], ["SERSIC_ELLIPSE"], (kl, ks, kll, None), [], amps, 41, {})
+    run_case("quad_and_star", kd, kern, num_kw, lens, dict(lens_model_list=["EPL", "SHEAR"]), ["SERSIC_ELLIPSE"],
+             ["SERSIC_ELLIPSE"], (kl, ks, kll, kps), ["LENSED_POSITION", "UNLENSED"], amps, 42, {})
+
+    n, dp = 32, 0.12
+    half = dp * (n - 1) / 2.0
+    kd = dict(numPix=n, transform_pix2angle=np.array([[dp, 0.0], [0.0, dp]]), ra_at_xy_0=-half, dec_at_xy_0=-half,
+              exposure_time=100.0, background_rms=0.05)
+    km = dict(lens_model_list=["EPL", "NFW_ELLIPSE_CSE", "SIS"], lens_redshift_list=[0.5, 0.3, 0.8], z_source=1.5,
+              multi_plane=True)
+    lmm = LensModel(km["lens_model_list"], z_source=km["z_source"], lens_redshift_list=km["lens_redshift_list"],
+                    multi_plane=True)
+    mp = lmm.lens_model
+    base = mp.multi_plane_base
+    consts = dict(sorted_index=np.asarray(base.sorted_redshift_index), T_ij_list=np.asarray(base.T_ij_list, dtype=float),
+                  T_z_list=np.asarray(base.T_z_list, dtype=float),
+                  reduced2physical=np.asarray(base._reduced2physical_factor, dtype=float),
+                  T_ij_stop=float(mp.T_ij_stop), T_z_source=float(mp._T_z_source))
+    kl5 = [dict(theta_E=1.1, gamma=2.0, e1=0.1, e2=-0.1, center_x=0.0, center_y=0.0),
+           dict(Rs=1.5, alpha_Rs=0.2, e1=0.05, e2=0.05, center_x=0.3, center_y=-0.2),
+           dict(theta_E=0.1, center_x=-0.5, center_y=0.4)]
+    ks5 = [dict(amp=15.0, R_sersic=0.3, n_sersic=2.0, e1=0.1, e2=0.1, center_x=0.05, center_y=0.0)]
+    kll5 = [dict(amp=25.0, R_sersic=0.6, n_sersic=3.0, e1=0.05, e2=0.0, center_x=0.0, center_y=0.0)]
+    run_case("multi_plane", kd, gk(11, 1.5), dict(supersampling_factor=2), lmm, km, ["SERSIC_ELLIPSE"], ["SERSIC_ELLIPSE"],
+             (kl5, ks5, kll5, None), [], dict(source=[15.0], lens_light=[25.0]), 43, consts)
+    st.save("gradients.npz")
+
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["gradients"]:
+        gen_gradients()
+        sys.exit(0)
     if sys.argv[1:] == ["baseline_shapes"]:
         gen_baseline_shapes()
         sys.exit(0)
@@ -863,3 +1008,4 @@ if __name__ == "__main__":
     gen_hessians()
     gen_position_likelihood()
     gen_baseline_shapes()
+    gen_gradients()
