@@ -967,6 +967,9 @@ int launch_conv_fft(const FftConv& f, const double* in, double* out, int64_t n_i
   return LSIM_OK;
 }
 
+template <int KT>
+void conv_direct_weights(const ConvSpec& c, ConvWeights<KT>& W);
+
 // weights by value (kernel parameter -> constant bank -> uniform registers)
 template <int KT, int R, int NW>
 int launch_conv_tiled_u(const ConvSpec& c, const double* in, double* out, int64_t n_images, cudaStream_t st) {
@@ -978,13 +981,7 @@ int launch_conv_tiled_u(const ConvSpec& c, const double* in, double* out, int64_
     configured = true;
   }
   ConvWeights<KT> W;  // wT[dx][dy] = kernel flipped (correlation form), zero padded from K to KT
-  const int K = c.K, pad = (KT - K) / 2;
-  for (int a = 0; a < KT; ++a)
-    for (int b = 0; b < KT; ++b) {
-      const int ka = a - pad, kb = b - pad;
-      const bool inside = ka >= 0 && ka < K && kb >= 0 && kb < K;
-      W.w[b * KT + a] = inside ? c.kernel_host[(K - 1 - ka) * K + (K - 1 - kb)] : 0.0;
-    }
+  conv_direct_weights<KT>(c, W);
   const int tiles = ((c.nx + 31) / 32) * ((c.ny + TH - 1) / TH);
   for (int64_t i0 = 0; i0 < n_images; i0 += 65535) {
     const int64_t ni = n_images - i0 < 65535 ? n_images - i0 : 65535;
@@ -999,9 +996,72 @@ int launch_conv_tiled_u(const ConvSpec& c, const double* in, double* out, int64_
 }
 
 template <int KT>
+void conv_direct_weights(const ConvSpec& c, ConvWeights<KT>& W) {
+  const int K = c.K, pad = (KT - K) / 2;
+  for (int a = 0; a < KT; ++a)
+    for (int b = 0; b < KT; ++b) {
+      const int ka = a - pad, kb = b - pad;
+      const bool inside = ka >= 0 && ka < K && kb >= 0 && kb < K;
+      W.w[b * KT + a] = inside ? c.kernel_host[(K - 1 - ka) * K + (K - 1 - kb)] : 0.0;
+    }
+}
+
+// The nine transformed kernels of k_conv_tiled_fxy: the column-direction transform (type b) of the kernel's rows,
+// then the row-direction transform of each resulting kernel column (ka, kb, f1 of lsim_kernels.cuh).
+template <int KT>
+void conv_fxy_weights(const ConvSpec& c, ConvWeightsFXY<KT>& F) {
+  constexpr int M = (KT + 1) / 2, WS = 3 * M - 1;
+  ConvWeights<KT> D;
+  conv_direct_weights<KT>(c, D);
+  auto f = [&](int dy, int dx) { return (dy >= 0 && dy < KT && dx >= 0 && dx < KT) ? D.w[dx * KT + dy] : 0.0; };
+  for (int b = 0; b < 3; ++b)
+    for (int tx = 0; tx < M; ++tx) {
+      auto g = [&](int dy) {  // column tx of the x-transformed kernel
+        if (b == 0) return f(dy, 2 * tx) - f(dy, 2 * tx - 1);
+        if (b == 1) return f(dy, 2 * tx) - f(dy, 2 * tx + 1);
+        return f(dy, 2 * tx + 1);
+      };
+      double* w = F.w + (b * M + tx) * WS;
+      for (int t = 0; t < M; ++t) {
+        w[t] = g(2 * t) - g(2 * t - 1);
+        w[M + t] = g(2 * t) - g(2 * t + 1);
+        if (t < M - 1) w[2 * M + t] = g(2 * t + 1);
+      }
+    }
+}
+
+template <int KT, int R, int NW>
+int launch_conv_tiled_fxy(const ConvSpec& c, const double* in, double* out, int64_t n_images, cudaStream_t st) {
+  constexpr int TH = R * NW, HALO = KT - 1, M = (KT + 1) / 2, PITCH = (32 + M - 1) | 1;
+  constexpr size_t smem = (size_t)2 * (TH + HALO) * PITCH * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    LSIM_CUDA(cudaFuncSetAttribute(k_conv_tiled_fxy<KT, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  ConvWeightsFXY<KT> W;
+  conv_fxy_weights<KT>(c, W);
+  const int tiles = ((c.nx + 63) / 64) * ((c.ny + TH - 1) / TH);
+  for (int64_t i0 = 0; i0 < n_images; i0 += 65535) {
+    const int64_t ni = n_images - i0 < 65535 ? n_images - i0 : 65535;
+    const size_t off = (size_t)i0 * c.nx * c.ny;
+    Timed timed(kClsConv, st);
+    k_conv_tiled_fxy<KT, R, NW><<<dim3((unsigned)tiles, (unsigned)ni), NW * 32, smem, st>>>(
+        in + off, out + off, c.nx, c.ny, c.mode, c.scale, c.accumulate, W);
+    int rc = after_launch("k_conv_tiled_fxy");
+    if (rc != LSIM_OK) return rc;
+  }
+  return LSIM_OK;
+}
+
+template <int KT>
 int launch_conv_tiled_kt(const ConvSpec& c, const double* in, double* out, int64_t n_images, cudaStream_t st) {
-  // pick the tile height (64 = 8 warps x 8 rows, or 60 rows) that wastes fewer rows
+  // pick the tile height (64 or 60 rows) that wastes fewer rows
   const int w64 = ((c.ny + 63) / 64) * 64, w60 = ((c.ny + 59) / 60) * 60;
+  if (!getenv("LSIM_CONV_NO_FF")) {  // the fast-FIR form (default); the direct form stays for A/B and as its check
+    if (w60 < w64) return launch_conv_tiled_fxy<KT, 12, 5>(c, in, out, n_images, st);
+    return launch_conv_tiled_fxy<KT, 16, 4>(c, in, out, n_images, st);
+  }
   // 60-row tiles: 4 warps x 15 rows measured 3 % faster than 6 x 10 for K <= 21 (more register reuse per loaded
   // column); the larger kernels keep 10 rows per warp to stay inside the register budget
   // 60-row tiles: 4 warps x 15 rows for K <= 21, 6 x 10 for the larger kernels (register budget); all shapes

@@ -21,7 +21,11 @@
   LSIM_HOT __global__ void k_conv_tiled_u<KT, 10, 6>(const double*, double*, int, int, int, double, int,                \
                                                       const __grid_constant__ ConvWeights<KT>);                                          \
   LSIM_HOT __global__ void k_conv_tiled_u<KT, 8, 8>(const double*, double*, int, int, int, double, int,                 \
-                                                     const __grid_constant__ ConvWeights<KT>);
+                                                     const __grid_constant__ ConvWeights<KT>);                                           \
+  LSIM_HOT __global__ void k_conv_tiled_fxy<KT, 12, 5>(const double*, double*, int, int, int, double, int,              \
+                                                        const __grid_constant__ ConvWeightsFXY<KT>);                   \
+  LSIM_HOT __global__ void k_conv_tiled_fxy<KT, 16, 4>(const double*, double*, int, int, int, double, int,              \
+                                                        const __grid_constant__ ConvWeightsFXY<KT>);
 
 namespace lsim {
 LSIM_HOT_FOLD(1, 3, 1) LSIM_HOT_FOLD(1, 3, 2) LSIM_HOT_FOLD(2, 3, 2)

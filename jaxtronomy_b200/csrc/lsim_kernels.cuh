@@ -737,6 +737,135 @@ k_conv_tiled_u(const double* __restrict__ in, double* __restrict__ out, int nx, 
   }
 }
 
+// Fast-FIR form of the same direct convolution, 2-parallel in both directions.
+// One direction: with the correlation weights f[d] split into even / odd taps and the input into even / odd samples,
+//   out[n] = sum_d f[d] v[n+d]   becomes, for the output pair (2j, 2j+1),
+//   out[2j]   = sum_t ka[t] v[2(j+t)]   + S[j],   ka[t] = f[2t] - f[2t-1]      ((KT+1)/2 taps)
+//   out[2j+1] = sum_t kb[t] v[2(j+t)+1] + S[j],   kb[t] = f[2t] - f[2t+1]      ((KT+1)/2 taps)
+//   S[j]      = sum_t f[2t+1] (v[2(j+t)+1] + v[2(j+t)+2])                       ((KT-1)/2 taps)
+// -- three half-length products for two outputs instead of four: (3 KT + 1) / 4 = 16 multiply-adds per output for
+// KT = 21 instead of 21, plus one addition per two input values to form the sums.
+// Row direction: applied inside the register column of k_conv_tiled_u's inner product (the loaded column v[] is split
+// in registers; the sums are recomputed per kernel column).  Column direction: the tile is staged as two half-width
+// planes P0[l][j] = in[l][2j], P1[l][j] = in[l][2j+1]; a lane owns the output column pair (2j, 2j+1) and runs three
+// passes of (KT+1)/2, (KT+1)/2, (KT-1)/2 kernel columns --
+//   both columns: f1_x on P1[j] + P0[j+1] (summed while loading),  odd columns: kb_x on P1,  even columns: ka_x on P0
+// -- nine transformed kernels in all (host: conv_fxy_weights, once per launch).  ((3 KT + 1) / 4)^2 = 256
+// multiply-adds per output pixel for KT = 21 instead of 441, ~290 fp64 instructions with the additions.
+// Same operand pattern as k_conv_tiled_u (value in the reuse cache x uniform-register weight + accumulator), 6
+// multiply-adds per shared-memory load.  Accumulators: the shared product is folded into the other passes' start
+// values, at most 5 (R/2) live.
+// Rounding: ka, kb cancel against S term by term, so an output carries a few ulp of the local image scale instead of
+// ~1 -- far inside the 1e-10 parity bar, not bit-identical to k_conv_tiled_u (LSIM_CONV_NO_FF=1 selects that one;
+// tests/test_gpu_parity.py compares the two).
+// Measured (1184 images 180 x 180, K = 21): 0.84 ms at 80 % of the fp64 pipe, k_conv_tiled_u 1.19 ms at 85 %.
+// Variants measured and dropped (profiles/r2_conv_fastfir.md): all nine products on quarter-resolution planes in shared
+// memory (11 x 11 sub-kernels leave 4 multiply-adds per shared-memory load: shared-memory bound, 1.59 ms); the row
+// split alone (1.02 ms); the sum plane built in shared memory between two barriers (0.90 ms).
+template <int KT>
+struct ConvWeightsFXY {
+  static constexpr int M = (KT + 1) / 2, WS = 3 * M - 1;
+  double w[3 * M * WS];  // [x type b: 0 ka, 1 kb, 2 f1][kernel column tx][row weights ka[M], kb[M], f1[M-1]]
+};
+
+template <int KT, int R, int B, int PITCH, int PLANE>
+__device__ __forceinline__ void conv_fxy_pass(const double* __restrict__ tcol, const ConvWeightsFXY<KT>& W,
+                                              double (&ae)[R / 2], double (&ao)[R / 2], double (&sh)[R / 2]) {
+  constexpr int M = (KT + 1) / 2, H = R / 2, WS = 3 * M - 1, NTX = (B == 2) ? M - 1 : M;
+#pragma unroll 1
+  for (int tx = 0; tx < NTX; ++tx) {
+    double v[R + KT - 1];
+#pragma unroll
+    for (int i = 0; i < R + KT - 1; ++i)
+      v[i] = (B == 2) ? tcol[PLANE + i * PITCH + tx] + tcol[i * PITCH + tx + 1] : tcol[(B == 1 ? PLANE : 0) + i * PITCH + tx];
+    double ps[H + M - 2];
+#pragma unroll
+    for (int i = 0; i < H + M - 2; ++i) ps[i] = v[2 * i + 1] + v[2 * i + 2];
+    const int wb0 = (B * M + tx) * WS;
+#pragma unroll
+    for (int t = 0; t < M; ++t) {
+      const double wa = W.w[wb0 + t], wb = W.w[wb0 + M + t];
+#pragma unroll
+      for (int j = 0; j < H; ++j) ae[j] = fma(wa, v[2 * (j + t)], ae[j]);
+#pragma unroll
+      for (int j = 0; j < H; ++j) ao[j] = fma(wb, v[2 * (j + t) + 1], ao[j]);
+      if (t < M - 1) {
+        const double ws = W.w[wb0 + 2 * M + t];
+#pragma unroll
+        for (int j = 0; j < H; ++j) sh[j] = fma(ws, ps[j + t], sh[j]);
+      }
+    }
+  }
+}
+
+template <int KT, int R, int NW>
+__global__ void __launch_bounds__(NW * 32, 2)
+k_conv_tiled_fxy(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int mode, double scale,
+                 int accumulate, const __grid_constant__ ConvWeightsFXY<KT> W) {
+  static_assert(R % 2 == 0 && KT % 2 == 1, "row pairs, odd kernel");
+  constexpr int NT = NW * 32, TH = R * NW, HALO = KT - 1, M = (KT + 1) / 2, H = R / 2, PCQ = 32 + M - 1, PITCH = PCQ | 1,
+                ROWS = TH + HALO, PLANE = ROWS * PITCH, rT = HALO / 2;
+  extern __shared__ double smem[];  // P0 [ROWS][PITCH], P1 [ROWS][PITCH]
+  const int tiles_x = (nx + 63) / 64;
+  const int tx0 = (blockIdx.x % tiles_x) * 64, ty0 = (blockIdx.x / tiles_x) * TH;
+  const double* img = in + (int64_t)blockIdx.y * nx * ny;
+  // U loads in flight per thread (one load per round trip left this phase at 16 % of the stall samples)
+  constexpr int U = 8;
+  for (int base = threadIdx.x; base < ROWS * 2 * PCQ; base += NT * U) {
+    double t[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NT, ly = i / (2 * PCQ), lx = i - ly * (2 * PCQ);
+      t[u] = i < ROWS * 2 * PCQ ? conv_fetch(img, nx, ny, tx0 + lx - rT, ty0 + ly - rT, mode) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NT, ly = i / (2 * PCQ), lx = i - ly * (2 * PCQ);
+      if (i < ROWS * 2 * PCQ) smem[(lx & 1) * PLANE + ly * PITCH + (lx >> 1)] = t[u];
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* tcol = smem + (warp * R) * PITCH + lane;
+  double* dst = out + (int64_t)blockIdx.y * nx * ny;
+  const int x = tx0 + 2 * lane;
+  auto store = [&](int beta, const double (&ae)[H], const double (&ao)[H], const double (&sh)[H]) {
+#pragma unroll
+    for (int o = 0; o < R; ++o) {
+      const int y = ty0 + warp * R + o;
+      const double acc = ((o & 1) ? ao[o / 2] : ae[o / 2]) + sh[o / 2];
+      if (x + beta < nx && y < ny) {
+        double* d = dst + (int64_t)y * nx + x + beta;
+        *d = accumulate ? fma(acc, scale, *d) : acc * scale;
+      }
+    }
+  };
+  // the product shared by both columns (its input P1[j] + P0[j+1] is formed while loading: a sum plane in shared
+  // memory cost two barriers and occupancy, measured slower), folded over the row split: te / to = what the even /
+  // odd rows of both columns start from
+  double te[H], to[H], ts[H];
+#pragma unroll
+  for (int j = 0; j < H; ++j) te[j] = to[j] = ts[j] = 0.0;
+  conv_fxy_pass<KT, R, 2, PITCH, PLANE>(tcol, W, te, to, ts);
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    te[j] += ts[j];
+    to[j] += ts[j];
+  }
+  {  // odd columns
+    double be[H], bo[H], bs[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) be[j] = te[j], bo[j] = to[j], bs[j] = 0.0;
+    conv_fxy_pass<KT, R, 1, PITCH, PLANE>(tcol, W, be, bo, bs);
+    store(1, be, bo, bs);
+  }
+  // even columns
+#pragma unroll
+  for (int j = 0; j < H; ++j) ts[j] = 0.0;
+  conv_fxy_pass<KT, R, 0, PITCH, PLANE>(tcol, W, te, to, ts);
+  store(0, te, to, ts);
+}
+
 // Separable variant (kernel == outer(k1, k1), e.g. the Gaussian PSF): row pass into shared memory, column pass out.
 static __global__ void __launch_bounds__(kBlock)
 k_conv_separable(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, int K,

@@ -230,6 +230,51 @@ def test_numerics_re_size_convolve(name):
     assert_close(out[1], 2 * c.out["image"], what=name + " batched", **BAR)
 
 
+@pytest.mark.parametrize("K,n,ss", [(21, 180, 1), (21, 97, 1), (7, 33, 1), (7, 40, 3), (11, 64, 1), (15, 61, 1), (25, 130, 1), (31, 70, 1)])
+def test_fast_fir_convolution_matches_the_direct_one(K, n, ss, monkeypatch):
+    """k_conv_tiled_fxy (the default) against k_conv_tiled_u (LSIM_CONV_NO_FF=1) and against the oracle's direct sum
+    on random non-negative images with a non-symmetric kernel: every kernel-size template, odd / even frame sizes,
+    partial tiles, and the supersampled-convolution path (accumulate mode).  The two kernels order their additions
+    differently (lsim_kernels.cuh): 1e-13 of the image peak; the oracle bar is the usual 1e-10."""
+    from jaxtronomy_b200.Data.pixel_grid import PixelGrid
+    from jaxtronomy_b200.Data.psf import PSF
+    from jaxtronomy_b200.ImSim.Numerics.numerics import Numerics
+    from oracle import imsim as oimsim
+    from oracle.lenstronomy_port import PSF as OPSF, PixelGrid as OPixelGrid
+
+    rng = np.random.default_rng(K * 1000 + n)
+    kern = rng.uniform(0.0, 1.0, (K, K)) * np.exp(-((np.arange(K) - K // 2) ** 2)[:, None] / (0.1 * K * K)
+                                                   - ((np.arange(K) - K // 2) ** 2)[None, :] / (0.07 * K * K))
+    if ss > 1:  # the supersampled kernel must have an odd size after degrading
+        kern = rng.uniform(0.0, 1.0, (K * ss if (K * ss) % 2 else K * ss + 1,) * 2)
+    M = np.array([[0.05, 0.0], [0.0, 0.05]])
+    kw_num = dict(supersampling_factor=ss, supersampling_convolution=ss > 1)
+    kw_psf = dict(psf_type="PIXEL", kernel_point_source=kern, point_source_supersampling_factor=ss)
+
+    def run():
+        pg = PixelGrid(n, n, M, -1.0, -1.0)
+        psf = PSF(**kw_psf)
+        psf.set_pixel_size(pg.pixel_width)
+        num = Numerics(pg, psf, **kw_num)
+        flux = rng2.uniform(0.0, 1.0, (3, n * ss * n * ss)) ** 3
+        return flux, np.asarray(num.re_size_convolve(flux))
+
+    rng2 = np.random.default_rng(5)
+    flux, fast = run()
+    monkeypatch.setenv("LSIM_CONV_NO_FF", "1")
+    rng2 = np.random.default_rng(5)
+    _, direct = run()
+    monkeypatch.delenv("LSIM_CONV_NO_FF")
+    assert np.abs(fast - direct).max() <= 1e-13 * np.abs(direct).max()
+    # the fast path really is another kernel (K >= 27 goes through cuFFT whatever the switch says)
+    assert not np.array_equal(fast, direct) or K >= 27
+    opg = OPixelGrid(n, n, M, -1.0, -1.0)
+    opsf = OPSF(**kw_psf)
+    opsf.set_pixel_size(opg.pixel_width)
+    onum = oimsim.Numerics(opg, opsf, **kw_num)
+    assert_close(fast[1], onum.re_size_convolve(flux[1]), what="fast FIR vs oracle", **BAR)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # ImageModel / ImageLinearFit against the reference fixtures
 # ---------------------------------------------------------------------------------------------------------------

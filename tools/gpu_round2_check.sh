@@ -1,7 +1,7 @@
 # Round-2 GPU check: parity tests, smoke, bench line (with secondary configs), ncu captures of the headline kernels.
 #   gpurun -- 'bash tools/gpu_round2_check.sh <tag> [ncu kernels]'
 TAG=${1:-r2}
-KERNELS=${2:-"k_image k_conv_tiled_u k_likelihood"}
+KERNELS=${2:-"k_image k_conv_tiled k_likelihood"}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 python -m pytest tests -m gpu -q -x > gpurun_out/${TAG}_pytest.log 2>&1; tail -4 gpurun_out/${TAG}_pytest.log

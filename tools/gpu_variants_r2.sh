@@ -1,11 +1,16 @@
-# A/B of the specialised k_ray_shoot (LSIM_NO_SPECIALISE=1 runs the interpreted instantiation) on C2 / C4 + parity
+# A/B of the fast-FIR convolutions against the direct one (LSIM_CONV_NO_FF=1): shapes 0-2 row split, 3-4 both directions
 mkdir -p gpurun_out
 {
-for v in 0 1; do
-  echo "== LSIM_NO_SPECIALISE=$v"
-  if [ $v = 1 ]; then export LSIM_NO_SPECIALISE=1; else unset LSIM_NO_SPECIALISE; fi
-  python tools/bench_configs.py c2 c4 2>&1 | grep config | cut -c1-200
+LSIM_FF_SHAPE=3 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+for v in noff 3 4; do
+  echo "== shape $v"
+  unset LSIM_CONV_NO_FF LSIM_FF_SHAPE
+  if [ $v = noff ]; then export LSIM_CONV_NO_FF=1; else export LSIM_FF_SHAPE=$v; fi
+  python bench.py --steps 10 --warmup 3 --no-cpu --no-secondary 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])"
 done
-unset LSIM_NO_SPECIALISE
-python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-} 2>&1 | tee gpurun_out/r2_variants6.txt
+export LSIM_FF_SHAPE=3
+bash tools/ncu_profile.sh r2w k_conv_tiled_fxy > /dev/null 2>&1
+head -60 gpurun_out/k_conv_tiled_fxy_r2w_summary.txt
+} 2>&1 | tee gpurun_out/r2_variants8.txt
