@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/lsim.h"
@@ -186,9 +187,28 @@ int upload_tables() {
   return LSIM_OK;
 }
 
-constexpr size_t kRaySmem = kLensChunk * sizeof(LensC) + (size_t)kMaxSeriesProfiles * kMaxSeries * sizeof(double);
+// Opt a kernel in to its dynamic shared memory.  Every kernel that evaluates profiles carries the 32 KB log2 / exp2
+// tables as STATIC shared memory, and static + dynamic above 48 KB needs the opt-in: done once per kernel and size.
+template <class K>
+int ensure_dyn_smem(K kernel, size_t bytes) {
+  static std::mutex m;
+  static std::unordered_map<const void*, size_t> have;
+  if (bytes <= 8 * 1024) return LSIM_OK;  // no kernel has more than 40 KB of static shared memory
+  std::lock_guard<std::mutex> g(m);
+  size_t& h = have[reinterpret_cast<const void*>(kernel)];
+  if (h >= bytes) return LSIM_OK;
+  LSIM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  h = bytes;
+  return LSIM_OK;
+}
+#define LSIM_SMEM(kernel, bytes)                          \
+  do {                                                    \
+    const int rc_smem_ = ensure_dyn_smem((kernel), (bytes)); \
+    if (rc_smem_ != LSIM_OK) return rc_smem_;             \
+  } while (0)
+
 constexpr size_t kConvSmemMax = 200 * 1024;
-constexpr size_t kGradSmemMax = 200 * 1024;
+constexpr size_t kGradSmemMax = 188 * 1024;  // + 34 KB static (math tables) <= 227 KB
 
 int configure_kernels() {
   LSIM_CUDA(cudaFuncSetAttribute(k_conv_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemMax));
@@ -549,6 +569,14 @@ int lsim_ray_shoot(const lsim_plan* plan, const double* params, int64_t B, const
     rpc = bpc * batch;
   }
   dim3 grid((unsigned)((N + rpc - 1) / rpc), (unsigned)B);
+  // one chunk of profiles + the coefficient pools of its series-bearing ones (sized per plan: three CTAs per SM for
+  // the two-profile headline lens, which the 77 KB of a full chunk + the math tables would not allow)
+  const size_t kRaySmem = (size_t)(plan->dev.n_lens < kLensChunk ? plan->dev.n_lens : kLensChunk) * sizeof(LensC) +
+                          (size_t)(plan->n_series < kMaxSeriesProfiles ? plan->n_series : kMaxSeriesProfiles) *
+                              kMaxSeries * sizeof(double);
+  LSIM_SMEM((k_ray_shoot<false, TypeList<LSIM_LENS_EPL, LSIM_LENS_SHEAR>>), kRaySmem);
+  LSIM_SMEM(k_ray_shoot<true>, kRaySmem);
+  LSIM_SMEM(k_ray_shoot<false>, kRaySmem);
   if (plan->ray_epl_shear)
     k_ray_shoot<false, TypeList<LSIM_LENS_EPL, LSIM_LENS_SHEAR>><<<grid, kBlock, kRaySmem, st>>>(
         plan->dev, params, x, y, N, coords_batched, out_x, out_y, what, rpc);
@@ -650,6 +678,7 @@ template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = Runt
 int launch_image_k(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
                    double scale, double* out, double* sub_out, cudaStream_t st, const unsigned char* prep) {
   dim3 grid((unsigned)tiles, (unsigned)n);
+  LSIM_SMEM((k_image<NSLOT, FULL, SS, LT, GT>), plan->image_smem);
   Timed timed(kClsImage, st);
   k_image<NSLOT, FULL, SS, LT, GT><<<grid, kImageBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale,
                                                                                 out, sub_out, prep, plan->n_series);
@@ -725,18 +754,26 @@ int launch_image_ns(const lsim_plan* plan, const double* params, int64_t set0, i
     Timed timed(kClsImage, st);
     const bool masked = plan->dev.eval_list != nullptr;
 #define LSIM_SUB_LAUNCH(FULLV, MASKV)                                                                          \
+  LSIM_SMEM((k_image<NSLOT, FULLV, 0, RuntimeTypes, RuntimeTypes, true, MASKV>), plan->image_smem);            \
   k_image<NSLOT, FULLV, 0, RuntimeTypes, RuntimeTypes, true, MASKV><<<grid, kImageBlock, plan->image_smem, st>>>( \
       plan->dev, params, set0, ppt, scale, out, sub_out, prep, plan->n_series)
-    if (plan->full && masked) LSIM_SUB_LAUNCH(true, true);
-    else if (plan->full) LSIM_SUB_LAUNCH(true, false);
-    else if (masked) LSIM_SUB_LAUNCH(false, true);
-    else LSIM_SUB_LAUNCH(false, false);
+    if (plan->full && masked) {
+      LSIM_SUB_LAUNCH(true, true);
+    } else if (plan->full) {
+      LSIM_SUB_LAUNCH(true, false);
+    } else if (masked) {
+      LSIM_SUB_LAUNCH(false, true);
+    } else {
+      LSIM_SUB_LAUNCH(false, false);
+    }
 #undef LSIM_SUB_LAUNCH
     return after_launch("k_image");
   }
   if (plan->dev.eval_list) {  // masked evaluation: interpreted kernel, runtime supersampling factor
     dim3 grid((unsigned)tiles, (unsigned)n);
     Timed timed(kClsImage, st);
+    LSIM_SMEM((k_image<NSLOT, true, 0, RuntimeTypes, RuntimeTypes, false, true>), plan->image_smem);
+    LSIM_SMEM((k_image<NSLOT, false, 0, RuntimeTypes, RuntimeTypes, false, true>), plan->image_smem);
     if (plan->full)
       k_image<NSLOT, true, 0, RuntimeTypes, RuntimeTypes, false, true><<<grid, kImageBlock, plan->image_smem, st>>>(
           plan->dev, params, set0, ppt, scale, out, sub_out, prep, plan->n_series);
@@ -761,13 +798,14 @@ int launch_image_f32_ns(const lsim_plan* plan, const double* params, int64_t set
   dim3 grid((unsigned)tiles, (unsigned)n);
   Timed timed(kClsImage, st);
 #define LSIM_F32_LAUNCH(SSV)                                                                                   \
+  LSIM_SMEM((k_image_f32<NSLOT, SSV>), plan->image_smem);                                                      \
   k_image_f32<NSLOT, SSV><<<grid, kImageBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, \
                                                                         plan->n_series, out, prep)
   switch (plan->dev.ss) {
-    case 1: LSIM_F32_LAUNCH(1); break;
-    case 2: LSIM_F32_LAUNCH(2); break;
-    case 3: LSIM_F32_LAUNCH(3); break;
-    default: LSIM_F32_LAUNCH(0); break;
+    case 1: { LSIM_F32_LAUNCH(1); break; }
+    case 2: { LSIM_F32_LAUNCH(2); break; }
+    case 3: { LSIM_F32_LAUNCH(3); break; }
+    default: { LSIM_F32_LAUNCH(0); break; }
   }
 #undef LSIM_F32_LAUNCH
   return after_launch("k_image_f32");
@@ -827,6 +865,7 @@ int launch_image(const lsim_plan* plan, const double* params, int64_t set0, int6
     Timed timed(kClsImage, st);
 #define LSIM_FOLD_CASE(NSV, SSV, NLV)                                                                               \
   if (ns == NSV && ss == SSV && nl == NLV) {                                                                        \
+    LSIM_SMEM((k_image_fold<NSV, SSV, NLV>), plan->image_smem);                                                      \
     k_image_fold<NSV, SSV, NLV><<<grid, kImageBlock, plan->image_smem, st>>>(plan->dev, params, set0, ppt, scale, out, \
                                                                              prep, plan->n_series);                 \
     return after_launch("k_image_fold");                                                                            \

@@ -211,9 +211,9 @@ k_image_f32(PlanDev P, const double* __restrict__ params, int64_t set0, int ppt,
     Gf[i].lensed = G[i].lensed;
     Gf[i].slot = G[i].slot;
     for (int k = 0; k < 12; ++k) {
-      // light_prepare stores the Sersic exponent constants c[5..8] pre-scaled by 256 (exp2_*_s of the fp64 kernels)
+      // light_prepare stores the Sersic exponent constants c[5..8] pre-scaled by kExp2Scale (exp2_*_s of the fp64 kernels)
       const bool scaled = G[i].type == LSIM_LIGHT_SERSIC_ELLIPSE && k >= 5 && k <= 8;
-      Gf[i].c[k] = (float)(scaled ? G[i].c[k] * 0.00390625 : G[i].c[k]);
+      Gf[i].c[k] = (float)(scaled ? G[i].c[k] * (1.0 / kExp2Scale) : G[i].c[k]);
     }
   }
   for (int i = threadIdx.x; i < n_series * kMaxSeries; i += kImageBlock) poolf[i] = (float)pool[i];

@@ -172,7 +172,7 @@ k_ray_shoot(PlanDev P, const double* __restrict__ params, const double* __restri
             int64_t N, int coords_batched, double* __restrict__ ox, double* __restrict__ oy, int what, int64_t rpc) {
   extern __shared__ double smem[];
   LensC* L = reinterpret_cast<LensC*>(smem);
-  double* pool = reinterpret_cast<double*>(L + kLensChunk);
+  double* pool = reinterpret_cast<double*>(L + min(P.n_lens, kLensChunk));  // the host sizes the launch the same way
   const int64_t b = blockIdx.y;
   const double* row = params + b * P.n_param_cols;
   const double* xb = coords_batched ? x + b * N : x;

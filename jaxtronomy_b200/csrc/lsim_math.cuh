@@ -36,12 +36,17 @@ constexpr double kPi = 3.14159265358979323846;
 constexpr double kLog2e = 1.44269504088896340736;
 constexpr double kLn2 = 0.69314718055994530942;
 
-// log2(1+u)/u = (1/ln2) (1 - u/2 + u^2/3 - ...): coefficients (-1)^(k+1)/(k ln2), k = 6..1, highest first
-LSIM_TABLE kLog2C[6] = {-kLog2e / 6.0, kLog2e / 5.0, -kLog2e / 4.0, kLog2e / 3.0, -kLog2e / 2.0, kLog2e};
+// exp2_*_s take their argument pre-scaled by the exp2 table size
+constexpr double kExp2Scale = (double)LSIM_EXP2_N;
 
-// Lookup tables (tools/gen_math_tables.py): exp2 T[j] = 2^(j/256) (stored as bit patterns with j << 12 subtracted
-// from the high word, see exp2_core_s); log2 {R[i], L[i]} = {~1/c_i, -log2 R[i]} for the 128 bins of the mantissa
-// (2 KB each).  The index differs from lane to lane, which constant memory would serialise, so every kernel that
+// log2(1+u)/u = (1/ln2) (1 - u/2 + u^2/3 - ...): coefficients (-1)^(k+1)/(k ln2), k = 4..1, highest first
+// (|u| <= 2^-11 with 1024 bins: the first dropped term is u^5/(5 ln2) <= 8e-18)
+LSIM_TABLE kLog2C[4] = {-kLog2e / 4.0, kLog2e / 3.0, -kLog2e / 2.0, kLog2e};
+
+// Lookup tables (tools/gen_math_tables.py): exp2 T[j] = 2^(j/2048) (stored as bit patterns with j << 9 subtracted
+// from the high word, see exp2_core_s); log2 {R[i], L[i]} = {~1/c_i, -log2 R[i]} for the 1024 bins of the mantissa
+// (16 KB each: round 2 traded table size for polynomial length -- two multiply-adds less per log2, one less per
+// exp2, 7 of the ~107 fp64 instructions of a headline sub-pixel).  The index differs from lane to lane, which constant memory would serialise, so every kernel that
 // evaluates profiles copies the tables from global into SHARED memory once per CTA (stage_math_tables): a lookup is
 // then one LDS at a 32-bit offset (no 64-bit address arithmetic, lower latency than an L1 hit).
 #if defined(__CUDACC__)
@@ -66,21 +71,18 @@ static const double h_log2_tab[2 * LSIM_LOG2_N] = LSIM_LOG2_TABLE;
 // the compiler does with __constant__ data it uses more than once) reads three and takes 3 cycles instead of 2
 // (profiles/r1_dfma_operand_probe.md).
 struct MathK {
-  double l[6];  // kLog2C
-  double e[4];  // kExp2S
+  double l[4];  // kLog2C
+  double e[3];  // kExp2S
 };
 LSIM_HD MathK math_k() {
   MathK k;
-  k.l[0] = -kLog2e / 6.0;
-  k.l[1] = kLog2e / 5.0;
-  k.l[2] = -kLog2e / 4.0;
-  k.l[3] = kLog2e / 3.0;
-  k.l[4] = -kLog2e / 2.0;
-  k.l[5] = kLog2e;
-  k.e[0] = kLn2 * kLn2 * kLn2 * kLn2 / 24.0 / 4294967296.0;
-  k.e[1] = kLn2 * kLn2 * kLn2 / 6.0 / 16777216.0;
-  k.e[2] = kLn2 * kLn2 / 2.0 / 65536.0;
-  k.e[3] = kLn2 / 256.0;
+  k.l[0] = -kLog2e / 4.0;
+  k.l[1] = kLog2e / 3.0;
+  k.l[2] = -kLog2e / 2.0;
+  k.l[3] = kLog2e;
+  k.e[0] = kLn2 * kLn2 * kLn2 / 6.0 / (kExp2Scale * kExp2Scale * kExp2Scale);
+  k.e[1] = kLn2 * kLn2 / 2.0 / (kExp2Scale * kExp2Scale);
+  k.e[2] = kLn2 / kExp2Scale;
   return k;
 }
 
@@ -181,14 +183,14 @@ LSIM_HD double rsqrt_fast3(double x) {
 // libdevice's log/exp/pow carry special-case branches and long polynomials; on a kernel bound by the fp64 pipe
 // every DFMA counts and every branch cuts the instruction stream into blocks the scheduler cannot interleave,
 // so both functions are table-driven and BRANCH-FREE here:
-//   log2_pos(x): x positive, finite, normal.  8 fp64 instructions.  |abs err| < 3e-16 max(1, |log2 x|)
+//   log2_pos(x): x positive, finite, normal.  6 fp64 instructions.  |abs err| < 3e-16 max(1, |log2 x|)
 //                (the result feeds exponents, where absolute accuracy is what matters).
-//   exp2_fin(x): any x; 7 fp64 instructions (6 for a pre-scaled argument, exp2_fin_s); |rel err| < 4e-16.  Results
+//   exp2_fin(x): any x; 6 fp64 instructions (5 for a pre-scaled argument, exp2_fin_s); |rel err| < 4e-16.  Results
 //                saturate at 2^-1022 (2.2e-308, instead of denormals / 0) and 2^1023 (instead of +inf) through one
 //                integer clamp of the table index; nan propagates, +-inf gives nan.
 //   exp2_neg(x): kept as a name for call sites whose argument is bounded above; the same function.
 
-// x = 2^e m, m in [1,2); bin i = top 7 mantissa bits; u = m R_i - 1, |u| <= 1/256;
+// x = 2^e m, m in [1,2); bin i = top 10 mantissa bits; u = m R_i - 1, |u| <= 2^-11;
 // log2 x = e + L_i + log2(1 + u)
 template <class CoefT>
 LSIM_HD double log2_pos_c(double x, const CoefT& C) {
@@ -197,35 +199,35 @@ LSIM_HD double log2_pos_c(double x, const CoefT& C) {
   const int e = (int)(hx >> 20) - 1023;
   const double m = i2d((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
 #if defined(__CUDA_ARCH__)
-  // byte offset of the bin's {R, L} pair: (top 7 mantissa bits) * 16 in one shift and one mask
-  const double2 rl = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(s_log2_tab) + ((hx >> 9) & 0x7f0u));
+  // byte offset of the bin's {R, L} pair: (top LSIM_LOG2_BITS mantissa bits) * 16 in one shift and one mask
+  const double2 rl = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(s_log2_tab) +
+                                                       ((hx >> (16 - LSIM_LOG2_BITS)) & ((LSIM_LOG2_N - 1) << 4)));
   const double R = rl.x, L = rl.y;
 #else
-  const int i = (int)(hx >> 13) & (LSIM_LOG2_N - 1);
+  const int i = (int)(hx >> (20 - LSIM_LOG2_BITS)) & (LSIM_LOG2_N - 1);
   const double R = h_log2_tab[2 * i], L = h_log2_tab[2 * i + 1];
 #endif
   const double u = fma(m, R, -1.0);
   double p = fma(C[0], u, C[1]);
   p = fma(p, u, C[2]);
   p = fma(p, u, C[3]);
-  p = fma(p, u, C[4]);
-  p = fma(p, u, C[5]);
   return (double)e + fma(u, p, L);
 }
 LSIM_HD double log2_pos(double x) { return log2_pos_c(x, kLog2C); }
 LSIM_HD double log2_pos(double x, const MathK& K) { return log2_pos_c(x, K.l); }
 
 // ---- exp2 ------------------------------------------------------------------------------------------------------------
-// Core, for a PRE-SCALED argument y = 256 x (the hot profiles compute their exponents with one FMA from prepared
-// constants, which carry the factor 256): k = rint(y), r = y - k (exact), k clamped to [-1022*256, 1022*256 + 255] with
-// ONE integer min/max, j = k & 255, E = k >> 8:
+// Core, for a PRE-SCALED argument y = N x, N = LSIM_EXP2_N = 2048 = kExp2Scale (the hot profiles compute their exponents
+// with one FMA from prepared constants, which carry the factor N): k = rint(y), r = y - k (exact), k clamped to
+// [-1022 N, 1022 N + N - 1] with ONE integer min/max, j = k & (N - 1), E = k >> 11:
 //   2^x = (2^E T[j]) (1 + r P(r)),
 // where 2^E T[j] costs one integer multiply-add on the high word of the table entry (the table stores T[j] with
-// j << 12 subtracted from its high word, so hi + (k << 12) = hi(T[j]) + (E << 20)).  P's coefficients are those of
-// (2^r - 1)/r scaled by powers of 256 (exact).  6 fp64 instructions; the result saturates at 2^-1022 / 2^1023 for finite
-// arguments out of range (the reduced argument stays |r| <= 1/2 whatever the clamp does), nan and +-inf give nan.
-LSIM_TABLE kExp2S[4] = {kLn2 * kLn2 * kLn2 * kLn2 / 24.0 / 4294967296.0, kLn2 * kLn2 * kLn2 / 6.0 / 16777216.0,
-                        kLn2 * kLn2 / 2.0 / 65536.0, kLn2 / 256.0};
+// j << 9 subtracted from its high word, so hi + (k << 9) = hi(T[j]) + (E << 20)).  P's coefficients are those of
+// (2^r - 1)/r through r^2, scaled by powers of N (exact); |r|/N <= 2^-12, so the first dropped term is
+// (ln2 2^-12)^4 / 24 = 3.4e-17.  5 fp64 instructions; the result saturates at 2^-1022 / 2^1023 for finite arguments out of
+// range (the reduced argument stays |r| <= 1/2 whatever the clamp does), nan and +-inf give nan.
+LSIM_TABLE kExp2S[3] = {kLn2 * kLn2 * kLn2 / 6.0 / (kExp2Scale * kExp2Scale * kExp2Scale),
+                        kLn2 * kLn2 / 2.0 / (kExp2Scale * kExp2Scale), kLn2 / kExp2Scale};
 
 template <class CoefT>
 LSIM_HD double exp2_core_s(double y, const CoefT& C) {
@@ -241,16 +243,16 @@ LSIM_HD double exp2_core_s(double y, const CoefT& C) {
   if (kf < -2e9) ki = -2000000000;
 #endif
   const double r = y - kf;  // exact: |r| <= 1/2 and both are multiples of ulp(y)
-  ki = ki < -261632 ? -261632 : (ki > 261887 ? 261887 : ki);
+  constexpr int kLo = -1022 * LSIM_EXP2_N, kHi = 1022 * LSIM_EXP2_N + LSIM_EXP2_N - 1;
+  ki = ki < kLo ? kLo : (ki > kHi ? kHi : ki);
   double p = fma(C[0], r, C[1]);
   p = fma(p, r, C[2]);
-  p = fma(p, r, C[3]);
 #if defined(__CUDA_ARCH__)
   const unsigned long long tb = s_exp2_tab[ki & (LSIM_EXP2_N - 1)];
-  const double T = __hiloint2double((int)((uint32_t)(tb >> 32) + ((uint32_t)ki << 12)), (int)(uint32_t)tb);
+  const double T = __hiloint2double((int)((uint32_t)(tb >> 32) + ((uint32_t)ki << (20 - LSIM_EXP2_BITS))), (int)(uint32_t)tb);
 #else
   const unsigned long long tb = h_exp2_tab[ki & (LSIM_EXP2_N - 1)];
-  const double T = i2d((int64_t)(tb + ((unsigned long long)((uint32_t)ki << 12) << 32)));
+  const double T = i2d((int64_t)(tb + ((unsigned long long)((uint32_t)ki << (20 - LSIM_EXP2_BITS)) << 32)));
 #endif
   return fma(T * r, p, T);
 }
@@ -263,7 +265,7 @@ struct TableK {};
 LSIM_HD double log2_pos(double x, const TableK&) { return log2_pos_c(x, kLog2C); }
 LSIM_HD double exp2_fin_s(double y, const TableK&) { return exp2_core_s(y, kExp2S); }
 // unscaled arguments (everything off the hot path)
-LSIM_HD double exp2_fin(double x) { return exp2_core_s(x * 256.0, kExp2S); }
-LSIM_HD double exp2_neg(double x) { return exp2_core_s(x * 256.0, kExp2S); }
+LSIM_HD double exp2_fin(double x) { return exp2_core_s(x * kExp2Scale, kExp2S); }
+LSIM_HD double exp2_neg(double x) { return exp2_core_s(x * kExp2Scale, kExp2S); }
 
 }  // namespace lsim

@@ -144,8 +144,8 @@ LSIM_HD void epl_prepare(LensC& L, double* coef, double theta_E, double gamma, d
   L.c[24] = (4.0 - f * f) / (4.0 * fe);
   L.c[25] = -0.25 * fe;
   L.c[26] = (2.0 - f) / (2.0 + f);
-  L.c[27] = 256.0 * L.c[6];
-  L.c[28] = 256.0 * (L.c[7] + log2((2.0 + f) / (fe * (1.0 + q))));
+  L.c[27] = kExp2Scale * L.c[6];
+  L.c[28] = kExp2Scale * (L.c[7] + log2((2.0 + f) / (fe * (1.0 + q))));
   int nmax = epl_nmax(f);
   double B = t / 2.0, C = 2.0 - B;
   coef[0] = 1.0;
@@ -999,7 +999,7 @@ LSIM_HD void ray_finish(const RayCfg& P, const Rays<J>& r, int j, double& bx, do
 
 // ---- light -----------------------------------------------------------------------------------------------
 // c[0..1] centre; SERSIC family: c[2..4] = product-average transform rows / norm, c[5] = 1/(2n),
-// c[6] = -log2(Rs_)/n, c[7] = -bn log2(e), c[8] = bn log2(e) (c[5..8] times 256: exp2_*_s), c[9] = (max_R_frac Rs_)^2,
+// c[6] = -log2(Rs_)/n, c[7] = -bn log2(e), c[8] = bn log2(e) (c[5..8] times kExp2Scale: exp2_*_s), c[9] = (max_R_frac Rs_)^2,
 // c[10] = amp, c[11..12] = the transform of -centre
 LSIM_HD void light_prepare(const lsim_light_desc& d, const double* row, LightC& G) {
   G.type = d.type;
@@ -1038,11 +1038,11 @@ LSIM_HD void light_prepare(const lsim_light_desc& d, const double* row, LightC& 
       G.c[10] = amp;
       G.c[11] = -(G.c[2] * cx + G.c[3] * cy);  // shift folded into the product-average transform
       G.c[12] = -(G.c[3] * cx + G.c[4] * cy);
-      // exponents pre-scaled by 256 for exp2_*_s
-      G.c[5] *= 256.0;
-      G.c[6] *= 256.0;
-      G.c[7] *= 256.0;
-      G.c[8] *= 256.0;
+      // exponents pre-scaled for exp2_*_s
+      G.c[5] *= kExp2Scale;
+      G.c[6] *= kExp2Scale;
+      G.c[7] *= kExp2Scale;
+      G.c[8] *= kExp2Scale;
       G.type = LSIM_LIGHT_SERSIC_ELLIPSE;
       break;
     }
@@ -1071,7 +1071,7 @@ LSIM_HD void sersic_core(const LightC& G, const double (&xt)[J], const double (&
   for (int j = 0; j < J; ++j) {
     const double R2c = max_nan(fma(yt[j], yt[j], xt[j] * xt[j]), 1e-8);  // R_ = max(1e-4, R)
     const double k = exp2_fin_s(fma(G.c[5], log2_pos(R2c, K), G.c[6]), K);
-    double v = exp2_fin_s(fma(G.c[7], k, G.c[8]), K);  // k >= 0, c[7] <= 0: the argument is at most c[8] <= 256 * 1021
+    double v = exp2_fin_s(fma(G.c[7], k, G.c[8]), K);  // k >= 0, c[7] <= 0: the argument is at most c[8] <= kExp2Scale * 1021
     v = (R2c <= G.c[9]) ? v : 0.0;  // R_/Rs_ <= max_R_frac
     e[j] = (v == v) ? v : 0.0;      // nan_to_num (the exponent is bounded above, so no +inf)
   }
@@ -1089,7 +1089,7 @@ LSIM_HD void light_unit(int type, const LightC& G, const double (&x)[J], const d
       const double yt = fma(G.c[3], x[j], fma(G.c[4], y[j], G.c[12]));
       const double R2c = max_nan(fma(yt, yt, xt * xt), 1e-8);  // R_ = max(1e-4, R)
       const double k = exp2_fin_s(fma(G.c[5], log2_pos(R2c, K), G.c[6]), K);
-      double v = exp2_fin_s(fma(G.c[7], k, G.c[8]), K);  // k >= 0, c[7] <= 0: the argument is at most c[8] <= 256 * 1021
+      double v = exp2_fin_s(fma(G.c[7], k, G.c[8]), K);  // k >= 0, c[7] <= 0: the argument is at most c[8] <= kExp2Scale * 1021
       v = (R2c <= G.c[9]) ? v : 0.0;  // R_/Rs_ <= max_R_frac
       e[j] = (v == v) ? v : 0.0;      // nan_to_num (the exponent is bounded above, so no +inf)
     }

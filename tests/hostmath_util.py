@@ -133,7 +133,7 @@ def exp2(x):
 
 
 def exp2_s(y):
-    """exp2 of a pre-scaled argument y = 256 x with the kernel-parameter coefficients (MathK)."""
+    """exp2 of a pre-scaled argument y = 2048 x (the exp2 table size) with the kernel-parameter coefficients (MathK)."""
     y = np.ascontiguousarray(y, dtype=np.float64)
     out = np.empty_like(y)
     lib().hm_exp2_s(_p(y), y.size, _p(out))

@@ -59,7 +59,7 @@ def test_log2_exp2_accuracy():
     got, ref = hm.exp2_neg(neg), np.exp2(neg)
     assert np.max(np.abs(got - ref) / ref) < 4e-16 and np.isnan(hm.exp2_neg(np.array([np.nan]))[0])
     # the pre-scaled form used by the hot profiles: bit-identical to the unscaled one
-    np.testing.assert_array_equal(hm.exp2_s(256.0 * e), hm.exp2(e))
+    np.testing.assert_array_equal(hm.exp2_s(2048.0 * e), hm.exp2(e))
 
 
 @pytest.mark.parametrize("name", [n for n, c in PROFILES.items() if "f_x" in c.out and "profile" in c.meta])
