@@ -672,7 +672,24 @@ size_t per_set_bytes(const lsim_plan* plan, bool need_conv_out) {
   return n * sizeof(double) + prefix_bytes(plan);
 }
 
-int64_t chunk_sets(const lsim_plan* plan) { return (int64_t)plan->n_sm * 8; }
+// Parameter sets per chunk (= per launch of each kernel of the step).  Forward path: 32 x SMs -- measured on the headline
+// (gpurun_out/r2_variants9.txt): 4 x 269.8k, 8 x 276.6k, 16 x 279.2k, 32 x 281.0k, 64 x 282.5k images/s; the launch tails
+// of the four kernels shrink with the chunk, the scratch grows (2.5 GB at 32 x for the headline) -- halved while the
+// chunk's scratch would exceed 4 GiB (large frames), never below 8 x SMs.  The gradient path keeps 8 x SMs (its
+// scratch per set is several times larger).  LSIM_CHUNK_MULT overrides the forward multiplier.
+int64_t chunk_sets(const lsim_plan* plan, bool grad = false) {
+  static const int mult = [] {
+    const char* e = getenv("LSIM_CHUNK_MULT");
+    const int m = e ? atoi(e) : 0;
+    return m > 0 ? m : 32;
+  }();
+  const int64_t base = (int64_t)plan->n_sm * 8;
+  if (grad) return base;
+  int64_t c = (int64_t)plan->n_sm * mult;
+  const size_t per = per_set_bytes(plan, true);
+  while (c > base && (size_t)c * per > ((size_t)4 << 30)) c /= 2;
+  return c < base ? base : c;
+}
 
 template <int NSLOT, bool FULL, int SS, class LT = RuntimeTypes, class GT = RuntimeTypes>
 int launch_image_k(const lsim_plan* plan, const double* params, int64_t set0, int64_t n, int ppt, int tiles,
@@ -1346,7 +1363,7 @@ extern "C" {
 
 size_t lsim_logl_grad_workspace_bytes(const lsim_plan* plan, int64_t B) {
   if (!plan || !plan->has_image || !plan->grad_ok || B <= 0) return 0;
-  int64_t c = chunk_sets(plan);
+  int64_t c = chunk_sets(plan, true);
   if (B < c) c = B;
   return grad_per_set_bytes(plan) * (size_t)c;
 }
@@ -1363,7 +1380,7 @@ int lsim_logl_grad(const lsim_plan* plan, const double* params, int64_t B, int l
   const bool conv = D.conv_mode != LSIM_CONV_NONE;
   int64_t chunk = (int64_t)(workspace_bytes / grad_per_set_bytes(plan));
   if (!workspace || chunk < 1) return LSIM_E_WORKSPACE;
-  if (chunk > chunk_sets(plan)) chunk = chunk_sets(plan);
+  if (chunk > chunk_sets(plan, true)) chunk = chunk_sets(plan, true);
   const size_t img = (size_t)D.nx * D.ny * D.n_slots;
   // layout: the forward scratch of `chunk` sets [prepared constants | U | C], then Abar, then the per-CTA partials
   double* ws = static_cast<double*>(workspace);

@@ -662,11 +662,15 @@ def test_batch_edge_cases(headline):
     l1, a1, _ = model.logL_linear_batch(params[:1])
     ref, _ = oracle_headline_logl(headline, 0)
     assert abs(float(l1[0]) - ref) <= 1e-10 * abs(ref)
-    # ragged: 2 x 1184 + 37 sets (chunk = 8 x 148 SMs) built by tiling the 296 fixture rows
-    big = params.repeat(9, 1)[: 2 * 1184 + 37].contiguous()
+    # ragged: one full chunk (32 x SMs sets, lsim_api.cu chunk_sets) + a quarter chunk + 37 sets, built by tiling the
+    # 296 fixture rows
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    n_big = 32 * n_sm + 8 * n_sm + 37
+    reps = -(-n_big // params.shape[0])
+    big = params.repeat(reps, 1)[:n_big].contiguous()
     lb, _, _ = model.logL_linear_batch(big)
     base, _, _ = model.logL_linear_batch(params)
-    assert torch.equal(lb, base.repeat(9)[: big.shape[0]])
+    assert torch.equal(lb, base.repeat(reps)[:n_big])
     # wild rows
     wild = params[:8].clone()
     wild[1, 0] = float("nan")      # theta_E

@@ -25,9 +25,8 @@ def main():
             except ValueError:
                 pass
     cycles = m["sm__cycles_elapsed.max"]
-    # grid = tiles x sets: the capture is of one bench launch; its set count comes from the write traffic's owner, the
-    # caller passes it through the grid (launch__grid_size = tiles * sets, sets = chunk of 8 x 148 SMs)
-    sets = 1184
+    # grid = tiles x sets: the capture is of one bench launch of the headline instantiation, 8 pixel tiles per set
+    sets = int(m["launch__grid_size"]) // 8
     sub = sets * sub_per_set
     per = lambda k: m["smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % k] * cycles / sub  # noqa: E731
     unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
