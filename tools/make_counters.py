@@ -3,7 +3,7 @@
 profiles/k_image_counters.json, the per-sub-pixel instruction counts and per-set DRAM bytes bench.py's `roofline`
 block uses.
 
-    python tools/make_counters.py profiles/image_r2a_ncu_summary.txt [sub-pixels per set = 291600]
+    python tools/make_counters.py profiles/image_r2a_ncu_summary.txt [sub-pixels per set = 291600] [sets in the launch]
 """
 
 import json
@@ -25,8 +25,9 @@ def main():
             except ValueError:
                 pass
     cycles = m["sm__cycles_elapsed.max"]
-    # grid = tiles x sets: the capture is of one bench launch of the headline instantiation, 8 pixel tiles per set
-    sets = int(m["launch__grid_size"]) // 8
+    # sets in the captured launch: tools/ncu_profile.sh profiles one full chunk (--batch 4736 = 32 x 148 SMs); the pixel
+    # tiling per set varies with the chunk, so the count is an argument, checked against the image bytes written
+    sets = int(sys.argv[3]) if len(sys.argv) > 3 else 4736
     sub = sets * sub_per_set
     per = lambda k: m["smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % k] * cycles / sub  # noqa: E731
     unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
@@ -38,6 +39,8 @@ def main():
                 return float(parts[1]) * unit[parts[2]]
         return None
 
+    w = dram("dram__bytes_write.sum")
+    assert w is None or 0.8 < w / (sets * 180 * 180 * 8.0) < 1.2, "set count does not match the bytes written"
     out = {
         "capture": os.path.relpath(path, ROOT),
         "kernel": "k_image_fold<1, 3, 1> (headline instantiation)", "sets_in_launch": sets, "subpixels_per_set": sub_per_set,
