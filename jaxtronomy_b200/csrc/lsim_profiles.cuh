@@ -241,27 +241,26 @@ LSIM_HD void epl_core(const LensC& L, const double* coef, const double (&a)[J], 
       b1[j] = fma(pp[j], b2[j], fma(qq[j], b1[j], ckm));
     }
   }
-  // F_0 = 1 for every parameter set (hyp2f1_util.py:152): an immediate operand, not a register
-  const double c0 = 1.0, c1 = k == 1 ? coef[1] : 0.0, cph = L.c[2], sph = L.c[3], rho = L.c[26];
-  const bool last = k == 1;
+  // F_0 = 1 for every parameter set (hyp2f1_util.py:152): an immediate operand, not a register.  epl_prepare always
+  // keeps at least two coefficients (nmax >= 10), so the loop above always ends at k = 1: term 1 is unconditional.
+  const double c0 = 1.0, c1 = coef[1], cph = L.c[2], sph = L.c[3], rho = L.c[26];
   double tr[J], ti[J];
-  uint32_t worst = 0;  // largest |high word| of the factors: >= 0x7ff00000 <=> some factor is inf / nan
+  // largest |high word| of s: >= 0x7ff00000 <=> some s is inf / nan.  s alone is enough: a non-finite coordinate,
+  // parameter or 1/E reaches s through h = R2 / E (0 x inf, inf x 0, nan), and with finite inputs the series factors are
+  // bounded (|w| < 1).
+  uint32_t worst = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int j = 0; j < J; ++j) {
     // term 1 (if any): (b1, b2) <- (F_1 + p b1 + q b2, b1); then S = F_0 + w b1 + q b2 with Re w = p/2
-    const double bn = last ? fma(pp[j], b1[j], fma(qq[j], b2[j], c1)) : b1[j];
-    const double bo = last ? b1[j] : b2[j];
+    const double bn = fma(pp[j], b1[j], fma(qq[j], b2[j], c1));
+    const double bo = b1[j];
     const double Sr = fma(bn, 0.5 * pp[j], fma(qq[j], bo, c0)), Si = bn * wi[j];
     const double cr = rho * c[j];
     tr[j] = fma(a[j], Sr, -(cr * Si));
     ti[j] = fma(a[j], Si, cr * Sr);
-    const uint32_t h0 = (uint32_t)((uint64_t)d2i(tr[j]) >> 32) & 0x7fffffffu;
-    const uint32_t h1 = (uint32_t)((uint64_t)d2i(ti[j]) >> 32) & 0x7fffffffu;
     const uint32_t h2 = (uint32_t)((uint64_t)d2i(s[j]) >> 32) & 0x7fffffffu;
-    worst = worst > h0 ? worst : h0;
-    worst = worst > h1 ? worst : h1;
     worst = worst > h2 ? worst : h2;
   }
   if (worst >= 0x7ff00000u) {  // rare
@@ -1072,8 +1071,8 @@ LSIM_HD void sersic_core(const LightC& G, const double (&xt)[J], const double (&
     const double R2c = max_nan(fma(yt[j], yt[j], xt[j] * xt[j]), 1e-8);  // R_ = max(1e-4, R)
     const double k = exp2_fin_s(fma(G.c[5], log2_pos(R2c, K), G.c[6]), K);
     double v = exp2_fin_s(fma(G.c[7], k, G.c[8]), K);  // k >= 0, c[7] <= 0: the argument is at most c[8] <= kExp2Scale * 1021
-    v = (R2c <= G.c[9]) ? v : 0.0;  // R_/Rs_ <= max_R_frac
-    e[j] = (v == v) ? v : 0.0;      // nan_to_num (the exponent is bounded above, so no +inf)
+    // R_/Rs_ <= max_R_frac, and nan_to_num (the exponent is bounded above, so no +inf): one select for both
+    e[j] = (R2c <= G.c[9] && v == v) ? v : 0.0;
   }
 }
 
