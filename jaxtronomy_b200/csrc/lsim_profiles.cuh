@@ -148,8 +148,10 @@ LSIM_HD void epl_prepare(LensC& L, double* coef, double theta_E, double gamma, d
   L.c[28] = kExp2Scale * (L.c[7] + log2((2.0 + f) / (fe * (1.0 + q))));
   int nmax = epl_nmax(f);
   double B = t / 2.0, C = 2.0 - B;
+  // epl_core takes term 1 unconditionally: at least two coefficients, F_1 = 0 when the reference sums nothing (f == 0)
   coef[0] = 1.0;
-  int n_used = 1;
+  coef[1] = 0.0;
+  int n_used = 2;
   if (nmax > 0) {
     double ppF = 1.0, pF = 1.0 - 2.0 * B / C;
     coef[1] = pF;
@@ -242,7 +244,8 @@ LSIM_HD void epl_core(const LensC& L, const double* coef, const double (&a)[J], 
     }
   }
   // F_0 = 1 for every parameter set (hyp2f1_util.py:152): an immediate operand, not a register.  epl_prepare always
-  // keeps at least two coefficients (nmax >= 10), so the loop above always ends at k = 1: term 1 is unconditional.
+  // keeps at least two coefficients (F_1 = 0 for f == 0, where the reference returns 1 without summing), so the loop
+  // above always ends at k = 1: term 1 is unconditional.
   const double c0 = 1.0, c1 = coef[1], cph = L.c[2], sph = L.c[3], rho = L.c[26];
   double tr[J], ti[J];
   // largest |high word| of s: >= 0x7ff00000 <=> some s is inf / nan.  s alone is enough: a non-finite coordinate,

@@ -1,10 +1,15 @@
 // tests/hostmath -- TEST HARNESS ONLY.  Compiles the product's host+device profile arithmetic
 // (jaxtronomy_b200/csrc/lsim_profiles.cuh) with g++ so that the exact per-point code the CUDA kernels run
 // can be checked against the oracle on a machine without a GPU.  Not linked into, or loaded by, the product.
+#include <limits>
 #include <vector>
 
 #include "../../jaxtronomy_b200/csrc/lsim_profiles.cuh"
 #include "../../jaxtronomy_b200/csrc/lsim_grad.cuh"
+
+// coefficient pools start out as NaN: a coefficient that is read without having been written (the device reads stale
+// shared memory in that case, invisible unless the stale value is huge or non-finite) poisons the result here
+static const double kPoison = std::numeric_limits<double>::quiet_NaN();
 
 using namespace lsim;
 
@@ -14,7 +19,7 @@ int hm_ray_shoot(const lsim_lens_desc* lens, int n_lens, int multi_plane, double
                  double T_z_source, const double* row, const double* x, const double* y, int64_t N, double* ox,
                  double* oy, int what, double series_tol) {
   std::vector<LensC> L(n_lens);
-  std::vector<double> pool((size_t)(n_lens + 1) * kMaxSeries);
+  std::vector<double> pool((size_t)(n_lens + 1) * kMaxSeries, kPoison);
   int off = 0;
   for (int i = 0; i < n_lens; ++i) {
     L[i].coef_off = off * kMaxSeries;
@@ -57,7 +62,7 @@ int hm_ray_shoot_epl_shear(const lsim_lens_desc* lens, double alpha_scaling, con
                            const double* y, int64_t N, double* ox, double* oy, double series_tol) {
   using LT = TypeList<LSIM_LENS_EPL, LSIM_LENS_SHEAR>;
   LensC L[2];
-  std::vector<double> pool(2 * kMaxSeries);
+  std::vector<double> pool(2 * kMaxSeries, kPoison);
   L[0].coef_off = 0;
   lens_prepare(lens[0], row, L[0], pool.data(), series_tol);
   L[1].coef_off = kMaxSeries;
@@ -109,7 +114,7 @@ void hm_exp2_neg(const double* x, int64_t n, double* out) {
 }
 int hm_epl_terms(const lsim_lens_desc* lens, const double* row, double series_tol) {
   LensC L;
-  std::vector<double> pool(kMaxSeries);
+  std::vector<double> pool(kMaxSeries, kPoison);
   lens_prepare(*lens, row, L, pool.data(), series_tol);
   return L.n_coef;
 }
@@ -119,7 +124,7 @@ int hm_epl_terms(const lsim_lens_desc* lens, const double* row, double series_to
 int hm_lens_jvp(const lsim_lens_desc* lens, int n_lens, const double* row, const double* x, const double* y, int64_t N,
                 double* ax, double* ay, double* dax, double* day) {
   std::vector<ad::GLens> L(n_lens);
-  std::vector<double> pool((size_t)(n_lens + 1) * ad::kGradPool);
+  std::vector<double> pool((size_t)(n_lens + 1) * ad::kGradPool, kPoison);
   int off = 0;
   for (int i = 0; i < n_lens; ++i) {
     L[i].coef_off = off * ad::kGradPool;
@@ -166,7 +171,7 @@ int hm_lens_hessian(const lsim_lens_desc* lens, int n_lens, const double* row, c
     if (!ad::lens_grad_supported(lens[i])) return -2;
   std::vector<ad::GLens> L(ngl > 0 ? ngl : 1);
   std::vector<int> slot(2 * (size_t)(ngl > 0 ? ngl : 1));
-  std::vector<double> pool((size_t)(ngl + 1) * ad::kGradPool);
+  std::vector<double> pool((size_t)(ngl + 1) * ad::kGradPool, kPoison);
   int off = 0;
   for (int i = 0; i < ngl; ++i) {
     L[i].coef_off = off * ad::kGradPool;
@@ -192,7 +197,7 @@ int hm_source_position_logl(const lsim_lens_desc* lens, int n_lens, const double
   if (ngl < 0) return -2;
   std::vector<ad::GLens> L(ngl > 0 ? ngl : 1);
   std::vector<int> slot(2 * (size_t)(ngl > 0 ? ngl : 1));
-  std::vector<double> pool((size_t)(ngl + 1) * ad::kGradPool);
+  std::vector<double> pool((size_t)(ngl + 1) * ad::kGradPool, kPoison);
   int off = 0;
   for (int i = 0; i < ngl; ++i) {
     L[i].coef_off = off * ad::kGradPool;
@@ -229,7 +234,7 @@ int hm_source_position_logl(const lsim_lens_desc* lens, int n_lens, const double
 int hm_lens_vjp(const lsim_lens_desc* lens, int n_lens, const double* row, const double* x, const double* y, int64_t N,
                 const double* vx, const double* vy, double* ax, double* ay, double* g) {
   std::vector<ad::GLens> L(n_lens);
-  std::vector<double> pool((size_t)(n_lens + 1) * ad::kGradPool);
+  std::vector<double> pool((size_t)(n_lens + 1) * ad::kGradPool, kPoison);
   int off = 0;
   for (int i = 0; i < n_lens; ++i) {
     L[i].coef_off = off * ad::kGradPool;
@@ -261,7 +266,7 @@ int hm_mp_ray_vjp(const lsim_lens_desc* lens, int n_lens, double T_ij_end, doubl
   if (n_lens > ad::kMaxGradPlanes) return -1;
   std::vector<ad::GLens> L(n_lens);
   std::vector<ad::MpPlane> pl(n_lens);
-  std::vector<double> pool((size_t)(n_lens + 1) * ad::kGradPool);
+  std::vector<double> pool((size_t)(n_lens + 1) * ad::kGradPool, kPoison);
   int off = 0;
   for (int i = 0; i < n_lens; ++i) {
     L[i].coef_off = off * ad::kGradPool;
@@ -315,7 +320,7 @@ int hm_eplm_vjp(const lsim_lens_desc* lens, const double* row, const double* x, 
   const int n = ad::expand_grad_lens(lens, 1, ex, 4);
   if (n != 4) return -2;
   std::vector<ad::GLens> L(n);
-  std::vector<double> pool((size_t)2 * ad::kGradPool);
+  std::vector<double> pool((size_t)2 * ad::kGradPool, kPoison);
   for (int i = 0; i < n; ++i) {
     L[i].coef_off = 0;
     if (!ad::lens_prepare_d(ex[i], row, L[i], pool.data(), pool.data() + kMaxSeries)) return -2;

@@ -125,3 +125,25 @@ def test_bulk_and_multi_plane():
     bx, by = hm.ray_shoot(names, kws, c.inp["x"], c.inp["y"], multi_plane=mp)
     assert_close(bx, c.out["beta_x"], what="multi-plane", **BAR)
     assert_close(by, c.out["beta_y"], what="multi-plane", **BAR)
+
+
+def test_round_epl_reads_no_unwritten_series_coefficient():
+    """e1 = e2 = 0 exactly: the reference returns 2F1 = 1 without summing (epl.py:308-319, nmax "0"), so the prepared
+    series is F_0 alone -- but epl_core takes term 1 unconditionally and must find F_1 = 0 there, not whatever the
+    coefficient pool held before (the host harness fills its pools with NaN; on the device the pool is stale shared
+    memory, which compute-sanitizer exposed as run-to-run differences for exactly this parameter set).  Against the
+    closed form of the round power law: alpha = theta_E^t R^(1-t) (x, y)/R, t = gamma - 1."""
+    rng = np.random.default_rng(3)
+    x, y = rng.uniform(-2, 2, 301), rng.uniform(-2, 2, 301)
+    kw = dict(theta_E=1.2, gamma=2.1, e1=0.0, e2=0.0, center_x=0.05, center_y=-0.02)
+    fx, fy = hm.ray_shoot(["EPL"], [kw], x, y, what=1)
+    assert np.all(np.isfinite(fx)) and np.all(np.isfinite(fy))
+    xs, ys = x - kw["center_x"], y - kw["center_y"]
+    R = np.hypot(xs, ys)
+    t = kw["gamma"] - 1
+    a = kw["theta_E"] ** t * R ** (1 - t)
+    np.testing.assert_allclose(fx, a * xs / R, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(fy, a * ys / R, rtol=1e-12, atol=1e-14)
+    bx, by = hm.ray_shoot_epl_shear([kw, dict(gamma1=0.0, gamma2=0.0, ra_0=0.0, dec_0=0.0)], x, y)
+    np.testing.assert_allclose(bx, x - a * xs / R, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(by, y - a * ys / R, rtol=1e-12, atol=1e-13)
