@@ -119,12 +119,12 @@ k_prepare(PlanDev P, const double* __restrict__ params, int64_t set0, int64_t n_
     int off = 0;
     if (lens_type_has_series(d))
       for (int j = 0; j < i; ++j) off += lens_type_has_series(P.lens[j]) ? 1 : 0;
-    LensC tmp;
+    LensC tmp = {};  // every field defined: the block is copied whole by the image kernels (initcheck-clean)
     tmp.coef_off = off * kMaxSeries;
     lens_prepare(d, row, tmp, pool + off * kMaxSeries, P.series_tol);
     L[i] = tmp;
   } else {
-    LightC tmp;
+    LightC tmp = {};
     light_prepare(P.light[i - P.n_lens], row, tmp);
     G[i - P.n_lens] = tmp;
   }
