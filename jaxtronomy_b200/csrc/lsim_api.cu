@@ -192,10 +192,12 @@ int upload_tables() {
 template <class K>
 int ensure_dyn_smem(K kernel, size_t bytes) {
   static std::mutex m;
-  static std::unordered_map<const void*, size_t> have;
+  static std::unordered_map<const void*, size_t> have[16];  // per device of this process (the attribute is per device)
   if (bytes <= 8 * 1024) return LSIM_OK;  // no kernel has more than 40 KB of static shared memory
+  int dev = 0;
+  LSIM_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> g(m);
-  size_t& h = have[reinterpret_cast<const void*>(kernel)];
+  size_t& h = have[dev & 15][reinterpret_cast<const void*>(kernel)];
   if (h >= bytes) return LSIM_OK;
   LSIM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   h = bytes;
@@ -1031,11 +1033,7 @@ template <int KT, int R, int NW>
 int launch_conv_tiled_u(const ConvSpec& c, const double* in, double* out, int64_t n_images, cudaStream_t st) {
   constexpr int TH = R * NW, HALO = KT - 1, PITCH = (32 + HALO) | 1;
   constexpr size_t smem = (size_t)(TH + HALO) * PITCH * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    LSIM_CUDA(cudaFuncSetAttribute(k_conv_tiled_u<KT, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  LSIM_SMEM((k_conv_tiled_u<KT, R, NW>), smem);
   ConvWeights<KT> W;  // wT[dx][dy] = kernel flipped (correlation form), zero padded from K to KT
   conv_direct_weights<KT>(c, W);
   const int tiles = ((c.nx + 31) / 32) * ((c.ny + TH - 1) / TH);
@@ -1090,11 +1088,7 @@ template <int KT, int R, int NW>
 int launch_conv_tiled_fxy(const ConvSpec& c, const double* in, double* out, int64_t n_images, cudaStream_t st) {
   constexpr int TH = R * NW, HALO = KT - 1, M = (KT + 1) / 2, PITCH = (32 + M - 1) | 1;
   constexpr size_t smem = (size_t)2 * (TH + HALO) * PITCH * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    LSIM_CUDA(cudaFuncSetAttribute(k_conv_tiled_fxy<KT, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  LSIM_SMEM((k_conv_tiled_fxy<KT, R, NW>), smem);
   ConvWeightsFXY<KT> W;
   conv_fxy_weights<KT>(c, W);
   const int tiles = ((c.nx + 63) / 64) * ((c.ny + TH - 1) / TH);
