@@ -674,22 +674,22 @@ size_t per_set_bytes(const lsim_plan* plan, bool need_conv_out) {
   return n * sizeof(double) + prefix_bytes(plan);
 }
 
-// Parameter sets per chunk (= per launch of each kernel of the step).  Forward path: 32 x SMs -- measured on the headline
+// Parameter sets per chunk (= per launch of each kernel of the step).  Forward path: 64 x SMs -- measured on the headline
 // (gpurun_out/r2_variants9.txt): 4 x 269.8k, 8 x 276.6k, 16 x 279.2k, 32 x 281.0k, 64 x 282.5k images/s; the launch tails
-// of the four kernels shrink with the chunk, the scratch grows (2.5 GB at 32 x for the headline) -- halved while the
-// chunk's scratch would exceed 4 GiB (large frames), never below 8 x SMs.  The gradient path keeps 8 x SMs (its
-// scratch per set is several times larger).  LSIM_CHUNK_MULT overrides the forward multiplier.
+// of the four kernels shrink with the chunk, the scratch grows (4.9 GB at 64 x for the headline) -- halved while the
+// chunk's scratch would exceed 8 GiB (large frames, many slots), never below 8 x SMs.  The gradient path keeps 8 x SMs
+// (its scratch per set is several times larger).  LSIM_CHUNK_MULT overrides the forward multiplier.
 int64_t chunk_sets(const lsim_plan* plan, bool grad = false) {
   static const int mult = [] {
     const char* e = getenv("LSIM_CHUNK_MULT");
     const int m = e ? atoi(e) : 0;
-    return m > 0 ? m : 32;
+    return m > 0 ? m : 64;
   }();
   const int64_t base = (int64_t)plan->n_sm * 8;
   if (grad) return base;
   int64_t c = (int64_t)plan->n_sm * mult;
   const size_t per = per_set_bytes(plan, true);
-  while (c > base && (size_t)c * per > ((size_t)4 << 30)) c /= 2;
+  while (c > base && (size_t)c * per > ((size_t)8 << 30)) c /= 2;
   return c < base ? base : c;
 }
 

@@ -662,10 +662,10 @@ def test_batch_edge_cases(headline):
     l1, a1, _ = model.logL_linear_batch(params[:1])
     ref, _ = oracle_headline_logl(headline, 0)
     assert abs(float(l1[0]) - ref) <= 1e-10 * abs(ref)
-    # ragged: one full chunk (32 x SMs sets, lsim_api.cu chunk_sets) + a quarter chunk + 37 sets, built by tiling the
-    # 296 fixture rows
+    # ragged: one full chunk (64 x SMs sets, lsim_api.cu chunk_sets) + an eighth of a chunk + 37 sets, built by tiling
+    # the 296 fixture rows
     n_sm = torch.cuda.get_device_properties(0).multi_processor_count
-    n_big = 32 * n_sm + 8 * n_sm + 37
+    n_big = 64 * n_sm + 8 * n_sm + 37
     reps = -(-n_big // params.shape[0])
     big = params.repeat(reps, 1)[:n_big].contiguous()
     lb, _, _ = model.logL_linear_batch(big)

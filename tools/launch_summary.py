@@ -20,7 +20,7 @@ for r in rows[1:]:
 step = {k: v for k, v in tot.items() if k.startswith("k_") and k != "k_fp64_peak"}
 s = sum(v[1] for v in step.values())
 tag = path.split("/")[-1].split("_")[0]
-print("# ncu launch list `%s`: `python bench.py --steps 1 --warmup 3 --batch 4736 --no-cpu --no-secondary`\n" % path)
+print("# ncu launch list `%s`: `python bench.py --steps 1 --warmup 3 --batch 9472 --no-cpu --no-secondary`\n" % path)
 print("Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv` via `tools/ncu_profile.sh %s` (cold-cache, "
       "serialised: compare SHARES).  Shares exclude the `k_fp64_peak` roofline microbenchmark and torch's own element-wise "
       "kernels (bound checks of the sampler boundary, < 0.1 %%).\n" % tag)

@@ -25,9 +25,9 @@ def main():
             except ValueError:
                 pass
     cycles = m["sm__cycles_elapsed.max"]
-    # sets in the captured launch: tools/ncu_profile.sh profiles one full chunk (--batch 4736 = 32 x 148 SMs); the pixel
+    # sets in the captured launch: tools/ncu_profile.sh profiles one full chunk (--batch 9472 = 64 x 148 SMs); the pixel
     # tiling per set varies with the chunk, so the count is an argument, checked against the image bytes written
-    sets = int(sys.argv[3]) if len(sys.argv) > 3 else 4736
+    sets = int(sys.argv[3]) if len(sys.argv) > 3 else 9472
     sub = sets * sub_per_set
     per = lambda k: m["smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % k] * cycles / sub  # noqa: E731
     unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}

@@ -4,7 +4,7 @@
 TAG=${1:-dev}
 KERNELS=${2:-"k_image k_conv_tiled_u k_likelihood"}
 mkdir -p gpurun_out /tmp/ncu
-CMD="python bench.py --steps 1 --warmup 3 --batch 4736 --no-cpu --no-secondary"
+CMD="python bench.py --steps 1 --warmup 3 --batch 9472 --no-cpu --no-secondary"
 for k in $KERNELS; do
   ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 4 -c 1 -f \
       -o /tmp/ncu/${k}_${TAG} $CMD > gpurun_out/ncu_${k}_${TAG}.log 2>&1
